@@ -1,0 +1,191 @@
+/*
+ * showtell_b200.h -- C ABI of libshowtell_b200.so: the B200 (sm_100a) kernels behind the
+ * show-tell caption-decoder classes.
+ *
+ * The reference (guptakhil/show-tell) has NO plugin / FFI interface: its decoder is a set of plain
+ * Python torch.nn.Module classes (rnn.py:10 RNN, LSTM/rnn_lstm.py:8 RNN, Attention/rnn_attn.py:33
+ * RNN_Attn, Attention/rnn_attn_LSTM.py:33 RNN_Attn) whose arithmetic is done by PyTorch library
+ * calls.  Each entry point below therefore cites the reference call site whose library call it
+ * replaces; the Python classes in showtell_b200/ keep the reference's names/signatures and bind
+ * these symbols with ctypes.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  Every pointer is a DEVICE pointer unless the name ends in
+ *     _host.  The library never allocates tensors; the caller owns inputs, outputs and workspaces.
+ *   - All matrices are dense row-major; "ld" = elements between consecutive rows.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, and
+ *     returns ST_OK or a negative st_status.  No exceptions, no aborts.  st_last_error() returns
+ *     a thread-local message for the last failure on the calling thread.
+ *   - "packed time-major" = rows of step 0 (batch_sizes[0] of them), then step 1, ... exactly the
+ *     PackedSequence.data order of torch.nn.utils.rnn.pack_padded_sequence (rnn.py:31).
+ *   - kind: ST_GRU gate order [r|z|n] (nn.GRU), ST_LSTM gate order [i|f|g|o] (nn.LSTM).
+ *   - There is no CPU fallback anywhere in this library.
+ */
+#ifndef SHOWTELL_B200_H_
+#define SHOWTELL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* st_stream_t; /* cudaStream_t */
+
+typedef enum {
+  ST_OK = 0,
+  ST_ERR_BAD_SHAPE = -1,    /* a dimension is <= 0, too large, or violates an alignment rule   */
+  ST_ERR_UNSORTED = -2,     /* batch_sizes not non-increasing (lengths not sorted descending)  */
+  ST_ERR_UNSUPPORTED = -3,  /* kind / dtype / option not supported by this build               */
+  ST_ERR_CUDA = -4,         /* a CUDA runtime / driver call failed; see st_last_error()        */
+  ST_ERR_NULL = -5,         /* a required pointer is NULL                                      */
+  ST_ERR_WORKSPACE = -6     /* workspace too small                                             */
+} st_status;
+
+enum { ST_GRU = 0, ST_LSTM = 1 };
+enum { ST_MAX_STEPS = 128 }; /* longest padded caption the sequence kernels accept */
+
+int st_version(void);
+const char* st_last_error(void);
+/* Device facts the host side sizes grids with. */
+int st_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_optin_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * fp32 GEMM (CUDA cores, FFMA): C[M,N] = alpha * op(A) * op(B) + beta * C + bias[N]
+ *   transA = 0: A is (M,K) lda;  1: A is (K,M) lda.   transB = 0: B is (K,N) ldb;  1: B is (N,K) ldb.
+ * Replaces every nn.Linear / GRU / LSTM input-side matmul of the fp32 reference:
+ * rnn.py:32-33 (W_ih hoist, vocabulary projection), rnn_attn.py:23,24,62,70 (encoder_att,
+ * decoder_att, init_h, embed) and their autograd transposes (dX = dY W, dW = dY^T X).
+ * bias may be NULL.  beta = 0 never reads C.
+ * ------------------------------------------------------------------------------------------ */
+int st_sgemm(int transA, int transB, int M, int N, int K, float alpha, const float* A, int lda,
+             const float* B, int ldb, float beta, float* C, int ldc, const float* bias,
+             st_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Input packing (rnn.py:29-31 Embedding + cat + pack_padded_sequence; rnn_attn.py:101 + :70).
+ * X (N, ldx) row n=(t,b):  with_feature=1: t==0 ? feature[b] : emb[caption[b, t-1]]   (rnn.py:30)
+ *                          with_feature=0: emb[caption[b, t]]                          (rnn_attn.py:70)
+ * caption is int64 (B, T_cap) row-major.  Only the first E columns of each X row are written.
+ * ------------------------------------------------------------------------------------------ */
+int st_pack_inputs(float* X, int ldx, const float* emb, int E, const float* feature,
+                   const int64_t* caption, int T_cap, int with_feature, int nsteps,
+                   const int* batch_sizes_host, st_stream_t stream);
+/* Backward of the above: dEmb[token] += dX row (atomic), dfeature[b] = dX row (0,b).
+ * dEmb must be zero-initialised (or hold the running gradient); dfeature may be NULL. */
+int st_pack_inputs_bwd(const float* dX, int ldx, float* dEmb, int E, float* dfeature,
+                       const int64_t* caption, int T_cap, int with_feature, int nsteps,
+                       const int* batch_sizes_host, st_stream_t stream);
+/* Packed targets for the loss: out[n=(t,b)] = caption[b,t]  (main.py:145). */
+int st_pack_targets(int64_t* out, const int64_t* caption, int T_cap, int nsteps,
+                    const int* batch_sizes_host, st_stream_t stream);
+
+/* out[c] (+)= sum_r M[r, c]  -- bias gradients.  accumulate=0 overwrites. */
+int st_colsum(float* out, const float* M, int rows, int cols, int ld, int accumulate,
+              st_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Recurrent sequence, forward (the inside of nn.GRU / nn.LSTM over a PackedSequence,
+ * rnn.py:32, rnn_lstm.py:30; one call per layer).  Persistent cooperative kernel: each CTA keeps
+ * its slice of W_hh in shared memory for all steps, fuses h.W_hh^T with the gate math and the
+ * state update, and meets the other CTAs of its batch tile at a device-wide barrier per step.
+ *   Gx   (N, g*H)  input-side pre-activations W_ih x + b_ih, packed time-major
+ *   Whh  (g*H, H), bhh (g*H)
+ *   h0, c0 (B0, H) or NULL (= zeros); B0 = batch_sizes[0]
+ *   Hs   (N, H)    out: h_t rows, packed time-major
+ *   Cs   (N, H)    out (LSTM only): c_t rows
+ *   gates(N, g*H)  out, saved for backward: GRU [r|z|n] post-activation, LSTM [i|f|g|o]
+ *   ghn  (N, H)    out (GRU only): W_hn h + b_hn, saved for backward
+ * gates/ghn may be NULL for inference.  barrier: >= 64 ints of scratch.
+ * Only steps [t_begin, t_end) are run (0, nsteps for a whole sequence; single steps are used by
+ * the decoders and by the attention models, whose step input depends on the previous state).
+ * ------------------------------------------------------------------------------------------ */
+int st_rnn_seq_fwd(int kind, int H, int nsteps, const int* batch_sizes_host, int t_begin, int t_end,
+                   const float* Gx, const float* Whh, const float* bhh, const float* h0,
+                   const float* c0, float* Hs, float* Cs, float* gates, float* ghn, int* barrier,
+                   st_stream_t stream);
+
+/* Backward through time of one layer (autograd of rnn.py:32), steps t_hi-1 down to t_lo.
+ *   dHs    (N, H)    in: gradient w.r.t. every h_t row from above (vocab projection / next layer)
+ *   dG     (N, g*H)  out: gradient w.r.t. Gx rows (= dgi)
+ *   dGh    (N, g*H)  out: gradient w.r.t. (W_hh h + b_hh) rows; equals dG for LSTM (may alias),
+ *                    differs in the n gate for GRU (da_n * r)
+ *   dstate (2, B0, H) in/out: running gradient w.r.t. the carried state, [0] = dh, [1] = dc.
+ *                    Rows are read only where a later step was processed in this or an earlier
+ *                    call with the same buffer; after t_lo == 0 it holds dh0 / dc0.  A caller that
+ *                    splits the range (attention models) may add further terms into the dh rows
+ *                    between calls.
+ *   barrier: >= 64 ints of scratch. */
+int st_rnn_seq_bwd(int kind, int H, int nsteps, const int* batch_sizes_host, int t_hi, int t_lo,
+                   const float* Whh, const float* h0, const float* c0, const float* Hs,
+                   const float* Cs, const float* gates, const float* ghn, const float* dHs,
+                   float* dG, float* dGh, float* dstate, int* barrier, st_stream_t stream);
+
+/* Hprev (N,H): row (t,b) = h_{t-1}[b] (h0 or zeros at t=0) -- the B operand of dW_hh = dGh^T Hprev. */
+int st_shift_states(float* Hprev, const float* Hs, const float* h0, int H, int nsteps,
+                    const int* batch_sizes_host, st_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Cross-entropy over materialised logits (nn.CrossEntropyLoss(), main.py:94,149).
+ *   logits (N, V) ld;  target (N) int64
+ *   loss_sum: out, 1 float, sum_n (lse_n - logit_n[target_n])  (caller divides by the global N)
+ *   lse (N) out, may be NULL
+ *   dlogits: if not NULL, (N, V) ld written with (softmax - onehot) * grad_scale; may alias logits.
+ * ------------------------------------------------------------------------------------------ */
+int st_ce_fwd_bwd(const float* logits, int ld, const int64_t* target, int N, int V,
+                  float* loss_sum, float* lse, float* dlogits, float grad_scale,
+                  st_stream_t stream);
+
+/* Row-wise arg-max (lowest index wins on ties, like Tensor.max(1)[1] on CPU; rnn.py:51) and
+ * top-K (descending; ties by lower index first; rnn.py:63,90-91).  K <= 32. */
+int st_argmax_rows(const float* X, int ld, int rows, int cols, int64_t* idx, int idx_stride,
+                   st_stream_t stream);   /* idx[row * idx_stride] */
+int st_topk_rows(const float* X, int ld, int rows, int cols, int K, float* val, int32_t* idx,
+                 int out_stride, st_stream_t stream);   /* val/idx[row * out_stride + k] */
+
+/* ------------------------------------------------------------------------------------------
+ * Decoding.  All loops run inside the library on `stream` with no host synchronisation.
+ * Weights: per layer l: Wih_l (g*H, in_l), Whh_l (g*H, H), bih_l, bhh_l (g*H); in_0 = E, in_l = H.
+ * Passed as arrays of L device pointers living in HOST memory (*_host).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int kind, L, E, H, V;
+  const float* emb;           /* (V, E) */
+  const float* const* Wih_host;
+  const float* const* Whh_host;
+  const float* const* bih_host;
+  const float* const* bhh_host;
+  const float* Wv;            /* (V, H) */
+  const float* bv;            /* (V)    */
+} st_rnn_weights;
+
+int64_t st_decode_workspace_bytes(const st_rnn_weights* w, int n_img, int K, int max_len);
+
+/* RNN.sentence_index(cnn_feature) greedy (rnn.py:44-58, rnn_lstm.py:35-57):
+ * feature (n_img, E) -> tokens (n_img, max_len) int64. */
+int st_decode_greedy(const st_rnn_weights* w, const float* feature, int n_img, int max_len,
+                     int64_t* tokens, void* workspace, int64_t workspace_bytes, st_stream_t stream);
+
+/* RNN.sentence_index(cnn_feature, beam_size=K) "chain" beam (rnn.py:60-108), batched over images
+ * (the reference handles one image per call, main.py:81-82; images are independent).
+ * tokens (n_img, max_len) int64 = old_beam_sentence[0].  Optional trace for parity checks:
+ * trace_scores (max_len, n_img, K) scores of the K surviving sentences of each round (round 0: the
+ * top-K logits), trace_words (max_len, n_img, K) surviving words (rnn.py:103 order).  May be NULL. */
+int st_decode_beam_chain(const st_rnn_weights* w, const float* feature, int n_img, int K,
+                         int max_len, int64_t* tokens, float* trace_scores, int32_t* trace_words,
+                         void* workspace, int64_t workspace_bytes, st_stream_t stream);
+
+/* beam_search.beam_search() semantics (beam_search.py:45-97) for the single-layer GRU decoder,
+ * batched over images: per-hypothesis state, cumulative -log softmax cost, <end> termination,
+ * hypotheses alive after max_length are dropped.
+ * out_tokens (n_img, num_hyp, max_length+1) int32 (position 0 = start_id, padded with -1),
+ * out_len (n_img, num_hyp) int32 (0 = no such hypothesis), out_cost (n_img, num_hyp) float. */
+int st_decode_beam_tree(const st_rnn_weights* w, const float* feature, int n_img, int beam_width,
+                        int num_hyp, int max_length, int start_id, int end_id, int32_t* out_tokens,
+                        int32_t* out_len, float* out_cost, void* workspace,
+                        int64_t workspace_bytes, st_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHOWTELL_B200_H_ */

@@ -1,0 +1,100 @@
+// Shared host/device helpers for libshowtell_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "showtell_b200.h"
+
+namespace st {
+
+void set_error(const char* fmt, ...);
+
+// batch_sizes + packed-row offsets of a PackedSequence, passed to kernels by value
+// (pack_padded_sequence semantics, rnn.py:31).
+struct StepTable {
+  int nsteps;
+  int bs[ST_MAX_STEPS + 1];   // bs[nsteps] = 0 sentinel
+  int off[ST_MAX_STEPS + 1];  // off[t] = sum_{s<t} bs[s]; off[nsteps] = N
+};
+
+// Validates (1 <= nsteps <= ST_MAX_STEPS, sizes positive and non-increasing) and fills `tab`.
+int make_step_table(StepTable& tab, int nsteps, const int* batch_sizes_host);
+
+inline cudaStream_t as_stream(st_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace st
+
+#define ST_CUDA_TRY(expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      st::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,      \
+                    __LINE__);                                                             \
+      return ST_ERR_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+#define ST_LAUNCH_TRY(what)                                                                \
+  do {                                                                                     \
+    cudaError_t _e = cudaGetLastError();                                                   \
+    if (_e != cudaSuccess) {                                                               \
+      st::set_error("launch of %s failed: %s (%s:%d)", what, cudaGetErrorString(_e),       \
+                    __FILE__, __LINE__);                                                   \
+      return ST_ERR_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+#define ST_REQUIRE(cond, code, ...)                                                        \
+  do {                                                                                     \
+    if (!(cond)) {                                                                         \
+      st::set_error(__VA_ARGS__);                                                          \
+      return (code);                                                                       \
+    }                                                                                      \
+  } while (0)
+
+#define ST_TRY(expr)                                                                       \
+  do {                                                                                     \
+    int _s = (expr);                                                                       \
+    if (_s != ST_OK) return _s;                                                            \
+  } while (0)
+
+#ifdef __CUDACC__
+namespace st {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Device-wide barrier among the CTAs that share `counter` (monotonic: the k-th barrier waits for
+// k * participants arrivals).  Requires all participants co-resident (cooperative launch).
+__device__ __forceinline__ void grid_barrier(int* counter, int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1);
+    while (ld_acquire_gpu(counter) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace st
+#endif

@@ -1,0 +1,581 @@
+// Decoding loops, run entirely on the stream (no host synchronisation inside a call):
+//   st_decode_greedy      RNN.sentence_index(beam_size=0)      rnn.py:44-58, rnn_lstm.py:35-57
+//   st_decode_beam_chain  RNN.sentence_index(beam_size=K)      rnn.py:60-108   ("chain" beam)
+//   st_decode_beam_tree   beam_search.beam_search()            beam_search.py:45-97 ("tree" beam)
+// Images are independent, so every step is batched over the images of the call: the recurrent
+// step is one launch of the rnn_seq kernel with a single time step, the vocabulary projection one
+// GEMM over all rows, followed by a row-wise arg-max / top-K and a per-image bookkeeping kernel
+// that reproduces the reference's ranking rules (documented at each kernel).
+#include <cfloat>
+
+#include "common.cuh"
+
+extern "C" int st_rnn_seq_fwd(int kind, int H, int nsteps, const int* batch_sizes_host, int t_begin,
+                              int t_end, const float* Gx, const float* Whh, const float* bhh,
+                              const float* h0, const float* c0, float* Hs, float* Cs, float* gates,
+                              float* ghn, int* barrier, st_stream_t stream);
+extern "C" int st_argmax_rows(const float* X, int ld, int rows, int cols, int64_t* idx, int idx_stride,
+                              st_stream_t stream);
+extern "C" int st_topk_rows(const float* X, int ld, int rows, int cols, int K, float* val,
+                            int32_t* idx, int out_stride, st_stream_t stream);
+
+namespace st {
+namespace {
+
+constexpr int MAXL = 16;
+
+struct Bump {
+  char* base;
+  int64_t cap, used;
+  template <typename T>
+  T* take(int64_t n) {
+    used = (used + 255) & ~int64_t(255);
+    T* p = reinterpret_cast<T*>(base + used);
+    used += n * (int64_t)sizeof(T);
+    return p;
+  }
+};
+
+int check_weights(const st_rnn_weights* w) {
+  ST_REQUIRE(w != nullptr, ST_ERR_NULL, "decode: weights struct is NULL");
+  ST_REQUIRE(w->kind == ST_GRU || w->kind == ST_LSTM, ST_ERR_UNSUPPORTED, "decode: kind=%d", w->kind);
+  ST_REQUIRE(w->L >= 1 && w->L <= MAXL, ST_ERR_BAD_SHAPE, "decode: L=%d outside [1,%d]", w->L, MAXL);
+  ST_REQUIRE(w->E >= 1 && w->H >= 4 && w->H % 4 == 0 && w->V >= 1, ST_ERR_BAD_SHAPE,
+             "decode: E=%d H=%d V=%d", w->E, w->H, w->V);
+  ST_REQUIRE(w->emb && w->Wih_host && w->Whh_host && w->bih_host && w->bhh_host && w->Wv && w->bv,
+             ST_ERR_NULL, "decode: NULL weight pointer");
+  for (int l = 0; l < w->L; ++l)
+    ST_REQUIRE(w->Wih_host[l] && w->Whh_host[l] && w->bih_host[l] && w->bhh_host[l], ST_ERR_NULL,
+               "decode: NULL weight pointer in layer %d", l);
+  return ST_OK;
+}
+
+// Per-call decoder state: double-buffered h/c per layer for `rows` rows, plus GEMM scratch.
+struct Rig {
+  const st_rnn_weights* w;
+  int rows, G;
+  float *X, *Gx0, *GxL, *logits;
+  float* h[2][MAXL];
+  float* c[2][MAXL];
+  int* barrier;
+  int cur;
+  cudaStream_t s;
+
+  void carve(Bump& b, const st_rnn_weights* w_, int rows_) {
+    w = w_;
+    rows = rows_;
+    G = (w->kind == ST_LSTM) ? 4 : 3;
+    X = b.take<float>((int64_t)rows * w->E);
+    Gx0 = b.take<float>((int64_t)rows * G * w->H);
+    GxL = b.take<float>((int64_t)rows * G * w->H);
+    logits = b.take<float>((int64_t)rows * w->V);
+    for (int i = 0; i < 2; ++i)
+      for (int l = 0; l < w->L; ++l) {
+        h[i][l] = b.take<float>((int64_t)rows * w->H);
+        c[i][l] = (w->kind == ST_LSTM) ? b.take<float>((int64_t)rows * w->H) : nullptr;
+      }
+    barrier = b.take<int>(64);
+    cur = 0;
+  }
+  // Gx0 = Xin (rows, E) . Wih_0^T + bih_0
+  int input_proj(const float* Xin) {
+    return st_sgemm(0, 1, rows, G * w->H, w->E, 1.f, Xin, w->E, w->Wih_host[0], w->E, 0.f, Gx0,
+                    G * w->H, w->bih_host[0], s);
+  }
+  // One time step through all layers; reads state `cur` (zeros when first), writes and flips.
+  int step(bool first) {
+    const int H = w->H, nxt = cur ^ 1;
+    for (int l = 0; l < w->L; ++l) {
+      const float* gx = Gx0;
+      if (l > 0) {
+        ST_TRY(st_sgemm(0, 1, rows, G * H, H, 1.f, h[nxt][l - 1], H, w->Wih_host[l], H, 0.f, GxL,
+                        G * H, w->bih_host[l], s));
+        gx = GxL;
+      }
+      ST_TRY(st_rnn_seq_fwd(w->kind, H, 1, &rows, 0, 1, gx, w->Whh_host[l], w->bhh_host[l],
+                            first ? nullptr : h[cur][l], first ? nullptr : c[cur][l], h[nxt][l],
+                            c[nxt][l], nullptr, nullptr, barrier, s));
+    }
+    cur = nxt;
+    return ST_OK;
+  }
+  float* top() { return h[cur][w->L - 1]; }
+  int vocab_logits() {
+    return st_sgemm(0, 1, rows, w->V, w->H, 1.f, top(), w->H, w->Wv, w->H, 0.f, logits, w->V, w->bv, s);
+  }
+};
+
+int64_t rig_bytes(const st_rnn_weights* w, int64_t rows) {
+  const int G = (w->kind == ST_LSTM) ? 4 : 3;
+  int64_t f = rows * w->E + 2 * rows * G * w->H + rows * w->V + 4 * (int64_t)w->L * rows * w->H;
+  return f * 4 + 256 * (8 + 4 * w->L) + 64 * 4;
+}
+
+template <typename I>
+__global__ void gather_emb_kernel(float* __restrict__ X, const float* __restrict__ emb, int E,
+                                  const I* __restrict__ tok, int stride) {
+  const int64_t id = (int64_t)tok[(size_t)blockIdx.x * stride];
+  const float* src = emb + id * E;
+  float* dst = X + (size_t)blockIdx.x * E;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) dst[e] = src[e];
+}
+
+// ----------------------------------------------------------------------------- chain beam
+__global__ void chain_init_kernel(int n, int K, int max_len, const int32_t* __restrict__ words,
+                                  const float* __restrict__ vals, int32_t* __restrict__ sent,
+                                  float* trace_scores, int32_t* trace_words) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * K) return;
+  const int img = i / K, k = i - img * K;
+  sent[((size_t)img * K + k) * max_len] = words[i];  // rnn.py:66-74
+  if (trace_scores) trace_scores[(size_t)img * K + k] = vals[i];
+  if (trace_words) trace_words[(size_t)img * K + k] = words[i];
+}
+
+// rnn.py:102-103: two independent descending sorts over the K*K candidates of one image,
+//   (score, sentence-so-far + word)  -> surviving sentences      (ties: lexicographic, larger first)
+//   (score, word)                    -> surviving words          (ties: larger word id first)
+// both stable w.r.t. generation order (k outer, j inner).  One thread per image; K passes of a
+// linear scan each (K*K <= 1024 candidates).
+__global__ void chain_select_kernel(int n, int K, int max_len, int pos, const float* __restrict__ cand_val,
+                                    const int32_t* __restrict__ cand_idx,
+                                    const int32_t* __restrict__ sent_old, int32_t* __restrict__ sent_new,
+                                    int32_t* __restrict__ words, float* trace_scores,
+                                    int32_t* trace_words) {
+  const int img = blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= n) return;
+  const int KK = K * K;
+  const float* cv = cand_val + (size_t)img * KK;
+  const int32_t* ci = cand_idx + (size_t)img * KK;
+  const int32_t* so = sent_old + (size_t)img * K * max_len;
+  int32_t* sn = sent_new + (size_t)img * K * max_len;
+  uint32_t taken[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) taken[i] = 0u;
+
+  for (int s = 0; s < K; ++s) {  // sort by (score, sentence)
+    int best = -1;
+    for (int c = 0; c < KK; ++c) {
+      if (taken[c >> 5] & (1u << (c & 31))) continue;
+      if (best < 0) { best = c; continue; }
+      bool better;
+      if (cv[c] != cv[best]) {
+        better = cv[c] > cv[best];
+      } else {
+        const int32_t* sa = so + (size_t)(c / K) * max_len;
+        const int32_t* sb = so + (size_t)(best / K) * max_len;
+        int q = 0;
+        while (q < pos && sa[q] == sb[q]) ++q;
+        if (q < pos) better = sa[q] > sb[q];
+        else better = ci[c] > ci[best];  // equal -> keep the earlier candidate (stable)
+      }
+      if (better) best = c;
+    }
+    taken[best >> 5] |= 1u << (best & 31);
+    const int32_t* sp = so + (size_t)(best / K) * max_len;
+    for (int q = 0; q < pos; ++q) sn[(size_t)s * max_len + q] = sp[q];
+    sn[(size_t)s * max_len + pos] = ci[best];
+    if (trace_scores) trace_scores[((size_t)pos * n + img) * K + s] = cv[best];
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) taken[i] = 0u;
+  for (int s = 0; s < K; ++s) {  // sort by (score, word)
+    int best = -1;
+    for (int c = 0; c < KK; ++c) {
+      if (taken[c >> 5] & (1u << (c & 31))) continue;
+      if (best < 0) { best = c; continue; }
+      bool better = (cv[c] != cv[best]) ? (cv[c] > cv[best]) : (ci[c] > ci[best]);
+      if (better) best = c;
+    }
+    taken[best >> 5] |= 1u << (best & 31);
+    words[(size_t)img * K + s] = ci[best];
+    if (trace_words) trace_words[((size_t)pos * n + img) * K + s] = ci[best];
+  }
+}
+
+__global__ void chain_finish_kernel(int n, int K, int max_len, const int32_t* __restrict__ sent,
+                                    int64_t* __restrict__ tokens) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * max_len) return;
+  const int img = i / max_len, q = i - img * max_len;
+  tokens[i] = sent[(size_t)img * K * max_len + q];  // old_beam_sentence[0], rnn.py:106
+}
+
+// ----------------------------------------------------------------------------- tree beam
+struct TreeBufs {
+  int n, K, num_hyp, SL;  // SL = max_length + 1 tokens per sequence
+  int32_t *node_val, *node_slot, *live_cnt;  // (n,K), (n,K), (n)
+  float* node_cost;                          // (n,K)
+  int32_t *seq[2];                           // (n,K,SL)
+  int32_t *fr_cnt, *fr_pos;                  // (n), (n,K): live-list positions still in the fringe
+  int32_t *parent_slot;                      // (n,K) state slot each new node inherits
+  int32_t *hyp_tok, *hyp_len, *hyp_cnt;      // (n,num_hyp,SL), (n,num_hyp), (n)
+  float* hyp_cost;                           // (n,num_hyp)
+  float *row_max, *row_sum;                  // (n*K)
+  float* tk_val;                             // (n*K, K)
+  int32_t* tk_idx;                           // (n*K, K)
+};
+
+__global__ void tree_init_kernel(TreeBufs b, int start_id) {
+  const int img = blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= b.n) return;
+  for (int k = 0; k < b.K; ++k) {
+    b.node_val[img * b.K + k] = (k == 0) ? start_id : 0;
+    b.node_slot[img * b.K + k] = k;
+    b.node_cost[img * b.K + k] = 0.f;
+  }
+  b.live_cnt[img] = 1;  // the root, beam_search.py:66
+  b.seq[0][(size_t)img * b.K * b.SL] = start_id;
+  b.hyp_cnt[img] = 0;
+  for (int j = 0; j < b.num_hyp; ++j) {
+    b.hyp_len[img * b.num_hyp + j] = 0;
+    b.hyp_cost[img * b.num_hyp + j] = 0.f;
+    for (int q = 0; q < b.SL; ++q) b.hyp_tok[((size_t)img * b.num_hyp + j) * b.SL + q] = -1;
+  }
+}
+
+// beam_search.py:70-78: finished nodes (value == end_id) leave the live list for `hypotheses`
+// (kept here as the num_hyp cheapest, inserted stably so that the final stable sort at :96 is
+// reproduced); the rest form the fringe.  len = tokens in each live sequence.
+__global__ void tree_retire_kernel(TreeBufs b, int cur_seq, int len, int end_id) {
+  const int img = blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= b.n) return;
+  const int K = b.K, NH = b.num_hyp, SL = b.SL;
+  int cnt = 0;
+  for (int i = 0; i < b.live_cnt[img]; ++i) {
+    if (b.node_val[img * K + i] != end_id) {
+      b.fr_pos[img * K + cnt++] = i;
+      continue;
+    }
+    const float cost = b.node_cost[img * K + i];
+    int hc = b.hyp_cnt[img];
+    int at = hc;  // stable: after every kept hypothesis with cost <= this one
+    while (at > 0 && b.hyp_cost[img * NH + at - 1] > cost) --at;
+    if (at >= NH) continue;
+    const int last = min(hc, NH - 1);
+    for (int j = last; j > at; --j) {
+      b.hyp_cost[img * NH + j] = b.hyp_cost[img * NH + j - 1];
+      b.hyp_len[img * NH + j] = b.hyp_len[img * NH + j - 1];
+      for (int q = 0; q < SL; ++q)
+        b.hyp_tok[((size_t)img * NH + j) * SL + q] = b.hyp_tok[((size_t)img * NH + j - 1) * SL + q];
+    }
+    b.hyp_cost[img * NH + at] = cost;
+    b.hyp_len[img * NH + at] = len;
+    const int32_t* src = b.seq[cur_seq] + ((size_t)img * K + i) * SL;
+    for (int q = 0; q < SL; ++q) b.hyp_tok[((size_t)img * NH + at) * SL + q] = (q < len) ? src[q] : -1;
+    b.hyp_cnt[img] = min(hc + 1, NH);
+  }
+  b.fr_cnt[img] = cnt;
+}
+
+__global__ void tree_tokens_kernel(TreeBufs b, int32_t* __restrict__ tok_rows) {
+  // token fed to each state slot this round (slots outside the fringe get a harmless 0)
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b.n * b.K) return;
+  tok_rows[i] = 0;
+  const int img = i / b.K, slot = i - img * b.K;
+  for (int f = 0; f < b.fr_cnt[img]; ++f) {
+    const int pos = b.fr_pos[img * b.K + f];
+    if (b.node_slot[img * b.K + pos] == slot) tok_rows[i] = b.node_val[img * b.K + pos];
+  }
+}
+
+__global__ void row_softmax_stats_kernel(const float* __restrict__ X, int ld, int cols,
+                                         float* __restrict__ rmax, float* __restrict__ rsum) {
+  __shared__ float red[8];
+  const float* row = X + (size_t)blockIdx.x * ld;
+  float m = -FLT_MAX;
+  for (int c = threadIdx.x; c < cols; c += 256) m = fmaxf(m, row[c]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float s = 0.f;
+  for (int c = threadIdx.x; c < cols; c += 256) s += expf(row[c] - m);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    rmax[blockIdx.x] = m;
+    rsum[blockIdx.x] = t;
+  }
+}
+
+// beam_search.py:84-94: per fringe node the beam_width most probable tokens in ASCENDING order of
+// probability (np.argsort(...)[:, -K:]), cost = -log p with p = softmax (float32, as numpy >= 2
+// keeps python-float + float32 in float32), cum_cost additive, then the K cheapest by a stable
+// sort in generation order.
+__global__ void tree_expand_kernel(TreeBufs b, int cur_seq, int len) {
+  const int img = blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= b.n) return;
+  const int K = b.K, SL = b.SL;
+  const int fc = b.fr_cnt[img];
+  if (fc == 0) {
+    b.live_cnt[img] = 0;
+    return;
+  }
+  const int ncand = fc * K;
+  float new_cost[32];
+  int32_t new_val[32], new_par[32];
+  uint32_t taken[32];
+  for (int i = 0; i < 32; ++i) taken[i] = 0u;
+  const int keep = min(K, ncand);
+  for (int s = 0; s < keep; ++s) {
+    int best = -1;
+    float best_cost = 0.f;
+    for (int c = 0; c < ncand; ++c) {
+      if (taken[c >> 5] & (1u << (c & 31))) continue;
+      const int f = c / K, jj = c - f * K;
+      const int pos = b.fr_pos[img * K + f];
+      const int row = img * K + b.node_slot[img * K + pos];
+      const float logit = b.tk_val[(size_t)row * K + (K - 1 - jj)];
+      const float p = expf(logit - b.row_max[row]) / b.row_sum[row];
+      const float cost = b.node_cost[img * K + pos] + (-logf(p));
+      if (best < 0 || cost < best_cost) {
+        best = c;
+        best_cost = cost;
+      }
+    }
+    taken[best >> 5] |= 1u << (best & 31);
+    const int f = best / K, jj = best - f * K;
+    const int pos = b.fr_pos[img * K + f];
+    const int slot = b.node_slot[img * K + pos];
+    new_cost[s] = best_cost;
+    new_val[s] = b.tk_idx[(size_t)(img * K + slot) * K + (K - 1 - jj)];
+    new_par[s] = pos;
+  }
+  int32_t par_slot[32];
+  for (int s = 0; s < keep; ++s) par_slot[s] = b.node_slot[img * K + new_par[s]];
+  const int32_t* so = b.seq[cur_seq] + (size_t)img * K * SL;
+  int32_t* sn = b.seq[cur_seq ^ 1] + (size_t)img * K * SL;
+  for (int s = 0; s < keep; ++s) {
+    for (int q = 0; q < len; ++q) sn[(size_t)s * SL + q] = so[(size_t)new_par[s] * SL + q];
+    sn[(size_t)s * SL + len] = new_val[s];
+  }
+  for (int s = 0; s < keep; ++s) {
+    b.node_val[img * K + s] = new_val[s];
+    b.node_cost[img * K + s] = new_cost[s];
+    b.node_slot[img * K + s] = s;
+    b.parent_slot[img * K + s] = par_slot[s];
+  }
+  for (int s = keep; s < K; ++s) b.parent_slot[img * K + s] = s;
+  b.live_cnt[img] = keep;
+}
+
+__global__ void gather_state_kernel(float* __restrict__ dst, const float* __restrict__ src, int H, int K,
+                                    const int32_t* __restrict__ parent_slot) {
+  const int row = blockIdx.x, img = row / K;
+  const float* s = src + (size_t)(img * K + parent_slot[row]) * H;
+  float* d = dst + (size_t)row * H;
+  for (int e = threadIdx.x; e < H; e += blockDim.x) d[e] = s[e];
+}
+
+__global__ void spread_root_kernel(float* __restrict__ dst, const float* __restrict__ src, int H, int K) {
+  // dst (n*K, H): slot 0 of each image <- src (n, H); other slots zero
+  const int row = blockIdx.x, img = row / K, slot = row - img * K;
+  float* d = dst + (size_t)row * H;
+  for (int e = threadIdx.x; e < H; e += blockDim.x) d[e] = slot == 0 ? src[(size_t)img * H + e] : 0.f;
+}
+
+__global__ void tree_finish_kernel(TreeBufs b, int32_t* __restrict__ out_tok, int32_t* __restrict__ out_len,
+                                   float* __restrict__ out_cost) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b.n * b.num_hyp) return;
+  const int img = i / b.num_hyp, j = i - img * b.num_hyp;
+  const bool ok = j < b.hyp_cnt[img];
+  out_len[i] = ok ? b.hyp_len[i] : 0;
+  out_cost[i] = ok ? b.hyp_cost[i] : 0.f;
+  for (int q = 0; q < b.SL; ++q) out_tok[(size_t)i * b.SL + q] = ok ? b.hyp_tok[(size_t)i * b.SL + q] : -1;
+}
+
+}  // namespace
+}  // namespace st
+
+extern "C" {
+
+int64_t st_decode_workspace_bytes(const st_rnn_weights* w, int n_img, int K, int max_len) {
+  using namespace st;
+  if (check_weights(w) != ST_OK || n_img < 1 || max_len < 1) return -1;
+  const int64_t k = K < 1 ? 1 : K;
+  const int64_t rows = (int64_t)n_img * k;  // tree beam keeps K states per image
+  const int64_t SL = max_len + 1;
+  int64_t extra = rows * SL * 8          // sentences / sequences, double buffered
+                  + rows * k * 8         // candidate / top-K values and ids
+                  + rows * 40            // per-node scalars
+                  + (int64_t)n_img * 32 * SL * 4 + (int64_t)n_img * 32 * 8 + (int64_t)n_img * 16  // hypotheses
+                  + (int64_t)n_img * w->H * 16   // initial-state scratch of the tree beam
+                  + 64 * 256;
+  return rig_bytes(w, rows) + extra;
+}
+
+int st_decode_greedy(const st_rnn_weights* w, const float* feature, int n_img, int max_len,
+                     int64_t* tokens, void* workspace, int64_t workspace_bytes, st_stream_t stream) {
+  using namespace st;
+  ST_TRY(check_weights(w));
+  ST_REQUIRE(feature && tokens && workspace, ST_ERR_NULL, "st_decode_greedy: NULL pointer");
+  ST_REQUIRE(n_img >= 1 && max_len >= 1, ST_ERR_BAD_SHAPE, "st_decode_greedy: n_img=%d max_len=%d", n_img, max_len);
+  Bump b{(char*)workspace, workspace_bytes, 0};
+  Rig rig;
+  rig.s = as_stream(stream);
+  rig.carve(b, w, n_img);
+  ST_REQUIRE(b.used <= b.cap, ST_ERR_WORKSPACE, "st_decode_greedy: workspace %lld < %lld",
+             (long long)b.cap, (long long)b.used);
+  ST_TRY(rig.input_proj(feature));                                           // rnn.py:41,49
+  for (int step = 0; step < max_len; ++step) {
+    ST_TRY(rig.step(step == 0));                                             // rnn.py:49
+    ST_TRY(rig.vocab_logits());                                              // rnn.py:50
+    ST_TRY(st_argmax_rows(rig.logits, w->V, n_img, w->V, tokens + step, max_len, stream));  // :51
+    if (step + 1 < max_len) {
+      gather_emb_kernel<int64_t><<<n_img, 128, 0, rig.s>>>(rig.X, w->emb, w->E, tokens + step, max_len);
+      ST_LAUNCH_TRY("gather_emb_kernel");                                    // rnn.py:53
+      ST_TRY(rig.input_proj(rig.X));
+    }
+  }
+  return ST_OK;
+}
+
+int st_decode_beam_chain(const st_rnn_weights* w, const float* feature, int n_img, int K, int max_len,
+                         int64_t* tokens, float* trace_scores, int32_t* trace_words, void* workspace,
+                         int64_t workspace_bytes, st_stream_t stream) {
+  using namespace st;
+  ST_TRY(check_weights(w));
+  ST_REQUIRE(w->kind == ST_GRU, ST_ERR_UNSUPPORTED,
+             "st_decode_beam_chain: the reference beam search exists for the GRU decoder only (rnn.py:60)");
+  ST_REQUIRE(feature && tokens && workspace, ST_ERR_NULL, "st_decode_beam_chain: NULL pointer");
+  ST_REQUIRE(n_img >= 1 && max_len >= 1 && K >= 1 && K <= 32 && K <= w->V, ST_ERR_BAD_SHAPE,
+             "st_decode_beam_chain: n_img=%d K=%d max_len=%d", n_img, K, max_len);
+  Bump b{(char*)workspace, workspace_bytes, 0};
+  Rig rig;
+  rig.s = as_stream(stream);
+  rig.carve(b, w, n_img);
+  int32_t* words = b.take<int32_t>((int64_t)n_img * K);
+  float* vals0 = b.take<float>((int64_t)n_img * K);
+  int32_t* sent[2] = {b.take<int32_t>((int64_t)n_img * K * max_len),
+                      b.take<int32_t>((int64_t)n_img * K * max_len)};
+  float* cand_val = b.take<float>((int64_t)n_img * K * K);
+  int32_t* cand_idx = b.take<int32_t>((int64_t)n_img * K * K);
+  ST_REQUIRE(b.used <= b.cap, ST_ERR_WORKSPACE, "st_decode_beam_chain: workspace %lld < %lld",
+             (long long)b.cap, (long long)b.used);
+  cudaStream_t s = rig.s;
+  const int tpb = 128;
+
+  ST_TRY(rig.input_proj(feature));
+  ST_TRY(rig.step(true));                                                    // rnn.py:61
+  ST_TRY(rig.vocab_logits());                                                // rnn.py:62
+  ST_TRY(st_topk_rows(rig.logits, w->V, n_img, w->V, K, vals0, words, K, stream));  // rnn.py:63
+  chain_init_kernel<<<(n_img * K + tpb - 1) / tpb, tpb, 0, s>>>(n_img, K, max_len, words, vals0, sent[0],
+                                                               trace_scores, trace_words);
+  ST_LAUNCH_TRY("chain_init_kernel");
+  int cur = 0;
+  for (int pos = 1; pos < max_len; ++pos) {                                  // rnn.py:77-79
+    for (int k = 0; k < K; ++k) {                                            // rnn.py:83
+      gather_emb_kernel<int32_t><<<n_img, 128, 0, s>>>(rig.X, w->emb, w->E, words + k, K);
+      ST_LAUNCH_TRY("gather_emb_kernel");                                    // rnn.py:85
+      ST_TRY(rig.input_proj(rig.X));
+      ST_TRY(rig.step(false));            // the ONE chained state, rnn.py:87
+      ST_TRY(rig.vocab_logits());                                            // rnn.py:88
+      ST_TRY(st_topk_rows(rig.logits, w->V, n_img, w->V, K, cand_val + k * K, cand_idx + k * K, K * K,
+                          stream));                                          // rnn.py:90-91
+    }
+    chain_select_kernel<<<(n_img + 63) / 64, 64, 0, s>>>(n_img, K, max_len, pos, cand_val, cand_idx,
+                                                         sent[cur], sent[cur ^ 1], words, trace_scores,
+                                                         trace_words);
+    ST_LAUNCH_TRY("chain_select_kernel");
+    cur ^= 1;
+  }
+  chain_finish_kernel<<<(n_img * max_len + tpb - 1) / tpb, tpb, 0, s>>>(n_img, K, max_len, sent[cur], tokens);
+  ST_LAUNCH_TRY("chain_finish_kernel");
+  return ST_OK;
+}
+
+int st_decode_beam_tree(const st_rnn_weights* w, const float* feature, int n_img, int beam_width,
+                        int num_hyp, int max_length, int start_id, int end_id, int32_t* out_tokens,
+                        int32_t* out_len, float* out_cost, void* workspace, int64_t workspace_bytes,
+                        st_stream_t stream) {
+  using namespace st;
+  ST_TRY(check_weights(w));
+  ST_REQUIRE(w->kind == ST_GRU && w->L == 1, ST_ERR_UNSUPPORTED,
+             "st_decode_beam_tree: single-layer GRU only (beam_search.py:23 keeps one flattened state)");
+  ST_REQUIRE(feature && out_tokens && out_len && out_cost && workspace, ST_ERR_NULL,
+             "st_decode_beam_tree: NULL pointer");
+  const int K = beam_width;
+  ST_REQUIRE(n_img >= 1 && K >= 1 && K <= 32 && K <= w->V && num_hyp >= 1 && num_hyp <= 32 &&
+                 max_length >= 1 && start_id >= 0 && start_id < w->V,
+             ST_ERR_BAD_SHAPE, "st_decode_beam_tree: n_img=%d beam_width=%d num_hyp=%d max_length=%d",
+             n_img, K, num_hyp, max_length);
+  Bump b{(char*)workspace, workspace_bytes, 0};
+  Rig rig;
+  rig.s = as_stream(stream);
+  const int rows = n_img * K;
+  rig.carve(b, w, rows);
+  TreeBufs tb;
+  tb.n = n_img; tb.K = K; tb.num_hyp = num_hyp; tb.SL = max_length + 1;
+  tb.node_val = b.take<int32_t>(rows);
+  tb.node_slot = b.take<int32_t>(rows);
+  tb.live_cnt = b.take<int32_t>(n_img);
+  tb.node_cost = b.take<float>(rows);
+  tb.seq[0] = b.take<int32_t>((int64_t)rows * tb.SL);
+  tb.seq[1] = b.take<int32_t>((int64_t)rows * tb.SL);
+  tb.fr_cnt = b.take<int32_t>(n_img);
+  tb.fr_pos = b.take<int32_t>(rows);
+  tb.parent_slot = b.take<int32_t>(rows);
+  tb.hyp_tok = b.take<int32_t>((int64_t)n_img * num_hyp * tb.SL);
+  tb.hyp_len = b.take<int32_t>((int64_t)n_img * num_hyp);
+  tb.hyp_cnt = b.take<int32_t>(n_img);
+  tb.hyp_cost = b.take<float>((int64_t)n_img * num_hyp);
+  tb.row_max = b.take<float>(rows);
+  tb.row_sum = b.take<float>(rows);
+  tb.tk_val = b.take<float>((int64_t)rows * K);
+  tb.tk_idx = b.take<int32_t>((int64_t)rows * K);
+  int32_t* tok_rows = b.take<int32_t>(rows);
+  float* h_init = b.take<float>((int64_t)n_img * w->H);
+  float* gx_init = b.take<float>((int64_t)n_img * 3 * w->H);
+  ST_REQUIRE(b.used <= b.cap, ST_ERR_WORKSPACE, "st_decode_beam_tree: workspace %lld < %lld",
+             (long long)b.cap, (long long)b.used);
+  cudaStream_t s = rig.s;
+  const int tpb = 64, gi = (n_img + tpb - 1) / tpb;
+  const int H = w->H;
+
+  // initial state = GRU state after consuming the image feature from zeros (rnn.py:47-49, step 0)
+  ST_TRY(st_sgemm(0, 1, n_img, 3 * H, w->E, 1.f, feature, w->E, w->Wih_host[0], w->E, 0.f, gx_init,
+                  3 * H, w->bih_host[0], stream));
+  ST_TRY(st_rnn_seq_fwd(ST_GRU, H, 1, &n_img, 0, 1, gx_init, w->Whh_host[0], w->bhh_host[0], nullptr,
+                        nullptr, h_init, nullptr, nullptr, nullptr, rig.barrier, stream));
+  spread_root_kernel<<<rows, 128, 0, s>>>(rig.h[rig.cur][0], h_init, H, K);
+  ST_LAUNCH_TRY("spread_root_kernel");
+  tree_init_kernel<<<gi, tpb, 0, s>>>(tb, start_id);
+  ST_LAUNCH_TRY("tree_init_kernel");
+
+  int cur_seq = 0;
+  for (int round = 0; round < max_length; ++round) {                          // beam_search.py:68
+    const int len = round + 1;
+    tree_retire_kernel<<<gi, tpb, 0, s>>>(tb, cur_seq, len, end_id);          // :70-78
+    ST_LAUNCH_TRY("tree_retire_kernel");
+    tree_tokens_kernel<<<(rows + 127) / 128, 128, 0, s>>>(tb, tok_rows);
+    ST_LAUNCH_TRY("tree_tokens_kernel");
+    gather_emb_kernel<int32_t><<<rows, 128, 0, s>>>(rig.X, w->emb, w->E, tok_rows, 1);
+    ST_LAUNCH_TRY("gather_emb_kernel");
+    ST_TRY(rig.input_proj(rig.X));
+    ST_TRY(rig.step(false));                                                  // generate_function, :83
+    ST_TRY(rig.vocab_logits());
+    row_softmax_stats_kernel<<<rows, 256, 0, s>>>(rig.logits, w->V, w->V, tb.row_max, tb.row_sum);
+    ST_LAUNCH_TRY("row_softmax_stats_kernel");
+    ST_TRY(st_topk_rows(rig.logits, w->V, rows, w->V, K, tb.tk_val, tb.tk_idx, K, stream));  // :84
+    tree_expand_kernel<<<gi, tpb, 0, s>>>(tb, cur_seq, len);                  // :86-94
+    ST_LAUNCH_TRY("tree_expand_kernel");
+    // new node s inherits the post-step state of its parent: gather h[cur] -> h[cur^1], flip
+    gather_state_kernel<<<rows, 128, 0, s>>>(rig.h[rig.cur ^ 1][0], rig.h[rig.cur][0], H, K, tb.parent_slot);
+    ST_LAUNCH_TRY("gather_state_kernel");
+    rig.cur ^= 1;
+    cur_seq ^= 1;
+  }
+  tree_finish_kernel<<<(n_img * num_hyp + 127) / 128, 128, 0, s>>>(tb, out_tokens, out_len, out_cost);
+  ST_LAUNCH_TRY("tree_finish_kernel");                                        // :96-97
+  return ST_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,181 @@
+// Packing / gather / scatter kernels around the recurrence (all HBM-bound row copies).
+//   rnn.py:29-31    Embedding + cat(feature) + pack_padded_sequence   -> st_pack_inputs
+//   rnn_attn.py:70  caption_embedding[:b_t, t]                         -> st_pack_inputs(with_feature=0)
+//   main.py:145     pack_padded_sequence(caption)[0]                   -> st_pack_targets
+//   autograd of nn.Embedding / torch.cat                               -> st_pack_inputs_bwd
+#include "common.cuh"
+
+namespace st {
+namespace {
+
+// packed row n -> (t, b): binary search over the (<=128 entry) offset table held in param space.
+__device__ __forceinline__ void row_to_tb(const StepTable& tab, int n, int& t, int& b) {
+  int lo = 0, hi = tab.nsteps - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (tab.off[mid] <= n) lo = mid; else hi = mid - 1;
+  }
+  t = lo;
+  b = n - tab.off[lo];
+}
+
+__global__ void pack_inputs_kernel(const __grid_constant__ StepTable tab, float* __restrict__ X, int ldx,
+                                   const float* __restrict__ emb, int E,
+                                   const float* __restrict__ feature,
+                                   const int64_t* __restrict__ caption, int T_cap, int with_feature) {
+  const int n = blockIdx.x;
+  int t, b;
+  row_to_tb(tab, n, t, b);
+  const float* src;
+  if (with_feature) {
+    src = (t == 0) ? feature + (size_t)b * E : emb + (size_t)caption[(size_t)b * T_cap + (t - 1)] * E;
+  } else {
+    src = emb + (size_t)caption[(size_t)b * T_cap + t] * E;
+  }
+  float* dst = X + (size_t)n * ldx;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) dst[e] = src[e];
+}
+
+__global__ void pack_inputs_bwd_kernel(const __grid_constant__ StepTable tab, const float* __restrict__ dX,
+                                       int ldx, float* __restrict__ dEmb, int E,
+                                       float* __restrict__ dfeature,
+                                       const int64_t* __restrict__ caption, int T_cap,
+                                       int with_feature) {
+  const int n = blockIdx.x;
+  int t, b;
+  row_to_tb(tab, n, t, b);
+  const float* src = dX + (size_t)n * ldx;
+  if (with_feature && t == 0) {
+    if (dfeature) {
+      float* dst = dfeature + (size_t)b * E;
+      for (int e = threadIdx.x; e < E; e += blockDim.x) dst[e] = src[e];
+    }
+    return;
+  }
+  const int64_t tok = caption[(size_t)b * T_cap + (with_feature ? t - 1 : t)];
+  float* dst = dEmb + (size_t)tok * E;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) atomicAdd(dst + e, src[e]);
+}
+
+__global__ void pack_targets_kernel(const __grid_constant__ StepTable tab, int64_t* __restrict__ out,
+                                    const int64_t* __restrict__ caption, int T_cap, int N) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  int t, b;
+  row_to_tb(tab, n, t, b);
+  out[n] = caption[(size_t)b * T_cap + t];
+}
+
+// out[c] (+)= sum_r M[r,c].  CTA = 32 columns x 8 row-stripes over a 256-row slab.
+__global__ void colsum_kernel(float* __restrict__ out, const float* __restrict__ M, int rows, int cols,
+                              int ld) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * 256;
+  float s = 0.f;
+  if (c < cols) {
+    const int r1 = min(rows, r0 + 256);
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) s += M[(size_t)r * ld + c];
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v += red[i][threadIdx.x];
+    atomicAdd(out + c, v);
+  }
+}
+
+__global__ void shift_states_kernel(const __grid_constant__ StepTable tab, float* __restrict__ Hprev,
+                                    const float* __restrict__ Hs, const float* __restrict__ h0, int H) {
+  const int n = blockIdx.x;
+  int t, b;
+  row_to_tb(tab, n, t, b);
+  float* dst = Hprev + (size_t)n * H;
+  if (t == 0) {
+    for (int e = threadIdx.x; e < H; e += blockDim.x) dst[e] = h0 ? h0[(size_t)b * H + e] : 0.f;
+  } else {
+    const float* src = Hs + (size_t)(tab.off[t - 1] + b) * H;
+    for (int e = threadIdx.x; e < H; e += blockDim.x) dst[e] = src[e];
+  }
+}
+
+}  // namespace
+}  // namespace st
+
+extern "C" {
+
+int st_pack_inputs(float* X, int ldx, const float* emb, int E, const float* feature,
+                   const int64_t* caption, int T_cap, int with_feature, int nsteps,
+                   const int* batch_sizes_host, st_stream_t stream) {
+  using namespace st;
+  StepTable tab;
+  ST_TRY(make_step_table(tab, nsteps, batch_sizes_host));
+  ST_REQUIRE(X && emb && caption, ST_ERR_NULL, "st_pack_inputs: NULL pointer");
+  ST_REQUIRE(!with_feature || feature, ST_ERR_NULL, "st_pack_inputs: feature is NULL");
+  ST_REQUIRE(E >= 1 && ldx >= E, ST_ERR_BAD_SHAPE, "st_pack_inputs: E=%d ldx=%d", E, ldx);
+  ST_REQUIRE(nsteps <= T_cap + (with_feature ? 1 : 0), ST_ERR_BAD_SHAPE,
+             "st_pack_inputs: nsteps=%d exceeds caption length %d", nsteps, T_cap);
+  pack_inputs_kernel<<<tab.off[nsteps], 128, 0, as_stream(stream)>>>(tab, X, ldx, emb, E, feature,
+                                                                     caption, T_cap, with_feature);
+  ST_LAUNCH_TRY("pack_inputs_kernel");
+  return ST_OK;
+}
+
+int st_pack_inputs_bwd(const float* dX, int ldx, float* dEmb, int E, float* dfeature,
+                       const int64_t* caption, int T_cap, int with_feature, int nsteps,
+                       const int* batch_sizes_host, st_stream_t stream) {
+  using namespace st;
+  StepTable tab;
+  ST_TRY(make_step_table(tab, nsteps, batch_sizes_host));
+  ST_REQUIRE(dX && dEmb && caption, ST_ERR_NULL, "st_pack_inputs_bwd: NULL pointer");
+  ST_REQUIRE(E >= 1 && ldx >= E, ST_ERR_BAD_SHAPE, "st_pack_inputs_bwd: E=%d ldx=%d", E, ldx);
+  pack_inputs_bwd_kernel<<<tab.off[nsteps], 128, 0, as_stream(stream)>>>(
+      tab, dX, ldx, dEmb, E, dfeature, caption, T_cap, with_feature);
+  ST_LAUNCH_TRY("pack_inputs_bwd_kernel");
+  return ST_OK;
+}
+
+int st_pack_targets(int64_t* out, const int64_t* caption, int T_cap, int nsteps,
+                    const int* batch_sizes_host, st_stream_t stream) {
+  using namespace st;
+  StepTable tab;
+  ST_TRY(make_step_table(tab, nsteps, batch_sizes_host));
+  ST_REQUIRE(out && caption, ST_ERR_NULL, "st_pack_targets: NULL pointer");
+  ST_REQUIRE(nsteps <= T_cap, ST_ERR_BAD_SHAPE, "st_pack_targets: nsteps=%d > T_cap=%d", nsteps, T_cap);
+  const int N = tab.off[nsteps];
+  pack_targets_kernel<<<(N + 255) / 256, 256, 0, as_stream(stream)>>>(tab, out, caption, T_cap, N);
+  ST_LAUNCH_TRY("pack_targets_kernel");
+  return ST_OK;
+}
+
+int st_colsum(float* out, const float* M, int rows, int cols, int ld, int accumulate,
+              st_stream_t stream) {
+  using namespace st;
+  ST_REQUIRE(out && M, ST_ERR_NULL, "st_colsum: NULL pointer");
+  ST_REQUIRE(rows >= 0 && cols >= 1 && ld >= cols, ST_ERR_BAD_SHAPE, "st_colsum: rows=%d cols=%d ld=%d",
+             rows, cols, ld);
+  cudaStream_t s = as_stream(stream);
+  if (!accumulate) ST_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * cols, s));
+  if (rows == 0) return ST_OK;
+  dim3 grid((cols + 31) / 32, (rows + 255) / 256), block(32, 8);
+  ST_REQUIRE(grid.y <= 65535, ST_ERR_BAD_SHAPE, "st_colsum: too many rows (%d)", rows);
+  colsum_kernel<<<grid, block, 0, s>>>(out, M, rows, cols, ld);
+  ST_LAUNCH_TRY("colsum_kernel");
+  return ST_OK;
+}
+
+int st_shift_states(float* Hprev, const float* Hs, const float* h0, int H, int nsteps,
+                    const int* batch_sizes_host, st_stream_t stream) {
+  using namespace st;
+  StepTable tab;
+  ST_TRY(make_step_table(tab, nsteps, batch_sizes_host));
+  ST_REQUIRE(Hprev && Hs, ST_ERR_NULL, "st_shift_states: NULL pointer");
+  ST_REQUIRE(H >= 1, ST_ERR_BAD_SHAPE, "st_shift_states: H=%d", H);
+  shift_states_kernel<<<tab.off[nsteps], 128, 0, as_stream(stream)>>>(tab, Hprev, Hs, h0, H);
+  ST_LAUNCH_TRY("shift_states_kernel");
+  return ST_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+"""Tensor-level wrappers over the C ABI: each takes CUDA tensors, passes raw pointers and sizes.
+
+These are host-side plumbing only (allocation with torch.empty, stream = torch's current stream);
+all arithmetic happens inside libshowtell_b200.so.
+"""
+import torch
+
+from . import _lib
+from ._lib import check, int_array, ptr, stream_ptr
+
+F32, I64, I32 = torch.float32, torch.int64, torch.int32
+
+
+def sgemm(A, B, *, transA=False, transB=False, bias=None, out=None, alpha=1.0, beta=0.0):
+    """out[M,N] = alpha * op(A) op(B) + beta * out + bias.  2-D fp32 tensors; the last dim must be
+    contiguous, rows may be strided (sub-matrix views of a wider matrix are fine)."""
+    lib = _lib.load()
+    for t in (A, B):
+        if t.dim() != 2 or t.stride(1) != 1 or t.dtype != F32 or not t.is_cuda:
+            raise ValueError("sgemm operands must be 2-D fp32 CUDA tensors with unit inner stride")
+    M, K = (A.shape[1], A.shape[0]) if transA else (A.shape[0], A.shape[1])
+    Kb, N = (B.shape[1], B.shape[0]) if transB else (B.shape[0], B.shape[1])
+    if K != Kb:
+        raise ValueError(f"sgemm: inner dimensions differ ({K} vs {Kb})")
+    if out is None:
+        out = torch.empty(M, N, dtype=F32, device=A.device)
+    elif out.shape != (M, N) or out.stride(1) != 1 or out.dtype != F32:
+        raise ValueError("sgemm: bad `out`")
+    if bias is not None and (bias.numel() != N or bias.dtype != F32):
+        raise ValueError("sgemm: bad bias")
+    import ctypes as C
+    check(lib.st_sgemm(int(transA), int(transB), M, N, K, float(alpha), C.c_void_p(A.data_ptr()),
+                       max(A.stride(0), 1), C.c_void_p(B.data_ptr()), max(B.stride(0), 1), float(beta),
+                       C.c_void_p(out.data_ptr()), max(out.stride(0), 1), ptr(bias), stream_ptr()),
+          "st_sgemm")
+    return out
+
+
+def pack_inputs(emb, feature, caption, bs, with_feature):
+    lib = _lib.load()
+    N, E = sum(bs), emb.shape[1]
+    X = torch.empty(N, E, dtype=F32, device=emb.device)
+    check(lib.st_pack_inputs(ptr(X, F32), E, ptr(emb, F32), E, ptr(feature, F32) if with_feature else None,
+                             ptr(caption, I64), caption.shape[1], int(with_feature), len(bs),
+                             int_array(bs), stream_ptr()), "st_pack_inputs")
+    return X
+
+
+def pack_inputs_bwd(dX, dEmb, dfeature, caption, bs, with_feature):
+    lib = _lib.load()
+    check(lib.st_pack_inputs_bwd(ptr(dX, F32), dX.shape[1], ptr(dEmb, F32), dEmb.shape[1],
+                                 ptr(dfeature, F32), ptr(caption, I64), caption.shape[1],
+                                 int(with_feature), len(bs), int_array(bs), stream_ptr()),
+          "st_pack_inputs_bwd")
+
+
+def pack_targets(caption, bs):
+    lib = _lib.load()
+    out = torch.empty(sum(bs), dtype=I64, device=caption.device)
+    check(lib.st_pack_targets(ptr(out, I64), ptr(caption, I64), caption.shape[1], len(bs), int_array(bs),
+                              stream_ptr()), "st_pack_targets")
+    return out
+
+
+def colsum(M, out=None, accumulate=False):
+    lib = _lib.load()
+    if M.dim() != 2 or M.stride(1) != 1:
+        raise ValueError("colsum: 2-D tensor with unit inner stride expected")
+    if out is None:
+        out = torch.empty(M.shape[1], dtype=F32, device=M.device)
+    import ctypes as C
+    check(lib.st_colsum(ptr(out, F32), C.c_void_p(M.data_ptr()), M.shape[0], M.shape[1],
+                        max(M.stride(0), 1), int(accumulate), stream_ptr()), "st_colsum")
+    return out
+
+
+def _barrier(device):
+    return torch.zeros(64, dtype=I32, device=device)
+
+
+def rnn_seq_fwd(kind, Gx, Whh, bhh, bs, *, h0=None, c0=None, save=True, t_range=None, out=None):
+    """Returns dict(Hs, Cs, gates, ghn).  `out` lets a caller that runs single steps (attention
+    models) keep writing into the same packed buffers."""
+    lib = _lib.load()
+    N, H = sum(bs), Whh.shape[1]
+    dev = Gx.device
+    o = out or {}
+    if "Hs" not in o:
+        o["Hs"] = torch.empty(N, H, dtype=F32, device=dev)
+        o["Cs"] = torch.empty(N, H, dtype=F32, device=dev) if kind == _lib.ST_LSTM else None
+        o["gates"] = torch.empty(N, Whh.shape[0], dtype=F32, device=dev) if save else None
+        o["ghn"] = torch.empty(N, H, dtype=F32, device=dev) if (save and kind == _lib.ST_GRU) else None
+        o["barrier"] = _barrier(dev)
+    t0, t1 = t_range if t_range is not None else (0, len(bs))
+    check(lib.st_rnn_seq_fwd(kind, H, len(bs), int_array(bs), t0, t1, ptr(Gx, F32), ptr(Whh, F32),
+                             ptr(bhh, F32), ptr(h0, F32), ptr(c0, F32), ptr(o["Hs"], F32), ptr(o["Cs"]),
+                             ptr(o["gates"]), ptr(o["ghn"]), ptr(o["barrier"], I32), stream_ptr()),
+          "st_rnn_seq_fwd")
+    return o
+
+
+def rnn_seq_bwd(kind, Whh, bs, saved, dHs, *, h0=None, c0=None, t_range=None, out=None):
+    """Returns dict(dG, dGh, dstate).  dstate (2, B0, H): [0] = dh0, [1] = dc0 once t reaches 0."""
+    lib = _lib.load()
+    N, H, GH = sum(bs), Whh.shape[1], Whh.shape[0]
+    dev = dHs.device
+    o = out or {}
+    if "dG" not in o:
+        o["dG"] = torch.empty(N, GH, dtype=F32, device=dev)
+        o["dGh"] = torch.empty(N, GH, dtype=F32, device=dev) if kind == _lib.ST_GRU else o["dG"]
+        o["dstate"] = torch.zeros(2, bs[0], H, dtype=F32, device=dev)
+        o["barrier"] = _barrier(dev)
+    t_hi, t_lo = t_range if t_range is not None else (len(bs), 0)
+    check(lib.st_rnn_seq_bwd(kind, H, len(bs), int_array(bs), t_hi, t_lo, ptr(Whh, F32), ptr(h0, F32),
+                             ptr(c0, F32), ptr(saved["Hs"], F32), ptr(saved["Cs"]), ptr(saved["gates"], F32),
+                             ptr(saved["ghn"]), ptr(dHs, F32), ptr(o["dG"], F32), ptr(o["dGh"], F32),
+                             ptr(o["dstate"], F32), ptr(o["barrier"], I32), stream_ptr()),
+          "st_rnn_seq_bwd")
+    return o
+
+
+def shift_states(Hs, bs, h0=None):
+    lib = _lib.load()
+    out = torch.empty_like(Hs)
+    check(lib.st_shift_states(ptr(out, F32), ptr(Hs, F32), ptr(h0, F32), Hs.shape[1], len(bs),
+                              int_array(bs), stream_ptr()), "st_shift_states")
+    return out
+
+
+def ce_fwd_bwd(logits, target, grad_scale=None, inplace=False):
+    """Returns (loss_sum (1,), lse (N,), dlogits or None).  dlogits = (softmax - onehot) * grad_scale."""
+    lib = _lib.load()
+    N, V = logits.shape
+    dev = logits.device
+    loss_sum = torch.empty(1, dtype=F32, device=dev)
+    lse = torch.empty(N, dtype=F32, device=dev)
+    dl = None
+    if grad_scale is not None:
+        dl = logits if inplace else torch.empty_like(logits)
+    check(lib.st_ce_fwd_bwd(ptr(logits, F32), logits.stride(0), ptr(target, I64), N, V, ptr(loss_sum),
+                            ptr(lse), ptr(dl), float(grad_scale or 0.0), stream_ptr()), "st_ce_fwd_bwd")
+    return loss_sum, lse, dl
+
+
+def argmax_rows(X):
+    lib = _lib.load()
+    idx = torch.empty(X.shape[0], dtype=I64, device=X.device)
+    check(lib.st_argmax_rows(ptr(X, F32), X.stride(0), X.shape[0], X.shape[1], ptr(idx), 1, stream_ptr()),
+          "st_argmax_rows")
+    return idx
+
+
+def topk_rows(X, K):
+    lib = _lib.load()
+    val = torch.empty(X.shape[0], K, dtype=F32, device=X.device)
+    idx = torch.empty(X.shape[0], K, dtype=I32, device=X.device)
+    check(lib.st_topk_rows(ptr(X, F32), X.stride(0), X.shape[0], X.shape[1], K, ptr(val), ptr(idx), K,
+                           stream_ptr()), "st_topk_rows")
+    return val, idx

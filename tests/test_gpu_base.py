@@ -1,0 +1,209 @@
+"""GPU parity of the base decoders (rnn.py / LSTM/rnn_lstm.py) against
+  (a) the golden fixtures produced by the unmodified reference, and
+  (b) the CPU oracle on seeded inputs at larger sizes.
+fp32 mode; the bar is north_star's 1e-4 relative for loss / logits / gradients and bit-exact token
+ids (outside rounding-noise-decided rankings, see oracle.rnn_beam_chain)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import BASE_CASES, golden_grads, golden_params, load_golden, rel_err
+from oracle import showtell_oracle as O
+
+TOL = 1e-4
+
+
+def _module(g, dev):
+    E, H, V, L, _, _ = g["dims"].tolist()
+    kind = str(g["kind"])
+    if kind == "gru":
+        from showtell_b200.rnn import RNN
+    else:
+        from showtell_b200.rnn_lstm import RNN
+    m = RNN(E, H, V, L)
+    m.load_state_dict(golden_params(g))           # reference checkpoint keys load unchanged
+    return m.to(dev)
+
+
+@pytest.mark.parametrize("name", BASE_CASES)
+def test_golden_forward_backward(name):
+    dev = torch.device("cuda:0")
+    g = load_golden(name)
+    m = _module(g, dev)
+    feat = torch.from_numpy(g["cnn_feature"]).to(dev).requires_grad_(True)
+    cap = torch.from_numpy(g["caption"]).to(dev)
+    lengths = g["lengths"].tolist()
+    logits = m(feat, cap, lengths)                                        # main.py:148
+    assert logits.shape == g["logits"].shape
+    assert rel_err(logits, g["logits"]) < TOL
+    target = torch.nn.utils.rnn.pack_padded_sequence(cap, lengths, batch_first=True)[0]
+    loss = torch.nn.CrossEntropyLoss()(logits, target)                    # main.py:149
+    assert abs(float(loss) - float(g["loss"])) < TOL * abs(float(g["loss"]))
+    loss.backward()
+    gg = golden_grads(g)
+    for n, p in m.named_parameters():
+        assert rel_err(p.grad, gg[n]) < TOL, n
+    assert rel_err(feat.grad, gg["cnn_feature"]) < TOL
+
+
+@pytest.mark.parametrize("name", BASE_CASES)
+def test_golden_fused_loss(name):
+    dev = torch.device("cuda:0")
+    g = load_golden(name)
+    m = _module(g, dev)
+    feat = torch.from_numpy(g["cnn_feature"]).to(dev).requires_grad_(True)
+    cap = torch.from_numpy(g["caption"]).to(dev)
+    loss = m.forward_loss(feat, cap, g["lengths"].tolist())
+    assert abs(float(loss) - float(g["loss"])) < TOL * abs(float(g["loss"]))
+    (loss * 3.0).backward()
+    gg = golden_grads(g)
+    for n, p in m.named_parameters():
+        assert rel_err(p.grad / 3.0, gg[n]) < TOL, n
+    assert rel_err(feat.grad / 3.0, gg["cnn_feature"]) < TOL
+
+
+@pytest.mark.parametrize("name", BASE_CASES)
+def test_golden_greedy(name):
+    dev = torch.device("cuda:0")
+    g = load_golden(name)
+    m = _module(g, dev)
+    feat = torch.from_numpy(g["cnn_feature"]).to(dev)
+    tok = m.sentence_index(feat)
+    assert tok.shape == (feat.shape[0], 25) and tok.dtype == torch.int64
+    assert np.array_equal(tok.cpu().numpy(), g["greedy"])
+    tok1 = m.sentence_index(feat[:1])
+    assert tok1.shape == (25,)                                            # squeeze quirk (rnn.py:56)
+    assert np.array_equal(tok1.cpu().numpy(), g["greedy_b1"])
+
+
+def _check_chain(m, p, feat, K, max_len=25, eps=1e-5):
+    """CUDA chain beam vs the oracle, row by row: identical survivors (words + scores) in every
+    round up to the first round whose ranking hangs on <= eps of logit; identical final sentence
+    when no round is that close.  Returns (#rows compared to the end, #rows)."""
+    from showtell_b200 import decode
+    tok, ts, tw = decode.beam_chain(m, feat, K, max_len, trace=True)
+    tok, ts, tw = tok.cpu(), ts.cpu(), tw.cpu()
+    full = 0
+    pc = {k: v.cpu() for k, v in p.items()}
+    for i in range(feat.shape[0]):
+        with torch.no_grad():
+            seq, trace = O.rnn_beam_chain(pc, feat[i:i + 1].cpu(), K, max_len, return_trace=True)
+        stop = O.beam_chain_margin(trace, K, eps)
+        for r in range(min(stop, len(trace))):
+            assert tw[r, i].tolist() == trace[r]["words"], (i, r)
+            assert np.allclose(ts[r, i].numpy(), np.array(trace[r]["scores"][:K]), atol=2e-5), (i, r)
+        if stop == len(trace):
+            full += 1
+            assert tok[i].tolist() == seq.tolist(), i
+    return full, feat.shape[0]
+
+
+@pytest.mark.parametrize("name,K", [("gru_l1", 1), ("gru_l1", 3), ("gru_l1", 5), ("gru_tiny", 2),
+                                    ("gru_l2", 3), ("gru_med", 3)])
+def test_golden_beam_chain(name, K):
+    dev = torch.device("cuda:0")
+    g = load_golden(name)
+    m = _module(g, dev)
+    feat = torch.from_numpy(g["cnn_feature"]).to(dev)
+    _check_chain(m, golden_params(g), feat, K)
+    tok = m.sentence_index(feat, beam_size=K)
+    same = (tok.cpu().numpy() == g[f"beam_chain_k{K}"]).all(axis=1).sum()
+    print(f"{name} K={K}: {same}/{feat.shape[0]} rows identical to the reference run")
+    if K == 1:
+        assert np.array_equal(tok.cpu().numpy(), g["greedy"])             # rnn.py:43
+    one = m.sentence_index(feat[:1], beam_size=K)
+    assert one.shape == (25,)                                             # rnn.py:107 squeeze
+
+
+def test_golden_beam_tree():
+    dev = torch.device("cuda:0")
+    g = load_golden("gru_tiny")
+    t = load_golden("tree_beam_gru_tiny")
+    K, max_length, end_id, rows, _ = t["meta"].tolist()
+    m = _module(g, dev)
+    feat = torch.from_numpy(g["cnn_feature"]).to(dev)
+    tok, ln, cost = m.sentence_index(feat, beam_size=K, beam_mode="tree", max_len=max_length,
+                                     start_id=1, end_id=end_id, num_hypotheses=K)
+    tok, ln, cost = tok.cpu(), ln.cpu(), cost.cpu()
+    for i in range(rows):
+        n = int(t[f"row{i}.n"])
+        assert int((ln[i] > 0).sum()) == n
+        for j in range(n):
+            ref = t[f"row{i}.hyp{j}.seq"].tolist()
+            assert tok[i, j, :int(ln[i, j])].tolist() == ref, (i, j)
+            assert abs(float(cost[i, j]) - float(t[f"row{i}.hyp{j}.cost"])) < 1e-4
+
+
+def _random_case(kind, E, H, V, L, B, T, seed, ragged):
+    torch.manual_seed(seed)
+    g = torch.Generator().manual_seed(seed)
+    if kind == "gru":
+        from showtell_b200.rnn import RNN
+    else:
+        from showtell_b200.rnn_lstm import RNN
+    m = RNN(E, H, V, L)
+    lengths = sorted(torch.randint(max(2, T // 3), T + 1, (B,), generator=g).tolist(), reverse=True) \
+        if ragged else [T] * B
+    lengths[0] = T
+    cap = torch.zeros(B, T, dtype=torch.int64)
+    for b, l in enumerate(lengths):
+        cap[b, 0] = 1
+        cap[b, 1:l - 1] = torch.randint(4, V, (l - 2,), generator=g)
+        cap[b, l - 1] = 2
+    feat = torch.randn(B, E, generator=g)
+    return m, feat, cap, lengths
+
+
+@pytest.mark.parametrize("kind,E,H,V,L,B,T,ragged", [
+    ("gru", 512, 512, 10000, 1, 32, 20, False),      # BASELINE config 1
+    ("lstm", 512, 512, 10000, 1, 48, 20, True),
+    ("gru", 96, 160, 1000, 3, 150, 12, True),        # >128 rows: two batch tiles, 3 layers
+    ("lstm", 64, 128, 777, 2, 9, 5, True),
+])
+def test_oracle_parity_train(kind, E, H, V, L, B, T, ragged):
+    dev = torch.device("cuda:0")
+    m, feat, cap, lengths = _random_case(kind, E, H, V, L, B, T, 7, ragged)
+    p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    loss_ref, grads_ref, ex = O.train_step(p, kind, feat, cap, lengths)
+    m = m.to(dev)
+    featg = feat.to(dev).requires_grad_(True)
+    loss = m.forward_loss(featg, cap.to(dev), lengths)
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) < TOL * float(loss_ref)
+    for n, q in m.named_parameters():
+        assert rel_err(q.grad, grads_ref[n]) < TOL, n
+    assert rel_err(featg.grad, grads_ref["cnn_feature"]) < TOL
+    with torch.no_grad():
+        logits = m(feat.to(dev), cap.to(dev), lengths)
+    assert rel_err(logits, ex["logits"]) < TOL
+
+
+@pytest.mark.parametrize("kind,L", [("gru", 1), ("lstm", 1), ("gru", 2)])
+def test_oracle_parity_greedy_full_size(kind, L):
+    dev = torch.device("cuda:0")
+    m, feat, _, _ = _random_case(kind, 512, 512, 10000, L, 16, 20, 11, False)
+    p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref = O.rnn_greedy(p, kind, feat)
+    tok = m.to(dev).sentence_index(feat.to(dev))
+    assert np.array_equal(tok.cpu().numpy(), ref.numpy())
+
+
+@pytest.mark.parametrize("K", [3, 5])
+def test_oracle_parity_beam_chain_full_size(K):
+    dev = torch.device("cuda:0")
+    m, feat, _, _ = _random_case("gru", 512, 512, 10000, 1, 6, 20, 13, False)
+    p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    full, n = _check_chain(m.to(dev), p, feat.to(dev), K, max_len=20)
+    print(f"beam-{K} chain, full size: {full}/{n} rows separated in every round and bit-exact")
+
+
+def test_cpu_tensors_raise():
+    from showtell_b200.rnn import RNN
+    m = RNN(8, 8, 11, 1).cuda()
+    with pytest.raises(RuntimeError):
+        m(torch.randn(2, 8), torch.zeros(2, 3, dtype=torch.int64), [3, 2])
+    with pytest.raises(RuntimeError):
+        m(torch.randn(2, 8).cuda(), torch.zeros(2, 3, dtype=torch.int64).cuda(), [2, 3])   # unsorted

@@ -1,0 +1,66 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls without a GPU)."""
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def test_library_exports_every_header_symbol():
+    from showtell_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "showtell_b200.h")).read()
+    declared = set(re.findall(r"\b(st_[a-z0-9_]+)\s*\(", header))
+    declared -= {"st_status"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/showtell_b200.h but not exported"
+    assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
+    assert lib.st_version() >= 100
+
+
+def test_batch_sizes_matches_pack_padded_sequence():
+    from showtell_b200 import _lib
+    for lengths in ([7, 6, 4, 4, 2], [5], [3, 3, 3], [20] * 32, [9, 1]):
+        x = torch.zeros(len(lengths), max(lengths), 1)
+        ref = torch.nn.utils.rnn.pack_padded_sequence(x, lengths, batch_first=True).batch_sizes.tolist()
+        assert _lib.batch_sizes(lengths) == ref
+    for bad in ([2, 3], [], [3, 0]):
+        with pytest.raises(RuntimeError):
+            _lib.batch_sizes(bad)
+
+
+def test_state_dict_keys_match_reference_checkpoints():
+    from helpers import golden_params, load_golden
+    from showtell_b200.rnn import RNN as GRU
+    from showtell_b200.rnn_lstm import RNN as LSTM
+    for name, cls in (("gru_l2", GRU), ("lstm_l3", LSTM)):
+        g = load_golden(name)
+        E, H, V, L, _, _ = g["dims"].tolist()
+        m = cls(E, H, V, L)
+        p = golden_params(g)
+        assert set(m.state_dict().keys()) == set(p.keys())
+        m.load_state_dict(p)
+        for k, v in m.state_dict().items():
+            assert v.shape == p[k].shape
+
+
+def test_no_cpu_fallback():
+    from showtell_b200.rnn import RNN
+    m = RNN(8, 8, 11, 1)
+    with pytest.raises(RuntimeError):
+        m(torch.randn(2, 8), torch.zeros(2, 3, dtype=torch.int64), [3, 2])
+    with pytest.raises(RuntimeError):
+        m.sentence_index(torch.randn(2, 8))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "showtell_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f
