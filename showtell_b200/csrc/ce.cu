@@ -12,23 +12,26 @@ namespace {
 
 constexpr int NT = 256;
 
+// Block-wide reductions: warp shuffle, then every thread folds the NT/32 per-warp partials.
 __device__ __forceinline__ float block_reduce_max(float v, float* red) {
   v = warp_max(v);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  float r = (threadIdx.x < NT / 32) ? red[threadIdx.x] : -FLT_MAX;
-  r = warp_max(r);
+  float r = red[0];
+#pragma unroll
+  for (int i = 1; i < NT / 32; ++i) r = fmaxf(r, red[i]);
   __syncthreads();
-  return __shfl_sync(0xffffffffu, r, 0);
+  return r;
 }
 __device__ __forceinline__ float block_reduce_sum(float v, float* red) {
   v = warp_sum(v);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
-  float r = (threadIdx.x < NT / 32) ? red[threadIdx.x] : 0.f;
-  r = warp_sum(r);
+  float r = red[0];
+#pragma unroll
+  for (int i = 1; i < NT / 32; ++i) r += red[i];
   __syncthreads();
-  return __shfl_sync(0xffffffffu, r, 0);
+  return r;
 }
 
 __global__ void __launch_bounds__(NT) ce_kernel(const float* logits, int ld,
@@ -76,14 +79,9 @@ __device__ __forceinline__ VI block_reduce_vi(VI x, VI* red) {
   }
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
   __syncthreads();
-  VI r = (threadIdx.x < NT / 32) ? red[threadIdx.x] : VI{-FLT_MAX, 0x7fffffff};
+  VI r = red[0];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    VI y{__shfl_xor_sync(0xffffffffu, r.v, o), __shfl_xor_sync(0xffffffffu, r.i, o)};
-    r = vi_better(r, y);
-  }
-  r.v = __shfl_sync(0xffffffffu, r.v, 0);
-  r.i = __shfl_sync(0xffffffffu, r.i, 0);
+  for (int i = 1; i < NT / 32; ++i) r = vi_better(r, red[i]);
   __syncthreads();
   return r;
 }

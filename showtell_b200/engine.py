@@ -98,7 +98,7 @@ class BaseLogitsFn(torch.autograd.Function):
         feature_c = feature.detach().contiguous().to(F32)
         caption_c = caption.contiguous()
         bs = _check_inputs(feature_c, caption_c, lengths, mod.embed_dim)
-        save = torch.is_grad_enabled() and (feature.requires_grad or any(p.requires_grad for p in params))
+        save = any(ctx.needs_input_grad)
         Hs, layers = base_forward(P, mod._kind, mod.num_layers, feature_c, caption_c, bs, save)
         logits = vocab_logits(P, Hs)
         ctx.names, ctx.P, ctx.mod = names, P, mod
@@ -130,7 +130,7 @@ class BaseLossFn(torch.autograd.Function):
         bs = _check_inputs(feature_c, caption_c, lengths, mod.embed_dim)
         if len(bs) > caption_c.shape[1]:
             raise ValueError("caption_size exceeds the padded caption length")
-        need = torch.is_grad_enabled() and (feature.requires_grad or any(p.requires_grad for p in params))
+        need = any(ctx.needs_input_grad)
         N = sum(bs)
         denom = float(denom if denom is not None else N)
         Hs, layers = base_forward(P, mod._kind, mod.num_layers, feature_c, caption_c, bs, need)
@@ -142,7 +142,7 @@ class BaseLossFn(torch.autograd.Function):
         ctx.grads, ctx.dfeat = None, None
         if need:
             ctx.grads, ctx.dfeat = base_backward(P, mod._kind, mod.num_layers, caption_c, bs, layers, Hs, dl,
-                                                 feature.requires_grad, feature_c.shape)
+                                                 ctx.needs_input_grad[1], feature_c.shape)
         return (loss_sum / denom).reshape(())
 
     @staticmethod
