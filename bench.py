@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the show-tell caption-decoder hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload lstm_train|gru_train|beam3] [--dtype fp32|bf16]
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on that fits one GPU):
+LSTM/rnn_lstm.py decoder training step -- forward + cross-entropy + backward -- with E = H = 512,
+V = 10 000, batch 256 per GPU, caption length 20, L = 1, synthetic N(0,1) features of the ResNet
+head's output shape and random-init weights.  One "step" = one such iteration on one batch
+(5120 tokens per GPU).  Metric: training tokens/s, whole job.
+
+Our arm times the repo's public API (RNN.forward_loss + backward) with CUDA events on the
+launching stream; `value` has the batch resident in HBM, `e2e` copies features + captions from
+pinned host memory and reads the loss back every step.  Between timed steps a 256 MiB buffer is
+rewritten to flush the 126 MB L2 (outside the per-step event pairs).  N > 1: one process per GPU
+(torchrun), batch-sharded, gradients all-reduced over NCCL inside the timed step, max over ranks.
+
+`--impl reference` times the reference algorithm on the host CPU cores (the oracle port; the
+reference is pure Python over torch CPU kernels and is not shipped to the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+E = H = 512
+V = 10000
+T = 20
+WORKLOADS = {
+    # name: (model kind, per-GPU batch, description)
+    "lstm_train": ("lstm", 256, "rnn_lstm.py LSTM decoder train step fwd+CE+bwd, E=H=512 V=10000 B=256/GPU T=20 L=1"),
+    "gru_train": ("gru", 32, "rnn.py GRU decoder train step fwd+CE+bwd, E=H=512 V=10000 B=32/GPU T=20 L=1"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+        self.t0 = self.t1 = None          # wall-clock window of the timed region
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        try:
+            self.proc.terminate()
+        except Exception:
+            pass
+        rows = [r for t, r in self.rows if self.t0 is None or (self.t0 - 0.05 <= t <= (self.t1 or t) + 0.15)]
+        self.rows = rows or [r for _, r in self.rows]
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_batch(kind, B, seed):
+    g = torch.Generator().manual_seed(seed)
+    feat = torch.randn(B, E, generator=g)
+    cap = torch.randint(4, V, (B, T), generator=g)
+    cap[:, 0] = 1
+    cap[:, -1] = 2
+    return feat, cap, [T] * B
+
+
+def train_flops(kind, B):
+    g = 3 if kind == "gru" else 4
+    return 3.0 * 2.0 * B * T * (g * H * (E + H) + H * V)
+
+
+def cpu_reference(kind, B, steps, warmup, budget_s=150.0):
+    """Reference algorithm on the host cores: oracle port (explicit-equation torch CPU) of
+    rnn(_lstm).py forward + CrossEntropyLoss + backward.  Bounded: if K+W full batches would not fit
+    in budget_s, each step runs a row-sample of the batch and tokens are counted accordingly."""
+    from oracle import showtell_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(1)
+    from showtell_b200.rnn import RNN as G
+    from showtell_b200.rnn_lstm import RNN as L_
+    m = (G if kind == "gru" else L_)(E, H, V, 1)
+    p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    feat, cap, lengths = make_batch(kind, B, 1)
+    t0 = time.perf_counter()
+    O.train_step(p, kind, feat[:32], cap[:32], lengths[:32])
+    per32 = time.perf_counter() - t0
+    bs = B
+    while bs > 32 and per32 * (bs / 32) * (steps + warmup) > budget_s:
+        bs //= 2
+    f, c, l = feat[:bs], cap[:bs], lengths[:bs]
+    for _ in range(warmup):
+        O.train_step(p, kind, f, c, l)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.train_step(p, kind, f, c, l)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": bs * T / dt, "unit": "tokens/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} steps of {bs}/{B} rows x {T} tokens (fwd+CE+bwd, fp32, torch CPU {torch.__version__})",
+            "ms_per_step": dt * 1e3}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="lstm_train", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default=None, choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    kind, B, desc = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = cpu_reference(kind, B, args.steps, min(args.warmup, 2))
+        line = {"impl": "reference", "metric": "train_tokens_per_s", "value": r["value"], "unit": "tokens/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 2),
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc + " [reference algorithm on host CPU]"},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch.distributed as dist
+    from showtell_b200 import _lib, ops
+    from showtell_b200.rnn import RNN as GruRNN
+    from showtell_b200.rnn_lstm import RNN as LstmRNN
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    lib = _lib.load()
+    dtype = args.dtype or "fp32"
+    torch.manual_seed(1)
+    model = (GruRNN if kind == "gru" else LstmRNN)(E, H, V, 1, dtype=dtype).to(dev)
+    params = [p for p in model.parameters()]
+    feat_h, cap_h, lengths = make_batch(kind, B, 1 + rank)
+    feat_p, cap_p = feat_h.pin_memory(), cap_h.pin_memory()
+    feat_d, cap_d = feat_h.to(dev), cap_h.to(dev)
+    global_tokens = B * T * world
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def allreduce_grads():
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            off = 0
+            for p in params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+
+    def step(f, c):
+        for p in params:
+            p.grad = None
+        loss = model.forward_loss(f, c, lengths, global_tokens=global_tokens)
+        loss.backward()
+        allreduce_grads()
+        return loss
+
+    def step_e2e():
+        f = feat_p.to(dev, non_blocking=True)
+        c = cap_p.to(dev, non_blocking=True)
+        loss = step(f, c)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, K):
+        evs = []
+        barrier()
+        for _ in range(K):
+            flush.fill_(1)                       # L2 flush, outside the event pair
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        total = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([total], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t)
+        return total / K
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    for _ in range(warmup):
+        step(feat_d, cap_d)
+    ops.TIMER = ops.KernelTimer()
+    l0 = lib.st_launch_count()
+    if sampler:
+        sampler.t0 = time.time()
+    ms = timed(lambda: step(feat_d, cap_d), args.steps)
+    launches = (lib.st_launch_count() - l0) // args.steps
+    ksum = ops.TIMER.summary()
+    ops.TIMER = None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    if sampler:
+        sampler.t1 = time.time()
+    clocks = sampler.finish() if sampler else None
+    loss_val = float(loss_host)
+
+    if rank == 0:
+        pk = peaks()
+        # dominant kernel: the vocabulary-projection GEMMs (fwd logits, dW, dH: 3 x 2*N*H*V FLOPs)
+        n_tok = B * T
+        vocab_flops = 2.0 * n_tok * H * V
+        tags = [t for t in ("vocab_fwd", "vocab_dw", "vocab_dh") if t in ksum]
+        vocab_ms = sum(ksum[t][1] for t in tags) / max(len(tags), 1)
+        ach = vocab_flops / (vocab_ms * 1e-3) / 1e12 if tags else None
+        roof = {"bound": "tensor", "kernel": "vocabulary projection GEMM (fwd / dW / dH, mean of the three)",
+                "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": (ach / pk["tf_sustained"]) if ach else None, "traffic": None,
+                "peak_source": pk["src"] + " (bf16 cuBLAS sustained)",
+                "kernels_ms": {k: round(v[1], 4) for k, v in ksum.items()},
+                "step_flops": train_flops(kind, B),
+                "step_tflops": train_flops(kind, B) / (ms * 1e-3) / 1e12}
+        line = {"metric": "train_tokens_per_s", "value": global_tokens / (ms * 1e-3), "unit": "tokens/s",
+                "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if dtype == "fp32" else "bf16", "data": "synthetic",
+                "config": {"workload": desc, "global_batch": B * world, "seq_len": T, "parallelism": f"dp{world}",
+                           "l2": "flushed between timed steps (256 MiB fill, outside the event pairs)",
+                           "loss": loss_val},
+                "e2e": {"value": global_tokens / (ms_e2e * 1e-3), "unit": "tokens/s",
+                        "h2d_bytes_per_step": feat_p.numel() * 4 + cap_p.numel() * 8, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference(kind, B, 6, 1, budget_s=25.0)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

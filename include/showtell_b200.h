@@ -47,6 +47,8 @@ enum { ST_MAX_STEPS = 128 }; /* longest padded caption the sequence kernels acce
 
 int st_version(void);
 const char* st_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t st_launch_count(void);
 /* Device facts the host side sizes grids with. */
 int st_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_optin_bytes);
 

@@ -32,6 +32,7 @@ _IP = C.POINTER(C.c_int)
 _SIGS = {
     "st_version": (C.c_int, []),
     "st_last_error": (C.c_char_p, []),
+    "st_launch_count": (C.c_int64, []),
     "st_device_info": (_I, [_IP, _IP, _IP, C.POINTER(_L)]),
     "st_sgemm": (_I, [_I, _I, _I, _I, _I, _F, _P, _I, _P, _I, _F, _P, _I, _P, _P]),
     "st_pack_inputs": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _IP, _P]),

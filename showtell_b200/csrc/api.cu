@@ -6,6 +6,9 @@
 namespace st {
 
 static thread_local char g_err[512] = "";
+static long long g_launches = 0;
+
+void note_launch(int n) { __atomic_fetch_add(&g_launches, (long long)n, __ATOMIC_RELAXED); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -43,6 +46,8 @@ extern "C" {
 int st_version(void) { return 100; }
 
 const char* st_last_error(void) { return st::g_err; }
+
+int64_t st_launch_count(void) { return (int64_t)__atomic_load_n(&st::g_launches, __ATOMIC_RELAXED); }
 
 int st_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_optin_bytes) {
   int dev = 0;

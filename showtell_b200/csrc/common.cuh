@@ -10,6 +10,7 @@
 namespace st {
 
 void set_error(const char* fmt, ...);
+void note_launch(int n = 1);  // counts kernel launches issued by this library (st_launch_count)
 
 // batch_sizes + packed-row offsets of a PackedSequence, passed to kernels by value
 // (pack_padded_sequence semantics, rnn.py:31).
@@ -44,6 +45,7 @@ inline cudaStream_t as_stream(st_stream_t s) { return reinterpret_cast<cudaStrea
                     __FILE__, __LINE__);                                                   \
       return ST_ERR_CUDA;                                                                  \
     }                                                                                      \
+    st::note_launch();                                                                     \
   } while (0)
 
 #define ST_REQUIRE(cond, code, ...)                                                        \

@@ -294,6 +294,7 @@ int launch_fwd(const StepTable& tab, SeqFwdParams p, cudaStream_t s) {
     ST_CUDA_TRY(cudaMemsetAsync(p.barrier, 0, sizeof(int) * 64, s));
     void* args[] = {(void*)&tab, (void*)&p};
     ST_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, grid, dim3(NT), args, smem, s));
+    note_launch();
   } else {
     for (int t = p.t_begin; t < p.t_end; ++t) {
       SeqFwdParams q = p;
@@ -327,6 +328,7 @@ int launch_bwd(const StepTable& tab, SeqBwdParams p, cudaStream_t s) {
     ST_CUDA_TRY(cudaMemsetAsync(p.barrier, 0, sizeof(int) * 64, s));
     void* args[] = {(void*)&tab, (void*)&p};
     ST_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, grid, dim3(NT), args, smem, s));
+    note_launch();
   } else {
     for (int t = p.t_hi - 1; t >= p.t_lo; --t) {
       dim3 g((p.H + UT - 1) / UT, (tab.bs[t] + BT - 1) / BT);

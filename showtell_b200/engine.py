@@ -23,8 +23,8 @@ def stack_forward(P, kind, L, X, bs, save):
     layers, inp = [], X
     for l in range(L):
         Wih, Whh, bih, bhh = layer_params(P, l)
-        Gx = ops.sgemm(inp, Wih, transB=True, bias=bih)                    # W_ih x + b_ih, all steps
-        o = ops.rnn_seq_fwd(kind, Gx, Whh, bhh, bs, save=save)
+        Gx = ops.sgemm(inp, Wih, transB=True, bias=bih, tag="ih_fwd")      # W_ih x + b_ih, all steps
+        o = ops.rnn_seq_fwd(kind, Gx, Whh, bhh, bs, save=save, tag="seq_fwd")
         layers.append({"inp": inp, "out": o})
         inp = o["Hs"]
     return inp, layers
@@ -37,13 +37,13 @@ def stack_backward(P, kind, L, bs, layers, dHs_top, grads):
     for l in reversed(range(L)):
         Wih, Whh, bih, bhh = layer_params(P, l)
         sv = layers[l]
-        b = ops.rnn_seq_bwd(kind, Whh, bs, sv["out"], dH)
+        b = ops.rnn_seq_bwd(kind, Whh, bs, sv["out"], dH, tag="seq_bwd")
         Hprev = ops.shift_states(sv["out"]["Hs"], bs)
-        grads[f"unit.weight_hh_l{l}"] = ops.sgemm(b["dGh"], Hprev, transA=True)       # dGh^T Hprev
+        grads[f"unit.weight_hh_l{l}"] = ops.sgemm(b["dGh"], Hprev, transA=True, tag="hh_dw")   # dGh^T Hprev
         grads[f"unit.bias_hh_l{l}"] = ops.colsum(b["dGh"])
-        grads[f"unit.weight_ih_l{l}"] = ops.sgemm(b["dG"], sv["inp"], transA=True)    # dG^T X
+        grads[f"unit.weight_ih_l{l}"] = ops.sgemm(b["dG"], sv["inp"], transA=True, tag="ih_dw")  # dG^T X
         grads[f"unit.bias_ih_l{l}"] = ops.colsum(b["dG"])
-        dH = ops.sgemm(b["dG"], Wih)                                                  # dX = dG W_ih
+        dH = ops.sgemm(b["dG"], Wih, tag="ih_dx")                                     # dX = dG W_ih
     return dH
 
 
@@ -54,16 +54,16 @@ def base_forward(P, kind, L, feature, caption, bs, save):
 
 
 def vocab_logits(P, Hs):
-    return ops.sgemm(Hs, P["linear.weight"], transB=True, bias=P["linear.bias"])      # rnn.py:33
+    return ops.sgemm(Hs, P["linear.weight"], transB=True, bias=P["linear.bias"], tag="vocab_fwd")  # rnn.py:33
 
 
 def base_backward(P, kind, L, caption, bs, layers, Hs_top, dlogits, want_dfeature, feature_shape):
     """Gradients of everything given dlogits (N, V).  Returns (grads dict, dfeature or None)."""
     grads = {}
     Wv = P["linear.weight"]
-    grads["linear.weight"] = ops.sgemm(dlogits, Hs_top, transA=True)                  # dlogits^T Hs
+    grads["linear.weight"] = ops.sgemm(dlogits, Hs_top, transA=True, tag="vocab_dw")  # dlogits^T Hs
     grads["linear.bias"] = ops.colsum(dlogits)
-    dHs = ops.sgemm(dlogits, Wv)                                                      # dlogits W_v
+    dHs = ops.sgemm(dlogits, Wv, tag="vocab_dh")                                      # dlogits W_v
     dX = stack_backward(P, kind, L, bs, layers, dHs, grads)
     dEmb = torch.zeros_like(P["embeddings.weight"])
     dfeat = torch.empty(feature_shape, dtype=F32, device=dX.device) if want_dfeature else None

@@ -11,7 +11,32 @@ from ._lib import check, int_array, ptr, stream_ptr
 F32, I64, I32 = torch.float32, torch.int64, torch.int32
 
 
-def sgemm(A, B, *, transA=False, transB=False, bias=None, out=None, alpha=1.0, beta=0.0):
+class KernelTimer:
+    """Optional CUDA-event timing of tagged kernel launches (used by bench.py for the roofline of
+    the dominant kernel; events are recorded on the launching stream, inside the timed step)."""
+
+    def __init__(self):
+        self.spans = {}
+
+    def begin(self, tag):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        return (tag, e0)
+
+    def end(self, tok):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.spans.setdefault(tok[0], []).append((tok[1], e1))
+
+    def summary(self):
+        """tag -> (launches, mean ms).  Call after a synchronize."""
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v) / len(v)) for k, v in self.spans.items()}
+
+
+TIMER = None      # set to a KernelTimer to time tagged launches
+
+
+def sgemm(A, B, *, transA=False, transB=False, bias=None, out=None, alpha=1.0, beta=0.0, tag=None):
     """out[M,N] = alpha * op(A) op(B) + beta * out + bias.  2-D fp32 tensors; the last dim must be
     contiguous, rows may be strided (sub-matrix views of a wider matrix are fine)."""
     lib = _lib.load()
@@ -29,10 +54,13 @@ def sgemm(A, B, *, transA=False, transB=False, bias=None, out=None, alpha=1.0, b
     if bias is not None and (bias.numel() != N or bias.dtype != F32):
         raise ValueError("sgemm: bad bias")
     import ctypes as C
+    tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
     check(lib.st_sgemm(int(transA), int(transB), M, N, K, float(alpha), C.c_void_p(A.data_ptr()),
                        max(A.stride(0), 1), C.c_void_p(B.data_ptr()), max(B.stride(0), 1), float(beta),
                        C.c_void_p(out.data_ptr()), max(out.stride(0), 1), ptr(bias), stream_ptr()),
           "st_sgemm")
+    if tok:
+        TIMER.end(tok)
     return out
 
 
@@ -78,7 +106,7 @@ def _barrier(device):
     return torch.zeros(64, dtype=I32, device=device)
 
 
-def rnn_seq_fwd(kind, Gx, Whh, bhh, bs, *, h0=None, c0=None, save=True, t_range=None, out=None):
+def rnn_seq_fwd(kind, Gx, Whh, bhh, bs, *, h0=None, c0=None, save=True, t_range=None, out=None, tag=None):
     """Returns dict(Hs, Cs, gates, ghn).  `out` lets a caller that runs single steps (attention
     models) keep writing into the same packed buffers."""
     lib = _lib.load()
@@ -92,14 +120,17 @@ def rnn_seq_fwd(kind, Gx, Whh, bhh, bs, *, h0=None, c0=None, save=True, t_range=
         o["ghn"] = torch.empty(N, H, dtype=F32, device=dev) if (save and kind == _lib.ST_GRU) else None
         o["barrier"] = _barrier(dev)
     t0, t1 = t_range if t_range is not None else (0, len(bs))
+    tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
     check(lib.st_rnn_seq_fwd(kind, H, len(bs), int_array(bs), t0, t1, ptr(Gx, F32), ptr(Whh, F32),
                              ptr(bhh, F32), ptr(h0, F32), ptr(c0, F32), ptr(o["Hs"], F32), ptr(o["Cs"]),
                              ptr(o["gates"]), ptr(o["ghn"]), ptr(o["barrier"], I32), stream_ptr()),
           "st_rnn_seq_fwd")
+    if tok:
+        TIMER.end(tok)
     return o
 
 
-def rnn_seq_bwd(kind, Whh, bs, saved, dHs, *, h0=None, c0=None, t_range=None, out=None):
+def rnn_seq_bwd(kind, Whh, bs, saved, dHs, *, h0=None, c0=None, t_range=None, out=None, tag=None):
     """Returns dict(dG, dGh, dstate).  dstate (2, B0, H): [0] = dh0, [1] = dc0 once t reaches 0."""
     lib = _lib.load()
     N, H, GH = sum(bs), Whh.shape[1], Whh.shape[0]
@@ -111,11 +142,14 @@ def rnn_seq_bwd(kind, Whh, bs, saved, dHs, *, h0=None, c0=None, t_range=None, ou
         o["dstate"] = torch.zeros(2, bs[0], H, dtype=F32, device=dev)
         o["barrier"] = _barrier(dev)
     t_hi, t_lo = t_range if t_range is not None else (len(bs), 0)
+    tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
     check(lib.st_rnn_seq_bwd(kind, H, len(bs), int_array(bs), t_hi, t_lo, ptr(Whh, F32), ptr(h0, F32),
                              ptr(c0, F32), ptr(saved["Hs"], F32), ptr(saved["Cs"]), ptr(saved["gates"], F32),
                              ptr(saved["ghn"]), ptr(dHs, F32), ptr(o["dG"], F32), ptr(o["dGh"], F32),
                              ptr(o["dstate"], F32), ptr(o["barrier"], I32), stream_ptr()),
           "st_rnn_seq_bwd")
+    if tok:
+        TIMER.end(tok)
     return o
 
 
