@@ -65,6 +65,41 @@ int st_sgemm(int transA, int transB, int M, int N, int K, float alpha, const flo
              st_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * bf16 GEMM on the tensor cores (tcgen05.mma, TMEM accumulators, TMA operand loads):
+ *   C[M,N] = alpha * A[M,K] . B[N,K]^T + bias[N]        A, B bf16 row-major, K contiguous
+ * C is fp32 (c_is_bf16 = 0) or bf16.  The bf16-mode replacement of the same nn.Linear call sites
+ * as st_sgemm.  A, B 16-byte aligned, lda/ldb multiples of 8; M, N, K arbitrary (TMA zero-fills
+ * the tails).
+ * ------------------------------------------------------------------------------------------ */
+int st_gemm_bf16(int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
+                 int c_is_bf16, const float* bias, float alpha, st_stream_t stream);
+
+/* fp32 (rows, cols) -> bf16 copy `dst` (rows, cols) and/or bf16 transpose `dstT` (cols, rows);
+ * either may be NULL.  Produces the K-major operands st_gemm_bf16 needs for dX = dY W and
+ * dW = dY^T X. */
+int st_cast_bf16(const float* src, int rows, int cols, int lds, void* dst, int ldd, void* dstT, int lddT,
+                 st_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Vocabulary projection fused with cross-entropy (rnn.py:33 + main.py:94,149), bf16 mode.
+ * Forward: logits = Hs Wv^T + bv are formed tile by tile in TMEM and reduced on the fly to a per-row
+ * (max, sum-exp) partial per 128-column tile; the (N,V) logits never reach HBM.
+ *   Hs (M, H) bf16, Wv (V, H) bf16, bv (V) fp32, target (M) int64
+ *   part_max / part_sum (M, st_vocab_ce_parts(V)) scratch; tlogit (M) scratch
+ *   lse (M) out; loss_sum (1) out = sum_m (lse_m - logit_m[target_m])
+ * Backward: recomputes each logits tile and writes dlogits = (softmax - onehot) * scale as bf16,
+ * row-major P (M, ldp) and transposed PT (V, ldpt) (PT may be NULL): the operands of
+ * dHs = P Wv and dWv = P^T Hs.
+ * ------------------------------------------------------------------------------------------ */
+int st_vocab_ce_parts(int V);
+int st_vocab_ce_fwd(int M, int V, int H, const void* Hs, int ldh, const void* Wv, int ldw, const float* bv,
+                    const int64_t* target, float* part_max, float* part_sum, float* tlogit, float* lse,
+                    float* loss_sum, st_stream_t stream);
+int st_vocab_ce_bwd(int M, int V, int H, const void* Hs, int ldh, const void* Wv, int ldw, const float* bv,
+                    const int64_t* target, const float* lse, float scale, void* P, int ldp, void* PT, int ldpt,
+                    st_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Input packing (rnn.py:29-31 Embedding + cat + pack_padded_sequence; rnn_attn.py:101 + :70).
  * X (N, ldx) row n=(t,b):  with_feature=1: t==0 ? feature[b] : emb[caption[b, t-1]]   (rnn.py:30)
  *                          with_feature=0: emb[caption[b, t]]                          (rnn_attn.py:70)

@@ -1,0 +1,510 @@
+// bf16 GEMM on the 5th-generation tensor cores: tcgen05.mma (UMMA) with the accumulator in TMEM,
+// operands staged in shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle), mbarrier
+// pipelines between the roles, persistent CTAs (one per SM) walking a static tile schedule.
+//
+//     D[M,N] = A[M,K] . B[N,K]^T          A, B bf16 row-major with K contiguous ("K-major")
+//
+// This is the nn.Linear shape (weights are (out, in)); the transposed products of the backward
+// pass are brought to the same form by the caller with transposed bf16 copies.
+//
+// CTA = 256 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane each), warp 2 =
+// TMEM allocator, warps 4..7 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31 = 32 rows of the
+// 128x128 tile).  6-stage smem ring (A 16 KB + B 16 KB per stage), 2 TMEM accumulator stages
+// (2 x 128 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Epilogues (template parameter):
+//   EPI_STORE   C = alpha*acc + bias[n]  as fp32 or bf16                     (W_ih / att1 hoists, dX, dW)
+//   EPI_CE_FWD  per-row online (max, sum-exp) over this tile's 128 vocabulary columns + the
+//               target logit: the (N,V) logits are never written              (rnn.py:33 + main.py:149)
+//   EPI_CE_BWD  recomputes the logits tile and writes dlogits = (softmax - onehot)*scale as bf16,
+//               row-major and transposed, the operands of the two backward GEMMs
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace st {
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, UK = 16;
+constexpr int STAGES = 6, ACC_STAGES = 2, NTHREADS = 256;
+constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;
+constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256;
+
+enum { EPI_STORE = 0, EPI_CE_FWD = 1, EPI_CE_BWD = 2 };
+
+struct TcParams {
+  int M, N, K;
+  // EPI_STORE
+  void* C;
+  int ldc, c_bf16;
+  const float* bias;  // [N] or null (all epilogues)
+  float alpha;
+  // CE
+  const int64_t* target;  // [M]
+  float *pmax, *psum, *tlogit;  // fwd: (M, npart) partials, (M) target logit
+  int npart;
+  const float* lse;  // bwd: [M]
+  float scale;
+  __nv_bfloat16 *P, *PT;  // bwd: (M, ldp) and (N, ldpt)
+  int ldp, ldpt;
+};
+
+// ---------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded spin: a pipeline bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, kind::f16 (bf16 in, fp32 accumulate)
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets lane (base_lane + t).
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows of 128 B (64 bf16), 8-row
+// swizzle atoms 1024 B apart (SBO); LBO unused for swizzled K-major; version 1 (Blackwell).
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                    // leading byte offset (ignored), 16 B
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                    // descriptor version
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor: D fp32, A/B bf16, both K-major, M x N tile.
+__host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = (p.M + BM - 1) / BM, nt = (p.N + BN - 1) / BN;
+  const int ntiles = mt * nt, kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < ACC_STAGES; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------------------------------------------------- TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = (tile % mt) * BM, n0 = (tile / mt) * BN;
+        for (int k = 0; k < kb; ++k) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          uint8_t* a = smem + (size_t)stage * STAGE_BYTES;
+          tma_load_2d(a, &tmA, k * BK, m0, &full[stage]);
+          tma_load_2d(a + A_BYTES, &tmB, k * BK, n0, &full[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc = umma_idesc(BM, BN);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int k = 0; k < kb; ++k) {
+          mbar_wait(&full[stage], phase);  // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / UK; ++kk)
+            tc_mma(d_tmem, umma_desc_k128(a_addr + kk * UK * 2), umma_desc_k128(b_addr + kk * UK * 2), idesc,
+                   (k | kk) != 0);
+          tc_commit(&empty[stage]);  // smem slot free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull[acc]);  // accumulator complete
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {  // ------------------------------------------------------ epilogue
+    const int ew = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int m0 = (tile % mt) * BM, n0 = (tile / mt) * BN;
+      const int row = m0 + ew * 32 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16);
+
+      float run_m = -FLT_MAX, run_s = 0.f, tl = 0.f;  // EPI_CE_FWD
+      bool have_tl = false;
+      int64_t tgt = -1;
+      float lse_r = 0.f;
+      if (EPI != EPI_STORE && row_ok) tgt = p.target[row];
+      if (EPI == EPI_CE_BWD && row_ok) lse_r = p.lse[row];
+
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(tbase + c * 32, v);
+        const int nb = n0 + c * 32;
+        if (EPI == EPI_STORE) {
+          if (row_ok) {
+            if (p.c_bf16) {
+              __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + nb;
+              if (nb + 32 <= p.N && (p.ldc & 7) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint32_t w[4];
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    float x0 = p.alpha * v[j + 2 * q] + (p.bias ? p.bias[nb + j + 2 * q] : 0.f);
+                    float x1 = p.alpha * v[j + 2 * q + 1] + (p.bias ? p.bias[nb + j + 2 * q + 1] : 0.f);
+                    __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                    w[q] = *reinterpret_cast<uint32_t*>(&h);
+                  }
+                  *reinterpret_cast<uint4*>(out + j) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (nb + j < p.N)
+                    out[j] = __float2bfloat16(p.alpha * v[j] + (p.bias ? p.bias[nb + j] : 0.f));
+              }
+            } else {
+              float* out = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + nb;
+              if (nb + 32 <= p.N && (p.ldc & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float4 o;
+                  o.x = p.alpha * v[j] + (p.bias ? p.bias[nb + j] : 0.f);
+                  o.y = p.alpha * v[j + 1] + (p.bias ? p.bias[nb + j + 1] : 0.f);
+                  o.z = p.alpha * v[j + 2] + (p.bias ? p.bias[nb + j + 2] : 0.f);
+                  o.w = p.alpha * v[j + 3] + (p.bias ? p.bias[nb + j + 3] : 0.f);
+                  *reinterpret_cast<float4*>(out + j) = o;
+                }
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (nb + j < p.N) out[j] = p.alpha * v[j] + (p.bias ? p.bias[nb + j] : 0.f);
+              }
+            }
+          }
+        } else if (EPI == EPI_CE_FWD) {
+          float cm = -FLT_MAX;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = nb + j;
+            v[j] = (n < p.N) ? v[j] + (p.bias ? p.bias[n] : 0.f) : -FLT_MAX;
+            cm = fmaxf(cm, v[j]);
+            if (n == tgt) { tl = v[j]; have_tl = true; }
+          }
+          const float nm = fmaxf(run_m, cm);
+          float s = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s += (nb + j < p.N) ? __expf(v[j] - nm) : 0.f;
+          run_s = run_s * __expf(run_m - nm) + s;
+          run_m = nm;
+        } else {  // EPI_CE_BWD
+          float d[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = nb + j;
+            const float logit = v[j] + ((p.bias && n < p.N) ? p.bias[n] : 0.f);
+            d[j] = (n < p.N && row_ok) ? (__expf(logit - lse_r) - (n == tgt ? 1.f : 0.f)) * p.scale : 0.f;
+          }
+          if (row_ok) {
+            __nv_bfloat16* out = p.P + (size_t)row * p.ldp + nb;
+            if (nb + 32 <= p.N && (p.ldp & 7) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint32_t w[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  __nv_bfloat162 h = __floats2bfloat162_rn(d[j + 2 * q], d[j + 2 * q + 1]);
+                  w[q] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                *reinterpret_cast<uint4*>(out + j) = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) out[j] = __float2bfloat16(d[j]);
+            }
+            if (p.PT) {  // transposed copy: lanes are consecutive rows -> 64 B contiguous per column
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nb + j < p.N) p.PT[(size_t)(nb + j) * p.ldpt + row] = __float2bfloat16(d[j]);
+            }
+          }
+        }
+      }
+      if (EPI == EPI_CE_FWD && row_ok) {
+        const int part = tile / mt;
+        p.pmax[(size_t)row * p.npart + part] = run_m;
+        p.psum[(size_t)row * p.npart + part] = run_s;
+        if (have_tl) p.tlogit[row] = tl;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// lse[m] = log sum_v exp(logit) from the per-tile partials; loss_sum += lse - target logit.
+__global__ void ce_combine_kernel(int M, int npart, const float* __restrict__ pmax, const float* __restrict__ psum,
+                                  const float* __restrict__ tlogit, float* __restrict__ lse,
+                                  float* __restrict__ loss_sum) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  float contrib = 0.f;
+  if (m < M) {
+    float mx = -FLT_MAX;
+    for (int j = 0; j < npart; ++j) mx = fmaxf(mx, pmax[(size_t)m * npart + j]);
+    float s = 0.f;
+    for (int j = 0; j < npart; ++j) s += psum[(size_t)m * npart + j] * expf(pmax[(size_t)m * npart + j] - mx);
+    const float l = mx + logf(s);
+    lse[m] = l;
+    contrib = l - tlogit[m];
+  }
+  contrib = warp_sum(contrib);
+  if ((threadIdx.x & 31) == 0) atomicAdd(loss_sum, contrib);
+}
+
+// fp32 (rows, cols) -> bf16 copy and/or bf16 transpose (cols, rows).  32x32 tiles through smem.
+__global__ void cast_bf16_kernel(const float* __restrict__ src, int rows, int cols, int lds,
+                                 __nv_bfloat16* __restrict__ dst, int ldd, __nv_bfloat16* __restrict__ dstT,
+                                 int lddT) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    float v = (r < rows && c < cols) ? src[(size_t)r * lds + c] : 0.f;
+    tile[i][threadIdx.x] = v;
+    if (dst && r < rows && c < cols) dst[(size_t)r * ldd + c] = __float2bfloat16(v);
+  }
+  if (!dstT) return;
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) dstT[(size_t)c * lddT + r] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode(EncodeFn* out) {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    ST_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q));
+    ST_REQUIRE(sym != nullptr && q == cudaDriverEntryPointSuccess, ST_ERR_CUDA,
+               "cuTensorMapEncodeTiled not available from the driver");
+    fn = reinterpret_cast<EncodeFn>(sym);
+  }
+  *out = fn;
+  return ST_OK;
+}
+
+// Row-major bf16 matrix (rows, cols), ld elements; box = 64 columns (128 B) x box_rows, SW128.
+int make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, const char* what) {
+  ST_REQUIRE(ptr != nullptr, ST_ERR_NULL, "gemm_bf16: %s is NULL", what);
+  ST_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 8 == 0 && ld >= cols, ST_ERR_BAD_SHAPE,
+             "gemm_bf16: %s must be 16-byte aligned with a leading dimension that is a multiple of 8 "
+             "(ld=%d cols=%d)", what, ld, cols);
+  EncodeFn enc;
+  ST_TRY(get_encode(&enc));
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ST_REQUIRE(r == CUDA_SUCCESS, ST_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return ST_OK;
+}
+
+template <int EPI>
+int launch_tc(const TcParams& p, const void* A, int lda, const void* B, int ldb, cudaStream_t s) {
+  ST_REQUIRE(p.M >= 1 && p.N >= 1 && p.K >= 1, ST_ERR_BAD_SHAPE, "gemm_bf16: M=%d N=%d K=%d", p.M, p.N, p.K);
+  CUtensorMap tmA, tmB;
+  ST_TRY(make_tmap(&tmA, A, p.M, p.K, lda, BM, "A"));
+  ST_TRY(make_tmap(&tmB, B, p.N, p.K, ldb, BN, "B"));
+  auto kern = gemm_tc_kernel<EPI>;
+  ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  int sms = 0;
+  ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
+  const int ntiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  const int grid = ntiles < sms ? ntiles : sms;
+  kern<<<grid, NTHREADS, SMEM_BYTES, s>>>(tmA, tmB, p);
+  ST_LAUNCH_TRY("gemm_tc_kernel");
+  return ST_OK;
+}
+
+}  // namespace
+}  // namespace st
+
+extern "C" {
+
+int st_gemm_bf16(int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
+                 int c_is_bf16, const float* bias, float alpha, st_stream_t stream) {
+  using namespace st;
+  ST_REQUIRE(C != nullptr, ST_ERR_NULL, "st_gemm_bf16: C is NULL");
+  ST_REQUIRE(ldc >= N, ST_ERR_BAD_SHAPE, "st_gemm_bf16: ldc=%d < N=%d", ldc, N);
+  TcParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.C = C; p.ldc = ldc; p.c_bf16 = c_is_bf16; p.bias = bias; p.alpha = alpha;
+  return launch_tc<EPI_STORE>(p, A, lda, B, ldb, as_stream(stream));
+}
+
+int st_vocab_ce_fwd(int M, int V, int H, const void* Hs, int ldh, const void* Wv, int ldw, const float* bv,
+                    const int64_t* target, float* part_max, float* part_sum, float* tlogit, float* lse,
+                    float* loss_sum, st_stream_t stream) {
+  using namespace st;
+  ST_REQUIRE(target && part_max && part_sum && tlogit && lse && loss_sum, ST_ERR_NULL, "st_vocab_ce_fwd: NULL pointer");
+  cudaStream_t s = as_stream(stream);
+  TcParams p{};
+  p.M = M; p.N = V; p.K = H;
+  p.bias = bv; p.target = target; p.pmax = part_max; p.psum = part_sum; p.tlogit = tlogit;
+  p.npart = (V + BN - 1) / BN;
+  ST_CUDA_TRY(cudaMemsetAsync(loss_sum, 0, sizeof(float), s));
+  ST_TRY(launch_tc<EPI_CE_FWD>(p, Hs, ldh, Wv, ldw, s));
+  ce_combine_kernel<<<(M + 127) / 128, 128, 0, s>>>(M, p.npart, part_max, part_sum, tlogit, lse, loss_sum);
+  ST_LAUNCH_TRY("ce_combine_kernel");
+  return ST_OK;
+}
+
+int st_vocab_ce_parts(int V) { return (V + st::BN - 1) / st::BN; }
+
+int st_vocab_ce_bwd(int M, int V, int H, const void* Hs, int ldh, const void* Wv, int ldw, const float* bv,
+                    const int64_t* target, const float* lse, float scale, void* P, int ldp, void* PT, int ldpt,
+                    st_stream_t stream) {
+  using namespace st;
+  ST_REQUIRE(target && lse && P, ST_ERR_NULL, "st_vocab_ce_bwd: NULL pointer");
+  ST_REQUIRE(ldp >= V && (!PT || ldpt >= M), ST_ERR_BAD_SHAPE, "st_vocab_ce_bwd: ldp=%d ldpt=%d", ldp, ldpt);
+  TcParams p{};
+  p.M = M; p.N = V; p.K = H;
+  p.bias = bv; p.target = target; p.lse = lse; p.scale = scale;
+  p.P = reinterpret_cast<__nv_bfloat16*>(P); p.ldp = ldp;
+  p.PT = reinterpret_cast<__nv_bfloat16*>(PT); p.ldpt = ldpt;
+  return launch_tc<EPI_CE_BWD>(p, Hs, ldh, Wv, ldw, as_stream(stream));
+}
+
+int st_cast_bf16(const float* src, int rows, int cols, int lds, void* dst, int ldd, void* dstT, int lddT,
+                 st_stream_t stream) {
+  using namespace st;
+  ST_REQUIRE(src && (dst || dstT), ST_ERR_NULL, "st_cast_bf16: NULL pointer");
+  ST_REQUIRE(rows >= 1 && cols >= 1 && lds >= cols && (!dst || ldd >= cols) && (!dstT || lddT >= rows),
+             ST_ERR_BAD_SHAPE, "st_cast_bf16: rows=%d cols=%d lds=%d ldd=%d lddT=%d", rows, cols, lds, ldd, lddT);
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  ST_REQUIRE(grid.y <= 65535, ST_ERR_BAD_SHAPE, "st_cast_bf16: too many rows");
+  cast_bf16_kernel<<<grid, block, 0, as_stream(stream)>>>(src, rows, cols, lds,
+                                                          reinterpret_cast<__nv_bfloat16*>(dst), ldd,
+                                                          reinterpret_cast<__nv_bfloat16*>(dstT), lddT);
+  ST_LAUNCH_TRY("cast_bf16_kernel");
+  return ST_OK;
+}
+
+}  // extern "C"

@@ -191,3 +191,88 @@ def topk_rows(X, K):
     check(lib.st_topk_rows(ptr(X, F32), X.stride(0), X.shape[0], X.shape[1], K, ptr(val), ptr(idx), K,
                            stream_ptr()), "st_topk_rows")
     return val, idx
+
+
+# ----------------------------------------------------------------------------- bf16 / tensor cores
+BF16 = torch.bfloat16
+
+
+def _raw(t):
+    import ctypes as C
+    return C.c_void_p(t.data_ptr())
+
+
+def gemm_bf16(A, B, *, bias=None, out_dtype=F32, alpha=1.0, out=None, tag=None):
+    """out[M,N] = alpha * A[M,K] . B[N,K]^T + bias on tcgen05 tensor cores.  A, B bf16 with unit inner
+    stride and row strides that are multiples of 8."""
+    lib = _lib.load()
+    for t in (A, B):
+        if t.dim() != 2 or t.dtype != BF16 or t.stride(1) != 1 or not t.is_cuda:
+            raise ValueError("gemm_bf16 operands must be 2-D bf16 CUDA tensors with unit inner stride")
+    M, K = A.shape
+    N, Kb = B.shape
+    if K != Kb:
+        raise ValueError(f"gemm_bf16: inner dimensions differ ({K} vs {Kb})")
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=A.device)
+    tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
+    check(lib.st_gemm_bf16(M, N, K, _raw(A), A.stride(0), _raw(B), B.stride(0), _raw(out), out.stride(0),
+                           int(out.dtype == BF16), ptr(bias, F32), float(alpha), stream_ptr()), "st_gemm_bf16")
+    if tok:
+        TIMER.end(tok)
+    return out
+
+
+def cast_bf16(src, want=True, want_t=False):
+    """fp32 (R,C) -> (bf16 (R,C) or None, bf16 transpose (C,R) or None).  Leading dimensions are
+    padded to multiples of 8 so the results are valid TMA operands; the returned tensors are the
+    un-padded views."""
+    lib = _lib.load()
+    R, Cc = src.shape
+    pad = lambda n: (n + 7) // 8 * 8
+    d = torch.empty(R, pad(Cc), dtype=BF16, device=src.device)[:, :Cc] if want else None
+    dT = torch.empty(Cc, pad(R), dtype=BF16, device=src.device)[:, :R] if want_t else None
+    check(lib.st_cast_bf16(_raw(src), R, Cc, src.stride(0), _raw(d) if want else None,
+                           d.stride(0) if want else 0, _raw(dT) if want_t else None,
+                           dT.stride(0) if want_t else 0, stream_ptr()), "st_cast_bf16")
+    return d, dT
+
+
+def vocab_ce_fwd(Hs, Wv, bv, target, tag=None):
+    """Fused vocabulary projection + cross-entropy forward.  Returns (loss_sum (1,), lse (M,))."""
+    lib = _lib.load()
+    M, H = Hs.shape
+    V = Wv.shape[0]
+    dev = Hs.device
+    parts = lib.st_vocab_ce_parts(V)
+    pm = torch.empty(M, parts, dtype=F32, device=dev)
+    ps = torch.empty(M, parts, dtype=F32, device=dev)
+    tl = torch.empty(M, dtype=F32, device=dev)
+    lse = torch.empty(M, dtype=F32, device=dev)
+    loss = torch.empty(1, dtype=F32, device=dev)
+    tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
+    check(lib.st_vocab_ce_fwd(M, V, H, _raw(Hs), Hs.stride(0), _raw(Wv), Wv.stride(0), ptr(bv, F32),
+                              ptr(target, I64), ptr(pm), ptr(ps), ptr(tl), ptr(lse), ptr(loss), stream_ptr()),
+          "st_vocab_ce_fwd")
+    if tok:
+        TIMER.end(tok)
+    return loss, lse
+
+
+def vocab_ce_bwd(Hs, Wv, bv, target, lse, scale, want_t=True, tag=None):
+    """dlogits as bf16: P (M,V) and (optionally) its transpose PT (V,M)."""
+    lib = _lib.load()
+    M, H = Hs.shape
+    V = Wv.shape[0]
+    dev = Hs.device
+    pad = lambda n: (n + 7) // 8 * 8
+    P = torch.empty(M, pad(V), dtype=BF16, device=dev)[:, :V]
+    PT = torch.empty(V, pad(M), dtype=BF16, device=dev)[:, :M] if want_t else None
+    tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
+    check(lib.st_vocab_ce_bwd(M, V, H, _raw(Hs), Hs.stride(0), _raw(Wv), Wv.stride(0), ptr(bv, F32),
+                              ptr(target, I64), ptr(lse, F32), float(scale), _raw(P), P.stride(0),
+                              _raw(PT) if want_t else None, PT.stride(0) if want_t else 0, stream_ptr()),
+          "st_vocab_ce_bwd")
+    if tok:
+        TIMER.end(tok)
+    return P, PT

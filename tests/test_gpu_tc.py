@@ -1,0 +1,59 @@
+"""GPU: tcgen05/TMEM/TMA GEMM and its fused cross-entropy epilogues against torch float64 on the
+same bf16-rounded operands (so the only difference is fp32 accumulation order)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import rel_err
+
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 512), (256, 384, 128), (5120, 2048, 512),
+                                   (100, 50, 40), (129, 257, 72), (640, 10000, 512), (37, 1000, 2048)])
+def test_gemm_bf16(M, N, K):
+    from showtell_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    Kp = (K + 7) // 8 * 8
+    A = torch.randn(M, Kp, generator=g).to(DEV).bfloat16()[:, :K]
+    B = torch.randn(N, Kp, generator=g).to(DEV).bfloat16()[:, :K]
+    bias = torch.randn(N, generator=g).to(DEV)
+    ref = A.double() @ B.double().t()
+    out = ops.gemm_bf16(A, B)
+    assert out.dtype == torch.float32 and rel_err(out, ref) < 1e-5
+    out2 = ops.gemm_bf16(A, B, bias=bias, alpha=0.5)
+    assert rel_err(out2, 0.5 * ref + bias.double()) < 1e-5
+    out3 = ops.gemm_bf16(A, B, bias=bias, out_dtype=torch.bfloat16)
+    assert out3.dtype == torch.bfloat16 and rel_err(out3, ref + bias.double()) < 1e-2
+
+
+def test_cast_bf16():
+    from showtell_b200 import ops
+    x = torch.randn(70, 45, device=DEV)
+    d, dT = ops.cast_bf16(x, True, True)
+    assert torch.equal(d, x.bfloat16()) and torch.equal(dT, x.bfloat16().t())
+    assert d.stride(0) % 8 == 0 and dT.stride(0) % 8 == 0
+
+
+@pytest.mark.parametrize("M,V,H", [(64, 128, 64), (300, 1000, 128), (640, 10000, 512), (5120, 10000, 512)])
+def test_vocab_ce_fused(M, V, H):
+    from showtell_b200 import ops
+    g = torch.Generator().manual_seed(M + V)
+    Hs = (torch.randn(M, H, generator=g) * 0.5).to(DEV).bfloat16()
+    Wv = (torch.randn(V, H, generator=g) * 0.1).to(DEV).bfloat16()
+    bv = (torch.randn(V, generator=g) * 0.1).to(DEV)
+    tgt = torch.randint(0, V, (M,), generator=g).to(DEV)
+    logits = (Hs.double() @ Wv.double().t() + bv.double()).requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(logits, tgt, reduction="sum")
+    ref.backward()
+    loss, lse = ops.vocab_ce_fwd(Hs, Wv, bv, tgt)
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+    assert rel_err(lse, torch.logsumexp(logits.detach(), 1)) < 1e-5
+    scale = 1.0 / M
+    P, PT = ops.vocab_ce_bwd(Hs, Wv, bv, tgt, lse, scale)
+    dref = logits.grad * scale
+    assert rel_err(P, dref) < 1e-2                     # bf16 storage of dlogits
+    assert torch.equal(PT, P.t())
+    # fp32-level check of the recompute: row sums of dlogits vanish
+    assert float(P.float().sum(1).abs().max()) < 2e-2 * scale
