@@ -176,7 +176,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     lib = _lib.load()
-    dtype = args.dtype or "fp32"
+    dtype = args.dtype or "bf16"
     torch.manual_seed(1)
     model = (GruRNN if kind == "gru" else LstmRNN)(E, H, V, 1, dtype=dtype).to(dev)
     params = [p for p in model.parameters()]
@@ -260,10 +260,10 @@ def main():
         # dominant kernel: the vocabulary-projection GEMMs (fwd logits, dW, dH: 3 x 2*N*H*V FLOPs)
         n_tok = B * T
         vocab_flops = 2.0 * n_tok * H * V
-        tags = [t for t in ("vocab_fwd", "vocab_dw", "vocab_dh") if t in ksum]
+        tags = [t for t in ("vocab_fwd", "vocab_dlogits", "vocab_dw", "vocab_dx") if t in ksum]
         vocab_ms = sum(ksum[t][1] for t in tags) / max(len(tags), 1)
         ach = vocab_flops / (vocab_ms * 1e-3) / 1e12 if tags else None
-        roof = {"bound": "tensor", "kernel": "vocabulary projection GEMM (fwd / dW / dH, mean of the three)",
+        roof = {"bound": "tensor", "kernel": "vocabulary projection GEMMs (" + " / ".join(tags) + ", mean; each 2*N*H*V FLOPs)",
                 "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": (ach / pk["tf_sustained"]) if ach else None, "traffic": None,
                 "peak_source": pk["src"] + " (bf16 cuBLAS sustained)",

@@ -117,8 +117,8 @@ int st_pack_inputs_bwd(const float* dX, int ldx, float* dEmb, int E, float* dfea
 int st_pack_targets(int64_t* out, const int64_t* caption, int T_cap, int nsteps,
                     const int* batch_sizes_host, st_stream_t stream);
 
-/* out[c] (+)= sum_r M[r, c]  -- bias gradients.  accumulate=0 overwrites. */
-int st_colsum(float* out, const float* M, int rows, int cols, int ld, int accumulate,
+/* out[c] (+)= sum_r M[r, c]  -- bias gradients.  M fp32 or bf16; accumulate=0 overwrites. */
+int st_colsum(float* out, const void* M, int m_is_bf16, int rows, int cols, int ld, int accumulate,
               st_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -43,7 +43,7 @@ _SIGS = {
     "st_pack_inputs": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _IP, _P]),
     "st_pack_inputs_bwd": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _IP, _P]),
     "st_pack_targets": (_I, [_P, _P, _I, _I, _IP, _P]),
-    "st_colsum": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "st_colsum": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "st_rnn_seq_fwd": (_I, [_I, _I, _I, _IP, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "st_rnn_seq_bwd": (_I, [_I, _I, _I, _IP, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "st_shift_states": (_I, [_P, _P, _P, _I, _I, _IP, _P]),

@@ -3,6 +3,8 @@
 //   rnn_attn.py:70  caption_embedding[:b_t, t]                         -> st_pack_inputs(with_feature=0)
 //   main.py:145     pack_padded_sequence(caption)[0]                   -> st_pack_targets
 //   autograd of nn.Embedding / torch.cat                               -> st_pack_inputs_bwd
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace st {
@@ -66,8 +68,12 @@ __global__ void pack_targets_kernel(const __grid_constant__ StepTable tab, int64
   out[n] = caption[(size_t)b * T_cap + t];
 }
 
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+
 // out[c] (+)= sum_r M[r,c].  CTA = 32 columns x 8 row-stripes over a 256-row slab.
-__global__ void colsum_kernel(float* __restrict__ out, const float* __restrict__ M, int rows, int cols,
+template <typename T>
+__global__ void colsum_kernel(float* __restrict__ out, const T* __restrict__ M, int rows, int cols,
                               int ld) {
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -75,7 +81,7 @@ __global__ void colsum_kernel(float* __restrict__ out, const float* __restrict__
   float s = 0.f;
   if (c < cols) {
     const int r1 = min(rows, r0 + 256);
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) s += M[(size_t)r * ld + c];
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) s += to_f32(M[(size_t)r * ld + c]);
   }
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
@@ -150,7 +156,7 @@ int st_pack_targets(int64_t* out, const int64_t* caption, int T_cap, int nsteps,
   return ST_OK;
 }
 
-int st_colsum(float* out, const float* M, int rows, int cols, int ld, int accumulate,
+int st_colsum(float* out, const void* M, int m_is_bf16, int rows, int cols, int ld, int accumulate,
               st_stream_t stream) {
   using namespace st;
   ST_REQUIRE(out && M, ST_ERR_NULL, "st_colsum: NULL pointer");
@@ -161,7 +167,10 @@ int st_colsum(float* out, const float* M, int rows, int cols, int ld, int accumu
   if (rows == 0) return ST_OK;
   dim3 grid((cols + 31) / 32, (rows + 255) / 256), block(32, 8);
   ST_REQUIRE(grid.y <= 65535, ST_ERR_BAD_SHAPE, "st_colsum: too many rows (%d)", rows);
-  colsum_kernel<<<grid, block, 0, s>>>(out, M, rows, cols, ld);
+  if (m_is_bf16)
+    colsum_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(out, reinterpret_cast<const __nv_bfloat16*>(M), rows, cols, ld);
+  else
+    colsum_kernel<float><<<grid, block, 0, s>>>(out, reinterpret_cast<const float*>(M), rows, cols, ld);
   ST_LAUNCH_TRY("colsum_kernel");
   return ST_OK;
 }

@@ -2,7 +2,12 @@
 for RNN.forward / forward_loss / backward.  Mirrors the data flow of rnn.py:27-35 + main.py:145-151
 with the time-invariant input projection hoisted out of the recurrence.
 
-fp32 mode: CUDA-core GEMMs (st_sgemm), persistent recurrent kernels, materialised logits.
+Two arithmetic modes (module ctor `dtype=`):
+  fp32  CUDA-core GEMMs (st_sgemm), materialised logits; parity bar 1e-4 relative.
+  bf16  tcgen05 tensor-core GEMMs on bf16 copies of fp32 master weights / activations with fp32
+        accumulation (st_gemm_bf16), vocabulary projection fused with cross-entropy so the (N,V)
+        logits never reach HBM (st_vocab_ce_fwd/bwd); parity bar 2e-2 relative.
+The recurrent kernels keep fp32 state in both modes.
 """
 import torch
 
@@ -11,65 +16,92 @@ from . import _lib, ops
 F32 = torch.float32
 
 
+class Linear:
+    """y = x W^T + b and its backward, in the arithmetic of `mode`.  Keeps the operand copies the
+    backward GEMMs need (bf16 mode: K-major bf16 transposes for dX = dY W and dW = dY^T X)."""
+
+    def __init__(self, mode, W, bias, need_bwd, tag):
+        self.mode, self.W, self.bias, self.need_bwd, self.tag = mode, W, bias, need_bwd, tag
+        if mode == "bf16":
+            self.Wb, self.WT = ops.cast_bf16(W, True, need_bwd)
+
+    def fwd(self, X):
+        if self.mode == "fp32":
+            self.X = X
+            return ops.sgemm(X, self.W, transB=True, bias=self.bias, tag=self.tag + "_fwd")
+        Xb, self.XT = ops.cast_bf16(X, True, self.need_bwd)
+        return ops.gemm_bf16(Xb, self.Wb, bias=self.bias, tag=self.tag + "_fwd")
+
+    def bwd(self, dY, need_dx=True):
+        """Returns (dX or None, dW, db)."""
+        db = ops.colsum(dY) if self.bias is not None else None
+        if self.mode == "fp32":
+            dW = ops.sgemm(dY, self.X, transA=True, tag=self.tag + "_dw")
+            dX = ops.sgemm(dY, self.W, tag=self.tag + "_dx") if need_dx else None
+            return dX, dW, db
+        dYb, dYT = ops.cast_bf16(dY, need_dx, True)
+        dW = ops.gemm_bf16(dYT, self.XT, tag=self.tag + "_dw")
+        dX = ops.gemm_bf16(dYb, self.WT, tag=self.tag + "_dx") if need_dx else None
+        return dX, dW, db
+
+
+def weight_grad(mode, dY, X, tag):
+    """dW = dY^T X for a product whose forward ran inside another kernel (W_hh)."""
+    if mode == "fp32":
+        return ops.sgemm(dY, X, transA=True, tag=tag)
+    _, dYT = ops.cast_bf16(dY, False, True)
+    _, XT = ops.cast_bf16(X, False, True)
+    return ops.gemm_bf16(dYT, XT, tag=tag)
+
+
 def layer_params(P, l):
     return (P[f"unit.weight_ih_l{l}"], P[f"unit.weight_hh_l{l}"],
             P[f"unit.bias_ih_l{l}"], P[f"unit.bias_hh_l{l}"])
 
 
-def stack_forward(P, kind, L, X, bs, save):
+def stack_forward(mode, P, kind, L, X, bs, save):
     """All L recurrent layers over the packed input X (N, in).  Layer l's input projection is one
     hoisted GEMM over every time step; the recurrence is one persistent kernel per layer.
     Returns (top-layer Hs (N,H), per-layer saved state)."""
     layers, inp = [], X
     for l in range(L):
         Wih, Whh, bih, bhh = layer_params(P, l)
-        Gx = ops.sgemm(inp, Wih, transB=True, bias=bih, tag="ih_fwd")      # W_ih x + b_ih, all steps
+        lin = Linear(mode, Wih, bih, save, "ih")
+        Gx = lin.fwd(inp)                                                  # W_ih x + b_ih, all steps
         o = ops.rnn_seq_fwd(kind, Gx, Whh, bhh, bs, save=save, tag="seq_fwd")
-        layers.append({"inp": inp, "out": o})
+        layers.append({"lin": lin, "out": o})
         inp = o["Hs"]
     return inp, layers
 
 
-def stack_backward(P, kind, L, bs, layers, dHs_top, grads):
+def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True):
     """BPTT through the L layers, top down.  Fills grads[...] for the unit.* parameters and returns
     the gradient w.r.t. the packed layer-0 input (N, in_0)."""
     dH = dHs_top
     for l in reversed(range(L)):
-        Wih, Whh, bih, bhh = layer_params(P, l)
+        _, Whh, _, _ = layer_params(P, l)
         sv = layers[l]
         b = ops.rnn_seq_bwd(kind, Whh, bs, sv["out"], dH, tag="seq_bwd")
         Hprev = ops.shift_states(sv["out"]["Hs"], bs)
-        grads[f"unit.weight_hh_l{l}"] = ops.sgemm(b["dGh"], Hprev, transA=True, tag="hh_dw")   # dGh^T Hprev
+        grads[f"unit.weight_hh_l{l}"] = weight_grad(mode, b["dGh"], Hprev, "hh_dw")  # dGh^T Hprev
         grads[f"unit.bias_hh_l{l}"] = ops.colsum(b["dGh"])
-        grads[f"unit.weight_ih_l{l}"] = ops.sgemm(b["dG"], sv["inp"], transA=True, tag="ih_dw")  # dG^T X
-        grads[f"unit.bias_ih_l{l}"] = ops.colsum(b["dG"])
-        dH = ops.sgemm(b["dG"], Wih, tag="ih_dx")                                     # dX = dG W_ih
+        dH, dW, db = sv["lin"].bwd(b["dG"], need_dx=(l > 0 or need_dx0))
+        grads[f"unit.weight_ih_l{l}"], grads[f"unit.bias_ih_l{l}"] = dW, db
     return dH
 
 
-def base_forward(P, kind, L, feature, caption, bs, save):
+def base_forward(mode, P, kind, L, feature, caption, bs, save):
     X = ops.pack_inputs(P["embeddings.weight"], feature, caption, bs, True)           # rnn.py:29-31
-    Hs, layers = stack_forward(P, kind, L, X, bs, save)
-    return Hs, layers
+    return stack_forward(mode, P, kind, L, X, bs, save)
 
 
-def vocab_logits(P, Hs):
-    return ops.sgemm(Hs, P["linear.weight"], transB=True, bias=P["linear.bias"], tag="vocab_fwd")  # rnn.py:33
-
-
-def base_backward(P, kind, L, caption, bs, layers, Hs_top, dlogits, want_dfeature, feature_shape):
-    """Gradients of everything given dlogits (N, V).  Returns (grads dict, dfeature or None)."""
-    grads = {}
-    Wv = P["linear.weight"]
-    grads["linear.weight"] = ops.sgemm(dlogits, Hs_top, transA=True, tag="vocab_dw")  # dlogits^T Hs
-    grads["linear.bias"] = ops.colsum(dlogits)
-    dHs = ops.sgemm(dlogits, Wv, tag="vocab_dh")                                      # dlogits W_v
-    dX = stack_backward(P, kind, L, bs, layers, dHs, grads)
+def base_backward_from_dHs(mode, P, kind, L, caption, bs, layers, dHs, grads, want_dfeature, feature_shape):
+    dX = stack_backward(mode, P, kind, L, bs, layers, dHs, grads)
     dEmb = torch.zeros_like(P["embeddings.weight"])
     dfeat = torch.empty(feature_shape, dtype=F32, device=dX.device) if want_dfeature else None
     ops.pack_inputs_bwd(dX, dEmb, dfeat, caption, bs, True)
     grads["embeddings.weight"] = dEmb
-    return grads, dfeat
+    return dfeat
 
 
 def _check_inputs(feature, caption, lengths, E):
@@ -95,55 +127,83 @@ class BaseLogitsFn(torch.autograd.Function):
     def forward(ctx, mod, feature, caption, lengths, *params):
         names = [n for n, _ in mod.named_parameters()]
         P = {n: p.detach() for n, p in zip(names, params)}
+        mode = mod.compute_dtype
         feature_c = feature.detach().contiguous().to(F32)
         caption_c = caption.contiguous()
         bs = _check_inputs(feature_c, caption_c, lengths, mod.embed_dim)
         save = any(ctx.needs_input_grad)
-        Hs, layers = base_forward(P, mod._kind, mod.num_layers, feature_c, caption_c, bs, save)
-        logits = vocab_logits(P, Hs)
-        ctx.names, ctx.P, ctx.mod = names, P, mod
-        ctx.bs, ctx.layers, ctx.Hs, ctx.caption = bs, layers, Hs, caption_c
+        Hs, layers = base_forward(mode, P, mod._kind, mod.num_layers, feature_c, caption_c, bs, save)
+        vocab = Linear(mode, P["linear.weight"], P["linear.bias"], save, "vocab")
+        logits = vocab.fwd(Hs)                                                        # rnn.py:33
+        ctx.names, ctx.P, ctx.mod, ctx.vocab = names, P, mod, vocab
+        ctx.bs, ctx.layers, ctx.caption = bs, layers, caption_c
         ctx.feature_shape = feature_c.shape
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
-        mod = ctx.mod
+        mod, grads = ctx.mod, {}
         dlogits = dlogits.contiguous().to(F32)
-        grads, dfeat = base_backward(ctx.P, mod._kind, mod.num_layers, ctx.caption, ctx.bs, ctx.layers,
-                                     ctx.Hs, dlogits, ctx.needs_input_grad[1], ctx.feature_shape)
+        dHs, grads["linear.weight"], grads["linear.bias"] = ctx.vocab.bwd(dlogits)
+        dfeat = base_backward_from_dHs(mod.compute_dtype, ctx.P, mod._kind, mod.num_layers, ctx.caption, ctx.bs,
+                                       ctx.layers, dHs, grads, ctx.needs_input_grad[1], ctx.feature_shape)
         return (None, dfeat, None, None) + tuple(grads[n] for n in ctx.names)
+
+
+def vocab_ce(mode, P, Hs, target, denom, need):
+    """Mean cross-entropy of the vocabulary projection of Hs (N,H) and, if `need`, its gradients.
+    Returns (loss (0-d), dHs or None, grads dict)."""
+    Wv, bv = P["linear.weight"], P["linear.bias"]
+    grads = {}
+    if mode == "fp32":
+        logits = ops.sgemm(Hs, Wv, transB=True, bias=bv, tag="vocab_fwd")             # rnn.py:33
+        loss_sum, _, dl = ops.ce_fwd_bwd(logits, target, grad_scale=(1.0 / denom) if need else None,
+                                         inplace=True)                                # main.py:149
+        dHs = None
+        if need:
+            grads["linear.weight"] = ops.sgemm(dl, Hs, transA=True, tag="vocab_dw")   # dlogits^T Hs
+            grads["linear.bias"] = ops.colsum(dl)
+            dHs = ops.sgemm(dl, Wv, tag="vocab_dx")                                   # dlogits W_v
+        return (loss_sum / denom).reshape(()), dHs, grads
+    Wb, WT = ops.cast_bf16(Wv, True, need)
+    Hb, HT = ops.cast_bf16(Hs, True, need)
+    loss_sum, lse = ops.vocab_ce_fwd(Hb, Wb, bv, target, tag="vocab_fwd")
+    dHs = None
+    if need:
+        Pm, PT = ops.vocab_ce_bwd(Hb, Wb, bv, target, lse, 1.0 / denom, tag="vocab_dlogits")
+        grads["linear.weight"] = ops.gemm_bf16(PT, HT, tag="vocab_dw")
+        grads["linear.bias"] = ops.colsum(Pm)
+        dHs = ops.gemm_bf16(Pm, WT, tag="vocab_dx")
+    return (loss_sum / denom).reshape(()), dHs, grads
 
 
 class BaseLossFn(torch.autograd.Function):
     """forward_loss: mean cross-entropy over the packed tokens (main.py:145,149), with forward and
-    backward run back to back so the (N, V) logits buffer is turned into its own gradient in place
-    and released before the call returns.  `denom` = number of tokens the mean runs over (the
+    backward run back to back (fp32 mode turns the logits buffer into its own gradient in place;
+    bf16 mode never materialises logits).  `denom` = number of tokens the mean runs over (the
     global token count under data parallelism)."""
 
     @staticmethod
     def forward(ctx, mod, feature, caption, lengths, denom, *params):
         names = [n for n, _ in mod.named_parameters()]
         P = {n: p.detach() for n, p in zip(names, params)}
+        mode = mod.compute_dtype
         feature_c = feature.detach().contiguous().to(F32)
         caption_c = caption.contiguous()
         bs = _check_inputs(feature_c, caption_c, lengths, mod.embed_dim)
         if len(bs) > caption_c.shape[1]:
             raise ValueError("caption_size exceeds the padded caption length")
         need = any(ctx.needs_input_grad)
-        N = sum(bs)
-        denom = float(denom if denom is not None else N)
-        Hs, layers = base_forward(P, mod._kind, mod.num_layers, feature_c, caption_c, bs, need)
-        logits = vocab_logits(P, Hs)
+        denom = float(denom if denom is not None else sum(bs))
+        Hs, layers = base_forward(mode, P, mod._kind, mod.num_layers, feature_c, caption_c, bs, need)
         target = ops.pack_targets(caption_c, bs)
-        loss_sum, _, dl = ops.ce_fwd_bwd(logits, target, grad_scale=(1.0 / denom) if need else None,
-                                         inplace=True)
-        ctx.names = names
-        ctx.grads, ctx.dfeat = None, None
+        loss, dHs, grads = vocab_ce(mode, P, Hs, target, denom, need)
+        ctx.names, ctx.grads, ctx.dfeat = names, None, None
         if need:
-            ctx.grads, ctx.dfeat = base_backward(P, mod._kind, mod.num_layers, caption_c, bs, layers, Hs, dl,
-                                                 ctx.needs_input_grad[1], feature_c.shape)
-        return (loss_sum / denom).reshape(())
+            ctx.dfeat = base_backward_from_dHs(mode, P, mod._kind, mod.num_layers, caption_c, bs, layers, dHs,
+                                               grads, ctx.needs_input_grad[1], feature_c.shape)
+            ctx.grads = grads
+        return loss
 
     @staticmethod
     def backward(ctx, g):

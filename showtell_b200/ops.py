@@ -97,8 +97,8 @@ def colsum(M, out=None, accumulate=False):
     if out is None:
         out = torch.empty(M.shape[1], dtype=F32, device=M.device)
     import ctypes as C
-    check(lib.st_colsum(ptr(out, F32), C.c_void_p(M.data_ptr()), M.shape[0], M.shape[1],
-                        max(M.stride(0), 1), int(accumulate), stream_ptr()), "st_colsum")
+    check(lib.st_colsum(ptr(out, F32), C.c_void_p(M.data_ptr()), int(M.dtype == torch.bfloat16), M.shape[0],
+                        M.shape[1], max(M.stride(0), 1), int(accumulate), stream_ptr()), "st_colsum")
     return out
 
 

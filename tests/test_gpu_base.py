@@ -136,14 +136,14 @@ def test_golden_beam_tree():
             assert abs(float(cost[i, j]) - float(t[f"row{i}.hyp{j}.cost"])) < 1e-4
 
 
-def _random_case(kind, E, H, V, L, B, T, seed, ragged):
+def _random_case(kind, E, H, V, L, B, T, seed, ragged, dtype="fp32"):
     torch.manual_seed(seed)
     g = torch.Generator().manual_seed(seed)
     if kind == "gru":
         from showtell_b200.rnn import RNN
     else:
         from showtell_b200.rnn_lstm import RNN
-    m = RNN(E, H, V, L)
+    m = RNN(E, H, V, L, dtype=dtype)
     lengths = sorted(torch.randint(max(2, T // 3), T + 1, (B,), generator=g).tolist(), reverse=True) \
         if ragged else [T] * B
     lengths[0] = T
@@ -163,8 +163,22 @@ def _random_case(kind, E, H, V, L, B, T, seed, ragged):
     ("lstm", 64, 128, 777, 2, 9, 5, True),
 ])
 def test_oracle_parity_train(kind, E, H, V, L, B, T, ragged):
+    _parity_train(kind, E, H, V, L, B, T, ragged, "fp32", TOL)
+
+
+@pytest.mark.parametrize("kind,E,H,V,L,B,T,ragged", [
+    ("lstm", 512, 512, 10000, 1, 64, 20, False),     # BASELINE config 2 shapes (smaller batch)
+    ("gru", 512, 512, 10000, 1, 32, 20, True),
+    ("lstm", 64, 128, 777, 2, 150, 7, True),         # odd vocabulary, two layers, two batch tiles
+])
+def test_oracle_parity_train_bf16(kind, E, H, V, L, B, T, ragged):
+    """bf16 mode (tensor-core GEMMs, fused vocabulary CE): north_star's 2e-2 relative bar."""
+    _parity_train(kind, E, H, V, L, B, T, ragged, "bf16", 2e-2)
+
+
+def _parity_train(kind, E, H, V, L, B, T, ragged, dtype, TOL):
     dev = torch.device("cuda:0")
-    m, feat, cap, lengths = _random_case(kind, E, H, V, L, B, T, 7, ragged)
+    m, feat, cap, lengths = _random_case(kind, E, H, V, L, B, T, 7, ragged, dtype)
     p = {k: v.detach().clone() for k, v in m.state_dict().items()}
     loss_ref, grads_ref, ex = O.train_step(p, kind, feat, cap, lengths)
     m = m.to(dev)
