@@ -46,6 +46,10 @@ _SIGS = {
     "st_colsum": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "st_rnn_seq_fwd": (_I, [_I, _I, _I, _IP, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "st_rnn_seq_bwd": (_I, [_I, _I, _I, _IP, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "st_rnn_seq_tc_supported": (_I, [_I, _I]),
+    "st_rnn_seq_tc_fwd": (_I, [_I, _I, _I, _IP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "st_rnn_seq_tc_bwd": (_I, [_I, _I, _I, _IP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P,
+                               _P, _P]),
     "st_shift_states": (_I, [_P, _P, _P, _I, _I, _IP, _P]),
     "st_ce_fwd_bwd": (_I, [_P, _I, _P, _I, _I, _P, _P, _P, _F, _P]),
     "st_argmax_rows": (_I, [_P, _I, _I, _I, _P, _I, _P]),

@@ -1,0 +1,45 @@
+// Host-side TMA tensor-map construction shared by the tensor-core kernels.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace st {
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode(EncodeFn* out) {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    ST_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q));
+    ST_REQUIRE(sym != nullptr && q == cudaDriverEntryPointSuccess, ST_ERR_CUDA,
+               "cuTensorMapEncodeTiled not available from the driver");
+    fn = reinterpret_cast<EncodeFn>(sym);
+  }
+  *out = fn;
+  return ST_OK;
+}
+
+// Row-major bf16 matrix (rows, cols), ld elements; box = 64 columns (128 B) x box_rows, SW128.
+int make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, const char* what) {
+  ST_REQUIRE(ptr != nullptr, ST_ERR_NULL, "gemm_bf16: %s is NULL", what);
+  ST_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 8 == 0 && ld >= cols, ST_ERR_BAD_SHAPE,
+             "gemm_bf16: %s must be 16-byte aligned with a leading dimension that is a multiple of 8 "
+             "(ld=%d cols=%d)", what, ld, cols);
+  EncodeFn enc;
+  ST_TRY(get_encode(&enc));
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ST_REQUIRE(r == CUDA_SUCCESS, ST_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return ST_OK;
+}
+
+
+}  // namespace st

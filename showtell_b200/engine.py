@@ -32,6 +32,12 @@ class Linear:
         Xb, self.XT = ops.cast_bf16(X, True, self.need_bwd)
         return ops.gemm_bf16(Xb, self.Wb, bias=self.bias, tag=self.tag + "_fwd")
 
+    def bwd_bf16(self, dYb, dYT, need_dx=True):
+        """Backward from gate gradients that already are bf16 GEMM operands (row-major + transposed)."""
+        dW = ops.gemm_bf16(dYT, self.XT, tag=self.tag + "_dw")
+        dX = ops.gemm_bf16(dYb, self.WT, tag=self.tag + "_dx") if need_dx else None
+        return dX, dW
+
     def bwd(self, dY, need_dx=True):
         """Returns (dX or None, dW, db)."""
         db = ops.colsum(dY) if self.bias is not None else None
@@ -68,8 +74,13 @@ def stack_forward(mode, P, kind, L, X, bs, save):
         Wih, Whh, bih, bhh = layer_params(P, l)
         lin = Linear(mode, Wih, bih, save, "ih")
         Gx = lin.fwd(inp)                                                  # W_ih x + b_ih, all steps
-        o = ops.rnn_seq_fwd(kind, Gx, Whh, bhh, bs, save=save, tag="seq_fwd")
-        layers.append({"lin": lin, "out": o})
+        o, WhhT = None, None
+        if mode == "bf16" and ops.rnn_seq_tc_supported(kind, Whh.shape[1]):
+            Whh_b, WhhT = ops.cast_bf16(Whh, True, save)
+            o = ops.rnn_seq_tc_fwd(kind, Gx, Whh_b, bhh, bs, save=save, tag="seq_fwd")
+        if o is None:                                                      # CUDA-core recurrent kernel
+            o, WhhT = ops.rnn_seq_fwd(kind, Gx, Whh, bhh, bs, save=save, tag="seq_fwd"), None
+        layers.append({"lin": lin, "out": o, "WhhT": WhhT})
         inp = o["Hs"]
     return inp, layers
 
@@ -81,8 +92,15 @@ def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True):
     for l in reversed(range(L)):
         _, Whh, _, _ = layer_params(P, l)
         sv = layers[l]
-        b = ops.rnn_seq_bwd(kind, Whh, bs, sv["out"], dH, tag="seq_bwd")
         Hprev = ops.shift_states(sv["out"]["Hs"], bs)
+        b = ops.rnn_seq_tc_bwd(kind, sv["WhhT"], bs, sv["out"], dH, tag="seq_bwd") if sv["WhhT"] is not None else None
+        if b is not None:                                                  # tensor-core BPTT: bf16 operands out
+            _, HprevT = ops.cast_bf16(Hprev, False, True)
+            grads[f"unit.weight_hh_l{l}"] = ops.gemm_bf16(b["dGhT"], HprevT, tag="hh_dw")
+            grads[f"unit.bias_hh_l{l}"], grads[f"unit.bias_ih_l{l}"] = b["dbhh"], b["dbih"]
+            dH, grads[f"unit.weight_ih_l{l}"] = sv["lin"].bwd_bf16(b["dGb"], b["dGT"], need_dx=(l > 0 or need_dx0))
+            continue
+        b = ops.rnn_seq_bwd(kind, Whh, bs, sv["out"], dH, tag="seq_bwd")
         grads[f"unit.weight_hh_l{l}"] = weight_grad(mode, b["dGh"], Hprev, "hh_dw")  # dGh^T Hprev
         grads[f"unit.bias_hh_l{l}"] = ops.colsum(b["dGh"])
         dH, dW, db = sv["lin"].bwd(b["dG"], need_dx=(l > 0 or need_dx0))

@@ -276,3 +276,55 @@ def vocab_ce_bwd(Hs, Wv, bv, target, lse, scale, want_t=True, tag=None):
     if tok:
         TIMER.end(tok)
     return P, PT
+
+
+def rnn_seq_tc_supported(kind, H):
+    return bool(_lib.load().st_rnn_seq_tc_supported(kind, H))
+
+
+def rnn_seq_tc_fwd(kind, Gx, Whh_b, bhh, bs, *, h0=None, h0_b=None, c0=None, save=True, tag=None):
+    """Tensor-core persistent recurrence.  Returns dict(Hs, Hsb, Cs, gates, ghn) or None when the
+    library reports the shape / grid as unsupported (caller falls back to rnn_seq_fwd)."""
+    lib = _lib.load()
+    N, H = sum(bs), Whh_b.shape[1]
+    dev = Gx.device
+    o = {"Hs": torch.empty(N, H, dtype=F32, device=dev), "Hsb": torch.empty(N, H, dtype=BF16, device=dev),
+         "Cs": torch.empty(N, H, dtype=F32, device=dev) if kind == _lib.ST_LSTM else None,
+         "gates": torch.empty(N, Whh_b.shape[0], dtype=F32, device=dev) if save else None,
+         "ghn": torch.empty(N, H, dtype=F32, device=dev) if (save and kind == _lib.ST_GRU) else None,
+         "barrier": _barrier(dev)}
+    tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
+    st = lib.st_rnn_seq_tc_fwd(kind, H, len(bs), int_array(bs), ptr(Gx, F32), ptr(Whh_b, BF16), ptr(bhh, F32),
+                               ptr(h0, F32), ptr(h0_b, BF16), ptr(c0, F32), ptr(o["Hs"]), ptr(o["Hsb"]),
+                               ptr(o["Cs"]), ptr(o["gates"]), ptr(o["ghn"]), ptr(o["barrier"]), stream_ptr())
+    if st == -3:
+        return None
+    check(st, "st_rnn_seq_tc_fwd")
+    if tok:
+        TIMER.end(tok)
+    return o
+
+
+def rnn_seq_tc_bwd(kind, WhhT_b, bs, saved, dHs, *, h0=None, c0=None, tag=None):
+    """Returns dict(dGb, dGT, dGhb, dGhT, dbih, dbhh, dstate) (bf16 GEMM operands) or None if unsupported."""
+    lib = _lib.load()
+    N, H, GH = sum(bs), WhhT_b.shape[0], WhhT_b.shape[1]
+    dev = dHs.device
+    ldt = (N + 7) // 8 * 8
+    mk = lambda: (torch.empty(N, GH, dtype=BF16, device=dev), torch.empty(GH, ldt, dtype=BF16, device=dev))
+    dGb, dGT = mk()
+    dGhb, dGhT = mk() if kind == _lib.ST_GRU else (dGb, dGT)
+    o = {"dGb": dGb, "dGT": dGT[:, :N], "dGhb": dGhb, "dGhT": dGhT[:, :N],
+         "dbih": torch.empty(GH, dtype=F32, device=dev), "dbhh": torch.empty(GH, dtype=F32, device=dev),
+         "dstate": torch.zeros(2, bs[0], H, dtype=F32, device=dev), "barrier": _barrier(dev)}
+    tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
+    st = lib.st_rnn_seq_tc_bwd(kind, H, len(bs), int_array(bs), ptr(WhhT_b, BF16), ptr(h0, F32), ptr(c0, F32),
+                               ptr(saved["Hs"], F32), ptr(saved["Cs"]), ptr(saved["gates"], F32),
+                               ptr(saved["ghn"]), ptr(dHs, F32), _raw(dGb), _raw(dGT), _raw(dGhb), _raw(dGhT), ldt,
+                               ptr(o["dbih"]), ptr(o["dbhh"]), ptr(o["dstate"]), ptr(o["barrier"]), stream_ptr())
+    if st == -3:
+        return None
+    check(st, "st_rnn_seq_tc_bwd")
+    if tok:
+        TIMER.end(tok)
+    return o

@@ -57,3 +57,48 @@ def test_vocab_ce_fused(M, V, H):
     assert torch.equal(PT, P.t())
     # fp32-level check of the recompute: row sums of dlogits vanish
     assert float(P.float().sum(1).abs().max()) < 2e-2 * scale
+
+
+@pytest.mark.parametrize("kind", ["gru", "lstm"])
+@pytest.mark.parametrize("H,lengths,init", [
+    (64, [5, 5, 4, 2], False),
+    (128, sorted([9, 9, 8, 6, 5, 3] * 30, reverse=True), True),    # 180 rows: two batch tiles, ragged
+    (512, [20] * 200 + [13] * 56, False),                          # config-2 shape
+])
+def test_rnn_seq_tensor_core_vs_cuda_core(kind, H, lengths, init):
+    """The tcgen05 persistent recurrence (bf16 operands, fp32 state) against the fp32 CUDA-core
+    kernels on the same bf16-rounded W_hh: forward states, gate gradients, dh0/dc0, bias grads."""
+    from showtell_b200 import _lib, ops
+    k = _lib.ST_LSTM if kind == "lstm" else _lib.ST_GRU
+    G = 4 if kind == "lstm" else 3
+    bs = _lib.batch_sizes(lengths)
+    N, B0 = sum(bs), bs[0]
+    g = torch.Generator().manual_seed(H)
+    s = 1.0 / H ** 0.5
+    Gx = torch.randn(N, G * H, generator=g).to(DEV)
+    Whh = ((torch.rand(G * H, H, generator=g) * 2 - 1) * s).to(DEV).bfloat16().float()
+    bhh = ((torch.rand(G * H, generator=g) * 2 - 1) * s).to(DEV)
+    h0 = (torch.randn(B0, H, generator=g) * 0.5).to(DEV).bfloat16().float() if init else None
+    c0 = (torch.randn(B0, H, generator=g) * 0.5).to(DEV) if (init and kind == "lstm") else None
+    dHs = torch.randn(N, H, generator=g).to(DEV)
+    ref = ops.rnn_seq_fwd(k, Gx, Whh, bhh, bs, h0=h0, c0=c0)
+    Wb, WT = ops.cast_bf16(Whh, True, True)
+    out = ops.rnn_seq_tc_fwd(k, Gx, Wb, bhh, bs, h0=h0, h0_b=None if h0 is None else h0.bfloat16(), c0=c0)
+    assert out is not None, "tensor-core recurrent kernel reported unsupported"
+    assert rel_err(out["Hs"], ref["Hs"]) < 1e-2
+    assert torch.equal(out["Hsb"], out["Hs"].bfloat16())
+    if kind == "lstm":
+        assert rel_err(out["Cs"], ref["Cs"]) < 1e-2
+    assert rel_err(out["gates"], ref["gates"]) < 1e-2
+    # backward on the tensor-core forward's own saved state
+    rb = ops.rnn_seq_bwd(k, Whh, bs, out, dHs, h0=h0, c0=c0)
+    tb = ops.rnn_seq_tc_bwd(k, WT, bs, out, dHs, h0=h0, c0=c0)
+    assert tb is not None
+    assert rel_err(tb["dGb"], rb["dG"]) < 2e-2
+    assert rel_err(tb["dGhb"], rb["dGh"]) < 2e-2
+    assert torch.equal(tb["dGT"], tb["dGb"].t()) and torch.equal(tb["dGhT"], tb["dGhb"].t())
+    assert rel_err(tb["dstate"][0], rb["dstate"][0]) < 2e-2
+    if kind == "lstm":
+        assert rel_err(tb["dstate"][1], rb["dstate"][1]) < 2e-2
+    assert rel_err(tb["dbih"], ops.colsum(rb["dG"])) < 2e-2
+    assert rel_err(tb["dbhh"], ops.colsum(rb["dGh"])) < 2e-2
