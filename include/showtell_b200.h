@@ -117,6 +117,10 @@ int st_pack_inputs_bwd(const float* dX, int ldx, float* dEmb, int E, float* dfea
 int st_pack_targets(int64_t* out, const int64_t* caption, int T_cap, int nsteps,
                     const int* batch_sizes_host, st_stream_t stream);
 
+/* dst[i, :width] = table[idx[i * idx_stride], :]  (nn.Embedding lookup of the decode loops, rnn.py:53). */
+int st_gather_rows(float* dst, int ld_dst, const float* table, int width, const int64_t* idx, int idx_stride,
+                   int n, st_stream_t stream);
+
 /* out[c] (+)= sum_r M[r, c]  -- bias gradients.  M fp32 or bf16; accumulate=0 overwrites. */
 int st_colsum(float* out, const void* M, int m_is_bf16, int rows, int cols, int ld, int accumulate,
               st_stream_t stream);
@@ -183,6 +187,45 @@ int st_rnn_seq_tc_bwd(int kind, int H, int nsteps, const int* batch_sizes_host, 
 /* Hprev (N,H): row (t,b) = h_{t-1}[b] (h0 or zeros at t=0) -- the B operand of dW_hh = dGh^T Hprev. */
 int st_shift_states(float* Hprev, const float* Hs, const float* h0, int H, int nsteps,
                     const int* batch_sizes_host, st_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Soft attention (Attention/rnn_attn.py:8-31 Attention_Net, :60-76 rnn_iterator).  The reference
+ * recomputes encoder_att(f) inside every step; here the state-independent parts are hoisted
+ * (att1 = F W_enc^T + b_enc and Fe = F W_embed^T, both one GEMM per iteration) and each step runs
+ * one fused kernel.  Storage type of F / att1 / Fe: fp32 (in_bf16 = 0) or bf16.
+ * act: 0 = LeakyReLU(0.2) (the reference, rnn_attn.py:18), 1 = tanh.
+ *
+ * st_attn_relayout: f (B,C,P) fp32 channels-first (cnn_attn.py:49) -> F (B*P, C), optional
+ *   FT (C, ldft >= B*P) (the K-major operand of dW_enc = datt1^T F), mean_f (B,C) (rnn_attn.py:62).
+ * st_attn_step_fwd, one CTA per live batch row b < rows:
+ *   e_p = w_f . act(att1[b,p,:] + att2[b,:]) + b_f;  alpha = softmax_P(e)            (rnn_attn.py:25-26)
+ *   ctx_out[b,:E] = sum_p alpha_p Fe[b,p,:] + b_embed   (= embed(sum_p alpha_p f_p), rnn_attn.py:29,70)
+ *   alphas[b*alpha_stride + p] = alpha_p (the caller points it at alphas[:, t, :]);  S[b,p] += alpha_p
+ * st_attn_step_bwd: dalpha_p = <dctx[b,:], Fe[b,p,:]> + dalpha[b*dalpha_stride + p] (may be NULL);
+ *   de = alpha * (dalpha - sum alpha dalpha) -> de_out (rows,P);  datt2 (rows,A) = sum_p de_p w_f act'(.)
+ * st_attn_hoist_bwd (after the loop; de (N,P), att2 (N,A) packed time-major):
+ *   datt1[b,p,a] = w_f[a] sum_t de[t,b,p] act'(att1[b,p,a] + att2[t,b,a]) (+ transposed copy),
+ *   dwf[a] = sum_{t,b,p} de act(.)
+ * st_attn_ctx_all: ctx[(t,b), c] = sum_p alphas[b,t,p] F[b,p,c] for all live (t,b) (for dW_embed).
+ * st_attn_penalty: pen_sum = sum (1 - S)^2, Gpen = -2 coef (1 - S)          (main_attn.py:131)
+ * st_add_rows: dst[r,:] += src[r,:] (attention query gradient into the carried dh rows).
+ * ------------------------------------------------------------------------------------------ */
+int st_attn_relayout(const float* f, int B, int C, int P, void* F, void* FT, int ldft, int out_bf16,
+                     float* mean_f, st_stream_t stream);
+int st_attn_step_fwd(int rows, int P, int A, int E, const void* att1, const void* Fe, int in_bf16,
+                     const float* att2, const float* wf, const float* bf, const float* b_embed, float* alphas,
+                     int alpha_stride, float* S, float* ctx_out, int ld_ctx, int act, st_stream_t stream);
+int st_attn_step_bwd(int rows, int P, int A, int E, const void* att1, const void* Fe, int in_bf16,
+                     const float* att2, const float* wf, const float* alphas, int alpha_stride,
+                     const float* dalpha, int dalpha_stride, const float* dctx, int ld_dctx, float* de_out,
+                     float* datt2, int act, st_stream_t stream);
+int st_attn_hoist_bwd(int nsteps, const int* batch_sizes_host, int P, int A, const void* att1, int in_bf16,
+                      const float* att2, const float* de, const float* wf, void* datt1, void* datt1T, int ldt,
+                      int out_bf16, float* dwf, int act, st_stream_t stream);
+int st_attn_ctx_all(int nsteps, const int* batch_sizes_host, int P, int C, int T_cap, const void* F, int in_bf16,
+                    const float* alphas, void* ctx, void* ctxT, int ldt, st_stream_t stream);
+int st_attn_penalty(int n, const float* S, float coef, float* pen_sum, float* Gpen, st_stream_t stream);
+int st_add_rows(float* dst, const float* src, int rows, int cols, st_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Cross-entropy over materialised logits (nn.CrossEntropyLoss(), main.py:94,149).

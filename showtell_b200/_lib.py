@@ -43,6 +43,7 @@ _SIGS = {
     "st_pack_inputs": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _IP, _P]),
     "st_pack_inputs_bwd": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _IP, _P]),
     "st_pack_targets": (_I, [_P, _P, _I, _I, _IP, _P]),
+    "st_gather_rows": (_I, [_P, _I, _P, _I, _P, _I, _I, _P]),
     "st_colsum": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "st_rnn_seq_fwd": (_I, [_I, _I, _I, _IP, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "st_rnn_seq_bwd": (_I, [_I, _I, _I, _IP, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -51,6 +52,13 @@ _SIGS = {
     "st_rnn_seq_tc_bwd": (_I, [_I, _I, _I, _IP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P,
                                _P, _P]),
     "st_shift_states": (_I, [_P, _P, _P, _I, _I, _IP, _P]),
+    "st_attn_relayout": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
+    "st_attn_step_fwd": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _P]),
+    "st_attn_step_bwd": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _I, _P]),
+    "st_attn_hoist_bwd": (_I, [_I, _IP, _I, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P]),
+    "st_attn_ctx_all": (_I, [_I, _IP, _I, _I, _I, _P, _I, _P, _P, _P, _I, _P]),
+    "st_attn_penalty": (_I, [_I, _P, _F, _P, _P, _P]),
+    "st_add_rows": (_I, [_P, _P, _I, _I, _P]),
     "st_ce_fwd_bwd": (_I, [_P, _I, _P, _I, _I, _P, _P, _P, _F, _P]),
     "st_argmax_rows": (_I, [_P, _I, _I, _I, _P, _I, _P]),
     "st_topk_rows": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _P]),

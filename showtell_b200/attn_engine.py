@@ -1,0 +1,255 @@
+"""Host-side orchestration of the attention decoders (Attention/rnn_attn.py, rnn_attn_LSTM.py +
+the loss of main_attn.py:126-131).
+
+Reference per step t (rnn_attn.py:66-74): attention over the full grid with a freshly recomputed
+encoder projection, embed(context), one GRU/LSTM step on [emb_t | embed(ctx)], vocabulary
+projection.  Here (see csrc/attn.cu): the encoder projection att1 and the embedded grid Fe are
+hoisted GEMMs, each step is {small GEMM for decoder_att(h), one fused attention kernel, small GEMM
+for the context half of W_ih, one recurrent step per layer}, and the vocabulary projection + CE
+runs once over all packed top-layer states after the loop (the reference's `op` is never fed back,
+rnn_attn.py:71-72).  Backward mirrors it, with d att1 / d w_f / d W_embed / all weight gradients
+hoisted out of the reverse loop.
+"""
+import torch
+
+from . import _lib, ops
+from .engine import Linear, layer_params, vocab_ce, weight_grad
+
+F32, BF16 = torch.float32, torch.bfloat16
+
+
+def _offsets(bs):
+    off, o = [], 0
+    for b in bs:
+        off.append(o)
+        o += b
+    return off
+
+
+def _lin_small(x, W, bias=None, out=None, beta=0.0):
+    """Per-step product on fp32 operands (M ~ live batch rows)."""
+    return ops.sgemm(x, W, transB=True, bias=bias, out=out, beta=beta)
+
+
+def attn_forward(mode, P, kind, L, feature, caption, bs, save):
+    """Returns (Hs_top (N,H), alphas (B,Tcap,P), saved dict)."""
+    B, C, Pn = feature.shape
+    T, N, off = len(bs), sum(bs), _offsets(bs)
+    Tcap = caption.shape[1]
+    E = P["embeddings.weight"].shape[1]
+    dev = feature.device
+    sv = {"bs": bs, "off": off, "Pn": Pn, "B": B}
+
+    F, FT, mean_f = ops.attn_relayout(feature, bf16=(mode == "bf16"), want_t=(save and mode == "bf16"))
+    sv.update(F=F, FT=FT, mean_f=mean_f)
+    # rnn_attn.py:62: every layer starts from init_h(mean_P f) (init_c likewise for the LSTM)
+    h0 = _lin_small(mean_f, P["init_h.weight"], P["init_h.bias"])
+    c0 = _lin_small(mean_f, P["init_c.weight"], P["init_c.bias"]) if kind == _lib.ST_LSTM else None
+    sv.update(h0=h0, c0=c0)
+    # hoisted, state-independent projections of the grid
+    store = BF16 if mode == "bf16" else F32
+    enc = Linear(mode, P["attn.encoder_att.weight"], P["attn.encoder_att.bias"], save, "att1")
+    att1 = enc.fwd(F, FT, out_dtype=store)                                            # rnn_attn.py:23
+    emb_lin = Linear(mode, P["embed.weight"], None, False, "fe")
+    Fe = emb_lin.fwd(F, None, out_dtype=store)                                        # embed() applied per location
+    sv.update(att1=att1, Fe=Fe)
+    # layer-0 input rows [emb(caption[:, t]) | embed(ctx_t)]  (rnn_attn.py:70: no input/target shift)
+    X0 = ops.pack_inputs(P["embeddings.weight"], None, caption, bs, False, width=2 * E)
+    Wih0, _, bih0, _ = layer_params(P, 0)
+    Gx = [ops.sgemm(X0[:, :E], Wih0[:, :E], transB=True, bias=bih0, tag="ih_fwd")]    # emb half hoisted
+    H = P["unit.weight_hh_l0"].shape[1]
+    G = Wih0.shape[0]
+    for l in range(1, L):
+        Gx.append(torch.empty(N, G, dtype=F32, device=dev))
+    alphas = torch.zeros(B, Tcap, Pn, dtype=F32, device=dev)                          # rnn_attn.py:65
+    S = torch.zeros(B, Pn, dtype=F32, device=dev)
+    att2_all = torch.empty(N, P["attn.decoder_att.weight"].shape[0], dtype=F32, device=dev)
+    outs = [None] * L
+    wf = P["attn.full_att.weight"].reshape(-1)
+    for t in range(T):
+        bt, o0 = bs[t], off[t]
+        o1 = o0 + bt
+        q = h0[:bt] if t == 0 else outs[L - 1]["Hs"][off[t - 1]:off[t - 1] + bt]      # pre-step top hidden, :69
+        _lin_small(q, P["attn.decoder_att.weight"], P["attn.decoder_att.bias"], out=att2_all[o0:o1])
+        ops.attn_step_fwd(bt, Pn, att1, Fe, att2_all[o0:o1], wf, P["attn.full_att.bias"], P["embed.bias"],
+                          alphas[:, t, :], Tcap * Pn, S, X0[o0:o1, E:])
+        _lin_small(X0[o0:o1, E:], Wih0[:, E:], out=Gx[0][o0:o1], beta=1.0)           # + W_ih[:, E:] embed(ctx)
+        for l in range(L):
+            Wih, Whh, bih, bhh = layer_params(P, l)
+            if l > 0:
+                _lin_small(outs[l - 1]["Hs"][o0:o1], Wih, bih, out=Gx[l][o0:o1])
+            outs[l] = ops.rnn_seq_fwd(kind, Gx[l], Whh, bhh, bs, h0=h0, c0=c0, save=save, t_range=(t, t + 1),
+                                      out=outs[l])
+    sv.update(X0=X0, outs=outs, att2_all=att2_all, alphas=alphas, S=S, enc=enc)
+    return outs[L - 1]["Hs"], alphas, sv
+
+
+def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=None):
+    """Gradients of every parameter given dHs_top (N,H) and the gradient w.r.t. alphas, either a
+    full (B,Tcap,P) tensor `dalphas` (drop-in forward) or the per-(b,p) penalty term `Gpen`."""
+    bs, off, Pn, B = sv["bs"], sv["off"], sv["Pn"], sv["B"]
+    T, N = len(bs), sum(bs)
+    E = P["embeddings.weight"].shape[1]
+    H = P["unit.weight_hh_l0"].shape[1]
+    dev = dHs_top.device
+    outs, X0, att1, Fe, att2_all, alphas, h0, c0 = (sv[k] for k in
+                                                    ("outs", "X0", "att1", "Fe", "att2_all", "alphas", "h0", "c0"))
+    Tcap = alphas.shape[1]
+    Wih0 = P["unit.weight_ih_l0"]
+    wf = P["attn.full_att.weight"].reshape(-1)
+    Wd = P["attn.decoder_att.weight"]
+    A = Wd.shape[0]
+    grads = {}
+    de_all = torch.empty(N, Pn, dtype=F32, device=dev)
+    datt2_all = torch.empty(N, A, dtype=F32, device=dev)
+    dctx_all = torch.empty(N, E, dtype=F32, device=dev)
+    dHs = [torch.empty(N, H, dtype=F32, device=dev) for _ in range(L - 1)] + [dHs_top]
+    bouts = [None] * L
+    for t in reversed(range(T)):
+        bt, o0 = bs[t], off[t]
+        o1 = o0 + bt
+        for l in reversed(range(L)):
+            Wih, Whh, _, _ = layer_params(P, l)
+            bouts[l] = ops.rnn_seq_bwd(kind, Whh, bs, outs[l], dHs[l], h0=h0, c0=c0, t_range=(t + 1, t),
+                                       out=bouts[l])
+            if l > 0:
+                ops.sgemm(bouts[l]["dG"][o0:o1], Wih, out=dHs[l - 1][o0:o1])          # dX of layer l at step t
+        ops.sgemm(bouts[0]["dG"][o0:o1], Wih0[:, E:], out=dctx_all[o0:o1])            # d embed(ctx_t)
+        if dalphas is not None:
+            dal, dal_stride = dalphas[:, t, :], Tcap * Pn
+        else:
+            dal, dal_stride = Gpen, Pn
+        ops.attn_step_bwd(bt, Pn, att1, Fe, att2_all[o0:o1], wf, alphas[:, t, :], Tcap * Pn, dal, dal_stride,
+                          dctx_all[o0:o1], de_all[o0:o1], datt2_all[o0:o1])
+        # the query was the PRE-step top-layer hidden: its gradient joins the carried dh of the top layer
+        dq = ops.sgemm(datt2_all[o0:o1], Wd)
+        ops.add_rows(bouts[L - 1]["dstate"][0], dq, bt)
+
+    # ---- hoisted weight gradients
+    for l in range(L):
+        Hprev = ops.shift_states(outs[l]["Hs"], bs, h0)
+        grads[f"unit.weight_hh_l{l}"] = weight_grad(mode, bouts[l]["dGh"], Hprev, "hh_dw")
+        grads[f"unit.bias_hh_l{l}"] = ops.colsum(bouts[l]["dGh"])
+        inp = X0 if l == 0 else outs[l - 1]["Hs"]
+        grads[f"unit.weight_ih_l{l}"] = weight_grad(mode, bouts[l]["dG"], inp, "ih_dw")
+        grads[f"unit.bias_ih_l{l}"] = ops.colsum(bouts[l]["dG"])
+        if l == L - 1:
+            Hprev_top = Hprev
+    dXemb = ops.sgemm(bouts[0]["dG"], Wih0[:, :E], tag="ih_dx")
+    dEmb = torch.zeros_like(P["embeddings.weight"])
+    ops.pack_inputs_bwd(dXemb, dEmb, None, caption, bs, False)
+    grads["embeddings.weight"] = dEmb
+    # attention parameters
+    datt1, datt1T, dwf = ops.attn_hoist_bwd(bs, Pn, att1, att2_all, de_all, wf, want_t=(mode == "bf16"))
+    if mode == "bf16":
+        grads["attn.encoder_att.weight"] = ops.gemm_bf16(datt1T, sv["FT"], tag="att1_dw")   # datt1^T F
+    else:
+        grads["attn.encoder_att.weight"] = ops.sgemm(datt1, sv["F"], transA=True, tag="att1_dw")
+    grads["attn.encoder_att.bias"] = ops.colsum(datt1)
+    grads["attn.decoder_att.weight"] = weight_grad(mode, datt2_all, Hprev_top, "att2_dw")
+    grads["attn.decoder_att.bias"] = ops.colsum(datt2_all)
+    grads["attn.full_att.weight"] = dwf.reshape(1, -1)
+    grads["attn.full_att.bias"] = ops.colsum(de_all.reshape(-1, 1))
+    # embed: ctx_e = W_embed ctx + b with ctx = sum_p alpha_p F_p rebuilt for all (t,b) in one pass
+    if mode == "bf16":
+        _, ctxT = ops.attn_ctx_all(bs, Pn, sv["F"], alphas, want=False, want_t=True)
+        _, dcT = ops.cast_bf16(dctx_all, False, True)
+        grads["embed.weight"] = ops.gemm_bf16(dcT, ctxT, tag="embed_dw")
+    else:
+        ctx, _ = ops.attn_ctx_all(bs, Pn, sv["F"], alphas)
+        grads["embed.weight"] = ops.sgemm(dctx_all, ctx, transA=True, tag="embed_dw")
+    grads["embed.bias"] = ops.colsum(dctx_all)
+    # initial state: every layer started from the same h0 / c0 (rnn_attn.py:62)
+    dh0 = bouts[0]["dstate"][0]
+    dc0 = bouts[0]["dstate"][1]
+    for l in range(1, L):
+        dh0 = dh0 + bouts[l]["dstate"][0]
+        dc0 = dc0 + bouts[l]["dstate"][1]
+    grads["init_h.weight"] = ops.sgemm(dh0, sv["mean_f"], transA=True)
+    grads["init_h.bias"] = ops.colsum(dh0)
+    if kind == _lib.ST_LSTM:
+        grads["init_c.weight"] = ops.sgemm(dc0, sv["mean_f"], transA=True)
+        grads["init_c.bias"] = ops.colsum(dc0)
+    return grads
+
+
+def _check_inputs(feature, caption, lengths, C):
+    if not (feature.is_cuda and caption.is_cuda):
+        raise RuntimeError("showtell_b200 runs on CUDA tensors only (no CPU fallback)")
+    if feature.dim() != 3 or feature.shape[1] != C:
+        raise ValueError(f"cnn_feature must be (B, {C}, P) channels-first, got {tuple(feature.shape)}")
+    if caption.dim() != 2 or caption.shape[0] != feature.shape[0] or caption.dtype != torch.int64:
+        raise ValueError("image_caption must be (B, T) int64")
+    if len(lengths) != feature.shape[0]:
+        raise ValueError("caption_size must have one entry per batch row")
+    bs = _lib.batch_sizes(lengths)
+    if len(bs) > caption.shape[1]:
+        raise ValueError("caption_size exceeds the padded caption length")
+    return bs
+
+
+class AttnLogitsFn(torch.autograd.Function):
+    """RNN_Attn.forward as the reference exposes it: (logits (N,V) packed, alphas (B,T,P))."""
+
+    @staticmethod
+    def forward(ctx, mod, feature, caption, lengths, *params):
+        names = [n for n, _ in mod.named_parameters()]
+        P = {n: p.detach() for n, p in zip(names, params)}
+        mode = mod.compute_dtype
+        f = feature.detach().contiguous().to(F32)
+        cap = caption.contiguous()
+        bs = _check_inputs(f, cap, lengths, mod.nos_filters)
+        save = any(ctx.needs_input_grad)
+        Hs, alphas, sv = attn_forward(mode, P, mod._kind, mod.num_layers, f, cap, bs, save)
+        vocab = Linear(mode, P["linear.weight"], P["linear.bias"], save, "vocab")
+        logits = vocab.fwd(Hs)                                                        # rnn_attn.py:71,115
+        ctx.names, ctx.P, ctx.mod, ctx.vocab, ctx.sv, ctx.caption = names, P, mod, vocab, sv, cap
+        return logits, alphas
+
+    @staticmethod
+    def backward(ctx, dlogits, dalphas):
+        mod = ctx.mod
+        dHs, dWv, dbv = ctx.vocab.bwd(dlogits.contiguous().to(F32))
+        if dalphas is None:
+            dalphas = torch.zeros_like(ctx.sv["alphas"])
+        grads = attn_backward(mod.compute_dtype, ctx.P, mod._kind, mod.num_layers, ctx.caption, ctx.sv, dHs,
+                              dalphas=dalphas.contiguous().to(F32))
+        grads["linear.weight"], grads["linear.bias"] = dWv, dbv
+        return (None, None, None, None) + tuple(grads[n] for n in ctx.names)
+
+
+class AttnLossFn(torch.autograd.Function):
+    """forward_loss: CE(mean over packed tokens, same-index targets) + alpha_c * mean_{B,P}((1 -
+    sum_t alpha)^2)  (main_attn.py:126,130-131), forward and backward in one pass.  `denom_tokens` /
+    `denom_batch` are the global token / batch counts under data parallelism."""
+
+    @staticmethod
+    def forward(ctx, mod, feature, caption, lengths, alpha_c, denom_tokens, denom_batch, *params):
+        names = [n for n, _ in mod.named_parameters()]
+        P = {n: p.detach() for n, p in zip(names, params)}
+        mode = mod.compute_dtype
+        f = feature.detach().contiguous().to(F32)
+        cap = caption.contiguous()
+        bs = _check_inputs(f, cap, lengths, mod.nos_filters)
+        need = any(ctx.needs_input_grad)
+        Hs, alphas, sv = attn_forward(mode, P, mod._kind, mod.num_layers, f, cap, bs, need)
+        target = ops.pack_targets(cap, bs)
+        dt = float(denom_tokens if denom_tokens is not None else sum(bs))
+        db = float(denom_batch if denom_batch is not None else f.shape[0])
+        loss, dHs, grads = vocab_ce(mode, P, Hs, target, dt, need)
+        coef = float(alpha_c) / (db * f.shape[2])
+        pen_sum, Gpen = ops.attn_penalty(sv["S"], coef)
+        loss = loss + coef * pen_sum.reshape(())
+        ctx.names, ctx.grads = names, None
+        if need:
+            g2 = attn_backward(mode, P, mod._kind, mod.num_layers, cap, sv, dHs, Gpen=Gpen)
+            g2.update(grads)
+            ctx.grads = g2
+        ctx.mark_non_differentiable(alphas)
+        return loss, alphas
+
+    @staticmethod
+    def backward(ctx, g, _dalphas):
+        if ctx.grads is None:
+            raise RuntimeError("forward_loss was run without grad enabled")
+        return (None,) * 7 + tuple(ctx.grads[n] * g for n in ctx.names)

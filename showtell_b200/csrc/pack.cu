@@ -93,6 +93,14 @@ __global__ void colsum_kernel(float* __restrict__ out, const T* __restrict__ M, 
   }
 }
 
+// dst[i, :width] = table[idx[i * idx_stride], :]  (nn.Embedding lookup of the decode loops, rnn.py:53)
+__global__ void gather_rows_kernel(float* __restrict__ dst, int ld_dst, const float* __restrict__ table, int width,
+                                   const int64_t* __restrict__ idx, int idx_stride) {
+  const float* src = table + (size_t)idx[(size_t)blockIdx.x * idx_stride] * width;
+  float* d = dst + (size_t)blockIdx.x * ld_dst;
+  for (int e = threadIdx.x; e < width; e += blockDim.x) d[e] = src[e];
+}
+
 __global__ void shift_states_kernel(const __grid_constant__ StepTable tab, float* __restrict__ Hprev,
                                     const float* __restrict__ Hs, const float* __restrict__ h0, int H) {
   const int n = blockIdx.x;
@@ -172,6 +180,16 @@ int st_colsum(float* out, const void* M, int m_is_bf16, int rows, int cols, int 
   else
     colsum_kernel<float><<<grid, block, 0, s>>>(out, reinterpret_cast<const float*>(M), rows, cols, ld);
   ST_LAUNCH_TRY("colsum_kernel");
+  return ST_OK;
+}
+
+int st_gather_rows(float* dst, int ld_dst, const float* table, int width, const int64_t* idx, int idx_stride,
+                   int n, st_stream_t stream) {
+  using namespace st;
+  ST_REQUIRE(dst && table && idx, ST_ERR_NULL, "st_gather_rows: NULL pointer");
+  ST_REQUIRE(n >= 1 && width >= 1 && ld_dst >= width && idx_stride >= 1, ST_ERR_BAD_SHAPE, "st_gather_rows: bad shape");
+  gather_rows_kernel<<<n, 128, 0, as_stream(stream)>>>(dst, ld_dst, table, width, idx, idx_stride);
+  ST_LAUNCH_TRY("gather_rows_kernel");
   return ST_OK;
 }
 

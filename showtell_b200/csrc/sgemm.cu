@@ -123,6 +123,57 @@ __global__ void __launch_bounds__(NT) sgemm_kernel(int M, int N, int K, float al
   }
 }
 
+// Small-problem variant (per-step products of the attention / decode loops, M ~ batch): 32x32x32
+// tiles so that a 128 x 512 output still spreads over 64 CTAs; 2x2 outputs per thread.
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(NT) sgemm_small_kernel(int M, int N, int K, float alpha,
+                                                         const float* __restrict__ A, int lda,
+                                                         const float* __restrict__ B, int ldb, float beta,
+                                                         float* __restrict__ C, int ldc,
+                                                         const float* __restrict__ bias) {
+  __shared__ float As[32][33], Bs[32][33];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      {  // A element (m, k): TA=0 memory (M,K) k-contiguous; TA=1 memory (K,M) m-contiguous
+        const int k = TA ? (tid >> 5) + 8 * i : (tid & 31), m = TA ? (tid & 31) : (tid >> 5) + 8 * i;
+        const int gm = m0 + m, gk = k0 + k;
+        As[k][m] = (gm < M && gk < K) ? (TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk]) : 0.f;
+      }
+      {  // B element (n, k): TB=1 memory (N,K) k-contiguous; TB=0 memory (K,N) n-contiguous
+        const int k = TB ? (tid & 31) : (tid >> 5) + 8 * i, n = TB ? (tid >> 5) + 8 * i : (tid & 31);
+        const int gn = n0 + n, gk = k0 + k;
+        Bs[k][n] = (gn < N && gk < K) ? (TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn]) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float a0 = As[k][ty * 2], a1 = As[k][ty * 2 + 1], b0 = Bs[k][tx * 2], b1 = Bs[k][tx * 2 + 1];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]);
+      acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]);
+      acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int m = m0 + ty * 2 + i, n = n0 + tx * 2 + j;
+      if (m < M && n < N) {
+        float v = alpha * acc[i][j];
+        if (bias) v += bias[n];
+        if (beta != 0.f) v += beta * C[(size_t)m * ldc + n];
+        C[(size_t)m * ldc + n] = v;
+      }
+    }
+}
+
 }  // namespace
 }  // namespace st
 
@@ -138,6 +189,19 @@ extern "C" int st_sgemm(int transA, int transB, int M, int N, int K, float alpha
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   ST_REQUIRE(grid.y <= 65535, ST_ERR_BAD_SHAPE, "st_sgemm: M=%d too large", M);
   cudaStream_t s = as_stream(stream);
+  if (grid.x * grid.y < 48) {  // too few 128x128 tiles to fill the GPU: small-tile kernel
+    dim3 g2((N + 31) / 32, (M + 31) / 32);
+    if (!transA && !transB)
+      sgemm_small_kernel<false, false><<<g2, NT, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
+    else if (!transA && transB)
+      sgemm_small_kernel<false, true><<<g2, NT, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
+    else if (transA && !transB)
+      sgemm_small_kernel<true, false><<<g2, NT, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
+    else
+      sgemm_small_kernel<true, true><<<g2, NT, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
+    ST_LAUNCH_TRY("sgemm_small_kernel");
+    return ST_OK;
+  }
   if (!transA && !transB)
     sgemm_kernel<false, false><<<grid, NT, 0, s>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias);
   else if (!transA && transB)

@@ -25,12 +25,16 @@ class Linear:
         if mode == "bf16":
             self.Wb, self.WT = ops.cast_bf16(W, True, need_bwd)
 
-    def fwd(self, X):
+    def fwd(self, X, XT=None, out_dtype=F32):
+        """X fp32, or (bf16 mode) already bf16 together with its transpose XT when a backward follows."""
         if self.mode == "fp32":
             self.X = X
             return ops.sgemm(X, self.W, transB=True, bias=self.bias, tag=self.tag + "_fwd")
-        Xb, self.XT = ops.cast_bf16(X, True, self.need_bwd)
-        return ops.gemm_bf16(Xb, self.Wb, bias=self.bias, tag=self.tag + "_fwd")
+        if X.dtype == torch.bfloat16:
+            Xb, self.XT = X, XT
+        else:
+            Xb, self.XT = ops.cast_bf16(X, True, self.need_bwd)
+        return ops.gemm_bf16(Xb, self.Wb, bias=self.bias, out_dtype=out_dtype, tag=self.tag + "_fwd")
 
     def bwd_bf16(self, dYb, dYT, need_dx=True):
         """Backward from gate gradients that already are bf16 GEMM operands (row-major + transposed)."""

@@ -64,11 +64,13 @@ def sgemm(A, B, *, transA=False, transB=False, bias=None, out=None, alpha=1.0, b
     return out
 
 
-def pack_inputs(emb, feature, caption, bs, with_feature):
+def pack_inputs(emb, feature, caption, bs, with_feature, width=None):
+    """Packed inputs (N, width >= E); only the first E columns are written (attention models use
+    width = 2E and let the attention kernel fill the other half)."""
     lib = _lib.load()
     N, E = sum(bs), emb.shape[1]
-    X = torch.empty(N, E, dtype=F32, device=emb.device)
-    check(lib.st_pack_inputs(ptr(X, F32), E, ptr(emb, F32), E, ptr(feature, F32) if with_feature else None,
+    X = torch.empty(N, width or E, dtype=F32, device=emb.device)
+    check(lib.st_pack_inputs(ptr(X, F32), X.shape[1], ptr(emb, F32), E, ptr(feature, F32) if with_feature else None,
                              ptr(caption, I64), caption.shape[1], int(with_feature), len(bs),
                              int_array(bs), stream_ptr()), "st_pack_inputs")
     return X
@@ -76,7 +78,7 @@ def pack_inputs(emb, feature, caption, bs, with_feature):
 
 def pack_inputs_bwd(dX, dEmb, dfeature, caption, bs, with_feature):
     lib = _lib.load()
-    check(lib.st_pack_inputs_bwd(ptr(dX, F32), dX.shape[1], ptr(dEmb, F32), dEmb.shape[1],
+    check(lib.st_pack_inputs_bwd(ptr(dX, F32), dX.stride(0), ptr(dEmb, F32), dEmb.shape[1],
                                  ptr(dfeature, F32), ptr(caption, I64), caption.shape[1],
                                  int(with_feature), len(bs), int_array(bs), stream_ptr()),
           "st_pack_inputs_bwd")
@@ -176,12 +178,24 @@ def ce_fwd_bwd(logits, target, grad_scale=None, inplace=False):
     return loss_sum, lse, dl
 
 
-def argmax_rows(X):
+def argmax_rows(X, out=None):
+    """Row-wise arg-max (first maximal index).  `out` may be a strided 1-D int64 view (a column of the
+    token matrix)."""
     lib = _lib.load()
-    idx = torch.empty(X.shape[0], dtype=I64, device=X.device)
-    check(lib.st_argmax_rows(ptr(X, F32), X.stride(0), X.shape[0], X.shape[1], ptr(idx), 1, stream_ptr()),
-          "st_argmax_rows")
+    idx = torch.empty(X.shape[0], dtype=I64, device=X.device) if out is None else out
+    import ctypes as C
+    check(lib.st_argmax_rows(ptr(X, F32), X.stride(0), X.shape[0], X.shape[1], C.c_void_p(idx.data_ptr()),
+                             idx.stride(0), stream_ptr()), "st_argmax_rows")
     return idx
+
+
+def gather_rows(dst, table, idx):
+    """dst[i, :W] = table[idx[i]] for a (possibly strided) 1-D int64 idx and a row-strided dst view."""
+    lib = _lib.load()
+    import ctypes as C
+    check(lib.st_gather_rows(C.c_void_p(dst.data_ptr()), dst.stride(0), ptr(table, F32), table.shape[1],
+                             C.c_void_p(idx.data_ptr()), idx.stride(0), idx.shape[0], stream_ptr()),
+          "st_gather_rows")
 
 
 def topk_rows(X, K):
@@ -328,3 +342,87 @@ def rnn_seq_tc_bwd(kind, WhhT_b, bs, saved, dHs, *, h0=None, c0=None, tag=None):
     if tok:
         TIMER.end(tok)
     return o
+
+
+# ----------------------------------------------------------------------------- attention
+ACT_LEAKY, ACT_TANH = 0, 1
+
+
+def attn_relayout(f, bf16=False, want_t=True):
+    """f (B,C,P) fp32 channels-first -> F (B*P, C), FT (C, B*P) or None, mean_f (B,C)."""
+    lib = _lib.load()
+    B, Cc, Pn = f.shape
+    dt = BF16 if bf16 else F32
+    F = torch.empty(B * Pn, Cc, dtype=dt, device=f.device)
+    ld = (B * Pn + 7) // 8 * 8
+    FT = torch.empty(Cc, ld, dtype=dt, device=f.device)[:, :B * Pn] if want_t else None
+    mean_f = torch.empty(B, Cc, dtype=F32, device=f.device)
+    check(lib.st_attn_relayout(ptr(f, F32), B, Cc, Pn, _raw(F), _raw(FT) if want_t else None, ld, int(bf16),
+                               ptr(mean_f), stream_ptr()), "st_attn_relayout")
+    return F, FT, mean_f
+
+
+def attn_step_fwd(rows, Pn, att1, Fe, att2, wf, bf, b_embed, alphas_t, alpha_stride, S, ctx_out, act=ACT_LEAKY):
+    """att1 (B*P, A), Fe (B*P, E) (fp32 or bf16), att2 (rows, A).  alphas_t / ctx_out are (possibly
+    strided) views whose first element is row 0; ctx_out row stride = ctx_out.stride(0)."""
+    lib = _lib.load()
+    A, E = att1.shape[1], Fe.shape[1]
+    check(lib.st_attn_step_fwd(rows, Pn, A, E, _raw(att1), _raw(Fe), int(att1.dtype == BF16), _raw(att2),
+                               ptr(wf, F32), ptr(bf, F32), ptr(b_embed, F32), _raw(alphas_t), alpha_stride,
+                               ptr(S, F32), _raw(ctx_out), ctx_out.stride(0), act, stream_ptr()),
+          "st_attn_step_fwd")
+
+
+def attn_step_bwd(rows, Pn, att1, Fe, att2, wf, alphas_t, alpha_stride, dalpha, dalpha_stride, dctx, de_out,
+                  datt2, act=ACT_LEAKY):
+    lib = _lib.load()
+    A, E = att1.shape[1], Fe.shape[1]
+    check(lib.st_attn_step_bwd(rows, Pn, A, E, _raw(att1), _raw(Fe), int(att1.dtype == BF16), _raw(att2),
+                               ptr(wf, F32), _raw(alphas_t), alpha_stride,
+                               _raw(dalpha) if dalpha is not None else None, dalpha_stride, _raw(dctx),
+                               dctx.stride(0), _raw(de_out), _raw(datt2), act, stream_ptr()), "st_attn_step_bwd")
+
+
+def attn_hoist_bwd(bs, Pn, att1, att2_all, de_all, wf, want_t=True, act=ACT_LEAKY):
+    """Returns (datt1 (B*P, A), datt1T (A, B*P) or None, dwf (A,)) in att1's storage type."""
+    lib = _lib.load()
+    A = att1.shape[1]
+    BP = att1.shape[0]
+    dev = att1.device
+    datt1 = torch.empty_like(att1)
+    ld = (BP + 7) // 8 * 8
+    dT = torch.empty(A, ld, dtype=att1.dtype, device=dev)[:, :BP] if want_t else None
+    dwf = torch.empty(A, dtype=F32, device=dev)
+    isb = int(att1.dtype == BF16)
+    check(lib.st_attn_hoist_bwd(len(bs), int_array(bs), Pn, A, _raw(att1), isb, ptr(att2_all, F32),
+                                ptr(de_all, F32), ptr(wf, F32), _raw(datt1), _raw(dT) if want_t else None, ld,
+                                isb, ptr(dwf), act, stream_ptr()), "st_attn_hoist_bwd")
+    return datt1, dT, dwf
+
+
+def attn_ctx_all(bs, Pn, F, alphas, want=True, want_t=False):
+    """ctx (N, C) and/or ctxT (C, N) in F's storage type; alphas (B, Tcap, P) fp32."""
+    lib = _lib.load()
+    N, Cc = sum(bs), F.shape[1]
+    dev = F.device
+    ctx = torch.empty(N, Cc, dtype=F.dtype, device=dev) if want else None
+    ld = (N + 7) // 8 * 8
+    cT = torch.empty(Cc, ld, dtype=F.dtype, device=dev)[:, :N] if want_t else None
+    check(lib.st_attn_ctx_all(len(bs), int_array(bs), Pn, Cc, alphas.shape[1], _raw(F), int(F.dtype == BF16),
+                              ptr(alphas, F32), _raw(ctx) if want else None, _raw(cT) if want_t else None, ld,
+                              stream_ptr()), "st_attn_ctx_all")
+    return ctx, cT
+
+
+def attn_penalty(S, coef):
+    lib = _lib.load()
+    pen = torch.empty(1, dtype=F32, device=S.device)
+    G = torch.empty_like(S)
+    check(lib.st_attn_penalty(S.numel(), ptr(S, F32), float(coef), ptr(pen), ptr(G), stream_ptr()),
+          "st_attn_penalty")
+    return pen, G
+
+
+def add_rows(dst, src, rows):
+    lib = _lib.load()
+    check(lib.st_add_rows(_raw(dst), _raw(src), rows, dst.shape[-1], stream_ptr()), "st_add_rows")

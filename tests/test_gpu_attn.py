@@ -1,0 +1,145 @@
+"""GPU parity of the attention decoders (Attention/rnn_attn.py, rnn_attn_LSTM.py) against the golden
+fixtures of the unmodified reference and against the CPU oracle at larger sizes."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import ATTN_CASES, golden_grads, golden_params, load_golden, rel_err
+from oracle import showtell_oracle as O
+
+TOL = 1e-4
+DEV = "cuda:0"
+
+
+def _cls(kind):
+    if kind == "attn_gru":
+        from showtell_b200.rnn_attn import RNN_Attn
+    else:
+        from showtell_b200.rnn_attn_LSTM import RNN_Attn
+    return RNN_Attn
+
+
+def _module(g):
+    E, C, A, H, V, L, P, _, _ = g["dims"].tolist()
+    m = _cls(str(g["kind"]))(E, C, A, H, V, L)
+    m.load_state_dict(golden_params(g))
+    return m.to(DEV)
+
+
+def _check_grads(m, gg, tol, scale=1.0):
+    for n, p in m.named_parameters():
+        ref = gg[n]
+        if n == "attn.full_att.bias":               # == 0 up to rounding (softmax is shift invariant)
+            assert float(p.grad.abs().max()) / scale < 1e-5
+            continue
+        assert rel_err(p.grad / scale, ref) < tol, n
+
+
+@pytest.mark.parametrize("name", ATTN_CASES)
+def test_golden_forward_backward(name):
+    g = load_golden(name)
+    m = _module(g)
+    feat = torch.from_numpy(g["cnn_feature"]).to(DEV)
+    cap = torch.from_numpy(g["caption"]).to(DEV)
+    lengths = g["lengths"].tolist()
+    logits, alphas = m(feat, cap, lengths)                                          # main_attn.py:129
+    assert logits.shape == g["logits"].shape and alphas.shape == g["alphas"].shape
+    assert rel_err(logits, g["logits"]) < TOL
+    assert rel_err(alphas, g["alphas"]) < TOL
+    target = torch.nn.utils.rnn.pack_padded_sequence(cap, lengths, batch_first=True)[0]
+    loss = torch.nn.CrossEntropyLoss()(logits, target)                              # main_attn.py:130
+    loss = loss + float(g["alpha_c"]) * ((1. - alphas.sum(dim=1)) ** 2).mean()      # main_attn.py:131
+    assert abs(float(loss) - float(g["loss"])) < TOL * float(g["loss"])
+    loss.backward()
+    _check_grads(m, golden_grads(g), TOL)
+
+
+@pytest.mark.parametrize("name", ATTN_CASES)
+def test_golden_fused_loss(name):
+    g = load_golden(name)
+    m = _module(g)
+    feat = torch.from_numpy(g["cnn_feature"]).to(DEV)
+    cap = torch.from_numpy(g["caption"]).to(DEV)
+    loss, alphas = m.forward_loss(feat, cap, g["lengths"].tolist(), alpha_c=float(g["alpha_c"]))
+    assert abs(float(loss) - float(g["loss"])) < TOL * float(g["loss"])
+    assert rel_err(alphas, g["alphas"]) < TOL
+    (2.0 * loss).backward()
+    _check_grads(m, golden_grads(g), TOL, scale=2.0)
+
+
+@pytest.mark.parametrize("name", ATTN_CASES)
+def test_golden_greedy(name):
+    g = load_golden(name)
+    m = _module(g)
+    feat = torch.from_numpy(g["cnn_feature"]).to(DEV)
+    vocab = lambda w: {"<pad>": 0, "<start>": 1, "<end>": 2, "<unk>": 3}[w]
+    tok = m.sentence_index(feat, vocab)                                             # main_attn.py:189
+    assert tok.shape == g["greedy"].shape and tok.dtype == torch.int64
+    assert np.array_equal(tok.cpu().numpy(), g["greedy"])
+    assert m.sentence_index(feat[:1], vocab).shape == (25,)
+
+
+def _random_case(kind, E, C, A, H, V, L, P, B, T, seed, dtype):
+    torch.manual_seed(seed)
+    g = torch.Generator().manual_seed(seed)
+    m = _cls(kind)(E, C, A, H, V, L, dtype=dtype)
+    lengths = sorted(torch.randint(max(2, T // 3), T + 1, (B,), generator=g).tolist(), reverse=True)
+    lengths[0] = T
+    cap = torch.zeros(B, T, dtype=torch.int64)
+    for b, l in enumerate(lengths):
+        cap[b, 0] = 1
+        cap[b, 1:l - 1] = torch.randint(4, V, (l - 2,), generator=g)
+        cap[b, l - 1] = 2
+    feat = torch.relu(torch.randn(B, C, P, generator=g))
+    return m, feat, cap, lengths
+
+
+@pytest.mark.parametrize("kind,E,C,A,H,V,L,P,B,T,dtype,tol", [
+    ("attn_gru", 512, 2048, 512, 512, 10000, 1, 49, 12, 20, "fp32", 1e-4),    # config 3 shapes, 7x7 grid
+    ("attn_lstm", 512, 2048, 512, 512, 10000, 1, 196, 6, 12, "fp32", 1e-4),   # config 4 shapes, 14x14 grid
+    ("attn_gru", 64, 96, 48, 64, 333, 3, 30, 140, 9, "fp32", 1e-4),           # 3 layers, two batch tiles
+    ("attn_gru", 512, 2048, 512, 512, 10000, 1, 196, 16, 20, "bf16", 2e-2),
+    ("attn_lstm", 512, 2048, 512, 512, 10000, 1, 49, 16, 20, "bf16", 2e-2),
+])
+def test_oracle_parity_train(kind, E, C, A, H, V, L, P, B, T, dtype, tol):
+    """encoder_att.weight is the one ill-conditioned gradient: it sums act'(att1 + att2) over every
+    (b, p, a, t), and LeakyReLU' jumps 0.2 -> 1 at 0, so pre-activations within rounding distance
+    of the kink flip whole terms.  The fp32 reference itself is only as close to exact arithmetic
+    as that allows; the bar for this tensor is therefore calibrated on the float32-vs-float64
+    oracle gap (fp32 mode) and checked in the L2 norm (bf16 mode, whose att1 is stored in bf16)."""
+    m, feat, cap, lengths = _random_case(kind, E, C, A, H, V, L, P, B, T, 5, dtype)
+    p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    loss_ref, grads_ref, ex = O.train_step(p, kind, feat, cap, lengths, alpha_c=1.0)
+    p64 = {k: v.double() for k, v in p.items()}
+    _, grads64, _ = O.train_step(p64, kind, feat.double(), cap, lengths, alpha_c=1.0)
+    kink = "attn.encoder_att.weight"
+    gap = rel_err(grads_ref[kink], grads64[kink])
+    m = m.to(DEV)
+    loss, alphas = m.forward_loss(feat.to(DEV), cap.to(DEV), lengths, alpha_c=1.0)
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) < tol * float(loss_ref)
+    assert rel_err(alphas, ex["alphas"]) < tol
+    for n, q in m.named_parameters():
+        if n == "attn.full_att.bias":
+            continue
+        if n == kink:
+            err = rel_err(q.grad, grads64[n])
+            l2 = float((q.grad.cpu().double() - grads64[n]).norm() / grads64[n].norm())
+            print(f"{kink}: max-rel {err:.2e}, L2-rel {l2:.2e}; fp32 oracle vs fp64 oracle {gap:.2e}")
+            if dtype == "fp32":
+                assert err < max(tol, 5 * gap), n
+            else:
+                assert l2 < tol and err < 3 * tol, n
+            continue
+        assert rel_err(q.grad, grads_ref[n]) < tol, n
+
+
+def test_oracle_parity_greedy_full_size():
+    m, feat, _, _ = _random_case("attn_gru", 512, 2048, 512, 512, 10000, 1, 49, 8, 20, 9, "fp32")
+    p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref = O.attn_greedy(p, "gru", feat)
+    tok = m.to(DEV).sentence_index(feat.to(DEV), lambda w: 1)
+    assert np.array_equal(tok.cpu().numpy(), ref.numpy())
