@@ -2,22 +2,26 @@
 """bench.py -- headline benchmark of the show-tell caption-decoder hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload lstm_train|gru_train|beam3] [--dtype fp32|bf16]
+                    [--workload lstm_train|gru_train|attn_gru_train|attn_lstm_train|beam3|beam5]
+                    [--dtype fp32|bf16]
 
-Workload (BASELINE.json configs[1], the configuration the metric is quoted on that fits one GPU):
-LSTM/rnn_lstm.py decoder training step -- forward + cross-entropy + backward -- with E = H = 512,
-V = 10 000, batch 256 per GPU, caption length 20, L = 1, synthetic N(0,1) features of the ResNet
-head's output shape and random-init weights.  One "step" = one such iteration on one batch
-(5120 tokens per GPU).  Metric: training tokens/s, whole job.
+Default workload (BASELINE.json configs[1], the configuration the metric is quoted on that fits one
+GPU): LSTM/rnn_lstm.py decoder training step -- forward + cross-entropy + backward -- with
+E = H = 512, V = 10 000, batch 256 per GPU, caption length 20, L = 1, bf16 tensor-core arithmetic
+with fp32 state/accumulation, synthetic N(0,1) features of the ResNet head's output shape and
+random-init weights.  One "step" = one such iteration on one batch (5120 tokens per GPU).
+Metric: training tokens/s, whole job.  The other workloads are the remaining BASELINE configs
+(attention decoders on a 14x14x2048 grid, chain beam search), selectable for reporting.
 
-Our arm times the repo's public API (RNN.forward_loss + backward) with CUDA events on the
-launching stream; `value` has the batch resident in HBM, `e2e` copies features + captions from
-pinned host memory and reads the loss back every step.  Between timed steps a 256 MiB buffer is
-rewritten to flush the 126 MB L2 (outside the per-step event pairs).  N > 1: one process per GPU
-(torchrun), batch-sharded, gradients all-reduced over NCCL inside the timed step, max over ranks.
+Our arm times the repo's public API (forward_loss + backward, or sentence_index) with CUDA events
+on the launching stream; `value` has the batch resident in HBM, `e2e` copies the step's inputs
+from pinned host memory and reads the result back every step.  Between timed steps a 256 MiB
+buffer is rewritten to flush the 126 MB L2 (outside the per-step event pairs).  N > 1: one process
+per GPU (torchrun), batch-sharded (weak scaling), gradients all-reduced over NCCL inside the timed
+step on a side stream overlapped with backward; time = max over ranks.
 
-`--impl reference` times the reference algorithm on the host CPU cores (the oracle port; the
-reference is pure Python over torch CPU kernels and is not shipped to the GPU box).
+`--impl reference` times the reference algorithm on the host CPU cores (the oracle port: the
+reference is pure Python over torch CPU kernels and cannot travel to the GPU box).
 """
 import argparse
 import json
@@ -32,13 +36,22 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-E = H = 512
+E = H = A = 512
+C = 2048
 V = 10000
 T = 20
 WORKLOADS = {
-    # name: (model kind, per-GPU batch, description)
-    "lstm_train": ("lstm", 256, "rnn_lstm.py LSTM decoder train step fwd+CE+bwd, E=H=512 V=10000 B=256/GPU T=20 L=1"),
-    "gru_train": ("gru", 32, "rnn.py GRU decoder train step fwd+CE+bwd, E=H=512 V=10000 B=32/GPU T=20 L=1"),
+    # name: (model, per-GPU batch, grid locations / beam width, description)
+    "lstm_train": ("lstm", 256, 0, "rnn_lstm.py LSTM decoder train step fwd+CE+bwd, E=H=512 V=10000 B=256/GPU T=20 L=1"),
+    "gru_train": ("gru", 32, 0, "rnn.py GRU decoder train step fwd+CE+bwd, E=H=512 V=10000 B=32/GPU T=20 L=1"),
+    "attn_gru_train": ("attn_gru", 128, 196, "rnn_attn.py GRU+soft attention train step (CE + alpha_c=1 penalty) "
+                       "fwd+bwd, 14x14x2048 grid, E=H=A=512 V=10000 B=128/GPU T=20 L=1"),
+    "attn_lstm_train": ("attn_lstm", 512, 196, "rnn_attn_LSTM.py LSTM+soft attention train step fwd+bwd, "
+                        "14x14x2048 grid, E=H=A=512 V=10000 B=512/GPU T=20 L=1"),
+    "beam3": ("beam", 4096, 3, "rnn.py sentence_index(beam_size=3) chain beam search, GRU E=H=512 V=10000 L=1, "
+              "max_len 20, 4096 images/GPU per step"),
+    "beam5": ("beam", 4096, 5, "rnn.py sentence_index(beam_size=5) chain beam search, GRU E=H=512 V=10000 L=1, "
+              "max_len 20, 4096 images/GPU per step"),
 }
 
 
@@ -64,7 +77,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
@@ -79,59 +92,95 @@ class ClockSampler(threading.Thread):
             self.proc.terminate()
         except Exception:
             pass
-        rows = [r for t, r in self.rows if self.t0 is None or (self.t0 - 0.05 <= t <= (self.t1 or t) + 0.15)]
-        self.rows = rows or [r for _, r in self.rows]
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        rows = [r for t, r in self.rows if self.t0 is None or (self.t0 - 0.05 <= t <= (self.t1 or t) + 0.05)]
+        rows = rows or [r for _, r in self.rows]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
 
-def make_batch(kind, B, seed):
+def make_batch(model, B, Pn, seed):
     g = torch.Generator().manual_seed(seed)
-    feat = torch.randn(B, E, generator=g)
+    if model == "beam":
+        return torch.randn(B, E, generator=g), None, None
+    feat = torch.relu(torch.randn(B, C, Pn, generator=g)) if model.startswith("attn") else torch.randn(B, E, generator=g)
     cap = torch.randint(4, V, (B, T), generator=g)
     cap[:, 0] = 1
     cap[:, -1] = 2
     return feat, cap, [T] * B
 
 
-def train_flops(kind, B):
-    g = 3 if kind == "gru" else 4
-    return 3.0 * 2.0 * B * T * (g * H * (E + H) + H * V)
+def build_model(model, dtype):
+    from showtell_b200.rnn import RNN as GruRNN
+    from showtell_b200.rnn_attn import RNN_Attn as AttnGru
+    from showtell_b200.rnn_attn_LSTM import RNN_Attn as AttnLstm
+    from showtell_b200.rnn_lstm import RNN as LstmRNN
+    torch.manual_seed(1)
+    if model == "gru" or model == "beam":
+        return GruRNN(E, H, V, 1, dtype="fp32" if model == "beam" else dtype)
+    if model == "lstm":
+        return LstmRNN(E, H, V, 1, dtype=dtype)
+    return (AttnGru if model == "attn_gru" else AttnLstm)(E, C, A, H, V, 1, dtype=dtype)
 
 
-def cpu_reference(kind, B, steps, warmup, budget_s=150.0):
-    """Reference algorithm on the host cores: oracle port (explicit-equation torch CPU) of
-    rnn(_lstm).py forward + CrossEntropyLoss + backward.  Bounded: if K+W full batches would not fit
-    in budget_s, each step runs a row-sample of the batch and tokens are counted accordingly."""
+def train_flops(model, B, Pn):
+    """Algorithmic FLOPs of one training step: 3 x forward."""
+    g = 3 if "gru" in model else 4
+    N = B * T
+    if not model.startswith("attn"):
+        return 3.0 * 2.0 * N * (g * H * (E + H) + H * V)
+    step = 2.0 * B * (H * A + Pn * A + Pn * C + C * E + g * H * (E + H))
+    hoist = 2.0 * B * Pn * C * A + 2.0 * N * g * H * E + 2.0 * B * C * H * (2 if g == 4 else 1)
+    return 3.0 * (hoist + T * step + 2.0 * N * H * V) - 2.0 * B * Pn * C * A
+
+
+def cpu_reference(model, B, Pn, steps, warmup, budget_s=150.0):
+    """Reference algorithm on the host cores (oracle port, explicit-equation torch CPU ops, all
+    threads).  Training: forward + loss + backward; beam: rnn.py chain beam, batch 1 per call as the
+    reference requires.  Bounded: the per-step sample shrinks until K+W steps fit in budget_s."""
     from oracle import showtell_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(1)
-    from showtell_b200.rnn import RNN as G
-    from showtell_b200.rnn_lstm import RNN as L_
-    m = (G if kind == "gru" else L_)(E, H, V, 1)
+    m = build_model(model, "fp32")
     p = {k: v.detach().clone() for k, v in m.state_dict().items()}
-    feat, cap, lengths = make_batch(kind, B, 1)
+    feat, cap, lengths = make_batch(model, B if model != "beam" else 64, Pn, 1)
+    if model == "beam":
+        K = Pn
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            O.rnn_beam_chain(p, feat[:1], K, T)
+        per = time.perf_counter() - t0
+        n = max(1, min(64, int(budget_s / max(per, 1e-3) / max(steps + warmup, 1))))
+        for _ in range(warmup):
+            with torch.no_grad():
+                O.rnn_beam_chain(p, feat[:1], K, T)
+        t0 = time.perf_counter()
+        for s in range(steps):
+            with torch.no_grad():
+                for i in range(n):
+                    O.rnn_beam_chain(p, feat[i:i + 1], K, T)
+        dt = (time.perf_counter() - t0) / steps
+        return {"value": n / dt, "unit": "captions/s", "cores": cores, "kind": "port", "ms_per_step": dt * 1e3,
+                "sample": f"{steps} steps of {n} images, beam {K}, max_len {T}, one image per call (torch CPU {torch.__version__})"}
+    probe = min(B, 16)
     t0 = time.perf_counter()
-    O.train_step(p, kind, feat[:32], cap[:32], lengths[:32])
-    per32 = time.perf_counter() - t0
+    O.train_step(p, model, feat[:probe], cap[:probe], lengths[:probe])
+    per = (time.perf_counter() - t0) / probe
     bs = B
-    while bs > 32 and per32 * (bs / 32) * (steps + warmup) > budget_s:
+    while bs > probe and per * bs * (steps + warmup) > budget_s:
         bs //= 2
     f, c, l = feat[:bs], cap[:bs], lengths[:bs]
     for _ in range(warmup):
-        O.train_step(p, kind, f, c, l)
+        O.train_step(p, model, f, c, l)
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.train_step(p, kind, f, c, l)
+        O.train_step(p, model, f, c, l)
     dt = (time.perf_counter() - t0) / steps
-    return {"value": bs * T / dt, "unit": "tokens/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} steps of {bs}/{B} rows x {T} tokens (fwd+CE+bwd, fp32, torch CPU {torch.__version__})",
-            "ms_per_step": dt * 1e3}
+    return {"value": bs * T / dt, "unit": "tokens/s", "cores": cores, "kind": "port", "ms_per_step": dt * 1e3,
+            "sample": f"{steps} steps of {bs}/{B} rows x {T} tokens (fwd+loss+bwd, fp32, torch CPU {torch.__version__})"}
 
 
 def main():
@@ -141,10 +190,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="lstm_train", choices=sorted(WORKLOADS))
-    ap.add_argument("--dtype", default=None, choices=["fp32", "bf16"])
+    ap.add_argument("--dtype", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    kind, B, desc = WORKLOADS[args.workload]
+    model, B, Pn, desc = WORKLOADS[args.workload]
+    is_beam = model == "beam"
+    metric, unit = ("beam_captions_per_s", "captions/s") if is_beam else ("train_tokens_per_s", "tokens/s")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -153,22 +204,20 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        r = cpu_reference(kind, B, args.steps, min(args.warmup, 2))
-        line = {"impl": "reference", "metric": "train_tokens_per_s", "value": r["value"], "unit": "tokens/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 2),
-                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        w = min(args.warmup, 2)
+        r = cpu_reference(model, B, Pn, args.steps, w)
+        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": w, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": desc + " [reference algorithm on host CPU]"},
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                "e2e": {"value": r["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
         return 0
 
     import torch.distributed as dist
-    from showtell_b200 import _lib, ops
-    from showtell_b200.rnn import RNN as GruRNN
-    from showtell_b200.rnn_lstm import RNN as LstmRNN
+    from showtell_b200 import _lib, ops, parallel
 
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -176,40 +225,38 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     lib = _lib.load()
-    dtype = args.dtype or "bf16"
-    torch.manual_seed(1)
-    model = (GruRNN if kind == "gru" else LstmRNN)(E, H, V, 1, dtype=dtype).to(dev)
-    params = [p for p in model.parameters()]
-    feat_h, cap_h, lengths = make_batch(kind, B, 1 + rank)
-    feat_p, cap_p = feat_h.pin_memory(), cap_h.pin_memory()
-    feat_d, cap_d = feat_h.to(dev), cap_h.to(dev)
-    global_tokens = B * T * world
+    dtype = "fp32" if is_beam else args.dtype
+    net = build_model(model, dtype).to(dev)
+    params = [p for p in net.parameters()]
+    if world > 1 and not is_beam:
+        net.grad_reducer = parallel.GradReducer()          # NCCL all-reduce on a side stream
+    feat_h, cap_h, lengths = make_batch(model, B, Pn, 1 + rank)
+    feat_p = feat_h.pin_memory()
+    cap_p = cap_h.pin_memory() if cap_h is not None else None
+    feat_d = feat_h.to(dev)
+    cap_d = cap_h.to(dev) if cap_h is not None else None
+    units_per_step = (B if is_beam else B * T) * world
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-
-    def allreduce_grads():
-        if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
-            off = 0
-            for p in params:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
+    out_host = (torch.empty(B, T, dtype=torch.int64) if is_beam else torch.empty((), dtype=torch.float32)).pin_memory()
 
     def step(f, c):
+        if is_beam:
+            return net.sentence_index(f, beam_size=Pn, max_len=T)                # utils.py:194
         for p in params:
             p.grad = None
-        loss = model.forward_loss(f, c, lengths, global_tokens=global_tokens)
+        if model.startswith("attn"):
+            loss, _ = net.forward_loss(f, c, lengths, alpha_c=1.0, global_tokens=units_per_step,
+                                       global_batch=B * world)
+        else:
+            loss = net.forward_loss(f, c, lengths, global_tokens=units_per_step)
         loss.backward()
-        allreduce_grads()
         return loss
 
     def step_e2e():
         f = feat_p.to(dev, non_blocking=True)
-        c = cap_p.to(dev, non_blocking=True)
-        loss = step(f, c)
-        loss_host.copy_(loss.detach(), non_blocking=True)
-        return loss
+        c = cap_p.to(dev, non_blocking=True) if cap_p is not None else None
+        out = step(f, c)
+        out_host.copy_(out.detach(), non_blocking=True)
 
     def barrier():
         if world > 1:
@@ -253,36 +300,50 @@ def main():
     if sampler:
         sampler.t1 = time.time()
     clocks = sampler.finish() if sampler else None
-    loss_val = float(loss_host)
 
     if rank == 0:
         pk = peaks()
-        # dominant kernel: the vocabulary-projection GEMMs (fwd logits, dW, dH: 3 x 2*N*H*V FLOPs)
-        n_tok = B * T
-        vocab_flops = 2.0 * n_tok * H * V
-        tags = [t for t in ("vocab_fwd", "vocab_dlogits", "vocab_dw", "vocab_dx") if t in ksum]
-        vocab_ms = sum(ksum[t][1] for t in tags) / max(len(tags), 1)
-        ach = vocab_flops / (vocab_ms * 1e-3) / 1e12 if tags else None
-        roof = {"bound": "tensor", "kernel": "vocabulary projection GEMMs (" + " / ".join(tags) + ", mean; each 2*N*H*V FLOPs)",
-                "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": (ach / pk["tf_sustained"]) if ach else None, "traffic": None,
-                "peak_source": pk["src"] + " (bf16 cuBLAS sustained)",
-                "kernels_ms": {k: round(v[1], 4) for k, v in ksum.items()},
-                "step_flops": train_flops(kind, B),
-                "step_tflops": train_flops(kind, B) / (ms * 1e-3) / 1e12}
-        line = {"metric": "train_tokens_per_s", "value": global_tokens / (ms * 1e-3), "unit": "tokens/s",
-                "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32" if dtype == "fp32" else "bf16", "data": "synthetic",
+        kms = {k: round(v[1], 4) for k, v in ksum.items()}
+        if model.startswith("attn"):
+            # dominant per-step kernel: fused attention (HBM/L2-bound): reads att1 (B,P,A) + Fe (B,P,E)
+            esz = 2 if dtype == "bf16" else 4
+            bytes_step = B * Pn * (A + E) * esz
+            tags = [t for t in ("attn_fwd", "attn_bwd") if t in ksum]
+            k_ms = sum(ksum[t][1] for t in tags) / max(len(tags), 1)
+            ach = bytes_step / (k_ms * 1e-3) / 1e9 if tags else None
+            roof = {"bound": "hbm", "kernel": "fused attention step (fwd / bwd mean), algorithmic bytes = B*P*(A+E)*sizeof",
+                    "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"] if ach else None,
+                    "traffic": None, "peak_source": pk["src"] + " (copy bandwidth)"}
+        elif is_beam:
+            roof = {"bound": "tensor", "kernel": "per-step vocabulary projection (fp32 CUDA-core path in round 1)",
+                    "achieved": None, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": None, "traffic": None,
+                    "peak_source": pk["src"]}
+        else:
+            # dominant kernels: the vocabulary-projection GEMMs (each 2*N*H*V FLOPs)
+            vocab_flops = 2.0 * B * T * H * V
+            tags = [t for t in ("vocab_fwd", "vocab_dlogits", "vocab_dw", "vocab_dx") if t in ksum]
+            k_ms = sum(ksum[t][1] for t in tags) / max(len(tags), 1)
+            ach = vocab_flops / (k_ms * 1e-3) / 1e12 if tags else None
+            roof = {"bound": "tensor", "kernel": "vocabulary projection GEMMs (" + " / ".join(tags) + ", mean; each 2*N*H*V FLOPs)",
+                    "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tf_sustained"] if ach else None, "traffic": None,
+                    "peak_source": pk["src"] + " (bf16 cuBLAS sustained)"}
+        roof["kernels_ms"] = kms
+        if not is_beam:
+            roof["step_flops"] = train_flops(model, B, Pn)
+            roof["step_tflops"] = roof["step_flops"] / (ms * 1e-3) / 1e12
+        h2d = feat_p.numel() * 4 + (cap_p.numel() * 8 if cap_p is not None else 0)
+        line = {"metric": metric, "value": units_per_step / (ms * 1e-3), "unit": unit, "n_gpus": world,
+                "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if dtype == "fp32" else "bf16",
+                "data": "synthetic",
                 "config": {"workload": desc, "global_batch": B * world, "seq_len": T, "parallelism": f"dp{world}",
-                           "l2": "flushed between timed steps (256 MiB fill, outside the event pairs)",
-                           "loss": loss_val},
-                "e2e": {"value": global_tokens / (ms_e2e * 1e-3), "unit": "tokens/s",
-                        "h2d_bytes_per_step": feat_p.numel() * 4 + cap_p.numel() * 8, "d2h_bytes_per_step": 4,
-                        "ms_per_step": ms_e2e},
+                           "l2": "flushed between timed steps (256 MiB fill, outside the event pairs)"},
+                "e2e": {"value": units_per_step / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": out_host.numel() * out_host.element_size(), "ms_per_step": ms_e2e},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference(kind, B, 6, 1, budget_s=25.0)
+            r = cpu_reference(model, B, Pn, 5, 1, budget_s=25.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     if world > 1:

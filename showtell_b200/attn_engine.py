@@ -242,7 +242,13 @@ class AttnLossFn(torch.autograd.Function):
         loss = loss + coef * pen_sum.reshape(())
         ctx.names, ctx.grads = names, None
         if need:
+            red = getattr(mod, "grad_reducer", None)       # data parallelism: parallel.GradReducer
+            if red is not None:
+                red.reduce([grads["linear.weight"], grads["linear.bias"]])   # overlaps with the reverse loop
             g2 = attn_backward(mode, P, mod._kind, mod.num_layers, cap, sv, dHs, Gpen=Gpen)
+            if red is not None:
+                red.reduce([g2[n] for n in names if n in g2])
+                red.finish()
             g2.update(grads)
             ctx.grads = g2
         ctx.mark_non_differentiable(alphas)

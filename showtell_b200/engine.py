@@ -222,8 +222,15 @@ class BaseLossFn(torch.autograd.Function):
         loss, dHs, grads = vocab_ce(mode, P, Hs, target, denom, need)
         ctx.names, ctx.grads, ctx.dfeat = names, None, None
         if need:
+            red = getattr(mod, "grad_reducer", None)       # data parallelism: parallel.GradReducer
+            if red is not None:
+                red.reduce([grads["linear.weight"], grads["linear.bias"]])   # overlaps with BPTT below
+            first = set(grads)
             ctx.dfeat = base_backward_from_dHs(mode, P, mod._kind, mod.num_layers, caption_c, bs, layers, dHs,
                                                grads, ctx.needs_input_grad[1], feature_c.shape)
+            if red is not None:
+                red.reduce([grads[n] for n in names if n not in first])
+                red.finish()
             ctx.grads = grads
         return loss
 

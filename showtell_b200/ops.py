@@ -362,25 +362,32 @@ def attn_relayout(f, bf16=False, want_t=True):
     return F, FT, mean_f
 
 
-def attn_step_fwd(rows, Pn, att1, Fe, att2, wf, bf, b_embed, alphas_t, alpha_stride, S, ctx_out, act=ACT_LEAKY):
+def attn_step_fwd(rows, Pn, att1, Fe, att2, wf, bf, b_embed, alphas_t, alpha_stride, S, ctx_out, act=ACT_LEAKY,
+                  tag="attn_fwd"):
     """att1 (B*P, A), Fe (B*P, E) (fp32 or bf16), att2 (rows, A).  alphas_t / ctx_out are (possibly
     strided) views whose first element is row 0; ctx_out row stride = ctx_out.stride(0)."""
     lib = _lib.load()
     A, E = att1.shape[1], Fe.shape[1]
+    tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
     check(lib.st_attn_step_fwd(rows, Pn, A, E, _raw(att1), _raw(Fe), int(att1.dtype == BF16), _raw(att2),
                                ptr(wf, F32), ptr(bf, F32), ptr(b_embed, F32), _raw(alphas_t), alpha_stride,
                                ptr(S, F32), _raw(ctx_out), ctx_out.stride(0), act, stream_ptr()),
           "st_attn_step_fwd")
+    if tok:
+        TIMER.end(tok)
 
 
 def attn_step_bwd(rows, Pn, att1, Fe, att2, wf, alphas_t, alpha_stride, dalpha, dalpha_stride, dctx, de_out,
-                  datt2, act=ACT_LEAKY):
+                  datt2, act=ACT_LEAKY, tag="attn_bwd"):
     lib = _lib.load()
     A, E = att1.shape[1], Fe.shape[1]
+    tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
     check(lib.st_attn_step_bwd(rows, Pn, A, E, _raw(att1), _raw(Fe), int(att1.dtype == BF16), _raw(att2),
                                ptr(wf, F32), _raw(alphas_t), alpha_stride,
                                _raw(dalpha) if dalpha is not None else None, dalpha_stride, _raw(dctx),
                                dctx.stride(0), _raw(de_out), _raw(datt2), act, stream_ptr()), "st_attn_step_bwd")
+    if tok:
+        TIMER.end(tok)
 
 
 def attn_hoist_bwd(bs, Pn, att1, att2_all, de_all, wf, want_t=True, act=ACT_LEAKY):
