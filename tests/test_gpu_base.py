@@ -136,6 +136,22 @@ def test_golden_beam_tree():
             assert abs(float(cost[i, j]) - float(t[f"row{i}.hyp{j}.cost"])) < 1e-4
 
 
+def test_beam_search_module_api():
+    """showtell_b200.beam_search.beam_search mirrors beam_search.py's results (golden fixture)."""
+    from showtell_b200.beam_search import beam_search
+    g = load_golden("gru_tiny")
+    t = load_golden("tree_beam_gru_tiny")
+    K, max_length, end_id, rows, _ = t["meta"].tolist()
+    m = _module(g, torch.device("cuda:0"))
+    res = beam_search(m, torch.from_numpy(g["cnn_feature"]).cuda(), 1, end_id, beam_width=K, num_hypotheses=K,
+                      max_length=max_length)
+    for i in range(rows):
+        assert len(res[i]) == int(t[f"row{i}.n"])
+        for j, h in enumerate(res[i]):
+            assert h.to_sequence_of_values() == t[f"row{i}.hyp{j}.seq"].tolist()
+            assert abs(h.cum_cost - float(t[f"row{i}.hyp{j}.cost"])) < 1e-4
+
+
 def _random_case(kind, E, H, V, L, B, T, seed, ragged, dtype="fp32"):
     torch.manual_seed(seed)
     g = torch.Generator().manual_seed(seed)
