@@ -125,6 +125,9 @@ int st_gather_rows(float* dst, int ld_dst, const float* table, int width, const 
 int st_colsum(float* out, const void* M, int m_is_bf16, int rows, int cols, int ld, int accumulate,
               st_stream_t stream);
 
+/* out[r] = sum_c M[r, c], M bf16 (rows, ld): db_v from the transposed dlogits. */
+int st_rowsum_bf16(float* out, const void* M, int rows, int cols, int ld, st_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Recurrent sequence, forward (the inside of nn.GRU / nn.LSTM over a PackedSequence,
  * rnn.py:32, rnn_lstm.py:30; one call per layer).  Persistent cooperative kernel: each CTA keeps

@@ -44,6 +44,7 @@ _SIGS = {
     "st_pack_inputs_bwd": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _IP, _P]),
     "st_pack_targets": (_I, [_P, _P, _I, _I, _IP, _P]),
     "st_gather_rows": (_I, [_P, _I, _P, _I, _P, _I, _I, _P]),
+    "st_rowsum_bf16": (_I, [_P, _P, _I, _I, _I, _P]),
     "st_colsum": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "st_rnn_seq_fwd": (_I, [_I, _I, _I, _IP, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "st_rnn_seq_bwd": (_I, [_I, _I, _I, _IP, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -7,9 +7,9 @@
 // This is the nn.Linear shape (weights are (out, in)); the transposed products of the backward
 // pass are brought to the same form by the caller with transposed bf16 copies.
 //
-// CTA = 256 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane each), warp 2 =
-// TMEM allocator, warps 4..7 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31 = 32 rows of the
-// 128x128 tile).  6-stage smem ring (A 16 KB + B 16 KB per stage), 2 TMEM accumulator stages
+// CTA = 384 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane each), warp 2 =
+// TMEM allocator, warps 4..11 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31 = 32 rows and one
+// 64-column half of the 128x128 tile; two warps per SM sub-partition hide each other's latency).  6-stage smem ring (A 16 KB + B 16 KB per stage), 2 TMEM accumulator stages
 // (2 x 128 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Epilogues (template parameter):
@@ -30,7 +30,7 @@ namespace st {
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64, UK = 16;
-constexpr int STAGES = 6, ACC_STAGES = 2, NTHREADS = 256;
+constexpr int STAGES = 6, ACC_STAGES = 2, NTHREADS = 384;  // 4 control warps + 8 epilogue warps
 constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;
 constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256;
@@ -81,7 +81,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);  // one arrival per epilogue warp
+      mbar_init(&tempty[i], 8);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -138,7 +138,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {  // ------------------------------------------------------ epilogue
-    const int ew = warp & 3;
+    // 8 warps: warp w owns TMEM lanes 32*(w%4)..+31 (32 rows) and columns 64*((w-4)/4)..+63.
+    const int ew = warp & 3, half = (warp - 4) >> 2;
+    constexpr float LOG2E = 1.4426950408889634f;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -151,106 +153,137 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       float run_m = -FLT_MAX, run_s = 0.f, tl = 0.f;  // EPI_CE_FWD
       bool have_tl = false;
-      int64_t tgt = -1;
-      float lse_r = 0.f;
-      if (EPI != EPI_STORE && row_ok) tgt = p.target[row];
-      if (EPI == EPI_CE_BWD && row_ok) lse_r = p.lse[row];
+      int tgt = -1;
+      float lse_l2 = 0.f;
+      if (EPI != EPI_STORE && row_ok) tgt = (int)p.target[row];
+      if (EPI == EPI_CE_BWD && row_ok) lse_l2 = p.lse[row] * LOG2E;
 
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = half * 2 + cc;
         float v[32];
         tmem_ld32(tbase + c * 32, v);
         const int nb = n0 + c * 32;
+        const bool full = nb + 32 <= p.N;
+        if (EPI != EPI_STORE && nb >= p.N) continue;  // chunk entirely past the vocabulary
+        // bias: uniform (same address in every lane) 128-bit loads on full chunks
+        if (p.bias) {
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+              if (EPI == EPI_STORE) {
+                v[j] = fmaf(p.alpha, v[j], b4.x); v[j + 1] = fmaf(p.alpha, v[j + 1], b4.y);
+                v[j + 2] = fmaf(p.alpha, v[j + 2], b4.z); v[j + 3] = fmaf(p.alpha, v[j + 3], b4.w);
+              } else {
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float bj = (nb + j < p.N) ? p.bias[nb + j] : 0.f;
+              v[j] = (EPI == EPI_STORE) ? fmaf(p.alpha, v[j], bj) : v[j] + bj;
+            }
+          }
+        } else if (EPI == EPI_STORE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+        }
+
         if (EPI == EPI_STORE) {
           if (row_ok) {
             if (p.c_bf16) {
               __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + nb;
-              if (nb + 32 <= p.N && (p.ldc & 7) == 0) {
+              if (full && (p.ldc & 7) == 0) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
                   uint32_t w[4];
 #pragma unroll
                   for (int q = 0; q < 4; ++q) {
-                    float x0 = p.alpha * v[j + 2 * q] + (p.bias ? p.bias[nb + j + 2 * q] : 0.f);
-                    float x1 = p.alpha * v[j + 2 * q + 1] + (p.bias ? p.bias[nb + j + 2 * q + 1] : 0.f);
-                    __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                    __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * q], v[j + 2 * q + 1]);
                     w[q] = *reinterpret_cast<uint32_t*>(&h);
                   }
                   *reinterpret_cast<uint4*>(out + j) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
               } else {
                 for (int j = 0; j < 32; ++j)
-                  if (nb + j < p.N)
-                    out[j] = __float2bfloat16(p.alpha * v[j] + (p.bias ? p.bias[nb + j] : 0.f));
+                  if (nb + j < p.N) out[j] = __float2bfloat16(v[j]);
               }
             } else {
               float* out = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + nb;
-              if (nb + 32 <= p.N && (p.ldc & 3) == 0) {
+              if (full && (p.ldc & 3) == 0) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  float4 o;
-                  o.x = p.alpha * v[j] + (p.bias ? p.bias[nb + j] : 0.f);
-                  o.y = p.alpha * v[j + 1] + (p.bias ? p.bias[nb + j + 1] : 0.f);
-                  o.z = p.alpha * v[j + 2] + (p.bias ? p.bias[nb + j + 2] : 0.f);
-                  o.w = p.alpha * v[j + 3] + (p.bias ? p.bias[nb + j + 3] : 0.f);
-                  *reinterpret_cast<float4*>(out + j) = o;
-                }
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
               } else {
                 for (int j = 0; j < 32; ++j)
-                  if (nb + j < p.N) out[j] = p.alpha * v[j] + (p.bias ? p.bias[nb + j] : 0.f);
+                  if (nb + j < p.N) out[j] = v[j];
               }
             }
           }
         } else if (EPI == EPI_CE_FWD) {
-          float cm = -FLT_MAX;
+          if (!full) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = nb + j;
-            v[j] = (n < p.N) ? v[j] + (p.bias ? p.bias[n] : 0.f) : -FLT_MAX;
-            cm = fmaxf(cm, v[j]);
-            if (n == tgt) { tl = v[j]; have_tl = true; }
+            for (int j = 0; j < 32; ++j)
+              if (nb + j >= p.N) v[j] = -FLT_MAX;
           }
+          if (tgt >= nb && tgt < nb + 32) {  // rare: pick the target logit
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j == tgt) tl = v[j];
+            have_tl = true;
+          }
+          float cm = v[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) cm = fmaxf(cm, v[j]);
           const float nm = fmaxf(run_m, cm);
+          const float nml2 = nm * LOG2E;
           float s = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s += (nb + j < p.N) ? __expf(v[j] - nm) : 0.f;
-          run_s = run_s * __expf(run_m - nm) + s;
+          for (int j = 0; j < 32; ++j) s += exp2f(fmaf(v[j], LOG2E, -nml2));  // exp(-huge) = 0 on masked columns
+          run_s = fmaf(run_s, exp2f(fmaf(run_m, LOG2E, -nml2)), s);
           run_m = nm;
-        } else {  // EPI_CE_BWD
-          float d[32];
+        } else {  // EPI_CE_BWD: d = (softmax - onehot) * scale
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = nb + j;
-            const float logit = v[j] + ((p.bias && n < p.N) ? p.bias[n] : 0.f);
-            d[j] = (n < p.N && row_ok) ? (__expf(logit - lse_r) - (n == tgt ? 1.f : 0.f)) * p.scale : 0.f;
+          for (int j = 0; j < 32; ++j) v[j] = exp2f(fmaf(v[j], LOG2E, -lse_l2)) * p.scale;
+          if (tgt >= nb && tgt < nb + 32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nb + j == tgt) v[j] -= p.scale;
           }
           if (row_ok) {
             __nv_bfloat16* out = p.P + (size_t)row * p.ldp + nb;
-            if (nb + 32 <= p.N && (p.ldp & 7) == 0) {
+            if (full && (p.ldp & 7) == 0) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 uint32_t w[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                  __nv_bfloat162 h = __floats2bfloat162_rn(d[j + 2 * q], d[j + 2 * q + 1]);
+                  __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * q], v[j + 2 * q + 1]);
                   w[q] = *reinterpret_cast<uint32_t*>(&h);
                 }
                 *reinterpret_cast<uint4*>(out + j) = make_uint4(w[0], w[1], w[2], w[3]);
               }
             } else {
               for (int j = 0; j < 32; ++j)
-                if (nb + j < p.N) out[j] = __float2bfloat16(d[j]);
+                if (nb + j < p.N) out[j] = __float2bfloat16(v[j]);
             }
             if (p.PT) {  // transposed copy: lanes are consecutive rows -> 64 B contiguous per column
+              __nv_bfloat16* outT = p.PT + (size_t)nb * p.ldpt + row;
+              if (full) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nb + j < p.N) p.PT[(size_t)(nb + j) * p.ldpt + row] = __float2bfloat16(d[j]);
+                for (int j = 0; j < 32; ++j) outT[(size_t)j * p.ldpt] = __float2bfloat16(v[j]);
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (nb + j < p.N) outT[(size_t)j * p.ldpt] = __float2bfloat16(v[j]);
+              }
             }
           }
         }
       }
       if (EPI == EPI_CE_FWD && row_ok) {
-        const int part = tile / mt;
+        const int part = (tile / mt) * 2 + half;
         p.pmax[(size_t)row * p.npart + part] = run_m;
         p.psum[(size_t)row * p.npart + part] = run_s;
         if (have_tl) p.tlogit[row] = tl;
@@ -351,7 +384,7 @@ int st_vocab_ce_fwd(int M, int V, int H, const void* Hs, int ldh, const void* Wv
   TcParams p{};
   p.M = M; p.N = V; p.K = H;
   p.bias = bv; p.target = target; p.pmax = part_max; p.psum = part_sum; p.tlogit = tlogit;
-  p.npart = (V + BN - 1) / BN;
+  p.npart = 2 * ((V + BN - 1) / BN);
   ST_CUDA_TRY(cudaMemsetAsync(loss_sum, 0, sizeof(float), s));
   ST_TRY(launch_tc<EPI_CE_FWD>(p, Hs, ldh, Wv, ldw, s));
   ce_combine_kernel<<<(M + 127) / 128, 128, 0, s>>>(M, p.npart, part_max, part_sum, tlogit, lse, loss_sum);
@@ -359,7 +392,7 @@ int st_vocab_ce_fwd(int M, int V, int H, const void* Hs, int ldh, const void* Wv
   return ST_OK;
 }
 
-int st_vocab_ce_parts(int V) { return (V + st::BN - 1) / st::BN; }
+int st_vocab_ce_parts(int V) { return 2 * ((V + st::BN - 1) / st::BN); }
 
 int st_vocab_ce_bwd(int M, int V, int H, const void* Hs, int ldh, const void* Wv, int ldw, const float* bv,
                     const int64_t* target, const float* lse, float scale, void* P, int ldp, void* PT, int ldpt,

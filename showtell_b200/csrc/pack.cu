@@ -101,6 +101,29 @@ __global__ void gather_rows_kernel(float* __restrict__ dst, int ld_dst, const fl
   for (int e = threadIdx.x; e < width; e += blockDim.x) d[e] = src[e];
 }
 
+// out[r] = sum_c M[r, c] for a bf16 matrix: one warp per row, 16-byte loads (bias gradient of the
+// vocabulary projection from the transposed dlogits, which are row-contiguous per vocabulary entry).
+__global__ void rowsum_bf16_kernel(float* __restrict__ out, const __nv_bfloat16* __restrict__ M, int rows,
+                                   int cols, int ld) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const __nv_bfloat16* row = M + (size_t)r * ld;
+  float s = 0.f;
+  const int c8 = (((uintptr_t)row & 15) == 0) ? (cols & ~7) : 0;
+  for (int c = lane * 8; c < c8; c += 256) {
+    const uint4 q = *reinterpret_cast<const uint4*>(row + c);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      s += f.x + f.y;
+    }
+  }
+  for (int c = c8 + lane; c < cols; c += 32) s += __bfloat162float(row[c]);
+  s = warp_sum(s);
+  if (lane == 0) out[r] = s;
+}
+
 __global__ void shift_states_kernel(const __grid_constant__ StepTable tab, float* __restrict__ Hprev,
                                     const float* __restrict__ Hs, const float* __restrict__ h0, int H) {
   const int n = blockIdx.x;
@@ -190,6 +213,16 @@ int st_gather_rows(float* dst, int ld_dst, const float* table, int width, const 
   ST_REQUIRE(n >= 1 && width >= 1 && ld_dst >= width && idx_stride >= 1, ST_ERR_BAD_SHAPE, "st_gather_rows: bad shape");
   gather_rows_kernel<<<n, 128, 0, as_stream(stream)>>>(dst, ld_dst, table, width, idx, idx_stride);
   ST_LAUNCH_TRY("gather_rows_kernel");
+  return ST_OK;
+}
+
+int st_rowsum_bf16(float* out, const void* M, int rows, int cols, int ld, st_stream_t stream) {
+  using namespace st;
+  ST_REQUIRE(out && M, ST_ERR_NULL, "st_rowsum_bf16: NULL pointer");
+  ST_REQUIRE(rows >= 1 && cols >= 1 && ld >= cols, ST_ERR_BAD_SHAPE, "st_rowsum_bf16: bad shape");
+  rowsum_bf16_kernel<<<(rows + 7) / 8, 256, 0, as_stream(stream)>>>(out, reinterpret_cast<const __nv_bfloat16*>(M),
+                                                                    rows, cols, ld);
+  ST_LAUNCH_TRY("rowsum_bf16_kernel");
   return ST_OK;
 }
 

@@ -194,7 +194,7 @@ def vocab_ce(mode, P, Hs, target, denom, need):
     if need:
         Pm, PT = ops.vocab_ce_bwd(Hb, Wb, bv, target, lse, 1.0 / denom, tag="vocab_dlogits")
         grads["linear.weight"] = ops.gemm_bf16(PT, HT, tag="vocab_dw")
-        grads["linear.bias"] = ops.colsum(Pm)
+        grads["linear.bias"] = ops.rowsum_bf16(PT)                                    # db_v = row sums of dlogits^T
         dHs = ops.gemm_bf16(Pm, WT, tag="vocab_dx")
     return (loss_sum / denom).reshape(()), dHs, grads
 

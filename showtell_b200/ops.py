@@ -104,6 +104,15 @@ def colsum(M, out=None, accumulate=False):
     return out
 
 
+def rowsum_bf16(M):
+    lib = _lib.load()
+    out = torch.empty(M.shape[0], dtype=F32, device=M.device)
+    import ctypes as C
+    check(lib.st_rowsum_bf16(ptr(out), C.c_void_p(M.data_ptr()), M.shape[0], M.shape[1], M.stride(0), stream_ptr()),
+          "st_rowsum_bf16")
+    return out
+
+
 def _barrier(device):
     return torch.zeros(64, dtype=I32, device=device)
 
