@@ -73,6 +73,15 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   return v;
 }
 
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// One-sided wait of a single thread for a monotonic arrival counter (bounded: traps instead of hanging).
+__device__ __forceinline__ void wait_counter_geq(const int* counter, int target) {
+  for (unsigned spin = 0; ld_acquire_gpu(counter) < target; ++spin)
+    if (spin > (1u << 27)) __trap();
+}
+
 // Device-wide barrier among the CTAs that share `counter` (monotonic: the k-th barrier waits for
 // k * participants arrivals).  Requires all participants co-resident (cooperative launch).
 __device__ __forceinline__ void grid_barrier(int* counter, int target) {

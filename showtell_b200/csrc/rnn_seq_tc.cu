@@ -16,10 +16,13 @@
 // gradients accumulated in registers; after the barrier phase 2 streams the 128 x (G*H) tile of
 // dGh_t through a TMA ring against the resident W_hh^T slice to form dh_{t-1} for the CTA's units.
 //
-// Generic-proxy global stores of step t are read by TMA (async proxy) in step t+1 / phase 2:
-// writers and the reader both issue fence.proxy.async around the device-wide barrier.
+// Generic-proxy global stores of step t are read by TMA (async proxy) in step t+1 / phase 2: the
+// writers publish with red.release.gpu on the batch tile's arrival counter, the single TMA-issuing
+// thread acquires it and issues fence.proxy.async before the loads.
 #include "common.cuh"
 #include "tc_common.cuh"
+
+extern "C" int st_rowsum_bf16(float* out, const void* M, int rows, int cols, int ld, st_stream_t stream);
 
 namespace st {
 namespace {
@@ -68,7 +71,18 @@ __device__ __forceinline__ void st8bf(__nv_bfloat16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// Optional per-step timeline of CTA (0,0) (development aid; NULL in production): 8 slots per step.
+long long* g_timeline = nullptr;
+__device__ __forceinline__ void stamp(long long* tl, int step, int slot) {
+  if (tl != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    tl[step * 8 + slot] = t;
+  }
+}
+
 struct TcFwdParams {
+  long long* tl;
   int H, nsteps, has_h0;
   const float *Gx, *bhh, *h0, *c0;
   float *Hs, *Cs, *gates, *ghn;
@@ -140,13 +154,17 @@ rnn_seq_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
 
   uint32_t ph = 0;       // parity of hfull[] / accbar uses
   bool w_ready = false;
-  int nbar = 0;
   for (int t = 0; t < p.nsteps; ++t) {
     const int nr = min(BT, tab.bs[t] - r0);
     if (nr <= 0) break;
     const bool use_mma = (t > 0) || p.has_h0;
 
     if (warp == 0 && lane == 0 && use_mma) {
+      // h_{t-1} is complete once every epilogue warp of every unit tile of this batch tile has
+      // arrived for step t-1 (8 arrivals per CTA per step, release/acquire on the counter)
+      stamp(p.tl, t, 0);
+      if (t > 0) wait_counter_geq(p.barrier + blockIdx.y, t * 8 * (int)gridDim.x);
+      stamp(p.tl, t, 1);
       proxy_fence_global();
       const CUtensorMap* src = (t == 0) ? &tmH0 : &tmH;
       const int rbase = (t == 0) ? r0 : tab.off[t - 1] + r0;
@@ -158,6 +176,8 @@ rnn_seq_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       constexpr uint32_t idesc = umma_idesc(BT, NC);
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(&hfull[kb], ph);
+        if (kb == 0) stamp(p.tl, t, 2);
+        if (kb == KB - 1) stamp(p.tl, t, 3);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(sA + (size_t)kb * KBLK_A);
         const uint32_t b_addr = smem_u32(sW + (size_t)kb * KBLK_W);
@@ -179,17 +199,19 @@ rnn_seq_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       float acc[G][HALF];
       if (use_mma) {
         mbar_wait(accbar, ph);
+        if (threadIdx.x == 64) stamp(p.tl, t, 4);
         tc_fence_after();
 #pragma unroll
         for (int g = 0; g < G; ++g) tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + g * UT + hf * HALF, acc[g]);
+        if (threadIdx.x == 64) stamp(p.tl, t, 5);
       } else {
 #pragma unroll
         for (int g = 0; g < G; ++g)
 #pragma unroll
           for (int j = 0; j < HALF; ++j) acc[g][j] = 0.f;
       }
+      float go[G][HALF], ghn[HALF];
       if (r_ok) {
-        float go[G][HALF], ghn[HALF];
 #pragma unroll
         for (int j = 0; j < HALF; ++j) {
           if (G == 4) {
@@ -209,23 +231,24 @@ rnn_seq_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
             go[0][j] = rr; go[1][j] = zz; go[2][j] = nn;
           }
         }
+        st8bf(p.Hsb + n * H + uu, hreg);      // the only store the next step depends on
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (threadIdx.x == 64) stamp(p.tl, t, 6);
+      if (lane == 0) red_release_gpu_add(p.barrier + blockIdx.y, 1);  // this warp's part of h_t is published
+      if (threadIdx.x == 64) stamp(p.tl, t, 7);
+      if (r_ok) {                             // off the critical path: fp32 state and saved gates
         st8(p.Hs + n * H + uu, hreg);
-        st8bf(p.Hsb + n * H + uu, hreg);
         if (G == 4) st8(p.Cs + n * H + uu, creg);
         if (p.gates) {
 #pragma unroll
           for (int g = 0; g < G; ++g) st8(p.gates + n * (size_t)(G * H) + g * H + uu, go[g]);
           if (G == 3) st8(p.ghn + n * H + uu, ghn);
         }
-        proxy_fence_global();
       }
-      tc_fence_before();
     }
     if (use_mma) ph ^= 1;
-    if (t + 1 < p.nsteps) {
-      ++nbar;
-      grid_barrier(p.barrier + blockIdx.y, nbar * (int)gridDim.x);
-    }
   }
 
   tc_fence_before();
@@ -238,9 +261,10 @@ rnn_seq_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
 }
 
 // --------------------------------------------------------------------------------------- backward
-constexpr int BSTAGES = 6;
+constexpr int BSTAGES = 9;  // 144 KB of dGh in flight per SM: the phase-2 stream is latency-bound
 
 struct TcBwdParams {
+  long long* tl;
   int H, nsteps;
   const float *h0, *c0, *Hs, *Cs, *gates, *ghn, *dHs;
   __nv_bfloat16 *dG, *dGT, *dGh, *dGhT;  // (N, GH), (GH, ldt); dGh* == dG* for LSTM
@@ -296,87 +320,95 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
   const int q = warp & 3, hf = (warp - 2) >> 2;
   const int row = q * 32 + lane, b = r0 + row;
   const int uu = u0 + hf * HALF;
-  float dhrec[HALF], dcrec[HALF], dbi[G][HALF], dbn[HALF], direct[HALF];
+  float dhrec[HALF], dcrec[HALF], direct[HALF];
 #pragma unroll
-  for (int j = 0; j < HALF; ++j) {
-    dhrec[j] = 0.f; dcrec[j] = 0.f; dbn[j] = 0.f; direct[j] = 0.f;
+  for (int j = 0; j < HALF; ++j) { dhrec[j] = 0.f; dcrec[j] = 0.f; direct[j] = 0.f; }
+  // phase-1 operands of one step, prefetched into registers while the previous phase 2 streams:
+  // pf_dh = dHs row, pf_g = saved gates, pf_a = c_t (LSTM) / gh_n (GRU), pf_b = c_{t-1} / h_{t-1}
+  float pf_dh[HALF], pf_g[G][HALF], pf_a[HALF], pf_b[HALF];
+  auto load_step = [&](int ts) {
+    const int nrs = min(BT, tab.bs[ts] - r0);
+    if (!is_epi || row >= nrs) return;
+    const size_t n = (size_t)tab.off[ts] + b;
+    ld8(p.dHs + n * H + uu, pf_dh);
+    const float* gs = p.gates + n * (size_t)GH + uu;
 #pragma unroll
-    for (int g = 0; g < G; ++g) dbi[g][j] = 0.f;
-  }
+    for (int g = 0; g < G; ++g) ld8(gs + g * H, pf_g[g]);
+    const float* cur = (G == 4) ? p.Cs : p.ghn;
+    const float* hist = (G == 4) ? p.Cs : p.Hs;
+    const float* init = (G == 4) ? p.c0 : p.h0;
+    ld8(cur + n * H + uu, pf_a);
+    if (ts > 0) ld8(hist + ((size_t)tab.off[ts - 1] + b) * H + uu, pf_b);
+    else if (init) ld8(init + (size_t)b * H + uu, pf_b);
+    else {
+#pragma unroll
+      for (int j = 0; j < HALF; ++j) pf_b[j] = 0.f;
+    }
+  };
 
   int stage_p = 0, stage_c = 0;   // ring positions of the producer (warp 0) / MMA issuer (warp 1)
   uint32_t phase_p = 0, phase_c = 0, aph = 0;
-  bool w_ready = false;
+  bool w_ready = false, have_pf = false;
   int nbar = 0;
   for (int t = p.nsteps - 1; t >= 0; --t) {
     const int nr = min(BT, tab.bs[t] - r0);
     if (nr <= 0) continue;
     const bool r_ok = row < nr;
+    if (!have_pf) { load_step(t); have_pf = true; }
 
     // ---------------- phase 1: gate gradients of this CTA's (row, unit) pairs (rnn.py:32 autograd)
+    if (threadIdx.x == 64) stamp(p.tl, t, 0);
+    float da[G][HALF], dan_r[HALF];
     if (is_epi && r_ok) {
       const size_t n = (size_t)tab.off[t] + b;
       float dh[HALF];
-      ld8(p.dHs + n * H + uu, dh);
 #pragma unroll
-      for (int j = 0; j < HALF; ++j) dh[j] += dhrec[j];   // dhrec is 0 for rows not live at t+1
-      float da[G][HALF], dan_r[HALF];
+      for (int j = 0; j < HALF; ++j) dh[j] = pf_dh[j] + dhrec[j];   // dhrec is 0 for rows not live at t+1
       if (G == 4) {
-        float ig[HALF], fg[HALF], gg[HALF], og[HALF], ct[HALF], cp[HALF];
-        const float* gs = p.gates + n * (size_t)(4 * H) + uu;
-        ld8(gs, ig); ld8(gs + H, fg); ld8(gs + 2 * H, gg); ld8(gs + 3 * H, og);
-        ld8(p.Cs + n * H + uu, ct);
-        if (t > 0) ld8(p.Cs + ((size_t)tab.off[t - 1] + b) * H + uu, cp);
-        else if (p.c0) ld8(p.c0 + (size_t)b * H + uu, cp);
-        else {
-#pragma unroll
-          for (int j = 0; j < HALF; ++j) cp[j] = 0.f;
-        }
 #pragma unroll
         for (int j = 0; j < HALF; ++j) {
-          const float tc = tanh_fast(ct[j]);
-          const float dc = fmaf(dh[j] * og[j], 1.f - tc * tc, dcrec[j]);
-          da[0][j] = dc * gg[j] * ig[j] * (1.f - ig[j]);
-          da[1][j] = dc * cp[j] * fg[j] * (1.f - fg[j]);
-          da[2][j] = dc * ig[j] * (1.f - gg[j] * gg[j]);
-          da[G - 1][j] = dh[j] * tc * og[j] * (1.f - og[j]);
-          dcrec[j] = dc * fg[j];
+          const float ig = pf_g[0][j], fg = pf_g[1][j], gg = pf_g[2][j], og = pf_g[G - 1][j];
+          const float tc = tanh_fast(pf_a[j]);
+          const float dc = fmaf(dh[j] * og, 1.f - tc * tc, dcrec[j]);
+          da[0][j] = dc * gg * ig * (1.f - ig);
+          da[1][j] = dc * pf_b[j] * fg * (1.f - fg);
+          da[2][j] = dc * ig * (1.f - gg * gg);
+          da[G - 1][j] = dh[j] * tc * og * (1.f - og);
+          dcrec[j] = dc * fg;
           direct[j] = 0.f;
         }
       } else {
-        float rr[HALF], zz[HALF], nn[HALF], gn[HALF], hp[HALF];
-        const float* gs = p.gates + n * (size_t)(3 * H) + uu;
-        ld8(gs, rr); ld8(gs + H, zz); ld8(gs + 2 * H, nn);
-        ld8(p.ghn + n * H + uu, gn);
-        if (t > 0) ld8(p.Hs + ((size_t)tab.off[t - 1] + b) * H + uu, hp);
-        else if (p.h0) ld8(p.h0 + (size_t)b * H + uu, hp);
-        else {
-#pragma unroll
-          for (int j = 0; j < HALF; ++j) hp[j] = 0.f;
-        }
 #pragma unroll
         for (int j = 0; j < HALF; ++j) {
-          da[2][j] = dh[j] * (1.f - zz[j]) * (1.f - nn[j] * nn[j]);
-          da[1][j] = dh[j] * (hp[j] - nn[j]) * zz[j] * (1.f - zz[j]);
-          da[0][j] = da[2][j] * gn[j] * rr[j] * (1.f - rr[j]);
-          dan_r[j] = da[2][j] * rr[j];
-          direct[j] = dh[j] * zz[j];
-          dbn[j] += dan_r[j];
+          const float rr = pf_g[0][j], zz = pf_g[1][j], nn = pf_g[2][j];
+          da[2][j] = dh[j] * (1.f - zz) * (1.f - nn * nn);
+          da[1][j] = dh[j] * (pf_b[j] - nn) * zz * (1.f - zz);
+          da[0][j] = da[2][j] * pf_a[j] * rr * (1.f - rr);
+          dan_r[j] = da[2][j] * rr;
+          direct[j] = dh[j] * zz;
         }
       }
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        st8bf(p.dG + n * (size_t)GH + g * H + uu, da[g]);
-#pragma unroll
-        for (int j = 0; j < HALF; ++j) {
-          dbi[g][j] += da[g][j];
-          p.dGT[(size_t)(g * H + uu + j) * p.ldt + n] = __float2bfloat16(da[g][j]);
-        }
-      }
+      for (int g = 0; g < G; ++g) st8bf(p.dG + n * (size_t)GH + g * H + uu, da[g]);
       if (G == 3) {
         st8bf(p.dGh + n * (size_t)GH + uu, da[0]);
         st8bf(p.dGh + n * (size_t)GH + H + uu, da[1]);
         st8bf(p.dGh + n * (size_t)GH + 2 * H + uu, dan_r);
+      }
+    }
+    ++nbar;
+    if (is_epi) {  // publish this warp's row-major gate gradients of step t (8 arrivals per CTA per step)
+      __syncwarp();
+      if (threadIdx.x == 64) stamp(p.tl, t, 1);
+      if (lane == 0) red_release_gpu_add(p.barrier + blockIdx.y, 1);
+    }
+    if (is_epi && r_ok) {  // off the critical path: transposed copies for the hoisted weight-gradient GEMMs
+      const size_t n = (size_t)tab.off[t] + b;
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int j = 0; j < HALF; ++j) p.dGT[(size_t)(g * H + uu + j) * p.ldt + n] = __float2bfloat16(da[g][j]);
+      if (G == 3) {
 #pragma unroll
         for (int j = 0; j < HALF; ++j) {
           p.dGhT[(size_t)(uu + j) * p.ldt + n] = __float2bfloat16(da[0][j]);
@@ -384,13 +416,13 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
           p.dGhT[(size_t)(2 * H + uu + j) * p.ldt + n] = __float2bfloat16(dan_r[j]);
         }
       }
-      proxy_fence_global();
     }
-    ++nbar;
-    grid_barrier(p.barrier + blockIdx.y, nbar * (int)gridDim.x);
+    if (t > 0) load_step(t - 1);  // overlaps with the phase-2 stream below
 
     // ---------------- phase 2: dh_{t-1}[rows, own units] = dGh_t[rows, :] . W_hh[:, own units]
     if (warp == 0 && lane == 0) {
+      wait_counter_geq(p.barrier + blockIdx.y, nbar * 8 * (int)gridDim.x);  // all unit tiles wrote dGh_t
+      stamp(p.tl, t, 2);
       proxy_fence_global();
       const int rbase = tab.off[t] + r0;
       for (int kb = 0; kb < KB; ++kb) {
@@ -404,6 +436,8 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
       constexpr uint32_t idesc = umma_idesc(BT, UT);
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(&full[stage_c], phase_c);
+        if (kb == 0) stamp(p.tl, t, 3);
+        if (kb == KB - 1) stamp(p.tl, t, 4);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(sA + (size_t)stage_c * KBLK_A);
         const uint32_t b_addr = smem_u32(sW + (size_t)kb * KBLK_W);
@@ -416,6 +450,7 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
       tc_commit(accbar);
     } else if (is_epi) {
       mbar_wait(accbar, aph);
+      if (threadIdx.x == 64) stamp(p.tl, t, 5);
       tc_fence_after();
       float acc[HALF];
       tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + hf * HALF, acc);
@@ -428,29 +463,9 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
     aph ^= 1;
   }
 
-  if (is_epi) {
-    if (b < tab.bs[0]) {
-      st8(p.dstate + (size_t)b * H + uu, dhrec);
-      if (G == 4) st8(p.dstate + (size_t)(tab.bs[0] + b) * H + uu, dcrec);
-    }
-    // bias gradients: sum the per-row register accumulators over the 32 rows of the warp
-#pragma unroll
-    for (int g = 0; g < G; ++g)
-#pragma unroll
-      for (int j = 0; j < HALF; ++j) {
-        const float s = warp_sum(dbi[g][j]);
-        if (lane == 0) {
-          atomicAdd(p.dbih + g * H + uu + j, s);
-          if (G == 4 || g < 2) atomicAdd(p.dbhh + g * H + uu + j, s);
-        }
-      }
-    if (G == 3) {
-#pragma unroll
-      for (int j = 0; j < HALF; ++j) {
-        const float s = warp_sum(dbn[j]);
-        if (lane == 0) atomicAdd(p.dbhh + 2 * H + uu + j, s);
-      }
-    }
+  if (is_epi && b < tab.bs[0]) {
+    st8(p.dstate + (size_t)b * H + uu, dhrec);
+    if (G == 4) st8(p.dstate + (size_t)(tab.bs[0] + b) * H + uu, dcrec);
   }
   tc_fence_before();
   __syncthreads();
@@ -508,11 +523,13 @@ int launch_tc_bwd(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cu
   ST_REQUIRE((int)(grid.x * grid.y) <= cores && grid.y <= 64, ST_ERR_UNSUPPORTED,
              "rnn_seq_tc_bwd: grid %ux%u is not co-resident (%d CTAs fit)", grid.x, grid.y, cores);
   ST_CUDA_TRY(cudaMemsetAsync(p.barrier, 0, sizeof(int) * 64, s));
-  ST_CUDA_TRY(cudaMemsetAsync(p.dbih, 0, sizeof(float) * GH, s));
-  ST_CUDA_TRY(cudaMemsetAsync(p.dbhh, 0, sizeof(float) * GH, s));
   void* args[] = {(void*)&tmWT, (void*)&tmD, (void*)&tab, (void*)&p};
   ST_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, grid, dim3(NTH), args, smem, s));
   note_launch();
+  // bias gradients = row sums of the transposed gate gradients (contiguous per gate row)
+  ST_TRY(st_rowsum_bf16(p.dbih, p.dGT, GH, N, p.ldt, s));
+  if (p.dGhT != p.dGT) ST_TRY(st_rowsum_bf16(p.dbhh, p.dGhT, GH, N, p.ldt, s));
+  else ST_CUDA_TRY(cudaMemcpyAsync(p.dbhh, p.dbih, sizeof(float) * GH, cudaMemcpyDeviceToDevice, s));
   return ST_OK;
 }
 
@@ -520,6 +537,9 @@ int launch_tc_bwd(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cu
 }  // namespace st
 
 extern "C" {
+
+/* development aid: device buffer of (nsteps * 8) int64 receiving %globaltimer stamps of CTA (0,0) */
+void st_debug_set_timeline(void* dev_ptr) { st::g_timeline = reinterpret_cast<long long*>(dev_ptr); }
 
 int st_rnn_seq_tc_supported(int kind, int H) {
   (void)kind;
@@ -540,7 +560,7 @@ int st_rnn_seq_tc_fwd(int kind, int H, int nsteps, const int* batch_sizes_host, 
   ST_REQUIRE(kind == ST_GRU || Cs, ST_ERR_NULL, "st_rnn_seq_tc_fwd: LSTM needs Cs");
   ST_REQUIRE(kind == ST_LSTM || !gates || ghn, ST_ERR_NULL, "st_rnn_seq_tc_fwd: GRU gates need ghn");
   ST_REQUIRE((h0 == nullptr) == (h0_bf16 == nullptr), ST_ERR_NULL, "st_rnn_seq_tc_fwd: h0 needs both copies");
-  TcFwdParams p{H, nsteps, h0 != nullptr, Gx, bhh, h0, c0, Hs, Cs, gates, ghn,
+  TcFwdParams p{g_timeline, H, nsteps, h0 != nullptr, Gx, bhh, h0, c0, Hs, Cs, gates, ghn,
                 reinterpret_cast<__nv_bfloat16*>(Hs_bf16), barrier};
   return kind == ST_LSTM ? launch_tc_fwd<4>(tab, p, Whh_bf16, h0_bf16, as_stream(stream))
                          : launch_tc_fwd<3>(tab, p, Whh_bf16, h0_bf16, as_stream(stream));
@@ -562,7 +582,7 @@ int st_rnn_seq_tc_bwd(int kind, int H, int nsteps, const int* batch_sizes_host, 
   ST_REQUIRE(kind == ST_LSTM || (ghn && dGh && dGhT), ST_ERR_NULL, "st_rnn_seq_tc_bwd: GRU needs ghn, dGh, dGhT");
   ST_REQUIRE(ldt >= tab.off[nsteps] && ldt % 8 == 0, ST_ERR_BAD_SHAPE, "st_rnn_seq_tc_bwd: ldt=%d", ldt);
   if (kind == ST_LSTM) { dGh = dG; dGhT = dGT; }
-  TcBwdParams p{H, nsteps, h0, c0, Hs, Cs, gates, ghn, dHs,
+  TcBwdParams p{g_timeline, H, nsteps, h0, c0, Hs, Cs, gates, ghn, dHs,
                 reinterpret_cast<__nv_bfloat16*>(dG), reinterpret_cast<__nv_bfloat16*>(dGT),
                 reinterpret_cast<__nv_bfloat16*>(dGh), reinterpret_cast<__nv_bfloat16*>(dGhT), ldt,
                 dbih, dbhh, dstate, barrier};
