@@ -27,8 +27,11 @@ extern "C" int st_rowsum_bf16(float* out, const void* M, int rows, int cols, int
 namespace st {
 namespace {
 
-constexpr int UT = 16, BT = 128, HALF = 8, NTH = 320, MAXKB = 8;
-constexpr uint32_t KBLK_A = BT * 128;  // one 64-wide k-block of a 128-row bf16 tile, bytes
+constexpr int UT = 16, HALF = 8, NTH = 320, MAXKB = 8;
+// Batch-tile height BT (template): 128 rows (UMMA M=128, accumulator row i in TMEM lane i) or 64 rows
+// (UMMA M=64: accumulator row i in lane 32*(i/16) + i%16, so each epilogue warp has 16 live lanes).
+// The per-step operand stream is bound by what ONE SM can pull from L2 (~30 B/clk measured), so the
+// launcher picks 64-row tiles whenever twice as many CTAs are still co-resident: twice the SMs pull.
 
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
@@ -90,13 +93,14 @@ struct TcFwdParams {
   int* barrier;
 };
 
-template <int G>
+template <int G, int BT>
 __global__ void __launch_bounds__(NTH, 1)
 rnn_seq_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmH,
                       const __grid_constant__ CUtensorMap tmH0, const __grid_constant__ StepTable tab,
                       const TcFwdParams p) {
   constexpr int NC = G * UT;                    // accumulator columns
   constexpr uint32_t KBLK_W = NC * 128;         // bytes of one k-block of the W slice
+  constexpr uint32_t KBLK_A = BT * 128;         // bytes of one 64-wide k-block of the h tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int H = p.H, KB = (H + 63) / 64;
@@ -138,7 +142,8 @@ rnn_seq_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   // epilogue role: warps 2..9; lane quarter q = warp % 4, unit half hf
   const bool is_epi = warp >= 2;
   const int q = warp & 3, hf = (warp - 2) >> 2;
-  const int row = q * 32 + lane;                 // row inside the batch tile == TMEM lane
+  const bool lane_ok = (BT == 128) || lane < 16;
+  const int row = (BT == 128) ? q * 32 + lane : q * 16 + lane;   // row of the batch tile held by this TMEM lane
   const int uu = u0 + hf * HALF;                 // first of this thread's 8 hidden units
   float hreg[HALF], creg[HALF], bh[G][HALF];
 #pragma unroll
@@ -146,7 +151,7 @@ rnn_seq_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   if (is_epi) {
 #pragma unroll
     for (int g = 0; g < G; ++g) ld8(p.bhh + g * H + uu, bh[g]);
-    if (r0 + row < tab.bs[0]) {
+    if (lane_ok && r0 + row < tab.bs[0]) {
       if (p.h0) ld8(p.h0 + (size_t)(r0 + row) * H + uu, hreg);
       if (G == 4 && p.c0) ld8(p.c0 + (size_t)(r0 + row) * H + uu, creg);
     }
@@ -189,7 +194,7 @@ rnn_seq_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     }
 
     if (is_epi) {
-      const bool r_ok = row < nr;
+      const bool r_ok = lane_ok && row < nr;
       const size_t n = (size_t)tab.off[t] + r0 + row;
       float gx[G][HALF];
       if (r_ok) {
@@ -274,7 +279,7 @@ struct TcBwdParams {
   int* barrier;
 };
 
-template <int G>
+template <int G, int BT>
 __global__ void __launch_bounds__(NTH, 1)
 rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant__ CUtensorMap tmD,
                       const __grid_constant__ StepTable tab, const TcBwdParams p) {
@@ -282,6 +287,7 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int H = p.H, GH = G * H, KB = (GH + 63) / 64;
   constexpr uint32_t KBLK_W = UT * 128;          // 16 rows x 128 B
+  constexpr uint32_t KBLK_A = BT * 128;          // one k-block of the dGh tile
   uint8_t* sW = smem;                            // [KB][16 rows][128 B]   W_hh^T slice (B operand)
   uint8_t* sA = smem + (size_t)KB * KBLK_W;      // [BSTAGES][128 rows][128 B]  dGh ring (A operand)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)BSTAGES * KBLK_A);
@@ -318,7 +324,8 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
 
   const bool is_epi = warp >= 2;
   const int q = warp & 3, hf = (warp - 2) >> 2;
-  const int row = q * 32 + lane, b = r0 + row;
+  const bool lane_ok = (BT == 128) || lane < 16;
+  const int row = (BT == 128) ? q * 32 + lane : q * 16 + lane, b = r0 + row;
   const int uu = u0 + hf * HALF;
   float dhrec[HALF], dcrec[HALF], direct[HALF];
 #pragma unroll
@@ -328,7 +335,7 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
   float pf_dh[HALF], pf_g[G][HALF], pf_a[HALF], pf_b[HALF];
   auto load_step = [&](int ts) {
     const int nrs = min(BT, tab.bs[ts] - r0);
-    if (!is_epi || row >= nrs) return;
+    if (!is_epi || !lane_ok || row >= nrs) return;
     const size_t n = (size_t)tab.off[ts] + b;
     ld8(p.dHs + n * H + uu, pf_dh);
     const float* gs = p.gates + n * (size_t)GH + uu;
@@ -353,7 +360,7 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
   for (int t = p.nsteps - 1; t >= 0; --t) {
     const int nr = min(BT, tab.bs[t] - r0);
     if (nr <= 0) continue;
-    const bool r_ok = row < nr;
+    const bool r_ok = lane_ok && row < nr;
     if (!have_pf) { load_step(t); have_pf = true; }
 
     // ---------------- phase 1: gate gradients of this CTA's (row, unit) pairs (rnn.py:32 autograd)
@@ -463,7 +470,7 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
     aph ^= 1;
   }
 
-  if (is_epi && b < tab.bs[0]) {
+  if (is_epi && lane_ok && b < tab.bs[0]) {
     st8(p.dstate + (size_t)b * H + uu, dhrec);
     if (G == 4) st8(p.dstate + (size_t)(tab.bs[0] + b) * H + uu, dcrec);
   }
@@ -486,21 +493,22 @@ int coresident(const void* kern, size_t smem, int* out) {
   return ST_OK;
 }
 
-template <int G>
-int launch_tc_fwd(const StepTable& tab, TcFwdParams p, const void* Whh_bf16, const void* h0_bf16, cudaStream_t s) {
+template <int G, int BT>
+int try_tc_fwd(const StepTable& tab, TcFwdParams p, const void* Whh_bf16, const void* h0_bf16, cudaStream_t s,
+               bool* launched) {
   const int H = p.H, KB = (H + 63) / 64, N = tab.off[tab.nsteps], B0 = tab.bs[0];
-  const size_t smem = 1024 + (size_t)KB * KBLK_A + (size_t)KB * (G * UT * 128) + 256;
-  CUtensorMap tmW, tmH, tmH0;
-  ST_TRY(make_tmap(&tmW, Whh_bf16, G * H, H, H, UT, "Whh_bf16"));
-  ST_TRY(make_tmap(&tmH, p.Hsb, N, H, H, BT, "Hs_bf16"));
-  ST_TRY(make_tmap(&tmH0, p.has_h0 ? h0_bf16 : (const void*)p.Hsb, p.has_h0 ? B0 : N, H, H, BT, "h0_bf16"));
-  auto kern = rnn_seq_tc_fwd_kernel<G>;
+  const size_t smem = 1024 + (size_t)KB * (BT * 128) + (size_t)KB * (G * UT * 128) + 256;
+  auto kern = rnn_seq_tc_fwd_kernel<G, BT>;
   ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(H / UT, (B0 + BT - 1) / BT);
   int cores = 0;
   ST_TRY(coresident((const void*)kern, smem, &cores));
-  ST_REQUIRE((int)(grid.x * grid.y) <= cores && grid.y <= 64, ST_ERR_UNSUPPORTED,
-             "rnn_seq_tc_fwd: grid %ux%u is not co-resident (%d CTAs fit)", grid.x, grid.y, cores);
+  *launched = (int)(grid.x * grid.y) <= cores && grid.y <= 64;
+  if (!*launched) return ST_OK;
+  CUtensorMap tmW, tmH, tmH0;
+  ST_TRY(make_tmap(&tmW, Whh_bf16, G * H, H, H, UT, "Whh_bf16"));
+  ST_TRY(make_tmap(&tmH, p.Hsb, N, H, H, BT, "Hs_bf16"));
+  ST_TRY(make_tmap(&tmH0, p.has_h0 ? h0_bf16 : (const void*)p.Hsb, p.has_h0 ? B0 : N, H, H, BT, "h0_bf16"));
   ST_CUDA_TRY(cudaMemsetAsync(p.barrier, 0, sizeof(int) * 64, s));
   void* args[] = {(void*)&tmW, (void*)&tmH, (void*)&tmH0, (void*)&tab, (void*)&p};
   ST_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, grid, dim3(NTH), args, smem, s));
@@ -509,19 +517,28 @@ int launch_tc_fwd(const StepTable& tab, TcFwdParams p, const void* Whh_bf16, con
 }
 
 template <int G>
-int launch_tc_bwd(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cudaStream_t s) {
+int launch_tc_fwd(const StepTable& tab, TcFwdParams p, const void* Whh_bf16, const void* h0_bf16, cudaStream_t s) {
+  bool ok = false;
+  ST_TRY((try_tc_fwd<G, 64>(tab, p, Whh_bf16, h0_bf16, s, &ok)));   // twice the CTAs when they fit
+  if (!ok) ST_TRY((try_tc_fwd<G, 128>(tab, p, Whh_bf16, h0_bf16, s, &ok)));
+  ST_REQUIRE(ok, ST_ERR_UNSUPPORTED, "rnn_seq_tc_fwd: batch %d x H %d is not co-resident", tab.bs[0], p.H);
+  return ST_OK;
+}
+
+template <int G, int BT>
+int try_tc_bwd(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cudaStream_t s, bool* launched) {
   const int H = p.H, GH = G * H, KB = (GH + 63) / 64, N = tab.off[tab.nsteps], B0 = tab.bs[0];
-  const size_t smem = 1024 + (size_t)KB * (UT * 128) + (size_t)BSTAGES * KBLK_A + 256;
-  CUtensorMap tmWT, tmD;
-  ST_TRY(make_tmap(&tmWT, WhhT_bf16, H, GH, GH, UT, "WhhT_bf16"));
-  ST_TRY(make_tmap(&tmD, p.dGh, N, GH, GH, BT, "dGh_bf16"));
-  auto kern = rnn_seq_tc_bwd_kernel<G>;
+  const size_t smem = 1024 + (size_t)KB * (UT * 128) + (size_t)BSTAGES * (BT * 128) + 256;
+  auto kern = rnn_seq_tc_bwd_kernel<G, BT>;
   ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(H / UT, (B0 + BT - 1) / BT);
   int cores = 0;
   ST_TRY(coresident((const void*)kern, smem, &cores));
-  ST_REQUIRE((int)(grid.x * grid.y) <= cores && grid.y <= 64, ST_ERR_UNSUPPORTED,
-             "rnn_seq_tc_bwd: grid %ux%u is not co-resident (%d CTAs fit)", grid.x, grid.y, cores);
+  *launched = (int)(grid.x * grid.y) <= cores && grid.y <= 64;
+  if (!*launched) return ST_OK;
+  CUtensorMap tmWT, tmD;
+  ST_TRY(make_tmap(&tmWT, WhhT_bf16, H, GH, GH, UT, "WhhT_bf16"));
+  ST_TRY(make_tmap(&tmD, p.dGh, N, GH, GH, BT, "dGh_bf16"));
   ST_CUDA_TRY(cudaMemsetAsync(p.barrier, 0, sizeof(int) * 64, s));
   void* args[] = {(void*)&tmWT, (void*)&tmD, (void*)&tab, (void*)&p};
   ST_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, grid, dim3(NTH), args, smem, s));
@@ -530,6 +547,15 @@ int launch_tc_bwd(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cu
   ST_TRY(st_rowsum_bf16(p.dbih, p.dGT, GH, N, p.ldt, s));
   if (p.dGhT != p.dGT) ST_TRY(st_rowsum_bf16(p.dbhh, p.dGhT, GH, N, p.ldt, s));
   else ST_CUDA_TRY(cudaMemcpyAsync(p.dbhh, p.dbih, sizeof(float) * GH, cudaMemcpyDeviceToDevice, s));
+  return ST_OK;
+}
+
+template <int G>
+int launch_tc_bwd(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cudaStream_t s) {
+  bool ok = false;
+  ST_TRY((try_tc_bwd<G, 64>(tab, p, WhhT_bf16, s, &ok)));
+  if (!ok) ST_TRY((try_tc_bwd<G, 128>(tab, p, WhhT_bf16, s, &ok)));
+  ST_REQUIRE(ok, ST_ERR_UNSUPPORTED, "rnn_seq_tc_bwd: batch %d x H %d is not co-resident", tab.bs[0], p.H);
   return ST_OK;
 }
 
