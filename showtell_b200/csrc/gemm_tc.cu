@@ -29,11 +29,18 @@
 namespace st {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, UK = 16;
-constexpr int STAGES = 6, ACC_STAGES = 2, NTHREADS = 384;  // 4 control warps + 8 epilogue warps
-constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;
-constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256;
+constexpr int BM = 128, BK = 64, UK = 16;
+constexpr int ACC_STAGES = 2, NTHREADS = 384;  // 4 control warps + 8 epilogue warps
+constexpr uint32_t A_BYTES = BM * BK * 2;
+// Tile width BN (template): 256 where the problem has enough tiles, else 128.  An SM ingests ~64 B/clk
+// from L2; a 128x128x64 k-block needs 32 KB for 256 MMA clocks (128 B/clk: port-bound at <= 50 % of the
+// tensor pipe), a 128x256x64 k-block 48 KB for 512 clocks (96 B/clk: <= 67 %).
+template <int BN> struct TileCfg {
+  static constexpr uint32_t B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;
+  static constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256;
+};
 
 enum { EPI_STORE = 0, EPI_CE_FWD = 1, EPI_CE_BWD = 2 };
 
@@ -54,10 +61,12 @@ struct TcParams {
   int ldp, ldpt;
 };
 
-template <int EPI>
+template <int EPI, int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
+  constexpr int STAGES = TileCfg<BN>::STAGES;
+  constexpr uint32_t STAGE_BYTES = TileCfg<BN>::STAGE_BYTES, TMEM_COLS = TileCfg<BN>::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
@@ -69,6 +78,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = (p.M + BM - 1) / BM, nt = (p.N + BN - 1) / BN;
   const int ntiles = mt * nt, kb = (p.K + BK - 1) / BK;
+  const bool nfast = nt < mt;  // consecutive tiles walk the shorter dimension: the long operand streams once
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -101,7 +111,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int m0 = (tile % mt) * BM, n0 = (tile / mt) * BN;
+        const int m0 = (nfast ? tile / nt : tile % mt) * BM, n0 = (nfast ? tile % nt : tile / mt) * BN;
         for (int k = 0; k < kb; ++k) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], STAGE_BYTES);
@@ -138,13 +148,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {  // ------------------------------------------------------ epilogue
-    // 8 warps: warp w owns TMEM lanes 32*(w%4)..+31 (32 rows) and columns 64*((w-4)/4)..+63.
+    // 8 warps: warp w owns TMEM lanes 32*(w%4)..+31 (32 rows) and one half of the tile's BN columns.
     const int ew = warp & 3, half = (warp - 4) >> 2;
     constexpr float LOG2E = 1.4426950408889634f;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int m0 = (tile % mt) * BM, n0 = (tile / mt) * BN;
+      const int m0 = (nfast ? tile / nt : tile % mt) * BM, n0 = (nfast ? tile % nt : tile / mt) * BN;
       const int row = m0 + ew * 32 + lane;
       const bool row_ok = row < p.M;
       mbar_wait(&tfull[acc], acc_phase);
@@ -159,8 +169,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (EPI == EPI_CE_BWD && row_ok) lse_l2 = p.lse[row] * LOG2E;
 
 #pragma unroll 1
-      for (int cc = 0; cc < 2; ++cc) {
-        const int c = half * 2 + cc;
+      for (int cc = 0; cc < BN / 64; ++cc) {
+        const int c = half * (BN / 64) + cc;
         float v[32];
         tmem_ld32(tbase + c * 32, v);
         const int nb = n0 + c * 32;
@@ -283,7 +293,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       if (EPI == EPI_CE_FWD && row_ok) {
-        const int part = (tile / mt) * 2 + half;
+        const int part = (n0 / BN) * 2 + half;
         p.pmax[(size_t)row * p.npart + part] = run_m;
         p.psum[(size_t)row * p.npart + part] = run_s;
         if (have_tl) p.tlogit[row] = tl;
@@ -342,21 +352,36 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, int rows, int co
   }
 }
 
-template <int EPI>
-int launch_tc(const TcParams& p, const void* A, int lda, const void* B, int ldb, cudaStream_t s) {
-  ST_REQUIRE(p.M >= 1 && p.N >= 1 && p.K >= 1, ST_ERR_BAD_SHAPE, "gemm_bf16: M=%d N=%d K=%d", p.M, p.N, p.K);
+template <int EPI, int BN>
+int launch_tc_bn(const TcParams& p, const void* A, int lda, const void* B, int ldb, cudaStream_t s, int sms) {
   CUtensorMap tmA, tmB;
   ST_TRY(make_tmap(&tmA, A, p.M, p.K, lda, BM, "A"));
   ST_TRY(make_tmap(&tmB, B, p.N, p.K, ldb, BN, "B"));
-  auto kern = gemm_tc_kernel<EPI>;
-  ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-  int sms = 0;
-  ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
+  auto kern = gemm_tc_kernel<EPI, BN>;
+  ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<BN>::SMEM_BYTES));
   const int ntiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int grid = ntiles < sms ? ntiles : sms;
-  kern<<<grid, NTHREADS, SMEM_BYTES, s>>>(tmA, tmB, p);
+  kern<<<grid, NTHREADS, TileCfg<BN>::SMEM_BYTES, s>>>(tmA, tmB, p);
   ST_LAUNCH_TRY("gemm_tc_kernel");
   return ST_OK;
+}
+
+// Tile width by estimated time: rounds of the persistent grid x clocks per k-block (measured ~600 for a
+// 128-wide and ~750 for a 256-wide tile, both L2-port-bound).
+inline int pick_bn(int M, int N, int sms) {
+  if (N <= 128) return 128;
+  const long mt = (M + BM - 1) / BM;
+  const long r128 = (mt * ((N + 127) / 128) + sms - 1) / sms, r256 = (mt * ((N + 255) / 256) + sms - 1) / sms;
+  return (r256 * 750 <= r128 * 600) ? 256 : 128;
+}
+
+template <int EPI>
+int launch_tc(const TcParams& p, const void* A, int lda, const void* B, int ldb, cudaStream_t s, int bn = 0) {
+  ST_REQUIRE(p.M >= 1 && p.N >= 1 && p.K >= 1, ST_ERR_BAD_SHAPE, "gemm_bf16: M=%d N=%d K=%d", p.M, p.N, p.K);
+  int sms = 0;
+  ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
+  if (bn == 0) bn = pick_bn(p.M, p.N, sms);
+  return bn == 256 ? launch_tc_bn<EPI, 256>(p, A, lda, B, ldb, s, sms) : launch_tc_bn<EPI, 128>(p, A, lda, B, ldb, s, sms);
 }
 
 }  // namespace
@@ -384,15 +409,18 @@ int st_vocab_ce_fwd(int M, int V, int H, const void* Hs, int ldh, const void* Wv
   TcParams p{};
   p.M = M; p.N = V; p.K = H;
   p.bias = bv; p.target = target; p.pmax = part_max; p.psum = part_sum; p.tlogit = tlogit;
-  p.npart = 2 * ((V + BN - 1) / BN);
+  int sms = 0;
+  ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
+  const int bn = pick_bn(M, V, sms);
+  p.npart = 2 * ((V + bn - 1) / bn);   // <= st_vocab_ce_parts(V)
   ST_CUDA_TRY(cudaMemsetAsync(loss_sum, 0, sizeof(float), s));
-  ST_TRY(launch_tc<EPI_CE_FWD>(p, Hs, ldh, Wv, ldw, s));
+  ST_TRY(launch_tc<EPI_CE_FWD>(p, Hs, ldh, Wv, ldw, s, bn));
   ce_combine_kernel<<<(M + 127) / 128, 128, 0, s>>>(M, p.npart, part_max, part_sum, tlogit, lse, loss_sum);
   ST_LAUNCH_TRY("ce_combine_kernel");
   return ST_OK;
 }
 
-int st_vocab_ce_parts(int V) { return 2 * ((V + st::BN - 1) / st::BN); }
+int st_vocab_ce_parts(int V) { return 2 * ((V + 127) / 128); }
 
 int st_vocab_ce_bwd(int M, int V, int H, const void* Hs, int ldh, const void* Wv, int ldw, const float* bv,
                     const int64_t* target, const float* lse, float scale, void* P, int ldp, void* PT, int ldpt,
