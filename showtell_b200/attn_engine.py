@@ -12,7 +12,7 @@ hoisted out of the reverse loop.
 """
 import torch
 
-from . import _lib, ops
+from . import _lib, graphs, ops
 from .engine import Linear, layer_params, vocab_ce, weight_grad
 
 F32, BF16 = torch.float32, torch.bfloat16
@@ -232,25 +232,34 @@ class AttnLossFn(torch.autograd.Function):
         cap = caption.contiguous()
         bs = _check_inputs(f, cap, lengths, mod.nos_filters)
         need = any(ctx.needs_input_grad)
-        Hs, alphas, sv = attn_forward(mode, P, mod._kind, mod.num_layers, f, cap, bs, need)
-        target = ops.pack_targets(cap, bs)
+        kind, L = mod._kind, mod.num_layers
         dt = float(denom_tokens if denom_tokens is not None else sum(bs))
         db = float(denom_batch if denom_batch is not None else f.shape[0])
-        loss, dHs, grads = vocab_ce(mode, P, Hs, target, dt, need)
         coef = float(alpha_c) / (db * f.shape[2])
-        pen_sum, Gpen = ops.attn_penalty(sv["S"], coef)
-        loss = loss + coef * pen_sum.reshape(())
-        ctx.names, ctx.grads = names, None
-        if need:
-            red = getattr(mod, "grad_reducer", None)       # data parallelism: parallel.GradReducer
-            if red is not None:
-                red.reduce([grads["linear.weight"], grads["linear.bias"]])   # overlaps with the reverse loop
-            g2 = attn_backward(mode, P, mod._kind, mod.num_layers, cap, sv, dHs, Gpen=Gpen)
-            if red is not None:
-                red.reduce([g2[n] for n in names if n in g2])
-                red.finish()
-            g2.update(grads)
-            ctx.grads = g2
+        red = getattr(mod, "grad_reducer", None)       # data parallelism: parallel.GradReducer
+
+        def body(feat, capt):
+            Hs, alphas, sv = attn_forward(mode, P, kind, L, feat, capt, bs, need)
+            target = ops.pack_targets(capt, bs)
+            loss, dHs, grads = vocab_ce(mode, P, Hs, target, dt, need)
+            pen_sum, Gpen = ops.attn_penalty(sv["S"], coef)
+            loss = loss + coef * pen_sum.reshape(())
+            g2 = None
+            if need:
+                if red is not None:
+                    red.reduce([grads["linear.weight"], grads["linear.bias"]])   # overlaps with the reverse loop
+                g2 = attn_backward(mode, P, kind, L, capt, sv, dHs, Gpen=Gpen)
+                if red is not None:
+                    red.reduce([g2[n] for n in names if n in g2])
+                    red.finish()
+                g2.update(grads)
+            return loss, alphas, g2
+
+        key = ("attn", mode, kind, L, tuple(bs), tuple(f.shape), tuple(cap.shape), need, dt, db, float(alpha_c),
+               tuple(p.data_ptr() for p in params))
+        loss, alphas, ctx.grads = graphs.run(mod, key, body, (f, cap))
+        ctx.names = names
+        loss, alphas = loss.clone(), alphas.clone()
         ctx.mark_non_differentiable(alphas)
         return loss, alphas
 

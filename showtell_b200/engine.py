@@ -11,7 +11,7 @@ The recurrent kernels keep fp32 state in both modes.
 """
 import torch
 
-from . import _lib, ops
+from . import _lib, graphs, ops
 
 F32 = torch.float32
 
@@ -216,23 +216,32 @@ class BaseLossFn(torch.autograd.Function):
         if len(bs) > caption_c.shape[1]:
             raise ValueError("caption_size exceeds the padded caption length")
         need = any(ctx.needs_input_grad)
+        want_dfeat = bool(ctx.needs_input_grad[1])
         denom = float(denom if denom is not None else sum(bs))
-        Hs, layers = base_forward(mode, P, mod._kind, mod.num_layers, feature_c, caption_c, bs, need)
-        target = ops.pack_targets(caption_c, bs)
-        loss, dHs, grads = vocab_ce(mode, P, Hs, target, denom, need)
-        ctx.names, ctx.grads, ctx.dfeat = names, None, None
-        if need:
-            red = getattr(mod, "grad_reducer", None)       # data parallelism: parallel.GradReducer
-            if red is not None:
-                red.reduce([grads["linear.weight"], grads["linear.bias"]])   # overlaps with BPTT below
-            first = set(grads)
-            ctx.dfeat = base_backward_from_dHs(mode, P, mod._kind, mod.num_layers, caption_c, bs, layers, dHs,
-                                               grads, ctx.needs_input_grad[1], feature_c.shape)
-            if red is not None:
-                red.reduce([grads[n] for n in names if n not in first])
-                red.finish()
-            ctx.grads = grads
-        return loss
+        kind, L = mod._kind, mod.num_layers
+        red = getattr(mod, "grad_reducer", None)       # data parallelism: parallel.GradReducer
+
+        def body(feat, cap):
+            Hs, layers = base_forward(mode, P, kind, L, feat, cap, bs, need)
+            target = ops.pack_targets(cap, bs)
+            loss, dHs, grads = vocab_ce(mode, P, Hs, target, denom, need)
+            dfeat = None
+            if need:
+                if red is not None:
+                    red.reduce([grads["linear.weight"], grads["linear.bias"]])   # overlaps with BPTT below
+                first = set(grads)
+                dfeat = base_backward_from_dHs(mode, P, kind, L, cap, bs, layers, dHs, grads, want_dfeat,
+                                               feat.shape)
+                if red is not None:
+                    red.reduce([grads[n] for n in names if n not in first])
+                    red.finish()
+            return loss, (grads if need else None), dfeat
+
+        key = ("base", mode, kind, L, tuple(bs), tuple(feature_c.shape), tuple(caption_c.shape), need, want_dfeat,
+               denom, tuple(p.data_ptr() for p in params))
+        loss, ctx.grads, ctx.dfeat = graphs.run(mod, key, body, (feature_c, caption_c))
+        ctx.names = names
+        return loss.clone()
 
     @staticmethod
     def backward(ctx, g):

@@ -1,0 +1,68 @@
+"""CUDA-graph replay of a whole training step (forward + loss + backward kernels).
+
+A step is 20-230 kernel launches issued from Python; at the benchmark shapes the GPU work (~1 ms for
+the LSTM step) is no longer than the host time to issue it.  After a step signature -- module,
+parameter storage, shapes, the tuple of batch_sizes -- has been seen twice eagerly, the third call
+captures the identical sequence of C-ABI calls on a capture stream into a `torch.cuda.CUDAGraph`
+and later calls replay it: inputs are copied into static buffers, one graph launch runs every
+kernel (cooperative launches and TMA descriptors included: all buffers come from the graph's
+private pool, so the raw pointers baked into kernel parameters stay valid), outputs are the
+graph's static loss / gradient tensors.
+
+Not used when a gradient reducer is attached (NCCL work on a side stream), while
+`ops.TIMER` records per-kernel events, or when `module.use_cuda_graphs` is False.  One loss per
+module may be outstanding: a second forward_loss before backward() overwrites the static gradients.
+"""
+import torch
+
+from . import ops
+
+_EAGER_CALLS_BEFORE_CAPTURE = 2
+
+
+class _Entry:
+    __slots__ = ("seen", "graph", "static_in", "out", "failed")
+
+    def __init__(self):
+        self.seen, self.graph, self.static_in, self.out, self.failed = 0, None, None, None, False
+
+
+def enabled(mod):
+    return (getattr(mod, "use_cuda_graphs", True) and ops.TIMER is None
+            and getattr(mod, "grad_reducer", None) is None)
+
+
+def run(mod, key, body, inputs):
+    """body(*inputs) -> pytree of tensors (dict / tuple / tensor / None).  Runs it eagerly, or via a
+    captured graph once `key` has been seen often enough."""
+    if not enabled(mod):
+        return body(*inputs)
+    cache = mod.__dict__.setdefault("_step_graphs", {})
+    e = cache.get(key)
+    if e is None:
+        if len(cache) > 16:                      # varying shapes: do not hoard graph pools
+            cache.clear()
+        e = cache[key] = _Entry()
+    if e.graph is not None:
+        for dst, src in zip(e.static_in, inputs):
+            dst.copy_(src, non_blocking=True)
+        e.graph.replay()
+        return e.out
+    e.seen += 1
+    if e.failed or e.seen <= _EAGER_CALLS_BEFORE_CAPTURE:
+        return body(*inputs)
+    try:
+        static_in = [t.clone() for t in inputs]
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, capture_error_mode="relaxed"):
+            out = body(*static_in)
+        e.graph, e.static_in, e.out = graph, static_in, out
+        graph.replay()                            # results of THIS call
+        return e.out
+    except Exception as exc:                      # capture unsupported for this sequence: stay eager
+        e.failed = True
+        import warnings
+        warnings.warn(f"showtell_b200: CUDA-graph capture failed ({exc}); continuing eagerly")
+        torch.cuda.synchronize()
+        return body(*inputs)
