@@ -168,9 +168,12 @@ int st_rnn_seq_bwd(int kind, int H, int nsteps, const int* batch_sizes_host, int
 /* ------------------------------------------------------------------------------------------
  * The same recurrence on the tensor cores (bf16 mode): tcgen05.mma with the W_hh slice resident in
  * shared memory for all steps, h_{t-1} tiles TMA-loaded each step, fp32 accumulators in TMEM, the
- * gate math and the fp32 c / h state carried in registers across steps.  Whole sequences only
- * (persistent cooperative launch); returns ST_ERR_UNSUPPORTED when the shape does not qualify
- * (st_rnn_seq_tc_supported) or the grid is not co-resident -- the caller then uses st_rnn_seq_fwd.
+ * gate math and the fp32 c / h state carried in registers across steps (persistent cooperative
+ * launch over steps [t_begin, t_end) / t_hi-1..t_lo; a partial range resumes from the Hs / Cs rows
+ * of step t_begin-1, resp. from `dstate`, which is also where a partial backward leaves the carried
+ * gradient).  Returns ST_ERR_UNSUPPORTED when the shape does not qualify (st_rnn_seq_tc_supported) or
+ * the grid is not co-resident -- the caller then uses st_rnn_seq_fwd.  dbih / dbhh may be NULL
+ * (skipped; they are only produced by a call that reaches t_lo = 0).
  *   Whh_bf16 (g*H, H) bf16;  h0 (B0,H) fp32 together with its bf16 copy h0_bf16, or both NULL
  *   Hs (N,H) fp32 and Hs_bf16 (N,H) bf16 out; Cs, gates, ghn as in st_rnn_seq_fwd.
  * Backward: WhhT_bf16 (H, g*H) bf16 (the transpose).  Outputs the gate gradients directly as the
@@ -178,11 +181,13 @@ int st_rnn_seq_bwd(int kind, int H, int nsteps, const int* batch_sizes_host, int
  * the bias gradients dbih / dbhh (g*H) and dstate (2, B0, H) = (dh0, dc0).
  * ------------------------------------------------------------------------------------------ */
 int st_rnn_seq_tc_supported(int kind, int H);
-int st_rnn_seq_tc_fwd(int kind, int H, int nsteps, const int* batch_sizes_host, const float* Gx,
+int st_rnn_seq_tc_fwd(int kind, int H, int nsteps, const int* batch_sizes_host, int t_begin, int t_end,
+                      const float* Gx,
                       const void* Whh_bf16, const float* bhh, const float* h0, const void* h0_bf16,
                       const float* c0, float* Hs, void* Hs_bf16, float* Cs, float* gates, float* ghn,
                       int* barrier, st_stream_t stream);
-int st_rnn_seq_tc_bwd(int kind, int H, int nsteps, const int* batch_sizes_host, const void* WhhT_bf16,
+int st_rnn_seq_tc_bwd(int kind, int H, int nsteps, const int* batch_sizes_host, int t_hi, int t_lo,
+                      const void* WhhT_bf16,
                       const float* h0, const float* c0, const float* Hs, const float* Cs, const float* gates,
                       const float* ghn, const float* dHs, void* dG, void* dGT, void* dGh, void* dGhT, int ldt,
                       float* dbih, float* dbhh, float* dstate, int* barrier, st_stream_t stream);

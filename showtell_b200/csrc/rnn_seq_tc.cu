@@ -86,7 +86,7 @@ __device__ __forceinline__ void stamp(long long* tl, int step, int slot) {
 
 struct TcFwdParams {
   long long* tl;
-  int H, nsteps, has_h0;
+  int H, t_begin, t_end, has_h0;
   const float *Gx, *bhh, *h0, *c0;
   float *Hs, *Cs, *gates, *ghn;
   __nv_bfloat16* Hsb;
@@ -151,15 +151,21 @@ rnn_seq_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   if (is_epi) {
 #pragma unroll
     for (int g = 0; g < G; ++g) ld8(p.bhh + g * H + uu, bh[g]);
-    if (lane_ok && r0 + row < tab.bs[0]) {
-      if (p.h0) ld8(p.h0 + (size_t)(r0 + row) * H + uu, hreg);
-      if (G == 4 && p.c0) ld8(p.c0 + (size_t)(r0 + row) * H + uu, creg);
+    if (p.t_begin == 0) {
+      if (lane_ok && r0 + row < tab.bs[0]) {
+        if (p.h0) ld8(p.h0 + (size_t)(r0 + row) * H + uu, hreg);
+        if (G == 4 && p.c0) ld8(p.c0 + (size_t)(r0 + row) * H + uu, creg);
+      }
+    } else if (lane_ok && r0 + row < tab.bs[p.t_begin]) {   // resume: carried state = rows of step t_begin-1
+      const size_t n = (size_t)tab.off[p.t_begin - 1] + r0 + row;
+      if (G == 3) ld8cg(p.Hs + n * H + uu, hreg);
+      if (G == 4) ld8cg(p.Cs + n * H + uu, creg);
     }
   }
 
   uint32_t ph = 0;       // parity of hfull[] / accbar uses
   bool w_ready = false;
-  for (int t = 0; t < p.nsteps; ++t) {
+  for (int t = p.t_begin; t < p.t_end; ++t) {
     const int nr = min(BT, tab.bs[t] - r0);
     if (nr <= 0) break;
     const bool use_mma = (t > 0) || p.has_h0;
@@ -168,7 +174,7 @@ rnn_seq_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       // h_{t-1} is complete once every epilogue warp of every unit tile of this batch tile has
       // arrived for step t-1 (8 arrivals per CTA per step, release/acquire on the counter)
       stamp(p.tl, t, 0);
-      if (t > 0) wait_counter_geq(p.barrier + blockIdx.y, t * 8 * (int)gridDim.x);
+      if (t > p.t_begin) wait_counter_geq(p.barrier + blockIdx.y, (t - p.t_begin) * 8 * (int)gridDim.x);
       stamp(p.tl, t, 1);
       proxy_fence_global();
       const CUtensorMap* src = (t == 0) ? &tmH0 : &tmH;
@@ -270,7 +276,7 @@ constexpr int BSTAGES = 9;  // 144 KB of dGh in flight per SM: the phase-2 strea
 
 struct TcBwdParams {
   long long* tl;
-  int H, nsteps;
+  int H, t_hi, t_lo, nsteps;
   const float *h0, *c0, *Hs, *Cs, *gates, *ghn, *dHs;
   __nv_bfloat16 *dG, *dGT, *dGh, *dGhT;  // (N, GH), (GH, ldt); dGh* == dG* for LSTM
   int ldt;
@@ -330,6 +336,10 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
   float dhrec[HALF], dcrec[HALF], direct[HALF];
 #pragma unroll
   for (int j = 0; j < HALF; ++j) { dhrec[j] = 0.f; dcrec[j] = 0.f; direct[j] = 0.f; }
+  if (is_epi && lane_ok && p.t_hi < p.nsteps && b < tab.bs[p.t_hi]) {   // resume: carried gradient of rows live at t_hi
+    ld8cg(p.dstate + (size_t)b * H + uu, dhrec);
+    if (G == 4) ld8cg(p.dstate + (size_t)(tab.bs[0] + b) * H + uu, dcrec);
+  }
   // phase-1 operands of one step, prefetched into registers while the previous phase 2 streams:
   // pf_dh = dHs row, pf_g = saved gates, pf_a = c_t (LSTM) / gh_n (GRU), pf_b = c_{t-1} / h_{t-1}
   float pf_dh[HALF], pf_g[G][HALF], pf_a[HALF], pf_b[HALF];
@@ -357,7 +367,7 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
   uint32_t phase_p = 0, phase_c = 0, aph = 0;
   bool w_ready = false, have_pf = false;
   int nbar = 0;
-  for (int t = p.nsteps - 1; t >= 0; --t) {
+  for (int t = p.t_hi - 1; t >= p.t_lo; --t) {
     const int nr = min(BT, tab.bs[t] - r0);
     if (nr <= 0) continue;
     const bool r_ok = lane_ok && row < nr;
@@ -424,7 +434,7 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
         }
       }
     }
-    if (t > 0) load_step(t - 1);  // overlaps with the phase-2 stream below
+    if (t > p.t_lo) load_step(t - 1);  // overlaps with the phase-2 stream below
 
     // ---------------- phase 2: dh_{t-1}[rows, own units] = dGh_t[rows, :] . W_hh[:, own units]
     if (warp == 0 && lane == 0) {
@@ -470,7 +480,7 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
     aph ^= 1;
   }
 
-  if (is_epi && lane_ok && b < tab.bs[0]) {
+  if (is_epi && lane_ok && b < tab.bs[p.t_lo]) {
     st8(p.dstate + (size_t)b * H + uu, dhrec);
     if (G == 4) st8(p.dstate + (size_t)(tab.bs[0] + b) * H + uu, dcrec);
   }
@@ -500,7 +510,7 @@ int try_tc_fwd(const StepTable& tab, TcFwdParams p, const void* Whh_bf16, const 
   const size_t smem = 1024 + (size_t)KB * (BT * 128) + (size_t)KB * (G * UT * 128) + 256;
   auto kern = rnn_seq_tc_fwd_kernel<G, BT>;
   ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(H / UT, (B0 + BT - 1) / BT);
+  dim3 grid(H / UT, (tab.bs[p.t_begin] + BT - 1) / BT);
   int cores = 0;
   ST_TRY(coresident((const void*)kern, smem, &cores));
   *launched = (int)(grid.x * grid.y) <= cores && grid.y <= 64;
@@ -531,7 +541,7 @@ int try_tc_bwd(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cudaS
   const size_t smem = 1024 + (size_t)KB * (UT * 128) + (size_t)BSTAGES * (BT * 128) + 256;
   auto kern = rnn_seq_tc_bwd_kernel<G, BT>;
   ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(H / UT, (B0 + BT - 1) / BT);
+  dim3 grid(H / UT, (tab.bs[p.t_lo] + BT - 1) / BT);
   int cores = 0;
   ST_TRY(coresident((const void*)kern, smem, &cores));
   *launched = (int)(grid.x * grid.y) <= cores && grid.y <= 64;
@@ -543,10 +553,12 @@ int try_tc_bwd(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cudaS
   void* args[] = {(void*)&tmWT, (void*)&tmD, (void*)&tab, (void*)&p};
   ST_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, grid, dim3(NTH), args, smem, s));
   note_launch();
-  // bias gradients = row sums of the transposed gate gradients (contiguous per gate row)
-  ST_TRY(st_rowsum_bf16(p.dbih, p.dGT, GH, N, p.ldt, s));
-  if (p.dGhT != p.dGT) ST_TRY(st_rowsum_bf16(p.dbhh, p.dGhT, GH, N, p.ldt, s));
-  else ST_CUDA_TRY(cudaMemcpyAsync(p.dbhh, p.dbih, sizeof(float) * GH, cudaMemcpyDeviceToDevice, s));
+  if (p.t_lo == 0 && p.dbih != nullptr) {
+    // bias gradients = row sums of the transposed gate gradients (contiguous per gate row)
+    ST_TRY(st_rowsum_bf16(p.dbih, p.dGT, GH, N, p.ldt, s));
+    if (p.dGhT != p.dGT) ST_TRY(st_rowsum_bf16(p.dbhh, p.dGhT, GH, N, p.ldt, s));
+    else ST_CUDA_TRY(cudaMemcpyAsync(p.dbhh, p.dbih, sizeof(float) * GH, cudaMemcpyDeviceToDevice, s));
+  }
   return ST_OK;
 }
 
@@ -572,7 +584,8 @@ int st_rnn_seq_tc_supported(int kind, int H) {
   return (H % 16 == 0 && H >= 16 && H <= 64 * st::MAXKB) ? 1 : 0;
 }
 
-int st_rnn_seq_tc_fwd(int kind, int H, int nsteps, const int* batch_sizes_host, const float* Gx,
+int st_rnn_seq_tc_fwd(int kind, int H, int nsteps, const int* batch_sizes_host, int t_begin, int t_end,
+                      const float* Gx,
                       const void* Whh_bf16, const float* bhh, const float* h0, const void* h0_bf16,
                       const float* c0, float* Hs, void* Hs_bf16, float* Cs, float* gates, float* ghn,
                       int* barrier, st_stream_t stream) {
@@ -586,13 +599,16 @@ int st_rnn_seq_tc_fwd(int kind, int H, int nsteps, const int* batch_sizes_host, 
   ST_REQUIRE(kind == ST_GRU || Cs, ST_ERR_NULL, "st_rnn_seq_tc_fwd: LSTM needs Cs");
   ST_REQUIRE(kind == ST_LSTM || !gates || ghn, ST_ERR_NULL, "st_rnn_seq_tc_fwd: GRU gates need ghn");
   ST_REQUIRE((h0 == nullptr) == (h0_bf16 == nullptr), ST_ERR_NULL, "st_rnn_seq_tc_fwd: h0 needs both copies");
-  TcFwdParams p{g_timeline, H, nsteps, h0 != nullptr, Gx, bhh, h0, c0, Hs, Cs, gates, ghn,
+  ST_REQUIRE(0 <= t_begin && t_begin < t_end && t_end <= nsteps, ST_ERR_BAD_SHAPE,
+             "st_rnn_seq_tc_fwd: step range [%d,%d) outside [0,%d)", t_begin, t_end, nsteps);
+  TcFwdParams p{g_timeline, H, t_begin, t_end, h0 != nullptr, Gx, bhh, h0, c0, Hs, Cs, gates, ghn,
                 reinterpret_cast<__nv_bfloat16*>(Hs_bf16), barrier};
   return kind == ST_LSTM ? launch_tc_fwd<4>(tab, p, Whh_bf16, h0_bf16, as_stream(stream))
                          : launch_tc_fwd<3>(tab, p, Whh_bf16, h0_bf16, as_stream(stream));
 }
 
-int st_rnn_seq_tc_bwd(int kind, int H, int nsteps, const int* batch_sizes_host, const void* WhhT_bf16,
+int st_rnn_seq_tc_bwd(int kind, int H, int nsteps, const int* batch_sizes_host, int t_hi, int t_lo,
+                      const void* WhhT_bf16,
                       const float* h0, const float* c0, const float* Hs, const float* Cs, const float* gates,
                       const float* ghn, const float* dHs, void* dG, void* dGT, void* dGh, void* dGhT, int ldt,
                       float* dbih, float* dbhh, float* dstate, int* barrier, st_stream_t stream) {
@@ -602,13 +618,16 @@ int st_rnn_seq_tc_bwd(int kind, int H, int nsteps, const int* batch_sizes_host, 
   ST_REQUIRE(kind == ST_GRU || kind == ST_LSTM, ST_ERR_UNSUPPORTED, "st_rnn_seq_tc_bwd: kind=%d", kind);
   ST_REQUIRE(st_rnn_seq_tc_supported(kind, H), ST_ERR_UNSUPPORTED,
              "st_rnn_seq_tc_bwd: H=%d must be a multiple of 16 and <= %d", H, 64 * MAXKB);
-  ST_REQUIRE(WhhT_bf16 && Hs && gates && dHs && dG && dGT && dbih && dbhh && dstate && barrier, ST_ERR_NULL,
+  ST_REQUIRE(WhhT_bf16 && Hs && gates && dHs && dG && dGT && dstate && barrier, ST_ERR_NULL,
              "st_rnn_seq_tc_bwd: NULL pointer");
+  ST_REQUIRE((dbih == nullptr) == (dbhh == nullptr), ST_ERR_NULL, "st_rnn_seq_tc_bwd: dbih/dbhh go together");
+  ST_REQUIRE(0 <= t_lo && t_lo < t_hi && t_hi <= nsteps, ST_ERR_BAD_SHAPE,
+             "st_rnn_seq_tc_bwd: step range [%d,%d) outside [0,%d)", t_lo, t_hi, nsteps);
   ST_REQUIRE(kind == ST_GRU || Cs, ST_ERR_NULL, "st_rnn_seq_tc_bwd: LSTM needs Cs");
   ST_REQUIRE(kind == ST_LSTM || (ghn && dGh && dGhT), ST_ERR_NULL, "st_rnn_seq_tc_bwd: GRU needs ghn, dGh, dGhT");
   ST_REQUIRE(ldt >= tab.off[nsteps] && ldt % 8 == 0, ST_ERR_BAD_SHAPE, "st_rnn_seq_tc_bwd: ldt=%d", ldt);
   if (kind == ST_LSTM) { dGh = dG; dGhT = dGT; }
-  TcBwdParams p{g_timeline, H, nsteps, h0, c0, Hs, Cs, gates, ghn, dHs,
+  TcBwdParams p{g_timeline, H, t_hi, t_lo, nsteps, h0, c0, Hs, Cs, gates, ghn, dHs,
                 reinterpret_cast<__nv_bfloat16*>(dG), reinterpret_cast<__nv_bfloat16*>(dGT),
                 reinterpret_cast<__nv_bfloat16*>(dGh), reinterpret_cast<__nv_bfloat16*>(dGhT), ldt,
                 dbih, dbhh, dstate, barrier};

@@ -305,21 +305,27 @@ def rnn_seq_tc_supported(kind, H):
     return bool(_lib.load().st_rnn_seq_tc_supported(kind, H))
 
 
-def rnn_seq_tc_fwd(kind, Gx, Whh_b, bhh, bs, *, h0=None, h0_b=None, c0=None, save=True, tag=None):
-    """Tensor-core persistent recurrence.  Returns dict(Hs, Hsb, Cs, gates, ghn) or None when the
-    library reports the shape / grid as unsupported (caller falls back to rnn_seq_fwd)."""
+def rnn_seq_tc_fwd(kind, Gx, Whh_b, bhh, bs, *, h0=None, h0_b=None, c0=None, save=True, t_range=None, out=None,
+                   tag=None):
+    """Tensor-core persistent recurrence over steps t_range (default: all).  Returns dict(Hs, Hsb, Cs,
+    gates, ghn) or None when the library reports the shape / grid as unsupported (caller falls back to
+    rnn_seq_fwd).  `out` = the dict of a previous partial call (same packed buffers)."""
     lib = _lib.load()
     N, H = sum(bs), Whh_b.shape[1]
     dev = Gx.device
-    o = {"Hs": torch.empty(N, H, dtype=F32, device=dev), "Hsb": torch.empty(N, H, dtype=BF16, device=dev),
-         "Cs": torch.empty(N, H, dtype=F32, device=dev) if kind == _lib.ST_LSTM else None,
-         "gates": torch.empty(N, Whh_b.shape[0], dtype=F32, device=dev) if save else None,
-         "ghn": torch.empty(N, H, dtype=F32, device=dev) if (save and kind == _lib.ST_GRU) else None,
-         "barrier": _barrier(dev)}
+    o = out
+    if o is None:
+        o = {"Hs": torch.empty(N, H, dtype=F32, device=dev), "Hsb": torch.empty(N, H, dtype=BF16, device=dev),
+             "Cs": torch.empty(N, H, dtype=F32, device=dev) if kind == _lib.ST_LSTM else None,
+             "gates": torch.empty(N, Whh_b.shape[0], dtype=F32, device=dev) if save else None,
+             "ghn": torch.empty(N, H, dtype=F32, device=dev) if (save and kind == _lib.ST_GRU) else None,
+             "barrier": _barrier(dev)}
+    t0, t1 = t_range if t_range is not None else (0, len(bs))
     tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
-    st = lib.st_rnn_seq_tc_fwd(kind, H, len(bs), int_array(bs), ptr(Gx, F32), ptr(Whh_b, BF16), ptr(bhh, F32),
-                               ptr(h0, F32), ptr(h0_b, BF16), ptr(c0, F32), ptr(o["Hs"]), ptr(o["Hsb"]),
-                               ptr(o["Cs"]), ptr(o["gates"]), ptr(o["ghn"]), ptr(o["barrier"]), stream_ptr())
+    st = lib.st_rnn_seq_tc_fwd(kind, H, len(bs), int_array(bs), t0, t1, ptr(Gx, F32), ptr(Whh_b, BF16),
+                               ptr(bhh, F32), ptr(h0, F32), ptr(h0_b, BF16), ptr(c0, F32), ptr(o["Hs"]),
+                               ptr(o["Hsb"]), ptr(o["Cs"]), ptr(o["gates"]), ptr(o["ghn"]), ptr(o["barrier"]),
+                               stream_ptr())
     if st == -3:
         return None
     check(st, "st_rnn_seq_tc_fwd")
@@ -328,117 +334,32 @@ def rnn_seq_tc_fwd(kind, Gx, Whh_b, bhh, bs, *, h0=None, h0_b=None, c0=None, sav
     return o
 
 
-def rnn_seq_tc_bwd(kind, WhhT_b, bs, saved, dHs, *, h0=None, c0=None, tag=None):
+def rnn_seq_tc_bwd(kind, WhhT_b, bs, saved, dHs, *, h0=None, c0=None, t_range=None, out=None, want_bias=True,
+                   tag=None):
     """Returns dict(dGb, dGT, dGhb, dGhT, dbih, dbhh, dstate) (bf16 GEMM operands) or None if unsupported."""
     lib = _lib.load()
     N, H, GH = sum(bs), WhhT_b.shape[0], WhhT_b.shape[1]
     dev = dHs.device
     ldt = (N + 7) // 8 * 8
-    mk = lambda: (torch.empty(N, GH, dtype=BF16, device=dev), torch.empty(GH, ldt, dtype=BF16, device=dev))
-    dGb, dGT = mk()
-    dGhb, dGhT = mk() if kind == _lib.ST_GRU else (dGb, dGT)
-    o = {"dGb": dGb, "dGT": dGT[:, :N], "dGhb": dGhb, "dGhT": dGhT[:, :N],
-         "dbih": torch.empty(GH, dtype=F32, device=dev), "dbhh": torch.empty(GH, dtype=F32, device=dev),
-         "dstate": torch.zeros(2, bs[0], H, dtype=F32, device=dev), "barrier": _barrier(dev)}
+    o = out
+    if o is None:
+        mk = lambda: (torch.empty(N, GH, dtype=BF16, device=dev), torch.empty(GH, ldt, dtype=BF16, device=dev))
+        dGb, dGT = mk()
+        dGhb, dGhT = mk() if kind == _lib.ST_GRU else (dGb, dGT)
+        o = {"dGb": dGb, "dGT_full": dGT, "dGT": dGT[:, :N], "dGhb": dGhb, "dGhT_full": dGhT, "dGhT": dGhT[:, :N],
+             "dbih": torch.empty(GH, dtype=F32, device=dev) if want_bias else None,
+             "dbhh": torch.empty(GH, dtype=F32, device=dev) if want_bias else None,
+             "dstate": torch.zeros(2, bs[0], H, dtype=F32, device=dev), "barrier": _barrier(dev)}
+    t_hi, t_lo = t_range if t_range is not None else (len(bs), 0)
     tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
-    st = lib.st_rnn_seq_tc_bwd(kind, H, len(bs), int_array(bs), ptr(WhhT_b, BF16), ptr(h0, F32), ptr(c0, F32),
-                               ptr(saved["Hs"], F32), ptr(saved["Cs"]), ptr(saved["gates"], F32),
-                               ptr(saved["ghn"]), ptr(dHs, F32), _raw(dGb), _raw(dGT), _raw(dGhb), _raw(dGhT), ldt,
-                               ptr(o["dbih"]), ptr(o["dbhh"]), ptr(o["dstate"]), ptr(o["barrier"]), stream_ptr())
+    st = lib.st_rnn_seq_tc_bwd(kind, H, len(bs), int_array(bs), t_hi, t_lo, ptr(WhhT_b, BF16), ptr(h0, F32),
+                               ptr(c0, F32), ptr(saved["Hs"], F32), ptr(saved["Cs"]), ptr(saved["gates"], F32),
+                               ptr(saved["ghn"]), ptr(dHs, F32), _raw(o["dGb"]), _raw(o["dGT_full"]),
+                               _raw(o["dGhb"]), _raw(o["dGhT_full"]), ldt, ptr(o["dbih"]), ptr(o["dbhh"]),
+                               ptr(o["dstate"]), ptr(o["barrier"]), stream_ptr())
     if st == -3:
         return None
     check(st, "st_rnn_seq_tc_bwd")
     if tok:
         TIMER.end(tok)
     return o
-
-
-# ----------------------------------------------------------------------------- attention
-ACT_LEAKY, ACT_TANH = 0, 1
-
-
-def attn_relayout(f, bf16=False, want_t=True):
-    """f (B,C,P) fp32 channels-first -> F (B*P, C), FT (C, B*P) or None, mean_f (B,C)."""
-    lib = _lib.load()
-    B, Cc, Pn = f.shape
-    dt = BF16 if bf16 else F32
-    F = torch.empty(B * Pn, Cc, dtype=dt, device=f.device)
-    ld = (B * Pn + 7) // 8 * 8
-    FT = torch.empty(Cc, ld, dtype=dt, device=f.device)[:, :B * Pn] if want_t else None
-    mean_f = torch.empty(B, Cc, dtype=F32, device=f.device)
-    check(lib.st_attn_relayout(ptr(f, F32), B, Cc, Pn, _raw(F), _raw(FT) if want_t else None, ld, int(bf16),
-                               ptr(mean_f), stream_ptr()), "st_attn_relayout")
-    return F, FT, mean_f
-
-
-def attn_step_fwd(rows, Pn, att1, Fe, att2, wf, bf, b_embed, alphas_t, alpha_stride, S, ctx_out, act=ACT_LEAKY,
-                  tag="attn_fwd"):
-    """att1 (B*P, A), Fe (B*P, E) (fp32 or bf16), att2 (rows, A).  alphas_t / ctx_out are (possibly
-    strided) views whose first element is row 0; ctx_out row stride = ctx_out.stride(0)."""
-    lib = _lib.load()
-    A, E = att1.shape[1], Fe.shape[1]
-    tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
-    check(lib.st_attn_step_fwd(rows, Pn, A, E, _raw(att1), _raw(Fe), int(att1.dtype == BF16), _raw(att2),
-                               ptr(wf, F32), ptr(bf, F32), ptr(b_embed, F32), _raw(alphas_t), alpha_stride,
-                               ptr(S, F32), _raw(ctx_out), ctx_out.stride(0), act, stream_ptr()),
-          "st_attn_step_fwd")
-    if tok:
-        TIMER.end(tok)
-
-
-def attn_step_bwd(rows, Pn, att1, Fe, att2, wf, alphas_t, alpha_stride, dalpha, dalpha_stride, dctx, de_out,
-                  datt2, act=ACT_LEAKY, tag="attn_bwd"):
-    lib = _lib.load()
-    A, E = att1.shape[1], Fe.shape[1]
-    tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
-    check(lib.st_attn_step_bwd(rows, Pn, A, E, _raw(att1), _raw(Fe), int(att1.dtype == BF16), _raw(att2),
-                               ptr(wf, F32), _raw(alphas_t), alpha_stride,
-                               _raw(dalpha) if dalpha is not None else None, dalpha_stride, _raw(dctx),
-                               dctx.stride(0), _raw(de_out), _raw(datt2), act, stream_ptr()), "st_attn_step_bwd")
-    if tok:
-        TIMER.end(tok)
-
-
-def attn_hoist_bwd(bs, Pn, att1, att2_all, de_all, wf, want_t=True, act=ACT_LEAKY):
-    """Returns (datt1 (B*P, A), datt1T (A, B*P) or None, dwf (A,)) in att1's storage type."""
-    lib = _lib.load()
-    A = att1.shape[1]
-    BP = att1.shape[0]
-    dev = att1.device
-    datt1 = torch.empty_like(att1)
-    ld = (BP + 7) // 8 * 8
-    dT = torch.empty(A, ld, dtype=att1.dtype, device=dev)[:, :BP] if want_t else None
-    dwf = torch.empty(A, dtype=F32, device=dev)
-    isb = int(att1.dtype == BF16)
-    check(lib.st_attn_hoist_bwd(len(bs), int_array(bs), Pn, A, _raw(att1), isb, ptr(att2_all, F32),
-                                ptr(de_all, F32), ptr(wf, F32), _raw(datt1), _raw(dT) if want_t else None, ld,
-                                isb, ptr(dwf), act, stream_ptr()), "st_attn_hoist_bwd")
-    return datt1, dT, dwf
-
-
-def attn_ctx_all(bs, Pn, F, alphas, want=True, want_t=False):
-    """ctx (N, C) and/or ctxT (C, N) in F's storage type; alphas (B, Tcap, P) fp32."""
-    lib = _lib.load()
-    N, Cc = sum(bs), F.shape[1]
-    dev = F.device
-    ctx = torch.empty(N, Cc, dtype=F.dtype, device=dev) if want else None
-    ld = (N + 7) // 8 * 8
-    cT = torch.empty(Cc, ld, dtype=F.dtype, device=dev)[:, :N] if want_t else None
-    check(lib.st_attn_ctx_all(len(bs), int_array(bs), Pn, Cc, alphas.shape[1], _raw(F), int(F.dtype == BF16),
-                              ptr(alphas, F32), _raw(ctx) if want else None, _raw(cT) if want_t else None, ld,
-                              stream_ptr()), "st_attn_ctx_all")
-    return ctx, cT
-
-
-def attn_penalty(S, coef):
-    lib = _lib.load()
-    pen = torch.empty(1, dtype=F32, device=S.device)
-    G = torch.empty_like(S)
-    check(lib.st_attn_penalty(S.numel(), ptr(S, F32), float(coef), ptr(pen), ptr(G), stream_ptr()),
-          "st_attn_penalty")
-    return pen, G
-
-
-def add_rows(dst, src, rows):
-    lib = _lib.load()
-    check(lib.st_add_rows(_raw(dst), _raw(src), rows, dst.shape[-1], stream_ptr()), "st_add_rows")

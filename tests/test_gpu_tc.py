@@ -102,3 +102,36 @@ def test_rnn_seq_tensor_core_vs_cuda_core(kind, H, lengths, init):
         assert rel_err(tb["dstate"][1], rb["dstate"][1]) < 2e-2
     assert rel_err(tb["dbih"], ops.colsum(rb["dG"])) < 2e-2
     assert rel_err(tb["dbhh"], ops.colsum(rb["dGh"])) < 2e-2
+
+
+@pytest.mark.parametrize("kind", ["gru", "lstm"])
+def test_rnn_seq_tensor_core_stepwise_equals_whole(kind):
+    """Partial step ranges (used by the attention loop) resume from the packed state rows and must
+    reproduce the whole-sequence persistent run bit for bit."""
+    from showtell_b200 import _lib, ops
+    k = _lib.ST_LSTM if kind == "lstm" else _lib.ST_GRU
+    G = 4 if kind == "lstm" else 3
+    H, lengths = 128, [7, 7, 6, 4, 4, 2]
+    bs = _lib.batch_sizes(lengths)
+    N, B0 = sum(bs), bs[0]
+    g = torch.Generator().manual_seed(5)
+    Gx = torch.randn(N, G * H, generator=g).to(DEV)
+    Whh = (torch.randn(G * H, H, generator=g) * 0.08).to(DEV)
+    bhh = (torch.randn(G * H, generator=g) * 0.1).to(DEV)
+    h0 = (torch.randn(B0, H, generator=g) * 0.5).to(DEV)
+    c0 = (torch.randn(B0, H, generator=g) * 0.5).to(DEV) if kind == "lstm" else None
+    dHs = torch.randn(N, H, generator=g).to(DEV)
+    Wb, WT = ops.cast_bf16(Whh, True, True)
+    h0b = h0.bfloat16()
+    whole = ops.rnn_seq_tc_fwd(k, Gx, Wb, bhh, bs, h0=h0, h0_b=h0b, c0=c0)
+    st = None
+    for t in range(len(bs)):
+        st = ops.rnn_seq_tc_fwd(k, Gx, Wb, bhh, bs, h0=h0, h0_b=h0b, c0=c0, t_range=(t, t + 1), out=st)
+    assert torch.equal(st["Hs"], whole["Hs"]) and torch.equal(st["Hsb"], whole["Hsb"])
+    assert torch.equal(st["gates"], whole["gates"])
+    bw = ops.rnn_seq_tc_bwd(k, WT, bs, whole, dHs, h0=h0, c0=c0)
+    bst = None
+    for t in reversed(range(len(bs))):
+        bst = ops.rnn_seq_tc_bwd(k, WT, bs, whole, dHs, h0=h0, c0=c0, t_range=(t + 1, t), out=bst, want_bias=False)
+    assert torch.equal(bst["dGb"], bw["dGb"]) and torch.equal(bst["dGT"], bw["dGT"])
+    assert torch.equal(bst["dstate"], bw["dstate"])
