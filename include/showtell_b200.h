@@ -66,13 +66,14 @@ int st_sgemm(int transA, int transB, int M, int N, int K, float alpha, const flo
 
 /* ------------------------------------------------------------------------------------------
  * bf16 GEMM on the tensor cores (tcgen05.mma, TMEM accumulators, TMA operand loads):
- *   C[M,N] = alpha * A[M,K] . B[N,K]^T + bias[N]        A, B bf16 row-major, K contiguous
+ *   C[M,N] = alpha * A[M,K] . B[N,K]^T + bias[N] + beta * C   A, B bf16 row-major, K contiguous
+ *   (beta != 0 accumulates into an fp32 C)
  * C is fp32 (c_is_bf16 = 0) or bf16.  The bf16-mode replacement of the same nn.Linear call sites
  * as st_sgemm.  A, B 16-byte aligned, lda/ldb multiples of 8; M, N, K arbitrary (TMA zero-fills
  * the tails).
  * ------------------------------------------------------------------------------------------ */
 int st_gemm_bf16(int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
-                 int c_is_bf16, const float* bias, float alpha, st_stream_t stream);
+                 int c_is_bf16, const float* bias, float alpha, float beta, st_stream_t stream);
 
 /* fp32 (rows, cols) -> bf16 copy `dst` (rows, cols) and/or bf16 transpose `dstT` (cols, rows);
  * either may be NULL.  Produces the K-major operands st_gemm_bf16 needs for dX = dY W and

@@ -50,7 +50,7 @@ struct TcParams {
   void* C;
   int ldc, c_bf16;
   const float* bias;  // [N] or null (all epilogues)
-  float alpha;
+  float alpha, beta;   // EPI_STORE fp32: C = alpha*acc + bias + beta*C
   // CE
   const int64_t* target;  // [M]
   float *pmax, *psum, *tlogit;  // fwd: (M, npart) partials, (M) target logit
@@ -224,11 +224,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float* out = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + nb;
               if (full && (p.ldc & 3) == 0) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int j = 0; j < 32; j += 4) {
+                  float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                  if (p.beta != 0.f) {
+                    const float4 c4 = *reinterpret_cast<const float4*>(out + j);
+                    o.x = fmaf(p.beta, c4.x, o.x); o.y = fmaf(p.beta, c4.y, o.y);
+                    o.z = fmaf(p.beta, c4.z, o.z); o.w = fmaf(p.beta, c4.w, o.w);
+                  }
+                  *reinterpret_cast<float4*>(out + j) = o;
+                }
               } else {
                 for (int j = 0; j < 32; ++j)
-                  if (nb + j < p.N) out[j] = v[j];
+                  if (nb + j < p.N) out[j] = (p.beta != 0.f) ? fmaf(p.beta, out[j], v[j]) : v[j];
               }
             }
           }
@@ -390,13 +397,14 @@ int launch_tc(const TcParams& p, const void* A, int lda, const void* B, int ldb,
 extern "C" {
 
 int st_gemm_bf16(int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
-                 int c_is_bf16, const float* bias, float alpha, st_stream_t stream) {
+                 int c_is_bf16, const float* bias, float alpha, float beta, st_stream_t stream) {
   using namespace st;
   ST_REQUIRE(C != nullptr, ST_ERR_NULL, "st_gemm_bf16: C is NULL");
   ST_REQUIRE(ldc >= N, ST_ERR_BAD_SHAPE, "st_gemm_bf16: ldc=%d < N=%d", ldc, N);
   TcParams p{};
   p.M = M; p.N = N; p.K = K;
-  p.C = C; p.ldc = ldc; p.c_bf16 = c_is_bf16; p.bias = bias; p.alpha = alpha;
+  ST_REQUIRE(beta == 0.f || !c_is_bf16, ST_ERR_UNSUPPORTED, "st_gemm_bf16: beta needs an fp32 C");
+  p.C = C; p.ldc = ldc; p.c_bf16 = c_is_bf16; p.bias = bias; p.alpha = alpha; p.beta = beta;
   return launch_tc<EPI_STORE>(p, A, lda, B, ldb, as_stream(stream));
 }
 

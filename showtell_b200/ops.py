@@ -225,7 +225,7 @@ def _raw(t):
     return C.c_void_p(t.data_ptr())
 
 
-def gemm_bf16(A, B, *, bias=None, out_dtype=F32, alpha=1.0, out=None, tag=None):
+def gemm_bf16(A, B, *, bias=None, out_dtype=F32, alpha=1.0, beta=0.0, out=None, tag=None):
     """out[M,N] = alpha * A[M,K] . B[N,K]^T + bias on tcgen05 tensor cores.  A, B bf16 with unit inner
     stride and row strides that are multiples of 8."""
     lib = _lib.load()
@@ -240,7 +240,8 @@ def gemm_bf16(A, B, *, bias=None, out_dtype=F32, alpha=1.0, out=None, tag=None):
         out = torch.empty(M, N, dtype=out_dtype, device=A.device)
     tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
     check(lib.st_gemm_bf16(M, N, K, _raw(A), A.stride(0), _raw(B), B.stride(0), _raw(out), out.stride(0),
-                           int(out.dtype == BF16), ptr(bias, F32), float(alpha), stream_ptr()), "st_gemm_bf16")
+                           int(out.dtype == BF16), ptr(bias, F32), float(alpha), float(beta), stream_ptr()),
+          "st_gemm_bf16")
     if tok:
         TIMER.end(tok)
     return out
@@ -363,3 +364,94 @@ def rnn_seq_tc_bwd(kind, WhhT_b, bs, saved, dHs, *, h0=None, c0=None, t_range=No
     if tok:
         TIMER.end(tok)
     return o
+
+
+# ----------------------------------------------------------------------------- attention
+ACT_LEAKY, ACT_TANH = 0, 1
+
+
+def attn_relayout(f, bf16=False, want_t=True):
+    """f (B,C,P) fp32 channels-first -> F (B*P, C), FT (C, B*P) or None, mean_f (B,C)."""
+    lib = _lib.load()
+    B, Cc, Pn = f.shape
+    dt = BF16 if bf16 else F32
+    F = torch.empty(B * Pn, Cc, dtype=dt, device=f.device)
+    ld = (B * Pn + 7) // 8 * 8
+    FT = torch.empty(Cc, ld, dtype=dt, device=f.device)[:, :B * Pn] if want_t else None
+    mean_f = torch.empty(B, Cc, dtype=F32, device=f.device)
+    check(lib.st_attn_relayout(ptr(f, F32), B, Cc, Pn, _raw(F), _raw(FT) if want_t else None, ld, int(bf16),
+                               ptr(mean_f), stream_ptr()), "st_attn_relayout")
+    return F, FT, mean_f
+
+
+def attn_step_fwd(rows, Pn, att1, Fe, att2, wf, bf, b_embed, alphas_t, alpha_stride, S, ctx_out, act=ACT_LEAKY,
+                  tag="attn_fwd"):
+    """att1 (B*P, A), Fe (B*P, E) (fp32 or bf16), att2 (rows, A).  alphas_t / ctx_out are (possibly
+    strided) views whose first element is row 0; ctx_out row stride = ctx_out.stride(0)."""
+    lib = _lib.load()
+    A, E = att1.shape[1], Fe.shape[1]
+    tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
+    check(lib.st_attn_step_fwd(rows, Pn, A, E, _raw(att1), _raw(Fe), int(att1.dtype == BF16), _raw(att2),
+                               ptr(wf, F32), ptr(bf, F32), ptr(b_embed, F32), _raw(alphas_t), alpha_stride,
+                               ptr(S, F32), _raw(ctx_out), ctx_out.stride(0), act, stream_ptr()),
+          "st_attn_step_fwd")
+    if tok:
+        TIMER.end(tok)
+
+
+def attn_step_bwd(rows, Pn, att1, Fe, att2, wf, alphas_t, alpha_stride, dalpha, dalpha_stride, dctx, de_out,
+                  datt2, act=ACT_LEAKY, tag="attn_bwd"):
+    lib = _lib.load()
+    A, E = att1.shape[1], Fe.shape[1]
+    tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
+    check(lib.st_attn_step_bwd(rows, Pn, A, E, _raw(att1), _raw(Fe), int(att1.dtype == BF16), _raw(att2),
+                               ptr(wf, F32), _raw(alphas_t), alpha_stride,
+                               _raw(dalpha) if dalpha is not None else None, dalpha_stride, _raw(dctx),
+                               dctx.stride(0), _raw(de_out), _raw(datt2), act, stream_ptr()), "st_attn_step_bwd")
+    if tok:
+        TIMER.end(tok)
+
+
+def attn_hoist_bwd(bs, Pn, att1, att2_all, de_all, wf, want_t=True, act=ACT_LEAKY):
+    """Returns (datt1 (B*P, A), datt1T (A, B*P) or None, dwf (A,)) in att1's storage type."""
+    lib = _lib.load()
+    A = att1.shape[1]
+    BP = att1.shape[0]
+    dev = att1.device
+    datt1 = torch.empty_like(att1)
+    ld = (BP + 7) // 8 * 8
+    dT = torch.empty(A, ld, dtype=att1.dtype, device=dev)[:, :BP] if want_t else None
+    dwf = torch.empty(A, dtype=F32, device=dev)
+    isb = int(att1.dtype == BF16)
+    check(lib.st_attn_hoist_bwd(len(bs), int_array(bs), Pn, A, _raw(att1), isb, ptr(att2_all, F32),
+                                ptr(de_all, F32), ptr(wf, F32), _raw(datt1), _raw(dT) if want_t else None, ld,
+                                isb, ptr(dwf), act, stream_ptr()), "st_attn_hoist_bwd")
+    return datt1, dT, dwf
+
+
+def attn_ctx_all(bs, Pn, F, alphas, want=True, want_t=False):
+    """ctx (N, C) and/or ctxT (C, N) in F's storage type; alphas (B, Tcap, P) fp32."""
+    lib = _lib.load()
+    N, Cc = sum(bs), F.shape[1]
+    dev = F.device
+    ctx = torch.empty(N, Cc, dtype=F.dtype, device=dev) if want else None
+    ld = (N + 7) // 8 * 8
+    cT = torch.empty(Cc, ld, dtype=F.dtype, device=dev)[:, :N] if want_t else None
+    check(lib.st_attn_ctx_all(len(bs), int_array(bs), Pn, Cc, alphas.shape[1], _raw(F), int(F.dtype == BF16),
+                              ptr(alphas, F32), _raw(ctx) if want else None, _raw(cT) if want_t else None, ld,
+                              stream_ptr()), "st_attn_ctx_all")
+    return ctx, cT
+
+
+def attn_penalty(S, coef):
+    lib = _lib.load()
+    pen = torch.empty(1, dtype=F32, device=S.device)
+    G = torch.empty_like(S)
+    check(lib.st_attn_penalty(S.numel(), ptr(S, F32), float(coef), ptr(pen), ptr(G), stream_ptr()),
+          "st_attn_penalty")
+    return pen, G
+
+
+def add_rows(dst, src, rows):
+    lib = _lib.load()
+    check(lib.st_add_rows(_raw(dst), _raw(src), rows, dst.shape[-1], stream_ptr()), "st_add_rows")
