@@ -210,8 +210,11 @@ int st_shift_states(float* Hprev, const float* Hs, const float* h0, int H, int n
  *   e_p = w_f . act(att1[b,p,:] + att2[b,:]) + b_f;  alpha = softmax_P(e)            (rnn_attn.py:25-26)
  *   ctx_out[b,:E] = sum_p alpha_p Fe[b,p,:] + b_embed   (= embed(sum_p alpha_p f_p), rnn_attn.py:29,70)
  *   alphas[b*alpha_stride + p] = alpha_p (the caller points it at alphas[:, t, :]);  S[b,p] += alpha_p
+ *   ctx_out_bf16 (optional): bf16 copy of ctx_out, the A operand of the tensor-core W_ih[:,E:] product
  * st_attn_step_bwd: dalpha_p = <dctx[b,:], Fe[b,p,:]> + dalpha[b*dalpha_stride + p] (may be NULL);
  *   de = alpha * (dalpha - sum alpha dalpha) -> de_out (rows,P);  datt2 (rows,A) = sum_p de_p w_f act'(.)
+ *   (+ optional bf16 copy datt2_bf16 (rows,A)).  Rows whose A*sizeof and E*sizeof are 512/1024/2048 bytes
+ *   run the streaming kernels (bulk-async-copy ring, attn_stream.cu), other shapes a generic kernel.
  * st_attn_hoist_bwd (after the loop; de (N,P), att2 (N,A) packed time-major):
  *   datt1[b,p,a] = w_f[a] sum_t de[t,b,p] act'(att1[b,p,a] + att2[t,b,a]) (+ transposed copy),
  *   dwf[a] = sum_{t,b,p} de act(.)
@@ -223,11 +226,12 @@ int st_attn_relayout(const float* f, int B, int C, int P, void* F, void* FT, int
                      float* mean_f, st_stream_t stream);
 int st_attn_step_fwd(int rows, int P, int A, int E, const void* att1, const void* Fe, int in_bf16,
                      const float* att2, const float* wf, const float* bf, const float* b_embed, float* alphas,
-                     int alpha_stride, float* S, float* ctx_out, int ld_ctx, int act, st_stream_t stream);
+                     int alpha_stride, float* S, float* ctx_out, int ld_ctx, void* ctx_out_bf16, int ld_ctx_bf16,
+                     int act, st_stream_t stream);
 int st_attn_step_bwd(int rows, int P, int A, int E, const void* att1, const void* Fe, int in_bf16,
                      const float* att2, const float* wf, const float* alphas, int alpha_stride,
                      const float* dalpha, int dalpha_stride, const float* dctx, int ld_dctx, float* de_out,
-                     float* datt2, int act, st_stream_t stream);
+                     float* datt2, void* datt2_bf16, int act, st_stream_t stream);
 int st_attn_hoist_bwd(int nsteps, const int* batch_sizes_host, int P, int A, const void* att1, int in_bf16,
                       const float* att2, const float* de, const float* wf, void* datt1, void* datt1T, int ldt,
                       int out_bf16, float* dwf, int act, st_stream_t stream);

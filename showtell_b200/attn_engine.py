@@ -31,6 +31,17 @@ def _lin_small(x, W, bias=None, out=None, beta=0.0):
     return ops.sgemm(x, W, transB=True, bias=bias, out=out, beta=beta)
 
 
+def _use_tc(mode, kind, P, B):
+    """bf16 mode runs the per-step products and the recurrence on the tensor-core kernels when the
+    shapes qualify (TMA operands need 16-byte rows; the persistent recurrent grid must be co-resident)."""
+    if mode != "bf16":
+        return False
+    H = P["unit.weight_hh_l0"].shape[1]
+    E = P["embeddings.weight"].shape[1]
+    A = P["attn.decoder_att.weight"].shape[0]
+    return (E % 8 == 0 and A % 8 == 0 and H % 8 == 0 and ops.rnn_seq_tc_fits(kind, H, B))
+
+
 def attn_forward(mode, P, kind, L, feature, caption, bs, save):
     """Returns (Hs_top (N,H), alphas (B,Tcap,P), saved dict)."""
     B, C, Pn = feature.shape
@@ -38,7 +49,8 @@ def attn_forward(mode, P, kind, L, feature, caption, bs, save):
     Tcap = caption.shape[1]
     E = P["embeddings.weight"].shape[1]
     dev = feature.device
-    sv = {"bs": bs, "off": off, "Pn": Pn, "B": B}
+    tc = _use_tc(mode, kind, P, B)
+    sv = {"bs": bs, "off": off, "Pn": Pn, "B": B, "tc": tc}
 
     F, FT, mean_f = ops.attn_relayout(feature, bf16=(mode == "bf16"), want_t=(save and mode == "bf16"))
     sv.update(F=F, FT=FT, mean_f=mean_f)
@@ -56,30 +68,64 @@ def attn_forward(mode, P, kind, L, feature, caption, bs, save):
     # layer-0 input rows [emb(caption[:, t]) | embed(ctx_t)]  (rnn_attn.py:70: no input/target shift)
     X0 = ops.pack_inputs(P["embeddings.weight"], None, caption, bs, False, width=2 * E)
     Wih0, _, bih0, _ = layer_params(P, 0)
-    Gx = [ops.sgemm(X0[:, :E], Wih0[:, :E], transB=True, bias=bih0, tag="ih_fwd")]    # emb half hoisted
     H = P["unit.weight_hh_l0"].shape[1]
     G = Wih0.shape[0]
-    for l in range(1, L):
-        Gx.append(torch.empty(N, G, dtype=F32, device=dev))
     alphas = torch.zeros(B, Tcap, Pn, dtype=F32, device=dev)                          # rnn_attn.py:65
     S = torch.zeros(B, Pn, dtype=F32, device=dev)
-    att2_all = torch.empty(N, P["attn.decoder_att.weight"].shape[0], dtype=F32, device=dev)
+    A = P["attn.decoder_att.weight"].shape[0]
+    att2_all = torch.empty(N, A, dtype=F32, device=dev)
     outs = [None] * L
     wf = P["attn.full_att.weight"].reshape(-1)
+    bd = P["attn.decoder_att.bias"]
+    if tc:
+        # bf16 K-major operand copies (and the transposes the reverse loop needs)
+        W = {"d": ops.cast_bf16(P["attn.decoder_att.weight"], True, save),
+             "ihe": ops.cast_bf16(Wih0[:, :E], True, save), "ihc": ops.cast_bf16(Wih0[:, E:], True, save)}
+        for l in range(L):
+            Wih, Whh, _, _ = layer_params(P, l)
+            W[f"hh{l}"] = ops.cast_bf16(Whh, True, save)
+            if l > 0:
+                W[f"ih{l}"] = ops.cast_bf16(Wih, True, save)
+        sv["W"] = W
+        Xe_b, _ = ops.cast_bf16(X0[:, :E], True, False)
+        Gx = [ops.gemm_bf16(Xe_b, W["ihe"][0], bias=bih0, tag="ih_fwd")]              # emb half hoisted
+        h0_b, _ = ops.cast_bf16(h0, True, False)
+        ctx_b = torch.empty(N, E, dtype=BF16, device=dev)
+    else:
+        Gx = [ops.sgemm(X0[:, :E], Wih0[:, :E], transB=True, bias=bih0, tag="ih_fwd")]
+    for l in range(1, L):
+        Gx.append(torch.empty(N, G, dtype=F32, device=dev))
     for t in range(T):
         bt, o0 = bs[t], off[t]
         o1 = o0 + bt
-        q = h0[:bt] if t == 0 else outs[L - 1]["Hs"][off[t - 1]:off[t - 1] + bt]      # pre-step top hidden, :69
-        _lin_small(q, P["attn.decoder_att.weight"], P["attn.decoder_att.bias"], out=att2_all[o0:o1])
+        # query = pre-step top-layer hidden (rnn_attn.py:69)
+        if tc:
+            q_b = h0_b[:bt] if t == 0 else outs[L - 1]["Hsb"][off[t - 1]:off[t - 1] + bt]
+            ops.gemm_bf16(q_b, W["d"][0], bias=bd, out=att2_all[o0:o1], tag="att2_fwd")
+        else:
+            q = h0[:bt] if t == 0 else outs[L - 1]["Hs"][off[t - 1]:off[t - 1] + bt]
+            _lin_small(q, P["attn.decoder_att.weight"], bd, out=att2_all[o0:o1])
         ops.attn_step_fwd(bt, Pn, att1, Fe, att2_all[o0:o1], wf, P["attn.full_att.bias"], P["embed.bias"],
-                          alphas[:, t, :], Tcap * Pn, S, X0[o0:o1, E:])
-        _lin_small(X0[o0:o1, E:], Wih0[:, E:], out=Gx[0][o0:o1], beta=1.0)           # + W_ih[:, E:] embed(ctx)
+                          alphas[:, t, :], Tcap * Pn, S, X0[o0:o1, E:], ctx_bf16=ctx_b[o0:o1] if tc else None)
+        # + W_ih[:, E:] embed(ctx)
+        if tc:
+            ops.gemm_bf16(ctx_b[o0:o1], W["ihc"][0], out=Gx[0][o0:o1], beta=1.0, tag="ihc_fwd")
+        else:
+            _lin_small(X0[o0:o1, E:], Wih0[:, E:], out=Gx[0][o0:o1], beta=1.0)
         for l in range(L):
             Wih, Whh, bih, bhh = layer_params(P, l)
-            if l > 0:
-                _lin_small(outs[l - 1]["Hs"][o0:o1], Wih, bih, out=Gx[l][o0:o1])
-            outs[l] = ops.rnn_seq_fwd(kind, Gx[l], Whh, bhh, bs, h0=h0, c0=c0, save=save, t_range=(t, t + 1),
-                                      out=outs[l])
+            if tc:
+                if l > 0:
+                    ops.gemm_bf16(outs[l - 1]["Hsb"][o0:o1], W[f"ih{l}"][0], bias=bih, out=Gx[l][o0:o1])
+                outs[l] = ops.rnn_seq_tc_fwd(kind, Gx[l], W[f"hh{l}"][0], bhh, bs, h0=h0, h0_b=h0_b, c0=c0, save=save,
+                                             t_range=(t, t + 1), out=outs[l], tag="step_fwd")
+                if outs[l] is None:
+                    raise RuntimeError("rnn_seq_tc_fwd refused a shape that rnn_seq_tc_fits accepted")
+            else:
+                if l > 0:
+                    _lin_small(outs[l - 1]["Hs"][o0:o1], Wih, bih, out=Gx[l][o0:o1])
+                outs[l] = ops.rnn_seq_fwd(kind, Gx[l], Whh, bhh, bs, h0=h0, c0=c0, save=save, t_range=(t, t + 1),
+                                          out=outs[l], tag="step_fwd")
     sv.update(X0=X0, outs=outs, att2_all=att2_all, alphas=alphas, S=S, enc=enc)
     return outs[L - 1]["Hs"], alphas, sv
 
@@ -87,7 +133,7 @@ def attn_forward(mode, P, kind, L, feature, caption, bs, save):
 def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=None):
     """Gradients of every parameter given dHs_top (N,H) and the gradient w.r.t. alphas, either a
     full (B,Tcap,P) tensor `dalphas` (drop-in forward) or the per-(b,p) penalty term `Gpen`."""
-    bs, off, Pn, B = sv["bs"], sv["off"], sv["Pn"], sv["B"]
+    bs, off, Pn, B, tc = sv["bs"], sv["off"], sv["Pn"], sv["B"], sv["tc"]
     T, N = len(bs), sum(bs)
     E = P["embeddings.weight"].shape[1]
     H = P["unit.weight_hh_l0"].shape[1]
@@ -99,9 +145,11 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
     wf = P["attn.full_att.weight"].reshape(-1)
     Wd = P["attn.decoder_att.weight"]
     A = Wd.shape[0]
+    W = sv.get("W")
     grads = {}
     de_all = torch.empty(N, Pn, dtype=F32, device=dev)
     datt2_all = torch.empty(N, A, dtype=F32, device=dev)
+    datt2_b = torch.empty(N, A, dtype=BF16, device=dev) if tc else None
     dctx_all = torch.empty(N, E, dtype=F32, device=dev)
     dHs = [torch.empty(N, H, dtype=F32, device=dev) for _ in range(L - 1)] + [dHs_top]
     bouts = [None] * L
@@ -110,32 +158,58 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
         o1 = o0 + bt
         for l in reversed(range(L)):
             Wih, Whh, _, _ = layer_params(P, l)
-            bouts[l] = ops.rnn_seq_bwd(kind, Whh, bs, outs[l], dHs[l], h0=h0, c0=c0, t_range=(t + 1, t),
-                                       out=bouts[l])
-            if l > 0:
-                ops.sgemm(bouts[l]["dG"][o0:o1], Wih, out=dHs[l - 1][o0:o1])          # dX of layer l at step t
-        ops.sgemm(bouts[0]["dG"][o0:o1], Wih0[:, E:], out=dctx_all[o0:o1])            # d embed(ctx_t)
+            if tc:
+                bouts[l] = ops.rnn_seq_tc_bwd(kind, W[f"hh{l}"][1], bs, outs[l], dHs[l], h0=h0, c0=c0,
+                                              t_range=(t + 1, t), out=bouts[l], tag="step_bwd")
+                if bouts[l] is None:
+                    raise RuntimeError("rnn_seq_tc_bwd refused a shape that rnn_seq_tc_fits accepted")
+                if l > 0:                                                             # dX of layer l at step t
+                    ops.gemm_bf16(bouts[l]["dGb"][o0:o1], W[f"ih{l}"][1], out=dHs[l - 1][o0:o1])
+            else:
+                bouts[l] = ops.rnn_seq_bwd(kind, Whh, bs, outs[l], dHs[l], h0=h0, c0=c0, t_range=(t + 1, t),
+                                           out=bouts[l], tag="step_bwd")
+                if l > 0:
+                    ops.sgemm(bouts[l]["dG"][o0:o1], Wih, out=dHs[l - 1][o0:o1])
+        # d embed(ctx_t) = dG W_ih[:, E:]
+        if tc:
+            ops.gemm_bf16(bouts[0]["dGb"][o0:o1], W["ihc"][1], out=dctx_all[o0:o1], tag="ihc_dx")
+        else:
+            ops.sgemm(bouts[0]["dG"][o0:o1], Wih0[:, E:], out=dctx_all[o0:o1])
         if dalphas is not None:
             dal, dal_stride = dalphas[:, t, :], Tcap * Pn
         else:
             dal, dal_stride = Gpen, Pn
         ops.attn_step_bwd(bt, Pn, att1, Fe, att2_all[o0:o1], wf, alphas[:, t, :], Tcap * Pn, dal, dal_stride,
-                          dctx_all[o0:o1], de_all[o0:o1], datt2_all[o0:o1])
+                          dctx_all[o0:o1], de_all[o0:o1], datt2_all[o0:o1],
+                          datt2_bf16=datt2_b[o0:o1] if tc else None)
         # the query was the PRE-step top-layer hidden: its gradient joins the carried dh of the top layer
-        dq = ops.sgemm(datt2_all[o0:o1], Wd)
-        ops.add_rows(bouts[L - 1]["dstate"][0], dq, bt)
+        if tc:
+            ops.gemm_bf16(datt2_b[o0:o1], W["d"][1], out=bouts[L - 1]["dstate"][0][:bt], beta=1.0, tag="att2_dx")
+        else:
+            dq = ops.sgemm(datt2_all[o0:o1], Wd)
+            ops.add_rows(bouts[L - 1]["dstate"][0], dq, bt)
 
     # ---- hoisted weight gradients
     for l in range(L):
         Hprev = ops.shift_states(outs[l]["Hs"], bs, h0)
-        grads[f"unit.weight_hh_l{l}"] = weight_grad(mode, bouts[l]["dGh"], Hprev, "hh_dw")
-        grads[f"unit.bias_hh_l{l}"] = ops.colsum(bouts[l]["dGh"])
         inp = X0 if l == 0 else outs[l - 1]["Hs"]
-        grads[f"unit.weight_ih_l{l}"] = weight_grad(mode, bouts[l]["dG"], inp, "ih_dw")
-        grads[f"unit.bias_ih_l{l}"] = ops.colsum(bouts[l]["dG"])
+        if tc:
+            _, HprevT = ops.cast_bf16(Hprev, False, True)
+            _, inpT = ops.cast_bf16(inp, False, True)
+            grads[f"unit.weight_hh_l{l}"] = ops.gemm_bf16(bouts[l]["dGhT"], HprevT, tag="hh_dw")
+            grads[f"unit.weight_ih_l{l}"] = ops.gemm_bf16(bouts[l]["dGT"], inpT, tag="ih_dw")
+            grads[f"unit.bias_hh_l{l}"], grads[f"unit.bias_ih_l{l}"] = bouts[l]["dbhh"], bouts[l]["dbih"]
+        else:
+            grads[f"unit.weight_hh_l{l}"] = weight_grad(mode, bouts[l]["dGh"], Hprev, "hh_dw")
+            grads[f"unit.bias_hh_l{l}"] = ops.colsum(bouts[l]["dGh"])
+            grads[f"unit.weight_ih_l{l}"] = weight_grad(mode, bouts[l]["dG"], inp, "ih_dw")
+            grads[f"unit.bias_ih_l{l}"] = ops.colsum(bouts[l]["dG"])
         if l == L - 1:
             Hprev_top = Hprev
-    dXemb = ops.sgemm(bouts[0]["dG"], Wih0[:, :E], tag="ih_dx")
+    if tc:
+        dXemb = ops.gemm_bf16(bouts[0]["dGb"], W["ihe"][1], tag="ih_dx")
+    else:
+        dXemb = ops.sgemm(bouts[0]["dG"], Wih0[:, :E], tag="ih_dx")
     dEmb = torch.zeros_like(P["embeddings.weight"])
     ops.pack_inputs_bwd(dXemb, dEmb, None, caption, bs, False)
     grads["embeddings.weight"] = dEmb

@@ -22,6 +22,7 @@
 
 #include <cfloat>
 
+#include "attn_stream.cuh"
 #include "common.cuh"
 
 namespace st {
@@ -101,7 +102,8 @@ __global__ void __launch_bounds__(NT)
 attn_step_fwd_kernel(int P, int A, int E, const T* __restrict__ att1, const T* __restrict__ Fe,
                      const float* __restrict__ att2, const float* __restrict__ wf, const float* __restrict__ bfp,
                      const float* __restrict__ b_embed, float* __restrict__ alphas, int alpha_stride,
-                     float* __restrict__ S, float* __restrict__ ctx_out, int ld_ctx) {
+                     float* __restrict__ S, float* __restrict__ ctx_out, int ld_ctx,
+                     __nv_bfloat16* __restrict__ ctx_bf16, int ld_ctx_bf16) {
   extern __shared__ float sm[];
   float* s_att2 = sm;            // [A]
   float* s_wf = sm + A;          // [A]
@@ -149,6 +151,7 @@ attn_step_fwd_kernel(int P, int A, int E, const T* __restrict__ att1, const T* _
     float acc = 0.f;
     for (int p = 0; p < P; ++p) acc = fmaf(s_e[p], ldf(fe + (size_t)p * E + e), acc);
     ctx_out[(size_t)b * ld_ctx + e] = acc + b_embed[e];
+    if (ctx_bf16) ctx_bf16[(size_t)b * ld_ctx_bf16 + e] = __float2bfloat16(acc + b_embed[e]);
   }
 }
 
@@ -158,7 +161,7 @@ attn_step_bwd_kernel(int P, int A, int E, const T* __restrict__ att1, const T* _
                      const float* __restrict__ att2, const float* __restrict__ wf,
                      const float* __restrict__ alphas, int alpha_stride, const float* __restrict__ dal,
                      int dal_stride, const float* __restrict__ dctx, int ld_dctx, float* __restrict__ de_out,
-                     float* __restrict__ datt2) {
+                     float* __restrict__ datt2, __nv_bfloat16* __restrict__ datt2_bf16) {
   extern __shared__ float sm[];
   float* s_att2 = sm;             // [A]
   float* s_wf = sm + A;           // [A]
@@ -198,6 +201,7 @@ attn_step_bwd_kernel(int P, int A, int E, const T* __restrict__ att1, const T* _
     const float a2 = s_att2[a];
     for (int p = 0; p < P; ++p) acc = fmaf(s_de[p], act_d<ACT>(ldf(a1 + (size_t)p * A + a) + a2), acc);
     datt2[(size_t)b * A + a] = acc * s_wf[a];
+    if (datt2_bf16) datt2_bf16[(size_t)b * A + a] = __float2bfloat16(acc * s_wf[a]);
   }
 }
 
@@ -310,19 +314,31 @@ int st_attn_relayout(const float* f, int B, int C, int P, void* F, void* FT, int
 
 int st_attn_step_fwd(int rows, int P, int A, int E, const void* att1, const void* Fe, int in_bf16,
                      const float* att2, const float* wf, const float* bf, const float* b_embed, float* alphas,
-                     int alpha_stride, float* S, float* ctx_out, int ld_ctx, int act, st_stream_t stream) {
+                     int alpha_stride, float* S, float* ctx_out, int ld_ctx, void* ctx_out_bf16, int ld_ctx_bf16,
+                     int act, st_stream_t stream) {
   using namespace st;
   ST_REQUIRE(att1 && Fe && att2 && wf && bf && b_embed && alphas && S && ctx_out, ST_ERR_NULL,
              "st_attn_step_fwd: NULL pointer");
-  ST_REQUIRE(rows >= 1 && P >= 1 && A >= 1 && E >= 1 && alpha_stride >= P && ld_ctx >= E, ST_ERR_BAD_SHAPE,
-             "st_attn_step_fwd: rows=%d P=%d A=%d E=%d", rows, P, A, E);
+  ST_REQUIRE(rows >= 1 && P >= 1 && A >= 1 && E >= 1 && alpha_stride >= P && ld_ctx >= E &&
+                 (!ctx_out_bf16 || ld_ctx_bf16 >= E),
+             ST_ERR_BAD_SHAPE, "st_attn_step_fwd: rows=%d P=%d A=%d E=%d", rows, P, A, E);
   ST_REQUIRE(act == 0 || act == 1, ST_ERR_UNSUPPORTED, "st_attn_step_fwd: act=%d", act);
+  {
+    StreamParams sp{};
+    sp.P = P; sp.A = A; sp.E = E; sp.att1 = att1; sp.Fe = Fe; sp.att2 = att2; sp.wf = wf;
+    sp.bfp = bf; sp.b_embed = b_embed; sp.alphas_w = alphas; sp.S = S; sp.ctx_out = ctx_out;
+    sp.ctx_bf16 = reinterpret_cast<__nv_bfloat16*>(ctx_out_bf16);
+    sp.alpha_stride = alpha_stride; sp.ld_ctx = ld_ctx; sp.ld_ctx_bf16 = ld_ctx_bf16;
+    const int r = attn_stream_try(false, rows, in_bf16, act, sp, as_stream(stream));
+    if (r != 0) return r < 0 ? r : ST_OK;
+  }
   const size_t smem = sizeof(float) * (2 * (size_t)A + P);
   ST_REQUIRE(smem <= 48 * 1024, ST_ERR_BAD_SHAPE, "st_attn_step_fwd: A=%d P=%d too large", A, P);
   cudaStream_t s = as_stream(stream);
 #define ST_LAUNCH_FWD(T, ACT)                                                                         \
   attn_step_fwd_kernel<T, ACT><<<rows, NT, smem, s>>>(P, A, E, (const T*)att1, (const T*)Fe, att2, wf, bf, \
-                                                      b_embed, alphas, alpha_stride, S, ctx_out, ld_ctx)
+                                                      b_embed, alphas, alpha_stride, S, ctx_out, ld_ctx, \
+                                                      (__nv_bfloat16*)ctx_out_bf16, ld_ctx_bf16)
   if (in_bf16) { if (act == 0) ST_LAUNCH_FWD(__nv_bfloat16, 0); else ST_LAUNCH_FWD(__nv_bfloat16, 1); }
   else         { if (act == 0) ST_LAUNCH_FWD(float, 0); else ST_LAUNCH_FWD(float, 1); }
 #undef ST_LAUNCH_FWD
@@ -333,19 +349,29 @@ int st_attn_step_fwd(int rows, int P, int A, int E, const void* att1, const void
 int st_attn_step_bwd(int rows, int P, int A, int E, const void* att1, const void* Fe, int in_bf16,
                      const float* att2, const float* wf, const float* alphas, int alpha_stride,
                      const float* dalpha, int dalpha_stride, const float* dctx, int ld_dctx, float* de_out,
-                     float* datt2, int act, st_stream_t stream) {
+                     float* datt2, void* datt2_bf16, int act, st_stream_t stream) {
   using namespace st;
   ST_REQUIRE(att1 && Fe && att2 && wf && alphas && dctx && de_out && datt2, ST_ERR_NULL,
              "st_attn_step_bwd: NULL pointer");
   ST_REQUIRE(rows >= 1 && P >= 1 && A >= 1 && E >= 1 && alpha_stride >= P && ld_dctx >= E, ST_ERR_BAD_SHAPE,
              "st_attn_step_bwd: rows=%d P=%d A=%d E=%d", rows, P, A, E);
   ST_REQUIRE(act == 0 || act == 1, ST_ERR_UNSUPPORTED, "st_attn_step_bwd: act=%d", act);
+  {
+    StreamParams sp{};
+    sp.P = P; sp.A = A; sp.E = E; sp.att1 = att1; sp.Fe = Fe; sp.att2 = att2; sp.wf = wf;
+    sp.alphas_r = alphas; sp.alpha_stride = alpha_stride; sp.dal = dalpha; sp.dal_stride = dalpha_stride;
+    sp.dctx = dctx; sp.ld_dctx = ld_dctx; sp.de_out = de_out; sp.datt2 = datt2;
+    sp.datt2_bf16 = reinterpret_cast<__nv_bfloat16*>(datt2_bf16);
+    const int r = attn_stream_try(true, rows, in_bf16, act, sp, as_stream(stream));
+    if (r != 0) return r < 0 ? r : ST_OK;
+  }
   const size_t smem = sizeof(float) * (2 * (size_t)A + E + P);
   ST_REQUIRE(smem <= 48 * 1024, ST_ERR_BAD_SHAPE, "st_attn_step_bwd: A=%d E=%d P=%d too large", A, E, P);
   cudaStream_t s = as_stream(stream);
 #define ST_LAUNCH_BWD(T, ACT)                                                                         \
   attn_step_bwd_kernel<T, ACT><<<rows, NT, smem, s>>>(P, A, E, (const T*)att1, (const T*)Fe, att2, wf, alphas, \
-                                                      alpha_stride, dalpha, dalpha_stride, dctx, ld_dctx, de_out, datt2)
+                                                      alpha_stride, dalpha, dalpha_stride, dctx, ld_dctx, de_out, datt2, \
+                                                      (__nv_bfloat16*)datt2_bf16)
   if (in_bf16) { if (act == 0) ST_LAUNCH_BWD(__nv_bfloat16, 0); else ST_LAUNCH_BWD(__nv_bfloat16, 1); }
   else         { if (act == 0) ST_LAUNCH_BWD(float, 0); else ST_LAUNCH_BWD(float, 1); }
 #undef ST_LAUNCH_BWD

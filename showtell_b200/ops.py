@@ -306,6 +306,17 @@ def rnn_seq_tc_supported(kind, H):
     return bool(_lib.load().st_rnn_seq_tc_supported(kind, H))
 
 
+def rnn_seq_tc_fits(kind, H, B):
+    """True if the persistent tensor-core recurrent grid for batch B is co-resident on this GPU
+    ((H/16) unit tiles x ceil(B/128) batch tiles, one CTA per SM)."""
+    if not rnn_seq_tc_supported(kind, H):
+        return False
+    import ctypes as C
+    sms = C.c_int(0)
+    check(_lib.load().st_device_info(C.byref(sms), None, None, None), "st_device_info")
+    return (H // 16) * ((B + 127) // 128) <= sms.value
+
+
 def rnn_seq_tc_fwd(kind, Gx, Whh_b, bhh, bs, *, h0=None, h0_b=None, c0=None, save=True, t_range=None, out=None,
                    tag=None):
     """Tensor-core persistent recurrence over steps t_range (default: all).  Returns dict(Hs, Hsb, Cs,
@@ -385,7 +396,7 @@ def attn_relayout(f, bf16=False, want_t=True):
 
 
 def attn_step_fwd(rows, Pn, att1, Fe, att2, wf, bf, b_embed, alphas_t, alpha_stride, S, ctx_out, act=ACT_LEAKY,
-                  tag="attn_fwd"):
+                  ctx_bf16=None, tag="attn_fwd"):
     """att1 (B*P, A), Fe (B*P, E) (fp32 or bf16), att2 (rows, A).  alphas_t / ctx_out are (possibly
     strided) views whose first element is row 0; ctx_out row stride = ctx_out.stride(0)."""
     lib = _lib.load()
@@ -393,21 +404,25 @@ def attn_step_fwd(rows, Pn, att1, Fe, att2, wf, bf, b_embed, alphas_t, alpha_str
     tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
     check(lib.st_attn_step_fwd(rows, Pn, A, E, _raw(att1), _raw(Fe), int(att1.dtype == BF16), _raw(att2),
                                ptr(wf, F32), ptr(bf, F32), ptr(b_embed, F32), _raw(alphas_t), alpha_stride,
-                               ptr(S, F32), _raw(ctx_out), ctx_out.stride(0), act, stream_ptr()),
+                               ptr(S, F32), _raw(ctx_out), ctx_out.stride(0),
+                               _raw(ctx_bf16) if ctx_bf16 is not None else None,
+                               ctx_bf16.stride(0) if ctx_bf16 is not None else 0, act, stream_ptr()),
           "st_attn_step_fwd")
     if tok:
         TIMER.end(tok)
 
 
 def attn_step_bwd(rows, Pn, att1, Fe, att2, wf, alphas_t, alpha_stride, dalpha, dalpha_stride, dctx, de_out,
-                  datt2, act=ACT_LEAKY, tag="attn_bwd"):
+                  datt2, act=ACT_LEAKY, datt2_bf16=None, tag="attn_bwd"):
     lib = _lib.load()
     A, E = att1.shape[1], Fe.shape[1]
     tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
     check(lib.st_attn_step_bwd(rows, Pn, A, E, _raw(att1), _raw(Fe), int(att1.dtype == BF16), _raw(att2),
                                ptr(wf, F32), _raw(alphas_t), alpha_stride,
                                _raw(dalpha) if dalpha is not None else None, dalpha_stride, _raw(dctx),
-                               dctx.stride(0), _raw(de_out), _raw(datt2), act, stream_ptr()), "st_attn_step_bwd")
+                               dctx.stride(0), _raw(de_out), _raw(datt2),
+                               _raw(datt2_bf16) if datt2_bf16 is not None else None, act, stream_ptr()),
+          "st_attn_step_bwd")
     if tok:
         TIMER.end(tok)
 

@@ -5,7 +5,7 @@ import torch
 from showtell_b200.rnn_attn import RNN_Attn as GRU
 from showtell_b200.rnn_attn_LSTM import RNN_Attn as LSTM
 
-def run(kind, B, P, dtype, T=20, iters=3, prof=False):
+def run(kind, B, P, dtype, T=20, iters=5, prof=False):
     dev = torch.device("cuda:0")
     torch.manual_seed(1)
     m = (GRU if kind == "gru" else LSTM)(512, 2048, 512, 512, 10000, 1, dtype=dtype).to(dev)
@@ -14,7 +14,7 @@ def run(kind, B, P, dtype, T=20, iters=3, prof=False):
     lengths = [T] * B
     def step():
         m.zero_grad(); loss, _ = m.forward_loss(feat, cap, lengths); loss.backward(); return loss
-    for _ in range(2): step()
+    for _ in range(5): step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
