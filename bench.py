@@ -352,7 +352,17 @@ def main():
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line))
     if world > 1:
+        # Tear down in dependency order: captured step graphs hold NCCL work, so they go first; a
+        # communicator teardown that still stalls must not keep torchrun alive (watchdog exit).
+        sys.stdout.flush()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        net.__dict__.pop("_step_graphs", None)
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
     return 0
 
 

@@ -10,10 +10,10 @@
 // bound by the bytes of the two slabs (B*P*(A+E)*sizeof per step; at B=128, P=196 bf16 they stay
 // L2-resident across the 20 steps).
 //
-// One CTA per batch row, 8 consumer warps + 1 producer warp.  The producer's elected lane streams
-// the two slabs back to back through a 4-stage, 16 KB/stage shared-memory ring with 1-D bulk
-// async copies (cp.async.bulk ... mbarrier::complete_tx), so 64 KB are in flight per CTA regardless
-// of what the consumers are doing (the second slab is already arriving during the softmax).
+// Persistent CTAs (one per SM) walk the batch rows; 8 consumer warps + 1 producer warp.  The producer's elected lane streams
+// the two slabs back to back through a 12-stage, 16 KB/stage shared-memory ring with 1-D bulk
+// async copies (cp.async.bulk ... mbarrier::complete_tx), so up to 192 KB are in flight per SM regardless
+// of what the consumers are doing (the second slab, and then the next row's first slab, are already arriving during the softmax).
 // Consumers read 16-byte vectors from shared memory (conflict-free), keep the per-column constants
 // (w_f, att2 / dctx) in registers, and hand slots back through "empty" mbarriers.
 //
@@ -31,7 +31,7 @@ namespace st {
 namespace {
 
 constexpr int NCW = 8, NCT = NCW * 32, SNT = NCT + 32;   // consumer warps / threads, + producer warp
-constexpr int STG = 4;
+constexpr int STG = 12;   // 192 KB in flight per SM: the stream is latency-bound (HBM ~2 us under load)
 constexpr uint32_t CHUNK = 16384;
 
 template <typename T> struct V16;
@@ -86,7 +86,7 @@ __device__ __forceinline__ float cons_max(float v, float* red) {
 
 // VPL1 = 16-byte vectors per lane of a pass-1 row (row bytes / 512); RV2 = vectors per pass-2 row.
 template <typename T, int ACT, bool BWD, int VPL1, int RV2>
-__global__ void __launch_bounds__(SNT) attn_stream_kernel(const StreamParams p) {
+__global__ void __launch_bounds__(SNT) attn_stream_kernel(const int nrows, const StreamParams p) {
   constexpr int EPV = V16<T>::N;
   constexpr int NG = NCT / RV2;                   // pass-2 row groups
   extern __shared__ uint8_t smem_raw[];
@@ -96,11 +96,9 @@ __global__ void __launch_bounds__(SNT) attn_stream_kernel(const StreamParams p) 
   __shared__ float s_part[NCT * 8];               // pass-2 cross-group reduction: [NG][RV2*EPV] <= 2048 floats
   __shared__ uint64_t full[STG], empty[STG];
 
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int P = p.P;
   const int R1 = BWD ? p.E : p.A, R2 = BWD ? p.A : p.E;          // row elements of pass 1 / pass 2
-  const T* slab1 = reinterpret_cast<const T*>(BWD ? p.Fe : p.att1) + (size_t)b * P * R1;
-  const T* slab2 = reinterpret_cast<const T*>(BWD ? p.att1 : p.Fe) + (size_t)b * P * R2;
   const uint32_t rb1 = R1 * sizeof(T), rb2 = R2 * sizeof(T);
   const int cp1 = CHUNK / rb1, cp2 = CHUNK / rb2;                // rows per chunk
   const int nc1 = (P + cp1 - 1) / cp1, nc2 = (P + cp2 - 1) / cp2;
@@ -113,22 +111,29 @@ __global__ void __launch_bounds__(SNT) attn_stream_kernel(const StreamParams p) 
 
   if (warp == NCW) {  // ------------------------------------------------------------- producer
     if (lane == 0) {
-      for (int c = 0; c < nc1 + nc2; ++c) {
-        const int stage = c % STG, use = c / STG;
-        if (use > 0) mbar_wait(&empty[stage], (use - 1) & 1);
-        const bool first = c < nc1;
-        const int ci = first ? c : c - nc1, cp = first ? cp1 : cp2;
-        const uint32_t rb = first ? rb1 : rb2;
-        const int rows = min(cp, P - ci * cp);
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(first ? slab1 : slab2) + (size_t)ci * cp * rb;
-        mbar_expect_tx(&full[stage], rows * rb);
-        bulk_load(ring + stage * CHUNK, src, rows * rb, &full[stage]);
+      int c = 0;
+      for (int b = blockIdx.x; b < nrows; b += gridDim.x) {
+        const uint8_t* slab1 = reinterpret_cast<const uint8_t*>(BWD ? p.Fe : p.att1) + (size_t)b * P * rb1;
+        const uint8_t* slab2 = reinterpret_cast<const uint8_t*>(BWD ? p.att1 : p.Fe) + (size_t)b * P * rb2;
+        for (int k = 0; k < nc1 + nc2; ++k, ++c) {
+          const int stage = c % STG, use = c / STG;
+          if (use > 0) mbar_wait(&empty[stage], (use - 1) & 1);
+          const bool first = k < nc1;
+          const int ci = first ? k : k - nc1, cp = first ? cp1 : cp2;
+          const uint32_t rb = first ? rb1 : rb2;
+          const int rows = min(cp, P - ci * cp);
+          const uint8_t* src = (first ? slab1 : slab2) + (size_t)ci * cp * rb;
+          mbar_expect_tx(&full[stage], rows * rb);
+          bulk_load(ring + stage * CHUNK, src, rows * rb, &full[stage]);
+        }
       }
     }
     return;
   }
 
   // --------------------------------------------------------------------------------- consumers
+  int c = 0;
+  for (int b = blockIdx.x; b < nrows; b += gridDim.x) {
   // pass-1 per-lane constants: lane owns vectors lane, lane+32, ... of every row
   float w1[VPL1][EPV], a1[VPL1][EPV];
 #pragma unroll
@@ -140,7 +145,6 @@ __global__ void __launch_bounds__(SNT) attn_stream_kernel(const StreamParams p) 
       else     { w1[k][j] = p.wf[el]; a1[k][j] = p.att2[(size_t)b * p.A + el]; }
     }
 
-  int c = 0;
   for (int ci = 0; ci < nc1; ++ci, ++c) {
     const int stage = c % STG;
     mbar_wait(&full[stage], (c / STG) & 1);
@@ -256,15 +260,18 @@ __global__ void __launch_bounds__(SNT) attn_stream_kernel(const StreamParams p) 
       if (p.datt2_bf16) p.datt2_bf16[(size_t)b * p.A + col] = __float2bfloat16(s);
     }
   }
+  }  // rows
 }
 
 template <typename T, int ACT, bool BWD, int VPL1>
 int launch_rv2(int rows, const StreamParams& p, int rv2, size_t smem, cudaStream_t s) {
+  int sms = 0;
+  ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
 #define ST_GO(RV2)                                                                                         \
   do {                                                                                                     \
     auto kern = attn_stream_kernel<T, ACT, BWD, VPL1, RV2>;                                                \
     ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-    kern<<<rows, SNT, smem, s>>>(p);                                                                       \
+    kern<<<rows < sms ? rows : sms, SNT, smem, s>>>(rows, p);                                                                       \
   } while (0)
   if (rv2 == 32) ST_GO(32);
   else if (rv2 == 64) ST_GO(64);

@@ -9,8 +9,10 @@ kernel (cooperative launches and TMA descriptors included: all buffers come from
 private pool, so the raw pointers baked into kernel parameters stay valid), outputs are the
 graph's static loss / gradient tensors.
 
-Not used when a gradient reducer is attached (NCCL work on a side stream), while
-`ops.TIMER` records per-kernel events, or when `module.use_cuda_graphs` is False.  One loss per
+A gradient reducer (parallel.GradReducer: NCCL all-reduces on a side stream) is captured with the
+step -- the side stream forks from and joins the capture stream through events, NCCL collectives
+are graph-capturable -- so data-parallel ranks replay {kernels + all-reduces} as one graph each.
+Not used while `ops.TIMER` records per-kernel events or when `module.use_cuda_graphs` is False.  One loss per
 module may be outstanding: a second forward_loss before backward() overwrites the static gradients.
 """
 import torch
@@ -28,8 +30,7 @@ class _Entry:
 
 
 def enabled(mod):
-    return (getattr(mod, "use_cuda_graphs", True) and ops.TIMER is None
-            and getattr(mod, "grad_reducer", None) is None)
+    return getattr(mod, "use_cuda_graphs", True) and ops.TIMER is None
 
 
 def run(mod, key, body, inputs):

@@ -29,7 +29,10 @@ def run(kind, B, P, dtype, T=20, iters=5, prof=False):
         print(p.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=60))
 
 if __name__ == "__main__":
-    run("gru", 128, 196, "fp32")
-    run("gru", 128, 196, "bf16", prof=True)
-    run("gru", 128, 49, "bf16")
-    run("lstm", 512, 196, "bf16")
+    if len(sys.argv) > 1:      # e.g.  time_attn.py gru 128 196 bf16 [prof]
+        run(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4], prof="prof" in sys.argv[5:])
+    else:
+        run("gru", 128, 196, "fp32")
+        run("gru", 128, 196, "bf16", prof=True)
+        run("gru", 128, 49, "bf16")
+        run("lstm", 512, 196, "bf16")
