@@ -218,7 +218,8 @@ int st_shift_states(float* Hprev, const float* Hs, const float* h0, int H, int n
  * st_attn_hoist_bwd (after the loop; de (N,P), att2 (N,A) packed time-major):
  *   datt1[b,p,a] = w_f[a] sum_t de[t,b,p] act'(att1[b,p,a] + att2[t,b,a]) (+ transposed copy),
  *   dwf[a] = sum_{t,b,p} de act(.)
- * st_attn_ctx_all: ctx[(t,b), c] = sum_p alphas[b,t,p] F[b,p,c] for all live (t,b) (for dW_embed).
+ * st_attn_ctx_all: ctx[(t,b), c] = sum_p alphas[b,t,p] F[b,p,c] for all live (t,b) (for dW_embed); ctx / ctxT
+ *   are fp32 (out_bf16 = 0) or bf16.
  * st_attn_penalty: pen_sum = sum (1 - S)^2, Gpen = -2 coef (1 - S)          (main_attn.py:131)
  * st_add_rows: dst[r,:] += src[r,:] (attention query gradient into the carried dh rows).
  * ------------------------------------------------------------------------------------------ */
@@ -236,7 +237,7 @@ int st_attn_hoist_bwd(int nsteps, const int* batch_sizes_host, int P, int A, con
                       const float* att2, const float* de, const float* wf, void* datt1, void* datt1T, int ldt,
                       int out_bf16, float* dwf, int act, st_stream_t stream);
 int st_attn_ctx_all(int nsteps, const int* batch_sizes_host, int P, int C, int T_cap, const void* F, int in_bf16,
-                    const float* alphas, void* ctx, void* ctxT, int ldt, st_stream_t stream);
+                    const float* alphas, void* ctx, void* ctxT, int ldt, int out_bf16, st_stream_t stream);
 int st_attn_penalty(int n, const float* S, float coef, float* pen_sum, float* Gpen, st_stream_t stream);
 int st_add_rows(float* dst, const float* src, int rows, int cols, st_stream_t stream);
 

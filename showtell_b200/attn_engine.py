@@ -226,7 +226,8 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
     grads["attn.full_att.bias"] = ops.colsum(de_all.reshape(-1, 1))
     # embed: ctx_e = W_embed ctx + b with ctx = sum_p alpha_p F_p rebuilt for all (t,b) in one pass
     if mode == "bf16":
-        _, ctxT = ops.attn_ctx_all(bs, Pn, sv["F"], alphas, want=False, want_t=True)
+        ctx, _ = ops.attn_ctx_all(bs, Pn, sv["F"], alphas, out_dtype=F32)    # row-major: coalesced stores
+        _, ctxT = ops.cast_bf16(ctx, False, True)
         _, dcT = ops.cast_bf16(dctx_all, False, True)
         grads["embed.weight"] = ops.gemm_bf16(dcT, ctxT, tag="embed_dw")
     else:

@@ -34,6 +34,11 @@ __device__ __forceinline__ float ldf(const float* p) { return *p; }
 __device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 __device__ __forceinline__ void stf(float* p, float v) { *p = v; }
 __device__ __forceinline__ void stf(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+// two adjacent elements; p must be aligned to 2 elements
+__device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void st2(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
 
 template <int ACT>
 __device__ __forceinline__ float act_f(float s) { return ACT == 0 ? (s > 0.f ? s : 0.2f * s) : tanhf(s); }
@@ -66,34 +71,61 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 }
 
 // f (B,C,P) fp32 channels-first (cnn_attn.py:49) -> F (B,P,C) [T], FT (C, ldft) [T] with column b*P+p,
-// mean_f (B,C) fp32 (rnn_attn.py:62 `cnn_feature.mean(dim=2)`).  One CTA per (32-channel slab, image).
+// mean_f (B,C) fp32 (rnn_attn.py:62 `cnn_feature.mean(dim=2)`).  One CTA per (64-channel slab, image):
+// the slab (64 x P floats, contiguous in f) is read once into shared memory with coalesced loads, then
+// written out twice: F rows get 64 channels = 128 B (bf16) per location, FT rows get P contiguous
+// locations per channel.  HBM-bound: 4 + 2*sizeof(T) bytes per element.
+constexpr int RL_CH = 64;
 template <typename T>
-__global__ void relayout_kernel(const float* __restrict__ f, int C, int P, T* __restrict__ F, T* __restrict__ FT,
-                                int ldft, float* __restrict__ mean_f) {
-  __shared__ float tile[32][33];
-  const int b = blockIdx.y, c0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 rows of 32
-  float msum[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int p0 = 0; p0 < P; p0 += 32) {
-    for (int i = ty; i < 32; i += 8) {  // read (c, p): p contiguous
-      const int c = c0 + i, p = p0 + tx;
-      float v = (c < C && p < P) ? f[((size_t)b * C + c) * P + p] : 0.f;
-      tile[i][tx] = v;
-      msum[i >> 3] += v;
-      if (FT && c < C && p < P) stf(FT + (size_t)c * ldft + (size_t)b * P + p, v);
+__global__ void __launch_bounds__(NT)
+relayout_kernel(const float* __restrict__ f, int C, int P, T* __restrict__ F, T* __restrict__ FT, int ldft,
+                float* __restrict__ mean_f) {
+  extern __shared__ float tile[];                 // [RL_CH][PS], PS odd: conflict-free column reads
+  const int PS = P | 1;
+  const int b = blockIdx.y, c0 = blockIdx.x * RL_CH;
+  const int nch = min(RL_CH, C - c0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* src = f + ((size_t)b * C + c0) * P;
+  if ((P & 3) == 0) {   // the slab is contiguous and 16-byte aligned: 128-bit loads, running (row, col)
+    const int nv = nch * P / 4;
+    int col = tid * 4, row = 0;
+    while (col >= P) { col -= P; ++row; }
+    for (int i = tid; i < nv; i += NT) {
+      const float4 v = *reinterpret_cast<const float4*>(src + (size_t)i * 4);
+      float* d = tile + row * PS + col;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      col += NT * 4;
+      while (col >= P) { col -= P; ++row; }
     }
-    __syncthreads();
-    for (int i = ty; i < 32; i += 8) {  // write (p, c): c contiguous
-      const int p = p0 + i, c = c0 + tx;
-      if (p < P && c < C) stf(F + ((size_t)b * P + p) * C + c, tile[tx][i]);
-    }
-    __syncthreads();
+  } else {
+    for (int i = tid; i < nch * P; i += NT) tile[(i / P) * PS + (i % P)] = src[i];
   }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float s = warp_sum(msum[k]);
-    const int c = c0 + ty + 8 * k;
-    if (tx == 0 && c < C) mean_f[(size_t)b * C + c] = s / (float)P;
+  __syncthreads();
+  // F[(b*P + p), c0 + c]: warp per location, a lane writes two adjacent channels (128 B per warp in bf16)
+  for (int p = warp; p < P; p += NT / 32) {
+    T* dst = F + ((size_t)b * P + p) * C + c0;
+    if (nch == RL_CH && (C & 1) == 0) st2(dst + 2 * lane, tile[(2 * lane) * PS + p], tile[(2 * lane + 1) * PS + p]);
+    else
+      for (int c = lane; c < nch; c += 32) stf(dst + c, tile[c * PS + p]);
+  }
+  // FT[c0 + c, b*P + p] and the channel means: warp per channel, a lane owns two adjacent locations
+  const bool pair_ok = FT && ((ldft & 1) == 0) && (((size_t)b * P) & 1) == 0;
+  for (int c = warp; c < nch; c += NT / 32) {
+    float s = 0.f;
+    T* dst = FT ? FT + (size_t)(c0 + c) * ldft + (size_t)b * P : nullptr;
+    for (int p = 2 * lane; p < P; p += 64) {
+      const float v0 = tile[c * PS + p], v1 = (p + 1 < P) ? tile[c * PS + p + 1] : 0.f;
+      s += v0 + v1;
+      if (FT) {
+        if (pair_ok && p + 1 < P) st2(dst + p, v0, v1);
+        else {
+          stf(dst + p, v0);
+          if (p + 1 < P) stf(dst + p + 1, v1);
+        }
+      }
+    }
+    s = warp_sum(s);
+    if (lane == 0) mean_f[(size_t)b * C + c0 + c] = s / (float)P;
   }
 }
 
@@ -207,64 +239,163 @@ attn_step_bwd_kernel(int P, int A, int E, const T* __restrict__ att1, const T* _
 
 // After the time loop: d att1[b,p,a] = w_f[a] sum_t de[t,b,p] act'(att1[b,p,a] + att2[t,b,a]) and
 // d w_f[a] += sum_{t,b,p} de[t,b,p] act(att1[b,p,a] + att2[t,b,a]).  de (N,P), att2 (N,A) packed.
-// One CTA per (image, 8 grid locations); threads over A.
+// ALU-bound (B*P*A*T tuples): one CTA per (image, HB_P grid locations); a thread owns one attention
+// unit a per pass and keeps att2[t,b,a] for up to HB_T steps in registers; de of the CTA's locations
+// sits in shared memory as [p][t] so four steps come with one broadcast 128-bit read.  The
+// transposed copy (the K-major operand of dW_enc = datt1^T F) is staged through shared memory so
+// each attention unit's row gets HB_P contiguous locations.
+constexpr int HB_P = 28, HB_T = 20;
 template <typename T, typename TO, int ACT>
 __global__ void __launch_bounds__(NT)
 attn_hoist_bwd_kernel(const __grid_constant__ StepTable tab, int P, int A, const T* __restrict__ att1,
                       const float* __restrict__ att2, const float* __restrict__ de, const float* __restrict__ wf,
                       TO* __restrict__ datt1, TO* __restrict__ datt1T, int ldt, float* __restrict__ dwf) {
-  const int b = blockIdx.y, p0 = blockIdx.x * 8;
+  extern __shared__ float hsm[];
+  float* s_de = hsm;                                   // [HB_P][HB_T]
+  TO* s_out = reinterpret_cast<TO*>(hsm + HB_P * HB_T); // [A][HB_P + 1] (only if datt1T)
+  const int b = blockIdx.y, p0 = blockIdx.x * HB_P, np = min(HB_P, P - p0);
   int len = 0;
-  while (len < tab.nsteps && tab.bs[len] > b) ++len;  // steps in which row b is live
-  for (int a = threadIdx.x; a < A; a += NT) {
-    float w = wf[a], dw = 0.f;
-    for (int pi = 0; pi < 8; ++pi) {
-      const int p = p0 + pi;
-      if (p >= P) break;
-      const float s1 = ldf(att1 + ((size_t)b * P + p) * A + a);
-      float acc = 0.f;
-      for (int t = 0; t < len; ++t) {
-        const size_t n = (size_t)tab.off[t] + b;
-        const float d = de[n * P + p], s = s1 + att2[n * A + a];
-        acc = fmaf(d, act_d<ACT>(s), acc);
-        dw = fmaf(d, act_f<ACT>(s), dw);
+  while (len < tab.nsteps && tab.bs[len] > b) ++len;   // steps in which row b is live
+  const int OS = HB_P + 1;
+  for (int a0 = 0; a0 < A; a0 += NT) {
+    const int a = a0 + threadIdx.x;
+    const bool a_ok = a < A;
+    const float w = a_ok ? wf[a] : 0.f;
+    float dw = 0.f;
+    float acc[HB_P];
+#pragma unroll
+    for (int i = 0; i < HB_P; ++i) acc[i] = 0.f;
+    for (int t0 = 0; t0 < len; t0 += HB_T) {
+      const int nt = min(HB_T, len - t0);
+      __syncthreads();
+      for (int i = threadIdx.x; i < HB_P * HB_T; i += NT) {
+        const int pi = i / HB_T, ti = i % HB_T;
+        s_de[i] = (pi < np && ti < nt) ? de[((size_t)tab.off[t0 + ti] + b) * P + p0 + pi] : 0.f;
       }
-      const float v = acc * w;
-      stf(datt1 + ((size_t)b * P + p) * A + a, v);
-      if (datt1T) stf(datt1T + (size_t)a * ldt + (size_t)b * P + p, v);
+      float a2[HB_T];
+#pragma unroll
+      for (int ti = 0; ti < HB_T; ++ti)
+        a2[ti] = (a_ok && ti < nt) ? att2[((size_t)tab.off[t0 + ti] + b) * A + a] : 0.f;
+      __syncthreads();
+      if (a_ok) {
+#pragma unroll
+        for (int pi = 0; pi < HB_P; ++pi) {
+          if (pi < np) {
+            const float s1 = ldf(att1 + ((size_t)b * P + p0 + pi) * A + a);
+#pragma unroll
+            for (int ti = 0; ti < HB_T; ti += 4) {
+              const float4 d4 = *reinterpret_cast<const float4*>(s_de + pi * HB_T + ti);
+              const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float sv = s1 + a2[ti + k];
+                if (ACT == 0) {   // LeakyReLU: act(s) = s * act'(s)
+                  const float g = sv > 0.f ? dd[k] : 0.2f * dd[k];
+                  acc[pi] += g;
+                  dw = fmaf(sv, g, dw);
+                } else {
+                  acc[pi] = fmaf(dd[k], act_d<ACT>(sv), acc[pi]);
+                  dw = fmaf(dd[k], act_f<ACT>(sv), dw);
+                }
+              }
+            }
+          }
+        }
+      }
     }
-    atomicAdd(dwf + a, dw);
+    if (a_ok) {
+#pragma unroll
+      for (int pi = 0; pi < HB_P; ++pi) {
+        if (pi < np) {
+          const float v = acc[pi] * w;
+          stf(datt1 + ((size_t)b * P + p0 + pi) * A + a, v);
+          if (datt1T) stf(s_out + (size_t)a * OS + pi, v);
+        }
+      }
+      atomicAdd(dwf + a, dw);
+    }
+  }
+  if (datt1T) {
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int a = warp; a < A; a += NT / 32) {
+      TO* dst = datt1T + (size_t)a * ldt + (size_t)b * P + p0;
+      for (int pi = lane; pi < np; pi += 32) dst[pi] = s_out[(size_t)a * OS + pi];
+    }
   }
 }
 
 // ctx[n=(t,b), c] = sum_p alpha[b,t,p] F[b,p,c]  (feature-space context, needed only for d W_embed).
-// One CTA per (image, 256-channel slab); alpha rows of the image in shared memory; 8 steps at a time.
+// Bound by one read of F: one CTA per (image, 4*NT-channel slab); a thread owns 4 adjacent channels
+// (one 8- or 16-byte load per location) and accumulates CX_T steps at a time, the alpha rows of those
+// steps sitting in shared memory as [p][t] (four steps per broadcast 128-bit read).
+constexpr int CX_T = 20;
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+__device__ __forceinline__ void ld4(const __nv_bfloat16* p, float (&v)[4]) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+  v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+}
 template <typename T, typename TO>
 __global__ void __launch_bounds__(NT)
 attn_ctx_all_kernel(const __grid_constant__ StepTable tab, int P, int C, int Tcap, const T* __restrict__ F,
                     const float* __restrict__ alphas, TO* __restrict__ ctx, TO* __restrict__ ctxT, int ldt) {
-  extern __shared__ float s_al[];  // [8][P]
-  const int b = blockIdx.y, c = blockIdx.x * NT + threadIdx.x;
+  extern __shared__ float s_al[];  // [P][CX_T]
+  const int b = blockIdx.y, c = (blockIdx.x * NT + threadIdx.x) * 4;
+  const bool vec_ok = (C & 3) == 0 && c + 4 <= C;
   int len = 0;
   while (len < tab.nsteps && tab.bs[len] > b) ++len;
-  for (int t0 = 0; t0 < len; t0 += 8) {
-    const int nt = min(8, len - t0);
+  for (int t0 = 0; t0 < len; t0 += CX_T) {
+    const int nt = min(CX_T, len - t0);
     __syncthreads();
-    for (int i = threadIdx.x; i < nt * P; i += NT)
-      s_al[i] = alphas[((size_t)b * Tcap + t0 + i / P) * P + (i % P)];
+    for (int i = threadIdx.x; i < P * CX_T; i += NT) {
+      const int pi = i / CX_T, ti = i % CX_T;
+      s_al[i] = ti < nt ? alphas[((size_t)b * Tcap + t0 + ti) * P + pi] : 0.f;
+    }
     __syncthreads();
     if (c < C) {
-      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int p = 0; p < P; ++p) {
-        const float fv = ldf(F + ((size_t)b * P + p) * C + c);
+      float acc[CX_T][4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (k < nt) acc[k] = fmaf(s_al[k * P + p], fv, acc[k]);
+      for (int k = 0; k < CX_T; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
+      for (int p0 = 0; p0 < P; p0 += 4) {       // four locations' loads in flight per thread
+        float fv[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int p = min(p0 + u, P - 1);
+          const T* src = F + ((size_t)b * P + p) * C + c;
+          if (vec_ok) ld4(src, fv[u]);
+          else
+            for (int j = 0; j < 4; ++j) fv[u][j] = (c + j < C) ? ldf(src + j) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (p0 + u < P) {
+#pragma unroll
+            for (int k = 0; k < CX_T; k += 4) {
+              const float4 a4 = *reinterpret_cast<const float4*>(s_al + (p0 + u) * CX_T + k);
+              const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[k + q][j] = fmaf(aa[q], fv[u][j], acc[k + q][j]);
+            }
+          }
+        }
       }
-      for (int k = 0; k < nt; ++k) {
-        const size_t n = (size_t)tab.off[t0 + k] + b;
-        if (ctx) stf(ctx + n * C + c, acc[k]);
-        if (ctxT) stf(ctxT + (size_t)c * ldt + n, acc[k]);
+#pragma unroll
+      for (int k = 0; k < CX_T; ++k) {
+        if (k < nt) {
+          const size_t n = (size_t)tab.off[t0 + k] + b;
+          for (int j = 0; j < 4; ++j) {
+            if (c + j < C) {
+              if (ctx) stf(ctx + n * C + c + j, acc[k][j]);
+              if (ctxT) stf(ctxT + (size_t)(c + j) * ldt + n, acc[k][j]);
+            }
+          }
+        }
       }
     }
   }
@@ -301,13 +432,20 @@ int st_attn_relayout(const float* f, int B, int C, int P, void* F, void* FT, int
   ST_REQUIRE(f && F && mean_f, ST_ERR_NULL, "st_attn_relayout: NULL pointer");
   ST_REQUIRE(B >= 1 && C >= 1 && P >= 1 && (!FT || ldft >= B * P), ST_ERR_BAD_SHAPE,
              "st_attn_relayout: B=%d C=%d P=%d ldft=%d", B, C, P, ldft);
-  dim3 grid((C + 31) / 32, B);
+  dim3 grid((C + RL_CH - 1) / RL_CH, B);
   ST_REQUIRE(grid.y <= 65535, ST_ERR_BAD_SHAPE, "st_attn_relayout: batch too large");
+  const size_t smem = sizeof(float) * RL_CH * (size_t)(P | 1);
+  ST_REQUIRE(smem <= 200 * 1024, ST_ERR_BAD_SHAPE, "st_attn_relayout: P=%d too large", P);
   cudaStream_t s = as_stream(stream);
-  if (out_bf16)
-    relayout_kernel<__nv_bfloat16><<<grid, NT, 0, s>>>(f, C, P, (__nv_bfloat16*)F, (__nv_bfloat16*)FT, ldft, mean_f);
-  else
-    relayout_kernel<float><<<grid, NT, 0, s>>>(f, C, P, (float*)F, (float*)FT, ldft, mean_f);
+  if (out_bf16) {
+    auto kern = relayout_kernel<__nv_bfloat16>;
+    ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NT, smem, s>>>(f, C, P, (__nv_bfloat16*)F, (__nv_bfloat16*)FT, ldft, mean_f);
+  } else {
+    auto kern = relayout_kernel<float>;
+    ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NT, smem, s>>>(f, C, P, (float*)F, (float*)FT, ldft, mean_f);
+  }
   ST_LAUNCH_TRY("relayout_kernel");
   return ST_OK;
 }
@@ -390,12 +528,18 @@ int st_attn_hoist_bwd(int nsteps, const int* batch_sizes_host, int P, int A, con
   ST_REQUIRE(in_bf16 == out_bf16, ST_ERR_UNSUPPORTED, "st_attn_hoist_bwd: mixed storage types");
   const int B = tab.bs[0];
   ST_REQUIRE(!datt1T || ldt >= B * P, ST_ERR_BAD_SHAPE, "st_attn_hoist_bwd: ldt=%d", ldt);
-  dim3 grid((P + 7) / 8, B);
+  dim3 grid((P + HB_P - 1) / HB_P, B);
+  ST_REQUIRE(grid.y <= 65535, ST_ERR_BAD_SHAPE, "st_attn_hoist_bwd: batch too large");
   cudaStream_t s = as_stream(stream);
   ST_CUDA_TRY(cudaMemsetAsync(dwf, 0, sizeof(float) * A, s));
-#define ST_LAUNCH_H(T, ACT)                                                                               \
-  attn_hoist_bwd_kernel<T, T, ACT><<<grid, NT, 0, s>>>(tab, P, A, (const T*)att1, att2, de, wf, (T*)datt1, \
-                                                       (T*)datt1T, ldt, dwf)
+  const size_t smem = sizeof(float) * HB_P * HB_T + (datt1T ? (size_t)A * (HB_P + 1) * (in_bf16 ? 2 : 4) : 0);
+  ST_REQUIRE(smem <= 200 * 1024, ST_ERR_BAD_SHAPE, "st_attn_hoist_bwd: A=%d too large", A);
+#define ST_LAUNCH_H(T, ACT)                                                                                 \
+  do {                                                                                                      \
+    auto kern = attn_hoist_bwd_kernel<T, T, ACT>;                                                           \
+    ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+    kern<<<grid, NT, smem, s>>>(tab, P, A, (const T*)att1, att2, de, wf, (T*)datt1, (T*)datt1T, ldt, dwf);   \
+  } while (0)
   if (in_bf16) { if (act == 0) ST_LAUNCH_H(__nv_bfloat16, 0); else ST_LAUNCH_H(__nv_bfloat16, 1); }
   else         { if (act == 0) ST_LAUNCH_H(float, 0); else ST_LAUNCH_H(float, 1); }
 #undef ST_LAUNCH_H
@@ -404,20 +548,24 @@ int st_attn_hoist_bwd(int nsteps, const int* batch_sizes_host, int P, int A, con
 }
 
 int st_attn_ctx_all(int nsteps, const int* batch_sizes_host, int P, int C, int T_cap, const void* F, int in_bf16,
-                    const float* alphas, void* ctx, void* ctxT, int ldt, st_stream_t stream) {
+                    const float* alphas, void* ctx, void* ctxT, int ldt, int out_bf16, st_stream_t stream) {
   using namespace st;
   StepTable tab;
   ST_TRY(make_step_table(tab, nsteps, batch_sizes_host));
   ST_REQUIRE(F && alphas && (ctx || ctxT), ST_ERR_NULL, "st_attn_ctx_all: NULL pointer");
   ST_REQUIRE(T_cap >= nsteps && (!ctxT || ldt >= tab.off[nsteps]), ST_ERR_BAD_SHAPE,
              "st_attn_ctx_all: T_cap=%d ldt=%d", T_cap, ldt);
-  const size_t smem = sizeof(float) * 8 * (size_t)P;
+  const size_t smem = sizeof(float) * CX_T * (size_t)P;
   ST_REQUIRE(smem <= 48 * 1024, ST_ERR_BAD_SHAPE, "st_attn_ctx_all: P=%d too large", P);
-  dim3 grid((C + NT - 1) / NT, tab.bs[0]);
+  dim3 grid((C + 4 * NT - 1) / (4 * NT), tab.bs[0]);
   cudaStream_t s = as_stream(stream);
-  if (in_bf16)
+  ST_REQUIRE(in_bf16 || !out_bf16, ST_ERR_UNSUPPORTED, "st_attn_ctx_all: fp32 features with bf16 output");
+  if (in_bf16 && out_bf16)
     attn_ctx_all_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, NT, smem, s>>>(
         tab, P, C, T_cap, (const __nv_bfloat16*)F, alphas, (__nv_bfloat16*)ctx, (__nv_bfloat16*)ctxT, ldt);
+  else if (in_bf16)
+    attn_ctx_all_kernel<__nv_bfloat16, float><<<grid, NT, smem, s>>>(
+        tab, P, C, T_cap, (const __nv_bfloat16*)F, alphas, (float*)ctx, (float*)ctxT, ldt);
   else
     attn_ctx_all_kernel<float, float><<<grid, NT, smem, s>>>(tab, P, C, T_cap, (const float*)F, alphas,
                                                              (float*)ctx, (float*)ctxT, ldt);

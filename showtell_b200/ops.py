@@ -444,17 +444,18 @@ def attn_hoist_bwd(bs, Pn, att1, att2_all, de_all, wf, want_t=True, act=ACT_LEAK
     return datt1, dT, dwf
 
 
-def attn_ctx_all(bs, Pn, F, alphas, want=True, want_t=False):
-    """ctx (N, C) and/or ctxT (C, N) in F's storage type; alphas (B, Tcap, P) fp32."""
+def attn_ctx_all(bs, Pn, F, alphas, want=True, want_t=False, out_dtype=None):
+    """ctx (N, C) and/or ctxT (C, N) in F's storage type (or `out_dtype`); alphas (B, Tcap, P) fp32."""
     lib = _lib.load()
     N, Cc = sum(bs), F.shape[1]
     dev = F.device
-    ctx = torch.empty(N, Cc, dtype=F.dtype, device=dev) if want else None
+    dt = out_dtype or F.dtype
+    ctx = torch.empty(N, Cc, dtype=dt, device=dev) if want else None
     ld = (N + 7) // 8 * 8
-    cT = torch.empty(Cc, ld, dtype=F.dtype, device=dev)[:, :N] if want_t else None
+    cT = torch.empty(Cc, ld, dtype=dt, device=dev)[:, :N] if want_t else None
     check(lib.st_attn_ctx_all(len(bs), int_array(bs), Pn, Cc, alphas.shape[1], _raw(F), int(F.dtype == BF16),
                               ptr(alphas, F32), _raw(ctx) if want else None, _raw(cT) if want_t else None, ld,
-                              stream_ptr()), "st_attn_ctx_all")
+                              int(dt == BF16), stream_ptr()), "st_attn_ctx_all")
     return ctx, cT
 
 
