@@ -93,6 +93,9 @@ int st_cast_bf16(const float* src, int rows, int cols, int lds, void* dst, int l
  * dHs = P Wv and dWv = P^T Hs.
  * ------------------------------------------------------------------------------------------ */
 int st_vocab_ce_parts(int V);
+/* Development / test aid: pin the kernel behind st_gemm_bf16 and st_vocab_ce_*: 2 = CTA-pair kernel
+ * (cta_group::2, 256x256 tiles, stream-K), 128 / 256 = single-CTA kernel with that tile width, 0 = choose. */
+int st_debug_gemm_variant(int variant);
 int st_vocab_ce_fwd(int M, int V, int H, const void* Hs, int ldh, const void* Wv, int ldw, const float* bv,
                     const int64_t* target, float* part_max, float* part_sum, float* tlogit, float* lse,
                     float* loss_sum, st_stream_t stream);
@@ -181,6 +184,16 @@ int st_rnn_seq_bwd(int kind, int H, int nsteps, const int* batch_sizes_host, int
  * bf16 GEMM operands dG (N, g*H) and dGT (g*H, ldt >= N, multiple of 8) (GRU: also dGh / dGhT),
  * the bias gradients dbih / dbhh (g*H) and dstate (2, B0, H) = (dh0, dc0).
  * ------------------------------------------------------------------------------------------ */
+/* Cluster-resident variant of st_rnn_seq_tc_fwd (rnn_cluster.cu): a thread-block cluster of H/32 CTAs
+ * keeps the recurrence of a 16/32/48-row batch slice entirely in shared memory -- W_hh slices resident,
+ * h_t exchanged through distributed shared memory, no global memory on the step-to-step chain.
+ * Same arguments and outputs as st_rnn_seq_tc_fwd (no barrier workspace).  H in {64,128,256,512};
+ * returns ST_ERR_UNSUPPORTED if the GPU cannot co-schedule clusters of that size. */
+int st_rnn_cluster_supported(int kind, int H);
+int st_rnn_cluster_fwd(int kind, int H, int nsteps, const int* batch_sizes_host, int t_begin, int t_end,
+                       const float* Gx, const void* Whh_bf16, const float* bhh, const float* h0, const void* h0_bf16,
+                       const float* c0, float* Hs, void* Hs_bf16, float* Cs, float* gates, float* ghn,
+                       st_stream_t stream);
 int st_rnn_seq_tc_supported(int kind, int H);
 int st_rnn_seq_tc_fwd(int kind, int H, int nsteps, const int* batch_sizes_host, int t_begin, int t_end,
                       const float* Gx,

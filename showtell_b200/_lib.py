@@ -38,6 +38,7 @@ _SIGS = {
     "st_gemm_bf16": (_I, [_I, _I, _I, _P, _I, _P, _I, _P, _I, _I, _P, _F, _F, _P]),
     "st_cast_bf16": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _P]),
     "st_vocab_ce_parts": (_I, [_I]),
+    "st_debug_gemm_variant": (_I, [_I]),
     "st_vocab_ce_fwd": (_I, [_I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "st_vocab_ce_bwd": (_I, [_I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _F, _P, _I, _P, _I, _P]),
     "st_pack_inputs": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _IP, _P]),
@@ -49,6 +50,8 @@ _SIGS = {
     "st_rnn_seq_fwd": (_I, [_I, _I, _I, _IP, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "st_rnn_seq_bwd": (_I, [_I, _I, _I, _IP, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "st_rnn_seq_tc_supported": (_I, [_I, _I]),
+    "st_rnn_cluster_supported": (_I, [_I, _I]),
+    "st_rnn_cluster_fwd": (_I, [_I, _I, _I, _IP, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "st_rnn_seq_tc_fwd": (_I, [_I, _I, _I, _IP, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "st_rnn_seq_tc_bwd": (_I, [_I, _I, _I, _IP, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P,
                                _P, _P, _P]),

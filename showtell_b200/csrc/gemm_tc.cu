@@ -1,20 +1,34 @@
 // bf16 GEMM on the 5th-generation tensor cores: tcgen05.mma (UMMA) with the accumulator in TMEM,
 // operands staged in shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle), mbarrier
-// pipelines between the roles, persistent CTAs (one per SM) walking a static tile schedule.
+// pipelines between the roles, persistent CTAs walking a static schedule.
 //
 //     D[M,N] = A[M,K] . B[N,K]^T          A, B bf16 row-major with K contiguous ("K-major")
 //
 // This is the nn.Linear shape (weights are (out, in)); the transposed products of the backward
 // pass are brought to the same form by the caller with transposed bf16 copies.
 //
+// Two kernels share one epilogue:
+//   gemm_tc2_kernel  (large problems) -- CTA PAIRS (cluster 2x1x1, tcgen05.mma.cta_group::2): one 256x256
+//       tile per pair, each CTA holds its 128 rows of A and HALF of the B tile (128 rows), so a 64-deep
+//       k-block costs every SM 32 KB of L2 ingress for 512 tensor-pipe clocks (64 B/clk -- the 1-CTA
+//       128x256 tile needs 96 B/clk and is port-bound at <= 67 %).  The leader CTA issues the MMAs for
+//       both; TMA of both CTAs completes on the leader's mbarrier; tcgen05.commit multicasts "slot free"
+//       / "accumulator full" to both.  Schedule: data-parallel tiles, or STREAM-K (the k-blocks of all
+//       tiles are cut into equal contiguous ranges, one per pair; tiles cut by a range boundary are
+//       accumulated with vector fp32 reductions into a zeroed C) when whole tiles would leave a large
+//       part of the GPU idle (dX / dW of the vocabulary projection: 40 / 80 tiles on 74 pairs).
+//   gemm_tc_kernel   (small problems: per-step products of the attention loop) -- one CTA per 128x128
+//       or 128x256 tile.
 // CTA = 384 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane each), warp 2 =
 // TMEM allocator, warps 4..11 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31 = 32 rows and one
-// 64-column half of the 128x128 tile; two warps per SM sub-partition hide each other's latency).  6-stage smem ring (A 16 KB + B 16 KB per stage), 2 TMEM accumulator stages
-// (2 x 128 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// half of the tile's columns; two warps per SM sub-partition hide each other's latency).  2 TMEM
+// accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
-// Epilogues (template parameter):
-//   EPI_STORE   C = alpha*acc + bias[n]  as fp32 or bf16                     (W_ih / att1 hoists, dX, dW)
-//   EPI_CE_FWD  per-row online (max, sum-exp) over this tile's 128 vocabulary columns + the
+// Epilogues (template parameter); a warp's 32x32 chunk goes through a private swizzled shared-memory
+// staging tile so that every global store instruction writes whole 128-byte lines (the TMEM layout
+// has one ROW per lane: storing straight from registers would touch 32 lines per instruction):
+//   EPI_STORE   C = alpha*acc + bias[n] (+ beta*C)  as fp32 or bf16              (hoists, dX, dW)
+//   EPI_CE_FWD  per-row online (max, sum-exp) over this tile's vocabulary columns + the
 //               target logit: the (N,V) logits are never written              (rnn.py:33 + main.py:149)
 //   EPI_CE_BWD  recomputes the logits tile and writes dlogits = (softmax - onehot)*scale as bf16,
 //               row-major and transposed, the operands of the two backward GEMMs
@@ -32,17 +46,24 @@ namespace {
 constexpr int BM = 128, BK = 64, UK = 16;
 constexpr int ACC_STAGES = 2, NTHREADS = 384;  // 4 control warps + 8 epilogue warps
 constexpr uint32_t A_BYTES = BM * BK * 2;
-// Tile width BN (template): 256 where the problem has enough tiles, else 128.  An SM ingests ~64 B/clk
-// from L2; a 128x128x64 k-block needs 32 KB for 256 MMA clocks (128 B/clk: port-bound at <= 50 % of the
-// tensor pipe), a 128x256x64 k-block 48 KB for 512 clocks (96 B/clk: <= 67 %).
+constexpr uint32_t STG_BYTES = 8 * 4096;       // epilogue staging: 4 KB per epilogue warp
+// Tile width BN (template, 1-CTA kernel): 256 where the problem has enough tiles, else 128.
 template <int BN> struct TileCfg {
   static constexpr uint32_t B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;
-  static constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256;
+  static constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + STG_BYTES + 256;
+};
+// CTA-pair kernel: per CTA and stage A 128x64 + B 128x64 (its half of the 256-row B tile).
+struct PairCfg {
+  static constexpr int BN = 256, STAGES = 5;
+  static constexpr uint32_t STAGE_BYTES = 2 * A_BYTES, TMEM_COLS = ACC_STAGES * BN;
+  static constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + STG_BYTES + 256;
 };
 
 enum { EPI_STORE = 0, EPI_CE_FWD = 1, EPI_CE_BWD = 2 };
+int g_variant = 0;   // st_debug_gemm_variant: 0 = choose, 128 / 256 = single-CTA tile width, 2 = CTA pairs
+int g_streamk = 1;   // st_debug_gemm_variant(v | 0x1000) turns stream-K off
 
 struct TcParams {
   int M, N, K;
@@ -59,8 +80,278 @@ struct TcParams {
   float scale;
   __nv_bfloat16 *P, *PT;  // bwd: (M, ldp) and (N, ldpt)
   int ldp, ldpt;
+  int streamk;            // pair kernel: 1 = stream-K schedule (C zeroed by the launcher)
 };
 
+__device__ __forceinline__ float ex2_fast(float x) {   // 2^x, MUFU only (inputs here are <= ~0: no range fix-up needed)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void red_add_v4(float* addr, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// One epilogue warp's part of an accumulator tile: 32 rows (TMEM lanes, row = row0 + lane) x
+// `nchunks` chunks of 32 columns starting at column n0 + 32*chunk0 of the problem.  `stg` = this warp's
+// 4 KB staging tile.  `partial`: the accumulator holds only a slice of K (stream-K) -> reduce into C;
+// `first_k`: the slice starts at k = 0 (adds the bias).  `part`: index of this warp's CE partial.
+template <int EPI>
+__device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tbase, int row0, int n0, int chunk0, int nchunks,
+                                              uint8_t* stg, int lane, bool partial, bool first_k, int part) {
+  constexpr float LOG2E = 1.4426950408889634f;
+  const int row = row0 + lane;
+  const bool row_ok = row < p.M;
+  const uint32_t stg_s = smem_u32(stg);
+  float run_m = -FLT_MAX, run_s = 0.f, tl = 0.f;  // EPI_CE_FWD
+  bool have_tl = false;
+  int tgt = -1;
+  float lse_l2 = 0.f;
+  if (EPI != EPI_STORE && row_ok) tgt = (int)p.target[row];
+  if (EPI == EPI_CE_BWD && row_ok) lse_l2 = p.lse[row] * LOG2E;
+  const float* bias = (p.bias && first_k) ? p.bias : nullptr;
+  // 16-byte vector stores need an aligned base and leading dimension (views into wider buffers may have neither)
+  const bool c_vec = EPI == EPI_STORE && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (p.ldc & (p.c_bf16 ? 7 : 3)) == 0;
+  const bool p_vec = EPI == EPI_CE_BWD && (reinterpret_cast<uintptr_t>(p.P) & 15) == 0 && (p.ldp & 7) == 0;
+
+#pragma unroll 1
+  for (int cc = 0; cc < nchunks; ++cc) {
+    const int c = chunk0 + cc;
+    const int nb = n0 + c * 32;
+    if (nb >= p.N) break;                          // chunk entirely past the last column
+    float v[32];
+    tmem_ld32(tbase + c * 32, v);
+    const bool full = nb + 32 <= p.N;
+    // bias: uniform (same address in every lane) 128-bit loads on full chunks
+    if (bias) {
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nb + j));
+          if (EPI == EPI_STORE) {
+            v[j] = fmaf(p.alpha, v[j], b4.x); v[j + 1] = fmaf(p.alpha, v[j + 1], b4.y);
+            v[j + 2] = fmaf(p.alpha, v[j + 2], b4.z); v[j + 3] = fmaf(p.alpha, v[j + 3], b4.w);
+          } else {
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float bj = (nb + j < p.N) ? bias[nb + j] : 0.f;
+          v[j] = (EPI == EPI_STORE) ? fmaf(p.alpha, v[j], bj) : v[j] + bj;
+        }
+      }
+    } else if (EPI == EPI_STORE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+    }
+
+    if (EPI == EPI_STORE) {
+      if (p.c_bf16) {
+        __nv_bfloat16* C = reinterpret_cast<__nv_bfloat16*>(p.C);
+        if (full && c_vec) {
+          // staging tile: 32 rows x 64 B, 16-byte groups XOR-swizzled by (row >> 1) & 3
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint32_t a = stg_s + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf2(v[8 * g], v[8 * g + 1])),
+                         "r"(pack_bf2(v[8 * g + 2], v[8 * g + 3])), "r"(pack_bf2(v[8 * g + 4], v[8 * g + 5])),
+                         "r"(pack_bf2(v[8 * g + 6], v[8 * g + 7]))
+                         : "memory");
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {             // 8 rows x 64 B per instruction
+            const int r = i * 8 + (lane >> 2), g = lane & 3;
+            uint4 o;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                         : "r"(stg_s + r * 64 + ((g ^ ((r >> 1) & 3)) << 4)));
+            if (row0 + r < p.M) *reinterpret_cast<uint4*>(C + (size_t)(row0 + r) * p.ldc + nb + g * 8) = o;
+          }
+          __syncwarp();
+        } else if (row_ok) {
+          __nv_bfloat16* out = C + (size_t)row * p.ldc + nb;
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) out[j] = __float2bfloat16(v[j]);
+        }
+      } else {
+        float* C = reinterpret_cast<float*>(p.C);
+        if (full && c_vec) {
+          // staging tile: 32 rows x 128 B, 16-byte groups XOR-swizzled by row & 7
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const uint32_t a = stg_s + lane * 128 + ((g ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * g]), "f"(v[4 * g + 1]),
+                         "f"(v[4 * g + 2]), "f"(v[4 * g + 3])
+                         : "memory");
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {             // 4 rows x 128 B per instruction
+            const int r = i * 4 + (lane >> 3), g = lane & 7;
+            float4 o;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                         : "r"(stg_s + r * 128 + ((g ^ (r & 7)) << 4)));
+            if (row0 + r < p.M) {
+              float* out = C + (size_t)(row0 + r) * p.ldc + nb + g * 4;
+              if (partial) {
+                red_add_v4(out, o);
+              } else {
+                if (p.beta != 0.f) {
+                  const float4 c4 = *reinterpret_cast<const float4*>(out);
+                  o.x = fmaf(p.beta, c4.x, o.x); o.y = fmaf(p.beta, c4.y, o.y);
+                  o.z = fmaf(p.beta, c4.z, o.z); o.w = fmaf(p.beta, c4.w, o.w);
+                }
+                *reinterpret_cast<float4*>(out) = o;
+              }
+            }
+          }
+          __syncwarp();
+        } else if (row_ok) {
+          float* out = C + (size_t)row * p.ldc + nb;
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) {
+              if (partial) atomicAdd(out + j, v[j]);
+              else out[j] = (p.beta != 0.f) ? fmaf(p.beta, out[j], v[j]) : v[j];
+            }
+        }
+      }
+    } else if (EPI == EPI_CE_FWD) {
+      if (!full) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nb + j >= p.N) v[j] = -FLT_MAX;
+      }
+      if (tgt >= nb && tgt < nb + 32) {  // rare: pick the target logit
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nb + j == tgt) tl = v[j];
+        have_tl = true;
+      }
+      float cm = v[0];
+#pragma unroll
+      for (int j = 1; j < 32; ++j) cm = fmaxf(cm, v[j]);
+      const float nm = fmaxf(run_m, cm);
+      const float nml2 = nm * LOG2E;
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {            // exp(-huge) = 0 on masked columns
+        s0 += ex2_fast(fmaf(v[j], LOG2E, -nml2));
+        s1 += ex2_fast(fmaf(v[j + 1], LOG2E, -nml2));
+      }
+      run_s = fmaf(run_s, ex2_fast(fmaf(run_m, LOG2E, -nml2)), s0 + s1);
+      run_m = nm;
+    } else {  // EPI_CE_BWD: d = (softmax - onehot) * scale
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = ex2_fast(fmaf(v[j], LOG2E, -lse_l2)) * p.scale;
+      if (tgt >= nb && tgt < nb + 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nb + j == tgt) v[j] -= p.scale;
+      }
+      uint32_t w[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w[j] = pack_bf2(v[2 * j], v[2 * j + 1]);
+      if (full && p_vec) {                        // row-major copy through the staging tile (see EPI_STORE bf16)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t a = stg_s + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[4 * g]), "r"(w[4 * g + 1]),
+                       "r"(w[4 * g + 2]), "r"(w[4 * g + 3])
+                       : "memory");
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = i * 8 + (lane >> 2), g = lane & 3;
+          uint4 o;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                       : "r"(stg_s + r * 64 + ((g ^ ((r >> 1) & 3)) << 4)));
+          if (row0 + r < p.M) *reinterpret_cast<uint4*>(p.P + (size_t)(row0 + r) * p.ldp + nb + g * 8) = o;
+        }
+        __syncwarp();
+      } else if (row_ok) {
+        __nv_bfloat16* out = p.P + (size_t)row * p.ldp + nb;
+        for (int j = 0; j < 32; ++j)
+          if (nb + j < p.N) out[j] = __float2bfloat16(v[j]);
+      }
+      if (p.PT) {
+        // transposed copy: lanes are consecutive rows.  Lane pairs swap halves so that every lane stores 4 B:
+        // even lanes hold (row, row+1) of the even columns, odd lanes of the odd columns.
+        const bool odd = lane & 1;
+        const int prow = row & ~1;                  // first row of this lane pair
+        const bool pair_ok = (prow + 1 < p.M) && ((p.ldpt & 1) == 0) && (reinterpret_cast<uintptr_t>(p.PT) & 3) == 0;
+        if (full && __all_sync(0xffffffffu, pair_ok)) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            // w[j] = (col 2j, col 2j+1) of my row.  Send the half the partner needs, keep the other.
+            const uint32_t mine = w[j];
+            const uint32_t send = odd ? (mine & 0xffffu) : (mine >> 16);          // odd lanes give col 2j, even give col 2j+1
+            const uint32_t got = __shfl_xor_sync(0xffffffffu, send, 1);
+            // even lane: col 2j of (row, row+1) = (my low, partner low); odd lane: col 2j+1 = (partner high, my high)
+            const uint32_t o = odd ? (got | (mine & 0xffff0000u)) : ((mine & 0xffffu) | (got << 16));
+            const int col = nb + 2 * j + (odd ? 1 : 0);
+            *reinterpret_cast<uint32_t*>(p.PT + (size_t)col * p.ldpt + prow) = o;
+          }
+        } else if (row_ok) {
+          __nv_bfloat16* outT = p.PT + (size_t)nb * p.ldpt + row;
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < p.N) {
+              const uint32_t h = (j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffffu);
+              outT[(size_t)j * p.ldpt] = __ushort_as_bfloat16((unsigned short)h);
+            }
+        }
+      }
+    }
+  }
+  if (EPI == EPI_CE_FWD && row_ok) {
+    p.pmax[(size_t)row * p.npart + part] = run_m;
+    p.psum[(size_t)row * p.npart + part] = run_s;
+    if (have_tl) p.tlogit[row] = tl;
+  }
+}
+
+// Static schedule of one worker (a CTA, or a CTA pair): a sequence of segments (tile, [k0, k1)).
+// Data-parallel: whole tiles, round-robin.  Stream-K: the worker's contiguous slice of the (tile-major)
+// k-block sequence; tiles cut by a slice boundary are reduced into C by their epilogues.
+struct WorkSched {
+  int kb, ntiles, npairs, streamk;
+  long cur, end;      // stream-K: global k-block range
+  int tile;           // data-parallel: next tile
+  __device__ WorkSched(int ntiles_, int kb_, int npairs_, int pair, int streamk_)
+      : kb(kb_), ntiles(ntiles_), npairs(npairs_), streamk(streamk_) {
+    if (streamk) {
+      const long total = (long)ntiles * kb, per = (total + npairs - 1) / npairs;
+      cur = per * pair;
+      end = cur + per < total ? cur + per : total;
+    } else {
+      tile = pair; cur = 0; end = 0;
+    }
+  }
+  __device__ bool next(int& t, int& k0, int& k1) {
+    if (streamk) {
+      if (cur >= end) return false;
+      t = (int)(cur / kb);
+      k0 = (int)(cur - (long)t * kb);
+      const long left = end - cur;
+      k1 = (k0 + left < kb) ? (int)(k0 + left) : kb;
+      cur += k1 - k0;
+      return true;
+    }
+    if (tile >= ntiles) return false;
+    t = tile; k0 = 0; k1 = kb;
+    tile += npairs;
+    return true;
+  }
+};
+
+// ------------------------------------------------------------------------------------ 1-CTA kernel
 template <int EPI, int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -69,7 +360,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr uint32_t STAGE_BYTES = TileCfg<BN>::STAGE_BYTES, TMEM_COLS = TileCfg<BN>::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint8_t* stg = smem + (size_t)STAGES * STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(stg + STG_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + ACC_STAGES;
@@ -108,11 +400,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------------------------------------------------- TMA producer
-      int stage = 0;
+      WorkSched sched(ntiles, kb, gridDim.x, blockIdx.x, p.streamk);
+      int stage = 0, tile, k0, k1;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      while (sched.next(tile, k0, k1)) {
         const int m0 = (nfast ? tile / nt : tile % mt) * BM, n0 = (nfast ? tile % nt : tile / mt) * BN;
-        for (int k = 0; k < kb; ++k) {
+        for (int k = k0; k < k1; ++k) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* a = smem + (size_t)stage * STAGE_BYTES;
@@ -125,13 +418,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     if (lane == 0) {  // ---------------------------------------------------------- MMA issuer
       constexpr uint32_t idesc = umma_idesc(BM, BN);
-      int stage = 0, acc = 0;
+      WorkSched sched(ntiles, kb, gridDim.x, blockIdx.x, p.streamk);
+      int stage = 0, acc = 0, tile, k0, k1;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      while (sched.next(tile, k0, k1)) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int k = 0; k < kb; ++k) {
+        for (int k = k0; k < k1; ++k) {
           mbar_wait(&full[stage], phase);  // TMA bytes have landed
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + (size_t)stage * STAGE_BYTES);
@@ -139,7 +433,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int kk = 0; kk < BK / UK; ++kk)
             tc_mma(d_tmem, umma_desc_k128(a_addr + kk * UK * 2), umma_desc_k128(b_addr + kk * UK * 2), idesc,
-                   (k | kk) != 0);
+                   (k > k0) || (kk != 0));
           tc_commit(&empty[stage]);  // smem slot free once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -150,161 +444,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 4) {  // ------------------------------------------------------ epilogue
     // 8 warps: warp w owns TMEM lanes 32*(w%4)..+31 (32 rows) and one half of the tile's BN columns.
     const int ew = warp & 3, half = (warp - 4) >> 2;
-    constexpr float LOG2E = 1.4426950408889634f;
-    int acc = 0;
+    WorkSched sched(ntiles, kb, gridDim.x, blockIdx.x, p.streamk);
+    int acc = 0, tile, k0, k1;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    while (sched.next(tile, k0, k1)) {
       const int m0 = (nfast ? tile / nt : tile % mt) * BM, n0 = (nfast ? tile % nt : tile / mt) * BN;
-      const int row = m0 + ew * 32 + lane;
-      const bool row_ok = row < p.M;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t tbase = tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16);
-
-      float run_m = -FLT_MAX, run_s = 0.f, tl = 0.f;  // EPI_CE_FWD
-      bool have_tl = false;
-      int tgt = -1;
-      float lse_l2 = 0.f;
-      if (EPI != EPI_STORE && row_ok) tgt = (int)p.target[row];
-      if (EPI == EPI_CE_BWD && row_ok) lse_l2 = p.lse[row] * LOG2E;
-
-#pragma unroll 1
-      for (int cc = 0; cc < BN / 64; ++cc) {
-        const int c = half * (BN / 64) + cc;
-        float v[32];
-        tmem_ld32(tbase + c * 32, v);
-        const int nb = n0 + c * 32;
-        const bool full = nb + 32 <= p.N;
-        if (EPI != EPI_STORE && nb >= p.N) continue;  // chunk entirely past the vocabulary
-        // bias: uniform (same address in every lane) 128-bit loads on full chunks
-        if (p.bias) {
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
-              if (EPI == EPI_STORE) {
-                v[j] = fmaf(p.alpha, v[j], b4.x); v[j + 1] = fmaf(p.alpha, v[j + 1], b4.y);
-                v[j + 2] = fmaf(p.alpha, v[j + 2], b4.z); v[j + 3] = fmaf(p.alpha, v[j + 3], b4.w);
-              } else {
-                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float bj = (nb + j < p.N) ? p.bias[nb + j] : 0.f;
-              v[j] = (EPI == EPI_STORE) ? fmaf(p.alpha, v[j], bj) : v[j] + bj;
-            }
-          }
-        } else if (EPI == EPI_STORE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
-        }
-
-        if (EPI == EPI_STORE) {
-          if (row_ok) {
-            if (p.c_bf16) {
-              __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + nb;
-              if (full && (p.ldc & 7) == 0) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  uint32_t w[4];
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * q], v[j + 2 * q + 1]);
-                    w[q] = *reinterpret_cast<uint32_t*>(&h);
-                  }
-                  *reinterpret_cast<uint4*>(out + j) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-              } else {
-                for (int j = 0; j < 32; ++j)
-                  if (nb + j < p.N) out[j] = __float2bfloat16(v[j]);
-              }
-            } else {
-              float* out = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + nb;
-              if (full && (p.ldc & 3) == 0) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                  if (p.beta != 0.f) {
-                    const float4 c4 = *reinterpret_cast<const float4*>(out + j);
-                    o.x = fmaf(p.beta, c4.x, o.x); o.y = fmaf(p.beta, c4.y, o.y);
-                    o.z = fmaf(p.beta, c4.z, o.z); o.w = fmaf(p.beta, c4.w, o.w);
-                  }
-                  *reinterpret_cast<float4*>(out + j) = o;
-                }
-              } else {
-                for (int j = 0; j < 32; ++j)
-                  if (nb + j < p.N) out[j] = (p.beta != 0.f) ? fmaf(p.beta, out[j], v[j]) : v[j];
-              }
-            }
-          }
-        } else if (EPI == EPI_CE_FWD) {
-          if (!full) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j >= p.N) v[j] = -FLT_MAX;
-          }
-          if (tgt >= nb && tgt < nb + 32) {  // rare: pick the target logit
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j == tgt) tl = v[j];
-            have_tl = true;
-          }
-          float cm = v[0];
-#pragma unroll
-          for (int j = 1; j < 32; ++j) cm = fmaxf(cm, v[j]);
-          const float nm = fmaxf(run_m, cm);
-          const float nml2 = nm * LOG2E;
-          float s = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) s += exp2f(fmaf(v[j], LOG2E, -nml2));  // exp(-huge) = 0 on masked columns
-          run_s = fmaf(run_s, exp2f(fmaf(run_m, LOG2E, -nml2)), s);
-          run_m = nm;
-        } else {  // EPI_CE_BWD: d = (softmax - onehot) * scale
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = exp2f(fmaf(v[j], LOG2E, -lse_l2)) * p.scale;
-          if (tgt >= nb && tgt < nb + 32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nb + j == tgt) v[j] -= p.scale;
-          }
-          if (row_ok) {
-            __nv_bfloat16* out = p.P + (size_t)row * p.ldp + nb;
-            if (full && (p.ldp & 7) == 0) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint32_t w[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  __nv_bfloat162 h = __floats2bfloat162_rn(v[j + 2 * q], v[j + 2 * q + 1]);
-                  w[q] = *reinterpret_cast<uint32_t*>(&h);
-                }
-                *reinterpret_cast<uint4*>(out + j) = make_uint4(w[0], w[1], w[2], w[3]);
-              }
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (nb + j < p.N) out[j] = __float2bfloat16(v[j]);
-            }
-            if (p.PT) {  // transposed copy: lanes are consecutive rows -> 64 B contiguous per column
-              __nv_bfloat16* outT = p.PT + (size_t)nb * p.ldpt + row;
-              if (full) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) outT[(size_t)j * p.ldpt] = __float2bfloat16(v[j]);
-              } else {
-                for (int j = 0; j < 32; ++j)
-                  if (nb + j < p.N) outT[(size_t)j * p.ldpt] = __float2bfloat16(v[j]);
-              }
-            }
-          }
-        }
-      }
-      if (EPI == EPI_CE_FWD && row_ok) {
-        const int part = (n0 / BN) * 2 + half;
-        p.pmax[(size_t)row * p.npart + part] = run_m;
-        p.psum[(size_t)row * p.npart + part] = run_s;
-        if (have_tl) p.tlogit[row] = tl;
-      }
+      epilogue_warp<EPI>(p, tbase, m0 + ew * 32, n0, half * (BN / 64), BN / 64, stg + (warp - 4) * 4096, lane,
+                         !(k0 == 0 && k1 == kb), k0 == 0, (n0 / BN) * 2 + half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -317,6 +466,186 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// --------------------------------------------------------------------------------- CTA-pair kernel
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(0u));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load into THIS CTA's shared memory; the bytes complete on the LEADER CTA's mbarrier (peer bit cleared).
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_at(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_at(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (spin > (1u << 26)) __trap();
+  }
+}
+// D[tmem of both CTAs] (+)= A . B^T over the CTA pair: M = 256 (128 rows per CTA), N = 256 (128 B rows per CTA)
+__device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// all prior MMAs of this thread retired -> one arrival on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const TcParams p) {
+  constexpr int STAGES = PairCfg::STAGES, BN = PairCfg::BN;
+  constexpr uint32_t STAGE_BYTES = PairCfg::STAGE_BYTES, TMEM_COLS = PairCfg::TMEM_COLS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stg = smem + (size_t)STAGES * STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(stg + STG_BYTES);   // used in the leader: 2 producers arrive (+ their bytes)
+  uint64_t* empty = full + STAGES;                                  // per CTA: multicast commit
+  uint64_t* tfull = empty + STAGES;                                 // per CTA: multicast commit
+  uint64_t* tempty = tfull + ACC_STAGES;                            // used in the leader: 16 epilogue warps arrive
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int mt = (p.M + 2 * BM - 1) / (2 * BM), nt = (p.N + BN - 1) / BN;
+  const int ntiles = mt * nt, kb = (p.K + BK - 1) / BK;
+  const bool nfast = nt < mt;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 2);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < ACC_STAGES; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 16);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    if (lane == 0) {  // ------------------------------------------------- TMA producer (both CTAs)
+      WorkSched sched(ntiles, kb, npairs, pair, p.streamk);
+      int stage = 0, tile, k0, k1;
+      uint32_t phase = 0;
+      while (sched.next(tile, k0, k1)) {
+        const int m0 = (nfast ? tile / nt : tile % mt) * 2 * BM + (int)rank * BM;
+        const int n0 = (nfast ? tile % nt : tile / mt) * BN + (int)rank * (BN / 2);
+        for (int k = k0; k < k1; ++k) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx_at(mapa_rank0(smem_u32(&full[stage])), STAGE_BYTES);
+          uint8_t* a = smem + (size_t)stage * STAGE_BYTES;
+          tma_load_2d_pair(a, &tmA, k * BK, m0, &full[stage]);
+          tma_load_2d_pair(a + A_BYTES, &tmB, k * BK, n0, &full[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {  // ------------------------------------ MMA issuer (leader CTA only)
+      constexpr uint32_t idesc = umma_idesc(2 * BM, BN);
+      WorkSched sched(ntiles, kb, npairs, pair, p.streamk);
+      int stage = 0, acc = 0, tile, k0, k1;
+      uint32_t phase = 0, acc_phase = 0;
+      while (sched.next(tile, k0, k1)) {
+        mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);  // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int k = k0; k < k1; ++k) {
+          mbar_wait(&full[stage], phase);  // both CTAs' TMA bytes have landed
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / UK; ++kk)
+            tc_mma_pair(d_tmem, umma_desc_k128(a_addr + kk * UK * 2), umma_desc_k128(b_addr + kk * UK * 2), idesc,
+                        (k > k0) || (kk != 0));
+          tc_commit_pair(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_pair(&tfull[acc]);
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {  // ------------------------------------------------------ epilogue (both CTAs)
+    const int ew = warp & 3, half = (warp - 4) >> 2;
+    WorkSched sched(ntiles, kb, npairs, pair, p.streamk);
+    int acc = 0, tile, k0, k1;
+    uint32_t acc_phase = 0;
+    while (sched.next(tile, k0, k1)) {
+      const int m0 = (nfast ? tile / nt : tile % mt) * 2 * BM + (int)rank * BM;
+      const int n0 = (nfast ? tile % nt : tile / mt) * BN;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16);
+      epilogue_warp<EPI>(p, tbase, m0 + ew * 32, n0, half * (BN / 64), BN / 64, stg + (warp - 4) * 4096, lane,
+                         !(k0 == 0 && k1 == kb), k0 == 0, (n0 / BN) * 2 + half);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_at(mapa_rank0(smem_u32(&tempty[acc])));
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer may still be reading this CTA's operands / signalling its barriers
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -359,22 +688,44 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, int rows, int co
   }
 }
 
+// Stream-K pays (a zero fill of C + fp32 reductions of the cut tiles) when whole tiles would leave a good part
+// of the workers idle and K is long enough to cut: dX / dW of the vocabulary projection (80 tiles on 148 SMs),
+// dW_hh / dW_ih (32 tiles), dW_enc of the attention (32 tiles, 392 k-blocks).  Cost model fitted on B200
+// (tools/time_kernels.py gemmv): a k-block costs ~0.42 us of main loop; cutting every tile costs ~12 us of
+// un-overlapped reductions at the end + ~0.15 us per MB of C.
+template <int EPI>
+inline bool want_streamk(const TcParams& p, int ntiles, int kb, int workers) {
+  if (g_streamk == 0) return false;
+  if (!(EPI == EPI_STORE && !p.c_bf16 && p.beta == 0.f && (p.ldc & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && kb >= 16))
+    return false;
+  const long rounds = (ntiles + workers - 1) / workers;
+  const long per = ((long)ntiles * kb + workers - 1) / workers;
+  const double saved_us = 0.42 * (double)(rounds * kb - per);
+  const double cost_us = 12.0 + 0.15 * ((double)p.M * p.N * 4.0 / 1e6);
+  return saved_us > cost_us;
+}
+
 template <int EPI, int BN>
-int launch_tc_bn(const TcParams& p, const void* A, int lda, const void* B, int ldb, cudaStream_t s, int sms) {
+int launch_tc_bn(TcParams p, const void* A, int lda, const void* B, int ldb, cudaStream_t s, int sms) {
   CUtensorMap tmA, tmB;
   ST_TRY(make_tmap(&tmA, A, p.M, p.K, lda, BM, "A"));
   ST_TRY(make_tmap(&tmB, B, p.N, p.K, ldb, BN, "B"));
   auto kern = gemm_tc_kernel<EPI, BN>;
   ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<BN>::SMEM_BYTES));
-  const int ntiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
-  const int grid = ntiles < sms ? ntiles : sms;
+  const int ntiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN), kb = (p.K + BK - 1) / BK;
+  int grid = ntiles < sms ? ntiles : sms;
+  p.streamk = want_streamk<EPI>(p, ntiles, kb, sms) ? 1 : 0;
+  if (p.streamk) {
+    grid = sms;
+    ST_CUDA_TRY(cudaMemset2DAsync(p.C, (size_t)p.ldc * 4, 0, (size_t)p.N * 4, p.M, s));
+  }
   kern<<<grid, NTHREADS, TileCfg<BN>::SMEM_BYTES, s>>>(tmA, tmB, p);
   ST_LAUNCH_TRY("gemm_tc_kernel");
   return ST_OK;
 }
 
-// Tile width by estimated time: rounds of the persistent grid x clocks per k-block (measured ~600 for a
-// 128-wide and ~750 for a 256-wide tile, both L2-port-bound).
+// Tile width without stream-K: estimated time = rounds of the persistent grid x clocks per k-block.
 inline int pick_bn(int M, int N, int sms) {
   if (N <= 128) return 128;
   const long mt = (M + BM - 1) / BM;
@@ -383,11 +734,53 @@ inline int pick_bn(int M, int N, int sms) {
 }
 
 template <int EPI>
+int launch_tc_pair(TcParams p, const void* A, int lda, const void* B, int ldb, cudaStream_t s, int sms) {
+  CUtensorMap tmA, tmB;
+  ST_TRY(make_tmap(&tmA, A, p.M, p.K, lda, BM, "A"));
+  ST_TRY(make_tmap(&tmB, B, p.N, p.K, ldb, BM, "B"));
+  auto kern = gemm_tc2_kernel<EPI>;
+  ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairCfg::SMEM_BYTES));
+  const int pairs = sms / 2;
+  const int ntiles = ((p.M + 255) / 256) * ((p.N + 255) / 256), kb = (p.K + BK - 1) / BK;
+  p.streamk = want_streamk<EPI>(p, ntiles, kb, pairs) ? 1 : 0;
+  int npairs = ntiles < pairs ? ntiles : pairs;
+  if (p.streamk) {
+    npairs = pairs;
+    ST_CUDA_TRY(cudaMemset2DAsync(p.C, (size_t)p.ldc * 4, 0, (size_t)p.N * 4, p.M, s));
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * npairs);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = PairCfg::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  ST_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  note_launch();
+  return ST_OK;
+}
+
+// Kernel + tile choice for a problem: 128 / 256 = single-CTA kernel with that tile width; 2 = CTA-pair kernel
+// (only when pinned: measured on B200 it does not beat the 256-wide single-CTA tiles).
+template <int EPI>
+inline int pick_variant(const TcParams& p, int sms) {
+  if (g_variant) return g_variant;
+  if (p.N > 128) {
+    const int ntiles = ((p.M + BM - 1) / BM) * ((p.N + 255) / 256), kb = (p.K + BK - 1) / BK;
+    if (want_streamk<EPI>(p, ntiles, kb, sms)) return 256;
+  }
+  return pick_bn(p.M, p.N, sms);
+}
+
+template <int EPI>
 int launch_tc(const TcParams& p, const void* A, int lda, const void* B, int ldb, cudaStream_t s, int bn = 0) {
   ST_REQUIRE(p.M >= 1 && p.N >= 1 && p.K >= 1, ST_ERR_BAD_SHAPE, "gemm_bf16: M=%d N=%d K=%d", p.M, p.N, p.K);
   int sms = 0;
   ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
-  if (bn == 0) bn = pick_bn(p.M, p.N, sms);
+  if (bn == 0) bn = pick_variant<EPI>(p, sms);
+  if (bn == 2) return launch_tc_pair<EPI>(p, A, lda, B, ldb, s, sms);
   return bn == 256 ? launch_tc_bn<EPI, 256>(p, A, lda, B, ldb, s, sms) : launch_tc_bn<EPI, 128>(p, A, lda, B, ldb, s, sms);
 }
 
@@ -419,12 +812,19 @@ int st_vocab_ce_fwd(int M, int V, int H, const void* Hs, int ldh, const void* Wv
   p.bias = bv; p.target = target; p.pmax = part_max; p.psum = part_sum; p.tlogit = tlogit;
   int sms = 0;
   ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
-  const int bn = pick_bn(M, V, sms);
-  p.npart = 2 * ((V + bn - 1) / bn);   // <= st_vocab_ce_parts(V)
+  const int bn = pick_variant<EPI_CE_FWD>(p, sms);
+  p.npart = 2 * ((V + (bn == 128 ? 127 : 255)) / (bn == 128 ? 128 : 256));   // <= st_vocab_ce_parts(V)
   ST_CUDA_TRY(cudaMemsetAsync(loss_sum, 0, sizeof(float), s));
   ST_TRY(launch_tc<EPI_CE_FWD>(p, Hs, ldh, Wv, ldw, s, bn));
   ce_combine_kernel<<<(M + 127) / 128, 128, 0, s>>>(M, p.npart, part_max, part_sum, tlogit, lse, loss_sum);
   ST_LAUNCH_TRY("ce_combine_kernel");
+  return ST_OK;
+}
+
+int st_debug_gemm_variant(int variant) {
+  st::g_streamk = (variant & 0x1000) ? 0 : 1;
+  variant &= 0xfff;
+  st::g_variant = (variant == 2 || variant == 128 || variant == 256) ? variant : 0;
   return ST_OK;
 }
 

@@ -25,6 +25,7 @@
 extern "C" int st_rowsum_bf16(float* out, const void* M, int rows, int cols, int ld, st_stream_t stream);
 
 namespace st {
+long long* g_timeline = nullptr;   // development aid, see st_debug_set_timeline
 namespace {
 
 constexpr int UT = 16, HALF = 8, NTH = 320, MAXKB = 8;
@@ -75,7 +76,6 @@ __device__ __forceinline__ void st8bf(__nv_bfloat16* p, const float (&v)[8]) {
 }
 
 // Optional per-step timeline of CTA (0,0) (development aid; NULL in production): 8 slots per step.
-long long* g_timeline = nullptr;
 __device__ __forceinline__ void stamp(long long* tl, int step, int slot) {
   if (tl != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
     long long t;

@@ -302,6 +302,9 @@ def vocab_ce_bwd(Hs, Wv, bv, target, lse, scale, want_t=True, tag=None):
     return P, PT
 
 
+USE_CLUSTER = True      # cluster-resident recurrent kernels where the shape / GPU allow them
+
+
 def rnn_seq_tc_supported(kind, H):
     return bool(_lib.load().st_rnn_seq_tc_supported(kind, H))
 
@@ -334,6 +337,17 @@ def rnn_seq_tc_fwd(kind, Gx, Whh_b, bhh, bs, *, h0=None, h0_b=None, c0=None, sav
              "barrier": _barrier(dev)}
     t0, t1 = t_range if t_range is not None else (0, len(bs))
     tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
+    if USE_CLUSTER and t1 - t0 > 1 and lib.st_rnn_cluster_supported(kind, H):
+        # whole-sequence runs: the cluster-resident kernel (h exchanged through distributed shared memory)
+        st = lib.st_rnn_cluster_fwd(kind, H, len(bs), int_array(bs), t0, t1, ptr(Gx, F32), ptr(Whh_b, BF16),
+                                    ptr(bhh, F32), ptr(h0, F32), ptr(h0_b, BF16), ptr(c0, F32), ptr(o["Hs"]),
+                                    ptr(o["Hsb"]), ptr(o["Cs"]), ptr(o["gates"]), ptr(o["ghn"]), stream_ptr())
+        if st == 0:
+            if tok:
+                TIMER.end(tok)
+            return o
+        if st != -3:
+            check(st, "st_rnn_cluster_fwd")
     st = lib.st_rnn_seq_tc_fwd(kind, H, len(bs), int_array(bs), t0, t1, ptr(Gx, F32), ptr(Whh_b, BF16),
                                ptr(bhh, F32), ptr(h0, F32), ptr(h0_b, BF16), ptr(c0, F32), ptr(o["Hs"]),
                                ptr(o["Hsb"]), ptr(o["Cs"]), ptr(o["gates"]), ptr(o["ghn"]), ptr(o["barrier"]),

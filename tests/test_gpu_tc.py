@@ -10,22 +10,47 @@ from helpers import rel_err
 DEV = "cuda:0"
 
 
+@pytest.fixture
+def gemm_variant():
+    """Pins the kernel behind st_gemm_bf16 / st_vocab_ce_* (st_debug_gemm_variant) and restores the choice."""
+    from showtell_b200 import _lib
+    lib = _lib.load()
+    yield lambda v: lib.st_debug_gemm_variant(v)
+    lib.st_debug_gemm_variant(0)
+
+
+# variant: 0 = the library's choice, 128 / 256 = single-CTA kernel, 2 = CTA-pair kernel (cta_group::2)
+@pytest.mark.parametrize("variant", [0, 128, 256, 2])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 512), (256, 384, 128), (5120, 2048, 512),
-                                   (100, 50, 40), (129, 257, 72), (640, 10000, 512), (37, 1000, 2048)])
-def test_gemm_bf16(M, N, K):
+                                   (100, 50, 40), (129, 257, 72), (640, 10000, 512), (37, 1000, 2048),
+                                   (5120, 512, 10000),      # dX of the vocabulary projection: stream-K, 40 tiles
+                                   (10000, 512, 5120),      # dW of the vocabulary projection: stream-K, ragged M
+                                   (2048, 512, 5120),       # dW_hh: 16 tiles cut into 74 ranges
+                                   (300, 700, 4000)])       # stream-K with ragged M, N and K
+def test_gemm_bf16(M, N, K, variant, gemm_variant):
     from showtell_b200 import ops
+    gemm_variant(variant)
     g = torch.Generator().manual_seed(M + N + K)
     Kp = (K + 7) // 8 * 8
     A = torch.randn(M, Kp, generator=g).to(DEV).bfloat16()[:, :K]
     B = torch.randn(N, Kp, generator=g).to(DEV).bfloat16()[:, :K]
     bias = torch.randn(N, generator=g).to(DEV)
     ref = A.double() @ B.double().t()
+    tol = 1e-5 if K <= 2048 else 4e-5                  # fp32 accumulation over K terms
     out = ops.gemm_bf16(A, B)
-    assert out.dtype == torch.float32 and rel_err(out, ref) < 1e-5
+    assert out.dtype == torch.float32 and rel_err(out, ref) < tol
     out2 = ops.gemm_bf16(A, B, bias=bias, alpha=0.5)
-    assert rel_err(out2, 0.5 * ref + bias.double()) < 1e-5
+    assert rel_err(out2, 0.5 * ref + bias.double()) < tol
     out3 = ops.gemm_bf16(A, B, bias=bias, out_dtype=torch.bfloat16)
     assert out3.dtype == torch.bfloat16 and rel_err(out3, ref + bias.double()) < 1e-2
+    acc = torch.randn(M, N, generator=g).to(DEV)
+    out4 = ops.gemm_bf16(A, B, beta=1.0, out=acc.clone())
+    assert rel_err(out4, ref + acc.double()) < tol
+    # a view into a wider buffer (ldc > N): columns outside the view are untouched (stream-K zeroes C itself)
+    wide = torch.full((M, N + 12), 7.0, device=DEV)
+    ops.gemm_bf16(A, B, bias=bias, out=wide[:, 4:4 + N])
+    assert rel_err(wide[:, 4:4 + N], ref + bias.double()) < tol
+    assert bool((wide[:, :4] == 7).all()) and bool((wide[:, 4 + N:] == 7).all())
 
 
 def test_cast_bf16():
@@ -36,9 +61,12 @@ def test_cast_bf16():
     assert d.stride(0) % 8 == 0 and dT.stride(0) % 8 == 0
 
 
-@pytest.mark.parametrize("M,V,H", [(64, 128, 64), (300, 1000, 128), (640, 10000, 512), (5120, 10000, 512)])
-def test_vocab_ce_fused(M, V, H):
+@pytest.mark.parametrize("variant", [0, 128, 256, 2])
+@pytest.mark.parametrize("M,V,H", [(64, 128, 64), (300, 1000, 128), (640, 10000, 512), (5120, 10000, 512),
+                                   (2555, 9999, 512)])
+def test_vocab_ce_fused(M, V, H, variant, gemm_variant):
     from showtell_b200 import ops
+    gemm_variant(variant)
     g = torch.Generator().manual_seed(M + V)
     Hs = (torch.randn(M, H, generator=g) * 0.5).to(DEV).bfloat16()
     Wv = (torch.randn(V, H, generator=g) * 0.1).to(DEV).bfloat16()
@@ -105,7 +133,7 @@ def test_rnn_seq_tensor_core_vs_cuda_core(kind, H, lengths, init):
 
 
 @pytest.mark.parametrize("kind", ["gru", "lstm"])
-def test_rnn_seq_tensor_core_stepwise_equals_whole(kind):
+def test_rnn_seq_tensor_core_stepwise_equals_whole(kind, monkeypatch):
     """Partial step ranges (used by the attention loop) resume from the packed state rows and must
     reproduce the whole-sequence persistent run bit for bit."""
     from showtell_b200 import _lib, ops
@@ -123,6 +151,7 @@ def test_rnn_seq_tensor_core_stepwise_equals_whole(kind):
     dHs = torch.randn(N, H, generator=g).to(DEV)
     Wb, WT = ops.cast_bf16(Whh, True, True)
     h0b = h0.bfloat16()
+    monkeypatch.setattr(ops, "USE_CLUSTER", False)       # the device-wide tc kernel on both sides
     whole = ops.rnn_seq_tc_fwd(k, Gx, Wb, bhh, bs, h0=h0, h0_b=h0b, c0=c0)
     st = None
     for t in range(len(bs)):
@@ -135,3 +164,47 @@ def test_rnn_seq_tensor_core_stepwise_equals_whole(kind):
         bst = ops.rnn_seq_tc_bwd(k, WT, bs, whole, dHs, h0=h0, c0=c0, t_range=(t + 1, t), out=bst, want_bias=False)
     assert torch.equal(bst["dGb"], bw["dGb"]) and torch.equal(bst["dGT"], bw["dGT"])
     assert torch.equal(bst["dstate"], bw["dstate"])
+
+
+@pytest.mark.parametrize("kind", ["gru", "lstm"])
+@pytest.mark.parametrize("H,lengths,init", [
+    (64, [5, 5, 4, 2], True),                                      # cluster of 2, one 16-row slice
+    (256, sorted([9, 9, 8, 6, 5, 3] * 30, reverse=True), True),    # cluster of 8, 180 ragged rows
+    (512, [20] * 200 + [13] * 56, False),                          # config-2 shape: cluster of 16, 48-row slices
+    (512, [20] * 40, True),                                        # 32-row slices
+])
+def test_rnn_cluster_resident_forward(kind, H, lengths, init, monkeypatch):
+    """The cluster-resident recurrence (h exchanged through distributed shared memory) against the
+    device-wide tcgen05 kernel (same bf16 operands, fp32 state); split step ranges resume exactly."""
+    from showtell_b200 import _lib, ops
+    k = _lib.ST_LSTM if kind == "lstm" else _lib.ST_GRU
+    G = 4 if kind == "lstm" else 3
+    bs = _lib.batch_sizes(lengths)
+    N, B0, T = sum(bs), bs[0], len(bs)
+    g = torch.Generator().manual_seed(H + 1)
+    s = 1.0 / H ** 0.5
+    Gx = torch.randn(N, G * H, generator=g).to(DEV)
+    Whh = ((torch.rand(G * H, H, generator=g) * 2 - 1) * s).to(DEV)
+    bhh = ((torch.rand(G * H, generator=g) * 2 - 1) * s).to(DEV)
+    h0 = (torch.randn(B0, H, generator=g) * 0.5).to(DEV).bfloat16().float() if init else None
+    c0 = (torch.randn(B0, H, generator=g) * 0.5).to(DEV) if (init and kind == "lstm") else None
+    h0b = None if h0 is None else h0.bfloat16()
+    Wb, _ = ops.cast_bf16(Whh, True, False)
+    lib = _lib.load()
+    assert lib.st_rnn_cluster_supported(k, H)
+    monkeypatch.setattr(ops, "USE_CLUSTER", False)
+    ref = ops.rnn_seq_tc_fwd(k, Gx, Wb, bhh, bs, h0=h0, h0_b=h0b, c0=c0)
+    monkeypatch.setattr(ops, "USE_CLUSTER", True)
+    l0 = lib.st_launch_count()
+    out = ops.rnn_seq_tc_fwd(k, Gx, Wb, bhh, bs, h0=h0, h0_b=h0b, c0=c0)
+    assert lib.st_launch_count() - l0 == 1
+    torch.cuda.synchronize()
+    for key in ("Hs", "Cs", "gates", "ghn"):
+        if ref[key] is not None:
+            assert rel_err(out[key], ref[key]) < 2e-3, key
+    assert torch.equal(out["Hsb"], out["Hs"].bfloat16())
+    # split ranges: [0, 3) then [3, T) resumes from the packed state rows
+    if T > 4:
+        part = ops.rnn_seq_tc_fwd(k, Gx, Wb, bhh, bs, h0=h0, h0_b=h0b, c0=c0, t_range=(0, 3))
+        part = ops.rnn_seq_tc_fwd(k, Gx, Wb, bhh, bs, h0=h0, h0_b=h0b, c0=c0, t_range=(3, T), out=part)
+        assert torch.equal(part["Hs"], out["Hs"]) and torch.equal(part["gates"], out["gates"])
