@@ -129,6 +129,13 @@ int st_gather_rows(float* dst, int ld_dst, const float* table, int width, const 
 int st_colsum(float* out, const void* M, int m_is_bf16, int rows, int cols, int ld, int accumulate,
               st_stream_t stream);
 
+/* dst[i][:] = src[i][:] * (*g) for n <= ST_SCALE_MAX fp32 tensors in one launch; g is a device scalar.
+ * This is autograd's chain rule for forward_loss: loss.backward() (main.py:150) hands the step's
+ * already-computed gradients a grad_output that is only known on the device. */
+#define ST_SCALE_MAX 32
+int st_scale_multi(int n, const float* const* src, float* const* dst, const int64_t* count, const float* g,
+                   st_stream_t stream);
+
 /* out[r] = sum_c M[r, c], M bf16 (rows, ld): db_v from the transposed dlogits. */
 int st_rowsum_bf16(float* out, const void* M, int rows, int cols, int ld, st_stream_t stream);
 

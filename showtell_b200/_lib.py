@@ -39,6 +39,7 @@ _SIGS = {
     "st_cast_bf16": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _P]),
     "st_vocab_ce_parts": (_I, [_I]),
     "st_debug_gemm_variant": (_I, [_I]),
+    "st_scale_multi": (_I, [_I, _P, _P, _P, _P, _P]),
     "st_vocab_ce_fwd": (_I, [_I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "st_vocab_ce_bwd": (_I, [_I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _F, _P, _I, _P, _I, _P]),
     "st_pack_inputs": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _IP, _P]),

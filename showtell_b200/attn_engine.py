@@ -316,14 +316,15 @@ class AttnLossFn(torch.autograd.Function):
         def body(feat, capt):
             Hs, alphas, sv = attn_forward(mode, P, kind, L, feat, capt, bs, need)
             target = ops.pack_targets(capt, bs)
-            loss, dHs, grads = vocab_ce(mode, P, Hs, target, dt, need)
+            loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, dt, need)
             pen_sum, Gpen = ops.attn_penalty(sv["S"], coef)
             loss = loss + coef * pen_sum.reshape(())
             g2 = None
             if need:
-                if red is not None:
-                    red.reduce([grads["linear.weight"], grads["linear.bias"]])   # overlaps with the reverse loop
+                if red is not None:                     # overlaps with the reverse loop
+                    red.reduce([grads["linear.weight"], grads["linear.bias"]], ready=vdone)
                 g2 = attn_backward(mode, P, kind, L, capt, sv, dHs, Gpen=Gpen)
+                ops.join(vdone)
                 if red is not None:
                     red.reduce([g2[n] for n in names if n in g2])
                     red.finish()
@@ -342,4 +343,4 @@ class AttnLossFn(torch.autograd.Function):
     def backward(ctx, g, _dalphas):
         if ctx.grads is None:
             raise RuntimeError("forward_loss was run without grad enabled")
-        return (None,) * 7 + tuple(ctx.grads[n] * g for n in ctx.names)
+        return (None,) * 7 + tuple(ops.scale_multi([ctx.grads[n] for n in ctx.names], g))   # chain rule, one launch

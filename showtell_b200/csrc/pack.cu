@@ -138,6 +138,33 @@ __global__ void shift_states_kernel(const __grid_constant__ StepTable tab, float
   }
 }
 
+
+// dst_i = src_i * (*g) for up to ST_SCALE_MAX tensors in one launch (blockIdx.y = tensor).
+struct ScaleTable {
+  int n;
+  const float* src[ST_SCALE_MAX];
+  float* dst[ST_SCALE_MAX];
+  long long count[ST_SCALE_MAX];
+};
+__global__ void scale_multi_kernel(const ScaleTable tab, const float* __restrict__ g) {
+  const int i = blockIdx.y;
+  const float a = __ldg(g);
+  const float* __restrict__ src = tab.src[i];
+  float* __restrict__ dst = tab.dst[i];
+  const long long n = tab.count[i];
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    const long long n4 = n >> 2;
+    for (long long j = tid; j < n4; j += nth) {
+      float4 v = __ldcs(reinterpret_cast<const float4*>(src) + j);
+      v.x *= a; v.y *= a; v.z *= a; v.w *= a;
+      reinterpret_cast<float4*>(dst)[j] = v;
+    }
+    for (long long j = (n4 << 2) + tid; j < n; j += nth) dst[j] = src[j] * a;
+  } else {
+    for (long long j = tid; j < n; j += nth) dst[j] = src[j] * a;
+  }
+}
 }  // namespace
 }  // namespace st
 
@@ -235,6 +262,31 @@ int st_shift_states(float* Hprev, const float* Hs, const float* h0, int H, int n
   ST_REQUIRE(H >= 1, ST_ERR_BAD_SHAPE, "st_shift_states: H=%d", H);
   shift_states_kernel<<<tab.off[nsteps], 128, 0, as_stream(stream)>>>(tab, Hprev, Hs, h0, H);
   ST_LAUNCH_TRY("shift_states_kernel");
+  return ST_OK;
+}
+
+int st_scale_multi(int n, const float* const* src, float* const* dst, const int64_t* count, const float* g,
+                   st_stream_t stream) {
+  using namespace st;
+  ST_REQUIRE(n >= 0 && n <= ST_SCALE_MAX, ST_ERR_BAD_SHAPE, "st_scale_multi: n=%d (max %d)", n, ST_SCALE_MAX);
+  ST_REQUIRE(n == 0 || (src && dst && count && g), ST_ERR_NULL, "st_scale_multi: NULL pointer");
+  if (n == 0) return ST_OK;
+  ScaleTable tab;
+  tab.n = n;
+  long long big = 0;
+  for (int i = 0; i < n; ++i) {
+    ST_REQUIRE(src[i] && dst[i] && count[i] >= 0, ST_ERR_NULL, "st_scale_multi: tensor %d is NULL", i);
+    tab.src[i] = src[i]; tab.dst[i] = dst[i]; tab.count[i] = count[i];
+    if (count[i] > big) big = count[i];
+  }
+  int sms = 0;
+  ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
+  long long bx = (big / 4 + 255) / 256;                 // one float4 per thread, capped at ~4 CTAs per SM in total
+  const long long cap = (4LL * sms + n - 1) / n;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  scale_multi_kernel<<<dim3((unsigned)bx, n), 256, 0, as_stream(stream)>>>(tab, g);
+  ST_LAUNCH_TRY("scale_multi_kernel");
   return ST_OK;
 }
 

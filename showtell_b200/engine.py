@@ -174,7 +174,10 @@ class BaseLogitsFn(torch.autograd.Function):
 
 def vocab_ce(mode, P, Hs, target, denom, need):
     """Mean cross-entropy of the vocabulary projection of Hs (N,H) and, if `need`, its gradients.
-    Returns (loss (0-d), dHs or None, grads dict)."""
+    Returns (loss (0-d), dHs or None, grads dict, event).  bf16 mode: the weight / bias gradients do
+    not feed the rest of the backward pass, so they run on the side stream (ops.fork) beside the BPTT
+    kernels; `event` marks their completion (None when they ran in line) -- ops.join it, or hand it to
+    the gradient reducer, before the gradients are read."""
     Wv, bv = P["linear.weight"], P["linear.bias"]
     grads = {}
     if mode == "fp32":
@@ -186,17 +189,18 @@ def vocab_ce(mode, P, Hs, target, denom, need):
             grads["linear.weight"] = ops.sgemm(dl, Hs, transA=True, tag="vocab_dw")   # dlogits^T Hs
             grads["linear.bias"] = ops.colsum(dl)
             dHs = ops.sgemm(dl, Wv, tag="vocab_dx")                                   # dlogits W_v
-        return (loss_sum / denom).reshape(()), dHs, grads
+        return (loss_sum / denom).reshape(()), dHs, grads, None
     Wb, WT = ops.cast_bf16(Wv, True, need)
     Hb, HT = ops.cast_bf16(Hs, True, need)
     loss_sum, lse = ops.vocab_ce_fwd(Hb, Wb, bv, target, tag="vocab_fwd")
-    dHs = None
+    dHs, done = None, None
     if need:
         Pm, PT = ops.vocab_ce_bwd(Hb, Wb, bv, target, lse, 1.0 / denom, tag="vocab_dlogits")
-        grads["linear.weight"] = ops.gemm_bf16(PT, HT, tag="vocab_dw")
-        grads["linear.bias"] = ops.rowsum_bf16(PT)                                    # db_v = row sums of dlogits^T
+        (grads["linear.weight"], grads["linear.bias"]), done = ops.fork(
+            lambda: (ops.gemm_bf16(PT, HT, tag="vocab_dw"), ops.rowsum_bf16(PT)),     # db_v = row sums of dlogits^T
+            uses=(PT, HT))
         dHs = ops.gemm_bf16(Pm, WT, tag="vocab_dx")
-    return (loss_sum / denom).reshape(()), dHs, grads
+    return (loss_sum / denom).reshape(()), dHs, grads, done
 
 
 class BaseLossFn(torch.autograd.Function):
@@ -224,14 +228,15 @@ class BaseLossFn(torch.autograd.Function):
         def body(feat, cap):
             Hs, layers = base_forward(mode, P, kind, L, feat, cap, bs, need)
             target = ops.pack_targets(cap, bs)
-            loss, dHs, grads = vocab_ce(mode, P, Hs, target, denom, need)
+            loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, denom, need)
             dfeat = None
             if need:
-                if red is not None:
-                    red.reduce([grads["linear.weight"], grads["linear.bias"]])   # overlaps with BPTT below
+                if red is not None:                     # overlaps with BPTT below
+                    red.reduce([grads["linear.weight"], grads["linear.bias"]], ready=vdone)
                 first = set(grads)
                 dfeat = base_backward_from_dHs(mode, P, kind, L, cap, bs, layers, dHs, grads, want_dfeat,
                                                feat.shape)
+                ops.join(vdone)
                 if red is not None:
                     red.reduce([grads[n] for n in names if n not in first])
                     red.finish()
@@ -247,5 +252,7 @@ class BaseLossFn(torch.autograd.Function):
     def backward(ctx, g):
         if ctx.grads is None:
             raise RuntimeError("forward_loss was run without grad enabled")
-        dfeat = ctx.dfeat * g if (ctx.dfeat is not None and ctx.needs_input_grad[1]) else None
-        return (None, dfeat, None, None, None) + tuple(ctx.grads[n] * g for n in ctx.names)
+        src = [ctx.grads[n] for n in ctx.names]
+        want_dfeat = ctx.dfeat is not None and ctx.needs_input_grad[1]
+        out = ops.scale_multi(src + ([ctx.dfeat] if want_dfeat else []), g)       # chain rule, one launch
+        return (None, out[-1] if want_dfeat else None, None, None, None) + tuple(out[:len(src)])

@@ -35,6 +35,43 @@ class KernelTimer:
 
 TIMER = None      # set to a KernelTimer to time tagged launches
 
+OVERLAP = True    # run independent kernel groups of a step on a second stream (see fork)
+_SIDE = {}
+
+
+def fork(fn, uses=()):
+    """Runs fn() on this device's side stream (`uses`: the tensors it reads, kept alive for it), ordered after everything issued so far on the current
+    stream, and returns (fn's result, event to join on).  Used for work that the rest of the step
+    does not depend on (the vocabulary dW GEMM runs beside the BPTT kernel, which occupies at most
+    128 of the 148 SMs and is latency-bound).  Capturable: fork/join become graph dependencies.
+    Serial (no second stream) while TIMER records per-kernel times or OVERLAP is off."""
+    if not OVERLAP or TIMER is not None:
+        return fn(), None
+    dev = torch.cuda.current_device()
+    side = _SIDE.get(dev)
+    if side is None:
+        side = _SIDE[dev] = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+    ready = torch.cuda.Event()
+    ready.record(main)
+    for t in uses:
+        t.record_stream(side)
+    with torch.cuda.stream(side):
+        side.wait_event(ready)
+        out = fn()
+        done = torch.cuda.Event()
+        done.record(side)
+    for t in (out if isinstance(out, (tuple, list)) else (out,)):
+        if torch.is_tensor(t):
+            t.record_stream(main)
+    return out, done
+
+
+def join(done):
+    """The current stream waits for a fork()ed group."""
+    if done is not None:
+        torch.cuda.current_stream().wait_event(done)
+
 
 def sgemm(A, B, *, transA=False, transB=False, bias=None, out=None, alpha=1.0, beta=0.0, tag=None):
     """out[M,N] = alpha * op(A) op(B) + beta * out + bias.  2-D fp32 tensors; the last dim must be
@@ -102,6 +139,31 @@ def colsum(M, out=None, accumulate=False):
     check(lib.st_colsum(ptr(out, F32), C.c_void_p(M.data_ptr()), int(M.dtype == torch.bfloat16), M.shape[0],
                         M.shape[1], max(M.stride(0), 1), int(accumulate), stream_ptr()), "st_colsum")
     return out
+
+
+def scale_multi(tensors, g):
+    """[t * g for t in tensors] (fp32, contiguous; g a 0-d device tensor) with one launch per 32 tensors.
+    The results are views of one flat buffer."""
+    import ctypes as C
+    lib = _lib.load()
+    tensors = [t.contiguous() for t in tensors]
+    if not tensors:
+        return []
+    g = g.to(F32).reshape(1)
+    pad = lambda n: (n + 3) // 4 * 4
+    flat = torch.empty(sum(pad(t.numel()) for t in tensors), dtype=F32, device=tensors[0].device)
+    outs, off = [], 0
+    for t in tensors:
+        outs.append(flat[off:off + t.numel()].view_as(t))
+        off += pad(t.numel())
+    for i in range(0, len(tensors), 32):
+        src, dst = tensors[i:i + 32], outs[i:i + 32]
+        n = len(src)
+        sp = (C.c_void_p * n)(*[t.data_ptr() for t in src])
+        dp = (C.c_void_p * n)(*[t.data_ptr() for t in dst])
+        cnt = (C.c_int64 * n)(*[t.numel() for t in src])
+        check(lib.st_scale_multi(n, sp, dp, cnt, ptr(g, F32), stream_ptr()), "st_scale_multi")
+    return outs
 
 
 def rowsum_bf16(M):

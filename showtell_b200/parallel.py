@@ -48,16 +48,18 @@ class GradReducer:
             self._stream = torch.cuda.Stream(device=device)
         return self._stream
 
-    def reduce(self, tensors):
+    def reduce(self, tensors, ready=None):
         """tensors: list of gradient tensors that are final.  Reduced in place (asynchronously on
-        CUDA: call finish() before reading them)."""
+        CUDA: call finish() before reading them).  `ready`: event after which the tensors are final
+        when their producers ran on another stream (ops.fork); default: the current stream's tail."""
         tensors = [t for t in tensors if t is not None]
         if self.world == 1 or not tensors:
             return
         if tensors[0].is_cuda:
             side = self._side_stream(tensors[0].device)
-            ready = torch.cuda.Event()
-            ready.record()                                 # producers ran on the current stream
+            if ready is None:
+                ready = torch.cuda.Event()
+                ready.record()                             # producers ran on the current stream
             with torch.cuda.stream(side):
                 side.wait_event(ready)
                 flat = torch.cat([t.reshape(-1) for t in tensors])
