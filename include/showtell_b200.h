@@ -49,6 +49,8 @@ int st_version(void);
 const char* st_last_error(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t st_launch_count(void);
+/* Development / test aid: programmatic dependent launch of the per-step kernels on (default) / off. */
+int st_debug_set_pdl(int on);
 /* Device facts the host side sizes grids with. */
 int st_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_optin_bytes);
 

@@ -39,6 +39,7 @@ _SIGS = {
     "st_cast_bf16": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _P]),
     "st_vocab_ce_parts": (_I, [_I]),
     "st_debug_gemm_variant": (_I, [_I]),
+    "st_debug_set_pdl": (_I, [_I]),
     "st_scale_multi": (_I, [_I, _P, _P, _P, _P, _P]),
     "st_vocab_ce_fwd": (_I, [_I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "st_vocab_ce_bwd": (_I, [_I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _F, _P, _I, _P, _I, _P]),
@@ -90,6 +91,8 @@ def load():
         fn = getattr(lib, name)          # AttributeError here = header and library out of sync
         fn.restype = res
         fn.argtypes = args
+    if os.environ.get("SHOWTELL_PDL", "1") == "0":       # A/B switch for programmatic dependent launch
+        lib.st_debug_set_pdl(0)
     _lib = lib
     return lib
 

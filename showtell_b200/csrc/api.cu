@@ -5,6 +5,7 @@
 
 namespace st {
 
+int g_pdl = 1;
 static thread_local char g_err[512] = "";
 static long long g_launches = 0;
 
@@ -46,6 +47,11 @@ extern "C" {
 int st_version(void) { return 100; }
 
 const char* st_last_error(void) { return st::g_err; }
+
+int st_debug_set_pdl(int on) {
+  st::g_pdl = on ? 1 : 0;
+  return ST_OK;
+}
 
 int64_t st_launch_count(void) { return (int64_t)__atomic_load_n(&st::g_launches, __ATOMIC_RELAXED); }
 

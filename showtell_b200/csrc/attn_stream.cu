@@ -110,6 +110,9 @@ __global__ void __launch_bounds__(SNT) attn_stream_kernel(const int nrows, const
   __syncthreads();
 
   if (warp == NCW) {  // ------------------------------------------------------------- producer
+    // PDL: the slabs (att1, Fe) are written once per iteration, long before the loop -- the producer does not
+    // wait for the previous kernel and fills the ring while that kernel (a small GEMM) is still running.
+    pdl_launch_dependents();
     if (lane == 0) {
       int c = 0;
       for (int b = blockIdx.x; b < nrows; b += gridDim.x) {
@@ -132,6 +135,8 @@ __global__ void __launch_bounds__(SNT) attn_stream_kernel(const int nrows, const
   }
 
   // --------------------------------------------------------------------------------- consumers
+  pdl_wait();               // att2 / dctx / alphas come from (or are still read by) the previous kernels
+  pdl_launch_dependents();
   int c = 0;
   for (int b = blockIdx.x; b < nrows; b += gridDim.x) {
   // pass-1 per-lane constants: lane owns vectors lane, lane+32, ... of every row
@@ -271,13 +276,13 @@ int launch_rv2(int rows, const StreamParams& p, int rv2, size_t smem, cudaStream
   do {                                                                                                     \
     auto kern = attn_stream_kernel<T, ACT, BWD, VPL1, RV2>;                                                \
     ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-    kern<<<rows < sms ? rows : sms, SNT, smem, s>>>(rows, p);                                                                       \
+    ST_CUDA_TRY(launch_pdl(kern, dim3(rows < sms ? rows : sms), dim3(SNT), smem, s, rows, p));            \
   } while (0)
   if (rv2 == 32) ST_GO(32);
   else if (rv2 == 64) ST_GO(64);
   else ST_GO(128);
 #undef ST_GO
-  ST_LAUNCH_TRY("attn_stream_kernel");
+  note_launch();
   return ST_OK;
 }
 

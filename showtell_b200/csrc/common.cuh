@@ -25,6 +25,22 @@ int make_step_table(StepTable& tab, int nsteps, const int* batch_sizes_host);
 
 inline cudaStream_t as_stream(st_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch (st_debug_set_pdl, default on): kernels that call pdl_wait() before they touch
+// anything the previous kernel of the stream wrote (or still reads) may be scheduled while that kernel drains,
+// so their prologue -- barrier init, TMEM allocation, tensor-map fetch, prefetch of step-invariant operands --
+// leaves the dependent chain of the per-step launches.
+extern int g_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 }  // namespace st
 
 #define ST_CUDA_TRY(expr)                                                                  \
@@ -64,6 +80,11 @@ inline cudaStream_t as_stream(st_stream_t s) { return reinterpret_cast<cudaStrea
 
 #ifdef __CUDACC__
 namespace st {
+
+// PDL, device side: wait until the preceding kernel(s) of the stream have completed and their writes are
+// visible (no-op without the launch attribute); allow the next kernel of the stream to be scheduled.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 

@@ -397,6 +397,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // PDL: everything above overlapped the previous kernel's tail; its outputs (our operands, and buffers it
+  // still reads that we overwrite) are safe from here on.
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------------------------------------------------- TMA producer
@@ -720,8 +724,8 @@ int launch_tc_bn(TcParams p, const void* A, int lda, const void* B, int ldb, cud
     grid = sms;
     ST_CUDA_TRY(cudaMemset2DAsync(p.C, (size_t)p.ldc * 4, 0, (size_t)p.N * 4, p.M, s));
   }
-  kern<<<grid, NTHREADS, TileCfg<BN>::SMEM_BYTES, s>>>(tmA, tmB, p);
-  ST_LAUNCH_TRY("gemm_tc_kernel");
+  ST_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(NTHREADS), TileCfg<BN>::SMEM_BYTES, s, tmA, tmB, p));
+  note_launch();
   return ST_OK;
 }
 

@@ -537,7 +537,7 @@ int launch_tc_fwd(const StepTable& tab, TcFwdParams p, const void* Whh_bf16, con
 
 template <int G, int BT>
 int try_tc_bwd(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cudaStream_t s, bool* launched) {
-  const int H = p.H, GH = G * H, KB = (GH + 63) / 64, N = tab.off[tab.nsteps], B0 = tab.bs[0];
+  const int H = p.H, GH = G * H, KB = (GH + 63) / 64, N = tab.off[tab.nsteps];
   const size_t smem = 1024 + (size_t)KB * (UT * 128) + (size_t)BSTAGES * (BT * 128) + 256;
   auto kern = rnn_seq_tc_bwd_kernel<G, BT>;
   ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
