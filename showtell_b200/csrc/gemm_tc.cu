@@ -402,48 +402,53 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   pdl_wait();
   pdl_launch_dependents();
 
-  if (warp == 0) {
-    if (lane == 0) {  // ---------------------------------------------------------- TMA producer
-      WorkSched sched(ntiles, kb, gridDim.x, blockIdx.x, p.streamk);
-      int stage = 0, tile, k0, k1;
-      uint32_t phase = 0;
-      while (sched.next(tile, k0, k1)) {
-        const int m0 = (nfast ? tile / nt : tile % mt) * BM, n0 = (nfast ? tile % nt : tile / mt) * BN;
-        for (int k = k0; k < k1; ++k) {
-          mbar_wait(&empty[stage], phase ^ 1);
+  // Producer and MMA warps run their loops with all 32 lanes (uniform control flow keeps addresses and UMMA
+  // descriptors in uniform registers); only the TMA / tcgen05 instructions are issued by one elected lane.
+  if (warp == 0) {  // ------------------------------------------------------------ TMA producer
+    WorkSched sched(ntiles, kb, gridDim.x, blockIdx.x, p.streamk);
+    int stage = 0, tile, k0, k1;
+    uint32_t phase = 0;
+    while (sched.next(tile, k0, k1)) {
+      const int m0 = (nfast ? tile / nt : tile % mt) * BM, n0 = (nfast ? tile % nt : tile / mt) * BN;
+      for (int k = k0; k < k1; ++k) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* a = smem + (size_t)stage * STAGE_BYTES;
           tma_load_2d(a, &tmA, k * BK, m0, &full[stage]);
           tma_load_2d(a + A_BYTES, &tmB, k * BK, n0, &full[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {  // ---------------------------------------------------------- MMA issuer
-      constexpr uint32_t idesc = umma_idesc(BM, BN);
-      WorkSched sched(ntiles, kb, gridDim.x, blockIdx.x, p.streamk);
-      int stage = 0, acc = 0, tile, k0, k1;
-      uint32_t phase = 0, acc_phase = 0;
-      while (sched.next(tile, k0, k1)) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+  } else if (warp == 1) {  // ----------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc = umma_idesc(BM, BN);
+    const uint64_t adesc0 = umma_desc_k128(smem_u32(smem)), bdesc0 = umma_desc_k128(smem_u32(smem) + A_BYTES);
+    WorkSched sched(ntiles, kb, gridDim.x, blockIdx.x, p.streamk);
+    int stage = 0, acc = 0, tile, k0, k1;
+    uint32_t phase = 0, acc_phase = 0;
+    while (sched.next(tile, k0, k1)) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int k = k0; k < k1; ++k) {
+        mbar_wait(&full[stage], phase);  // TMA bytes have landed
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int k = k0; k < k1; ++k) {
-          mbar_wait(&full[stage], phase);  // TMA bytes have landed
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_BYTES;
+        // descriptor address fields are in 16-byte units: + stage offset, + 2 per 16-element k-step
+        const uint64_t so = (uint64_t)(stage * (STAGE_BYTES >> 4));
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < BK / UK; ++kk)
-            tc_mma(d_tmem, umma_desc_k128(a_addr + kk * UK * 2), umma_desc_k128(b_addr + kk * UK * 2), idesc,
-                   (k > k0) || (kk != 0));
+            tc_mma(d_tmem, adesc0 + so + 2 * kk, bdesc0 + so + 2 * kk, idesc, (k > k0) || (kk != 0));
           tc_commit(&empty[stage]);  // smem slot free once these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull[acc]);  // accumulator complete
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) tc_commit(&tfull[acc]);  // accumulator complete
+      __syncwarp();
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {  // ------------------------------------------------------ epilogue
     // 8 warps: warp w owns TMEM lanes 32*(w%4)..+31 (32 rows) and one half of the tile's BN columns.
@@ -580,27 +585,29 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-  if (warp == 0) {
-    if (lane == 0) {  // ------------------------------------------------- TMA producer (both CTAs)
-      WorkSched sched(ntiles, kb, npairs, pair, p.streamk);
-      int stage = 0, tile, k0, k1;
-      uint32_t phase = 0;
-      while (sched.next(tile, k0, k1)) {
-        const int m0 = (nfast ? tile / nt : tile % mt) * 2 * BM + (int)rank * BM;
-        const int n0 = (nfast ? tile % nt : tile / mt) * BN + (int)rank * (BN / 2);
-        for (int k = k0; k < k1; ++k) {
-          mbar_wait(&empty[stage], phase ^ 1);
+  if (warp == 0) {  // --------------------------------------------------- TMA producer (both CTAs)
+    WorkSched sched(ntiles, kb, npairs, pair, p.streamk);
+    int stage = 0, tile, k0, k1;
+    uint32_t phase = 0;
+    while (sched.next(tile, k0, k1)) {
+      const int m0 = (nfast ? tile / nt : tile % mt) * 2 * BM + (int)rank * BM;
+      const int n0 = (nfast ? tile % nt : tile / mt) * BN + (int)rank * (BN / 2);
+      for (int k = k0; k < k1; ++k) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_expect_tx_at(mapa_rank0(smem_u32(&full[stage])), STAGE_BYTES);
           uint8_t* a = smem + (size_t)stage * STAGE_BYTES;
           tma_load_2d_pair(a, &tmA, k * BK, m0, &full[stage]);
           tma_load_2d_pair(a + A_BYTES, &tmB, k * BK, n0, &full[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {  // ------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0) {  // ------------------------------------------------- MMA issuer (leader CTA only)
       constexpr uint32_t idesc = umma_idesc(2 * BM, BN);
+      const uint64_t adesc0 = umma_desc_k128(smem_u32(smem)), bdesc0 = umma_desc_k128(smem_u32(smem) + A_BYTES);
       WorkSched sched(ntiles, kb, npairs, pair, p.streamk);
       int stage = 0, acc = 0, tile, k0, k1;
       uint32_t phase = 0, acc_phase = 0;
@@ -611,16 +618,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int k = k0; k < k1; ++k) {
           mbar_wait(&full[stage], phase);  // both CTAs' TMA bytes have landed
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_BYTES;
+          const uint64_t so = (uint64_t)(stage * (STAGE_BYTES >> 4));
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < BK / UK; ++kk)
-            tc_mma_pair(d_tmem, umma_desc_k128(a_addr + kk * UK * 2), umma_desc_k128(b_addr + kk * UK * 2), idesc,
-                        (k > k0) || (kk != 0));
-          tc_commit_pair(&empty[stage]);
+            for (int kk = 0; kk < BK / UK; ++kk)
+              tc_mma_pair(d_tmem, adesc0 + so + 2 * kk, bdesc0 + so + 2 * kk, idesc, (k > k0) || (kk != 0));
+            tc_commit_pair(&empty[stage]);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit_pair(&tfull[acc]);
+        if (elect_one()) tc_commit_pair(&tfull[acc]);
+        __syncwarp();
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }

@@ -170,33 +170,41 @@ rnn_seq_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     if (nr <= 0) break;
     const bool use_mma = (t > 0) || p.has_h0;
 
-    if (warp == 0 && lane == 0 && use_mma) {
+    if (warp == 0 && use_mma) {   // whole warp, uniform control flow; one elected lane issues (see elect_one)
       // h_{t-1} is complete once every epilogue warp of every unit tile of this batch tile has
-      // arrived for step t-1 (8 arrivals per CTA per step, release/acquire on the counter)
+      // arrived for step t-1 (8 arrivals per CTA per step, release/acquire on the counter; the 32
+      // lanes poll one address = one request)
       stamp(p.tl, t, 0);
       if (t > p.t_begin) wait_counter_geq(p.barrier + blockIdx.y, (t - p.t_begin) * 8 * (int)gridDim.x);
       stamp(p.tl, t, 1);
       proxy_fence_global();
       const CUtensorMap* src = (t == 0) ? &tmH0 : &tmH;
       const int rbase = (t == 0) ? r0 : tab.off[t - 1] + r0;
-      for (int kb = 0; kb < KB; ++kb) {
-        mbar_expect_tx(&hfull[kb], KBLK_A);
-        tma_load_2d(sA + (size_t)kb * KBLK_A, src, kb * 64, rbase, &hfull[kb]);
+      if (elect_one()) {
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_expect_tx(&hfull[kb], KBLK_A);
+          tma_load_2d(sA + (size_t)kb * KBLK_A, src, kb * 64, rbase, &hfull[kb]);
+        }
       }
+      __syncwarp();
       if (!w_ready) { mbar_wait(wbar, 0); w_ready = true; }
       constexpr uint32_t idesc = umma_idesc(BT, NC);
+      const uint64_t adesc0 = umma_desc_k128(smem_u32(sA)), bdesc0 = umma_desc_k128(smem_u32(sW));
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(&hfull[kb], ph);
         if (kb == 0) stamp(p.tl, t, 2);
         if (kb == KB - 1) stamp(p.tl, t, 3);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(sA + (size_t)kb * KBLK_A);
-        const uint32_t b_addr = smem_u32(sW + (size_t)kb * KBLK_W);
+        // descriptor address fields are in 16-byte units: + k-block offset, + 2 per 16-element k-step
+        const uint64_t ad = adesc0 + (uint64_t)(kb * (KBLK_A >> 4)), bd = bdesc0 + (uint64_t)(kb * (KBLK_W >> 4));
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          tc_mma(tmem_base, umma_desc_k128(a_addr + kk * 32), umma_desc_k128(b_addr + kk * 32), idesc, (kb | kk) != 0);
+          for (int kk = 0; kk < 4; ++kk) tc_mma(tmem_base, ad + 2 * kk, bd + 2 * kk, idesc, (kb | kk) != 0);
+        }
+        __syncwarp();
       }
-      tc_commit(accbar);
+      if (elect_one()) tc_commit(accbar);
+      __syncwarp();
     }
 
     if (is_epi) {
@@ -437,34 +445,41 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
     if (t > p.t_lo) load_step(t - 1);  // overlaps with the phase-2 stream below
 
     // ---------------- phase 2: dh_{t-1}[rows, own units] = dGh_t[rows, :] . W_hh[:, own units]
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {          // whole warp, uniform control flow; one elected lane issues (see elect_one)
       wait_counter_geq(p.barrier + blockIdx.y, nbar * 8 * (int)gridDim.x);  // all unit tiles wrote dGh_t
       stamp(p.tl, t, 2);
       proxy_fence_global();
       const int rbase = tab.off[t] + r0;
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(&empty[stage_p], phase_p ^ 1);
-        mbar_expect_tx(&full[stage_p], KBLK_A);
-        tma_load_2d(sA + (size_t)stage_p * KBLK_A, &tmD, kb * 64, rbase, &full[stage_p]);
+        if (elect_one()) {
+          mbar_expect_tx(&full[stage_p], KBLK_A);
+          tma_load_2d(sA + (size_t)stage_p * KBLK_A, &tmD, kb * 64, rbase, &full[stage_p]);
+        }
+        __syncwarp();
         if (++stage_p == BSTAGES) { stage_p = 0; phase_p ^= 1; }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {   // whole warp, uniform control flow; one elected lane issues (see elect_one)
       if (!w_ready) { mbar_wait(wbar, 0); w_ready = true; }
       constexpr uint32_t idesc = umma_idesc(BT, UT);
+      const uint64_t adesc0 = umma_desc_k128(smem_u32(sA)), bdesc0 = umma_desc_k128(smem_u32(sW));
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait(&full[stage_c], phase_c);
         if (kb == 0) stamp(p.tl, t, 3);
         if (kb == KB - 1) stamp(p.tl, t, 4);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(sA + (size_t)stage_c * KBLK_A);
-        const uint32_t b_addr = smem_u32(sW + (size_t)kb * KBLK_W);
+        // descriptor address fields are in 16-byte units: + stage / k-block offset, + 2 per 16-element k-step
+        const uint64_t ad = adesc0 + (uint64_t)(stage_c * (KBLK_A >> 4)), bd = bdesc0 + (uint64_t)(kb * (KBLK_W >> 4));
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-          tc_mma(tmem_base, umma_desc_k128(a_addr + kk * 32), umma_desc_k128(b_addr + kk * 32), idesc, (kb | kk) != 0);
-        tc_commit(&empty[stage_c]);
+          for (int kk = 0; kk < 4; ++kk) tc_mma(tmem_base, ad + 2 * kk, bd + 2 * kk, idesc, (kb | kk) != 0);
+          tc_commit(&empty[stage_c]);
+        }
+        __syncwarp();
         if (++stage_c == BSTAGES) { stage_c = 0; phase_c ^= 1; }
       }
-      tc_commit(accbar);
+      if (elect_one()) tc_commit(accbar);
+      __syncwarp();
     } else if (is_epi) {
       mbar_wait(accbar, aph);
       if (threadIdx.x == 64) stamp(p.tl, t, 5);

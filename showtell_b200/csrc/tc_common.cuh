@@ -44,6 +44,20 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// One lane of a converged warp (elect.sync).  Issue loops run with the WHOLE warp so that loop counters,
+// shared-memory addresses and UMMA descriptors live in uniform registers; only the asynchronous instruction
+// itself is predicated on the elected lane.  (Inside an `if (lane == 0)` region the compiler must assume
+// per-thread values and wraps every tcgen05.mma operand in an ELECT / R2UR.BROADCAST loop: ~25 dependent
+// instructions, ~140 clocks per MMA on the one issuing thread -- that, not data, bounded the recurrent steps.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
