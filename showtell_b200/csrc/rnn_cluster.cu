@@ -264,31 +264,33 @@ rnn_cluster_fwd_kernel(const __grid_constant__ CUtensorMap tmGx, const __grid_co
     const bool use_mma = (s > 0) || first_from_mem;
     const bool publish = (t + 1 < p.t_end) && (tab.bs[t + 1] - r0 > 0);   // uniform: a next step exists for this slice
 
-    if (warp == MW && lane == 0) {
+    if (warp == MW) {   // whole warp, uniform control flow; one elected lane issues (see elect_one in tc_common.cuh)
       stamp(p.tl, t, 0);
       if (s > 0) mbar_wait(hbar, (s - 1) & 1);         // every peer's part of h_{t-1} has landed (async-proxy writes)
       stamp(p.tl, t, 1);
-      if (publish) {
+      if (publish && elect_one()) {
         mbar_expect_tx(hbar, (uint32_t)RB * H * 2);    // arm the next phase before anyone can send h_t
         load_gx(t + 1, (s + 1) & 1);                   // that buffer was last read in step t-1, which is over
       }
       if (use_mma) {
         tc_fence_after();
         constexpr uint32_t idesc = umma_idesc(128, RB);
-        const uint32_t b0 = smem_u32(sH);
-        // k-steps round-robin over NACC accumulators (no MMA waits on its predecessor); fully unrolled with a
-        // running descriptor so the issue loop is nothing but the MMAs
-        const uint64_t d0 = umma_desc_nosw(b0, CHB, 128);
+        // k-steps round-robin over NACC accumulators; fully unrolled with a running descriptor so the issue
+        // loop is nothing but the MMAs
+        const uint64_t d0 = umma_desc_nosw(smem_u32(sH), CHB, 128);
         const int nks = H / 16;
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < CMAXKB * 4; ++ks)
-          if (ks < nks)
-            tc_mma_ts(tmem_base + DCOL + (ks % NACC) * ASTR, tmem_base + ks * 8, d0 + (uint64_t)(ks * ((2 * CHB) >> 4)), idesc,
-                      ks >= (int)NACC);
-        tc_commit(accbar);
-        if (publish) tc_commit_multicast(fbar, (uint16_t)((1u << CS) - 1));
+          for (int ks = 0; ks < CMAXKB * 4; ++ks)
+            if (ks < nks)
+              tc_mma_ts(tmem_base + DCOL + (ks % NACC) * ASTR, tmem_base + ks * 8, d0 + (uint64_t)(ks * ((2 * CHB) >> 4)), idesc,
+                        ks >= (int)NACC);
+          tc_commit(accbar);
+          if (publish) tc_commit_multicast(fbar, (uint16_t)((1u << CS) - 1));
+        }
         stamp(p.tl, t, 2);
       }
+      __syncwarp();
     }
 
     if (is_epi) {
