@@ -139,32 +139,39 @@ __global__ void shift_states_kernel(const __grid_constant__ StepTable tab, float
 }
 
 
-// dst_i = src_i * (*g) for up to ST_SCALE_MAX tensors in one launch (blockIdx.y = tensor).
+// dst_i = src_i * (*g) for up to ST_SCALE_MAX tensors in one launch: the tensors form one index space of
+// 4096-element chunks (first[i] = first chunk of tensor i), one chunk per CTA iteration.
 struct ScaleTable {
   int n;
   const float* src[ST_SCALE_MAX];
   float* dst[ST_SCALE_MAX];
   long long count[ST_SCALE_MAX];
+  int first[ST_SCALE_MAX + 1];
 };
-__global__ void scale_multi_kernel(const ScaleTable tab, const float* __restrict__ g) {
-  const int i = blockIdx.y;
+constexpr int SCALE_CHUNK = 4096;
+__global__ void __launch_bounds__(256) scale_multi_kernel(const ScaleTable tab, const float* __restrict__ g) {
   const float a = __ldg(g);
-  const float* __restrict__ src = tab.src[i];
-  float* __restrict__ dst = tab.dst[i];
-  const long long n = tab.count[i];
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
-  if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
-    const long long n4 = n >> 2;
-    for (long long j = tid; j < n4; j += nth) {
-      float4 v = __ldcs(reinterpret_cast<const float4*>(src) + j);
-      v.x *= a; v.y *= a; v.z *= a; v.w *= a;
-      reinterpret_cast<float4*>(dst)[j] = v;
+  for (int c = blockIdx.x; c < tab.first[tab.n]; c += gridDim.x) {
+    int i = 0;
+    while (c >= tab.first[i + 1]) ++i;
+    const long long base = (long long)(c - tab.first[i]) * SCALE_CHUNK;
+    const long long n = min((long long)SCALE_CHUNK, tab.count[i] - base);
+    const float* __restrict__ src = tab.src[i] + base;
+    float* __restrict__ dst = tab.dst[i] + base;
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+      const int n4 = (int)(n >> 2);
+      for (int j = threadIdx.x; j < n4; j += blockDim.x) {
+        float4 v = __ldcs(reinterpret_cast<const float4*>(src) + j);
+        v.x *= a; v.y *= a; v.z *= a; v.w *= a;
+        reinterpret_cast<float4*>(dst)[j] = v;
+      }
+      for (int j = (n4 << 2) + threadIdx.x; j < n; j += blockDim.x) dst[j] = src[j] * a;
+    } else {
+      for (int j = threadIdx.x; j < n; j += blockDim.x) dst[j] = src[j] * a;
     }
-    for (long long j = (n4 << 2) + tid; j < n; j += nth) dst[j] = src[j] * a;
-  } else {
-    for (long long j = tid; j < n; j += nth) dst[j] = src[j] * a;
   }
 }
+
 }  // namespace
 }  // namespace st
 
@@ -273,19 +280,20 @@ int st_scale_multi(int n, const float* const* src, float* const* dst, const int6
   if (n == 0) return ST_OK;
   ScaleTable tab;
   tab.n = n;
-  long long big = 0;
+  long long chunks = 0;
   for (int i = 0; i < n; ++i) {
-    ST_REQUIRE(src[i] && dst[i] && count[i] >= 0, ST_ERR_NULL, "st_scale_multi: tensor %d is NULL", i);
+    ST_REQUIRE(count[i] >= 0 && (count[i] == 0 || (src[i] && dst[i])), ST_ERR_NULL, "st_scale_multi: tensor %d is NULL", i);
     tab.src[i] = src[i]; tab.dst[i] = dst[i]; tab.count[i] = count[i];
-    if (count[i] > big) big = count[i];
+    tab.first[i] = (int)chunks;
+    chunks += (count[i] + SCALE_CHUNK - 1) / SCALE_CHUNK;
+    ST_REQUIRE(chunks < (1LL << 30), ST_ERR_BAD_SHAPE, "st_scale_multi: too many elements");
   }
+  tab.first[n] = (int)chunks;
+  if (chunks == 0) return ST_OK;
   int sms = 0;
   ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
-  long long bx = (big / 4 + 255) / 256;                 // one float4 per thread, capped at ~4 CTAs per SM in total
-  const long long cap = (4LL * sms + n - 1) / n;
-  if (bx > cap) bx = cap;
-  if (bx < 1) bx = 1;
-  scale_multi_kernel<<<dim3((unsigned)bx, n), 256, 0, as_stream(stream)>>>(tab, g);
+  const long long grid = chunks < 8LL * sms ? chunks : 8LL * sms;
+  scale_multi_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(tab, g);
   ST_LAUNCH_TRY("scale_multi_kernel");
   return ST_OK;
 }

@@ -228,3 +228,22 @@ def test_rnn_seq_stepwise_equals_whole(dev):
         for t in reversed(range(len(bs))):
             bst = ops.rnn_seq_bwd(k, Whh, bs, whole, dHs, t_range=(t + 1, t), out=bst)
         assert torch.equal(bst["dG"], bw["dG"]) and torch.equal(bst["dstate"], bw["dstate"])
+
+
+def test_scale_multi(dev):
+    """The chain rule of forward_loss.backward(): [t * g] for a list of gradient tensors in one launch."""
+    from showtell_b200 import _lib, ops
+    gen = torch.Generator().manual_seed(5)
+    shapes = [(10000, 512), (2048,), (1, 512), (37, 3), (5,), (4097,), (0,)]
+    ts = [torch.randn(*s, generator=gen).to(dev) for s in shapes]
+    ts.append(torch.randn(1001, generator=gen).to(dev)[1:])          # not 16-byte aligned
+    g = torch.tensor(0.37, device=dev)
+    lib = _lib.load()
+    l0 = lib.st_launch_count()
+    out = ops.scale_multi(ts, g)
+    assert lib.st_launch_count() - l0 == 1
+    for o, t in zip(out, ts):
+        assert o.shape == t.shape and torch.equal(o, t * g)
+    many = [torch.randn(17, generator=gen).to(dev) for _ in range(40)]  # more than one table
+    for o, t in zip(ops.scale_multi(many, g), many):
+        assert torch.equal(o, t * g)
