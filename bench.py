@@ -191,6 +191,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="lstm_train", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="bf16", choices=["fp32", "bf16"])
+    ap.add_argument("--decode-gemm", default="tf32x3", choices=["fp32", "tf32x3"],
+                    help="beam workloads: nn.Linear products on CUDA cores (fp32) or fp32-accurate 3xTF32 tensor cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     model, B, Pn, desc = WORKLOADS[args.workload]
@@ -227,6 +229,8 @@ def main():
     lib = _lib.load()
     dtype = "fp32" if is_beam else args.dtype
     net = build_model(model, dtype).to(dev)
+    if is_beam:
+        net.decode_gemm = args.decode_gemm
     params = [p for p in net.parameters()]
     if world > 1 and not is_beam:
         net.grad_reducer = parallel.GradReducer()          # NCCL all-reduce on a side stream
@@ -332,6 +336,12 @@ def main():
                     "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                     "frac": ach / pk["tf_sustained"] if ach else None, "traffic": None,
                     "peak_source": pk["src"] + " (bf16 cuBLAS sustained)"}
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp):                         # measured once per round under ncu --set full
+            ent = json.load(open(tp)).get(args.workload)
+            if ent and dtype == "bf16":
+                roof["traffic"] = ent["traffic_bytes_per_launch"]
+                roof["traffic_source"] = ent["source"]
         roof["kernels_ms"] = kms
         if not is_beam:
             roof["step_flops"] = train_flops(model, B, Pn)

@@ -95,6 +95,15 @@ int st_cast_bf16(const float* src, int rows, int cols, int lds, void* dst, int l
  * dHs = P Wv and dWv = P^T Hs.
  * ------------------------------------------------------------------------------------------ */
 int st_vocab_ce_parts(int V);
+/* fp32-accurate GEMM on the tensor cores (3xTF32): C[M,N] = alpha * A . B^T + bias (+ beta * C), where each fp32
+ * operand is given as hi + lo from st_split_tf32 (hi = upper 11 mantissa bits, lo = the exact remainder) and the
+ * product is hi.hi + hi.lo + lo.hi with fp32 accumulation.  Replaces the fp32 nn.Linear products of the decoding
+ * loops (rnn.py:50,88; beam_search generate_function), whose token ids are defined against fp32 arithmetic.
+ * Operands 16-byte aligned, lda / ldb multiples of 4. */
+int st_split_tf32(const float* src, int rows, int cols, int lds, float* hi, float* lo, int ldd, st_stream_t stream);
+int st_gemm_tf32x3(int M, int N, int K, const float* A_hi, const float* A_lo, int lda, const float* B_hi,
+                   const float* B_lo, int ldb, float* C, int ldc, const float* bias, float alpha, float beta,
+                   st_stream_t stream);
 /* Development / test aid: pin the kernel behind st_gemm_bf16 and st_vocab_ce_*: 2 = CTA-pair kernel
  * (cta_group::2, 256x256 tiles, stream-K), 128 / 256 = single-CTA kernel with that tile width, 0 = choose. */
 int st_debug_gemm_variant(int variant);
@@ -295,6 +304,8 @@ typedef struct {
   const float* const* bhh_host;
   const float* Wv;            /* (V, H) */
   const float* bv;            /* (V)    */
+  int gemm_mode;              /* nn.Linear products of the loops: 0 = fp32 CUDA cores, 1 = 3xTF32 tensor cores
+                                 (fp32-accurate, st_gemm_tf32x3; needs E, H multiples of 4, else falls back to 0) */
 } st_rnn_weights;
 
 int64_t st_decode_workspace_bytes(const st_rnn_weights* w, int n_img, int K, int max_len);

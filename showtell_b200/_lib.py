@@ -24,7 +24,8 @@ class RnnWeights(C.Structure):
     _fields_ = [("kind", C.c_int), ("L", C.c_int), ("E", C.c_int), ("H", C.c_int), ("V", C.c_int),
                 ("emb", C.c_void_p), ("Wih_host", C.POINTER(C.c_void_p)),
                 ("Whh_host", C.POINTER(C.c_void_p)), ("bih_host", C.POINTER(C.c_void_p)),
-                ("bhh_host", C.POINTER(C.c_void_p)), ("Wv", C.c_void_p), ("bv", C.c_void_p)]
+                ("bhh_host", C.POINTER(C.c_void_p)), ("Wv", C.c_void_p), ("bv", C.c_void_p),
+                ("gemm_mode", C.c_int)]
 
 
 _P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_int64
@@ -39,6 +40,8 @@ _SIGS = {
     "st_cast_bf16": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _P]),
     "st_vocab_ce_parts": (_I, [_I]),
     "st_debug_gemm_variant": (_I, [_I]),
+    "st_split_tf32": (_I, [_P, _I, _I, _I, _P, _P, _I, _P]),
+    "st_gemm_tf32x3": (_I, [_I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _F, _F, _P]),
     "st_debug_set_pdl": (_I, [_I]),
     "st_scale_multi": (_I, [_I, _P, _P, _P, _P, _P]),
     "st_vocab_ce_fwd": (_I, [_I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),

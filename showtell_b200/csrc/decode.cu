@@ -16,6 +16,11 @@ extern "C" int st_rnn_seq_fwd(int kind, int H, int nsteps, const int* batch_size
                               float* ghn, int* barrier, st_stream_t stream);
 extern "C" int st_argmax_rows(const float* X, int ld, int rows, int cols, int64_t* idx, int idx_stride,
                               st_stream_t stream);
+extern "C" int st_split_tf32(const float* src, int rows, int cols, int lds, float* hi, float* lo, int ldd,
+                             st_stream_t stream);
+extern "C" int st_gemm_tf32x3(int M, int N, int K, const float* A_hi, const float* A_lo, int lda, const float* B_hi,
+                              const float* B_lo, int ldb, float* C, int ldc, const float* bias, float alpha,
+                              float beta, st_stream_t stream);
 extern "C" int st_topk_rows(const float* X, int ld, int rows, int cols, int K, float* val,
                             int32_t* idx, int out_stride, st_stream_t stream);
 
@@ -50,13 +55,20 @@ int check_weights(const st_rnn_weights* w) {
   return ST_OK;
 }
 
+// The nn.Linear products of the loops (input projection, vocabulary projection) run either on the CUDA
+// cores in fp32 (gemm_mode 0) or on the tensor cores as 3xTF32 (gemm_mode 1: fp32-accurate, see
+// st_gemm_tf32x3); the latter needs rows of 4 floats (E, H multiples of 4).
+inline bool use_tc(const st_rnn_weights* w) { return w->gemm_mode == 1 && w->E % 4 == 0 && w->H % 4 == 0; }
+
 // Per-call decoder state: double-buffered h/c per layer for `rows` rows, plus GEMM scratch.
 struct Rig {
   const st_rnn_weights* w;
   int rows, G;
+  bool tc;
   float *X, *Gx0, *GxL, *logits;
   float* h[2][MAXL];
   float* c[2][MAXL];
+  float *Wih_hi[MAXL], *Wih_lo[MAXL], *Wv_hi, *Wv_lo, *act_hi, *act_lo;   // tc: tf32 splits
   int* barrier;
   int cur;
   cudaStream_t s;
@@ -65,6 +77,7 @@ struct Rig {
     w = w_;
     rows = rows_;
     G = (w->kind == ST_LSTM) ? 4 : 3;
+    tc = use_tc(w);
     X = b.take<float>((int64_t)rows * w->E);
     Gx0 = b.take<float>((int64_t)rows * G * w->H);
     GxL = b.take<float>((int64_t)rows * G * w->H);
@@ -74,13 +87,40 @@ struct Rig {
         h[i][l] = b.take<float>((int64_t)rows * w->H);
         c[i][l] = (w->kind == ST_LSTM) ? b.take<float>((int64_t)rows * w->H) : nullptr;
       }
+    if (tc) {
+      for (int l = 0; l < w->L; ++l) {
+        const int64_t n = (int64_t)G * w->H * (l == 0 ? w->E : w->H);
+        Wih_hi[l] = b.take<float>(n);
+        Wih_lo[l] = b.take<float>(n);
+      }
+      Wv_hi = b.take<float>((int64_t)w->V * w->H);
+      Wv_lo = b.take<float>((int64_t)w->V * w->H);
+      const int64_t wide = w->E > w->H ? w->E : w->H;
+      act_hi = b.take<float>((int64_t)rows * wide);
+      act_lo = b.take<float>((int64_t)rows * wide);
+    }
     barrier = b.take<int>(64);
     cur = 0;
   }
+  // tc: split the (constant) weights once per call
+  int prepare() {
+    if (!tc) return ST_OK;
+    for (int l = 0; l < w->L; ++l) {
+      const int in = l == 0 ? w->E : w->H;
+      ST_TRY(st_split_tf32(w->Wih_host[l], G * w->H, in, in, Wih_hi[l], Wih_lo[l], in, s));
+    }
+    return st_split_tf32(w->Wv, w->V, w->H, w->H, Wv_hi, Wv_lo, w->H, s);
+  }
+  // out (rows, N) = in (rows, K) . W^T + bias
+  int linear(const float* in, int K, const float* W, const float* W_hi, const float* W_lo, const float* bias, int N,
+             float* out) {
+    if (!tc) return st_sgemm(0, 1, rows, N, K, 1.f, in, K, W, K, 0.f, out, N, bias, s);
+    ST_TRY(st_split_tf32(in, rows, K, K, act_hi, act_lo, K, s));
+    return st_gemm_tf32x3(rows, N, K, act_hi, act_lo, K, W_hi, W_lo, K, out, N, bias, 1.f, 0.f, s);
+  }
   // Gx0 = Xin (rows, E) . Wih_0^T + bih_0
   int input_proj(const float* Xin) {
-    return st_sgemm(0, 1, rows, G * w->H, w->E, 1.f, Xin, w->E, w->Wih_host[0], w->E, 0.f, Gx0,
-                    G * w->H, w->bih_host[0], s);
+    return linear(Xin, w->E, w->Wih_host[0], Wih_hi[0], Wih_lo[0], w->bih_host[0], G * w->H, Gx0);
   }
   // One time step through all layers; reads state `cur` (zeros when first), writes and flips.
   int step(bool first) {
@@ -88,8 +128,7 @@ struct Rig {
     for (int l = 0; l < w->L; ++l) {
       const float* gx = Gx0;
       if (l > 0) {
-        ST_TRY(st_sgemm(0, 1, rows, G * H, H, 1.f, h[nxt][l - 1], H, w->Wih_host[l], H, 0.f, GxL,
-                        G * H, w->bih_host[l], s));
+        ST_TRY(linear(h[nxt][l - 1], H, w->Wih_host[l], Wih_hi[l], Wih_lo[l], w->bih_host[l], G * H, GxL));
         gx = GxL;
       }
       ST_TRY(st_rnn_seq_fwd(w->kind, H, 1, &rows, 0, 1, gx, w->Whh_host[l], w->bhh_host[l],
@@ -100,15 +139,19 @@ struct Rig {
     return ST_OK;
   }
   float* top() { return h[cur][w->L - 1]; }
-  int vocab_logits() {
-    return st_sgemm(0, 1, rows, w->V, w->H, 1.f, top(), w->H, w->Wv, w->H, 0.f, logits, w->V, w->bv, s);
-  }
+  int vocab_logits() { return linear(top(), w->H, w->Wv, Wv_hi, Wv_lo, w->bv, w->V, logits); }
 };
 
 int64_t rig_bytes(const st_rnn_weights* w, int64_t rows) {
   const int G = (w->kind == ST_LSTM) ? 4 : 3;
   int64_t f = rows * w->E + 2 * rows * G * w->H + rows * w->V + 4 * (int64_t)w->L * rows * w->H;
-  return f * 4 + 256 * (8 + 4 * w->L) + 64 * 4;
+  int64_t slots = 8 + 4 * w->L;
+  if (use_tc(w)) {
+    f += 2 * ((int64_t)G * w->H * w->E + (int64_t)(w->L - 1) * G * w->H * w->H + (int64_t)w->V * w->H);
+    f += 2 * rows * (w->E > w->H ? w->E : w->H);
+    slots += 2 * w->L + 4;
+  }
+  return f * 4 + 256 * slots + 64 * 4;
 }
 
 template <typename I>
@@ -424,6 +467,7 @@ int st_decode_greedy(const st_rnn_weights* w, const float* feature, int n_img, i
   rig.carve(b, w, n_img);
   ST_REQUIRE(b.used <= b.cap, ST_ERR_WORKSPACE, "st_decode_greedy: workspace %lld < %lld",
              (long long)b.cap, (long long)b.used);
+  ST_TRY(rig.prepare());
   ST_TRY(rig.input_proj(feature));                                           // rnn.py:41,49
   for (int step = 0; step < max_len; ++step) {
     ST_TRY(rig.step(step == 0));                                             // rnn.py:49
@@ -460,6 +504,7 @@ int st_decode_beam_chain(const st_rnn_weights* w, const float* feature, int n_im
   int32_t* cand_idx = b.take<int32_t>((int64_t)n_img * K * K);
   ST_REQUIRE(b.used <= b.cap, ST_ERR_WORKSPACE, "st_decode_beam_chain: workspace %lld < %lld",
              (long long)b.cap, (long long)b.used);
+  ST_TRY(rig.prepare());
   cudaStream_t s = rig.s;
   const int tpb = 128;
 
@@ -536,6 +581,7 @@ int st_decode_beam_tree(const st_rnn_weights* w, const float* feature, int n_img
   float* gx_init = b.take<float>((int64_t)n_img * 3 * w->H);
   ST_REQUIRE(b.used <= b.cap, ST_ERR_WORKSPACE, "st_decode_beam_tree: workspace %lld < %lld",
              (long long)b.cap, (long long)b.used);
+  ST_TRY(rig.prepare());
   cudaStream_t s = rig.s;
   const int tpb = 64, gi = (n_img + tpb - 1) / tpb;
   const int H = w->H;

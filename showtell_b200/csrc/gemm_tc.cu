@@ -478,6 +478,178 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------------ fp32-accurate GEMM (3xTF32)
+// C = A . B^T to fp32 accuracy on the tensor cores: every fp32 operand is split into hi = its upper 11 mantissa
+// bits (a valid tf32) and lo = a - hi (exact in fp32), and  a.b ~= hi_a.hi_b + hi_a.lo_b + lo_a.hi_b  with fp32
+// accumulation; the dropped lo.lo term and the tf32 rounding of lo are ~2^-22 relative, below the rounding noise
+// of an fp32 dot product of length K = 512.  Three kind::tf32 MMAs (K = 8 each) per 8 columns of K: one sixth of
+// the bf16 tensor rate, ~5x the FFMA rate of the SM.  Used by the decoding loops (decode.cu), whose token ids are
+// defined against fp32 arithmetic.  Same roles / pipeline / epilogue as gemm_tc_kernel; a stage holds the four
+// 32-column k-blocks A_hi | A_lo | B_hi | B_lo.
+template <int BN> struct Tf32Cfg {
+  static constexpr uint32_t A_B = BM * 128, B_B = BN * 128, STAGE_BYTES = 2 * (A_B + B_B);
+  static constexpr int STAGES = (BN == 256) ? 2 : 3;
+  static constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;
+  static constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + STG_BYTES + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                   const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const TcParams p) {
+  constexpr int STAGES = Tf32Cfg<BN>::STAGES, BK32 = 32;
+  constexpr uint32_t STAGE_BYTES = Tf32Cfg<BN>::STAGE_BYTES, TMEM_COLS = Tf32Cfg<BN>::TMEM_COLS;
+  constexpr uint32_t A_B = Tf32Cfg<BN>::A_B, B_B = Tf32Cfg<BN>::B_B;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stg = smem + (size_t)STAGES * STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(stg + STG_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = (p.M + BM - 1) / BM, nt = (p.N + BN - 1) / BN;
+  const int ntiles = mt * nt, kb = (p.K + BK32 - 1) / BK32;
+  const bool nfast = nt < mt;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAl) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBl) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < ACC_STAGES; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {  // ------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int m0 = (nfast ? tile / nt : tile % mt) * BM, n0 = (nfast ? tile % nt : tile / mt) * BN;
+      for (int k = 0; k < kb; ++k) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&full[stage], STAGE_BYTES);
+          uint8_t* a = smem + (size_t)stage * STAGE_BYTES;
+          tma_load_2d(a, &tmAh, k * BK32, m0, &full[stage]);
+          tma_load_2d(a + A_B, &tmAl, k * BK32, m0, &full[stage]);
+          tma_load_2d(a + 2 * A_B, &tmBh, k * BK32, n0, &full[stage]);
+          tma_load_2d(a + 2 * A_B + B_B, &tmBl, k * BK32, n0, &full[stage]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {  // ----------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
+    const uint32_t s0 = smem_u32(smem);
+    const uint64_t ah0 = umma_desc_k128(s0), al0 = umma_desc_k128(s0 + A_B), bh0 = umma_desc_k128(s0 + 2 * A_B),
+                   bl0 = umma_desc_k128(s0 + 2 * A_B + B_B);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int k = 0; k < kb; ++k) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint64_t so = (uint64_t)(stage * (STAGE_BYTES >> 4));
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {   // 8 tf32 = 32 bytes = 2 descriptor units per k-step
+            tc_mma_tf32(d_tmem, al0 + so + 2 * kk, bh0 + so + 2 * kk, idesc, (k != 0) || (kk != 0));   // small terms first
+            tc_mma_tf32(d_tmem, ah0 + so + 2 * kk, bl0 + so + 2 * kk, idesc, 1);
+            tc_mma_tf32(d_tmem, ah0 + so + 2 * kk, bh0 + so + 2 * kk, idesc, 1);
+          }
+          tc_commit(&empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (elect_one()) tc_commit(&tfull[acc]);
+      __syncwarp();
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {  // ------------------------------------------------------ epilogue
+    const int ew = warp & 3, half = (warp - 4) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int m0 = (nfast ? tile / nt : tile % mt) * BM, n0 = (nfast ? tile % nt : tile / mt) * BN;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16);
+      epilogue_warp<EPI_STORE>(p, tbase, m0 + ew * 32, n0, half * (BN / 64), BN / 64, stg + (warp - 4) * 4096, lane, false,
+                               true, 0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// hi = x with the low 13 mantissa bits cleared (exactly representable as tf32), lo = x - hi (exact).
+__global__ void split_tf32_kernel(const float* __restrict__ src, int rows, int cols, int lds, float* __restrict__ hi,
+                                  float* __restrict__ lo, int ldd) {
+  const long long n = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+    const float x = src[(size_t)r * lds + c];
+    const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    hi[(size_t)r * ldd + c] = h;
+    lo[(size_t)r * ldd + c] = x - h;
+  }
+}
+
+template <int BN>
+int launch_tf32x3(const TcParams& p, const float* Ah, const float* Al, int lda, const float* Bh, const float* Bl, int ldb,
+                  cudaStream_t s, int sms) {
+  CUtensorMap tmAh, tmAl, tmBh, tmBl;
+  ST_TRY(make_tmap_f32(&tmAh, Ah, p.M, p.K, lda, BM, "A_hi"));
+  ST_TRY(make_tmap_f32(&tmAl, Al, p.M, p.K, lda, BM, "A_lo"));
+  ST_TRY(make_tmap_f32(&tmBh, Bh, p.N, p.K, ldb, BN, "B_hi"));
+  ST_TRY(make_tmap_f32(&tmBl, Bl, p.N, p.K, ldb, BN, "B_lo"));
+  auto kern = gemm_tf32x3_kernel<BN>;
+  ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tf32Cfg<BN>::SMEM_BYTES));
+  const int ntiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
+  const int grid = ntiles < sms ? ntiles : sms;
+  ST_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(NTHREADS), Tf32Cfg<BN>::SMEM_BYTES, s, tmAh, tmAl, tmBh, tmBl, p));
+  note_launch();
+  return ST_OK;
+}
+
 // --------------------------------------------------------------------------------- CTA-pair kernel
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -832,6 +1004,33 @@ int st_vocab_ce_fwd(int M, int V, int H, const void* Hs, int ldh, const void* Wv
   ce_combine_kernel<<<(M + 127) / 128, 128, 0, s>>>(M, p.npart, part_max, part_sum, tlogit, lse, loss_sum);
   ST_LAUNCH_TRY("ce_combine_kernel");
   return ST_OK;
+}
+
+int st_split_tf32(const float* src, int rows, int cols, int lds, float* hi, float* lo, int ldd, st_stream_t stream) {
+  using namespace st;
+  ST_REQUIRE(src && hi && lo, ST_ERR_NULL, "st_split_tf32: NULL pointer");
+  ST_REQUIRE(rows >= 1 && cols >= 1 && lds >= cols && ldd >= cols, ST_ERR_BAD_SHAPE,
+             "st_split_tf32: rows=%d cols=%d lds=%d ldd=%d", rows, cols, lds, ldd);
+  const long long n = (long long)rows * cols;
+  const long long blocks = (n + 255) / 256;
+  split_tf32_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, as_stream(stream)>>>(src, rows, cols, lds, hi, lo, ldd);
+  ST_LAUNCH_TRY("split_tf32_kernel");
+  return ST_OK;
+}
+
+int st_gemm_tf32x3(int M, int N, int K, const float* A_hi, const float* A_lo, int lda, const float* B_hi,
+                   const float* B_lo, int ldb, float* C, int ldc, const float* bias, float alpha, float beta,
+                   st_stream_t stream) {
+  using namespace st;
+  ST_REQUIRE(C != nullptr, ST_ERR_NULL, "st_gemm_tf32x3: C is NULL");
+  ST_REQUIRE(M >= 1 && N >= 1 && K >= 1 && ldc >= N, ST_ERR_BAD_SHAPE, "st_gemm_tf32x3: M=%d N=%d K=%d ldc=%d", M, N, K, ldc);
+  TcParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.C = C; p.ldc = ldc; p.c_bf16 = 0; p.bias = bias; p.alpha = alpha; p.beta = beta;
+  int sms = 0;
+  ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
+  return pick_bn(M, N, sms) == 256 ? launch_tf32x3<256>(p, A_hi, A_lo, lda, B_hi, B_lo, ldb, as_stream(stream), sms)
+                                   : launch_tf32x3<128>(p, A_hi, A_lo, lda, B_hi, B_lo, ldb, as_stream(stream), sms);
 }
 
 int st_debug_gemm_variant(int variant) {

@@ -11,6 +11,8 @@ namespace st {
 // box_rows box and 128-byte swizzle; out-of-bounds elements read as zero.  (tmap.cu)
 int make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, const char* what);
 
+int make_tmap_f32(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, const char* what);
+
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -72,6 +74,15 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// kind::tf32: fp32 operands in shared memory, read as tf32 (10-bit mantissa), fp32 accumulate; K = 8 per instruction
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets lane (base_lane + t).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -105,7 +116,10 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-
+// Instruction descriptor for kind::tf32: D fp32, A/B tf32 (format 2), both K-major.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 
 #endif  // __CUDACC__
 }  // namespace st

@@ -41,5 +41,23 @@ int make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int
   return ST_OK;
 }
 
+// Row-major fp32 matrix (rows, cols), ld elements; box = 32 columns (128 B) x box_rows, SW128 (tf32 operands).
+int make_tmap_f32(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, const char* what) {
+  ST_REQUIRE(ptr != nullptr, ST_ERR_NULL, "gemm_tf32x3: %s is NULL", what);
+  ST_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 4 == 0 && ld >= cols, ST_ERR_BAD_SHAPE,
+             "gemm_tf32x3: %s must be 16-byte aligned with a leading dimension that is a multiple of 4 "
+             "(ld=%d cols=%d)", what, ld, cols);
+  EncodeFn enc;
+  ST_TRY(get_encode(&enc));
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ST_REQUIRE(r == CUDA_SUCCESS, ST_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+  return ST_OK;
+}
 
 }  // namespace st

@@ -9,6 +9,11 @@ from ._lib import RnnWeights, check, ptr, stream_ptr
 F32, I64, I32 = torch.float32, torch.int64, torch.int32
 
 
+# nn.Linear products inside the decoding loops: "fp32" = CUDA cores (the arithmetic token ids are defined
+# against), "tf32x3" = tensor cores with hi/lo-split operands (fp32-accurate, ~5x the throughput).
+GEMM_MODES = {"fp32": 0, "tf32x3": 1}
+
+
 class WeightPack:
     """Keeps the ctypes pointer arrays (host memory) alive for the duration of a call."""
 
@@ -24,7 +29,8 @@ class WeightPack:
         self.bih, self.bhh = arr("unit.bias_ih_l{}"), arr("unit.bias_hh_l{}")
         self.struct = RnnWeights(mod._kind, L, mod.embed_dim, mod.num_hidden_units, mod.vocab_size,
                                  sd["embeddings.weight"].data_ptr(), self.wih, self.whh, self.bih, self.bhh,
-                                 sd["linear.weight"].data_ptr(), sd["linear.bias"].data_ptr())
+                                 sd["linear.weight"].data_ptr(), sd["linear.bias"].data_ptr(),
+                                 GEMM_MODES[getattr(mod, "decode_gemm", "fp32")])
 
     def workspace(self, n_img, K, max_len, device):
         nbytes = _lib.load().st_decode_workspace_bytes(C.byref(self.struct), n_img, K, max_len)

@@ -309,6 +309,36 @@ def gemm_bf16(A, B, *, bias=None, out_dtype=F32, alpha=1.0, beta=0.0, out=None, 
     return out
 
 
+def split_tf32(x):
+    """fp32 (R,C) -> (hi, lo): hi keeps the upper 11 mantissa bits (a tf32), lo = x - hi exactly.  Leading
+    dimensions padded to multiples of 4 (TMA operands)."""
+    lib = _lib.load()
+    if x.dim() != 2 or x.dtype != F32 or x.stride(1) != 1 or not x.is_cuda:
+        raise ValueError("split_tf32: 2-D fp32 CUDA tensor with unit inner stride expected")
+    R, Cc = x.shape
+    ld = (Cc + 3) // 4 * 4
+    hi = torch.zeros(R, ld, dtype=F32, device=x.device)[:, :Cc]
+    lo = torch.zeros(R, ld, dtype=F32, device=x.device)[:, :Cc]
+    check(lib.st_split_tf32(ptr(x, F32), R, Cc, x.stride(0), _raw(hi), _raw(lo), ld, stream_ptr()), "st_split_tf32")
+    return hi, lo
+
+
+def gemm_tf32x3(A, B, *, bias=None, alpha=1.0, beta=0.0, out=None):
+    """out[M,N] = alpha * A . B^T + bias to fp32 accuracy on the tensor cores.  A, B: (hi, lo) pairs from
+    split_tf32."""
+    lib = _lib.load()
+    (Ah, Al), (Bh, Bl) = A, B
+    M, K = Ah.shape
+    N, Kb = Bh.shape
+    if K != Kb:
+        raise ValueError(f"gemm_tf32x3: inner dimensions differ ({K} vs {Kb})")
+    if out is None:
+        out = torch.empty(M, N, dtype=F32, device=Ah.device)
+    check(lib.st_gemm_tf32x3(M, N, K, _raw(Ah), _raw(Al), Ah.stride(0), _raw(Bh), _raw(Bl), Bh.stride(0), _raw(out),
+                             out.stride(0), ptr(bias, F32), float(alpha), float(beta), stream_ptr()), "st_gemm_tf32x3")
+    return out
+
+
 def cast_bf16(src, want=True, want_t=False):
     """fp32 (R,C) -> (bf16 (R,C) or None, bf16 transpose (C,R) or None).  Leading dimensions are
     padded to multiples of 8 so the results are valid TMA operands; the returned tensors are the

@@ -100,12 +100,16 @@ def _check_chain(m, p, feat, K, max_len=25, eps=1e-5):
     return full, feat.shape[0]
 
 
+# decode_gemm: the nn.Linear products of the decoding loops on the CUDA cores (fp32) or as 3xTF32 on the
+# tensor cores (fp32-accurate) -- the same parity criteria hold for both
+@pytest.mark.parametrize("gemm", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("name,K", [("gru_l1", 1), ("gru_l1", 3), ("gru_l1", 5), ("gru_tiny", 2),
                                     ("gru_l2", 3), ("gru_med", 3)])
-def test_golden_beam_chain(name, K):
+def test_golden_beam_chain(name, K, gemm):
     dev = torch.device("cuda:0")
     g = load_golden(name)
     m = _module(g, dev)
+    m.decode_gemm = gemm
     feat = torch.from_numpy(g["cnn_feature"]).to(dev)
     _check_chain(m, golden_params(g), feat, K)
     tok = m.sentence_index(feat, beam_size=K)
@@ -221,13 +225,30 @@ def test_oracle_parity_greedy_full_size(kind, L):
     assert np.array_equal(tok.cpu().numpy(), ref.numpy())
 
 
+@pytest.mark.parametrize("gemm", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("K", [3, 5])
-def test_oracle_parity_beam_chain_full_size(K):
+def test_oracle_parity_beam_chain_full_size(K, gemm):
     dev = torch.device("cuda:0")
     m, feat, _, _ = _random_case("gru", 512, 512, 10000, 1, 6, 20, 13, False)
+    m.decode_gemm = gemm
     p = {k: v.detach().clone() for k, v in m.state_dict().items()}
     full, n = _check_chain(m.to(dev), p, feat.to(dev), K, max_len=20)
     print(f"beam-{K} chain, full size: {full}/{n} rows separated in every round and bit-exact")
+
+
+@pytest.mark.parametrize("K", [0, 3])
+def test_decode_tensor_core_gemm_agrees_with_fp32(K):
+    """Bench-size check of decode_gemm="tf32x3": greedy / beam-3 captions of 512 images against the fp32
+    CUDA-core path.  Differences can only come from rankings decided inside fp32 rounding noise."""
+    dev = torch.device("cuda:0")
+    m, feat, _, _ = _random_case("gru", 512, 512, 10000, 1, 512, 20, 17, False)
+    m, feat = m.to(dev), feat.to(dev)
+    a = m.sentence_index(feat, beam_size=K, max_len=20)
+    m.decode_gemm = "tf32x3"
+    b = m.sentence_index(feat, beam_size=K, max_len=20)
+    same = int((a == b).all(dim=1).sum())
+    print(f"decode_gemm tf32x3 vs fp32, K={K}: {same}/512 captions identical")
+    assert same >= 500
 
 
 def test_cpu_tensors_raise():

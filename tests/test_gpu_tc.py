@@ -53,6 +53,28 @@ def test_gemm_bf16(M, N, K, variant, gemm_variant):
     assert bool((wide[:, :4] == 7).all()) and bool((wide[:, 4 + N:] == 7).all())
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (100, 50, 40), (129, 257, 72), (640, 10000, 512), (4096, 1536, 512),
+                                   (37, 1000, 2048), (4096, 10000, 512)])
+def test_gemm_tf32x3_is_fp32_accurate(M, N, K):
+    """The 3xTF32 tensor-core GEMM of the decoding loops against float64: its error must be of the size of the
+    fp32 CUDA-core GEMM's own rounding noise (it replaces that GEMM where token ids are defined against fp32)."""
+    from showtell_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    B = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    ref = A.double() @ B.double().t() + bias.double()
+    hiA, loA = ops.split_tf32(A)
+    assert torch.equal(hiA + loA, A) and bool(((hiA.view(torch.int32) & 0x1fff) == 0).all())
+    out = ops.gemm_tf32x3((hiA, loA), ops.split_tf32(B), bias=bias)
+    e_tc = rel_err(out, ref)
+    e_sg = rel_err(ops.sgemm(A, B, transB=True, bias=bias), ref)
+    assert e_tc < 2e-6 and e_tc < 4 * e_sg + 2e-7, (e_tc, e_sg)
+    acc = torch.randn(M, N, generator=g).to(DEV)
+    out2 = ops.gemm_tf32x3((hiA, loA), ops.split_tf32(B), alpha=0.5, beta=1.0, out=acc.clone())
+    assert rel_err(out2, 0.5 * (ref - bias.double()) + acc.double()) < 2e-6
+
+
 def test_cast_bf16():
     from showtell_b200 import ops
     x = torch.randn(70, 45, device=DEV)

@@ -20,6 +20,6 @@ $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches_lstm.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "ncu list rc=$?"
 $CMD > gpurun_out/plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'gemm_tc|rnn_seq_tc|rnn_cluster' -s 40 -c 12 -f -o gpurun_out/${TAG}_lstm_full $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'gemm_tc|rnn_seq_tc|rnn_cluster' -s 52 -c 14 -f -o gpurun_out/${TAG}_lstm_full $CMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"
 tail -2 gpurun_out/ncu_full.log

@@ -44,18 +44,18 @@ def full(rep, out, title):
     hdr, units, data = rows[0], rows[1], rows[2:]
     want = OrderedDict([
         ("time us", "gpu__time_duration.sum"),
-        ("tensor pipe %", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"),
+        ("tensor pipe %", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
         ("DRAM rd MB", "dram__bytes_read.sum"),
         ("DRAM wr MB", "dram__bytes_write.sum"),
         ("DRAM %", "dram__throughput.avg.pct_of_peak_sustained_elapsed"),
-        ("L2 MB", "lts__t_bytes.sum"),
-        ("warp insts", "sm__inst_executed.sum"),
+        ("L2 sectors", "lts__t_sectors.sum"),
+        ("warp insts", "smsp__inst_executed.sum"),
         ("regs", "launch__registers_per_thread"),
         ("smem KB", "launch__shared_mem_per_block_dynamic"),
     ])
     idx = {}
     for k, m in want.items():
-        idx[k] = next((i for i, h in enumerate(hdr) if h == m or h.endswith("." + m)), None)
+        idx[k] = next((i for i, h in enumerate(hdr) if h == m), None)
     kn, gs, bs = col(hdr, "Kernel Name"), col(hdr, "Grid Size"), col(hdr, "Block Size")
     lines = [f"# {title}", "",
              f"Source: `{rep}` (`ncu --set full --clock-control none --import-source on`; per-launch numbers are "
@@ -77,10 +77,13 @@ def full(rep, out, title):
                 cells.append(f"{to_bytes(r[i], u) / 1e6:.1f}")
             elif k == "smem KB":
                 cells.append(f"{to_bytes(r[i], u) / 1e3:.1f}")
-            elif k == "warp insts":
+            elif k in ("warp insts", "L2 sectors"):
                 cells.append(f"{int(float(r[i].replace(',', ''))):,}")
             else:
-                cells.append(r[i])
+                try:
+                    cells.append(f"{float(r[i].replace(',', '')):.1f}")
+                except ValueError:
+                    cells.append(r[i])
         lines.append(f"| {n} | `{short(r[kn])}` | {r[gs]} | {r[bs]} | " + " | ".join(cells) + " |")
     open(out, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines))
