@@ -78,6 +78,11 @@ def test_golden_greedy(name):
     assert np.array_equal(tok1.cpu().numpy(), g["greedy_b1"])
 
 
+# ranking margins (in logit units) below which a chain-beam round is decided by the rounding noise of the
+# products: 1e-5 for fp32 CUDA-core GEMMs, 4e-5 for the 3xTF32 tensor-core GEMMs (test_gemm_tf32x3_is_fp32_accurate)
+EPS = {"fp32": 1e-5, "tf32x3": 4e-5}
+
+
 def _check_chain(m, p, feat, K, max_len=25, eps=1e-5):
     """CUDA chain beam vs the oracle, row by row: identical survivors (words + scores) in every
     round up to the first round whose ranking hangs on <= eps of logit; identical final sentence
@@ -93,7 +98,7 @@ def _check_chain(m, p, feat, K, max_len=25, eps=1e-5):
         stop = O.beam_chain_margin(trace, K, eps)
         for r in range(min(stop, len(trace))):
             assert tw[r, i].tolist() == trace[r]["words"], (i, r)
-            assert np.allclose(ts[r, i].numpy(), np.array(trace[r]["scores"][:K]), atol=2e-5), (i, r)
+            assert np.allclose(ts[r, i].numpy(), np.array(trace[r]["scores"][:K]), atol=2 * eps), (i, r)
         if stop == len(trace):
             full += 1
             assert tok[i].tolist() == seq.tolist(), i
@@ -111,7 +116,7 @@ def test_golden_beam_chain(name, K, gemm):
     m = _module(g, dev)
     m.decode_gemm = gemm
     feat = torch.from_numpy(g["cnn_feature"]).to(dev)
-    _check_chain(m, golden_params(g), feat, K)
+    _check_chain(m, golden_params(g), feat, K, eps=EPS[gemm])
     tok = m.sentence_index(feat, beam_size=K)
     same = (tok.cpu().numpy() == g[f"beam_chain_k{K}"]).all(axis=1).sum()
     print(f"{name} K={K}: {same}/{feat.shape[0]} rows identical to the reference run")
@@ -232,7 +237,7 @@ def test_oracle_parity_beam_chain_full_size(K, gemm):
     m, feat, _, _ = _random_case("gru", 512, 512, 10000, 1, 6, 20, 13, False)
     m.decode_gemm = gemm
     p = {k: v.detach().clone() for k, v in m.state_dict().items()}
-    full, n = _check_chain(m.to(dev), p, feat.to(dev), K, max_len=20)
+    full, n = _check_chain(m.to(dev), p, feat.to(dev), K, max_len=20, eps=EPS[gemm])
     print(f"beam-{K} chain, full size: {full}/{n} rows separated in every round and bit-exact")
 
 
