@@ -151,6 +151,24 @@ int st_scale_multi(int n, const float* const* src, float* const* dst, const int6
 int st_rowsum_bf16(float* out, const void* M, int rows, int cols, int ld, st_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange.  The reference is single-process; under batch
+ * sharding the step after main.py:150 `loss.backward()` / main_attn.py:133 is a sum of every
+ * parameter gradient over the ranks before main.py:152 `optimizer.step()`.
+ *
+ * In-place sum all-reduce of `count` fp32 values held in a SYMMETRIC buffer: the same allocation on
+ * every GPU of the node, rank r's copy mapped into this process at peers_host[r] (NVLink peer
+ * mapping; peers_host[rank] is the local copy), optionally with one multicast mapping of all
+ * copies (`multicast`, NULL if the fabric has none: multimem.ld_reduce / multimem.st run the sum
+ * inside the NVSwitch).  flags_host[r]: rank r's flag area, st_allreduce_flag_words(world)
+ * uint32, zeroed ONCE before the first call (the barriers restore them to zero).  One kernel of
+ * `nblocks` CTAs per rank; every rank must issue the same sequence of calls with the same count and
+ * nblocks.  Stream-ordered, CUDA-graph capturable; count % 4 == 0 and 16-byte aligned mappings. */
+enum { ST_AR_MAX_WORLD = 8, ST_AR_MAX_BLOCKS = 64 };
+int st_allreduce_flag_words(int world);
+int st_allreduce_sum_f32(void* const* peers_host, void* multicast, void* const* flags_host, int rank, int world,
+                         int64_t count, int nblocks, st_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Recurrent sequence, forward (the inside of nn.GRU / nn.LSTM over a PackedSequence,
  * rnn.py:32, rnn_lstm.py:30; one call per layer).  Persistent cooperative kernel: each CTA keeps
  * its slice of W_hh in shared memory for all steps, fuses h.W_hh^T with the gate math and the

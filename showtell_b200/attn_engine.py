@@ -130,9 +130,11 @@ def attn_forward(mode, P, kind, L, feature, caption, bs, save):
     return outs[L - 1]["Hs"], alphas, sv
 
 
-def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=None):
+def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=None, emb_out=None, recurrent_done=None):
     """Gradients of every parameter given dHs_top (N,H) and the gradient w.r.t. alphas, either a
-    full (B,Tcap,P) tensor `dalphas` (drop-in forward) or the per-(b,p) penalty term `Gpen`."""
+    full (B,Tcap,P) tensor `dalphas` (drop-in forward) or the per-(b,p) penalty term `Gpen`.
+    Data parallelism: `emb_out()` supplies the embedding-gradient buffer, `recurrent_done(grads)` is
+    called once the unit.* and embedding gradients are final (the attention parameters follow)."""
     bs, off, Pn, B, tc = sv["bs"], sv["off"], sv["Pn"], sv["B"], sv["tc"]
     T, N = len(bs), sum(bs)
     E = P["embeddings.weight"].shape[1]
@@ -210,9 +212,11 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
         dXemb = ops.gemm_bf16(bouts[0]["dGb"], W["ihe"][1], tag="ih_dx")
     else:
         dXemb = ops.sgemm(bouts[0]["dG"], Wih0[:, :E], tag="ih_dx")
-    dEmb = torch.zeros_like(P["embeddings.weight"])
+    dEmb = emb_out().zero_() if emb_out is not None else torch.zeros_like(P["embeddings.weight"])
     ops.pack_inputs_bwd(dXemb, dEmb, None, caption, bs, False)
     grads["embeddings.weight"] = dEmb
+    if recurrent_done is not None:
+        recurrent_done(grads)
     # attention parameters
     datt1, datt1T, dwf = ops.attn_hoist_bwd(bs, Pn, att1, att2_all, de_all, wf, want_t=(mode == "bf16"))
     if mode == "bf16":
@@ -316,18 +320,34 @@ class AttnLossFn(torch.autograd.Function):
         def body(feat, capt):
             Hs, alphas, sv = attn_forward(mode, P, kind, L, feat, capt, bs, need)
             target = ops.pack_targets(capt, bs)
-            loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, dt, need)
+            gout = red.slots([P["linear.weight"].shape, P["linear.bias"].shape]) if (red is not None and need) else None
+            loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, dt, need, gout=gout)
             pen_sum, Gpen = ops.attn_penalty(sv["S"], coef)
             loss = loss + coef * pen_sum.reshape(())
             g2 = None
-            if need:
-                if red is not None:                     # overlaps with the reverse loop
-                    red.reduce([grads["linear.weight"], grads["linear.bias"]], ready=vdone)
+            if need and red is None:
                 g2 = attn_backward(mode, P, kind, L, capt, sv, dHs, Gpen=Gpen)
                 ops.join(vdone)
-                if red is not None:
-                    red.reduce([g2[n] for n in names if n in g2])
-                    red.finish()
+                g2.update(grads)
+            elif need:
+                # data parallel: the vocabulary projection's exchange overlaps the reverse loop, the
+                # recurrent + embedding gradients' overlaps the hoisted attention passes, the rest is last
+                lin = ["linear.weight", "linear.bias"]
+                grads.update(zip(lin, red.reduce([grads[n] for n in lin], ready=vdone)))
+                rec = sorted(n for n in names if n.startswith("unit.")) + ["embeddings.weight"]
+
+                def emb_out():
+                    v = red.slots([P[n].shape for n in rec])
+                    return v[-1] if v else torch.empty_like(P["embeddings.weight"])
+
+                def recurrent_done(g):
+                    g.update(zip(rec, red.reduce([g[n] for n in rec])))
+
+                g2 = attn_backward(mode, P, kind, L, capt, sv, dHs, Gpen=Gpen, emb_out=emb_out,
+                                   recurrent_done=recurrent_done)
+                rest = [n for n in names if n in g2 and n not in rec]
+                g2.update(zip(rest, red.reduce([g2[n] for n in rest])))
+                red.finish()
                 g2.update(grads)
             return loss, alphas, g2
 

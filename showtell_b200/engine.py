@@ -36,9 +36,12 @@ class Linear:
             Xb, self.XT = ops.cast_bf16(X, True, self.need_bwd)
         return ops.gemm_bf16(Xb, self.Wb, bias=self.bias, out_dtype=out_dtype, tag=self.tag + "_fwd")
 
-    def bwd_bf16(self, dYb, dYT, need_dx=True):
-        """Backward from gate gradients that already are bf16 GEMM operands (row-major + transposed)."""
+    def bwd_bf16(self, dYb, dYT, need_dx=True, after_dw=None):
+        """Backward from gate gradients that already are bf16 GEMM operands (row-major + transposed).
+        `after_dw(dW)`: called between the weight-gradient and the input-gradient product."""
         dW = ops.gemm_bf16(dYT, self.XT, tag=self.tag + "_dw")
+        if after_dw is not None:
+            after_dw(dW)
         dX = ops.gemm_bf16(dYb, self.WT, tag=self.tag + "_dx") if need_dx else None
         return dX, dW
 
@@ -89,9 +92,11 @@ def stack_forward(mode, P, kind, L, X, bs, save):
     return inp, layers
 
 
-def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True):
+def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True, weights_done=None):
     """BPTT through the L layers, top down.  Fills grads[...] for the unit.* parameters and returns
-    the gradient w.r.t. the packed layer-0 input (N, in_0)."""
+    the gradient w.r.t. the packed layer-0 input (N, in_0).  `weights_done()`: called as soon as every
+    unit.* gradient is final (bf16 mode: before layer 0's input-gradient product), so a gradient
+    reducer can start their exchange while the embedding gradient is still being formed."""
     dH = dHs_top
     for l in reversed(range(L)):
         _, Whh, _, _ = layer_params(P, l)
@@ -102,13 +107,19 @@ def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True):
             _, HprevT = ops.cast_bf16(Hprev, False, True)
             grads[f"unit.weight_hh_l{l}"] = ops.gemm_bf16(b["dGhT"], HprevT, tag="hh_dw")
             grads[f"unit.bias_hh_l{l}"], grads[f"unit.bias_ih_l{l}"] = b["dbhh"], b["dbih"]
-            dH, grads[f"unit.weight_ih_l{l}"] = sv["lin"].bwd_bf16(b["dGb"], b["dGT"], need_dx=(l > 0 or need_dx0))
+            def _dw_ready(dW, l=l):
+                grads[f"unit.weight_ih_l{l}"] = dW
+                if l == 0 and weights_done is not None:
+                    weights_done()
+            dH, _ = sv["lin"].bwd_bf16(b["dGb"], b["dGT"], need_dx=(l > 0 or need_dx0), after_dw=_dw_ready)
             continue
         b = ops.rnn_seq_bwd(kind, Whh, bs, sv["out"], dH, tag="seq_bwd")
         grads[f"unit.weight_hh_l{l}"] = weight_grad(mode, b["dGh"], Hprev, "hh_dw")  # dGh^T Hprev
         grads[f"unit.bias_hh_l{l}"] = ops.colsum(b["dGh"])
         dH, dW, db = sv["lin"].bwd(b["dG"], need_dx=(l > 0 or need_dx0))
         grads[f"unit.weight_ih_l{l}"], grads[f"unit.bias_ih_l{l}"] = dW, db
+        if l == 0 and weights_done is not None:
+            weights_done()
     return dH
 
 
@@ -117,9 +128,10 @@ def base_forward(mode, P, kind, L, feature, caption, bs, save):
     return stack_forward(mode, P, kind, L, X, bs, save)
 
 
-def base_backward_from_dHs(mode, P, kind, L, caption, bs, layers, dHs, grads, want_dfeature, feature_shape):
-    dX = stack_backward(mode, P, kind, L, bs, layers, dHs, grads)
-    dEmb = torch.zeros_like(P["embeddings.weight"])
+def base_backward_from_dHs(mode, P, kind, L, caption, bs, layers, dHs, grads, want_dfeature, feature_shape,
+                           weights_done=None, emb_out=None):
+    dX = stack_backward(mode, P, kind, L, bs, layers, dHs, grads, weights_done=weights_done)
+    dEmb = emb_out().zero_() if emb_out is not None else torch.zeros_like(P["embeddings.weight"])
     dfeat = torch.empty(feature_shape, dtype=F32, device=dX.device) if want_dfeature else None
     ops.pack_inputs_bwd(dX, dEmb, dfeat, caption, bs, True)
     grads["embeddings.weight"] = dEmb
@@ -172,12 +184,13 @@ class BaseLogitsFn(torch.autograd.Function):
         return (None, dfeat, None, None) + tuple(grads[n] for n in ctx.names)
 
 
-def vocab_ce(mode, P, Hs, target, denom, need):
+def vocab_ce(mode, P, Hs, target, denom, need, gout=None):
     """Mean cross-entropy of the vocabulary projection of Hs (N,H) and, if `need`, its gradients.
     Returns (loss (0-d), dHs or None, grads dict, event).  bf16 mode: the weight / bias gradients do
     not feed the rest of the backward pass, so they run on the side stream (ops.fork) beside the BPTT
     kernels; `event` marks their completion (None when they ran in line) -- ops.join it, or hand it to
-    the gradient reducer, before the gradients are read."""
+    the gradient reducer, before the gradients are read.  `gout`: optional [dW, db] output tensors (a
+    gradient reducer's symmetric bucket) for bf16 mode."""
     Wv, bv = P["linear.weight"], P["linear.bias"]
     grads = {}
     if mode == "fp32":
@@ -197,7 +210,8 @@ def vocab_ce(mode, P, Hs, target, denom, need):
     if need:
         Pm, PT = ops.vocab_ce_bwd(Hb, Wb, bv, target, lse, 1.0 / denom, tag="vocab_dlogits")
         (grads["linear.weight"], grads["linear.bias"]), done = ops.fork(
-            lambda: (ops.gemm_bf16(PT, HT, tag="vocab_dw"), ops.rowsum_bf16(PT)),     # db_v = row sums of dlogits^T
+            lambda: (ops.gemm_bf16(PT, HT, tag="vocab_dw", out=gout[0] if gout else None),
+                     ops.rowsum_bf16(PT, out=gout[1] if gout else None)),             # db_v = row sums of dlogits^T
             uses=(PT, HT))
         dHs = ops.gemm_bf16(Pm, WT, tag="vocab_dx")
     return (loss_sum / denom).reshape(()), dHs, grads, done
@@ -228,18 +242,32 @@ class BaseLossFn(torch.autograd.Function):
         def body(feat, cap):
             Hs, layers = base_forward(mode, P, kind, L, feat, cap, bs, need)
             target = ops.pack_targets(cap, bs)
-            loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, denom, need)
+            gout = red.slots([P["linear.weight"].shape, P["linear.bias"].shape]) if (red is not None and need) else None
+            loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, denom, need, gout=gout)
             dfeat = None
-            if need:
-                if red is not None:                     # overlaps with BPTT below
-                    red.reduce([grads["linear.weight"], grads["linear.bias"]], ready=vdone)
-                first = set(grads)
-                dfeat = base_backward_from_dHs(mode, P, kind, L, cap, bs, layers, dHs, grads, want_dfeat,
-                                               feat.shape)
+            if need and red is None:
+                dfeat = base_backward_from_dHs(mode, P, kind, L, cap, bs, layers, dHs, grads, want_dfeat, feat.shape)
                 ops.join(vdone)
-                if red is not None:
-                    red.reduce([grads[n] for n in names if n not in first])
-                    red.finish()
+            elif need:
+                # data parallel: three exchanges on the reducer's side stream, each issued the moment its
+                # gradients are final -- the vocabulary projection's overlaps BPTT, the recurrent weights'
+                # overlaps the embedding gradient (input-gradient product + scatter), the embedding's is last
+                lin = ["linear.weight", "linear.bias"]
+                grads.update(zip(lin, red.reduce([grads[n] for n in lin], ready=vdone)))
+                unit = [n for n in names if n.startswith("unit.")]
+
+                def weights_done():
+                    grads.update(zip(unit, red.reduce([grads[n] for n in unit])))
+
+                def emb_out():
+                    v = red.slots([P["embeddings.weight"].shape])
+                    return v[0] if v else torch.empty_like(P["embeddings.weight"])
+
+                dfeat = base_backward_from_dHs(mode, P, kind, L, cap, bs, layers, dHs, grads, want_dfeat, feat.shape,
+                                               weights_done=weights_done, emb_out=emb_out)
+                rest = [n for n in names if n not in lin and n not in unit]
+                grads.update(zip(rest, red.reduce([grads[n] for n in rest])))
+                red.finish()
             return loss, (grads if need else None), dfeat
 
         key = ("base", mode, kind, L, tuple(bs), tuple(feature_c.shape), tuple(caption_c.shape), need, want_dfeat,

@@ -141,21 +141,22 @@ def colsum(M, out=None, accumulate=False):
     return out
 
 
-def scale_multi(tensors, g):
+def scale_multi(tensors, g, outs=None):
     """[t * g for t in tensors] (fp32, contiguous; g a 0-d device tensor) with one launch per 32 tensors.
-    The results are views of one flat buffer."""
+    The results are views of one flat buffer, or the given contiguous `outs`."""
     import ctypes as C
     lib = _lib.load()
     tensors = [t.contiguous() for t in tensors]
     if not tensors:
         return []
     g = g.to(F32).reshape(1)
-    pad = lambda n: (n + 3) // 4 * 4
-    flat = torch.empty(sum(pad(t.numel()) for t in tensors), dtype=F32, device=tensors[0].device)
-    outs, off = [], 0
-    for t in tensors:
-        outs.append(flat[off:off + t.numel()].view_as(t))
-        off += pad(t.numel())
+    if outs is None:
+        pad = lambda n: (n + 3) // 4 * 4
+        flat = torch.empty(sum(pad(t.numel()) for t in tensors), dtype=F32, device=tensors[0].device)
+        outs, off = [], 0
+        for t in tensors:
+            outs.append(flat[off:off + t.numel()].view_as(t))
+            off += pad(t.numel())
     for i in range(0, len(tensors), 32):
         src, dst = tensors[i:i + 32], outs[i:i + 32]
         n = len(src)
@@ -166,9 +167,10 @@ def scale_multi(tensors, g):
     return outs
 
 
-def rowsum_bf16(M):
+def rowsum_bf16(M, out=None):
     lib = _lib.load()
-    out = torch.empty(M.shape[0], dtype=F32, device=M.device)
+    if out is None:
+        out = torch.empty(M.shape[0], dtype=F32, device=M.device)
     import ctypes as C
     check(lib.st_rowsum_bf16(ptr(out), C.c_void_p(M.data_ptr()), M.shape[0], M.shape[1], M.stride(0), stream_ptr()),
           "st_rowsum_bf16")
