@@ -36,12 +36,9 @@ class Linear:
             Xb, self.XT = ops.cast_bf16(X, True, self.need_bwd)
         return ops.gemm_bf16(Xb, self.Wb, bias=self.bias, out_dtype=out_dtype, tag=self.tag + "_fwd")
 
-    def bwd_bf16(self, dYb, dYT, need_dx=True, after_dw=None):
-        """Backward from gate gradients that already are bf16 GEMM operands (row-major + transposed).
-        `after_dw(dW)`: called between the weight-gradient and the input-gradient product."""
+    def bwd_bf16(self, dYb, dYT, need_dx=True):
+        """Backward from gate gradients that already are bf16 GEMM operands (row-major + transposed)."""
         dW = ops.gemm_bf16(dYT, self.XT, tag=self.tag + "_dw")
-        if after_dw is not None:
-            after_dw(dW)
         dX = ops.gemm_bf16(dYb, self.WT, tag=self.tag + "_dx") if need_dx else None
         return dX, dW
 
@@ -92,11 +89,11 @@ def stack_forward(mode, P, kind, L, X, bs, save):
     return inp, layers
 
 
-def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True, weights_done=None):
+def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True, dx0_ready=None):
     """BPTT through the L layers, top down.  Fills grads[...] for the unit.* parameters and returns
-    the gradient w.r.t. the packed layer-0 input (N, in_0).  `weights_done()`: called as soon as every
-    unit.* gradient is final (bf16 mode: before layer 0's input-gradient product), so a gradient
-    reducer can start their exchange while the embedding gradient is still being formed."""
+    the gradient w.r.t. the packed layer-0 input (N, in_0).  `dx0_ready(dX)`: called as soon as that
+    input gradient exists (bf16 mode: before layer 0's weight-gradient products), so the embedding
+    gradient and its exchange can start while the last weight gradients are still being formed."""
     dH = dHs_top
     for l in reversed(range(L)):
         _, Whh, _, _ = layer_params(P, l)
@@ -104,22 +101,22 @@ def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True, 
         Hprev = ops.shift_states(sv["out"]["Hs"], bs)
         b = ops.rnn_seq_tc_bwd(kind, sv["WhhT"], bs, sv["out"], dH, tag="seq_bwd") if sv["WhhT"] is not None else None
         if b is not None:                                                  # tensor-core BPTT: bf16 operands out
+            need_dx = l > 0 or need_dx0
+            dH = ops.gemm_bf16(b["dGb"], sv["lin"].WT, tag="ih_dx") if need_dx else None
+            if l == 0 and dx0_ready is not None:
+                dx0_ready(dH)
             _, HprevT = ops.cast_bf16(Hprev, False, True)
             grads[f"unit.weight_hh_l{l}"] = ops.gemm_bf16(b["dGhT"], HprevT, tag="hh_dw")
             grads[f"unit.bias_hh_l{l}"], grads[f"unit.bias_ih_l{l}"] = b["dbhh"], b["dbih"]
-            def _dw_ready(dW, l=l):
-                grads[f"unit.weight_ih_l{l}"] = dW
-                if l == 0 and weights_done is not None:
-                    weights_done()
-            dH, _ = sv["lin"].bwd_bf16(b["dGb"], b["dGT"], need_dx=(l > 0 or need_dx0), after_dw=_dw_ready)
+            _, grads[f"unit.weight_ih_l{l}"] = sv["lin"].bwd_bf16(b["dGb"], b["dGT"], need_dx=False)
             continue
         b = ops.rnn_seq_bwd(kind, Whh, bs, sv["out"], dH, tag="seq_bwd")
         grads[f"unit.weight_hh_l{l}"] = weight_grad(mode, b["dGh"], Hprev, "hh_dw")  # dGh^T Hprev
         grads[f"unit.bias_hh_l{l}"] = ops.colsum(b["dGh"])
         dH, dW, db = sv["lin"].bwd(b["dG"], need_dx=(l > 0 or need_dx0))
         grads[f"unit.weight_ih_l{l}"], grads[f"unit.bias_ih_l{l}"] = dW, db
-        if l == 0 and weights_done is not None:
-            weights_done()
+        if l == 0 and dx0_ready is not None:
+            dx0_ready(dH)
     return dH
 
 
@@ -129,13 +126,21 @@ def base_forward(mode, P, kind, L, feature, caption, bs, save):
 
 
 def base_backward_from_dHs(mode, P, kind, L, caption, bs, layers, dHs, grads, want_dfeature, feature_shape,
-                           weights_done=None, emb_out=None):
-    dX = stack_backward(mode, P, kind, L, bs, layers, dHs, grads, weights_done=weights_done)
-    dEmb = emb_out().zero_() if emb_out is not None else torch.zeros_like(P["embeddings.weight"])
-    dfeat = torch.empty(feature_shape, dtype=F32, device=dX.device) if want_dfeature else None
-    ops.pack_inputs_bwd(dX, dEmb, dfeat, caption, bs, True)
-    grads["embeddings.weight"] = dEmb
-    return dfeat
+                           emb_out=None, emb_done=None):
+    """`emb_out()` / `emb_done()`: data parallelism -- buffer for the embedding gradient, and a call
+    the moment it is final (the layer-0 weight gradients are formed after it)."""
+    box = {}
+
+    def dx0_ready(dX):
+        dEmb = emb_out().zero_() if emb_out is not None else torch.zeros_like(P["embeddings.weight"])
+        box["dfeat"] = torch.empty(feature_shape, dtype=F32, device=dX.device) if want_dfeature else None
+        ops.pack_inputs_bwd(dX, dEmb, box["dfeat"], caption, bs, True)
+        grads["embeddings.weight"] = dEmb
+        if emb_done is not None:
+            emb_done()
+
+    stack_backward(mode, P, kind, L, bs, layers, dHs, grads, dx0_ready=dx0_ready)
+    return box["dfeat"]
 
 
 def _check_inputs(feature, caption, lengths, E):
@@ -250,22 +255,22 @@ class BaseLossFn(torch.autograd.Function):
                 ops.join(vdone)
             elif need:
                 # data parallel: three exchanges on the reducer's side stream, each issued the moment its
-                # gradients are final -- the vocabulary projection's overlaps BPTT, the recurrent weights'
-                # overlaps the embedding gradient (input-gradient product + scatter), the embedding's is last
+                # gradients are final -- the vocabulary projection's overlaps BPTT, the embedding's (the
+                # large one) overlaps the layer-0 weight-gradient products, the small recurrent weights' is last
                 lin = ["linear.weight", "linear.bias"]
                 grads.update(zip(lin, red.reduce([grads[n] for n in lin], ready=vdone)))
-                unit = [n for n in names if n.startswith("unit.")]
-
-                def weights_done():
-                    grads.update(zip(unit, red.reduce([grads[n] for n in unit])))
+                emb = ["embeddings.weight"]
 
                 def emb_out():
                     v = red.slots([P["embeddings.weight"].shape])
                     return v[0] if v else torch.empty_like(P["embeddings.weight"])
 
+                def emb_done():
+                    grads.update(zip(emb, red.reduce([grads[n] for n in emb])))
+
                 dfeat = base_backward_from_dHs(mode, P, kind, L, cap, bs, layers, dHs, grads, want_dfeat, feat.shape,
-                                               weights_done=weights_done, emb_out=emb_out)
-                rest = [n for n in names if n not in lin and n not in unit]
+                                               emb_out=emb_out, emb_done=emb_done)
+                rest = [n for n in names if n not in lin and n not in emb]
                 grads.update(zip(rest, red.reduce([grads[n] for n in rest])))
                 red.finish()
             return loss, (grads if need else None), dfeat

@@ -94,6 +94,8 @@ class GradReducer:
         self._pending = []
         self._buckets = {}
         self._call = 0
+        # development aid: exchanges (by position in the step) whose kernel is not launched -- timing breakdowns only
+        self._skip = {int(x) for x in os.environ.get("SHOWTELL_AR_SKIP", "").split(",") if x.strip()}
 
     def _side_stream(self, device):
         if self._stream is None:
@@ -154,7 +156,8 @@ class GradReducer:
                 todo = [(t, v) for t, v in zip(tensors, bucket.views) if t.data_ptr() != v.data_ptr()]
                 if todo:                                   # gather what was not produced in place: one launch
                     ops.scale_multi([t for t, _ in todo], bucket.ones, outs=[v for _, v in todo])
-                bucket.allreduce(self.nblocks)
+                if self._call - 1 not in self._skip:
+                    bucket.allreduce(self.nblocks)
                 out = bucket.views
                 for t, _ in todo:
                     t.record_stream(side)
