@@ -55,8 +55,11 @@ def attn_forward(mode, P, kind, L, feature, caption, bs, save):
     F, FT, mean_f = ops.attn_relayout(feature, bf16=(mode == "bf16"), want_t=(save and mode == "bf16"))
     sv.update(F=F, FT=FT, mean_f=mean_f)
     # rnn_attn.py:62: every layer starts from init_h(mean_P f) (init_c likewise for the LSTM)
-    h0 = _lin_small(mean_f, P["init_h.weight"], P["init_h.bias"])
-    c0 = _lin_small(mean_f, P["init_c.weight"], P["init_c.bias"]) if kind == _lib.ST_LSTM else None
+    # (a skinny fp32 product: it runs on the side stream beside the hoisted grid projections below)
+    (h0, c0), init_done = ops.fork(
+        lambda: (_lin_small(mean_f, P["init_h.weight"], P["init_h.bias"]),
+                 _lin_small(mean_f, P["init_c.weight"], P["init_c.bias"]) if kind == _lib.ST_LSTM else None),
+        uses=(mean_f,))
     sv.update(h0=h0, c0=c0)
     # hoisted, state-independent projections of the grid
     store = BF16 if mode == "bf16" else F32
@@ -89,10 +92,12 @@ def attn_forward(mode, P, kind, L, feature, caption, bs, save):
         sv["W"] = W
         Xe_b, _ = ops.cast_bf16(X0[:, :E], True, False)
         Gx = [ops.gemm_bf16(Xe_b, W["ihe"][0], bias=bih0, tag="ih_fwd")]              # emb half hoisted
+        ops.join(init_done)
         h0_b, _ = ops.cast_bf16(h0, True, False)
         ctx_b = torch.empty(N, E, dtype=BF16, device=dev)
     else:
         Gx = [ops.sgemm(X0[:, :E], Wih0[:, :E], transB=True, bias=bih0, tag="ih_fwd")]
+        ops.join(init_done)
     for l in range(1, L):
         Gx.append(torch.empty(N, G, dtype=F32, device=dev))
     for t in range(T):
@@ -130,6 +135,12 @@ def attn_forward(mode, P, kind, L, feature, caption, bs, save):
     return outs[L - 1]["Hs"], alphas, sv
 
 
+def _ctx_bf16(bs, Pn, F, alphas):
+    ctx, _ = ops.attn_ctx_all(bs, Pn, F, alphas, out_dtype=F32)              # row-major: coalesced stores
+    _, ctxT = ops.cast_bf16(ctx, False, True)
+    return ctx, ctxT
+
+
 def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=None, emb_out=None, recurrent_done=None):
     """Gradients of every parameter given dHs_top (N,H) and the gradient w.r.t. alphas, either a
     full (B,Tcap,P) tensor `dalphas` (drop-in forward) or the per-(b,p) penalty term `Gpen`.
@@ -155,6 +166,10 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
     dctx_all = torch.empty(N, E, dtype=F32, device=dev)
     dHs = [torch.empty(N, H, dtype=F32, device=dev) for _ in range(L - 1)] + [dHs_top]
     bouts = [None] * L
+    # embed.weight needs the feature-space contexts ctx = sum_p alpha_p F_p of every (t,b): known since the
+    # forward pass, so the pass over F runs on the side stream beside the latency-bound reverse loop
+    if mode == "bf16":
+        (ctx, ctxT), ctx_done = ops.fork(lambda: _ctx_bf16(bs, Pn, sv["F"], alphas), uses=(sv["F"], alphas))
     for t in reversed(range(T)):
         bt, o0 = bs[t], off[t]
         o1 = o0 + bt
@@ -191,7 +206,17 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
             dq = ops.sgemm(datt2_all[o0:o1], Wd)
             ops.add_rows(bouts[L - 1]["dstate"][0], dq, bt)
 
-    # ---- hoisted weight gradients
+    # ---- hoisted weight gradients.  The encoder-projection chain (one pass over att1, then the largest GEMM
+    # of the step) is independent of the recurrent ones: side stream.
+    def enc_chain():
+        datt1, datt1T, dwf = ops.attn_hoist_bwd(bs, Pn, att1, att2_all, de_all, wf, want_t=(mode == "bf16"))
+        if mode == "bf16":
+            dWe = ops.gemm_bf16(datt1T, sv["FT"], tag="att1_dw")                                # datt1^T F
+        else:
+            dWe = ops.sgemm(datt1, sv["F"], transA=True, tag="att1_dw")
+        return dWe, ops.colsum(datt1), dwf
+
+    (dWe, dbe, dwf), enc_done = ops.fork(enc_chain, uses=(att1, att2_all, de_all, wf, sv["FT"] if mode == "bf16" else sv["F"]))
     for l in range(L):
         Hprev = ops.shift_states(outs[l]["Hs"], bs, h0)
         inp = X0 if l == 0 else outs[l - 1]["Hs"]
@@ -218,21 +243,15 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
     if recurrent_done is not None:
         recurrent_done(grads)
     # attention parameters
-    datt1, datt1T, dwf = ops.attn_hoist_bwd(bs, Pn, att1, att2_all, de_all, wf, want_t=(mode == "bf16"))
-    if mode == "bf16":
-        grads["attn.encoder_att.weight"] = ops.gemm_bf16(datt1T, sv["FT"], tag="att1_dw")   # datt1^T F
-    else:
-        grads["attn.encoder_att.weight"] = ops.sgemm(datt1, sv["F"], transA=True, tag="att1_dw")
-    grads["attn.encoder_att.bias"] = ops.colsum(datt1)
+    grads["attn.encoder_att.weight"], grads["attn.encoder_att.bias"] = dWe, dbe
     grads["attn.decoder_att.weight"] = weight_grad(mode, datt2_all, Hprev_top, "att2_dw")
     grads["attn.decoder_att.bias"] = ops.colsum(datt2_all)
     grads["attn.full_att.weight"] = dwf.reshape(1, -1)
     grads["attn.full_att.bias"] = ops.colsum(de_all.reshape(-1, 1))
     # embed: ctx_e = W_embed ctx + b with ctx = sum_p alpha_p F_p rebuilt for all (t,b) in one pass
     if mode == "bf16":
-        ctx, _ = ops.attn_ctx_all(bs, Pn, sv["F"], alphas, out_dtype=F32)    # row-major: coalesced stores
-        _, ctxT = ops.cast_bf16(ctx, False, True)
         _, dcT = ops.cast_bf16(dctx_all, False, True)
+        ops.join(ctx_done)
         grads["embed.weight"] = ops.gemm_bf16(dcT, ctxT, tag="embed_dw")
     else:
         ctx, _ = ops.attn_ctx_all(bs, Pn, sv["F"], alphas)
@@ -249,6 +268,7 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
     if kind == _lib.ST_LSTM:
         grads["init_c.weight"] = ops.sgemm(dc0, sv["mean_f"], transA=True)
         grads["init_c.bias"] = ops.colsum(dc0)
+    ops.join(enc_done)
     return grads
 
 

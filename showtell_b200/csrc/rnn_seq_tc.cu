@@ -139,6 +139,12 @@ rnn_seq_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         tma_load_2d(sW + (size_t)kb * KBLK_W + g * UT * 128, &tmW, kb * 64, g * H + u0, wbar);
   }
 
+  // PDL (single-step launches of the attention loop): everything above -- barrier init, TMEM allocation, the
+  // W_hh slice (cast long before the loop) -- overlapped the previous kernel's tail; its outputs (Gx, h_{t-1})
+  // are read only from here on.  No-op under a cooperative launch.
+  pdl_wait();
+  pdl_launch_dependents();
+
   // epilogue role: warps 2..9; lane quarter q = warp % 4, unit half hf
   const bool is_epi = warp >= 2;
   const int q = warp & 3, hf = (warp - 2) >> 2;
@@ -284,7 +290,7 @@ constexpr int BSTAGES = 9;  // 144 KB of dGh in flight per SM: the phase-2 strea
 
 struct TcBwdParams {
   long long* tl;
-  int H, t_hi, t_lo, nsteps;
+  int H, t_hi, t_lo, nsteps, t_zero;
   const float *h0, *c0, *Hs, *Cs, *gates, *ghn, *dHs;
   __nv_bfloat16 *dG, *dGT, *dGh, *dGhT;  // (N, GH), (GH, ldt); dGh* == dG* for LSTM
   int ldt;
@@ -336,6 +342,9 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
     for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + (size_t)kb * KBLK_W, &tmWT, kb * 64, u0, wbar);
   }
 
+  pdl_wait();                 // see the forward kernel: the prologue overlapped the previous kernel's tail
+  pdl_launch_dependents();
+
   const bool is_epi = warp >= 2;
   const int q = warp & 3, hf = (warp - 2) >> 2;
   const bool lane_ok = (BT == 128) || lane < 16;
@@ -374,7 +383,10 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
   int stage_p = 0, stage_c = 0;   // ring positions of the producer (warp 0) / MMA issuer (warp 1)
   uint32_t phase_p = 0, phase_c = 0, aph = 0;
   bool w_ready = false, have_pf = false;
+  // arrivals this batch tile's counter already holds: the steps [t_hi, t_zero) processed by earlier launches
+  // since the counters were last zeroed (8 per unit tile per step in which the tile had live rows)
   int nbar = 0;
+  for (int tt = p.t_hi; tt < p.t_zero; ++tt) nbar += (tab.bs[tt] > r0) ? 1 : 0;
   for (int t = p.t_hi - 1; t >= p.t_lo; --t) {
     const int nr = min(BT, tab.bs[t] - r0);
     if (nr <= 0) continue;
@@ -534,6 +546,12 @@ int try_tc_fwd(const StepTable& tab, TcFwdParams p, const void* Whh_bf16, const 
   ST_TRY(make_tmap(&tmW, Whh_bf16, G * H, H, H, UT, "Whh_bf16"));
   ST_TRY(make_tmap(&tmH, p.Hsb, N, H, H, BT, "Hs_bf16"));
   ST_TRY(make_tmap(&tmH0, p.has_h0 ? h0_bf16 : (const void*)p.Hsb, p.has_h0 ? B0 : N, H, H, BT, "h0_bf16"));
+  if (p.t_end - p.t_begin == 1) {
+    // one step has no inter-CTA dependency: an ordinary launch, programmatically chained to the previous kernel
+    ST_CUDA_TRY(launch_pdl(kern, grid, dim3(NTH), smem, s, tmW, tmH, tmH0, tab, p));
+    note_launch();
+    return ST_OK;
+  }
   ST_CUDA_TRY(cudaMemsetAsync(p.barrier, 0, sizeof(int) * 64, s));
   void* args[] = {(void*)&tmW, (void*)&tmH, (void*)&tmH0, (void*)&tab, (void*)&p};
   ST_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, grid, dim3(NTH), args, smem, s));
@@ -559,14 +577,25 @@ int try_tc_bwd(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cudaS
   dim3 grid(H / UT, (tab.bs[p.t_lo] + BT - 1) / BT);
   int cores = 0;
   ST_TRY(coresident((const void*)kern, smem, &cores));
-  *launched = (int)(grid.x * grid.y) <= cores && grid.y <= 64;
+  // the tile height is chosen from the FULL batch so that every launch of a reverse pass agrees on it
+  // (the barrier counters carry over between the launches)
+  const int gy_full = (tab.bs[0] + BT - 1) / BT;
+  *launched = (int)(grid.x * gy_full) <= cores && gy_full <= 64;
   if (!*launched) return ST_OK;
   CUtensorMap tmWT, tmD;
   ST_TRY(make_tmap(&tmWT, WhhT_bf16, H, GH, GH, UT, "WhhT_bf16"));
   ST_TRY(make_tmap(&tmD, p.dGh, N, GH, GH, BT, "dGh_bf16"));
-  ST_CUDA_TRY(cudaMemsetAsync(p.barrier, 0, sizeof(int) * 64, s));
-  void* args[] = {(void*)&tmWT, (void*)&tmD, (void*)&tab, (void*)&p};
-  ST_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, grid, dim3(NTH), args, smem, s));
+  // Barrier counters are zeroed by the launch that starts a reverse pass (t_hi == nsteps); later launches
+  // of the pass continue them (TcBwdParams::t_zero), which spares a memset node per step.
+  if (p.t_hi == p.nsteps) ST_CUDA_TRY(cudaMemsetAsync(p.barrier, 0, sizeof(int) * 64, s));
+  if (p.t_hi - p.t_lo == 1) {
+    // one step: phase 1 -> barrier -> phase 2 among CTAs that all fit on the device (checked above); an
+    // ordinary launch, programmatically chained to the previous kernel, instead of a cooperative one
+    ST_CUDA_TRY(launch_pdl(kern, grid, dim3(NTH), smem, s, tmWT, tmD, tab, p));
+  } else {
+    void* args[] = {(void*)&tmWT, (void*)&tmD, (void*)&tab, (void*)&p};
+    ST_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, grid, dim3(NTH), args, smem, s));
+  }
   note_launch();
   if (p.t_lo == 0 && p.dbih != nullptr) {
     // bias gradients = row sums of the transposed gate gradients (contiguous per gate row)
@@ -642,7 +671,7 @@ int st_rnn_seq_tc_bwd(int kind, int H, int nsteps, const int* batch_sizes_host, 
   ST_REQUIRE(kind == ST_LSTM || (ghn && dGh && dGhT), ST_ERR_NULL, "st_rnn_seq_tc_bwd: GRU needs ghn, dGh, dGhT");
   ST_REQUIRE(ldt >= tab.off[nsteps] && ldt % 8 == 0, ST_ERR_BAD_SHAPE, "st_rnn_seq_tc_bwd: ldt=%d", ldt);
   if (kind == ST_LSTM) { dGh = dG; dGhT = dGT; }
-  TcBwdParams p{g_timeline, H, t_hi, t_lo, nsteps, h0, c0, Hs, Cs, gates, ghn, dHs,
+  TcBwdParams p{g_timeline, H, t_hi, t_lo, nsteps, nsteps, h0, c0, Hs, Cs, gates, ghn, dHs,
                 reinterpret_cast<__nv_bfloat16*>(dG), reinterpret_cast<__nv_bfloat16*>(dGT),
                 reinterpret_cast<__nv_bfloat16*>(dGh), reinterpret_cast<__nv_bfloat16*>(dGhT), ldt,
                 dbih, dbhh, dstate, barrier};
