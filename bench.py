@@ -194,6 +194,8 @@ def main():
     ap.add_argument("--decode-gemm", default="tf32x3", choices=["fp32", "tf32x3"],
                     help="beam workloads: nn.Linear products on CUDA cores (fp32) or fp32-accurate 3xTF32 tensor cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--optimizer", default="none", choices=["none", "sgd", "adam"],
+                    help="training workloads: also run the fused optimizer step (main.py:152) inside the timed step")
     args = ap.parse_args()
     model, B, Pn, desc = WORKLOADS[args.workload]
     is_beam = model == "beam"
@@ -232,6 +234,10 @@ def main():
     if is_beam:
         net.decode_gemm = args.decode_gemm
     params = [p for p in net.parameters()]
+    opt = None
+    if args.optimizer != "none" and not is_beam:
+        from showtell_b200 import optim
+        opt = optim.Adam(params, lr=1e-4) if args.optimizer == "adam" else optim.SGD(params, lr=1e-3, momentum=0.9)
     if world > 1 and not is_beam:
         net.grad_reducer = parallel.GradReducer()          # NCCL all-reduce on a side stream
     feat_h, cap_h, lengths = make_batch(model, B, Pn, 1 + rank)
@@ -254,6 +260,8 @@ def main():
         else:
             loss = net.forward_loss(f, c, lengths, global_tokens=units_per_step)
         loss.backward()
+        if opt is not None:
+            opt.step()                                                            # main.py:152
         return loss
 
     def step_e2e():
@@ -353,7 +361,8 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": desc, "global_batch": B * world, "seq_len": T, "parallelism": f"dp{world}",
                            "l2": "flushed between timed steps (256 MiB fill, outside the event pairs)",
-                           "launch": "whole step replayed as one CUDA graph (captured on the 3rd identical step)"},
+                           "launch": "whole step replayed as one CUDA graph (captured on the 3rd identical step)",
+                           "optimizer": "excluded" if opt is None else args.optimizer + " step (fused, one launch) included"},
                 "e2e": {"value": units_per_step / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": out_host.numel() * out_host.element_size(), "ms_per_step": ms_e2e},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}

@@ -147,6 +147,31 @@ int st_colsum(float* out, const void* M, int m_is_bf16, int rows, int cols, int 
 int st_scale_multi(int n, const float* const* src, float* const* dst, const int64_t* count, const float* g,
                    st_stream_t stream);
 
+/* Encoder head of the base models, cnn.py:37-38,49: nn.BatchNorm1d(E, momentum) over the rows of Y (B, E) =
+ * Linear(2048, E)(pooled features) (the Linear product itself is st_sgemm / st_gemm_bf16).
+ * Forward, training (use_running_stats = 0): batch statistics (biased variance), running_mean / running_var
+ * (may be NULL) updated with `momentum` (unbiased variance), save_mean / save_invstd (E) kept for the backward.
+ * Forward, eval: normalises with the running statistics.  Backward (training statistics): dgamma, dbeta (E) and dY. */
+int st_bn1d_fwd(const float* Y, int ldy, int B, int E, const float* gamma, const float* beta, float eps, float momentum,
+                int use_running_stats, float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                float* out, int ldo, st_stream_t stream);
+int st_bn1d_bwd(const float* Y, int ldy, const float* dOut, int ldd, int B, int E, const float* gamma,
+                const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float* dY, int ldg,
+                st_stream_t stream);
+
+/* Optimizer step over n <= ST_OPT_MAX fp32 tensors in one launch (main.py:97-100,152, main_attn.py:91-94,134:
+ * torch.optim.SGD(lr, momentum) / torch.optim.Adam(lr)); arithmetic as torch's reference implementations.
+ * param / grad / state are host arrays of device pointers, count[i] elements each.  momentum_buf may be NULL when
+ * momentum == 0; first_step != 0 initialises the momentum buffers with the gradient (torch's first step).
+ * `step` is Adam's 1-based step count.  grad_scale: optional device scalar multiplied into every gradient (the
+ * grad_output of forward_loss's autograd node), NULL = 1. */
+#define ST_OPT_MAX 32
+int st_sgd_step(int n, float* const* param, const float* const* grad, float* const* momentum_buf, const int64_t* count,
+                float lr, float momentum, int first_step, const float* grad_scale, st_stream_t stream);
+int st_adam_step(int n, float* const* param, const float* const* grad, float* const* exp_avg, float* const* exp_avg_sq,
+                 const int64_t* count, float lr, float beta1, float beta2, float eps, int64_t step,
+                 const float* grad_scale, st_stream_t stream);
+
 /* out[r] = sum_c M[r, c], M bf16 (rows, ld): db_v from the transposed dlogits. */
 int st_rowsum_bf16(float* out, const void* M, int rows, int cols, int ld, st_stream_t stream);
 

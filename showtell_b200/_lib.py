@@ -44,6 +44,10 @@ _SIGS = {
     "st_gemm_tf32x3": (_I, [_I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _F, _F, _P]),
     "st_debug_set_pdl": (_I, [_I]),
     "st_scale_multi": (_I, [_I, _P, _P, _P, _P, _P]),
+    "st_bn1d_fwd": (_I, [_P, _I, _I, _I, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _I, _P]),
+    "st_bn1d_bwd": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "st_sgd_step": (_I, [_I, _P, _P, _P, _P, _F, _F, _I, _P, _P]),
+    "st_adam_step": (_I, [_I, _P, _P, _P, _P, _P, _F, _F, _F, _F, _L, _P, _P]),
     "st_allreduce_flag_words": (_I, [_I]),
     "st_allreduce_sum_f32": (_I, [C.POINTER(C.c_void_p), _P, C.POINTER(C.c_void_p), _I, _I, _L, _I, _P]),
     "st_vocab_ce_fwd": (_I, [_I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
