@@ -147,6 +147,19 @@ int st_colsum(float* out, const void* M, int m_is_bf16, int rows, int cols, int 
 int st_scale_multi(int n, const float* const* src, float* const* dst, const int64_t* count, const float* g,
                    st_stream_t stream);
 
+/* One recurrent step of the attention decoders with the context half of the input projection folded in
+ * (rnn_attn.py:70 / rnn_attn_LSTM.py:72: unit([emb_t | embed(ctx_t)], h_{t-1}), step t of the packed sequence):
+ *   gates = Gx[rows of t] + [h_{t-1} | X[rows of t]] . [Whh | Wx]^T + bhh   on tcgen05, one kernel per step.
+ * Gx (N, G*H) fp32 = hoisted W_ih[:, :E] emb + b_ih; X (N, EX) bf16 = embed(ctx) rows (packed, ld = ldx);
+ * Whh (G*H, H) / Wx (G*H, EX) bf16 K-major; h_{t-1} = h0 (t = 0: fp32 h0 + bf16 h0_bf16, (B0, H)) or rows of
+ * step t-1 of Hs / Hs_bf16.  Writes rows of step t of Hs, Hs_bf16, Cs (LSTM), gates / ghn (may be NULL).
+ * Replaces {st_gemm_bf16(beta = 1) into Gx; st_rnn_seq_tc_fwd over [t, t+1)}. */
+int st_rnn_step_x_tc_supported(int kind, int H, int EX);
+int st_rnn_step_x_tc_fwd(int kind, int H, int EX, int nsteps, const int* batch_sizes_host, int t, const float* Gx,
+                         const void* X_bf16, int ldx, const void* Whh_bf16, const void* Wx_bf16, int ldwx,
+                         const float* bhh, const float* h0, const void* h0_bf16, const float* c0, float* Hs,
+                         void* Hs_bf16, float* Cs, float* gates, float* ghn, st_stream_t stream);
+
 /* Encoder head of the base models, cnn.py:37-38,49: nn.BatchNorm1d(E, momentum) over the rows of Y (B, E) =
  * Linear(2048, E)(pooled features) (the Linear product itself is st_sgemm / st_gemm_bf16).
  * Forward, training (use_running_stats = 0): batch statistics (biased variance), running_mean / running_var
@@ -169,7 +182,7 @@ int st_bn1d_bwd(const float* Y, int ldy, const float* dOut, int ldd, int B, int 
 int st_sgd_step(int n, float* const* param, const float* const* grad, float* const* momentum_buf, const int64_t* count,
                 float lr, float momentum, int first_step, const float* grad_scale, st_stream_t stream);
 int st_adam_step(int n, float* const* param, const float* const* grad, float* const* exp_avg, float* const* exp_avg_sq,
-                 const int64_t* count, float lr, float beta1, float beta2, float eps, int64_t step,
+                 const int64_t* count, float lr, double beta1, double beta2, float eps, int64_t step,
                  const float* grad_scale, st_stream_t stream);
 
 /* out[r] = sum_c M[r, c], M bf16 (rows, ld): db_v from the transposed dlogits. */

@@ -112,12 +112,21 @@ def attn_forward(mode, P, kind, L, feature, caption, bs, save):
             _lin_small(q, P["attn.decoder_att.weight"], bd, out=att2_all[o0:o1])
         ops.attn_step_fwd(bt, Pn, att1, Fe, att2_all[o0:o1], wf, P["attn.full_att.bias"], P["embed.bias"],
                           alphas[:, t, :], Tcap * Pn, S, X0[o0:o1, E:], ctx_bf16=ctx_b[o0:o1] if tc else None)
-        # + W_ih[:, E:] embed(ctx)
+        # + W_ih[:, E:] embed(ctx): on the tensor-core path it is accumulated inside the layer-0 step kernel
+        # (K-concatenated operand [h | embed(ctx)]); otherwise a small product into the hoisted pre-activations
+        fused0 = None
         if tc:
-            ops.gemm_bf16(ctx_b[o0:o1], W["ihc"][0], out=Gx[0][o0:o1], beta=1.0, tag="ihc_fwd")
+            fused0 = ops.rnn_step_x_tc_fwd(kind, Gx[0], ctx_b, W["hh0"][0], W["ihc"][0], layer_params(P, 0)[3], bs, t,
+                                           h0=h0, h0_b=h0_b, c0=c0, save=save, out=outs[0], tag="step_fwd")
+            if fused0 is None:
+                ops.gemm_bf16(ctx_b[o0:o1], W["ihc"][0], out=Gx[0][o0:o1], beta=1.0, tag="ihc_fwd")
+            else:
+                outs[0] = fused0
         else:
             _lin_small(X0[o0:o1, E:], Wih0[:, E:], out=Gx[0][o0:o1], beta=1.0)
         for l in range(L):
+            if l == 0 and fused0 is not None:
+                continue
             Wih, Whh, bih, bhh = layer_params(P, l)
             if tc:
                 if l > 0:

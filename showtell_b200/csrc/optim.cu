@@ -26,15 +26,15 @@ struct OptTable {
   int first[ST_OPT_MAX + 1];
 };
 struct OptHyper {
-  float lr, momentum, b1, b2, eps, bc1, sqrt_bc2;   // bc1 = 1 - b1^t, sqrt_bc2 = sqrt(1 - b2^t)
+  float lr, momentum, b1, b2, omb1, omb2, eps, bc1, sqrt_bc2;   // omb = 1 - beta (rounded from double, as torch passes it); bc1 = 1 - b1^t, sqrt_bc2 = sqrt(1 - b2^t)
   int first_step;
 };
 
 template <bool ADAM>
 __device__ __forceinline__ void update(float& p, float g, float& m, float& v, const OptHyper& h) {
   if (ADAM) {
-    m = fmaf(g - m, 1.f - h.b1, m);                       // exp_avg.lerp_(grad, 1 - beta1)
-    v = fmaf(h.b2, v, (1.f - h.b2) * g * g);              // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    m = fmaf(g - m, h.omb1, m);                           // exp_avg.lerp_(grad, 1 - beta1)
+    v = fmaf(h.omb2 * g, g, h.b2 * v);                    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
     const float denom = sqrtf(v) / h.sqrt_bc2 + h.eps;
     p -= (h.lr / h.bc1) * (m / denom);
   } else {
@@ -122,7 +122,7 @@ int st_sgd_step(int n, float* const* param, const float* const* grad, float* con
   long long chunks = 0;
   ST_TRY(build_table(tab, n, param, grad, momentum_buf, nullptr, count, momentum != 0.f, false, &chunks));
   if (chunks == 0) return ST_OK;
-  OptHyper h{lr, momentum, 0.f, 0.f, 0.f, 1.f, 1.f, first_step};
+  OptHyper h{lr, momentum, 0.f, 0.f, 1.f, 1.f, 0.f, 1.f, 1.f, first_step};
   int sms = 0;
   ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
   const long long grid = chunks < 8LL * sms ? chunks : 8LL * sms;
@@ -132,9 +132,10 @@ int st_sgd_step(int n, float* const* param, const float* const* grad, float* con
 }
 
 int st_adam_step(int n, float* const* param, const float* const* grad, float* const* exp_avg, float* const* exp_avg_sq,
-                 const int64_t* count, float lr, float beta1, float beta2, float eps, int64_t step,
+                 const int64_t* count, float lr, double beta1_d, double beta2_d, float eps, int64_t step,
                  const float* grad_scale, st_stream_t stream) {
   using namespace st;
+  const float beta1 = (float)beta1_d, beta2 = (float)beta2_d;   // betas come as doubles: 1 - beta is rounded once, as torch does
   ST_REQUIRE(step >= 1, ST_ERR_BAD_SHAPE, "st_adam_step: step=%lld must be >= 1", (long long)step);
   ST_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, ST_ERR_BAD_SHAPE,
              "st_adam_step: betas (%g, %g) eps %g", beta1, beta2, eps);
@@ -142,8 +143,8 @@ int st_adam_step(int n, float* const* param, const float* const* grad, float* co
   long long chunks = 0;
   ST_TRY(build_table(tab, n, param, grad, exp_avg, exp_avg_sq, count, true, true, &chunks));
   if (chunks == 0) return ST_OK;
-  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-  OptHyper h{lr, 0.f, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), 0};
+  const double bc1 = 1.0 - pow(beta1_d, (double)step), bc2 = 1.0 - pow(beta2_d, (double)step);
+  OptHyper h{lr, 0.f, beta1, beta2, (float)(1.0 - beta1_d), (float)(1.0 - beta2_d), eps, (float)bc1, (float)sqrt(bc2), 0};
   int sms = 0;
   ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
   const long long grid = chunks < 8LL * sms ? chunks : 8LL * sms;

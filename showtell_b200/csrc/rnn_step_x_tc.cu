@@ -1,0 +1,313 @@
+// One recurrent step of the attention decoders on the tensor cores with the context half of the input
+// projection folded in (rnn_attn.py:70, rnn_attn_LSTM.py:72: unit([emb_t | embed(ctx_t)], h_{t-1})).
+//
+// The attention loop feeds the recurrence an input whose second half, embed(ctx_t), only exists after the
+// attention of the same step, so its projection W_ih[:, E:] . embed(ctx_t) cannot be hoisted; as a separate
+// small GEMM it costs a dependent kernel per step (~11 us of launch / fill / drain for 0.2 GFLOP).  Here it is
+// the same accumulation as the recurrent product: the CTA's gate rows see the K-concatenated operand
+//     [ h_{t-1} | embed(ctx_t) ]  .  [ W_hh | W_ih[:, E:] ]^T
+// with both weight slices resident in shared memory and both activation tiles streamed through one TMA ring.
+// LSTM: all four gates accumulate over the whole concatenated K.  GRU keeps W_hn h apart from the input side
+// (n = tanh(gi_n + r * (W_hn h + b_hn))): accumulator columns [r | z | gh_n | gi_n(ctx)], the ctx k-blocks go to
+// r, z (N = 32) and to the fourth group (N = 16) with two MMAs per k-step.
+//
+// CTA = 16 hidden units x BT batch rows (as rnn_seq_tc.cu); warp 0 = TMA producer, warp 1 = TMEM + MMA issue,
+// warps 2..9 = epilogue (gate math, state update, stores).  One step has no inter-CTA dependency: an ordinary
+// launch chained to the previous kernel with programmatic dependent launch; the prologue (barriers, TMEM,
+// the two weight slices, which were cast long before the loop) overlaps that kernel's tail.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace st {
+namespace {
+
+constexpr int UT = 16, HALF = 8, NTH = 320, MAXKB = 8, MAXST = 16;
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8bf(__nv_bfloat16* p, const float (&v)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+    w[q] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+struct StepXParams {
+  int H, EX, t, nstages;
+  const float *Gx, *bhh, *h0, *c0;      // Gx (N, G*H): hoisted W_ih[:, :E] emb + b_ih
+  float *Hs, *Cs, *gates, *ghn;
+  __nv_bfloat16* Hsb;
+};
+
+template <int G, int BT>
+__global__ void __launch_bounds__(NTH, 1)
+rnn_step_x_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWx,
+                     const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmX,
+                     const __grid_constant__ StepTable tab, const StepXParams p) {
+  constexpr int NG = G * UT;                     // gate rows of one weight slice k-block (48 / 64)
+  constexpr uint32_t KBLK_W = NG * 128;          // bytes of one k-block of a weight slice
+  constexpr uint32_t KBLK_A = BT * 128;          // bytes of one 64-wide k-block of an activation tile
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int H = p.H, KBH = (H + 63) / 64, KBX = (p.EX + 63) / 64, KT = KBH + KBX, NST = p.nstages;
+  uint8_t* sW = smem;                            // [KT][NG rows][128 B]: W_hh slice k-blocks, then W_x slice k-blocks
+  uint8_t* sA = smem + (size_t)KT * KBLK_W;      // [NST][BT rows][128 B] ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)NST * KBLK_A);
+  uint64_t* wbar = bars;
+  uint64_t* accbar = bars + 1;
+  uint64_t* full = bars + 2;                     // [MAXST]
+  uint64_t* empty = full + MAXST;                // [MAXST]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty + MAXST);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u0 = blockIdx.x * UT, r0 = blockIdx.y * BT;
+  const int t = p.t;
+  const int nr = min(BT, tab.bs[t] - r0);        // > 0: the grid covers live rows only
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(wbar, 1);
+    mbar_init(accbar, 1);
+    for (int i = 0; i < MAXST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(64u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0 && lane == 0) {  // resident weight slices: G boxes of 16 rows per k-block (constant during the loop)
+    mbar_expect_tx(wbar, (uint32_t)KT * KBLK_W);
+    for (int kb = 0; kb < KBH; ++kb)
+      for (int g = 0; g < G; ++g) tma_load_2d(sW + (size_t)kb * KBLK_W + g * UT * 128, &tmWh, kb * 64, g * H + u0, wbar);
+    for (int kb = 0; kb < KBX; ++kb)
+      for (int g = 0; g < G; ++g)
+        tma_load_2d(sW + (size_t)(KBH + kb) * KBLK_W + g * UT * 128, &tmWx, kb * 64, g * H + u0, wbar);
+  }
+  // everything above overlapped the previous kernel's tail; its outputs (ctx, h_{t-1}) are read from here on
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {            // ---- TMA producer: h_{t-1} k-blocks, then embed(ctx_t) k-blocks
+    const int hbase = (t == 0) ? r0 : tab.off[t - 1] + r0;     // tmH maps h0 (t == 0) or the packed bf16 states
+    const int xbase = tab.off[t] + r0;
+    for (int k = 0; k < KT; ++k) {
+      const int stage = k % NST;
+      if (k >= NST) mbar_wait(&empty[stage], ((k / NST) - 1) & 1);
+      if (elect_one()) {
+        mbar_expect_tx(&full[stage], KBLK_A);
+        if (k < KBH) tma_load_2d(sA + (size_t)stage * KBLK_A, &tmH, k * 64, hbase, &full[stage]);
+        else tma_load_2d(sA + (size_t)stage * KBLK_A, &tmX, (k - KBH) * 64, xbase, &full[stage]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {     // ---- MMA issue (whole warp, uniform control flow; one elected lane issues)
+    mbar_wait(wbar, 0);
+    const uint64_t adesc0 = umma_desc_k128(smem_u32(sA)), bdesc0 = umma_desc_k128(smem_u32(sW));
+    for (int k = 0; k < KT; ++k) {
+      const int stage = k % NST;
+      mbar_wait(&full[stage], (k / NST) & 1);
+      tc_fence_after();
+      const uint64_t ad = adesc0 + (uint64_t)(stage * (KBLK_A >> 4)), bd = bdesc0 + (uint64_t)(k * (KBLK_W >> 4));
+      if (elect_one()) {
+        if (G == 4 || k < KBH) {
+          // LSTM: every k-block feeds all four gates.  GRU, h k-blocks: [r | z | gh_n] = columns 0..47
+          constexpr uint32_t idesc = umma_idesc(BT, NG);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) tc_mma(tmem_base, ad + 2 * kk, bd + 2 * kk, idesc, (k | kk) != 0);
+        } else {
+          // GRU, ctx k-blocks: r, z rows (N = 32) accumulate into columns 0..31; the n rows (N = 16, 32 rows = 4096 B
+          // into the k-block) start / continue gi_n(ctx) in columns 48..63
+          constexpr uint32_t idesc_rz = umma_idesc(BT, 2 * UT), idesc_n = umma_idesc(BT, UT);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            tc_mma(tmem_base, ad + 2 * kk, bd + 2 * kk, idesc_rz, 1u);
+            tc_mma(tmem_base + 3 * UT, ad + 2 * kk, bd + (uint64_t)((2 * UT * 128) >> 4) + 2 * kk, idesc_n,
+                   (uint32_t)(((k - KBH) | kk) != 0));
+          }
+        }
+        tc_commit(&empty[stage]);
+      }
+      __syncwarp();
+    }
+    if (elect_one()) tc_commit(accbar);
+    __syncwarp();
+  } else {                    // ---- epilogue: warps 2..9; lane quarter q = warp % 4, unit half hf
+    const int q = warp & 3, hf = (warp - 2) >> 2;
+    const bool lane_ok = (BT == 128) || lane < 16;
+    const int row = (BT == 128) ? q * 32 + lane : q * 16 + lane;   // row of the batch tile held by this TMEM lane
+    const int uu = u0 + hf * HALF;
+    const bool r_ok = lane_ok && row < nr;
+    const size_t n = (size_t)tab.off[t] + r0 + row;
+    float hreg[HALF], creg[HALF], bh[G][HALF], gx[G][HALF];
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) { hreg[j] = 0.f; creg[j] = 0.f; }
+#pragma unroll
+    for (int g = 0; g < G; ++g) ld8(p.bhh + g * H + uu, bh[g]);
+    if (r_ok) {
+      if (t == 0) {
+        if (G == 3) ld8(p.h0 + (size_t)(r0 + row) * H + uu, hreg);
+        if (G == 4 && p.c0) ld8(p.c0 + (size_t)(r0 + row) * H + uu, creg);
+      } else {
+        const size_t np = (size_t)tab.off[t - 1] + r0 + row;
+        if (G == 3) ld8(p.Hs + np * H + uu, hreg);
+        if (G == 4) ld8(p.Cs + np * H + uu, creg);
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) ld8(p.Gx + n * (size_t)(G * H) + g * H + uu, gx[g]);
+    }
+    mbar_wait(accbar, 0);
+    tc_fence_after();
+    float acc[4][HALF];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + g * UT + hf * HALF, acc[g]);
+    tc_fence_before();
+    if (r_ok) {
+      float go[G][HALF], ghn[HALF];
+#pragma unroll
+      for (int j = 0; j < HALF; ++j) {
+        if (G == 4) {
+          const float ig = sigmoid_fast(gx[0][j] + acc[0][j] + bh[0][j]);
+          const float fg = sigmoid_fast(gx[1][j] + acc[1][j] + bh[1][j]);
+          const float gg = tanh_fast(gx[2][j] + acc[2][j] + bh[2][j]);
+          const float og = sigmoid_fast(gx[G - 1][j] + acc[3][j] + bh[G - 1][j]);
+          creg[j] = fmaf(fg, creg[j], ig * gg);
+          hreg[j] = og * tanh_fast(creg[j]);
+          go[0][j] = ig; go[1][j] = fg; go[2][j] = gg; go[G - 1][j] = og;
+        } else {
+          ghn[j] = acc[2][j] + bh[2][j];
+          const float rr = sigmoid_fast(gx[0][j] + acc[0][j] + bh[0][j]);
+          const float zz = sigmoid_fast(gx[1][j] + acc[1][j] + bh[1][j]);
+          const float nn = tanh_fast(fmaf(rr, ghn[j], gx[2][j] + acc[3][j]));
+          hreg[j] = fmaf(zz, hreg[j] - nn, nn);
+          go[0][j] = rr; go[1][j] = zz; go[2][j] = nn;
+        }
+      }
+      st8bf(p.Hsb + n * H + uu, hreg);
+      st8(p.Hs + n * H + uu, hreg);
+      if (G == 4) st8(p.Cs + n * H + uu, creg);
+      if (p.gates) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) st8(p.gates + n * (size_t)(G * H) + g * H + uu, go[g]);
+        if (G == 3) st8(p.ghn + n * H + uu, ghn);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
+  }
+}
+
+template <int G, int BT>
+int try_step_x(const StepTable& tab, StepXParams p, const void* Whh, const void* Wx, int ldwx, const void* hprev,
+               int hprev_rows, const void* X, int ldx, int x_rows, cudaStream_t s, bool* launched) {
+  const int H = p.H, KBH = (H + 63) / 64, KBX = (p.EX + 63) / 64, KT = KBH + KBX;
+  int dev = 0, optin = 0, sms = 0;
+  ST_CUDA_TRY(cudaGetDevice(&dev));
+  ST_CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  ST_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t fixed = 1024 + (size_t)KT * (G * UT * 128) + (2 + 2 * MAXST) * 8 + 64;
+  *launched = false;
+  if ((size_t)optin <= fixed) return ST_OK;
+  int nst = (int)(((size_t)optin - fixed) / (BT * 128));
+  nst = nst > KT ? KT : nst;
+  nst = nst > MAXST ? MAXST : nst;
+  if (nst < 2) return ST_OK;
+  dim3 grid(H / UT, (tab.bs[p.t] + BT - 1) / BT);
+  if (BT == 64 && (int)(grid.x * grid.y) > sms) return ST_OK;   // 64-row tiles only while every CTA gets its own SM
+  p.nstages = nst;
+  const size_t smem = fixed + (size_t)nst * (BT * 128);
+  auto kern = rnn_step_x_tc_kernel<G, BT>;
+  ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUtensorMap tmWh, tmWx, tmH, tmX;
+  ST_TRY(make_tmap(&tmWh, Whh, G * H, H, H, UT, "Whh_bf16"));
+  ST_TRY(make_tmap(&tmWx, Wx, G * H, p.EX, ldwx, UT, "Wx_bf16"));
+  ST_TRY(make_tmap(&tmH, hprev, hprev_rows, H, H, BT, "hprev_bf16"));
+  ST_TRY(make_tmap(&tmX, X, x_rows, p.EX, ldx, BT, "x_bf16"));
+  ST_CUDA_TRY(launch_pdl(kern, grid, dim3(NTH), smem, s, tmWh, tmWx, tmH, tmX, tab, p));
+  note_launch();
+  *launched = true;
+  return ST_OK;
+}
+
+template <int G>
+int launch_step_x(const StepTable& tab, StepXParams p, const void* Whh, const void* Wx, int ldwx, const void* hprev,
+                  int hprev_rows, const void* X, int ldx, int x_rows, cudaStream_t s) {
+  bool ok = false;
+  ST_TRY((try_step_x<G, 64>(tab, p, Whh, Wx, ldwx, hprev, hprev_rows, X, ldx, x_rows, s, &ok)));
+  if (!ok) ST_TRY((try_step_x<G, 128>(tab, p, Whh, Wx, ldwx, hprev, hprev_rows, X, ldx, x_rows, s, &ok)));
+  ST_REQUIRE(ok, ST_ERR_UNSUPPORTED, "rnn_step_x_tc_fwd: H=%d EX=%d does not fit shared memory", p.H, p.EX);
+  return ST_OK;
+}
+
+}  // namespace
+}  // namespace st
+
+extern "C" {
+
+int st_rnn_step_x_tc_supported(int kind, int H, int EX) {
+  (void)kind;
+  return (H % 16 == 0 && H >= 16 && H <= 64 * st::MAXKB && EX % 8 == 0 && EX >= 8 && EX <= 64 * st::MAXKB) ? 1 : 0;
+}
+
+int st_rnn_step_x_tc_fwd(int kind, int H, int EX, int nsteps, const int* batch_sizes_host, int t, const float* Gx,
+                         const void* X_bf16, int ldx, const void* Whh_bf16, const void* Wx_bf16, int ldwx,
+                         const float* bhh, const float* h0, const void* h0_bf16, const float* c0, float* Hs,
+                         void* Hs_bf16, float* Cs, float* gates, float* ghn, st_stream_t stream) {
+  using namespace st;
+  StepTable tab;
+  ST_TRY(make_step_table(tab, nsteps, batch_sizes_host));
+  ST_REQUIRE(kind == ST_GRU || kind == ST_LSTM, ST_ERR_UNSUPPORTED, "st_rnn_step_x_tc_fwd: kind=%d", kind);
+  ST_REQUIRE(st_rnn_step_x_tc_supported(kind, H, EX), ST_ERR_UNSUPPORTED,
+             "st_rnn_step_x_tc_fwd: H=%d (multiple of 16) / EX=%d (multiple of 8) must be <= %d", H, EX, 64 * MAXKB);
+  ST_REQUIRE(Gx && X_bf16 && Whh_bf16 && Wx_bf16 && bhh && h0 && h0_bf16 && Hs && Hs_bf16, ST_ERR_NULL,
+             "st_rnn_step_x_tc_fwd: NULL pointer");
+  ST_REQUIRE(kind == ST_GRU || Cs, ST_ERR_NULL, "st_rnn_step_x_tc_fwd: LSTM needs Cs");
+  ST_REQUIRE(kind == ST_LSTM || !gates || ghn, ST_ERR_NULL, "st_rnn_step_x_tc_fwd: GRU gates need ghn");
+  ST_REQUIRE(0 <= t && t < nsteps, ST_ERR_BAD_SHAPE, "st_rnn_step_x_tc_fwd: step %d outside [0,%d)", t, nsteps);
+  ST_REQUIRE(ldx >= EX && ldx % 8 == 0 && ldwx >= EX && ldwx % 8 == 0, ST_ERR_BAD_SHAPE,
+             "st_rnn_step_x_tc_fwd: ldx=%d ldwx=%d must be multiples of 8 and >= EX=%d", ldx, ldwx, EX);
+  const int N = tab.off[nsteps], B0 = tab.bs[0];
+  StepXParams p{H, EX, t, 0, Gx, bhh, h0, c0, Hs, Cs, gates, ghn, reinterpret_cast<__nv_bfloat16*>(Hs_bf16)};
+  const void* hprev = (t == 0) ? h0_bf16 : Hs_bf16;
+  const int hrows = (t == 0) ? B0 : N;
+  return kind == ST_LSTM
+             ? launch_step_x<4>(tab, p, Whh_bf16, Wx_bf16, ldwx, hprev, hrows, X_bf16, ldx, N, as_stream(stream))
+             : launch_step_x<3>(tab, p, Whh_bf16, Wx_bf16, ldwx, hprev, hrows, X_bf16, ldx, N, as_stream(stream));
+}
+
+}  // extern "C"

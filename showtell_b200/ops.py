@@ -454,6 +454,37 @@ def rnn_seq_tc_fwd(kind, Gx, Whh_b, bhh, bs, *, h0=None, h0_b=None, c0=None, sav
     return o
 
 
+STEP_X = True     # attention loop: fold the context half of W_ih into the recurrent step kernel (rnn_step_x_tc.cu)
+
+
+def rnn_step_x_tc_fwd(kind, Gx, X_b, Whh_b, Wx_b, bhh, bs, t, *, h0, h0_b, c0=None, save=True, out=None, tag=None):
+    """Step t of the attention decoders' recurrence with the projection of X_b (N, EX) bf16 -- embed(ctx) rows --
+    accumulated in the same kernel as W_hh h_{t-1}.  Same result dict as rnn_seq_tc_fwd; None when unsupported."""
+    lib = _lib.load()
+    N, H, EX = sum(bs), Whh_b.shape[1], Wx_b.shape[1]
+    if not STEP_X or not lib.st_rnn_step_x_tc_supported(kind, H, EX):
+        return None
+    dev = Gx.device
+    o = out
+    if o is None:
+        o = {"Hs": torch.empty(N, H, dtype=F32, device=dev), "Hsb": torch.empty(N, H, dtype=BF16, device=dev),
+             "Cs": torch.empty(N, H, dtype=F32, device=dev) if kind == _lib.ST_LSTM else None,
+             "gates": torch.empty(N, Whh_b.shape[0], dtype=F32, device=dev) if save else None,
+             "ghn": torch.empty(N, H, dtype=F32, device=dev) if (save and kind == _lib.ST_GRU) else None,
+             "barrier": _barrier(dev)}
+    tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
+    st = lib.st_rnn_step_x_tc_fwd(kind, H, EX, len(bs), int_array(bs), t, ptr(Gx, F32), _raw(X_b), X_b.stride(0),
+                                  _raw(Whh_b), _raw(Wx_b), Wx_b.stride(0), ptr(bhh, F32), ptr(h0, F32), _raw(h0_b),
+                                  ptr(c0, F32), ptr(o["Hs"]), ptr(o["Hsb"]), ptr(o["Cs"]), ptr(o["gates"]), ptr(o["ghn"]),
+                                  stream_ptr())
+    if st == -3:
+        return None
+    check(st, "st_rnn_step_x_tc_fwd")
+    if tok:
+        TIMER.end(tok)
+    return o
+
+
 def rnn_seq_tc_bwd(kind, WhhT_b, bs, saved, dHs, *, h0=None, c0=None, t_range=None, out=None, want_bias=True,
                    tag=None):
     """Returns dict(dGb, dGT, dGhb, dGhT, dbih, dbhh, dstate) (bf16 GEMM operands) or None if unsupported."""

@@ -64,12 +64,15 @@ class SGD(torch.optim.Optimizer):
                 if p.grad is None:
                     continue
                 g = _check(p)
+                if mom == 0.0:                                  # torch keeps no state without momentum
+                    warm.append((p, g, None))
+                    continue
                 st = self.state[p]
-                if mom != 0.0 and st.get("momentum_buffer") is None:
+                if st.get("momentum_buffer") is None:
                     st["momentum_buffer"] = torch.empty_like(p, memory_format=torch.contiguous_format)
                     fresh.append((p, g, st["momentum_buffer"]))
                 else:
-                    warm.append((p, g, st.get("momentum_buffer")))
+                    warm.append((p, g, st["momentum_buffer"]))
             for items, first in ((fresh, 1), (warm, 0)):
                 for i in range(0, len(items), _MAX):
                     part = items[i:i + _MAX]

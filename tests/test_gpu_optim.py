@@ -41,6 +41,9 @@ def test_matches_torch_optim(kind, kw):
         for p, q in zip(ps, qs):
             assert _err(p.detach(), q.detach()) < 2e-6, (kind, it, tuple(p.shape))
     so, sr = ours.state_dict(), ref.state_dict()
+    assert set(so["state"]) == set(sr["state"])
+    if not sr["state"]:
+        return                                                # SGD without momentum keeps no state
     assert set(so["state"][0]) == set(sr["state"][0])
     for k in sr["state"][0]:
         assert _err(torch.as_tensor(so["state"][0][k]).float().cpu(), torch.as_tensor(sr["state"][0][k]).float().cpu()) < 2e-6, k

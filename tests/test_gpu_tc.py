@@ -233,3 +233,46 @@ def test_rnn_cluster_resident_forward(kind, H, lengths, init, monkeypatch):
         part = ops.rnn_seq_tc_fwd(k, Gx, Wb, bhh, bs, h0=h0, h0_b=h0b, c0=c0, t_range=(0, 3))
         part = ops.rnn_seq_tc_fwd(k, Gx, Wb, bhh, bs, h0=h0, h0_b=h0b, c0=c0, t_range=(3, T), out=part)
         assert torch.equal(part["Hs"], out["Hs"]) and torch.equal(part["gates"], out["gates"])
+
+
+@pytest.mark.parametrize("kind", ["gru", "lstm"])
+@pytest.mark.parametrize("H,EX,lengths", [
+    (128, 64, [7, 7, 6, 4, 4, 2]),                                 # one 64-row tile, ragged
+    (512, 512, [6] * 100 + [4] * 28),                              # config-3 shape: 2 x 64-row tiles, ring reused
+    (512, 512, [3] * 300 + [2] * 212),                             # config-4 shape: 4 x 128-row tiles
+    (96, 40, [5, 3, 3, 1]),                                        # k tails (H, EX not multiples of 64)
+])
+def test_rnn_step_with_folded_context_projection(kind, H, EX, lengths):
+    """rnn_attn.py:70: the step kernel that accumulates W_ih[:, E:] embed(ctx) together with W_hh h (one
+    K-concatenated tensor-core product) against {small GEMM into the pre-activations; single-step kernel}."""
+    from showtell_b200 import _lib, ops
+    k = _lib.ST_LSTM if kind == "lstm" else _lib.ST_GRU
+    G = 4 if kind == "lstm" else 3
+    bs = _lib.batch_sizes(lengths)
+    N, B0 = sum(bs), bs[0]
+    g = torch.Generator().manual_seed(9)
+    Gx = torch.randn(N, G * H, generator=g).to(DEV)
+    Whh = (torch.randn(G * H, H, generator=g) * 0.08).to(DEV)
+    Wx = (torch.randn(G * H, EX, generator=g) * 0.08).to(DEV)
+    bhh = (torch.randn(G * H, generator=g) * 0.1).to(DEV)
+    h0 = (torch.randn(B0, H, generator=g) * 0.5).to(DEV)
+    c0 = (torch.randn(B0, H, generator=g) * 0.5).to(DEV) if kind == "lstm" else None
+    X = torch.randn(N, EX, generator=g).to(DEV)
+    Wb, _ = ops.cast_bf16(Whh, True, False)
+    Wxb, _ = ops.cast_bf16(Wx, True, False)
+    Xb, _ = ops.cast_bf16(X, True, False)
+    h0b, _ = ops.cast_bf16(h0, True, False)
+    ref, fused, Gref = None, None, Gx.clone()
+    off = 0
+    for t, bt in enumerate(bs):
+        ops.gemm_bf16(Xb[off:off + bt], Wxb, out=Gref[off:off + bt], beta=1.0)
+        ref = ops.rnn_seq_tc_fwd(k, Gref, Wb, bhh, bs, h0=h0, h0_b=h0b, c0=c0, t_range=(t, t + 1), out=ref)
+        fused = ops.rnn_step_x_tc_fwd(k, Gx, Xb, Wb, Wxb, bhh, bs, t, h0=h0, h0_b=h0b, c0=c0, out=fused)
+        assert ref is not None and fused is not None
+        off += bt
+    torch.cuda.synchronize()
+    # same bf16 operands, fp32 accumulation in a different order: agreement far inside the bf16-mode bar
+    for key in ("Hs", "gates") + (("Cs",) if kind == "lstm" else ("ghn",)):
+        err = float((fused[key] - ref[key]).abs().max())
+        assert err < 5e-3, (key, err)
+    assert float((fused["Hsb"].float() - ref["Hsb"].float()).abs().max()) < 2e-2
