@@ -179,11 +179,21 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
     # forward pass, so the pass over F runs on the side stream beside the latency-bound reverse loop
     if mode == "bf16":
         (ctx, ctxT), ctx_done = ops.fork(lambda: _ctx_bf16(bs, Pn, sv["F"], alphas), uses=(sv["F"], alphas))
+    fused_bwd = None                # layer-0 fused step kernel: None = not tried yet, then True / False for the pass
     for t in reversed(range(T)):
         bt, o0 = bs[t], off[t]
         o1 = o0 + bt
+        fused0 = False
         for l in reversed(range(L)):
             Wih, Whh, _, _ = layer_params(P, l)
+            if tc and l == 0 and fused_bwd is not False:
+                # layer 0: gate gradients and d embed(ctx_t) = dG W_ih[:, E:] from one stream of the gate-gradient tile
+                r = ops.rnn_step_x_tc_bwd(kind, W["hh0"][1], W["ihc"][1], bs, t, outs[0], dHs[0], dctx_all, h0=h0, c0=c0,
+                                          out=bouts[0], tag="step_bwd")
+                fused_bwd = r is not None
+                if fused_bwd:
+                    bouts[0], fused0 = r, True
+                    continue
             if tc:
                 bouts[l] = ops.rnn_seq_tc_bwd(kind, W[f"hh{l}"][1], bs, outs[l], dHs[l], h0=h0, c0=c0,
                                               t_range=(t + 1, t), out=bouts[l], tag="step_bwd")
@@ -197,7 +207,9 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
                 if l > 0:
                     ops.sgemm(bouts[l]["dG"][o0:o1], Wih, out=dHs[l - 1][o0:o1])
         # d embed(ctx_t) = dG W_ih[:, E:]
-        if tc:
+        if fused0:
+            pass
+        elif tc:
             ops.gemm_bf16(bouts[0]["dGb"][o0:o1], W["ihc"][1], out=dctx_all[o0:o1], tag="ihc_dx")
         else:
             ops.sgemm(bouts[0]["dG"][o0:o1], Wih0[:, E:], out=dctx_all[o0:o1])
@@ -215,6 +227,9 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
             dq = ops.sgemm(datt2_all[o0:o1], Wd)
             ops.add_rows(bouts[L - 1]["dstate"][0], dq, bt)
 
+    if fused_bwd:                   # bias gradients = row sums of the transposed gate gradients
+        bouts[0]["dbih"] = ops.rowsum_bf16(bouts[0]["dGT"])
+        bouts[0]["dbhh"] = ops.rowsum_bf16(bouts[0]["dGhT"]) if kind == _lib.ST_GRU else bouts[0]["dbih"]
     # ---- hoisted weight gradients.  The encoder-projection chain (one pass over att1, then the largest GEMM
     # of the step) is independent of the recurrent ones: side stream.
     def enc_chain():

@@ -485,6 +485,36 @@ def rnn_step_x_tc_fwd(kind, Gx, X_b, Whh_b, Wx_b, bhh, bs, t, *, h0, h0_b, c0=No
     return o
 
 
+def rnn_step_x_tc_bwd(kind, WhhT_b, WxT_b, bs, t, saved, dHs, dX, *, h0=None, c0=None, out=None, tag=None):
+    """Step t of the reverse pass through the fused step: the gate gradients (same dict as rnn_seq_tc_bwd) and
+    rows of step t of dX (N, EX) fp32 = dG_t W_x.  None when the shape is unsupported (needs EX == H, H % 64 == 0)."""
+    lib = _lib.load()
+    N, H, GH = sum(bs), WhhT_b.shape[0], WhhT_b.shape[1]
+    if not STEP_X or H % 64 != 0 or H > 512 or WxT_b.shape[0] != H or dX.shape[1] != H:
+        return None
+    dev = dHs.device
+    ldt = (N + 7) // 8 * 8
+    o = out
+    if o is None:
+        mk = lambda: (torch.empty(N, GH, dtype=BF16, device=dev), torch.empty(GH, ldt, dtype=BF16, device=dev))
+        dGb, dGT = mk()
+        dGhb, dGhT = mk() if kind == _lib.ST_GRU else (dGb, dGT)
+        o = {"dGb": dGb, "dGT_full": dGT, "dGT": dGT[:, :N], "dGhb": dGhb, "dGhT_full": dGhT, "dGhT": dGhT[:, :N],
+             "dbih": None, "dbhh": None, "dstate": torch.zeros(2, bs[0], H, dtype=F32, device=dev), "barrier": _barrier(dev)}
+    tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
+    st = lib.st_rnn_step_x_tc_bwd(kind, H, len(bs), int_array(bs), t, _raw(WhhT_b), _raw(WxT_b), WxT_b.stride(0),
+                                  ptr(h0, F32), ptr(c0, F32), ptr(saved["Hs"], F32), ptr(saved["Cs"]),
+                                  ptr(saved["gates"], F32), ptr(saved["ghn"]), ptr(dHs, F32), _raw(o["dGb"]),
+                                  _raw(o["dGT_full"]), _raw(o["dGhb"]), _raw(o["dGhT_full"]), ldt, ptr(o["dstate"]),
+                                  ptr(dX, F32), dX.stride(0), ptr(o["barrier"]), stream_ptr())
+    if st == -3:
+        return None
+    check(st, "st_rnn_step_x_tc_bwd")
+    if tok:
+        TIMER.end(tok)
+    return o
+
+
 def rnn_seq_tc_bwd(kind, WhhT_b, bs, saved, dHs, *, h0=None, c0=None, t_range=None, out=None, want_bias=True,
                    tag=None):
     """Returns dict(dGb, dGT, dGhb, dGhT, dbih, dbhh, dstate) (bf16 GEMM operands) or None if unsupported."""

@@ -276,3 +276,49 @@ def test_rnn_step_with_folded_context_projection(kind, H, EX, lengths):
         err = float((fused[key] - ref[key]).abs().max())
         assert err < 5e-3, (key, err)
     assert float((fused["Hsb"].float() - ref["Hsb"].float()).abs().max()) < 2e-2
+
+
+@pytest.mark.parametrize("kind", ["gru", "lstm"])
+@pytest.mark.parametrize("H,lengths", [
+    (128, [7, 7, 6, 4, 4, 2]),                                     # one 64-row tile, ragged
+    (512, [6] * 100 + [4] * 28),                                   # config-3 shape: 2 x 64-row tiles
+    (512, [3] * 300 + [2] * 212),                                  # config-4 shape: 4 x 128-row tiles
+])
+def test_rnn_step_backward_with_folded_context_gradient(kind, H, lengths, monkeypatch):
+    """The reverse step that forms d embed(ctx_t) = dG_t W_ih[:, E:] from the same stream of the gate-gradient
+    tile as dh_{t-1}, against {single-step BPTT kernel; small GEMM}, over a whole reverse pass."""
+    from showtell_b200 import _lib, ops
+    k = _lib.ST_LSTM if kind == "lstm" else _lib.ST_GRU
+    G = 4 if kind == "lstm" else 3
+    bs = _lib.batch_sizes(lengths)
+    N, B0 = sum(bs), bs[0]
+    g = torch.Generator().manual_seed(13)
+    Gx = torch.randn(N, G * H, generator=g).to(DEV)
+    Whh = (torch.randn(G * H, H, generator=g) * 0.08).to(DEV)
+    Wx = (torch.randn(G * H, H, generator=g) * 0.08).to(DEV)
+    bhh = (torch.randn(G * H, generator=g) * 0.1).to(DEV)
+    h0 = (torch.randn(B0, H, generator=g) * 0.5).to(DEV)
+    c0 = (torch.randn(B0, H, generator=g) * 0.5).to(DEV) if kind == "lstm" else None
+    dHs = torch.randn(N, H, generator=g).to(DEV)
+    Wb, WT = ops.cast_bf16(Whh, True, True)
+    _, WxT = ops.cast_bf16(Wx, False, True)
+    h0b, _ = ops.cast_bf16(h0, True, False)
+    monkeypatch.setattr(ops, "USE_CLUSTER", False)
+    saved = ops.rnn_seq_tc_fwd(k, Gx, Wb, bhh, bs, h0=h0, h0_b=h0b, c0=c0)
+    ref, fused = None, None
+    dX_ref = torch.zeros(N, H, device=DEV)
+    dX = torch.zeros(N, H, device=DEV)
+    offs = [sum(bs[:t]) for t in range(len(bs))]
+    for t in reversed(range(len(bs))):
+        o0, o1 = offs[t], offs[t] + bs[t]
+        ref = ops.rnn_seq_tc_bwd(k, WT, bs, saved, dHs, h0=h0, c0=c0, t_range=(t + 1, t), out=ref, want_bias=False)
+        ops.gemm_bf16(ref["dGb"][o0:o1], WxT, out=dX_ref[o0:o1])
+        fused = ops.rnn_step_x_tc_bwd(k, WT, WxT, bs, t, saved, dHs, dX, h0=h0, c0=c0, out=fused)
+        assert ref is not None and fused is not None
+        # the carried gradient is the only coupling between steps: compare it step by step
+        e = float((fused["dstate"] - ref["dstate"]).abs().max() / ref["dstate"].abs().max())
+        assert e < 1e-3, (t, e)
+    torch.cuda.synchronize()
+    assert float((fused["dGb"].float() - ref["dGb"].float()).abs().max()) <= 2e-2 * float(ref["dGb"].float().abs().max())
+    assert float((fused["dGT"].float() - ref["dGT"].float()).abs().max()) <= 2e-2 * float(ref["dGT"].float().abs().max())
+    assert float((dX - dX_ref).abs().max() / dX_ref.abs().max()) < 1e-3
