@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libshowtell_b200.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("SHOWTELL_B200_LIBNAME", "libshowtell_b200.so"))   # A/B builds only
 
 ST_GRU, ST_LSTM = 0, 1
 ST_MAX_STEPS = 128

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libshowtell_b200.so")
+LIB = os.path.join(HERE, os.environ.get("SHOWTELL_B200_LIBNAME", "libshowtell_b200.so"))   # A/B builds: other name
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
@@ -34,12 +34,16 @@ def _digest(path):
 
 
 def _compile(src, force):
-    obj = os.path.join(OBJ, os.path.basename(src) + ".o")
+    # A/B builds: SHOWTELL_B200_VARIANT="file.cu:-DX=1 -DY=2" compiles that one source with extra flags into its own object
+    var = os.environ.get("SHOWTELL_B200_VARIANT", "")
+    extra = var.split(":", 1)[1].split() if var and os.path.basename(src) == var.split(":", 1)[0] else []
+    tag = ("." + hashlib.sha1(" ".join(extra).encode()).hexdigest()[:8]) if extra else ""
+    obj = os.path.join(OBJ, os.path.basename(src) + tag + ".o")
     stamp = obj + ".sha1"
     dig = _digest(src)
     if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
         return obj, False, ""
-    r = subprocess.run([NVCC] + FLAGS + ["-c", src, "-o", obj], capture_output=True, text=True)
+    r = subprocess.run([NVCC] + FLAGS + extra + ["-c", src, "-o", obj], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
     with open(stamp, "w") as f:

@@ -30,9 +30,23 @@
 namespace st {
 namespace {
 
-constexpr int NCW = 8, NCT = NCW * 32, SNT = NCT + 32;   // consumer warps / threads, + producer warp
-constexpr int STG = 12;   // 192 KB in flight per SM: the stream is latency-bound (HBM ~2 us under load)
-constexpr uint32_t CHUNK = 16384;
+// Tunables, measured on B200 (tools/attn_variants.sh A/B builds): with at most one batch row
+// per SM (rows <= SM count, config 3: B = 128) the step is a latency chain and wants many consumer warps and big
+// chunks -- 24 warps, 4 x 48 KB; with several rows per SM (config 4: B = 512) it is bound by the bytes and two
+// smaller CTAs per SM (8 warps, 3 x 32 KB each) overlap one row's softmax with the other's stream: 85 -> 47 us.
+template <int NCW_, int STG_, int CHUNK_, int PER_SM_>
+struct StreamCfg {
+  static constexpr int NCW = NCW_, NCT = NCW_ * 32, SNT = NCW_ * 32 + 32;   // consumer warps / threads, + producer warp
+  static constexpr int STG = STG_, PER_SM = PER_SM_;
+  static constexpr uint32_t CHUNK = CHUNK_;
+};
+#ifdef ST_ATTN_NCW      // pinned A/B build
+using CfgWide = StreamCfg<ST_ATTN_NCW, ST_ATTN_STG, ST_ATTN_CHUNK, ST_ATTN_CTAS_PER_SM>;
+using CfgDual = CfgWide;
+#else
+using CfgWide = StreamCfg<24, 4, 49152, 1>;
+using CfgDual = StreamCfg<8, 3, 32768, 2>;
+#endif
 
 template <typename T> struct V16;
 template <> struct V16<__nv_bfloat16> {
@@ -60,33 +74,38 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
+template <int NCT> __device__ __forceinline__ void cons_sync_n() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
 
-__device__ __forceinline__ float cons_sum(float v, float* red) {
+template <int NCW> __device__ __forceinline__ float cons_sum_n(float v, float* red) {
   v = warp_sum(v);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  cons_sync();
+  cons_sync_n<NCW * 32>();
   float r = 0.f;
 #pragma unroll
   for (int i = 0; i < NCW; ++i) r += red[i];
-  cons_sync();
+  cons_sync_n<NCW * 32>();
   return r;
 }
-__device__ __forceinline__ float cons_max(float v, float* red) {
+template <int NCW> __device__ __forceinline__ float cons_max_n(float v, float* red) {
   v = warp_max(v);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  cons_sync();
+  cons_sync_n<NCW * 32>();
   float r = red[0];
 #pragma unroll
   for (int i = 1; i < NCW; ++i) r = fmaxf(r, red[i]);
-  cons_sync();
+  cons_sync_n<NCW * 32>();
   return r;
 }
 
 
 // VPL1 = 16-byte vectors per lane of a pass-1 row (row bytes / 512); RV2 = vectors per pass-2 row.
-template <typename T, int ACT, bool BWD, int VPL1, int RV2>
-__global__ void __launch_bounds__(SNT) attn_stream_kernel(const int nrows, const StreamParams p) {
+template <typename T, int ACT, bool BWD, int VPL1, int RV2, typename C>
+__global__ void __launch_bounds__(C::SNT) attn_stream_kernel(const int nrows, const StreamParams p) {
+  constexpr int NCW = C::NCW, NCT = C::NCT, STG = C::STG;
+  constexpr uint32_t CHUNK = C::CHUNK;
+  auto cons_sync = [] { cons_sync_n<NCT>(); };
+  auto cons_sum = [](float v, float* red) { return cons_sum_n<NCW>(v, red); };
+  auto cons_max = [](float v, float* red) { return cons_max_n<NCW>(v, red); };
   constexpr int EPV = V16<T>::N;
   constexpr int NG = NCT / RV2;                   // pass-2 row groups
   extern __shared__ uint8_t smem_raw[];
@@ -268,15 +287,15 @@ __global__ void __launch_bounds__(SNT) attn_stream_kernel(const int nrows, const
   }  // rows
 }
 
-template <typename T, int ACT, bool BWD, int VPL1>
-int launch_rv2(int rows, const StreamParams& p, int rv2, size_t smem, cudaStream_t s) {
-  int sms = 0;
-  ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
+template <typename T, int ACT, bool BWD, int VPL1, typename C>
+int launch_rv2(int rows, const StreamParams& p, int rv2, cudaStream_t s, int sms) {
+  const size_t smem = 128 + (size_t)C::STG * C::CHUNK + sizeof(float) * (size_t)p.P;
+  const int cap = sms * C::PER_SM;
 #define ST_GO(RV2)                                                                                         \
   do {                                                                                                     \
-    auto kern = attn_stream_kernel<T, ACT, BWD, VPL1, RV2>;                                                \
+    auto kern = attn_stream_kernel<T, ACT, BWD, VPL1, RV2, C>;                                             \
     ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-    ST_CUDA_TRY(launch_pdl(kern, dim3(rows < sms ? rows : sms), dim3(SNT), smem, s, rows, p));            \
+    ST_CUDA_TRY(launch_pdl(kern, dim3(rows < cap ? rows : cap), dim3(C::SNT), smem, s, rows, p));          \
   } while (0)
   if (rv2 == 32) ST_GO(32);
   else if (rv2 == 64) ST_GO(64);
@@ -290,10 +309,16 @@ template <typename T, int ACT, bool BWD>
 int launch_vpl(int rows, const StreamParams& p, cudaStream_t s) {
   const int R1 = BWD ? p.E : p.A, R2 = BWD ? p.A : p.E;
   const int vpl1 = R1 * (int)sizeof(T) / 512, rv2 = R2 * (int)sizeof(T) / 16;
-  const size_t smem = 128 + (size_t)STG * CHUNK + sizeof(float) * (size_t)p.P;
-  if (vpl1 == 1) return launch_rv2<T, ACT, BWD, 1>(rows, p, rv2, smem, s);
-  if (vpl1 == 2) return launch_rv2<T, ACT, BWD, 2>(rows, p, rv2, smem, s);
-  return launch_rv2<T, ACT, BWD, 4>(rows, p, rv2, smem, s);
+  int sms = 0;
+  ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
+  if (rows <= sms) {     // at most one row per SM: the wide configuration
+    if (vpl1 == 1) return launch_rv2<T, ACT, BWD, 1, CfgWide>(rows, p, rv2, s, sms);
+    if (vpl1 == 2) return launch_rv2<T, ACT, BWD, 2, CfgWide>(rows, p, rv2, s, sms);
+    return launch_rv2<T, ACT, BWD, 4, CfgWide>(rows, p, rv2, s, sms);
+  }
+  if (vpl1 == 1) return launch_rv2<T, ACT, BWD, 1, CfgDual>(rows, p, rv2, s, sms);
+  if (vpl1 == 2) return launch_rv2<T, ACT, BWD, 2, CfgDual>(rows, p, rv2, s, sms);
+  return launch_rv2<T, ACT, BWD, 4, CfgDual>(rows, p, rv2, s, sms);
 }
 
 bool row_ok(int elems, int esz) {
