@@ -331,9 +331,16 @@ def main():
                     "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"] if ach else None,
                     "traffic": None, "peak_source": pk["src"] + " (copy bandwidth)"}
         elif is_beam:
-            roof = {"bound": "tensor", "kernel": "per-step vocabulary projection (fp32 CUDA-core path in round 1)",
-                    "achieved": None, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": None, "traffic": None,
-                    "peak_source": pk["src"]}
+            # whole decode loop: (1 + K (T-1)) dependent steps per caption, each {GRU gates 2*3H(E+H), vocabulary
+            # projection 2HV} FLOPs.  The products run as 3xTF32 (three tf32 MMAs per fp32-accurate
+            # product, tf32 at half the bf16 rate), so 1/6 of the bf16 peak is the most this arithmetic can reach.
+            flops_caption = (1 + Pn * (T - 1)) * (2.0 * 3 * H * (E + H) + 2.0 * H * V)
+            ach = flops_caption * units_per_step / world / (ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "decode loop (gate + vocabulary products per dependent step, "
+                    + ("3xTF32 tensor-core" if args.decode_gemm == "tf32x3" else "fp32 CUDA-core") + " GEMMs), algorithmic "
+                    "FLOPs = (1 + K(T-1)) * (2*3H(E+H) + 2HV) per caption; fp32-accurate 3xTF32 can reach at most peak/6",
+                    "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
+                    "traffic": None, "peak_source": pk["src"] + " (bf16 cuBLAS sustained)"}
         else:
             # dominant kernels: the vocabulary-projection GEMMs (each 2*N*H*V FLOPs)
             vocab_flops = 2.0 * B * T * H * V
