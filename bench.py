@@ -194,6 +194,8 @@ def main():
     ap.add_argument("--decode-gemm", default="tf32x3", choices=["fp32", "tf32x3"],
                     help="beam workloads: nn.Linear products on CUDA cores (fp32) or fp32-accurate 3xTF32 tensor cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--features", default="fp32", choices=["fp32", "bf16"],
+                    help="attention workloads: dtype of the (B, 2048, P) grid handed to the decoder (reference: fp32)")
     ap.add_argument("--optimizer", default="none", choices=["none", "sgd", "adam"],
                     help="training workloads: also run the fused optimizer step (main.py:152) inside the timed step")
     args = ap.parse_args()
@@ -241,6 +243,8 @@ def main():
     if world > 1 and not is_beam:
         net.grad_reducer = parallel.GradReducer()          # NCCL all-reduce on a side stream
     feat_h, cap_h, lengths = make_batch(model, B, Pn, 1 + rank)
+    if args.features == "bf16" and model.startswith("attn"):
+        feat_h = feat_h.bfloat16()
     feat_p = feat_h.pin_memory()
     cap_p = cap_h.pin_memory() if cap_h is not None else None
     feat_d = feat_h.to(dev)
@@ -361,7 +365,7 @@ def main():
         if not is_beam:
             roof["step_flops"] = train_flops(model, B, Pn)
             roof["step_tflops"] = roof["step_flops"] / (ms * 1e-3) / 1e12
-        h2d = feat_p.numel() * 4 + (cap_p.numel() * 8 if cap_p is not None else 0)
+        h2d = feat_p.numel() * feat_p.element_size() + (cap_p.numel() * 8 if cap_p is not None else 0)
         line = {"metric": metric, "value": units_per_step / (ms * 1e-3), "unit": unit, "n_gpus": world,
                 "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32" if dtype == "fp32" else "bf16",
@@ -369,6 +373,7 @@ def main():
                 "config": {"workload": desc, "global_batch": B * world, "seq_len": T, "parallelism": f"dp{world}",
                            "l2": "flushed between timed steps (256 MiB fill, outside the event pairs)",
                            "launch": "whole step replayed as one CUDA graph (captured on the 3rd identical step)",
+                           "features": ("bf16 grid (autocast trunk)" if feat_h.dtype == torch.bfloat16 else "fp32 (as the reference's encoder emits them)"),
                            "optimizer": "excluded" if opt is None else args.optimizer + " step (fused, one launch) included"},
                 "e2e": {"value": units_per_step / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": out_host.numel() * out_host.element_size(), "ms_per_step": ms_e2e},

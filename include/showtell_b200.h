@@ -323,6 +323,10 @@ int st_shift_states(float* Hprev, const float* Hs, const float* h0, int H, int n
  * ------------------------------------------------------------------------------------------ */
 int st_attn_relayout(const float* f, int B, int C, int P, void* F, void* FT, int ldft, int out_bf16,
                      float* mean_f, st_stream_t stream);
+/* Same with the channels-first grid handed over in bf16 (a ResNet trunk run under autocast
+ * produces it; halves the largest host-to-device / HBM read of the step). */
+int st_attn_relayout_bf16in(const void* f_bf16, int B, int C, int P, void* F, void* FT, int ldft, int out_bf16,
+                            float* mean_f, st_stream_t stream);
 int st_attn_step_fwd(int rows, int P, int A, int E, const void* att1, const void* Fe, int in_bf16,
                      const float* att2, const float* wf, const float* bf, const float* b_embed, float* alphas,
                      int alpha_stride, float* S, float* ctx_out, int ld_ctx, void* ctx_out_bf16, int ld_ctx_bf16,

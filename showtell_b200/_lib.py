@@ -72,6 +72,7 @@ _SIGS = {
                                   _P, _P]),
     "st_shift_states": (_I, [_P, _P, _P, _I, _I, _IP, _P]),
     "st_attn_relayout": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
+    "st_attn_relayout_bf16in": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
     "st_attn_step_fwd": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _P, _I, _I, _P]),
     "st_attn_step_bwd": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _I, _P]),
     "st_attn_hoist_bwd": (_I, [_I, _IP, _I, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P]),

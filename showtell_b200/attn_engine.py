@@ -319,7 +319,8 @@ class AttnLogitsFn(torch.autograd.Function):
         names = [n for n, _ in mod.named_parameters()]
         P = {n: p.detach() for n, p in zip(names, params)}
         mode = mod.compute_dtype
-        f = feature.detach().contiguous().to(F32)
+        f = feature.detach().contiguous()
+        f = f if f.dtype == BF16 else f.to(F32)       # bf16 grids (autocast trunk) are consumed as they are
         cap = caption.contiguous()
         bs = _check_inputs(f, cap, lengths, mod.nos_filters)
         save = any(ctx.needs_input_grad)
@@ -351,7 +352,8 @@ class AttnLossFn(torch.autograd.Function):
         names = [n for n, _ in mod.named_parameters()]
         P = {n: p.detach() for n, p in zip(names, params)}
         mode = mod.compute_dtype
-        f = feature.detach().contiguous().to(F32)
+        f = feature.detach().contiguous()
+        f = f if f.dtype == BF16 else f.to(F32)       # bf16 grids (autocast trunk) are consumed as they are
         cap = caption.contiguous()
         bs = _check_inputs(f, cap, lengths, mod.nos_filters)
         need = any(ctx.needs_input_grad)
@@ -395,7 +397,7 @@ class AttnLossFn(torch.autograd.Function):
                 g2.update(grads)
             return loss, alphas, g2
 
-        key = ("attn", mode, kind, L, tuple(bs), tuple(f.shape), tuple(cap.shape), need, dt, db, float(alpha_c),
+        key = ("attn", mode, kind, L, tuple(bs), tuple(f.shape), str(f.dtype), tuple(cap.shape), need, dt, db, float(alpha_c),
                tuple(p.data_ptr() for p in params))
         loss, alphas, ctx.grads = graphs.run(mod, key, body, (f, cap))
         ctx.names = names

@@ -76,29 +76,49 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // written out twice: F rows get 64 channels = 128 B (bf16) per location, FT rows get P contiguous
 // locations per channel.  HBM-bound: 4 + 2*sizeof(T) bytes per element.
 constexpr int RL_CH = 64;
-template <typename T>
+// TI = float (the reference's feature dtype, cnn_attn.py:49) or __nv_bfloat16 (a trunk run under autocast: half the
+// bytes over PCIe / HBM for the largest input of the step).
+template <typename T, typename TI>
 __global__ void __launch_bounds__(NT)
-relayout_kernel(const float* __restrict__ f, int C, int P, T* __restrict__ F, T* __restrict__ FT, int ldft,
+relayout_kernel(const TI* __restrict__ f, int C, int P, T* __restrict__ F, T* __restrict__ FT, int ldft,
                 float* __restrict__ mean_f) {
   extern __shared__ float tile[];                 // [RL_CH][PS], PS odd: conflict-free column reads
   const int PS = P | 1;
   const int b = blockIdx.y, c0 = blockIdx.x * RL_CH;
   const int nch = min(RL_CH, C - c0);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float* src = f + ((size_t)b * C + c0) * P;
-  if ((P & 3) == 0) {   // the slab is contiguous and 16-byte aligned: 128-bit loads, running (row, col)
+  const TI* src = f + ((size_t)b * C + c0) * P;
+  if (sizeof(TI) == 2) {
+    if ((P & 3) == 0 && ((nch * P) & 7) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      // 8 bf16 per 128-bit load; P % 4 == 0, so each half of a vector stays inside one channel row
+      const int nv = nch * P / 8;
+      for (int i = tid; i < nv; i += NT) {
+        const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(src) + (size_t)i * 16);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int hq = 0; hq < 2; ++hq) {
+          const int e = i * 8 + hq * 4, row = e / P, col = e - row * P;
+          float* d = tile + row * PS + col;
+          d[0] = __uint_as_float(w[2 * hq] << 16); d[1] = __uint_as_float(w[2 * hq] & 0xffff0000u);
+          d[2] = __uint_as_float(w[2 * hq + 1] << 16); d[3] = __uint_as_float(w[2 * hq + 1] & 0xffff0000u);
+        }
+      }
+    } else {
+      for (int i = tid; i < nch * P; i += NT) tile[(i / P) * PS + (i % P)] = (float)src[i];
+    }
+  } else if ((P & 3) == 0) {   // the slab is contiguous and 16-byte aligned: 128-bit loads, running (row, col)
     const int nv = nch * P / 4;
     int col = tid * 4, row = 0;
     while (col >= P) { col -= P; ++row; }
     for (int i = tid; i < nv; i += NT) {
-      const float4 v = *reinterpret_cast<const float4*>(src + (size_t)i * 4);
+      const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + (size_t)i * 4);
       float* d = tile + row * PS + col;
       d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
       col += NT * 4;
       while (col >= P) { col -= P; ++row; }
     }
   } else {
-    for (int i = tid; i < nch * P; i += NT) tile[(i / P) * PS + (i % P)] = src[i];
+    for (int i = tid; i < nch * P; i += NT) tile[(i / P) * PS + (i % P)] = (float)src[i];
   }
   __syncthreads();
   // F[(b*P + p), c0 + c]: warp per location, a lane writes two adjacent channels (128 B per warp in bf16)
@@ -426,8 +446,8 @@ __global__ void add_rows_kernel(float* __restrict__ dst, const float* __restrict
 
 extern "C" {
 
-int st_attn_relayout(const float* f, int B, int C, int P, void* F, void* FT, int ldft, int out_bf16,
-                     float* mean_f, st_stream_t stream) {
+static int relayout_any(const void* f, int f_bf16, int B, int C, int P, void* F, void* FT, int ldft, int out_bf16,
+                        float* mean_f, st_stream_t stream) {
   using namespace st;
   ST_REQUIRE(f && F && mean_f, ST_ERR_NULL, "st_attn_relayout: NULL pointer");
   ST_REQUIRE(B >= 1 && C >= 1 && P >= 1 && (!FT || ldft >= B * P), ST_ERR_BAD_SHAPE,
@@ -437,17 +457,27 @@ int st_attn_relayout(const float* f, int B, int C, int P, void* F, void* FT, int
   const size_t smem = sizeof(float) * RL_CH * (size_t)(P | 1);
   ST_REQUIRE(smem <= 200 * 1024, ST_ERR_BAD_SHAPE, "st_attn_relayout: P=%d too large", P);
   cudaStream_t s = as_stream(stream);
-  if (out_bf16) {
-    auto kern = relayout_kernel<__nv_bfloat16>;
-    ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, NT, smem, s>>>(f, C, P, (__nv_bfloat16*)F, (__nv_bfloat16*)FT, ldft, mean_f);
-  } else {
-    auto kern = relayout_kernel<float>;
-    ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, NT, smem, s>>>(f, C, P, (float*)F, (float*)FT, ldft, mean_f);
-  }
+#define ST_RELAYOUT(T, TI)                                                                               \
+  do {                                                                                                   \
+    auto kern = relayout_kernel<T, TI>;                                                                  \
+    ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+    kern<<<grid, NT, smem, s>>>((const TI*)f, C, P, (T*)F, (T*)FT, ldft, mean_f);                        \
+  } while (0)
+  if (out_bf16) { if (f_bf16) ST_RELAYOUT(__nv_bfloat16, __nv_bfloat16); else ST_RELAYOUT(__nv_bfloat16, float); }
+  else          { if (f_bf16) ST_RELAYOUT(float, __nv_bfloat16); else ST_RELAYOUT(float, float); }
+#undef ST_RELAYOUT
   ST_LAUNCH_TRY("relayout_kernel");
   return ST_OK;
+}
+
+int st_attn_relayout(const float* f, int B, int C, int P, void* F, void* FT, int ldft, int out_bf16,
+                     float* mean_f, st_stream_t stream) {
+  return relayout_any(f, 0, B, C, P, F, FT, ldft, out_bf16, mean_f, stream);
+}
+
+int st_attn_relayout_bf16in(const void* f_bf16, int B, int C, int P, void* F, void* FT, int ldft, int out_bf16,
+                            float* mean_f, st_stream_t stream) {
+  return relayout_any(f_bf16, 1, B, C, P, F, FT, ldft, out_bf16, mean_f, stream);
 }
 
 int st_attn_step_fwd(int rows, int P, int A, int E, const void* att1, const void* Fe, int in_bf16,

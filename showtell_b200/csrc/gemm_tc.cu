@@ -959,11 +959,23 @@ inline int pick_variant(const TcParams& p, int sms) {
   return pick_bn(p.M, p.N, sms);
 }
 
+// The per-step products of the attention loop (M = live batch rows, N = K = 512) are a latency chain, not a
+// throughput problem: with 128-wide tiles only 4-16 CTAs work and each pulls a 16 KB B block per k-step; 64-wide
+// tiles double the CTAs and shorten the per-k-step TMA time.  Plain stores only (the CE epilogues index their
+// partials by 128-column tile).
+template <int EPI>
+inline bool want_narrow(const TcParams& p, int sms) {
+  if (EPI != EPI_STORE || g_variant || p.N <= 64) return false;
+  const long t128 = (long)((p.M + BM - 1) / BM) * ((p.N + 127) / 128);
+  return t128 * 8 <= sms;
+}
+
 template <int EPI>
 int launch_tc(const TcParams& p, const void* A, int lda, const void* B, int ldb, cudaStream_t s, int bn = 0) {
   ST_REQUIRE(p.M >= 1 && p.N >= 1 && p.K >= 1, ST_ERR_BAD_SHAPE, "gemm_bf16: M=%d N=%d K=%d", p.M, p.N, p.K);
   int sms = 0;
   ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
+  if (bn == 0 && want_narrow<EPI>(p, sms)) return launch_tc_bn<EPI_STORE, 64>(p, A, lda, B, ldb, s, sms);
   if (bn == 0) bn = pick_variant<EPI>(p, sms);
   if (bn == 2) return launch_tc_pair<EPI>(p, A, lda, B, ldb, s, sms);
   return bn == 256 ? launch_tc_bn<EPI, 256>(p, A, lda, B, ldb, s, sms) : launch_tc_bn<EPI, 128>(p, A, lda, B, ldb, s, sms);

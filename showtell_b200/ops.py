@@ -551,7 +551,7 @@ ACT_LEAKY, ACT_TANH = 0, 1
 
 
 def attn_relayout(f, bf16=False, want_t=True):
-    """f (B,C,P) fp32 channels-first -> F (B*P, C), FT (C, B*P) or None, mean_f (B,C)."""
+    """f (B,C,P) fp32 or bf16 channels-first -> F (B*P, C), FT (C, B*P) or None, mean_f (B,C)."""
     lib = _lib.load()
     B, Cc, Pn = f.shape
     dt = BF16 if bf16 else F32
@@ -559,8 +559,9 @@ def attn_relayout(f, bf16=False, want_t=True):
     ld = (B * Pn + 7) // 8 * 8
     FT = torch.empty(Cc, ld, dtype=dt, device=f.device)[:, :B * Pn] if want_t else None
     mean_f = torch.empty(B, Cc, dtype=F32, device=f.device)
-    check(lib.st_attn_relayout(ptr(f, F32), B, Cc, Pn, _raw(F), _raw(FT) if want_t else None, ld, int(bf16),
-                               ptr(mean_f), stream_ptr()), "st_attn_relayout")
+    fn = lib.st_attn_relayout_bf16in if f.dtype == BF16 else lib.st_attn_relayout
+    check(fn(ptr(f, f.dtype), B, Cc, Pn, _raw(F), _raw(FT) if want_t else None, ld, int(bf16),
+             ptr(mean_f), stream_ptr()), "st_attn_relayout")
     return F, FT, mean_f
 
 
