@@ -82,3 +82,52 @@ def test_host_modules_reference_only_defined_ops():
         for modname, mod in mods.items():
             for name in set(re.findall(r"(?<![\w.])" + modname + r"\.([A-Za-z_]\w*)", src)):
                 assert hasattr(mod, name), f"{f} uses {modname}.{name}, which does not exist"
+
+
+def test_optimizers_mirror_torch_and_refuse_cpu_tensors():
+    """showtell_b200.optim: same param-group keys as torch.optim (checkpoint interchange, utils.py:125-145), the
+    reference's bad-option errors, and no CPU path."""
+    from showtell_b200 import optim
+    p = [torch.nn.Parameter(torch.randn(3, 4))]
+    assert set(optim.Adam(p, lr=1e-3).param_groups[0]) == set(torch.optim.Adam(p, lr=1e-3).param_groups[0])
+    assert set(optim.SGD(p, lr=1e-3, momentum=0.9).param_groups[0]) == \
+        set(torch.optim.SGD(p, lr=1e-3, momentum=0.9).param_groups[0])
+    for bad in (lambda: optim.SGD(p, lr=-1.0), lambda: optim.SGD(p, lr=0.1, momentum=-0.5),
+                lambda: optim.Adam(p, lr=-1.0), lambda: optim.Adam(p, lr=1e-3, betas=(1.0, 0.9)),
+                lambda: optim.Adam(p, lr=1e-3, eps=-1.0)):
+        with pytest.raises(ValueError):
+            bad()
+    p[0].grad = torch.randn(3, 4)
+    for o in (optim.Adam(p, lr=1e-3), optim.SGD(p, lr=1e-3, momentum=0.9)):
+        with pytest.raises(RuntimeError):
+            o.step()
+    # a torch checkpoint loads
+    t = torch.optim.Adam(p, lr=1e-3)
+    t.step()
+    o = optim.Adam(p, lr=5e-4)
+    o.load_state_dict(t.state_dict())
+    assert o.param_groups[0]["lr"] == 1e-3 and set(o.state[p[0]]) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+def test_encoder_head_names_init_and_cpu_refusal():
+    """cnn.py:37-42: sub-module names / shapes of the two trained ResNet layers; CPU input raises."""
+    from showtell_b200.cnn_head import EncoderHead
+    h = EncoderHead(2048, 512)
+    assert set(h.state_dict()) == {"linear_secondlast_layer.weight", "linear_secondlast_layer.bias", "last_layer.weight",
+                                   "last_layer.bias", "last_layer.running_mean", "last_layer.running_var",
+                                   "last_layer.num_batches_tracked"}
+    assert h.last_layer.momentum == 0.01 and float(h.last_layer.bias.abs().max()) == 0.0
+    assert 0.04 < float(h.linear_secondlast_layer.weight.std()) < 0.06
+    with pytest.raises(RuntimeError):
+        h(torch.randn(4, 2048))
+    with pytest.raises(ValueError):
+        EncoderHead(8, 4, dtype="fp16")
+
+
+def test_grad_reducer_single_process_is_identity():
+    from showtell_b200 import parallel
+    red = parallel.GradReducer()
+    ts = [torch.randn(3, 3), torch.randn(5)]
+    out = red.reduce(ts)
+    assert all(a is b for a, b in zip(out, ts)) and red.slots([t.shape for t in ts]) is None
+    red.finish()
