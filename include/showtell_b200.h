@@ -164,12 +164,16 @@ int st_rnn_step_x_tc_fwd(int kind, int H, int EX, int nsteps, const int* batch_s
  * st_rnn_seq_tc_bwd over [t, t+1) AND, from the same stream of the gate-gradient tile, d embed(ctx_t) =
  * dG_t . W_ih[:, E:] into rows of step t of dX (N, ldx) fp32 -- replaces {st_rnn_seq_tc_bwd; st_gemm_bf16}.
  * WhhT (H, G*H), WxT (EX = H, G*H; ld = ldwxt) bf16.  dstate (2, B0, H) carries dh / dc between the calls, which
- * must walk t = nsteps-1 ... 0 (the first one zeroes the barrier counters).  H % 64 == 0, context width == H. */
+ * must walk t = nsteps-1 ... 0 (the first one zeroes the barrier counters).  H % 64 == 0, context width == H.
+ * Optional (both or neither; single-layer decoders): WdecT (H, A) bf16 = attn.decoder_att.weight^T and datt2 (N, A)
+ * bf16, the attention-query gradients: the attention of step t+1 read h_t as its query (rnn_attn.py:69), so the
+ * kernel first adds datt2[rows of t+1] . W_dec to the carried dh_t -- replaces the st_gemm_bf16(beta = 1) into
+ * dstate after every attention backward except the last (t = 0), which the caller still issues. */
 int st_rnn_step_x_tc_bwd(int kind, int H, int nsteps, const int* batch_sizes_host, int t, const void* WhhT_bf16,
                          const void* WxT_bf16, int ldwxt, const float* h0, const float* c0, const float* Hs,
                          const float* Cs, const float* gates, const float* ghn, const float* dHs, void* dG, void* dGT,
                          void* dGh, void* dGhT, int ldt, float* dstate, float* dX, int ldx, int* barrier,
-                         st_stream_t stream);
+                         const void* WdecT_bf16, int ldwdt, const void* datt2_bf16, int ldq, int A, st_stream_t stream);
 
 /* Encoder head of the base models, cnn.py:37-38,49: nn.BatchNorm1d(E, momentum) over the rows of Y (B, E) =
  * Linear(2048, E)(pooled features) (the Linear product itself is st_sgemm / st_gemm_bf16).

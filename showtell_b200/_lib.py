@@ -69,7 +69,7 @@ _SIGS = {
     "st_rnn_step_x_tc_supported": (_I, [_I, _I, _I]),
     "st_rnn_step_x_tc_fwd": (_I, [_I, _I, _I, _I, _IP, _I, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "st_rnn_step_x_tc_bwd": (_I, [_I, _I, _I, _IP, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I,
-                                  _P, _P]),
+                                  _P, _P, _I, _P, _I, _I, _P]),
     "st_shift_states": (_I, [_P, _P, _P, _I, _I, _IP, _P]),
     "st_attn_relayout": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
     "st_attn_relayout_bf16in": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P]),

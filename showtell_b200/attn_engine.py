@@ -188,8 +188,10 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
             Wih, Whh, _, _ = layer_params(P, l)
             if tc and l == 0 and fused_bwd is not False:
                 # layer 0: gate gradients and d embed(ctx_t) = dG W_ih[:, E:] from one stream of the gate-gradient tile
+                # (single-layer decoders: also the query gradient of step t+1's attention, datt2_{t+1} . W_dec)
+                qfold = L == 1 and ops.query_fold_ok(A)
                 r = ops.rnn_step_x_tc_bwd(kind, W["hh0"][1], W["ihc"][1], bs, t, outs[0], dHs[0], dctx_all, h0=h0, c0=c0,
-                                          out=bouts[0], tag="step_bwd")
+                                          out=bouts[0], tag="step_bwd", query=(W["d"][1], datt2_b) if qfold else None)
                 fused_bwd = r is not None
                 if fused_bwd:
                     bouts[0], fused0 = r, True
@@ -221,7 +223,9 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
                           dctx_all[o0:o1], de_all[o0:o1], datt2_all[o0:o1],
                           datt2_bf16=datt2_b[o0:o1] if tc else None)
         # the query was the PRE-step top-layer hidden: its gradient joins the carried dh of the top layer
-        if tc:
+        if tc and fused0 and L == 1 and ops.query_fold_ok(A) and t > 0:
+            pass                         # consumed by the next (t-1) fused step kernel
+        elif tc:
             ops.gemm_bf16(datt2_b[o0:o1], W["d"][1], out=bouts[L - 1]["dstate"][0][:bt], beta=1.0, tag="att2_dx")
         else:
             dq = ops.sgemm(datt2_all[o0:o1], Wd)

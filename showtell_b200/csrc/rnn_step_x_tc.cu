@@ -254,43 +254,55 @@ struct StepXBwdParams {
   float* dX;                             // (N, ldx) out: rows of step t of d embed(ctx)
   int ldx;
   int* barrier;
+  int KQ;                                // phase 0: k-blocks of the attention-query gradient (0 = off)
 };
 
 template <int G, int BT>
 __global__ void __launch_bounds__(NTH, 1)
 rnn_step_x_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant__ CUtensorMap tmXT,
                          const __grid_constant__ CUtensorMap tmDh, const __grid_constant__ CUtensorMap tmDg,
+                         const __grid_constant__ CUtensorMap tmQT, const __grid_constant__ CUtensorMap tmDq,
                          const __grid_constant__ StepTable tab, const StepXBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int H = p.H, GH = G * H, KB = GH / 64, KBN = H / 64, KBRZ = KB - KBN, NST = p.nstages;
   constexpr uint32_t KBLK_W = 2 * UT * 128;      // [W_hh^T rows of the 16 units ; W_x^T rows of the 16 ctx columns]
   constexpr uint32_t KBLK_A = BT * 128;
+  // phase 0 (optional, p.KQ > 0): the attention of step t+1 read the PRE-step hidden state as its query
+  // (rnn_attn.py:69), so dh_t also receives datt2_{t+1} . W_dec.  Those KQ k-blocks of the datt2 tile go through
+  // the same ring first, against a resident W_dec^T slice, into accumulator columns 32..47.
+  const int KQ = p.KQ;
   uint8_t* sW = smem;                            // [KB][32 rows][128 B]
-  uint8_t* sA = smem + (size_t)KB * KBLK_W;      // [NST][BT rows][128 B] ring
+  uint8_t* sQ = smem + (size_t)KB * KBLK_W;      // [KQ][16 rows][128 B]  W_dec^T slice
+  uint8_t* sA = sQ + (size_t)KQ * (UT * 128);    // [NST][BT rows][128 B] ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)NST * KBLK_A);
   uint64_t* wbar = bars;
   uint64_t* accbar = bars + 1;
+  uint64_t* qbar = bars + 2 + 2 * MAXST;         // phase-0 accumulator ready
   uint64_t* full = bars + 2;
   uint64_t* empty = full + MAXST;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty + MAXST);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty + MAXST + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u0 = blockIdx.x * UT, r0 = blockIdx.y * BT;
   const int t = p.t;
   const int nr = min(BT, tab.bs[t] - r0);        // > 0 by construction of the grid
+  // rows of this tile that were live at step t+1 carry a gradient (and a query gradient) from it
+  const bool have_next = (t + 1 < p.nsteps) && (tab.bs[t + 1] > r0);
+  const bool do_q = KQ > 0 && have_next;
   // ring loads of phase 2: LSTM one per k-block; GRU the n-gate k-blocks twice (dGh, then dG)
   const int NL = (G == 4) ? KB : KB + KBN;
 
   if (warp == 0 && lane == 0) {
     mbar_init(wbar, 1);
     mbar_init(accbar, 1);
+    mbar_init(qbar, 1);
     for (int i = 0; i < MAXST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(32u)
+                 "r"(64u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -300,7 +312,8 @@ rnn_step_x_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   if (warp == 0 && lane == 0) {                  // resident transposed weight slices (cast long before the loop)
-    mbar_expect_tx(wbar, (uint32_t)KB * KBLK_W);
+    mbar_expect_tx(wbar, (uint32_t)KB * KBLK_W + (uint32_t)KQ * (UT * 128));
+    for (int kb = 0; kb < KQ; ++kb) tma_load_2d(sQ + (size_t)kb * (UT * 128), &tmQT, kb * 64, u0, wbar);
     for (int kb = 0; kb < KB; ++kb) {
       tma_load_2d(sW + (size_t)kb * KBLK_W, &tmWT, kb * 64, u0, wbar);
       tma_load_2d(sW + (size_t)kb * KBLK_W + UT * 128, &tmXT, kb * 64, u0, wbar);
@@ -308,6 +321,41 @@ rnn_step_x_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_
   }
   pdl_wait();                 // the prologue overlapped the previous kernel's tail
   pdl_launch_dependents();
+
+  // ---------------- phase 0: dh_t[rows, own units] += datt2_{t+1}[rows, :] . W_dec[:, own units]  (ring slots 0..KQ-1)
+  if (do_q) {
+    if (warp == 0) {
+      const int qbase = tab.off[t + 1] + r0;
+      for (int k = 0; k < KQ; ++k) {
+        const int stage = k % NST;
+        if (k >= NST) mbar_wait(&empty[stage], ((k / NST) - 1) & 1);
+        if (elect_one()) {
+          mbar_expect_tx(&full[stage], KBLK_A);
+          tma_load_2d(sA + (size_t)stage * KBLK_A, &tmDq, k * 64, qbase, &full[stage]);
+        }
+        __syncwarp();
+      }
+    } else if (warp == 1) {
+      mbar_wait(wbar, 0);
+      const uint64_t adesc0 = umma_desc_k128(smem_u32(sA)), qdesc0 = umma_desc_k128(smem_u32(sQ));
+      constexpr uint32_t idesc16 = umma_idesc(BT, UT);
+      for (int k = 0; k < KQ; ++k) {
+        const int stage = k % NST;
+        mbar_wait(&full[stage], (k / NST) & 1);
+        tc_fence_after();
+        const uint64_t ad = adesc0 + (uint64_t)(stage * (KBLK_A >> 4)), bd = qdesc0 + (uint64_t)(k * ((UT * 128) >> 4));
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) tc_mma(tmem_base + 2 * UT, ad + 2 * kk, bd + 2 * kk, idesc16, (k | kk) != 0);
+          tc_commit(&empty[stage]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) tc_commit(qbar);
+      __syncwarp();
+    }
+  }
+  const int C0 = do_q ? KQ : 0;   // ring uses so far: phase 2 continues the slot / parity sequence from here
 
   const bool is_epi = warp >= 2;
   const int q = warp & 3, hf = (warp - 2) >> 2;
@@ -321,10 +369,20 @@ rnn_step_x_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_
   for (int j = 0; j < HALF; ++j) { dhrec[j] = 0.f; dcrec[j] = 0.f; direct[j] = 0.f; }
 
   // ---------------- phase 1: gate gradients of this CTA's (row, unit) pairs (as rnn_seq_tc.cu)
+  if (is_epi && do_q) {        // all lanes of the epilogue warps: tcgen05.ld is warp-collective
+    mbar_wait(qbar, 0);
+    tc_fence_after();
+    tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + 2 * UT + hf * HALF, direct);   // `direct` reused as scratch
+    tc_fence_before();
+  }
   if (r_ok) {
     if (t + 1 < p.nsteps && b < tab.bs[t + 1]) {               // carried gradient of rows live at t+1
       ld8(p.dstate + (size_t)b * H + uu, dhrec);
       if (G == 4) ld8(p.dstate + (size_t)(tab.bs[0] + b) * H + uu, dcrec);
+      if (do_q) {
+#pragma unroll
+        for (int j = 0; j < HALF; ++j) dhrec[j] += direct[j];
+      }
     }
     float dh[HALF], gsv[G][HALF], pa[HALF], pb[HALF], da[G][HALF], dan_r[HALF];
     ld8(p.dHs + n * H + uu, dh);
@@ -401,8 +459,8 @@ rnn_step_x_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_
     proxy_fence_global();
     const int rbase = tab.off[t] + r0;
     for (int i = 0; i < NL; ++i) {
-      const int stage = i % NST;
-      if (i >= NST) mbar_wait(&empty[stage], ((i / NST) - 1) & 1);
+      const int c = C0 + i, stage = c % NST;
+      if (c >= NST) mbar_wait(&empty[stage], ((c / NST) - 1) & 1);
       int kb = i;
       bool from_dg = false;
       if (G == 3 && i >= KBRZ) { kb = KBRZ + ((i - KBRZ) >> 1); from_dg = ((i - KBRZ) & 1) != 0; }
@@ -417,8 +475,8 @@ rnn_step_x_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_
     const uint64_t adesc0 = umma_desc_k128(smem_u32(sA)), bdesc0 = umma_desc_k128(smem_u32(sW));
     constexpr uint32_t idesc32 = umma_idesc(BT, 2 * UT), idesc16 = umma_idesc(BT, UT);
     for (int i = 0; i < NL; ++i) {
-      const int stage = i % NST;
-      mbar_wait(&full[stage], (i / NST) & 1);
+      const int c = C0 + i, stage = c % NST;
+      mbar_wait(&full[stage], (c / NST) & 1);
       tc_fence_after();
       int kb = i;
       bool from_dg = false;
@@ -462,19 +520,20 @@ rnn_step_x_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
   }
 }
 
 template <int G, int BT>
-int try_step_x_bwd(const StepTable& tab, StepXBwdParams p, const void* WhhT, const void* WxT, int ldwxt, cudaStream_t s,
-                   bool* launched) {
+int try_step_x_bwd(const StepTable& tab, StepXBwdParams p, const void* WhhT, const void* WxT, int ldwxt, const void* WqT,
+                   int ldwqt, const void* dQ, int ldq, int AQ, cudaStream_t s, bool* launched) {
   const int H = p.H, GH = G * H, KB = GH / 64, N = tab.off[tab.nsteps];
+  p.KQ = (WqT != nullptr) ? AQ / 64 : 0;
   int dev = 0, optin = 0, sms = 0;
   ST_CUDA_TRY(cudaGetDevice(&dev));
   ST_CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   ST_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const size_t fixed = 1024 + (size_t)KB * (2 * UT * 128) + (2 + 2 * MAXST) * 8 + 64;
+  const size_t fixed = 1024 + (size_t)KB * (2 * UT * 128) + (size_t)p.KQ * (UT * 128) + (4 + 2 * MAXST) * 8 + 64;
   *launched = false;
   if ((size_t)optin <= fixed) return ST_OK;
   int nst = (int)(((size_t)optin - fixed) / (BT * 128));
@@ -489,13 +548,20 @@ int try_step_x_bwd(const StepTable& tab, StepXBwdParams p, const void* WhhT, con
   const size_t smem = fixed + (size_t)nst * (BT * 128);
   auto kern = rnn_step_x_tc_bwd_kernel<G, BT>;
   ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUtensorMap tmWT, tmXT, tmDh, tmDg;
+  CUtensorMap tmWT, tmXT, tmDh, tmDg, tmQT, tmDq;
   ST_TRY(make_tmap(&tmWT, WhhT, H, GH, GH, UT, "WhhT_bf16"));
   ST_TRY(make_tmap(&tmXT, WxT, H, GH, ldwxt, UT, "WxT_bf16"));
   ST_TRY(make_tmap(&tmDh, p.dGh, N, GH, GH, BT, "dGh_bf16"));
   ST_TRY(make_tmap(&tmDg, p.dG, N, GH, GH, BT, "dG_bf16"));
+  if (p.KQ > 0) {
+    ST_TRY(make_tmap(&tmQT, WqT, H, AQ, ldwqt, UT, "WdecT_bf16"));
+    ST_TRY(make_tmap(&tmDq, dQ, N, AQ, ldq, BT, "datt2_bf16"));
+  } else {
+    tmQT = tmWT;
+    tmDq = tmDh;
+  }
   if (p.t == p.nsteps - 1) ST_CUDA_TRY(cudaMemsetAsync(p.barrier, 0, sizeof(int) * 64, s));
-  ST_CUDA_TRY(launch_pdl(kern, grid, dim3(NTH), smem, s, tmWT, tmXT, tmDh, tmDg, tab, p));
+  ST_CUDA_TRY(launch_pdl(kern, grid, dim3(NTH), smem, s, tmWT, tmXT, tmDh, tmDg, tmQT, tmDq, tab, p));
   note_launch();
   *launched = true;
   return ST_OK;
@@ -557,11 +623,15 @@ int st_rnn_step_x_tc_bwd(int kind, int H, int nsteps, const int* batch_sizes_hos
                          const void* WxT_bf16, int ldwxt, const float* h0, const float* c0, const float* Hs,
                          const float* Cs, const float* gates, const float* ghn, const float* dHs, void* dG, void* dGT,
                          void* dGh, void* dGhT, int ldt, float* dstate, float* dX, int ldx, int* barrier,
-                         st_stream_t stream) {
+                         const void* WdecT_bf16, int ldwdt, const void* datt2_bf16, int ldq, int A, st_stream_t stream) {
   using namespace st;
   StepTable tab;
   ST_TRY(make_step_table(tab, nsteps, batch_sizes_host));
   ST_REQUIRE(kind == ST_GRU || kind == ST_LSTM, ST_ERR_UNSUPPORTED, "st_rnn_step_x_tc_bwd: kind=%d", kind);
+  ST_REQUIRE((WdecT_bf16 == nullptr) == (datt2_bf16 == nullptr), ST_ERR_NULL,
+             "st_rnn_step_x_tc_bwd: WdecT_bf16 and datt2_bf16 go together");
+  ST_REQUIRE(!WdecT_bf16 || (A % 64 == 0 && A >= 64 && A <= 64 * MAXKB && ldwdt >= A && ldwdt % 8 == 0 && ldq >= A && ldq % 8 == 0),
+             ST_ERR_UNSUPPORTED, "st_rnn_step_x_tc_bwd: attention width A=%d must be a multiple of 64 and <= %d", A, 64 * MAXKB);
   ST_REQUIRE(H % 64 == 0 && H >= 64 && H <= 64 * MAXKB, ST_ERR_UNSUPPORTED,
              "st_rnn_step_x_tc_bwd: H=%d must be a multiple of 64 and <= %d (and equal the context width)", H, 64 * MAXKB);
   ST_REQUIRE(WhhT_bf16 && WxT_bf16 && Hs && gates && dHs && dG && dGT && dstate && dX && barrier, ST_ERR_NULL,
@@ -575,15 +645,15 @@ int st_rnn_step_x_tc_bwd(int kind, int H, int nsteps, const int* batch_sizes_hos
   if (kind == ST_LSTM) { dGh = dG; dGhT = dGT; }
   StepXBwdParams p{H, t, nsteps, 0, h0, c0, Hs, Cs, gates, ghn, dHs,
                    reinterpret_cast<__nv_bfloat16*>(dG), reinterpret_cast<__nv_bfloat16*>(dGT),
-                   reinterpret_cast<__nv_bfloat16*>(dGh), reinterpret_cast<__nv_bfloat16*>(dGhT), ldt, dstate, dX, ldx, barrier};
+                   reinterpret_cast<__nv_bfloat16*>(dGh), reinterpret_cast<__nv_bfloat16*>(dGhT), ldt, dstate, dX, ldx, barrier, 0};
   bool ok = false;
   cudaStream_t s = as_stream(stream);
   if (kind == ST_LSTM) {
-    ST_TRY((try_step_x_bwd<4, 64>(tab, p, WhhT_bf16, WxT_bf16, ldwxt, s, &ok)));
-    if (!ok) ST_TRY((try_step_x_bwd<4, 128>(tab, p, WhhT_bf16, WxT_bf16, ldwxt, s, &ok)));
+    ST_TRY((try_step_x_bwd<4, 64>(tab, p, WhhT_bf16, WxT_bf16, ldwxt, WdecT_bf16, ldwdt, datt2_bf16, ldq, A, s, &ok)));
+    if (!ok) ST_TRY((try_step_x_bwd<4, 128>(tab, p, WhhT_bf16, WxT_bf16, ldwxt, WdecT_bf16, ldwdt, datt2_bf16, ldq, A, s, &ok)));
   } else {
-    ST_TRY((try_step_x_bwd<3, 64>(tab, p, WhhT_bf16, WxT_bf16, ldwxt, s, &ok)));
-    if (!ok) ST_TRY((try_step_x_bwd<3, 128>(tab, p, WhhT_bf16, WxT_bf16, ldwxt, s, &ok)));
+    ST_TRY((try_step_x_bwd<3, 64>(tab, p, WhhT_bf16, WxT_bf16, ldwxt, WdecT_bf16, ldwdt, datt2_bf16, ldq, A, s, &ok)));
+    if (!ok) ST_TRY((try_step_x_bwd<3, 128>(tab, p, WhhT_bf16, WxT_bf16, ldwxt, WdecT_bf16, ldwdt, datt2_bf16, ldq, A, s, &ok)));
   }
   ST_REQUIRE(ok, ST_ERR_UNSUPPORTED, "st_rnn_step_x_tc_bwd: batch %d x H %d is not co-resident", tab.bs[0], H);
   return ST_OK;

@@ -485,9 +485,18 @@ def rnn_step_x_tc_fwd(kind, Gx, X_b, Whh_b, Wx_b, bhh, bs, t, *, h0, h0_b, c0=No
     return o
 
 
-def rnn_step_x_tc_bwd(kind, WhhT_b, WxT_b, bs, t, saved, dHs, dX, *, h0=None, c0=None, out=None, tag=None):
+STEP_X_QUERY = True   # ... and the attention-query gradient datt2_{t+1} . W_dec into dh_t
+
+
+def query_fold_ok(A):
+    """Shapes for which rnn_step_x_tc_bwd can take the attention-query gradient (`query=`)."""
+    return STEP_X_QUERY and A % 64 == 0 and 64 <= A <= 512
+
+
+def rnn_step_x_tc_bwd(kind, WhhT_b, WxT_b, bs, t, saved, dHs, dX, *, h0=None, c0=None, out=None, tag=None, query=None):
     """Step t of the reverse pass through the fused step: the gate gradients (same dict as rnn_seq_tc_bwd) and
-    rows of step t of dX (N, EX) fp32 = dG_t W_x.  None when the shape is unsupported (needs EX == H, H % 64 == 0)."""
+    rows of step t of dX (N, EX) fp32 = dG_t W_x.  None when the shape is unsupported (needs EX == H, H % 64 == 0).
+    `query` = (W_dec^T (H, A) bf16, datt2 (N, A) bf16): also adds datt2[rows of t+1] . W_dec to the carried dh_t."""
     lib = _lib.load()
     N, H, GH = sum(bs), WhhT_b.shape[0], WhhT_b.shape[1]
     if not STEP_X or H % 64 != 0 or H > 512 or WxT_b.shape[0] != H or dX.shape[1] != H:
@@ -506,7 +515,10 @@ def rnn_step_x_tc_bwd(kind, WhhT_b, WxT_b, bs, t, saved, dHs, dX, *, h0=None, c0
                                   ptr(h0, F32), ptr(c0, F32), ptr(saved["Hs"], F32), ptr(saved["Cs"]),
                                   ptr(saved["gates"], F32), ptr(saved["ghn"]), ptr(dHs, F32), _raw(o["dGb"]),
                                   _raw(o["dGT_full"]), _raw(o["dGhb"]), _raw(o["dGhT_full"]), ldt, ptr(o["dstate"]),
-                                  ptr(dX, F32), dX.stride(0), ptr(o["barrier"]), stream_ptr())
+                                  ptr(dX, F32), dX.stride(0), ptr(o["barrier"]),
+                                  _raw(query[0]) if query else None, query[0].stride(0) if query else 0,
+                                  _raw(query[1]) if query else None, query[1].stride(0) if query else 0,
+                                  query[0].shape[1] if query else 0, stream_ptr())
     if st == -3:
         return None
     check(st, "st_rnn_step_x_tc_bwd")

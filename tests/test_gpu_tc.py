@@ -305,10 +305,16 @@ def test_rnn_step_backward_with_folded_context_gradient(kind, H, lengths, monkey
     h0b, _ = ops.cast_bf16(h0, True, False)
     monkeypatch.setattr(ops, "USE_CLUSTER", False)
     saved = ops.rnn_seq_tc_fwd(k, Gx, Wb, bhh, bs, h0=h0, h0_b=h0b, c0=c0)
-    ref, fused = None, None
+    ref, fused, fq = None, None, None
     dX_ref = torch.zeros(N, H, device=DEV)
     dX = torch.zeros(N, H, device=DEV)
+    dXq = torch.zeros(N, H, device=DEV)
     offs = [sum(bs[:t]) for t in range(len(bs))]
+    # attention-query gradients (one row per packed token) and decoder_att^T, for the `query=` variant
+    A = 128
+    dq = (torch.randn(N, A, generator=g) * 0.3).to(DEV)
+    dqb, _ = ops.cast_bf16(dq, True, False)
+    _, WdT = ops.cast_bf16((torch.randn(A, H, generator=g) * 0.08).to(DEV), False, True)       # (H, A)
     for t in reversed(range(len(bs))):
         o0, o1 = offs[t], offs[t] + bs[t]
         ref = ops.rnn_seq_tc_bwd(k, WT, bs, saved, dHs, h0=h0, c0=c0, t_range=(t + 1, t), out=ref, want_bias=False)
@@ -318,6 +324,20 @@ def test_rnn_step_backward_with_folded_context_gradient(kind, H, lengths, monkey
         # the carried gradient is the only coupling between steps: compare it step by step
         e = float((fused["dstate"] - ref["dstate"]).abs().max() / ref["dstate"].abs().max())
         assert e < 1e-3, (t, e)
+        # query variant: the kernel of step t adds dq[rows of t+1] . W_dec itself; the reference adds it after step t+1
+        fq = ops.rnn_step_x_tc_bwd(k, WT, WxT, bs, t, saved, dHs, dXq, h0=h0, c0=c0, out=fq, query=(WdT, dqb))
+        assert fq is not None
+    # full-chain reference for the query variant
+    refc = None
+    for t in reversed(range(len(bs))):
+        o0, o1 = offs[t], offs[t] + bs[t]
+        refc = ops.rnn_seq_tc_bwd(k, WT, bs, saved, dHs, h0=h0, c0=c0, t_range=(t + 1, t), out=refc, want_bias=False)
+        if t > 0:
+            ops.gemm_bf16(dqb[o0:o1], WdT, out=refc["dstate"][0][:bs[t]], beta=1.0)
+    torch.cuda.synchronize()
+    eq = float((fq["dstate"] - refc["dstate"]).abs().max() / refc["dstate"].abs().max())
+    assert eq < 2e-3, eq
+    assert float((fq["dGb"].float() - refc["dGb"].float()).abs().max()) <= 2e-2 * float(refc["dGb"].float().abs().max())
     torch.cuda.synchronize()
     assert float((fused["dGb"].float() - ref["dGb"].float()).abs().max()) <= 2e-2 * float(ref["dGb"].float().abs().max())
     assert float((fused["dGT"].float() - ref["dGT"].float()).abs().max()) <= 2e-2 * float(ref["dGT"].float().abs().max())
