@@ -131,3 +131,37 @@ def test_grad_reducer_single_process_is_identity():
     out = red.reduce(ts)
     assert all(a is b for a, b in zip(out, ts)) and red.slots([t.shape for t in ts]) is None
     red.finish()
+
+
+def test_collate_contract_matches_create_batch():
+    """utils.py:61-77: length-descending stable order, zero padding, lengths list; sort_batch gives the same batch
+    from unsorted tensors and its permutation restores the caller's order."""
+    from showtell_b200 import _lib, collate
+    g = torch.Generator().manual_seed(0)
+    lens = [4, 7, 4, 2, 7, 5, 1]
+    data = [(f"img{i}.jpg", torch.randn(3, 4, 4, generator=g), torch.randint(1, 50, (n,), generator=g))
+            for i, n in enumerate(lens)]
+    # the reference, restated verbatim (it sorts the list in place)
+    ref = list(data)
+    ref.sort(key=lambda x: len(x[2]), reverse=True)
+    paths, images, target, caption_len = collate.create_batch(data)
+    assert list(paths) == [r[0] for r in ref] and caption_len == [len(r[2]) for r in ref] == [7, 7, 5, 4, 4, 2, 1]
+    assert paths[:2] == ("img1.jpg", "img4.jpg") and paths[3:5] == ("img0.jpg", "img2.jpg")      # ties keep their order
+    assert torch.equal(images, torch.stack([r[1] for r in ref]))
+    for i, r in enumerate(ref):
+        assert torch.equal(target[i, :len(r[2])], r[2]) and int(target[i, len(r[2]):].abs().sum()) == 0
+    assert _lib.batch_sizes(caption_len) == [7, 6, 5, 5, 3, 2, 2]
+    # unsorted padded tensors -> the same batch
+    padded = torch.zeros(len(lens), 9, dtype=torch.long)
+    for i, d in enumerate(data):
+        padded[i, :lens[i]] = d[2]
+    feats = torch.stack([d[1] for d in data])
+    f2, c2, l2, perm = collate.sort_batch(feats, padded, torch.tensor(lens))
+    assert l2 == caption_len and torch.equal(f2, images) and torch.equal(c2, target)
+    restored = torch.empty_like(f2)
+    restored[perm] = f2
+    assert torch.equal(restored, feats)
+    with pytest.raises(RuntimeError):
+        collate.sort_batch(feats, padded, [4, 7, 4, 0, 7, 5, 1])
+    with pytest.raises(ValueError):
+        collate.sort_batch(feats, padded, [4, 7, 4, 2, 7, 5])
