@@ -75,9 +75,13 @@ def _worker(rank, world, port, kind, q):
         names = sorted(q_)
         grads = [q_[n].grad if q_[n].grad is not None else torch.zeros_like(q_[n]) for n in names]
         red = parallel.GradReducer()
-        red.reduce(grads[:2])                 # two buckets, as the engine issues them
-        red.reduce(grads[2:])
+        # three exchanges, as the engine issues them; reduce() hands back the reduced tensors (views of a
+        # symmetric bucket on CUDA, the inputs themselves on the CPU / gloo path) and the engine uses THOSE
+        out = red.reduce(grads[:2]) + red.reduce(grads[2:3]) + red.reduce(grads[3:])
         red.finish()
+        assert len(out) == len(grads) and all(o.shape == g_.shape for o, g_ in zip(out, grads))
+        assert red.slots([g_.shape for g_ in grads[:2]]) is None          # no symmetric buckets off the GPU
+        grads = out
         lt = loss.detach().clone()
         dist.all_reduce(lt)
         err = max(float((a - full_grads[n]).abs().max() / (full_grads[n].abs().max() + 1e-30))
