@@ -3,25 +3,31 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--workload lstm_train|gru_train|attn_gru_train|attn_lstm_train|beam3|beam5]
-                    [--dtype fp32|bf16]
+                    [--dtype fp32|bf16] [--no-extras]
 
 Default workload (BASELINE.json configs[1], the configuration the metric is quoted on that fits one
 GPU): LSTM/rnn_lstm.py decoder training step -- forward + cross-entropy + backward -- with
 E = H = 512, V = 10 000, batch 256 per GPU, caption length 20, L = 1, bf16 tensor-core arithmetic
 with fp32 state/accumulation, synthetic N(0,1) features of the ResNet head's output shape and
 random-init weights.  One "step" = one such iteration on one batch (5120 tokens per GPU).
-Metric: training tokens/s, whole job.  The other workloads are the remaining BASELINE configs
-(attention decoders on a 14x14x2048 grid, chain beam search), selectable for reporting.
+Metric: training tokens/s, whole job.  Without an explicit --workload the same run also measures
+the north-star's other two headline workloads at the same N (attention-GRU training, configs[2];
+beam-3 decoding, configs[4]) and reports them under "others" in the one JSON line.
 
 Our arm times the repo's public API (forward_loss + backward, or sentence_index) with CUDA events
-on the launching stream; `value` has the batch resident in HBM, `e2e` copies the step's inputs
-from pinned host memory and reads the result back every step.  Between timed steps a 256 MiB
-buffer is rewritten to flush the 126 MB L2 (outside the per-step event pairs).  N > 1: one process
-per GPU (torchrun), batch-sharded (weak scaling), gradients all-reduced over NCCL inside the timed
-step on a side stream overlapped with backward; time = max over ranks.
+on the launching stream; `value` has the batch resident in HBM, `e2e` copies every step's inputs
+from pinned host memory (double-buffered on a copy stream, so step i+1's copy runs under step i's
+kernels) and reads the result back every step.  Between timed steps a 256 MiB buffer is rewritten
+to flush the 126 MB L2 (outside the per-step event pairs).  N > 1: one process per GPU (torchrun),
+batch-sharded (weak scaling), gradients all-reduced inside the timed step on a side stream
+overlapped with backward; time = max over ranks.
 
-`--impl reference` times the reference algorithm on the host CPU cores (the oracle port: the
-reference is pure Python over torch CPU kernels and cannot travel to the GPU box).
+Reference bars, all the UNMODIFIED reference modules from baseline/_ref (baseline/reference.py):
+  * `--impl reference`: on the host CPU cores, same batch / lengths / steps as our arm (a config that
+    is too slow runs fewer STEPS, never fewer rows);
+  * `cpu_baseline` (our arm, N = 1): the same, a bounded number of steps;
+  * `gpu_reference` (our arm, N = 1): the same modules in torch-eager on the same B200 (cuDNN RNN +
+    cuBLAS + ATen), fp32 and under bf16 autocast -- the existing Blackwell kernels to beat.
 """
 import argparse
 import json
@@ -49,10 +55,11 @@ WORKLOADS = {
     "attn_lstm_train": ("attn_lstm", 512, 196, "rnn_attn_LSTM.py LSTM+soft attention train step fwd+bwd, "
                         "14x14x2048 grid, E=H=A=512 V=10000 B=512/GPU T=20 L=1"),
     "beam3": ("beam", 4096, 3, "rnn.py sentence_index(beam_size=3) chain beam search, GRU E=H=512 V=10000 L=1, "
-              "max_len 20, 4096 images/GPU per step"),
+              "4096 images/GPU per step"),
     "beam5": ("beam", 4096, 5, "rnn.py sentence_index(beam_size=5) chain beam search, GRU E=H=512 V=10000 L=1, "
-              "max_len 20, 4096 images/GPU per step"),
+              "4096 images/GPU per step"),
 }
+EXTRAS = ["attn_gru_train", "beam3"]      # measured beside the default workload
 
 
 def peaks():
@@ -73,6 +80,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
         self.t0 = self.t1 = None          # wall-clock window of the timed region
+        self.proc = None
 
     def run(self):
         try:
@@ -137,98 +145,180 @@ def train_flops(model, B, Pn):
     return 3.0 * (hoist + T * step + 2.0 * N * H * V) - 2.0 * B * Pn * C * A
 
 
-def cpu_reference(model, B, Pn, steps, warmup, budget_s=150.0):
-    """Reference algorithm on the host cores (oracle port, explicit-equation torch CPU ops, all
-    threads).  Training: forward + loss + backward; beam: rnn.py chain beam, batch 1 per call as the
-    reference requires.  Bounded: the per-step sample shrinks until K+W steps fit in budget_s."""
-    from oracle import showtell_oracle as O
+# ------------------------------------------------------------------------------------------------ reference arms
+def _reference_module(model):
+    """Unmodified reference module (baseline/_ref), reference default init under seed 1 (main.py:26-27)."""
+    from baseline import reference as R
+    torch.manual_seed(1)
+    return R, R.make_module(model, E, H, V, 1, C, A)
+
+
+def cpu_reference(model, B, Pn, steps, warmup, budget_s=150.0, max_len=25):
+    """The reference's own modules on the host cores, all threads, same batch as our arm.  Training:
+    forward + loss + backward as main.py:145-151 / main_attn.py:126-133; beam: rnn.py beam search, one image
+    per call as the reference requires (main.py:81-82), 25 steps as it hard-codes (rnn.py:39).  A slow
+    configuration runs fewer timed STEPS (never fewer rows): timing stops once budget_s is spent (>= 2 steps)."""
+    from baseline import reference as R
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    if not R.available():
+        return cpu_port(model, B, Pn, steps, warmup, budget_s)
+    R, net = _reference_module(model)
+    n_img = 16
+    feat, cap, lengths = make_batch(model, B if model != "beam" else n_img, Pn, 1)
+    with R.cpu_cuda_shim():
+        if model == "beam":
+            run = lambda: R.beam_captions(net, feat, Pn)
+            units = n_img
+        else:
+            run = lambda: R.train_step(net, model, feat, cap, lengths, 1.0)
+            units = B * T
+        t_start = time.perf_counter()
+        for _ in range(warmup):
+            run()
+            if time.perf_counter() - t_start > budget_s / 3:
+                break
+        done, t0 = 0, time.perf_counter()
+        while done < steps:
+            run()
+            done += 1
+            if done >= 2 and time.perf_counter() - t_start > budget_s:
+                break
+        dt = (time.perf_counter() - t0) / done
+    what = (f"{done} steps of {n_img} images, beam {Pn}, 25 tokens (rnn.py:39), one image per call" if model == "beam"
+            else f"{done} steps of {B}/{B} rows x {T} tokens (fwd+loss+bwd)")
+    return {"value": units / dt, "unit": "captions/s" if model == "beam" else "tokens/s", "cores": cores,
+            "kind": "reference", "ms_per_step": dt * 1e3, "steps_done": done,
+            "sample": what + f", unmodified reference modules (baseline/_ref), fp32, torch CPU {torch.__version__}"}
+
+
+def cpu_port(model, B, Pn, steps, warmup, budget_s):
+    """Fallback when baseline/_ref is absent (a checkout that never saw /root/reference): the oracle port."""
+    from oracle import showtell_oracle as O
+    cores = os.cpu_count() or 1
     m = build_model(model, "fp32")
     p = {k: v.detach().clone() for k, v in m.state_dict().items()}
-    feat, cap, lengths = make_batch(model, B if model != "beam" else 64, Pn, 1)
+    n_img = 16
+    feat, cap, lengths = make_batch(model, B if model != "beam" else n_img, Pn, 1)
     if model == "beam":
-        K = Pn
-        t0 = time.perf_counter()
-        with torch.no_grad():
-            O.rnn_beam_chain(p, feat[:1], K, T)
-        per = time.perf_counter() - t0
-        n = max(1, min(64, int(budget_s / max(per, 1e-3) / max(steps + warmup, 1))))
-        for _ in range(warmup):
+        def run():
             with torch.no_grad():
-                O.rnn_beam_chain(p, feat[:1], K, T)
-        t0 = time.perf_counter()
-        for s in range(steps):
-            with torch.no_grad():
-                for i in range(n):
-                    O.rnn_beam_chain(p, feat[i:i + 1], K, T)
-        dt = (time.perf_counter() - t0) / steps
-        return {"value": n / dt, "unit": "captions/s", "cores": cores, "kind": "port", "ms_per_step": dt * 1e3,
-                "sample": f"{steps} steps of {n} images, beam {K}, max_len {T}, one image per call (torch CPU {torch.__version__})"}
-    probe = min(B, 16)
-    t0 = time.perf_counter()
-    O.train_step(p, model, feat[:probe], cap[:probe], lengths[:probe])
-    per = (time.perf_counter() - t0) / probe
-    bs = B
-    while bs > probe and per * bs * (steps + warmup) > budget_s:
-        bs //= 2
-    f, c, l = feat[:bs], cap[:bs], lengths[:bs]
-    for _ in range(warmup):
-        O.train_step(p, model, f, c, l)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        O.train_step(p, model, f, c, l)
-    dt = (time.perf_counter() - t0) / steps
-    return {"value": bs * T / dt, "unit": "tokens/s", "cores": cores, "kind": "port", "ms_per_step": dt * 1e3,
-            "sample": f"{steps} steps of {bs}/{B} rows x {T} tokens (fwd+loss+bwd, fp32, torch CPU {torch.__version__})"}
+                for i in range(n_img):
+                    O.rnn_beam_chain(p, feat[i:i + 1], Pn, 25)
+        units = n_img
+    else:
+        run = lambda: O.train_step(p, model, feat, cap, lengths)
+        units = B * T
+    t_start = time.perf_counter()
+    for _ in range(min(warmup, 1)):
+        run()
+    done, t0 = 0, time.perf_counter()
+    while done < steps:
+        run()
+        done += 1
+        if done >= 2 and time.perf_counter() - t_start > budget_s:
+            break
+    dt = (time.perf_counter() - t0) / done
+    return {"value": units / dt, "unit": "captions/s" if model == "beam" else "tokens/s", "cores": cores,
+            "kind": "port", "ms_per_step": dt * 1e3, "steps_done": done,
+            "sample": f"{done} steps, oracle port (baseline/_ref not installed), fp32, torch CPU {torch.__version__}"}
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="lstm_train", choices=sorted(WORKLOADS))
-    ap.add_argument("--dtype", default="bf16", choices=["fp32", "bf16"])
-    ap.add_argument("--decode-gemm", default="tf32x3", choices=["fp32", "tf32x3"],
-                    help="beam workloads: nn.Linear products on CUDA cores (fp32) or fp32-accurate 3xTF32 tensor cores")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--features", default="fp32", choices=["fp32", "bf16"],
-                    help="attention workloads: dtype of the (B, 2048, P) grid handed to the decoder (reference: fp32)")
-    ap.add_argument("--optimizer", default="none", choices=["none", "sgd", "adam"],
-                    help="training workloads: also run the fused optimizer step (main.py:152) inside the timed step")
-    args = ap.parse_args()
-    model, B, Pn, desc = WORKLOADS[args.workload]
-    is_beam = model == "beam"
-    metric, unit = ("beam_captions_per_s", "captions/s") if is_beam else ("train_tokens_per_s", "tokens/s")
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    warmup = max(args.warmup, 3)
+def gpu_reference(model, B, Pn, dev, steps=10, warmup=3):
+    """The same unmodified reference modules in torch-eager on this B200 (cuDNN RNN + cuBLAS + ATen kernels:
+    the existing Blackwell path), inputs resident, CUDA-event timed.  fp32 = torch defaults (what the reference's
+    mains run); bf16 = the same modules under torch.autocast(bfloat16).  Beam: batch 1 per call, 25 steps."""
+    from baseline import reference as R
+    if not R.available():
+        return {"unavailable": "baseline/_ref not installed"}
+    out = {"what": "unmodified reference modules, torch-eager on the same GPU (torch %s, cuDNN %s)"
+           % (torch.__version__, torch.backends.cudnn.version())}
+    n_img = 8
+    feat, cap, lengths = make_batch(model, B if model != "beam" else n_img, Pn, 1)
+    feat = feat.to(dev)
+    cap = cap.to(dev) if cap is not None else None
+    for mode in ("fp32", "bf16_autocast"):
+        try:
+            R_, net = _reference_module(model)
+            net = net.to(dev)
+            ctx = torch.autocast("cuda", dtype=torch.bfloat16) if mode != "fp32" else torch.autocast("cuda", enabled=False)
+            if model == "beam":
+                run = lambda: R.beam_captions(net, feat, Pn)
+                units = n_img
+            else:
+                run = lambda: R.train_step(net, model, feat, cap, lengths, 1.0)
+                units = B * T
+            with ctx:
+                for _ in range(warmup):
+                    run()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    run()
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[mode] = {"value": units / (ms * 1e-3), "ms_per_step": ms, "steps": steps,
+                         "units_per_step": units}
+            del net
+            torch.cuda.empty_cache()
+        except Exception as exc:                      # a library path that does not exist for this dtype / shape
+            out[mode] = {"error": f"{type(exc).__name__}: {str(exc)[:160]}"}
+    out["unit"] = "captions/s" if model == "beam" else "tokens/s"
+    return out
 
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        w = min(args.warmup, 2)
-        r = cpu_reference(model, B, Pn, args.steps, w)
-        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": w, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": desc + " [reference algorithm on host CPU]"},
-                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line))
-        return 0
 
+# ------------------------------------------------------------------------------------------------------ our arm
+class Prefetcher:
+    """Double-buffered host->device input copies on a copy stream: while step i computes, step i+1's inputs
+    travel.  Every step's inputs are copied from pinned host memory inside the timed region."""
+
+    def __init__(self, host_tensors, dev):
+        self.host = [t.pin_memory() if t is not None else None for t in host_tensors]
+        self.dev_bufs = [[torch.empty_like(t, device=dev) if t is not None else None for t in self.host] for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ready = [None, None]
+        self.free = [None, None]
+        self.i = 0
+
+    def issue(self):
+        k = self.i & 1
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(self.copy_stream):
+            if self.free[k] is not None:
+                self.copy_stream.wait_event(self.free[k])          # the step that read this buffer is done with it
+            for h, d in zip(self.host, self.dev_bufs[k]):
+                if h is not None:
+                    d.copy_(h, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self.ready[k] = ev
+        self.i += 1
+        return k
+
+    def take(self, k):
+        torch.cuda.current_stream().wait_event(self.ready[k])
+        return self.dev_bufs[k]
+
+    def release(self, k):
+        ev = torch.cuda.Event()
+        ev.record()
+        self.free[k] = ev
+
+    def bytes_per_step(self):
+        return sum(t.numel() * t.element_size() for t in self.host if t is not None)
+
+
+def run_ours(name, args, steps, warmup, rank, world, local, want_refs):
     import torch.distributed as dist
     from showtell_b200 import _lib, ops, parallel
-
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    torch.cuda.set_device(local)
+    model, B, Pn, desc = WORKLOADS[name]
+    is_beam = model == "beam"
+    max_len = args.max_len if is_beam else T
+    if is_beam:
+        desc += f", max_len {max_len}"
+    metric, unit = ("beam_captions_per_s", "captions/s") if is_beam else ("train_tokens_per_s", "tokens/s")
     dev = torch.device(f"cuda:{local}")
     lib = _lib.load()
     dtype = "fp32" if is_beam else args.dtype
@@ -241,21 +331,19 @@ def main():
         from showtell_b200 import optim
         opt = optim.Adam(params, lr=1e-4) if args.optimizer == "adam" else optim.SGD(params, lr=1e-3, momentum=0.9)
     if world > 1 and not is_beam:
-        net.grad_reducer = parallel.GradReducer()          # NCCL all-reduce on a side stream
+        net.grad_reducer = parallel.GradReducer()          # gradient exchange on a side stream
     feat_h, cap_h, lengths = make_batch(model, B, Pn, 1 + rank)
     if args.features == "bf16" and model.startswith("attn"):
         feat_h = feat_h.bfloat16()
-    feat_p = feat_h.pin_memory()
-    cap_p = cap_h.pin_memory() if cap_h is not None else None
     feat_d = feat_h.to(dev)
     cap_d = cap_h.to(dev) if cap_h is not None else None
     units_per_step = (B if is_beam else B * T) * world
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    out_host = (torch.empty(B, T, dtype=torch.int64) if is_beam else torch.empty((), dtype=torch.float32)).pin_memory()
+    out_host = (torch.empty(B, max_len, dtype=torch.int64) if is_beam else torch.empty((), dtype=torch.float32)).pin_memory()
 
     def step(f, c):
         if is_beam:
-            return net.sentence_index(f, beam_size=Pn, max_len=T)                # utils.py:194
+            return net.sentence_index(f, beam_size=Pn, max_len=max_len)          # utils.py:194
         for p in params:
             p.grad = None
         if model.startswith("attn"):
@@ -267,12 +355,6 @@ def main():
         if opt is not None:
             opt.step()                                                            # main.py:152
         return loss
-
-    def step_e2e():
-        f = feat_p.to(dev, non_blocking=True)
-        c = cap_p.to(dev, non_blocking=True) if cap_p is not None else None
-        out = step(f, c)
-        out_host.copy_(out.detach(), non_blocking=True)
 
     def barrier():
         if world > 1:
@@ -297,6 +379,30 @@ def main():
             total = float(t)
         return total / K
 
+    def timed_e2e(K):
+        """K steps, each with its own H2D copy (prefetched one step ahead on the copy stream) and D2H read of the
+        result; one event pair around the whole pipelined region (the first copy is not hidden)."""
+        pf = Prefetcher([feat_h, cap_h], dev)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        k = pf.issue()
+        for i in range(K):
+            f, c = pf.take(k)
+            k_next = pf.issue() if i + 1 < K else None
+            out = step(f, c)
+            pf.release(k)
+            out_host.copy_(out.detach(), non_blocking=True)
+            k = k_next
+        e1.record()
+        barrier()
+        total = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([total], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total = float(t)
+        return total / K, pf.bytes_per_step()
+
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -304,90 +410,195 @@ def main():
         step(feat_d, cap_d)
     if sampler:
         sampler.t0 = time.time()
-    ms = timed(lambda: step(feat_d, cap_d), args.steps)     # CUDA-graph replay after the warm-up steps
+    ms = timed(lambda: step(feat_d, cap_d), steps)     # CUDA-graph replay after the warm-up steps
     # per-kernel event timing + launch count: the same step issued eagerly (graphs are bypassed while
     # ops.TIMER is set), right after the timed region, same process, same buffers
     ops.TIMER = ops.KernelTimer()
     l0 = lib.st_launch_count()
-    ksteps = max(3, min(args.steps, 10))
+    ksteps = max(3, min(steps, 10))
     timed(lambda: step(feat_d, cap_d), ksteps)
     launches = (lib.st_launch_count() - l0) // ksteps
     ksum = ops.TIMER.summary()
     ops.TIMER = None
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    timed_e2e(2)
+    ms_e2e, h2d = timed_e2e(steps)
     if sampler:
         sampler.t1 = time.time()
     clocks = sampler.finish() if sampler else None
 
+    line = None
     if rank == 0:
         pk = peaks()
-        kms = {k: round(v[1], 4) for k, v in ksum.items()}
-        if model.startswith("attn"):
-            # dominant per-step kernel: fused attention (HBM/L2-bound): reads att1 (B,P,A) + Fe (B,P,E)
-            esz = 2 if dtype == "bf16" else 4
-            bytes_step = B * Pn * (A + E) * esz
-            tags = [t for t in ("attn_fwd", "attn_bwd") if t in ksum]
-            k_ms = sum(ksum[t][1] for t in tags) / max(len(tags), 1)
-            ach = bytes_step / (k_ms * 1e-3) / 1e9 if tags else None
-            roof = {"bound": "hbm", "kernel": "fused attention step (fwd / bwd mean), algorithmic bytes = B*P*(A+E)*sizeof",
-                    "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"] if ach else None,
-                    "traffic": None, "peak_source": pk["src"] + " (copy bandwidth)"}
-        elif is_beam:
+        kms = {k: round(v[1] * v[0] / ksteps, 4) for k, v in ksum.items()}    # ms per STEP spent under each tag
+        kcalls = {k: v[0] // ksteps for k, v in ksum.items()}
+        esz = 2 if dtype == "bf16" else 4
+        vocab_flops = 2.0 * B * T * H * V
+        g = 3 if "gru" in model else 4
+        # algorithmic work per launch of each tagged kernel: (flops or bytes, bound)
+        work = {"vocab_fwd": (vocab_flops, "tensor"), "vocab_bwd": (2 * vocab_flops, "tensor"),
+                "vocab_dlogits": (vocab_flops, "tensor"), "vocab_dw": (vocab_flops, "tensor"),
+                "vocab_dx": (vocab_flops, "tensor"),
+                "ih_fwd": (2.0 * B * T * g * H * E, "tensor"), "ih_dx": (2.0 * B * T * g * H * E, "tensor"),
+                "ih_dw": (2.0 * B * T * g * H * E, "tensor"), "hh_dw": (2.0 * B * T * g * H * H, "tensor"),
+                "seq_fwd": (2.0 * B * T * g * H * H, "tensor"), "seq_bwd": (2.0 * B * T * g * H * H, "tensor"),
+                "att1_fwd": (2.0 * B * Pn * C * A, "tensor"), "fe_fwd": (2.0 * B * Pn * C * E, "tensor"),
+                "att1_dw": (2.0 * B * Pn * C * A, "tensor"), "embed_dw": (2.0 * B * Pn * C * E, "tensor"),
+                "attn_fwd": (float(B * Pn * (A + E) * esz), "hbm"), "attn_bwd": (float(B * Pn * (A + E) * esz), "hbm")}
+        table = {}
+        for k, (n, mean_ms) in ksum.items():
+            if k in work and mean_ms > 0:
+                w, bound = work[k]
+                ach = w / (mean_ms * 1e-3) / (1e12 if bound == "tensor" else 1e9)
+                peak = pk["tf_burst"] if bound == "tensor" else pk["hbm_gbs"]
+                table[k] = {"ms": round(mean_ms, 4), "launches_per_step": n // ksteps, "bound": bound,
+                            "achieved": round(ach, 1), "frac": round(ach / peak, 3)}
+        if is_beam:
             # whole decode loop: (1 + K (T-1)) dependent steps per caption, each {GRU gates 2*3H(E+H), vocabulary
             # projection 2HV} FLOPs.  The products run as 3xTF32 (three tf32 MMAs per fp32-accurate
             # product, tf32 at half the bf16 rate), so 1/6 of the bf16 peak is the most this arithmetic can reach.
-            flops_caption = (1 + Pn * (T - 1)) * (2.0 * 3 * H * (E + H) + 2.0 * H * V)
-            ach = flops_caption * units_per_step / world / (ms * 1e-3) / 1e12
+            flops_caption = (1 + Pn * (max_len - 1)) * (2.0 * 3 * H * (E + H) + 2.0 * H * V)
+            ach = flops_caption * B / (ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "decode loop (gate + vocabulary products per dependent step, "
                     + ("3xTF32 tensor-core" if args.decode_gemm == "tf32x3" else "fp32 CUDA-core") + " GEMMs), algorithmic "
                     "FLOPs = (1 + K(T-1)) * (2*3H(E+H) + 2HV) per caption; fp32-accurate 3xTF32 can reach at most peak/6",
                     "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"],
-                    "traffic": None, "peak_source": pk["src"] + " (bf16 cuBLAS sustained)"}
+                    "traffic": None, "peak_source": pk["src"] + " (bf16 cuBLAS sustained: kernel timed inside a long step)"}
         else:
-            # dominant kernels: the vocabulary-projection GEMMs (each 2*N*H*V FLOPs)
-            vocab_flops = 2.0 * B * T * H * V
-            tags = [t for t in ("vocab_fwd", "vocab_dlogits", "vocab_dw", "vocab_dx") if t in ksum]
-            k_ms = sum(ksum[t][1] for t in tags) / max(len(tags), 1)
-            ach = vocab_flops / (k_ms * 1e-3) / 1e12 if tags else None
-            roof = {"bound": "tensor", "kernel": "vocabulary projection GEMMs (" + " / ".join(tags) + ", mean; each 2*N*H*V FLOPs)",
-                    "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tf_sustained"] if ach else None, "traffic": None,
-                    "peak_source": pk["src"] + " (bf16 cuBLAS sustained)"}
+            # the dominant kernel = the tag with the largest share of the step; its own algorithmic work per launch
+            # over its event-timed mean duration, against the BURST peak (a kernel timed alone between events)
+            dom = max((k for k in kms if k in table), key=lambda k: kms[k], default=None)
+            if dom is not None:
+                d = table[dom]
+                roof = {"bound": d["bound"], "kernel": f"{dom} (largest share of the step: {kms[dom]:.3f} of {ms:.3f} ms, "
+                        f"{d['launches_per_step']} launch(es) per step)", "achieved": d["achieved"],
+                        "peak": pk["tf_burst"] if d["bound"] == "tensor" else pk["hbm_gbs"],
+                        "unit": "TFLOP/s" if d["bound"] == "tensor" else "GB/s", "frac": d["frac"], "traffic": None,
+                        "peak_source": pk["src"] + (" (bf16 cuBLAS burst: kernel timed alone)" if d["bound"] == "tensor"
+                                                    else " (copy bandwidth)")}
+            else:
+                roof = {"bound": "tensor", "kernel": None, "achieved": None, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                        "frac": None, "traffic": None, "peak_source": pk["src"]}
+            roof["step_flops"] = train_flops(model, B, Pn)
+            roof["step_tflops"] = roof["step_flops"] / (ms * 1e-3) / 1e12
+            roof["step_frac_of_sustained_peak"] = roof["step_tflops"] / pk["tf_sustained"]
         tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tp):                         # measured once per round under ncu --set full
-            ent = json.load(open(tp)).get(args.workload)
+            ent = json.load(open(tp)).get(name)
             if ent and dtype == "bf16":
                 roof["traffic"] = ent["traffic_bytes_per_launch"]
                 roof["traffic_source"] = ent["source"]
-        roof["kernels_ms"] = kms
-        if not is_beam:
-            roof["step_flops"] = train_flops(model, B, Pn)
-            roof["step_tflops"] = roof["step_flops"] / (ms * 1e-3) / 1e12
-        h2d = feat_p.numel() * feat_p.element_size() + (cap_p.numel() * 8 if cap_p is not None else 0)
+        roof["kernels_ms_per_step"] = kms
+        roof["kernels"] = table
         line = {"metric": metric, "value": units_per_step / (ms * 1e-3), "unit": unit, "n_gpus": world,
-                "steps": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+                "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32" if dtype == "fp32" else "bf16",
                 "data": "synthetic",
-                "config": {"workload": desc, "global_batch": B * world, "seq_len": T, "parallelism": f"dp{world}",
+                "config": {"workload": desc, "global_batch": B * world, "seq_len": max_len, "parallelism": f"dp{world}",
                            "l2": "flushed between timed steps (256 MiB fill, outside the event pairs)",
                            "launch": "whole step replayed as one CUDA graph (captured on the 3rd identical step)",
                            "features": ("bf16 grid (autocast trunk)" if feat_h.dtype == torch.bfloat16 else "fp32 (as the reference's encoder emits them)"),
                            "optimizer": "excluded" if opt is None else args.optimizer + " step (fused, one launch) included"},
                 "e2e": {"value": units_per_step / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": out_host.numel() * out_host.element_size(), "ms_per_step": ms_e2e},
+                        "d2h_bytes_per_step": out_host.numel() * out_host.element_size(), "ms_per_step": ms_e2e,
+                        "how": "double-buffered H2D on a copy stream, one event pair around all steps"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
-        if world == 1 and not args.no_cpu_baseline:
+    # free this workload's device memory before the reference legs / the next workload
+    net.__dict__.pop("_step_graphs", None)
+    del net, params, flush, feat_d, cap_d
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and want_refs:
+        line["gpu_reference"] = gpu_reference(model, B, Pn, dev)
+        g32 = line["gpu_reference"].get("fp32", {}).get("value")
+        g16 = line["gpu_reference"].get("bf16_autocast", {}).get("value")
+        best = max([x for x in (g32, g16) if x], default=None)
+        line["gpu_reference"]["ours_over_best_eager"] = (line["value"] / best) if best else None
+        if not args.no_cpu_baseline:
             r = cpu_reference(model, B, Pn, 5, 1, budget_s=25.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="bf16", choices=["fp32", "bf16"])
+    ap.add_argument("--decode-gemm", default="tf32x3", choices=["fp32", "tf32x3"],
+                    help="beam workloads: nn.Linear products on CUDA cores (fp32) or fp32-accurate 3xTF32 tensor cores")
+    ap.add_argument("--max-len", type=int, default=20, help="beam workloads: caption length (BASELINE configs[4]: 20; "
+                    "the reference hard-codes 25)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="measure only the main workload")
+    ap.add_argument("--features", default="fp32", choices=["fp32", "bf16"],
+                    help="attention workloads: dtype of the (B, 2048, P) grid handed to the decoder (reference: fp32)")
+    ap.add_argument("--optimizer", default="none", choices=["none", "sgd", "adam"],
+                    help="training workloads: also run the fused optimizer step (main.py:152) inside the timed step")
+    args = ap.parse_args()
+    main_wl = args.workload or "lstm_train"
+    extras = [] if (args.workload is not None or args.no_extras) else EXTRAS
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        out = None
+        for name in [main_wl] + extras:
+            model, B, Pn, desc = WORKLOADS[name]
+            is_beam = model == "beam"
+            first = out is None
+            # same batch, same steps, same warm-up as our arm for the headline workload; the slow extras are
+            # bounded by time (fewer steps, never fewer rows)
+            r = cpu_reference(model, B, Pn, args.steps if first else 3, warmup if first else 1,
+                              budget_s=240.0 if first else 60.0)
+            metric, unit = ("beam_captions_per_s", "captions/s") if is_beam else ("train_tokens_per_s", "tokens/s")
+            line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
+                    "steps": r["steps_done"], "warmup": warmup if first else 1, "ms_per_step": r["ms_per_step"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": desc + (", max_len 25 (hard-coded, rnn.py:39), one image per call"
+                                                   if is_beam else "") + " [reference modules on host CPU]",
+                               "global_batch": B if not is_beam else 16, "seq_len": 25 if is_beam else T,
+                               "parallelism": "host cpu"},
+                    "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                    "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    "gpu_launches": 0}
+            if first:
+                out = line
+            else:
+                out.setdefault("others", {})[name] = line
+        print(json.dumps(out))
+        return 0
+
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    want_refs = not args.no_gpu_reference
+    line = run_ours(main_wl, args, args.steps, warmup, rank, world, local, want_refs)
+    for name in extras:
+        # fewer timed steps for the extras (a beam "step" is 58 dependent decode steps over 4096 images)
+        k = args.steps if not name.startswith("beam") else max(3, min(args.steps, 5))
+        try:
+            extra = run_ours(name, args, k, warmup, rank, world, local, want_refs)
+        except Exception as exc:
+            extra = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+        if rank == 0:
+            line.setdefault("others", {})[name] = extra
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
-        # Tear down in dependency order: captured step graphs hold NCCL work, so they go first; a
-        # communicator teardown that still stalls must not keep torchrun alive (watchdog exit).
+        # A communicator teardown that stalls must not keep torchrun alive (watchdog exit).
         sys.stdout.flush()
         threading.Timer(20.0, lambda: os._exit(0)).start()
-        net.__dict__.pop("_step_graphs", None)
         import gc
         gc.collect()
         torch.cuda.synchronize()

@@ -120,16 +120,22 @@ int st_vocab_ce_bwd(int M, int V, int H, const void* Hs, int ldh, const void* Wv
  *                          with_feature=0: emb[caption[b, t]]                          (rnn_attn.py:70)
  * caption is int64 (B, T_cap) row-major.  Only the first E columns of each X row are written.
  * ------------------------------------------------------------------------------------------ */
-int st_pack_inputs(float* X, int ldx, const float* emb, int E, const float* feature,
+/*
+ * Token ids outside [0, V) never index out of bounds: the access is clamped and the id is reported through
+ * st_token_error (the reference's nn.Embedding / CrossEntropyLoss device-assert on such an id). */
+int st_pack_inputs(float* X, int ldx, const float* emb, int E, int V, const float* feature,
                    const int64_t* caption, int T_cap, int with_feature, int nsteps,
                    const int* batch_sizes_host, st_stream_t stream);
+/* Number of out-of-range token ids the packing kernels have met since the last clear (host-mapped status word,
+ * no synchronisation: a step still in flight is seen by a later call); *first_bad_id = the first such id. */
+int st_token_error(int64_t* first_bad_id, int clear);
 /* Backward of the above: dEmb[token] += dX row (atomic), dfeature[b] = dX row (0,b).
  * dEmb must be zero-initialised (or hold the running gradient); dfeature may be NULL. */
-int st_pack_inputs_bwd(const float* dX, int ldx, float* dEmb, int E, float* dfeature,
+int st_pack_inputs_bwd(const float* dX, int ldx, float* dEmb, int E, int V, float* dfeature,
                        const int64_t* caption, int T_cap, int with_feature, int nsteps,
                        const int* batch_sizes_host, st_stream_t stream);
 /* Packed targets for the loss: out[n=(t,b)] = caption[b,t]  (main.py:145). */
-int st_pack_targets(int64_t* out, const int64_t* caption, int T_cap, int nsteps,
+int st_pack_targets(int64_t* out, const int64_t* caption, int T_cap, int V, int nsteps,
                     const int* batch_sizes_host, st_stream_t stream);
 
 /* dst[i, :width] = table[idx[i * idx_stride], :]  (nn.Embedding lookup of the decode loops, rnn.py:53). */

@@ -52,9 +52,10 @@ _SIGS = {
     "st_allreduce_sum_f32": (_I, [C.POINTER(C.c_void_p), _P, C.POINTER(C.c_void_p), _I, _I, _L, _I, _P]),
     "st_vocab_ce_fwd": (_I, [_I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "st_vocab_ce_bwd": (_I, [_I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _F, _P, _I, _P, _I, _P]),
-    "st_pack_inputs": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _IP, _P]),
-    "st_pack_inputs_bwd": (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _IP, _P]),
-    "st_pack_targets": (_I, [_P, _P, _I, _I, _IP, _P]),
+    "st_pack_inputs": (_I, [_P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _IP, _P]),
+    "st_pack_inputs_bwd": (_I, [_P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _IP, _P]),
+    "st_pack_targets": (_I, [_P, _P, _I, _I, _I, _IP, _P]),
+    "st_token_error": (_I, [C.POINTER(_L), _I]),
     "st_gather_rows": (_I, [_P, _I, _P, _I, _P, _I, _I, _P]),
     "st_rowsum_bf16": (_I, [_P, _P, _I, _I, _I, _P]),
     "st_colsum": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
@@ -129,6 +130,16 @@ def check(status, what=""):
     if status in (-2, -4):
         raise RuntimeError(msg)
     raise ValueError(msg)
+
+
+def raise_token_error():
+    """IndexError if a packing kernel has met a token id outside [0, vocab_size) (checked at call boundaries:
+    the step that contained it may have been issued one call earlier; the access itself was clamped)."""
+    bad = _L(0)
+    n = load().st_token_error(C.byref(bad), 1)
+    if n:
+        raise IndexError(f"showtell_b200: {n} caption token id(s) outside [0, vocab_size) in a previous step "
+                         f"(first: {bad.value}); nn.Embedding / CrossEntropyLoss of the reference assert on this")
 
 
 def ptr(t, dtype=None):

@@ -369,7 +369,7 @@ class AttnLossFn(torch.autograd.Function):
 
         def body(feat, capt):
             Hs, alphas, sv = attn_forward(mode, P, kind, L, feat, capt, bs, need)
-            target = ops.pack_targets(capt, bs)
+            target = ops.pack_targets(capt, bs, P["linear.weight"].shape[0])
             gout = red.slots([P["linear.weight"].shape, P["linear.bias"].shape]) if (red is not None and need) else None
             loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, dt, need, gout=gout)
             pen_sum, Gpen = ops.attn_penalty(sv["S"], coef)
@@ -404,7 +404,7 @@ class AttnLossFn(torch.autograd.Function):
         key = ("attn", mode, kind, L, tuple(bs), tuple(f.shape), str(f.dtype), tuple(cap.shape), need, dt, db, float(alpha_c),
                tuple(p.data_ptr() for p in params))
         loss, alphas, ctx.grads = graphs.run(mod, key, body, (f, cap))
-        ctx.names = names
+        ctx.names, ctx.mod, ctx.ticket = names, mod, graphs.ticket(mod)
         loss, alphas = loss.clone(), alphas.clone()
         ctx.mark_non_differentiable(alphas)
         return loss, alphas
@@ -413,4 +413,5 @@ class AttnLossFn(torch.autograd.Function):
     def backward(ctx, g, _dalphas):
         if ctx.grads is None:
             raise RuntimeError("forward_loss was run without grad enabled")
+        graphs.check_ticket(ctx.mod, ctx.ticket)
         return (None,) * 7 + tuple(ops.scale_multi([ctx.grads[n] for n in ctx.names], g))   # chain rule, one launch

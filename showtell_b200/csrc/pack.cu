@@ -21,18 +21,58 @@ __device__ __forceinline__ void row_to_tb(const StepTable& tab, int n, int& t, i
   b = n - tab.off[lo];
 }
 
+// Token ids index the embedding table and the logits row: an id outside [0, V) (vocabulary / checkpoint
+// mismatch, a bad padding value) must not become an out-of-bounds access.  The reference's nn.Embedding /
+// CrossEntropyLoss device-assert in that case; here the id is clamped for the access and reported through a
+// host-mapped status word {count, first bad id} that the host side reads at its next call (st_token_error).
+__device__ __forceinline__ int64_t checked_token(int64_t tok, int V, long long* status) {
+  if (tok >= 0 && tok < V) return tok;
+  if (status) {
+    if (atomicAdd_system(reinterpret_cast<unsigned long long*>(status), 1ull) == 0ull) status[1] = tok;
+    __threadfence_system();
+  }
+  return tok < 0 ? 0 : V - 1;
+}
+
+long long* g_token_status_host = nullptr;   // pinned, mapped; [0] = number of bad ids seen, [1] = the first one
+long long* g_token_status_dev = nullptr;
+
+long long* token_status() {
+  if (!g_token_status_dev) {
+    long long* h = nullptr;
+    if (cudaHostAlloc(&h, 2 * sizeof(long long), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;                         // no status word: ids are still clamped
+    }
+    h[0] = h[1] = 0;
+    long long* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) {
+      cudaGetLastError();
+      cudaFreeHost(h);
+      return nullptr;
+    }
+    g_token_status_host = h;
+    g_token_status_dev = d;
+  }
+  return g_token_status_dev;
+}
+
 __global__ void pack_inputs_kernel(const __grid_constant__ StepTable tab, float* __restrict__ X, int ldx,
-                                   const float* __restrict__ emb, int E,
+                                   const float* __restrict__ emb, int E, int V,
                                    const float* __restrict__ feature,
-                                   const int64_t* __restrict__ caption, int T_cap, int with_feature) {
+                                   const int64_t* __restrict__ caption, int T_cap, int with_feature,
+                                   long long* status) {
   const int n = blockIdx.x;
   int t, b;
   row_to_tb(tab, n, t, b);
   const float* src;
-  if (with_feature) {
-    src = (t == 0) ? feature + (size_t)b * E : emb + (size_t)caption[(size_t)b * T_cap + (t - 1)] * E;
+  if (with_feature && t == 0) {
+    src = feature + (size_t)b * E;
   } else {
-    src = emb + (size_t)caption[(size_t)b * T_cap + t] * E;
+    int64_t tok = caption[(size_t)b * T_cap + (with_feature ? t - 1 : t)];
+    if (threadIdx.x == 0) checked_token(tok, V, status);
+    tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
+    src = emb + (size_t)tok * E;
   }
   float* dst = X + (size_t)n * ldx;
   for (int e = threadIdx.x; e < E; e += blockDim.x) dst[e] = src[e];
@@ -42,7 +82,7 @@ __global__ void pack_inputs_bwd_kernel(const __grid_constant__ StepTable tab, co
                                        int ldx, float* __restrict__ dEmb, int E,
                                        float* __restrict__ dfeature,
                                        const int64_t* __restrict__ caption, int T_cap,
-                                       int with_feature) {
+                                       int with_feature, int V) {
   const int n = blockIdx.x;
   int t, b;
   row_to_tb(tab, n, t, b);
@@ -54,18 +94,20 @@ __global__ void pack_inputs_bwd_kernel(const __grid_constant__ StepTable tab, co
     }
     return;
   }
-  const int64_t tok = caption[(size_t)b * T_cap + (with_feature ? t - 1 : t)];
+  int64_t tok = caption[(size_t)b * T_cap + (with_feature ? t - 1 : t)];
+  tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);      // reported by the forward pack (same captions)
   float* dst = dEmb + (size_t)tok * E;
   for (int e = threadIdx.x; e < E; e += blockDim.x) atomicAdd(dst + e, src[e]);
 }
 
 __global__ void pack_targets_kernel(const __grid_constant__ StepTable tab, int64_t* __restrict__ out,
-                                    const int64_t* __restrict__ caption, int T_cap, int N) {
+                                    const int64_t* __restrict__ caption, int T_cap, int N, int V,
+                                    long long* status) {
   int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   int t, b;
   row_to_tb(tab, n, t, b);
-  out[n] = caption[(size_t)b * T_cap + t];
+  out[n] = checked_token(caption[(size_t)b * T_cap + t], V, status);
 }
 
 __device__ __forceinline__ float to_f32(float v) { return v; }
@@ -177,7 +219,7 @@ __global__ void __launch_bounds__(256) scale_multi_kernel(const ScaleTable tab, 
 
 extern "C" {
 
-int st_pack_inputs(float* X, int ldx, const float* emb, int E, const float* feature,
+int st_pack_inputs(float* X, int ldx, const float* emb, int E, int V, const float* feature,
                    const int64_t* caption, int T_cap, int with_feature, int nsteps,
                    const int* batch_sizes_host, st_stream_t stream) {
   using namespace st;
@@ -185,38 +227,50 @@ int st_pack_inputs(float* X, int ldx, const float* emb, int E, const float* feat
   ST_TRY(make_step_table(tab, nsteps, batch_sizes_host));
   ST_REQUIRE(X && emb && caption, ST_ERR_NULL, "st_pack_inputs: NULL pointer");
   ST_REQUIRE(!with_feature || feature, ST_ERR_NULL, "st_pack_inputs: feature is NULL");
-  ST_REQUIRE(E >= 1 && ldx >= E, ST_ERR_BAD_SHAPE, "st_pack_inputs: E=%d ldx=%d", E, ldx);
+  ST_REQUIRE(E >= 1 && ldx >= E && V >= 1, ST_ERR_BAD_SHAPE, "st_pack_inputs: E=%d ldx=%d V=%d", E, ldx, V);
   ST_REQUIRE(nsteps <= T_cap + (with_feature ? 1 : 0), ST_ERR_BAD_SHAPE,
              "st_pack_inputs: nsteps=%d exceeds caption length %d", nsteps, T_cap);
-  pack_inputs_kernel<<<tab.off[nsteps], 128, 0, as_stream(stream)>>>(tab, X, ldx, emb, E, feature,
-                                                                     caption, T_cap, with_feature);
+  pack_inputs_kernel<<<tab.off[nsteps], 128, 0, as_stream(stream)>>>(tab, X, ldx, emb, E, V, feature,
+                                                                     caption, T_cap, with_feature, token_status());
   ST_LAUNCH_TRY("pack_inputs_kernel");
   return ST_OK;
 }
 
-int st_pack_inputs_bwd(const float* dX, int ldx, float* dEmb, int E, float* dfeature,
+int st_pack_inputs_bwd(const float* dX, int ldx, float* dEmb, int E, int V, float* dfeature,
                        const int64_t* caption, int T_cap, int with_feature, int nsteps,
                        const int* batch_sizes_host, st_stream_t stream) {
   using namespace st;
   StepTable tab;
   ST_TRY(make_step_table(tab, nsteps, batch_sizes_host));
   ST_REQUIRE(dX && dEmb && caption, ST_ERR_NULL, "st_pack_inputs_bwd: NULL pointer");
-  ST_REQUIRE(E >= 1 && ldx >= E, ST_ERR_BAD_SHAPE, "st_pack_inputs_bwd: E=%d ldx=%d", E, ldx);
+  ST_REQUIRE(E >= 1 && ldx >= E && V >= 1, ST_ERR_BAD_SHAPE, "st_pack_inputs_bwd: E=%d ldx=%d V=%d", E, ldx, V);
   pack_inputs_bwd_kernel<<<tab.off[nsteps], 128, 0, as_stream(stream)>>>(
-      tab, dX, ldx, dEmb, E, dfeature, caption, T_cap, with_feature);
+      tab, dX, ldx, dEmb, E, dfeature, caption, T_cap, with_feature, V);
   ST_LAUNCH_TRY("pack_inputs_bwd_kernel");
   return ST_OK;
 }
 
-int st_pack_targets(int64_t* out, const int64_t* caption, int T_cap, int nsteps,
+int st_token_error(int64_t* first_bad_id, int clear) {
+  long long* h = st::g_token_status_host;
+  if (!h) return 0;
+  const long long n = __atomic_load_n(&h[0], __ATOMIC_ACQUIRE);
+  if (first_bad_id) *first_bad_id = (int64_t)h[1];
+  if (clear && n) {
+    h[1] = 0;
+    __atomic_store_n(&h[0], 0, __ATOMIC_RELEASE);
+  }
+  return n > 0x7fffffff ? 0x7fffffff : (int)n;
+}
+
+int st_pack_targets(int64_t* out, const int64_t* caption, int T_cap, int V, int nsteps,
                     const int* batch_sizes_host, st_stream_t stream) {
   using namespace st;
   StepTable tab;
   ST_TRY(make_step_table(tab, nsteps, batch_sizes_host));
   ST_REQUIRE(out && caption, ST_ERR_NULL, "st_pack_targets: NULL pointer");
-  ST_REQUIRE(nsteps <= T_cap, ST_ERR_BAD_SHAPE, "st_pack_targets: nsteps=%d > T_cap=%d", nsteps, T_cap);
+  ST_REQUIRE(nsteps <= T_cap && V >= 1, ST_ERR_BAD_SHAPE, "st_pack_targets: nsteps=%d > T_cap=%d (V=%d)", nsteps, T_cap, V);
   const int N = tab.off[nsteps];
-  pack_targets_kernel<<<(N + 255) / 256, 256, 0, as_stream(stream)>>>(tab, out, caption, T_cap, N);
+  pack_targets_kernel<<<(N + 255) / 256, 256, 0, as_stream(stream)>>>(tab, out, caption, T_cap, N, V, token_status());
   ST_LAUNCH_TRY("pack_targets_kernel");
   return ST_OK;
 }

@@ -246,7 +246,7 @@ class BaseLossFn(torch.autograd.Function):
 
         def body(feat, cap):
             Hs, layers = base_forward(mode, P, kind, L, feat, cap, bs, need)
-            target = ops.pack_targets(cap, bs)
+            target = ops.pack_targets(cap, bs, P["linear.weight"].shape[0])
             gout = red.slots([P["linear.weight"].shape, P["linear.bias"].shape]) if (red is not None and need) else None
             loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, denom, need, gout=gout)
             dfeat = None
@@ -278,13 +278,14 @@ class BaseLossFn(torch.autograd.Function):
         key = ("base", mode, kind, L, tuple(bs), tuple(feature_c.shape), tuple(caption_c.shape), need, want_dfeat,
                denom, tuple(p.data_ptr() for p in params))
         loss, ctx.grads, ctx.dfeat = graphs.run(mod, key, body, (feature_c, caption_c))
-        ctx.names = names
+        ctx.names, ctx.mod, ctx.ticket = names, mod, graphs.ticket(mod)
         return loss.clone()
 
     @staticmethod
     def backward(ctx, g):
         if ctx.grads is None:
             raise RuntimeError("forward_loss was run without grad enabled")
+        graphs.check_ticket(ctx.mod, ctx.ticket)
         src = [ctx.grads[n] for n in ctx.names]
         want_dfeat = ctx.dfeat is not None and ctx.needs_input_grad[1]
         out = ops.scale_multi(src + ([ctx.dfeat] if want_dfeat else []), g)       # chain rule, one launch

@@ -12,8 +12,14 @@ graph's static loss / gradient tensors.
 A gradient reducer (parallel.GradReducer: NCCL all-reduces on a side stream) is captured with the
 step -- the side stream forks from and joins the capture stream through events, NCCL collectives
 are graph-capturable -- so data-parallel ranks replay {kernels + all-reduces} as one graph each.
-Not used while `ops.TIMER` records per-kernel events or when `module.use_cuda_graphs` is False.  One loss per
-module may be outstanding: a second forward_loss before backward() overwrites the static gradients.
+Not used while `ops.TIMER` records per-kernel events or when `module.use_cuda_graphs` is False.
+
+One loss per module may be outstanding: the gradients a replayed step (or a data-parallel step, whose
+reduced gradients are views of the symmetric bucket) hands to autograd live in STATIC storage that the
+next forward_loss of the same module overwrites.  Every forward_loss takes a ticket (`ticket(mod)`), and
+backward() checks it (`check_ticket`): using a loss whose gradients have since been overwritten -- gradient
+accumulation over two losses, a validation forward_loss between forward and backward -- raises instead of
+silently returning the newer step's gradients.  ("One loss at a time".)
 """
 import torch
 
@@ -29,6 +35,27 @@ class _Entry:
         self.seen, self.graph, self.static_in, self.out, self.failed = 0, None, None, None, False
 
 
+def ticket(mod):
+    """Called by forward_loss after its gradients exist: invalidates the tickets of earlier losses.  Returns
+    (generation, static): static = the gradients live in storage the next step reuses (graph replay, or the
+    symmetric buckets of a gradient reducer)."""
+    static = bool(mod.__dict__.get("_last_run_static", False)) or getattr(mod, "grad_reducer", None) is not None
+    gen = mod.__dict__.get("_loss_generation", 0) + (1 if static else 0)     # eager single-GPU steps own fresh tensors
+    mod.__dict__["_loss_generation"] = gen
+    return gen, static
+
+
+def check_ticket(mod, tk):
+    """Called by backward(): raises if a later forward_loss of `mod` has overwritten the static gradients."""
+    gen, static = tk
+    if static and mod.__dict__.get("_loss_generation", 0) != gen:
+        raise RuntimeError(
+            "showtell_b200: backward() of a forward_loss result whose gradients were overwritten by a later "
+            "forward_loss call on the same module (the fused step keeps ONE set of static gradients per module: "
+            "call backward() before the next forward_loss, or use forward() + nn.CrossEntropyLoss for "
+            "several outstanding losses)")
+
+
 def enabled(mod):
     return getattr(mod, "use_cuda_graphs", True) and ops.TIMER is None
 
@@ -36,6 +63,7 @@ def enabled(mod):
 def run(mod, key, body, inputs):
     """body(*inputs) -> pytree of tensors (dict / tuple / tensor / None).  Runs it eagerly, or via a
     captured graph once `key` has been seen often enough."""
+    mod.__dict__["_last_run_static"] = False
     if not enabled(mod):
         return body(*inputs)
     cache = mod.__dict__.setdefault("_step_graphs", {})
@@ -48,6 +76,7 @@ def run(mod, key, body, inputs):
         for dst, src in zip(e.static_in, inputs):
             dst.copy_(src, non_blocking=True)
         e.graph.replay()
+        mod.__dict__["_last_run_static"] = True
         return e.out
     e.seen += 1
     if e.failed or e.seen <= _EAGER_CALLS_BEFORE_CAPTURE:
@@ -60,6 +89,7 @@ def run(mod, key, body, inputs):
             out = body(*static_in)
         e.graph, e.static_in, e.out = graph, static_in, out
         graph.replay()                            # results of THIS call
+        mod.__dict__["_last_run_static"] = True
         return e.out
     except Exception as exc:                      # capture unsupported for this sequence: stay eager
         e.failed = True

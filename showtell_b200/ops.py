@@ -105,9 +105,11 @@ def pack_inputs(emb, feature, caption, bs, with_feature, width=None):
     """Packed inputs (N, width >= E); only the first E columns are written (attention models use
     width = 2E and let the attention kernel fill the other half)."""
     lib = _lib.load()
+    _lib.raise_token_error()
     N, E = sum(bs), emb.shape[1]
     X = torch.empty(N, width or E, dtype=F32, device=emb.device)
-    check(lib.st_pack_inputs(ptr(X, F32), X.shape[1], ptr(emb, F32), E, ptr(feature, F32) if with_feature else None,
+    check(lib.st_pack_inputs(ptr(X, F32), X.shape[1], ptr(emb, F32), E, emb.shape[0],
+                             ptr(feature, F32) if with_feature else None,
                              ptr(caption, I64), caption.shape[1], int(with_feature), len(bs),
                              int_array(bs), stream_ptr()), "st_pack_inputs")
     return X
@@ -115,16 +117,17 @@ def pack_inputs(emb, feature, caption, bs, with_feature, width=None):
 
 def pack_inputs_bwd(dX, dEmb, dfeature, caption, bs, with_feature):
     lib = _lib.load()
-    check(lib.st_pack_inputs_bwd(ptr(dX, F32), dX.stride(0), ptr(dEmb, F32), dEmb.shape[1],
+    check(lib.st_pack_inputs_bwd(ptr(dX, F32), dX.stride(0), ptr(dEmb, F32), dEmb.shape[1], dEmb.shape[0],
                                  ptr(dfeature, F32), ptr(caption, I64), caption.shape[1],
                                  int(with_feature), len(bs), int_array(bs), stream_ptr()),
           "st_pack_inputs_bwd")
 
 
-def pack_targets(caption, bs):
+def pack_targets(caption, bs, V):
+    """Packed targets; ids outside [0, V) are clamped and reported (st_token_error)."""
     lib = _lib.load()
     out = torch.empty(sum(bs), dtype=I64, device=caption.device)
-    check(lib.st_pack_targets(ptr(out, I64), ptr(caption, I64), caption.shape[1], len(bs), int_array(bs),
+    check(lib.st_pack_targets(ptr(out, I64), ptr(caption, I64), caption.shape[1], int(V), len(bs), int_array(bs),
                               stream_ptr()), "st_pack_targets")
     return out
 

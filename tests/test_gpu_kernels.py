@@ -80,7 +80,7 @@ def test_pack_inputs_targets_and_bwd(dev):
         assert rel_err(dEmb, ref_e) < 1e-6
         if with_feature:
             assert rel_err(dfeat, ref_f) < 1e-7
-    tg = ops.pack_targets(cap.to(dev), bs).cpu()
+    tg = ops.pack_targets(cap.to(dev), bs, V).cpu()
     ref = torch.nn.utils.rnn.pack_padded_sequence(cap, lengths, batch_first=True)[0]
     assert torch.equal(tg, ref)
 
@@ -92,8 +92,43 @@ def test_unsorted_lengths_raise():
     lib = _lib.load()
     import ctypes as C
     bad = _lib.int_array([2, 3])
-    st = lib.st_pack_targets(C.c_void_p(8), C.c_void_p(8), 4, 2, bad, None)
+    st = lib.st_pack_targets(C.c_void_p(8), C.c_void_p(8), 4, 10, 2, bad, None)
     assert st == -2 and "non-increasing" in _lib.last_error()
+
+
+def test_bad_token_ids_are_reported_not_dereferenced(dev):
+    """An id outside [0, V) (the reference's nn.Embedding / CrossEntropyLoss device-assert on it) is clamped for the
+    access and raises IndexError at the next call boundary; the gradient scatter stays inside dEmb."""
+    from showtell_b200 import _lib, ops
+    from showtell_b200.rnn import RNN
+    V, E, B, T = 11, 8, 3, 4
+    emb = torch.randn(V, E, device=dev)
+    cap = torch.tensor([[1, 5, V + 7, 2], [1, -3, 2, 0], [1, 2, 0, 0]], device=dev)
+    bs = _lib.batch_sizes([4, 3, 2])
+    _lib.load().st_token_error(None, 1)
+    X = ops.pack_inputs(emb, None, cap, bs, False)
+    torch.cuda.synchronize()
+    assert torch.equal(X[bs[0] + bs[1]], emb[V - 1]) and torch.equal(X[bs[0] + 1], emb[0])     # clamped rows
+    with pytest.raises(IndexError, match="outside"):
+        ops.pack_inputs(emb, None, cap, bs, False)
+    tg = ops.pack_targets(cap, bs, V)
+    torch.cuda.synchronize()
+    assert int(tg.min()) >= 0 and int(tg.max()) < V
+    dEmb = torch.zeros(V + 64, E, device=dev)[:V]                   # guard rows behind the table stay zero
+    ops.pack_inputs_bwd(torch.ones(sum(bs), E, device=dev), dEmb, None, cap, bs, False)
+    torch.cuda.synchronize()
+    assert float(dEmb.sum()) == sum(bs) * E
+    with pytest.raises(IndexError):
+        _lib.raise_token_error()
+    _lib.raise_token_error()                                         # cleared
+    # through the module: the step after the bad one raises
+    m = RNN(E, 8, V, 1).to(dev)
+    feat = torch.randn(B, E, device=dev)
+    m.forward_loss(feat, cap, [4, 3, 2]).backward()
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError):
+        m.forward_loss(feat, cap.clamp(0, V - 1), [4, 3, 2])
+    m.forward_loss(feat, cap.clamp(0, V - 1), [4, 3, 2]).backward()
 
 
 @pytest.mark.parametrize("rows,cols", [(1, 1), (300, 37), (1000, 130)])

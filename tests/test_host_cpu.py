@@ -64,6 +64,20 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f
+                assert not re.search(r"^\s*(from|import)\s+baseline", src, re.M), f     # the reference arm is bench / test only
+
+
+def test_reference_install_is_verbatim():
+    """baseline/_ref holds the reference's decoder files byte for byte (bench.py's reference arm runs the stock code)."""
+    import filecmp
+    from baseline import reference as R
+    if not os.path.exists(os.path.join(R.REF_SRC, "rnn.py")):
+        pytest.skip("reference sources not on this machine")
+    assert R.install() == R.REF_DIR
+    for rel in R.FILES:
+        assert filecmp.cmp(os.path.join(R.REF_SRC, rel), os.path.join(R.REF_DIR, rel), shallow=False), rel
+    net = R.make_module("lstm", 8, 8, 20, 1)
+    assert type(net).__module__.startswith("showtell_ref_") and isinstance(net.unit, torch.nn.LSTM)
 
 
 def test_host_modules_reference_only_defined_ops():
