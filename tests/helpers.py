@@ -75,3 +75,63 @@ def reference_grads_on_gpu(model, p, feat, cap, lengths, alpha_c=1.0, autocast=N
         return {k: v.float().cpu() for k, v in grads.items()}, "oracle equations"
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+
+
+def kink_ambiguity(p, model, feat, cap, lengths, alpha_c=1.0, eps=1e-5):
+    """float64 oracle gradients + a componentwise bound on what the LeakyReLU kink can move in the four
+    attention-projection gradients when the pre-activation s = att1 + att2 (Attention/rnn_attn.py:25) is only known to
+    +-eps (fp32 rounding of a 2048-long dot product is ~1e-6).  LeakyReLU'(s) is 1 or 0.2; an implementation whose s
+    differs in the last bits may land on the other side for the entries with |s| <= eps, and each such entry
+    (t, b, p, a) moves d s by 0.8 * dL/du[t,b,p,a], i.e.
+        d encoder_att.weight[a, :] by 0.8 |dL/du| |f[b,p,:]|,   d encoder_att.bias[a] by 0.8 |dL/du|,
+        d decoder_att.weight[a, :] by 0.8 |dL/du| |h_{t-1}[b,:]|, d decoder_att.bias[a] by 0.8 |dL/du|.
+    Entries of those tensors that no ambiguous term touches get a zero bound, i.e. the plain bar.
+    Returns (grads64, bounds {name: tensor}, number of ambiguous entries)."""
+    from oracle import showtell_oracle as O
+    p64 = {k: v.double() for k, v in p.items()}
+    f64 = feat.double()
+    rec = []
+    orig_leaky, orig_att = O.leaky_relu02, O.attention
+
+    def leaky(x):
+        u = orig_leaky(x)
+        u.retain_grad()
+        rec[-1]["s"], rec[-1]["u"] = x.detach(), u
+        return u
+
+    def att(pp, feat_bpc, h):
+        rec.append({"h": h.detach()})
+        return orig_att(pp, feat_bpc, h)
+
+    O.leaky_relu02, O.attention = leaky, att
+    try:
+        _, g64, _ = O.train_step(p64, model, f64, cap, lengths, alpha_c)
+    finally:
+        O.leaky_relu02, O.attention = orig_leaky, orig_att
+    A, C = p["attn.encoder_att.weight"].shape
+    H = p["attn.decoder_att.weight"].shape[1]
+    bw_e, bb = torch.zeros(A, C, dtype=torch.float64), torch.zeros(A, dtype=torch.float64)
+    bw_d = torch.zeros(A, H, dtype=torch.float64)
+    fbpc = f64.transpose(1, 2).abs()
+    n_amb = 0
+    for r in rec:
+        idx = (r["s"].abs() <= eps).nonzero()
+        if idx.numel() == 0:
+            continue
+        n_amb += idx.shape[0]
+        b, pp_, a = idx[:, 0], idx[:, 1], idx[:, 2]
+        mag = 0.8 * r["u"].grad[b, pp_, a].abs()
+        bb.index_add_(0, a, mag)
+        bw_e.index_add_(0, a, mag[:, None] * fbpc[b, pp_])
+        bw_d.index_add_(0, a, mag[:, None] * r["h"][b].abs())
+    bounds = {"attn.encoder_att.weight": bw_e, "attn.encoder_att.bias": bb,
+              "attn.decoder_att.weight": bw_d, "attn.decoder_att.bias": bb.clone()}
+    return g64, bounds, n_amb
+
+
+def assert_close_with_kink_bound(name, got, ref64, bound, tol):
+    """|got - ref| <= tol * max|ref| + bound, componentwise."""
+    got = torch.as_tensor(got, dtype=torch.float64).cpu()
+    slack = tol * float(ref64.abs().max()) + (bound if bound is not None else 0.0)
+    excess = ((got - ref64).abs() - slack).max()
+    assert float(excess) <= 0.0, (name, float(excess), float((got - ref64).abs().max() / ref64.abs().max()))

@@ -104,15 +104,19 @@ def _random_case(kind, E, C, A, H, V, L, P, B, T, seed, dtype):
     ("attn_lstm", 512, 2048, 512, 512, 10000, 1, 49, 16, 20, "bf16", 2e-2),
 ])
 def test_oracle_parity_train(kind, E, C, A, H, V, L, P, B, T, dtype, tol):
-    """The gradients of attn.encoder_att.* and attn.decoder_att.* sum act'(att1 + att2) over every
+    """The gradients of attn.encoder_att.* and attn.decoder_att.* sum LeakyReLU'(att1 + att2) over every
     (b, p, a, t) -- millions of evaluations at these sizes -- and LeakyReLU' jumps 0.2 -> 1 at 0: two
-    implementations whose att1 / att2 differ in the last bit flip a handful of those terms, each worth a whole
-    de*w_f*0.8.  Those four tensors are held to max(bar, 1.5 x the MEASURED distance between two independent
-    runs of the reference) in both norms -- the same step run by the unmodified reference modules with torch's
-    CUDA kernels on this GPU (fp32, or under bf16 autocast for the bf16 bar) against the same CPU truth
-    (helpers.reference_grads_on_gpu).  Every other tensor is held to the bar in the max norm.  The small golden
-    cases, where no pre-activation lands on the kink, pass the plain bar for all tensors."""
-    from helpers import KINKED, l2_err, reference_grads_on_gpu
+    implementations whose att1 / att2 differ in the last bit flip a few of those terms, each worth a whole
+    0.8 * de * w_f.  (Measured, tests/test_gpu_bench_shapes.py: the unmodified reference in fp32 on this GPU is 5e-3
+    away from its own float64 evaluation on these four tensors, exactly like this library.)
+      fp32: truth = the float64 oracle; every gradient entry is held to the 1e-4 bar PLUS the exact amount the
+            terms with |att1 + att2| <= 1e-5 can move it (helpers.kink_ambiguity) -- zero for every entry no such
+            term touches, so the four tensors are checked at the plain bar almost everywhere;
+      bf16: bf16 rounding flips ~1 % of the terms (law of large numbers, not a handful): the four tensors are held
+            to max(2e-2, 1.5 x the measured error of the unmodified reference modules run under bf16 autocast by
+            torch's CUDA kernels on this GPU) in both norms (helpers.reference_grads_on_gpu).
+    Every other tensor is held to the bar in the max norm."""
+    from helpers import KINKED, assert_close_with_kink_bound, kink_ambiguity, l2_err, reference_grads_on_gpu
     m, feat, cap, lengths = _random_case(kind, E, C, A, H, V, L, P, B, T, 5, dtype)
     p = {k: v.detach().clone() for k, v in m.state_dict().items()}
     loss_ref, grads_ref, ex = O.train_step(p, kind, feat, cap, lengths, alpha_c=1.0)
@@ -121,8 +125,14 @@ def test_oracle_parity_train(kind, E, C, A, H, V, L, P, B, T, dtype, tol):
     loss.backward()
     assert abs(float(loss) - float(loss_ref)) < tol * float(loss_ref)
     assert rel_err(alphas, ex["alphas"]) < tol
-    spread, src = reference_grads_on_gpu(kind, p, feat, cap, lengths, 1.0,
-                                         autocast=torch.bfloat16 if dtype == "bf16" else None)
+    if dtype == "fp32":
+        g64, bounds, n_amb = kink_ambiguity(p, kind, feat, cap, lengths, 1.0, eps=1e-5)
+        print(f"{kind}/fp32: {n_amb} pre-activations within 1e-5 of the LeakyReLU kink")
+        for n, q in m.named_parameters():
+            if n != "attn.full_att.bias":
+                assert_close_with_kink_bound(n, q.grad, g64[n], bounds.get(n), tol)
+        return
+    spread, src = reference_grads_on_gpu(kind, p, feat, cap, lengths, 1.0, autocast=torch.bfloat16)
     for n, q in m.named_parameters():
         if n == "attn.full_att.bias":
             continue
