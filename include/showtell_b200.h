@@ -76,6 +76,12 @@ int st_sgemm(int transA, int transB, int M, int N, int K, float alpha, const flo
  * ------------------------------------------------------------------------------------------ */
 int st_gemm_bf16(int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
                  int c_is_bf16, const float* bias, float alpha, float beta, st_stream_t stream);
+/* Same, with operand-major flags: a_mn != 0 means A is passed as its transpose, the (K, M) row-major matrix
+ * (lda >= M); b_mn likewise B as (K, N) (ldb >= N).  The kernel consumes those layouts in place (MN-major UMMA
+ * operands), so the transposed products of the backward pass -- dW = dY^T X (a_mn = b_mn = 1: autograd of
+ * nn.Linear, rnn.py:33) and dX = dY W (b_mn = 1) -- need no transposed copies. */
+int st_gemm_bf16_ex(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
+                    int ldc, int c_is_bf16, const float* bias, float alpha, float beta, st_stream_t stream);
 
 /* fp32 (rows, cols) -> bf16 copy `dst` (rows, cols) and/or bf16 transpose `dstT` (cols, rows);
  * either may be NULL.  Produces the K-major operands st_gemm_bf16 needs for dX = dY W and

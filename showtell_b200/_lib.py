@@ -37,6 +37,7 @@ _SIGS = {
     "st_device_info": (_I, [_IP, _IP, _IP, C.POINTER(_L)]),
     "st_sgemm": (_I, [_I, _I, _I, _I, _I, _F, _P, _I, _P, _I, _F, _P, _I, _P, _P]),
     "st_gemm_bf16": (_I, [_I, _I, _I, _P, _I, _P, _I, _P, _I, _I, _P, _F, _F, _P]),
+    "st_gemm_bf16_ex": (_I, [_I, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _F, _F, _P]),
     "st_cast_bf16": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _P]),
     "st_vocab_ce_parts": (_I, [_I]),
     "st_debug_gemm_variant": (_I, [_I]),

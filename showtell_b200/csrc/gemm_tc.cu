@@ -354,7 +354,13 @@ struct WorkSched {
 };
 
 // ------------------------------------------------------------------------------------ 1-CTA kernel
-template <int EPI, int BN>
+// AMN / BMN = 1: that operand is given "MN-major" -- as the (K, M) resp. (K, N) row-major matrix, i.e. the
+// transpose of the K-major form -- and is consumed in place: TMA boxes of 64 k-rows x 64 (m|n) columns land
+// as 8 KB blocks [k][128 B] (128-byte swizzle), the UMMA descriptor walks them with LBO = 8 KB (next 64 m|n)
+// and SBO = 1 KB (next 8 k-rows), and the instruction descriptor flags the operand as MN-major.  This is what
+// lets every transposed product of the backward pass (dW = dY^T X, dX = dY W) read the tensors the forward
+// pass already has, with no transposed copy in HBM.
+template <int EPI, int BN, int AMN = 0, int BMN = 0>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const TcParams p) {
@@ -417,16 +423,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (elect_one()) {
           mbar_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* a = smem + (size_t)stage * STAGE_BYTES;
-          tma_load_2d(a, &tmA, k * BK, m0, &full[stage]);
-          tma_load_2d(a + A_BYTES, &tmB, k * BK, n0, &full[stage]);
+          if (AMN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(a + j * 8192, &tmA, m0 + 64 * j, k * BK, &full[stage]);
+          } else {
+            tma_load_2d(a, &tmA, k * BK, m0, &full[stage]);
+          }
+          if (BMN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(a + A_BYTES + j * 8192, &tmB, n0 + 64 * j, k * BK, &full[stage]);
+          } else {
+            tma_load_2d(a + A_BYTES, &tmB, k * BK, n0, &full[stage]);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {  // ----------------------------------------------------- MMA issuer
-    constexpr uint32_t idesc = umma_idesc(BM, BN);
-    const uint64_t adesc0 = umma_desc_k128(smem_u32(smem)), bdesc0 = umma_desc_k128(smem_u32(smem) + A_BYTES);
+    constexpr uint32_t idesc = umma_idesc(BM, BN) | (AMN ? (1u << 15) : 0u) | (BMN ? (1u << 16) : 0u);
+    const uint64_t adesc0 = AMN ? umma_desc_mn128(smem_u32(smem)) : umma_desc_k128(smem_u32(smem));
+    const uint64_t bdesc0 = BMN ? umma_desc_mn128(smem_u32(smem) + A_BYTES) : umma_desc_k128(smem_u32(smem) + A_BYTES);
+    // descriptor start-address step per 16-deep k-step, in 16-byte units: K-major 32 B, MN-major two 8-row groups
+    constexpr uint64_t astep = AMN ? 128 : 2, bstep = BMN ? 128 : 2;
     WorkSched sched(ntiles, kb, gridDim.x, blockIdx.x, p.streamk);
     int stage = 0, acc = 0, tile, k0, k1;
     uint32_t phase = 0, acc_phase = 0;
@@ -442,7 +461,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < BK / UK; ++kk)
-            tc_mma(d_tmem, adesc0 + so + 2 * kk, bdesc0 + so + 2 * kk, idesc, (k > k0) || (kk != 0));
+            tc_mma(d_tmem, adesc0 + so + astep * kk, bdesc0 + so + bstep * kk, idesc, (k > k0) || (kk != 0));
           tc_commit(&empty[stage]);  // smem slot free once these MMAs retire
         }
         __syncwarp();
@@ -909,12 +928,14 @@ inline bool want_streamk(const TcParams& p, int ntiles, int kb, int workers) {
   return saved_us > cost_us;
 }
 
-template <int EPI, int BN>
+template <int EPI, int BN, int AMN = 0, int BMN = 0>
 int launch_tc_bn(TcParams p, const void* A, int lda, const void* B, int ldb, cudaStream_t s, int sms) {
   CUtensorMap tmA, tmB;
-  ST_TRY(make_tmap(&tmA, A, p.M, p.K, lda, BM, "A"));
-  ST_TRY(make_tmap(&tmB, B, p.N, p.K, ldb, BN, "B"));
-  auto kern = gemm_tc_kernel<EPI, BN>;
+  if (AMN) ST_TRY(make_tmap(&tmA, A, p.K, p.M, lda, 64, "A (MN-major)"));
+  else ST_TRY(make_tmap(&tmA, A, p.M, p.K, lda, BM, "A"));
+  if (BMN) ST_TRY(make_tmap(&tmB, B, p.K, p.N, ldb, 64, "B (MN-major)"));
+  else ST_TRY(make_tmap(&tmB, B, p.N, p.K, ldb, BN, "B"));
+  auto kern = gemm_tc_kernel<EPI, BN, AMN, BMN>;
   ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<BN>::SMEM_BYTES));
   const int ntiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN), kb = (p.K + BK - 1) / BK;
   int grid = ntiles < sms ? ntiles : sms;
@@ -988,6 +1009,18 @@ inline bool want_narrow(const TcParams& p, int sms) {
   return t128 * 8 <= sms;
 }
 
+// EPI_STORE with operand-major flags (the backward products).  Tile width 128 or 256 (64-wide tiles are a
+// K-major latency-path special).
+template <int AMN, int BMN>
+int launch_tc_major(const TcParams& p, const void* A, int lda, const void* B, int ldb, cudaStream_t s) {
+  ST_REQUIRE(p.M >= 1 && p.N >= 1 && p.K >= 1, ST_ERR_BAD_SHAPE, "gemm_bf16: M=%d N=%d K=%d", p.M, p.N, p.K);
+  int sms = 0;
+  ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
+  const int bn = (g_variant == 128 || g_variant == 256) ? g_variant : pick_variant<EPI_STORE>(p, sms);
+  return bn == 256 ? launch_tc_bn<EPI_STORE, 256, AMN, BMN>(p, A, lda, B, ldb, s, sms)
+                   : launch_tc_bn<EPI_STORE, 128, AMN, BMN>(p, A, lda, B, ldb, s, sms);
+}
+
 template <int EPI>
 int launch_tc(const TcParams& p, const void* A, int lda, const void* B, int ldb, cudaStream_t s, int bn = 0) {
   ST_REQUIRE(p.M >= 1 && p.N >= 1 && p.K >= 1, ST_ERR_BAD_SHAPE, "gemm_bf16: M=%d N=%d K=%d", p.M, p.N, p.K);
@@ -1014,6 +1047,21 @@ int st_gemm_bf16(int M, int N, int K, const void* A, int lda, const void* B, int
   ST_REQUIRE(beta == 0.f || !c_is_bf16, ST_ERR_UNSUPPORTED, "st_gemm_bf16: beta needs an fp32 C");
   p.C = C; p.ldc = ldc; p.c_bf16 = c_is_bf16; p.bias = bias; p.alpha = alpha; p.beta = beta;
   return launch_tc<EPI_STORE>(p, A, lda, B, ldb, as_stream(stream));
+}
+
+int st_gemm_bf16_ex(int M, int N, int K, const void* A, int lda, int a_mn, const void* B, int ldb, int b_mn, void* C,
+                    int ldc, int c_is_bf16, const float* bias, float alpha, float beta, st_stream_t stream) {
+  using namespace st;
+  if (!a_mn && !b_mn) return st_gemm_bf16(M, N, K, A, lda, B, ldb, C, ldc, c_is_bf16, bias, alpha, beta, stream);
+  ST_REQUIRE(C != nullptr, ST_ERR_NULL, "st_gemm_bf16_ex: C is NULL");
+  ST_REQUIRE(ldc >= N, ST_ERR_BAD_SHAPE, "st_gemm_bf16_ex: ldc=%d < N=%d", ldc, N);
+  ST_REQUIRE(beta == 0.f || !c_is_bf16, ST_ERR_UNSUPPORTED, "st_gemm_bf16_ex: beta needs an fp32 C");
+  TcParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.C = C; p.ldc = ldc; p.c_bf16 = c_is_bf16; p.bias = bias; p.alpha = alpha; p.beta = beta;
+  if (a_mn && b_mn) return launch_tc_major<1, 1>(p, A, lda, B, ldb, as_stream(stream));
+  if (b_mn) return launch_tc_major<0, 1>(p, A, lda, B, ldb, as_stream(stream));
+  return launch_tc_major<1, 0>(p, A, lda, B, ldb, as_stream(stream));
 }
 
 int st_vocab_ce_fwd(int M, int V, int H, const void* Hs, int ldh, const void* Wv, int ldw, const float* bv,

@@ -112,7 +112,20 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
   return d;
 }
-// Instruction descriptor: D fp32, A/B bf16, both K-major, M x N tile.
+// Shared-memory matrix descriptor, MN-major operand (the matrix is stored as [k][m|n]), 128-byte swizzle: the tile
+// is a row of 8 KB blocks, each 64 k-rows x 128 B (64 bf16 along m|n) exactly as a 64 x 64 TMA box lands; canonical
+// layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: LBO = 8 KB to the next 64 (m|n), SBO = 1 KB to the next
+// 8 k-rows.  One MMA (K = 16) spans two 8-row groups: advance the start address by 2 KB per k-step.
+__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(8192 >> 4) << 16;          // leading byte offset: next 64-wide (m|n) block
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset: next 8 k-rows
+  d |= (uint64_t)1 << 46;                    // descriptor version
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor: D fp32, A/B bf16, both K-major, M x N tile (bit 15 / 16 set = A / B MN-major).
 __host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }

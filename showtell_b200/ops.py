@@ -292,23 +292,29 @@ def _raw(t):
     return C.c_void_p(t.data_ptr())
 
 
-def gemm_bf16(A, B, *, bias=None, out_dtype=F32, alpha=1.0, beta=0.0, out=None, tag=None):
+def gemm_bf16(A, B, *, bias=None, out_dtype=F32, alpha=1.0, beta=0.0, out=None, tag=None, a_t=False, b_t=False):
     """out[M,N] = alpha * A[M,K] . B[N,K]^T + bias on tcgen05 tensor cores.  A, B bf16 with unit inner
-    stride and row strides that are multiples of 8."""
+    stride and row strides that are multiples of 8.  a_t / b_t: that operand is passed as its transpose -- A as
+    (K, M), B as (K, N) -- and consumed in place (MN-major UMMA operand): dW = dY^T X is
+    gemm_bf16(dY, X, a_t=True, b_t=True), dX = dY W is gemm_bf16(dY, W, b_t=True)."""
     lib = _lib.load()
     for t in (A, B):
         if t.dim() != 2 or t.dtype != BF16 or t.stride(1) != 1 or not t.is_cuda:
             raise ValueError("gemm_bf16 operands must be 2-D bf16 CUDA tensors with unit inner stride")
-    M, K = A.shape
-    N, Kb = B.shape
+    M, K = (A.shape[1], A.shape[0]) if a_t else A.shape
+    N, Kb = (B.shape[1], B.shape[0]) if b_t else B.shape
     if K != Kb:
         raise ValueError(f"gemm_bf16: inner dimensions differ ({K} vs {Kb})")
     if out is None:
         out = torch.empty(M, N, dtype=out_dtype, device=A.device)
+    elif tuple(out.shape) != (M, N) or out.stride(1) != 1 or out.dtype not in (F32, BF16) or not out.is_cuda:
+        raise ValueError(f"gemm_bf16: `out` must be a ({M}, {N}) fp32 / bf16 CUDA tensor with unit inner stride")
+    if bias is not None and (bias.numel() != N or bias.dtype != F32):
+        raise ValueError("gemm_bf16: bad bias")
     tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
-    check(lib.st_gemm_bf16(M, N, K, _raw(A), A.stride(0), _raw(B), B.stride(0), _raw(out), out.stride(0),
-                           int(out.dtype == BF16), ptr(bias, F32), float(alpha), float(beta), stream_ptr()),
-          "st_gemm_bf16")
+    check(lib.st_gemm_bf16_ex(M, N, K, _raw(A), A.stride(0), int(a_t), _raw(B), B.stride(0), int(b_t), _raw(out),
+                              out.stride(0), int(out.dtype == BF16), ptr(bias, F32), float(alpha), float(beta),
+                              stream_ptr()), "st_gemm_bf16")
     if tok:
         TIMER.end(tok)
     return out

@@ -53,6 +53,40 @@ def test_gemm_bf16(M, N, K, variant, gemm_variant):
     assert bool((wide[:, :4] == 7).all()) and bool((wide[:, 4 + N:] == 7).all())
 
 
+@pytest.mark.parametrize("variant", [0, 128, 256])
+@pytest.mark.parametrize("a_t,b_t", [(True, True), (False, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 256, 128), (256, 384, 192), (100, 50, 40), (129, 257, 72),
+                                   (10000, 512, 5120),      # dW of the vocabulary projection: P^T . Hs
+                                   (5120, 512, 10000),      # dX of the vocabulary projection: P . W_v
+                                   (2048, 512, 5120),       # dW_hh / dW_ih
+                                   (300, 700, 4000)])
+def test_gemm_bf16_mn_major_operands(M, N, K, a_t, b_t, variant, gemm_variant):
+    """Operands passed as their transposes ((K, M) / (K, N) row-major) and consumed in place as MN-major UMMA
+    operands: the backward products dW = dY^T X and dX = dY W without transposed copies."""
+    from showtell_b200 import ops
+    gemm_variant(variant)
+    g = torch.Generator().manual_seed(M + 2 * N + 3 * K)
+    pad = lambda n: (n + 7) // 8 * 8
+    A = torch.randn(M, K, generator=g).to(DEV).bfloat16()
+    B = torch.randn(N, K, generator=g).to(DEV).bfloat16()
+    ref = A.double() @ B.double().t()
+    Ain = torch.zeros(K, pad(M), device=DEV, dtype=torch.bfloat16)[:, :M].copy_(A.t()) if a_t else \
+        torch.zeros(M, pad(K), device=DEV, dtype=torch.bfloat16)[:, :K].copy_(A)
+    Bin = torch.zeros(K, pad(N), device=DEV, dtype=torch.bfloat16)[:, :N].copy_(B.t()) if b_t else \
+        torch.zeros(N, pad(K), device=DEV, dtype=torch.bfloat16)[:, :K].copy_(B)
+    tol = 1e-5 if K <= 2048 else 4e-5
+    out = ops.gemm_bf16(Ain, Bin, a_t=a_t, b_t=b_t)
+    assert out.shape == (M, N) and rel_err(out, ref) < tol, rel_err(out, ref)
+    bias = torch.randn(N, generator=g).to(DEV)
+    acc = torch.randn(M, N, generator=g).to(DEV)
+    out2 = ops.gemm_bf16(Ain, Bin, a_t=a_t, b_t=b_t, bias=bias, alpha=0.5, beta=1.0, out=acc.clone())
+    assert rel_err(out2, 0.5 * ref + bias.double() + acc.double()) < tol
+    out3 = ops.gemm_bf16(Ain, Bin, a_t=a_t, b_t=b_t, out_dtype=torch.bfloat16)
+    assert rel_err(out3, ref) < 1e-2
+    with pytest.raises(ValueError):
+        ops.gemm_bf16(Ain, Bin, a_t=a_t, b_t=b_t, out=torch.empty(M + 1, N, device=DEV))
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (100, 50, 40), (129, 257, 72), (640, 10000, 512), (4096, 1536, 512),
                                    (37, 1000, 2048), (4096, 10000, 512)])
 def test_gemm_tf32x3_is_fp32_accurate(M, N, K):
