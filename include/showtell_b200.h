@@ -132,6 +132,10 @@ int st_vocab_ce_bwd(int M, int V, int H, const void* Hs, int ldh, const void* Wv
 int st_pack_inputs(float* X, int ldx, const float* emb, int E, int V, const float* feature,
                    const int64_t* caption, int T_cap, int with_feature, int nsteps,
                    const int* batch_sizes_host, st_stream_t stream);
+/* Same rows written as bf16 (the operand of the hoisted tensor-core input projection): no fp32 copy + cast. */
+int st_pack_inputs_bf16(void* X, int ldx, const float* emb, int E, int V, const float* feature,
+                        const int64_t* caption, int T_cap, int with_feature, int nsteps,
+                        const int* batch_sizes_host, st_stream_t stream);
 /* Number of out-of-range token ids the packing kernels have met since the last clear (host-mapped status word,
  * no synchronisation: a step still in flight is seen by a later call); *first_bad_id = the first such id. */
 int st_token_error(int64_t* first_bad_id, int clear);
@@ -204,12 +208,14 @@ int st_bn1d_bwd(const float* Y, int ldy, const float* dOut, int ldd, int B, int 
  * param / grad / state are host arrays of device pointers, count[i] elements each.  momentum_buf may be NULL when
  * momentum == 0; first_step != 0 initialises the momentum buffers with the gradient (torch's first step).
  * `step` is Adam's 1-based step count.  grad_scale: optional device scalar multiplied into every gradient (the
- * grad_output of forward_loss's autograd node), NULL = 1. */
+ * grad_output of forward_loss's autograd node), NULL = 1.
+ * shadow_bf16 (NULL, or n entries each NULL or a contiguous bf16 buffer of count[i] elements): rewritten with the
+ * updated parameter in the same pass -- the bf16 operands of the next step's tensor-core kernels. */
 #define ST_OPT_MAX 32
-int st_sgd_step(int n, float* const* param, const float* const* grad, float* const* momentum_buf, const int64_t* count,
-                float lr, float momentum, int first_step, const float* grad_scale, st_stream_t stream);
+int st_sgd_step(int n, float* const* param, const float* const* grad, float* const* momentum_buf, void* const* shadow_bf16,
+                const int64_t* count, float lr, float momentum, int first_step, const float* grad_scale, st_stream_t stream);
 int st_adam_step(int n, float* const* param, const float* const* grad, float* const* exp_avg, float* const* exp_avg_sq,
-                 const int64_t* count, float lr, double beta1, double beta2, float eps, int64_t step,
+                 void* const* shadow_bf16, const int64_t* count, float lr, double beta1, double beta2, float eps, int64_t step,
                  const float* grad_scale, st_stream_t stream);
 
 /* out[r] = sum_c M[r, c], M bf16 (rows, ld): db_v from the transposed dlogits. */
@@ -310,6 +316,9 @@ int st_rnn_seq_tc_bwd(int kind, int H, int nsteps, const int* batch_sizes_host, 
 /* Hprev (N,H): row (t,b) = h_{t-1}[b] (h0 or zeros at t=0) -- the B operand of dW_hh = dGh^T Hprev. */
 int st_shift_states(float* Hprev, const float* Hs, const float* h0, int H, int nsteps,
                     const int* batch_sizes_host, st_stream_t stream);
+/* Same on bf16 rows (Hs_bf16 of the tensor-core recurrent kernels -> the operand of dW_hh = dGh^T H_prev). */
+int st_shift_states_bf16(void* Hprev, const void* Hs, const void* h0, int H, int nsteps,
+                         const int* batch_sizes_host, st_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Soft attention (Attention/rnn_attn.py:8-31 Attention_Net, :60-76 rnn_iterator).  The reference

@@ -47,13 +47,14 @@ _SIGS = {
     "st_scale_multi": (_I, [_I, _P, _P, _P, _P, _P]),
     "st_bn1d_fwd": (_I, [_P, _I, _I, _I, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _I, _P]),
     "st_bn1d_bwd": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
-    "st_sgd_step": (_I, [_I, _P, _P, _P, _P, _F, _F, _I, _P, _P]),
-    "st_adam_step": (_I, [_I, _P, _P, _P, _P, _P, _F, C.c_double, C.c_double, _F, _L, _P, _P]),
+    "st_sgd_step": (_I, [_I, _P, _P, _P, _P, _P, _F, _F, _I, _P, _P]),
+    "st_adam_step": (_I, [_I, _P, _P, _P, _P, _P, _P, _F, C.c_double, C.c_double, _F, _L, _P, _P]),
     "st_allreduce_flag_words": (_I, [_I]),
     "st_allreduce_sum_f32": (_I, [C.POINTER(C.c_void_p), _P, C.POINTER(C.c_void_p), _I, _I, _L, _I, _P]),
     "st_vocab_ce_fwd": (_I, [_I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "st_vocab_ce_bwd": (_I, [_I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _F, _P, _I, _P, _I, _P]),
     "st_pack_inputs": (_I, [_P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _IP, _P]),
+    "st_pack_inputs_bf16": (_I, [_P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _IP, _P]),
     "st_pack_inputs_bwd": (_I, [_P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _IP, _P]),
     "st_pack_targets": (_I, [_P, _P, _I, _I, _I, _IP, _P]),
     "st_token_error": (_I, [C.POINTER(_L), _I]),
@@ -73,6 +74,7 @@ _SIGS = {
     "st_rnn_step_x_tc_bwd": (_I, [_I, _I, _I, _IP, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I,
                                   _P, _P, _I, _P, _I, _I, _P]),
     "st_shift_states": (_I, [_P, _P, _P, _I, _I, _IP, _P]),
+    "st_shift_states_bf16": (_I, [_P, _P, _P, _I, _I, _IP, _P]),
     "st_attn_relayout": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
     "st_attn_relayout_bf16in": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
     "st_attn_step_fwd": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _P, _I, _I, _P]),

@@ -52,8 +52,9 @@ def attn_forward(mode, P, kind, L, feature, caption, bs, save):
     tc = _use_tc(mode, kind, P, B)
     sv = {"bs": bs, "off": off, "Pn": Pn, "B": B, "tc": tc}
 
-    F, FT, mean_f = ops.attn_relayout(feature, bf16=(mode == "bf16"), want_t=(save and mode == "bf16"))
-    sv.update(F=F, FT=FT, mean_f=mean_f)
+    # (no transposed copy of the grid: dW_enc = datt1^T F reads F in place as an MN-major GEMM operand)
+    F, FT, mean_f = ops.attn_relayout(feature, bf16=(mode == "bf16"), want_t=False)
+    sv.update(F=F, mean_f=mean_f)
     # rnn_attn.py:62: every layer starts from init_h(mean_P f) (init_c likewise for the LSTM)
     # (a skinny fp32 product: it runs on the side stream beside the hoisted grid projections below)
     (h0, c0), init_done = ops.fork(
@@ -81,14 +82,15 @@ def attn_forward(mode, P, kind, L, feature, caption, bs, save):
     wf = P["attn.full_att.weight"].reshape(-1)
     bd = P["attn.decoder_att.bias"]
     if tc:
-        # bf16 K-major operand copies (and the transposes the reverse loop needs)
-        W = {"d": ops.cast_bf16(P["attn.decoder_att.weight"], True, save),
-             "ihe": ops.cast_bf16(Wih0[:, :E], True, save), "ihc": ops.cast_bf16(Wih0[:, E:], True, save)}
+        # bf16 shadows of the weights (cached until the optimizer changes them); the transposes are the K-major
+        # TMA operands of the reverse step kernels -- the GEMMs read either major in place
+        sh = lambda w, tr: (ops.bf16_shadow(w), ops.bf16_shadow(w, transposed=True) if tr else None)
+        W = {"d": sh(P["attn.decoder_att.weight"], save), "ihe": sh(Wih0[:, :E], False), "ihc": sh(Wih0[:, E:], save)}
         for l in range(L):
             Wih, Whh, _, _ = layer_params(P, l)
-            W[f"hh{l}"] = ops.cast_bf16(Whh, True, save)
+            W[f"hh{l}"] = sh(Whh, save)
             if l > 0:
-                W[f"ih{l}"] = ops.cast_bf16(Wih, True, save)
+                W[f"ih{l}"] = sh(Wih, False)
         sv["W"] = W
         Xe_b, _ = ops.cast_bf16(X0[:, :E], True, False)
         Gx = [ops.gemm_bf16(Xe_b, W["ihe"][0], bias=bih0, tag="ih_fwd")]              # emb half hoisted
@@ -145,9 +147,8 @@ def attn_forward(mode, P, kind, L, feature, caption, bs, save):
 
 
 def _ctx_bf16(bs, Pn, F, alphas):
-    ctx, _ = ops.attn_ctx_all(bs, Pn, F, alphas, out_dtype=F32)              # row-major: coalesced stores
-    _, ctxT = ops.cast_bf16(ctx, False, True)
-    return ctx, ctxT
+    ctx, _ = ops.attn_ctx_all(bs, Pn, F, alphas, out_dtype=BF16)             # row-major bf16: read in place by the GEMM
+    return ctx, None
 
 
 def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=None, emb_out=None, recurrent_done=None):
@@ -202,7 +203,7 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
                 if bouts[l] is None:
                     raise RuntimeError("rnn_seq_tc_bwd refused a shape that rnn_seq_tc_fits accepted")
                 if l > 0:                                                             # dX of layer l at step t
-                    ops.gemm_bf16(bouts[l]["dGb"][o0:o1], W[f"ih{l}"][1], out=dHs[l - 1][o0:o1])
+                    ops.gemm_bf16(bouts[l]["dGb"][o0:o1], W[f"ih{l}"][0], b_t=True, out=dHs[l - 1][o0:o1])
             else:
                 bouts[l] = ops.rnn_seq_bwd(kind, Whh, bs, outs[l], dHs[l], h0=h0, c0=c0, t_range=(t + 1, t),
                                            out=bouts[l], tag="step_bwd")
@@ -231,28 +232,30 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
             dq = ops.sgemm(datt2_all[o0:o1], Wd)
             ops.add_rows(bouts[L - 1]["dstate"][0], dq, bt)
 
-    if fused_bwd:                   # bias gradients = row sums of the transposed gate gradients
-        bouts[0]["dbih"] = ops.rowsum_bf16(bouts[0]["dGT"])
-        bouts[0]["dbhh"] = ops.rowsum_bf16(bouts[0]["dGhT"]) if kind == _lib.ST_GRU else bouts[0]["dbih"]
+    if tc:                          # bias gradients = column sums of the bf16 gate gradients
+        for l in range(L):
+            bouts[l]["dbih"] = ops.colsum(bouts[l]["dGb"])
+            bouts[l]["dbhh"] = ops.colsum(bouts[l]["dGhb"]) if kind == _lib.ST_GRU else bouts[l]["dbih"]
     # ---- hoisted weight gradients.  The encoder-projection chain (one pass over att1, then the largest GEMM
     # of the step) is independent of the recurrent ones: side stream.
     def enc_chain():
-        datt1, datt1T, dwf = ops.attn_hoist_bwd(bs, Pn, att1, att2_all, de_all, wf, want_t=(mode == "bf16"))
+        datt1, _, dwf = ops.attn_hoist_bwd(bs, Pn, att1, att2_all, de_all, wf, want_t=False)
         if mode == "bf16":
-            dWe = ops.gemm_bf16(datt1T, sv["FT"], tag="att1_dw")                                # datt1^T F
+            dWe = ops.gemm_bf16(datt1, sv["F"], a_t=True, b_t=True, tag="att1_dw")               # datt1^T F, both in place
         else:
             dWe = ops.sgemm(datt1, sv["F"], transA=True, tag="att1_dw")
         return dWe, ops.colsum(datt1), dwf
 
-    (dWe, dbe, dwf), enc_done = ops.fork(enc_chain, uses=(att1, att2_all, de_all, wf, sv["FT"] if mode == "bf16" else sv["F"]))
+    (dWe, dbe, dwf), enc_done = ops.fork(enc_chain, uses=(att1, att2_all, de_all, wf, sv["F"]))
+    h0_b16 = ops.cast_bf16(h0, True, False)[0] if tc else None
     for l in range(L):
-        Hprev = ops.shift_states(outs[l]["Hs"], bs, h0)
+        Hprev = ops.shift_states(outs[l]["Hs"], bs, h0) if not tc else None
         inp = X0 if l == 0 else outs[l - 1]["Hs"]
         if tc:
-            _, HprevT = ops.cast_bf16(Hprev, False, True)
-            _, inpT = ops.cast_bf16(inp, False, True)
-            grads[f"unit.weight_hh_l{l}"] = ops.gemm_bf16(bouts[l]["dGhT"], HprevT, tag="hh_dw")
-            grads[f"unit.weight_ih_l{l}"] = ops.gemm_bf16(bouts[l]["dGT"], inpT, tag="ih_dw")
+            Hprev_b = Hprev = ops.shift_states(outs[l]["Hsb"], bs, h0_b16)
+            inp_b = ops.cast_bf16(X0, True, False)[0] if l == 0 else outs[l - 1]["Hsb"]
+            grads[f"unit.weight_hh_l{l}"] = ops.gemm_bf16(bouts[l]["dGhb"], Hprev_b, a_t=True, b_t=True, tag="hh_dw")
+            grads[f"unit.weight_ih_l{l}"] = ops.gemm_bf16(bouts[l]["dGb"], inp_b, a_t=True, b_t=True, tag="ih_dw")
             grads[f"unit.bias_hh_l{l}"], grads[f"unit.bias_ih_l{l}"] = bouts[l]["dbhh"], bouts[l]["dbih"]
         else:
             grads[f"unit.weight_hh_l{l}"] = weight_grad(mode, bouts[l]["dGh"], Hprev, "hh_dw")
@@ -262,7 +265,7 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
         if l == L - 1:
             Hprev_top = Hprev
     if tc:
-        dXemb = ops.gemm_bf16(bouts[0]["dGb"], W["ihe"][1], tag="ih_dx")
+        dXemb = ops.gemm_bf16(bouts[0]["dGb"], W["ihe"][0], b_t=True, tag="ih_dx")
     else:
         dXemb = ops.sgemm(bouts[0]["dG"], Wih0[:, :E], tag="ih_dx")
     dEmb = emb_out().zero_() if emb_out is not None else torch.zeros_like(P["embeddings.weight"])
@@ -272,15 +275,15 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
         recurrent_done(grads)
     # attention parameters
     grads["attn.encoder_att.weight"], grads["attn.encoder_att.bias"] = dWe, dbe
-    grads["attn.decoder_att.weight"] = weight_grad(mode, datt2_all, Hprev_top, "att2_dw")
+    grads["attn.decoder_att.weight"] = weight_grad(mode, datt2_b if tc else datt2_all, Hprev_top, "att2_dw")
     grads["attn.decoder_att.bias"] = ops.colsum(datt2_all)
     grads["attn.full_att.weight"] = dwf.reshape(1, -1)
     grads["attn.full_att.bias"] = ops.colsum(de_all.reshape(-1, 1))
     # embed: ctx_e = W_embed ctx + b with ctx = sum_p alpha_p F_p rebuilt for all (t,b) in one pass
     if mode == "bf16":
-        _, dcT = ops.cast_bf16(dctx_all, False, True)
+        dc_b, _ = ops.cast_bf16(dctx_all, True, False)
         ops.join(ctx_done)
-        grads["embed.weight"] = ops.gemm_bf16(dcT, ctxT, tag="embed_dw")
+        grads["embed.weight"] = ops.gemm_bf16(dc_b, ctx, a_t=True, b_t=True, tag="embed_dw")
     else:
         ctx, _ = ops.attn_ctx_all(bs, Pn, sv["F"], alphas)
         grads["embed.weight"] = ops.sgemm(dctx_all, ctx, transA=True, tag="embed_dw")

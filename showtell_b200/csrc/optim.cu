@@ -10,6 +10,11 @@
 //         p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
 // `grad_scale` (device scalar, may be NULL = 1) multiplies every gradient first: autograd's grad_output of
 // forward_loss, so the chain-rule pass over the gradients folds into the optimizer's read of them.
+// `shadow_bf16[i]` (table and entries may be NULL): a contiguous bf16 copy of parameter i, rewritten from the
+// updated fp32 value in the same pass -- the operand the tensor-core kernels of the next step read, so no
+// separate fp32 -> bf16 cast launches exist in the training loop (2 more bytes written per parameter).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace st {
@@ -22,6 +27,7 @@ struct OptTable {
   const float* g[ST_OPT_MAX];
   float* m[ST_OPT_MAX];
   float* v[ST_OPT_MAX];
+  __nv_bfloat16* s[ST_OPT_MAX];
   long long count[ST_OPT_MAX];
   int first[ST_OPT_MAX + 1];
 };
@@ -59,7 +65,8 @@ __global__ void __launch_bounds__(256) optim_multi_kernel(const OptTable tab, co
     const float* __restrict__ G = tab.g[i] + base;
     float* __restrict__ M = has_m ? tab.m[i] + base : nullptr;
     float* __restrict__ V = ADAM ? tab.v[i] + base : nullptr;
-    const uintptr_t al = reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(M) |
+    __nv_bfloat16* __restrict__ S = tab.s[i] ? tab.s[i] + base : nullptr;
+    const uintptr_t al = (reinterpret_cast<uintptr_t>(S) << 1) | reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(M) |
                          reinterpret_cast<uintptr_t>(V);
     int done = 0;
     if ((al & 15) == 0) {
@@ -74,6 +81,10 @@ __global__ void __launch_bounds__(256) optim_multi_kernel(const OptTable tab, co
         update<ADAM>(p4.z, g4.z * a, m4.z, v4.z, h);
         update<ADAM>(p4.w, g4.w * a, m4.w, v4.w, h);
         reinterpret_cast<float4*>(P)[j] = p4;
+        if (S) {
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(p4.x, p4.y), hi = __floats2bfloat162_rn(p4.z, p4.w);
+          reinterpret_cast<uint2*>(S)[j] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        }
         if (has_m) reinterpret_cast<float4*>(M)[j] = m4;
         if (ADAM) reinterpret_cast<float4*>(V)[j] = v4;
       }
@@ -83,6 +94,7 @@ __global__ void __launch_bounds__(256) optim_multi_kernel(const OptTable tab, co
       float pj = P[j], mj = has_m ? M[j] : 0.f, vj = ADAM ? V[j] : 0.f;
       update<ADAM>(pj, G[j] * a, mj, vj, h);
       P[j] = pj;
+      if (S) S[j] = __float2bfloat16(pj);
       if (has_m) M[j] = mj;
       if (ADAM) V[j] = vj;
     }
@@ -90,7 +102,7 @@ __global__ void __launch_bounds__(256) optim_multi_kernel(const OptTable tab, co
 }
 
 int build_table(OptTable& tab, int n, float* const* p, const float* const* g, float* const* m, float* const* v,
-                const int64_t* count, bool need_m, bool need_v, long long* chunks_out) {
+                void* const* shadow, const int64_t* count, bool need_m, bool need_v, long long* chunks_out) {
   ST_REQUIRE(n >= 0 && n <= ST_OPT_MAX, ST_ERR_BAD_SHAPE, "optimizer step: n=%d tensors (max %d per call)", n, (int)ST_OPT_MAX);
   ST_REQUIRE(n == 0 || (p && g && count && (!need_m || m) && (!need_v || v)), ST_ERR_NULL, "optimizer step: NULL pointer table");
   tab.n = n;
@@ -100,6 +112,7 @@ int build_table(OptTable& tab, int n, float* const* p, const float* const* g, fl
     ST_REQUIRE(count[i] == 0 || (p[i] && g[i] && (!need_m || m[i]) && (!need_v || v[i])), ST_ERR_NULL,
                "optimizer step: tensor %d has a NULL pointer", i);
     tab.p[i] = p[i]; tab.g[i] = g[i]; tab.m[i] = need_m ? m[i] : nullptr; tab.v[i] = need_v ? v[i] : nullptr;
+    tab.s[i] = shadow ? reinterpret_cast<__nv_bfloat16*>(shadow[i]) : nullptr;
     tab.count[i] = count[i];
     tab.first[i] = (int)chunks;
     chunks += (count[i] + OPT_CHUNK - 1) / OPT_CHUNK;
@@ -115,12 +128,12 @@ int build_table(OptTable& tab, int n, float* const* p, const float* const* g, fl
 
 extern "C" {
 
-int st_sgd_step(int n, float* const* param, const float* const* grad, float* const* momentum_buf, const int64_t* count,
-                float lr, float momentum, int first_step, const float* grad_scale, st_stream_t stream) {
+int st_sgd_step(int n, float* const* param, const float* const* grad, float* const* momentum_buf, void* const* shadow_bf16,
+                const int64_t* count, float lr, float momentum, int first_step, const float* grad_scale, st_stream_t stream) {
   using namespace st;
   OptTable tab;
   long long chunks = 0;
-  ST_TRY(build_table(tab, n, param, grad, momentum_buf, nullptr, count, momentum != 0.f, false, &chunks));
+  ST_TRY(build_table(tab, n, param, grad, momentum_buf, nullptr, shadow_bf16, count, momentum != 0.f, false, &chunks));
   if (chunks == 0) return ST_OK;
   OptHyper h{lr, momentum, 0.f, 0.f, 1.f, 1.f, 0.f, 1.f, 1.f, first_step};
   int sms = 0;
@@ -132,7 +145,7 @@ int st_sgd_step(int n, float* const* param, const float* const* grad, float* con
 }
 
 int st_adam_step(int n, float* const* param, const float* const* grad, float* const* exp_avg, float* const* exp_avg_sq,
-                 const int64_t* count, float lr, double beta1_d, double beta2_d, float eps, int64_t step,
+                 void* const* shadow_bf16, const int64_t* count, float lr, double beta1_d, double beta2_d, float eps, int64_t step,
                  const float* grad_scale, st_stream_t stream) {
   using namespace st;
   const float beta1 = (float)beta1_d, beta2 = (float)beta2_d;   // betas come as doubles: 1 - beta is rounded once, as torch does
@@ -141,7 +154,7 @@ int st_adam_step(int n, float* const* param, const float* const* grad, float* co
              "st_adam_step: betas (%g, %g) eps %g", beta1, beta2, eps);
   OptTable tab;
   long long chunks = 0;
-  ST_TRY(build_table(tab, n, param, grad, exp_avg, exp_avg_sq, count, true, true, &chunks));
+  ST_TRY(build_table(tab, n, param, grad, exp_avg, exp_avg_sq, shadow_bf16, count, true, true, &chunks));
   if (chunks == 0) return ST_OK;
   const double bc1 = 1.0 - pow(beta1_d, (double)step), bc2 = 1.0 - pow(beta2_d, (double)step);
   OptHyper h{lr, 0.f, beta1, beta2, (float)(1.0 - beta1_d), (float)(1.0 - beta2_d), eps, (float)bc1, (float)sqrt(bc2), 0};

@@ -57,7 +57,11 @@ long long* token_status() {
   return g_token_status_dev;
 }
 
-__global__ void pack_inputs_kernel(const __grid_constant__ StepTable tab, float* __restrict__ X, int ldx,
+__device__ __forceinline__ void store_as(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_as(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+template <typename TX>
+__global__ void pack_inputs_kernel(const __grid_constant__ StepTable tab, TX* __restrict__ X, int ldx,
                                    const float* __restrict__ emb, int E, int V,
                                    const float* __restrict__ feature,
                                    const int64_t* __restrict__ caption, int T_cap, int with_feature,
@@ -74,8 +78,8 @@ __global__ void pack_inputs_kernel(const __grid_constant__ StepTable tab, float*
     tok = tok < 0 ? 0 : (tok >= V ? V - 1 : tok);
     src = emb + (size_t)tok * E;
   }
-  float* dst = X + (size_t)n * ldx;
-  for (int e = threadIdx.x; e < E; e += blockDim.x) dst[e] = src[e];
+  TX* dst = X + (size_t)n * ldx;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) store_as(dst + e, src[e]);
 }
 
 __global__ void pack_inputs_bwd_kernel(const __grid_constant__ StepTable tab, const float* __restrict__ dX,
@@ -135,6 +139,42 @@ __global__ void colsum_kernel(float* __restrict__ out, const T* __restrict__ M, 
   }
 }
 
+// bf16 matrix, 16-byte loads: CTA = 256 columns (32 lanes x 8) x 8 row-stripes over a 256-row slab.  Column sums of
+// the (N, V) dlogits (db_v) and of the (N, G*H) gate gradients (db_ih / db_hh) read the rows the GEMMs read.
+__global__ void __launch_bounds__(256) colsum_bf16v_kernel(float* __restrict__ out, const __nv_bfloat16* __restrict__ M,
+                                                           int rows, int cols, int ld) {
+  __shared__ float red[8][256 + 8];
+  const int c0 = blockIdx.x * 256 + threadIdx.x * 8;
+  const int r0 = blockIdx.y * 256, r1 = min(rows, r0 + 256);
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  if (c0 + 8 <= cols) {
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      const uint4 q = __ldcs(reinterpret_cast<const uint4*>(M + (size_t)r * ld + c0));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        s[2 * i] += f.x; s[2 * i + 1] += f.y;
+      }
+    }
+  } else if (c0 < cols) {
+    for (int r = r0 + threadIdx.y; r < r1; r += 8)
+      for (int i = 0; i < 8 && c0 + i < cols; ++i) s[i] += __bfloat162float(M[(size_t)r * ld + c0 + i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.y][threadIdx.x * 8 + i] = s[i];
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x, c = blockIdx.x * 256 + t;
+  if (c < cols) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v += red[i][t];
+    atomicAdd(out + c, v);
+  }
+}
+
 // dst[i, :width] = table[idx[i * idx_stride], :]  (nn.Embedding lookup of the decode loops, rnn.py:53)
 __global__ void gather_rows_kernel(float* __restrict__ dst, int ld_dst, const float* __restrict__ table, int width,
                                    const int64_t* __restrict__ idx, int idx_stride) {
@@ -166,16 +206,17 @@ __global__ void rowsum_bf16_kernel(float* __restrict__ out, const __nv_bfloat16*
   if (lane == 0) out[r] = s;
 }
 
-__global__ void shift_states_kernel(const __grid_constant__ StepTable tab, float* __restrict__ Hprev,
-                                    const float* __restrict__ Hs, const float* __restrict__ h0, int H) {
+template <typename T>
+__global__ void shift_states_kernel(const __grid_constant__ StepTable tab, T* __restrict__ Hprev,
+                                    const T* __restrict__ Hs, const T* __restrict__ h0, int H) {
   const int n = blockIdx.x;
   int t, b;
   row_to_tb(tab, n, t, b);
-  float* dst = Hprev + (size_t)n * H;
+  T* dst = Hprev + (size_t)n * H;
   if (t == 0) {
-    for (int e = threadIdx.x; e < H; e += blockDim.x) dst[e] = h0 ? h0[(size_t)b * H + e] : 0.f;
+    for (int e = threadIdx.x; e < H; e += blockDim.x) dst[e] = h0 ? h0[(size_t)b * H + e] : T(0.f);
   } else {
-    const float* src = Hs + (size_t)(tab.off[t - 1] + b) * H;
+    const T* src = Hs + (size_t)(tab.off[t - 1] + b) * H;
     for (int e = threadIdx.x; e < H; e += blockDim.x) dst[e] = src[e];
   }
 }
@@ -230,8 +271,25 @@ int st_pack_inputs(float* X, int ldx, const float* emb, int E, int V, const floa
   ST_REQUIRE(E >= 1 && ldx >= E && V >= 1, ST_ERR_BAD_SHAPE, "st_pack_inputs: E=%d ldx=%d V=%d", E, ldx, V);
   ST_REQUIRE(nsteps <= T_cap + (with_feature ? 1 : 0), ST_ERR_BAD_SHAPE,
              "st_pack_inputs: nsteps=%d exceeds caption length %d", nsteps, T_cap);
-  pack_inputs_kernel<<<tab.off[nsteps], 128, 0, as_stream(stream)>>>(tab, X, ldx, emb, E, V, feature,
-                                                                     caption, T_cap, with_feature, token_status());
+  pack_inputs_kernel<float><<<tab.off[nsteps], 128, 0, as_stream(stream)>>>(tab, X, ldx, emb, E, V, feature,
+                                                                            caption, T_cap, with_feature, token_status());
+  ST_LAUNCH_TRY("pack_inputs_kernel");
+  return ST_OK;
+}
+
+int st_pack_inputs_bf16(void* X, int ldx, const float* emb, int E, int V, const float* feature,
+                        const int64_t* caption, int T_cap, int with_feature, int nsteps,
+                        const int* batch_sizes_host, st_stream_t stream) {
+  using namespace st;
+  StepTable tab;
+  ST_TRY(make_step_table(tab, nsteps, batch_sizes_host));
+  ST_REQUIRE(X && emb && caption, ST_ERR_NULL, "st_pack_inputs_bf16: NULL pointer");
+  ST_REQUIRE(!with_feature || feature, ST_ERR_NULL, "st_pack_inputs_bf16: feature is NULL");
+  ST_REQUIRE(E >= 1 && ldx >= E && V >= 1, ST_ERR_BAD_SHAPE, "st_pack_inputs_bf16: E=%d ldx=%d V=%d", E, ldx, V);
+  ST_REQUIRE(nsteps <= T_cap + (with_feature ? 1 : 0), ST_ERR_BAD_SHAPE,
+             "st_pack_inputs_bf16: nsteps=%d exceeds caption length %d", nsteps, T_cap);
+  pack_inputs_kernel<__nv_bfloat16><<<tab.off[nsteps], 128, 0, as_stream(stream)>>>(
+      tab, reinterpret_cast<__nv_bfloat16*>(X), ldx, emb, E, V, feature, caption, T_cap, with_feature, token_status());
   ST_LAUNCH_TRY("pack_inputs_kernel");
   return ST_OK;
 }
@@ -286,7 +344,10 @@ int st_colsum(float* out, const void* M, int m_is_bf16, int rows, int cols, int 
   if (rows == 0) return ST_OK;
   dim3 grid((cols + 31) / 32, (rows + 255) / 256), block(32, 8);
   ST_REQUIRE(grid.y <= 65535, ST_ERR_BAD_SHAPE, "st_colsum: too many rows (%d)", rows);
-  if (m_is_bf16)
+  if (m_is_bf16 && (ld & 7) == 0 && (reinterpret_cast<uintptr_t>(M) & 15) == 0 && cols >= 64) {
+    dim3 gv((cols + 255) / 256, (rows + 255) / 256);
+    colsum_bf16v_kernel<<<gv, block, 0, s>>>(out, reinterpret_cast<const __nv_bfloat16*>(M), rows, cols, ld);
+  } else if (m_is_bf16)
     colsum_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(out, reinterpret_cast<const __nv_bfloat16*>(M), rows, cols, ld);
   else
     colsum_kernel<float><<<grid, block, 0, s>>>(out, reinterpret_cast<const float*>(M), rows, cols, ld);
@@ -321,7 +382,21 @@ int st_shift_states(float* Hprev, const float* Hs, const float* h0, int H, int n
   ST_TRY(make_step_table(tab, nsteps, batch_sizes_host));
   ST_REQUIRE(Hprev && Hs, ST_ERR_NULL, "st_shift_states: NULL pointer");
   ST_REQUIRE(H >= 1, ST_ERR_BAD_SHAPE, "st_shift_states: H=%d", H);
-  shift_states_kernel<<<tab.off[nsteps], 128, 0, as_stream(stream)>>>(tab, Hprev, Hs, h0, H);
+  shift_states_kernel<float><<<tab.off[nsteps], 128, 0, as_stream(stream)>>>(tab, Hprev, Hs, h0, H);
+  ST_LAUNCH_TRY("shift_states_kernel");
+  return ST_OK;
+}
+
+int st_shift_states_bf16(void* Hprev, const void* Hs, const void* h0, int H, int nsteps,
+                         const int* batch_sizes_host, st_stream_t stream) {
+  using namespace st;
+  StepTable tab;
+  ST_TRY(make_step_table(tab, nsteps, batch_sizes_host));
+  ST_REQUIRE(Hprev && Hs, ST_ERR_NULL, "st_shift_states_bf16: NULL pointer");
+  ST_REQUIRE(H >= 1, ST_ERR_BAD_SHAPE, "st_shift_states_bf16: H=%d", H);
+  shift_states_kernel<__nv_bfloat16><<<tab.off[nsteps], 128, 0, as_stream(stream)>>>(
+      tab, reinterpret_cast<__nv_bfloat16*>(Hprev), reinterpret_cast<const __nv_bfloat16*>(Hs),
+      reinterpret_cast<const __nv_bfloat16*>(h0), H);
   ST_LAUNCH_TRY("shift_states_kernel");
   return ST_OK;
 }

@@ -439,7 +439,7 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
       if (threadIdx.x == 64) stamp(p.tl, t, 1);
       if (lane == 0) red_release_gpu_add(p.barrier + blockIdx.y, 1);
     }
-    if (is_epi && r_ok) {  // off the critical path: transposed copies for the hoisted weight-gradient GEMMs
+    if (is_epi && r_ok && p.dGT) {  // optional (NULL: the weight-gradient GEMMs read dG in place, MN-major): transposed copies
       const size_t n = (size_t)tab.off[t] + b;
 #pragma unroll
       for (int g = 0; g < G; ++g)
@@ -597,7 +597,7 @@ int try_tc_bwd(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cudaS
     ST_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, grid, dim3(NTH), args, smem, s));
   }
   note_launch();
-  if (p.t_lo == 0 && p.dbih != nullptr) {
+  if (p.t_lo == 0 && p.dbih != nullptr && p.dGT != nullptr) {
     // bias gradients = row sums of the transposed gate gradients (contiguous per gate row)
     ST_TRY(st_rowsum_bf16(p.dbih, p.dGT, GH, N, p.ldt, s));
     if (p.dGhT != p.dGT) ST_TRY(st_rowsum_bf16(p.dbhh, p.dGhT, GH, N, p.ldt, s));
@@ -662,14 +662,15 @@ int st_rnn_seq_tc_bwd(int kind, int H, int nsteps, const int* batch_sizes_host, 
   ST_REQUIRE(kind == ST_GRU || kind == ST_LSTM, ST_ERR_UNSUPPORTED, "st_rnn_seq_tc_bwd: kind=%d", kind);
   ST_REQUIRE(st_rnn_seq_tc_supported(kind, H), ST_ERR_UNSUPPORTED,
              "st_rnn_seq_tc_bwd: H=%d must be a multiple of 16 and <= %d", H, 64 * MAXKB);
-  ST_REQUIRE(WhhT_bf16 && Hs && gates && dHs && dG && dGT && dstate && barrier, ST_ERR_NULL,
+  ST_REQUIRE(WhhT_bf16 && Hs && gates && dHs && dG && dstate && barrier, ST_ERR_NULL,
              "st_rnn_seq_tc_bwd: NULL pointer");
+  ST_REQUIRE(dGT || !dbih, ST_ERR_NULL, "st_rnn_seq_tc_bwd: bias gradients are formed from dGT (pass both or neither)");
   ST_REQUIRE((dbih == nullptr) == (dbhh == nullptr), ST_ERR_NULL, "st_rnn_seq_tc_bwd: dbih/dbhh go together");
   ST_REQUIRE(0 <= t_lo && t_lo < t_hi && t_hi <= nsteps, ST_ERR_BAD_SHAPE,
              "st_rnn_seq_tc_bwd: step range [%d,%d) outside [0,%d)", t_lo, t_hi, nsteps);
   ST_REQUIRE(kind == ST_GRU || Cs, ST_ERR_NULL, "st_rnn_seq_tc_bwd: LSTM needs Cs");
-  ST_REQUIRE(kind == ST_LSTM || (ghn && dGh && dGhT), ST_ERR_NULL, "st_rnn_seq_tc_bwd: GRU needs ghn, dGh, dGhT");
-  ST_REQUIRE(ldt >= tab.off[nsteps] && ldt % 8 == 0, ST_ERR_BAD_SHAPE, "st_rnn_seq_tc_bwd: ldt=%d", ldt);
+  ST_REQUIRE(kind == ST_LSTM || (ghn && dGh && (dGhT || !dGT)), ST_ERR_NULL, "st_rnn_seq_tc_bwd: GRU needs ghn, dGh (and dGhT with dGT)");
+  ST_REQUIRE(!dGT || (ldt >= tab.off[nsteps] && ldt % 8 == 0), ST_ERR_BAD_SHAPE, "st_rnn_seq_tc_bwd: ldt=%d", ldt);
   if (kind == ST_LSTM) { dGh = dG; dGhT = dGT; }
   TcBwdParams p{g_timeline, H, t_hi, t_lo, nsteps, nsteps, h0, c0, Hs, Cs, gates, ghn, dHs,
                 reinterpret_cast<__nv_bfloat16*>(dG), reinterpret_cast<__nv_bfloat16*>(dGT),

@@ -431,12 +431,14 @@ rnn_step_x_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_
       st8bf(p.dGh + n * (size_t)GH + H + uu, da[1]);
       st8bf(p.dGh + n * (size_t)GH + 2 * H + uu, dan_r);
     }
-    // transposed copies for the hoisted weight-gradient GEMMs (not on the step's critical path)
+    // optional (NULL: the weight-gradient GEMMs read dG in place, MN-major): transposed copies
+    if (p.dGT) {
 #pragma unroll
-    for (int g = 0; g < G; ++g)
+      for (int g = 0; g < G; ++g)
 #pragma unroll
-      for (int j = 0; j < HALF; ++j) p.dGT[(size_t)(g * H + uu + j) * p.ldt + n] = __float2bfloat16(da[g][j]);
-    if (G == 3) {
+        for (int j = 0; j < HALF; ++j) p.dGT[(size_t)(g * H + uu + j) * p.ldt + n] = __float2bfloat16(da[g][j]);
+    }
+    if (G == 3 && p.dGT) {
 #pragma unroll
       for (int j = 0; j < HALF; ++j) {
         p.dGhT[(size_t)(uu + j) * p.ldt + n] = __float2bfloat16(da[0][j]);
@@ -634,12 +636,12 @@ int st_rnn_step_x_tc_bwd(int kind, int H, int nsteps, const int* batch_sizes_hos
              ST_ERR_UNSUPPORTED, "st_rnn_step_x_tc_bwd: attention width A=%d must be a multiple of 64 and <= %d", A, 64 * MAXKB);
   ST_REQUIRE(H % 64 == 0 && H >= 64 && H <= 64 * MAXKB, ST_ERR_UNSUPPORTED,
              "st_rnn_step_x_tc_bwd: H=%d must be a multiple of 64 and <= %d (and equal the context width)", H, 64 * MAXKB);
-  ST_REQUIRE(WhhT_bf16 && WxT_bf16 && Hs && gates && dHs && dG && dGT && dstate && dX && barrier, ST_ERR_NULL,
+  ST_REQUIRE(WhhT_bf16 && WxT_bf16 && Hs && gates && dHs && dG && dstate && dX && barrier, ST_ERR_NULL,
              "st_rnn_step_x_tc_bwd: NULL pointer");
   ST_REQUIRE(kind == ST_GRU || Cs, ST_ERR_NULL, "st_rnn_step_x_tc_bwd: LSTM needs Cs");
-  ST_REQUIRE(kind == ST_LSTM || (ghn && dGh && dGhT), ST_ERR_NULL, "st_rnn_step_x_tc_bwd: GRU needs ghn, dGh, dGhT");
+  ST_REQUIRE(kind == ST_LSTM || (ghn && dGh && (dGhT || !dGT)), ST_ERR_NULL, "st_rnn_step_x_tc_bwd: GRU needs ghn, dGh (and dGhT with dGT)");
   ST_REQUIRE(0 <= t && t < nsteps, ST_ERR_BAD_SHAPE, "st_rnn_step_x_tc_bwd: step %d outside [0,%d)", t, nsteps);
-  ST_REQUIRE(ldt >= tab.off[nsteps] && ldt % 8 == 0 && ldx >= H && ldx % 4 == 0 && ldwxt >= (kind == ST_LSTM ? 4 : 3) * H &&
+  ST_REQUIRE((!dGT || (ldt >= tab.off[nsteps] && ldt % 8 == 0)) && ldx >= H && ldx % 4 == 0 && ldwxt >= (kind == ST_LSTM ? 4 : 3) * H &&
                  ldwxt % 8 == 0,
              ST_ERR_BAD_SHAPE, "st_rnn_step_x_tc_bwd: ldt=%d ldx=%d ldwxt=%d", ldt, ldx, ldwxt);
   if (kind == ST_LSTM) { dGh = dG; dGhT = dGT; }

@@ -16,30 +16,34 @@ from . import _lib, graphs, ops
 F32 = torch.float32
 
 
+def _bf16(X):
+    """bf16 view of an activation: as is if it already is one, else one cast."""
+    return X if X.dtype == torch.bfloat16 else ops.cast_bf16(X, True, False)[0]
+
+
 class Linear:
-    """y = x W^T + b and its backward, in the arithmetic of `mode`.  Keeps the operand copies the
-    backward GEMMs need (bf16 mode: K-major bf16 transposes for dX = dY W and dW = dY^T X)."""
+    """y = x W^T + b and its backward, in the arithmetic of `mode`.  bf16 mode keeps ONE bf16 copy of every
+    operand: the backward products dW = dY^T X and dX = dY W read X, W and dY in place as MN-major UMMA operands
+    (ops.gemm_bf16 a_t / b_t) -- no transposed copies, and the weight's bf16 shadow is cached until the optimizer
+    changes the parameter (ops.bf16_shadow)."""
 
     def __init__(self, mode, W, bias, need_bwd, tag):
         self.mode, self.W, self.bias, self.need_bwd, self.tag = mode, W, bias, need_bwd, tag
         if mode == "bf16":
-            self.Wb, self.WT = ops.cast_bf16(W, True, need_bwd)
+            self.Wb = ops.bf16_shadow(W)
 
     def fwd(self, X, XT=None, out_dtype=F32):
-        """X fp32, or (bf16 mode) already bf16 together with its transpose XT when a backward follows."""
+        """X fp32 or (bf16 mode) already bf16.  (`XT` is accepted for older callers and ignored.)"""
         if self.mode == "fp32":
             self.X = X
             return ops.sgemm(X, self.W, transB=True, bias=self.bias, tag=self.tag + "_fwd")
-        if X.dtype == torch.bfloat16:
-            Xb, self.XT = X, XT
-        else:
-            Xb, self.XT = ops.cast_bf16(X, True, self.need_bwd)
-        return ops.gemm_bf16(Xb, self.Wb, bias=self.bias, out_dtype=out_dtype, tag=self.tag + "_fwd")
+        self.Xb = _bf16(X)
+        return ops.gemm_bf16(self.Xb, self.Wb, bias=self.bias, out_dtype=out_dtype, tag=self.tag + "_fwd")
 
-    def bwd_bf16(self, dYb, dYT, need_dx=True):
-        """Backward from gate gradients that already are bf16 GEMM operands (row-major + transposed)."""
-        dW = ops.gemm_bf16(dYT, self.XT, tag=self.tag + "_dw")
-        dX = ops.gemm_bf16(dYb, self.WT, tag=self.tag + "_dx") if need_dx else None
+    def bwd_bf16(self, dYb, dYT=None, need_dx=True):
+        """Backward from gradients that already are bf16 (row-major): (dX or None, dW)."""
+        dW = ops.gemm_bf16(dYb, self.Xb, a_t=True, b_t=True, tag=self.tag + "_dw")           # dY^T X
+        dX = ops.gemm_bf16(dYb, self.Wb, b_t=True, tag=self.tag + "_dx") if need_dx else None  # dY W
         return dX, dW
 
     def bwd(self, dY, need_dx=True):
@@ -49,9 +53,7 @@ class Linear:
             dW = ops.sgemm(dY, self.X, transA=True, tag=self.tag + "_dw")
             dX = ops.sgemm(dY, self.W, tag=self.tag + "_dx") if need_dx else None
             return dX, dW, db
-        dYb, dYT = ops.cast_bf16(dY, need_dx, True)
-        dW = ops.gemm_bf16(dYT, self.XT, tag=self.tag + "_dw")
-        dX = ops.gemm_bf16(dYb, self.WT, tag=self.tag + "_dx") if need_dx else None
+        dX, dW = self.bwd_bf16(_bf16(dY), None, need_dx)
         return dX, dW, db
 
 
@@ -59,9 +61,7 @@ def weight_grad(mode, dY, X, tag):
     """dW = dY^T X for a product whose forward ran inside another kernel (W_hh)."""
     if mode == "fp32":
         return ops.sgemm(dY, X, transA=True, tag=tag)
-    _, dYT = ops.cast_bf16(dY, False, True)
-    _, XT = ops.cast_bf16(X, False, True)
-    return ops.gemm_bf16(dYT, XT, tag=tag)
+    return ops.gemm_bf16(_bf16(dY), _bf16(X), a_t=True, b_t=True, tag=tag)
 
 
 def layer_params(P, l):
@@ -78,15 +78,15 @@ def stack_forward(mode, P, kind, L, X, bs, save):
         Wih, Whh, bih, bhh = layer_params(P, l)
         lin = Linear(mode, Wih, bih, save, "ih")
         Gx = lin.fwd(inp)                                                  # W_ih x + b_ih, all steps
-        o, WhhT = None, None
+        o, tc = None, False
         if mode == "bf16" and ops.rnn_seq_tc_supported(kind, Whh.shape[1]):
-            Whh_b, WhhT = ops.cast_bf16(Whh, True, save)
-            o = ops.rnn_seq_tc_fwd(kind, Gx, Whh_b, bhh, bs, save=save, tag="seq_fwd")
+            o = ops.rnn_seq_tc_fwd(kind, Gx, ops.bf16_shadow(Whh), bhh, bs, save=save, tag="seq_fwd")
+            tc = o is not None
         if o is None:                                                      # CUDA-core recurrent kernel
-            o, WhhT = ops.rnn_seq_fwd(kind, Gx, Whh, bhh, bs, save=save, tag="seq_fwd"), None
-        layers.append({"lin": lin, "out": o, "WhhT": WhhT})
-        inp = o["Hs"]
-    return inp, layers
+            o = ops.rnn_seq_fwd(kind, Gx, Whh, bhh, bs, save=save, tag="seq_fwd")
+        layers.append({"lin": lin, "out": o, "tc": tc})
+        inp = o["Hsb"] if tc else o["Hs"]                                  # the tensor-core kernel also emits h_t as bf16
+    return layers[-1]["out"]["Hs"], layers
 
 
 def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True, dx0_ready=None):
@@ -98,18 +98,21 @@ def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True, 
     for l in reversed(range(L)):
         _, Whh, _, _ = layer_params(P, l)
         sv = layers[l]
-        Hprev = ops.shift_states(sv["out"]["Hs"], bs)
-        b = ops.rnn_seq_tc_bwd(kind, sv["WhhT"], bs, sv["out"], dH, tag="seq_bwd") if sv["WhhT"] is not None else None
-        if b is not None:                                                  # tensor-core BPTT: bf16 operands out
+        b = None
+        if sv["tc"]:
+            b = ops.rnn_seq_tc_bwd(kind, ops.bf16_shadow(Whh, transposed=True), bs, sv["out"], dH, tag="seq_bwd")
+        if b is not None:                                                  # tensor-core BPTT: bf16 gate gradients out
             need_dx = l > 0 or need_dx0
-            dH = ops.gemm_bf16(b["dGb"], sv["lin"].WT, tag="ih_dx") if need_dx else None
+            dH = ops.gemm_bf16(b["dGb"], sv["lin"].Wb, b_t=True, tag="ih_dx") if need_dx else None     # dG W_ih
             if l == 0 and dx0_ready is not None:
                 dx0_ready(dH)
-            _, HprevT = ops.cast_bf16(Hprev, False, True)
-            grads[f"unit.weight_hh_l{l}"] = ops.gemm_bf16(b["dGhT"], HprevT, tag="hh_dw")
-            grads[f"unit.bias_hh_l{l}"], grads[f"unit.bias_ih_l{l}"] = b["dbhh"], b["dbih"]
-            _, grads[f"unit.weight_ih_l{l}"] = sv["lin"].bwd_bf16(b["dGb"], b["dGT"], need_dx=False)
+            Hprev_b = ops.shift_states(sv["out"]["Hsb"], bs)
+            grads[f"unit.weight_hh_l{l}"] = ops.gemm_bf16(b["dGhb"], Hprev_b, a_t=True, b_t=True, tag="hh_dw")
+            grads[f"unit.bias_ih_l{l}"] = ops.colsum(b["dGb"])
+            grads[f"unit.bias_hh_l{l}"] = ops.colsum(b["dGhb"]) if b["dGhb"] is not b["dGb"] else grads[f"unit.bias_ih_l{l}"]
+            _, grads[f"unit.weight_ih_l{l}"] = sv["lin"].bwd_bf16(b["dGb"], None, need_dx=False)
             continue
+        Hprev = ops.shift_states(sv["out"]["Hs"], bs)
         b = ops.rnn_seq_bwd(kind, Whh, bs, sv["out"], dH, tag="seq_bwd")
         grads[f"unit.weight_hh_l{l}"] = weight_grad(mode, b["dGh"], Hprev, "hh_dw")  # dGh^T Hprev
         grads[f"unit.bias_hh_l{l}"] = ops.colsum(b["dGh"])
@@ -121,7 +124,7 @@ def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True, 
 
 
 def base_forward(mode, P, kind, L, feature, caption, bs, save):
-    X = ops.pack_inputs(P["embeddings.weight"], feature, caption, bs, True)           # rnn.py:29-31
+    X = ops.pack_inputs(P["embeddings.weight"], feature, caption, bs, True, bf16=(mode == "bf16"))   # rnn.py:29-31
     return stack_forward(mode, P, kind, L, X, bs, save)
 
 
@@ -173,7 +176,7 @@ class BaseLogitsFn(torch.autograd.Function):
         save = any(ctx.needs_input_grad)
         Hs, layers = base_forward(mode, P, mod._kind, mod.num_layers, feature_c, caption_c, bs, save)
         vocab = Linear(mode, P["linear.weight"], P["linear.bias"], save, "vocab")
-        logits = vocab.fwd(Hs)                                                        # rnn.py:33
+        logits = vocab.fwd(layers[-1]["out"]["Hsb"] if layers[-1]["tc"] else Hs)      # rnn.py:33
         ctx.names, ctx.P, ctx.mod, ctx.vocab = names, P, mod, vocab
         ctx.bs, ctx.layers, ctx.caption = bs, layers, caption_c
         ctx.feature_shape = feature_c.shape
@@ -189,13 +192,14 @@ class BaseLogitsFn(torch.autograd.Function):
         return (None, dfeat, None, None) + tuple(grads[n] for n in ctx.names)
 
 
-def vocab_ce(mode, P, Hs, target, denom, need, gout=None):
+def vocab_ce(mode, P, Hs, target, denom, need, gout=None, Hs_bf16=None):
     """Mean cross-entropy of the vocabulary projection of Hs (N,H) and, if `need`, its gradients.
     Returns (loss (0-d), dHs or None, grads dict, event).  bf16 mode: the weight / bias gradients do
     not feed the rest of the backward pass, so they run on the side stream (ops.fork) beside the BPTT
     kernels; `event` marks their completion (None when they ran in line) -- ops.join it, or hand it to
     the gradient reducer, before the gradients are read.  `gout`: optional [dW, db] output tensors (a
-    gradient reducer's symmetric bucket) for bf16 mode."""
+    gradient reducer's symmetric bucket) for bf16 mode.  `Hs_bf16`: the bf16 copy of Hs the recurrent kernel
+    already wrote (else Hs is cast once)."""
     Wv, bv = P["linear.weight"], P["linear.bias"]
     grads = {}
     if mode == "fp32":
@@ -208,17 +212,19 @@ def vocab_ce(mode, P, Hs, target, denom, need, gout=None):
             grads["linear.bias"] = ops.colsum(dl)
             dHs = ops.sgemm(dl, Wv, tag="vocab_dx")                                   # dlogits W_v
         return (loss_sum / denom).reshape(()), dHs, grads, None
-    Wb, WT = ops.cast_bf16(Wv, True, need)
-    Hb, HT = ops.cast_bf16(Hs, True, need)
+    Wb = ops.bf16_shadow(Wv)
+    Hb = Hs_bf16 if Hs_bf16 is not None else _bf16(Hs)
     loss_sum, lse = ops.vocab_ce_fwd(Hb, Wb, bv, target, tag="vocab_fwd")
     dHs, done = None, None
     if need:
-        Pm, PT = ops.vocab_ce_bwd(Hb, Wb, bv, target, lse, 1.0 / denom, tag="vocab_dlogits")
+        # dlogits = (softmax - onehot) / denom recomputed tile by tile and written ONCE, row-major bf16; the three
+        # products below read it in place: dW = dlogits^T Hs (both operands MN-major), db = column sums, dHs = dlogits W_v
+        Pm, _ = ops.vocab_ce_bwd(Hb, Wb, bv, target, lse, 1.0 / denom, want_t=False, tag="vocab_dlogits")
         (grads["linear.weight"], grads["linear.bias"]), done = ops.fork(
-            lambda: (ops.gemm_bf16(PT, HT, tag="vocab_dw", out=gout[0] if gout else None),
-                     ops.rowsum_bf16(PT, out=gout[1] if gout else None)),             # db_v = row sums of dlogits^T
-            uses=(PT, HT))
-        dHs = ops.gemm_bf16(Pm, WT, tag="vocab_dx")
+            lambda: (ops.gemm_bf16(Pm, Hb, a_t=True, b_t=True, tag="vocab_dw", out=gout[0] if gout else None),
+                     ops.colsum(Pm, out=gout[1] if gout else None)),
+            uses=(Pm, Hb))
+        dHs = ops.gemm_bf16(Pm, Wb, b_t=True, tag="vocab_dx")
     return (loss_sum / denom).reshape(()), dHs, grads, done
 
 
@@ -248,7 +254,8 @@ class BaseLossFn(torch.autograd.Function):
             Hs, layers = base_forward(mode, P, kind, L, feat, cap, bs, need)
             target = ops.pack_targets(cap, bs, P["linear.weight"].shape[0])
             gout = red.slots([P["linear.weight"].shape, P["linear.bias"].shape]) if (red is not None and need) else None
-            loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, denom, need, gout=gout)
+            loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, denom, need, gout=gout,
+                                               Hs_bf16=layers[-1]["out"]["Hsb"] if layers[-1]["tc"] else None)
             dfeat = None
             if need and red is None:
                 dfeat = base_backward_from_dHs(mode, P, kind, L, cap, bs, layers, dHs, grads, want_dfeat, feat.shape)

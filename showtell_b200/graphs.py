@@ -73,6 +73,7 @@ def run(mod, key, body, inputs):
             cache.clear()
         e = cache[key] = _Entry()
     if e.graph is not None:
+        ops.refresh_shadows()                     # bf16 weight shadows live outside the graph (ops.bf16_shadow)
         for dst, src in zip(e.static_in, inputs):
             dst.copy_(src, non_blocking=True)
         e.graph.replay()
@@ -83,6 +84,7 @@ def run(mod, key, body, inputs):
         return body(*inputs)
     try:
         static_in = [t.clone() for t in inputs]
+        ops.refresh_shadows()                     # fresh before capture: no cast becomes part of the graph
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, capture_error_mode="relaxed"):

@@ -101,12 +101,19 @@ def sgemm(A, B, *, transA=False, transB=False, bias=None, out=None, alpha=1.0, b
     return out
 
 
-def pack_inputs(emb, feature, caption, bs, with_feature, width=None):
+def pack_inputs(emb, feature, caption, bs, with_feature, width=None, bf16=False):
     """Packed inputs (N, width >= E); only the first E columns are written (attention models use
-    width = 2E and let the attention kernel fill the other half)."""
+    width = 2E and let the attention kernel fill the other half).  bf16: rows written as bf16 (the operand of the
+    hoisted tensor-core input projection), row stride padded to a multiple of 8."""
     lib = _lib.load()
     _lib.raise_token_error()
     N, E = sum(bs), emb.shape[1]
+    if bf16:
+        X = torch.empty(N, ((width or E) + 7) // 8 * 8, dtype=torch.bfloat16, device=emb.device)[:, :width or E]
+        check(lib.st_pack_inputs_bf16(_raw(X), X.stride(0), ptr(emb, F32), E, emb.shape[0],
+                                      ptr(feature, F32) if with_feature else None, ptr(caption, I64), caption.shape[1],
+                                      int(with_feature), len(bs), int_array(bs), stream_ptr()), "st_pack_inputs_bf16")
+        return X
     X = torch.empty(N, width or E, dtype=F32, device=emb.device)
     check(lib.st_pack_inputs(ptr(X, F32), X.shape[1], ptr(emb, F32), E, emb.shape[0],
                              ptr(feature, F32) if with_feature else None,
@@ -232,8 +239,13 @@ def rnn_seq_bwd(kind, Whh, bs, saved, dHs, *, h0=None, c0=None, t_range=None, ou
 
 
 def shift_states(Hs, bs, h0=None):
+    """Hprev[n=(t,b)] = Hs[(t-1,b)] (h0[b] or 0 at t = 0); fp32 or bf16 rows."""
     lib = _lib.load()
     out = torch.empty_like(Hs)
+    if Hs.dtype == torch.bfloat16:
+        check(lib.st_shift_states_bf16(ptr(out, Hs.dtype), ptr(Hs, Hs.dtype), ptr(h0, Hs.dtype) if h0 is not None else None,
+                                       Hs.shape[1], len(bs), int_array(bs), stream_ptr()), "st_shift_states_bf16")
+        return out
     check(lib.st_shift_states(ptr(out, F32), ptr(Hs, F32), ptr(h0, F32), Hs.shape[1], len(bs),
                               int_array(bs), stream_ptr()), "st_shift_states")
     return out
@@ -290,6 +302,10 @@ BF16 = torch.bfloat16
 def _raw(t):
     import ctypes as C
     return C.c_void_p(t.data_ptr())
+
+
+def _rawn(t):
+    return _raw(t) if t is not None else None
 
 
 def gemm_bf16(A, B, *, bias=None, out_dtype=F32, alpha=1.0, beta=0.0, out=None, tag=None, a_t=False, b_t=False):
@@ -363,6 +379,78 @@ def cast_bf16(src, want=True, want_t=False):
                            d.stride(0) if want else 0, _raw(dT) if want_t else None,
                            dT.stride(0) if want_t else 0, stream_ptr()), "st_cast_bf16")
     return d, dT
+
+
+# ---- bf16 shadows of the fp32 master parameters.
+# The tensor-core kernels read bf16 weights; the parameters stay fp32 nn.Parameters (optimizer / checkpoint
+# compatible).  Each parameter gets ONE persistent bf16 copy (stable pointer, so CUDA-graph replays keep reading it)
+# that is re-cast only when the parameter changed: torch bumps `Tensor._version` on every in-place update (optimizer
+# steps, load_state_dict), and showtell_b200.optim writes the shadow inside its own update kernel.  A transposed
+# copy exists only where a kernel needs one as a K-major TMA operand (W_hh^T in the BPTT kernels); the GEMMs take
+# operands in either major (gemm_bf16 a_t / b_t).  Writes through `.data` bypass the version counter: call
+# invalidate_shadows() after such a write.
+class _Shadow:
+    __slots__ = ("buf", "version", "param")
+
+
+_SHADOWS = {}
+
+
+def _shadow_key(W, transposed):
+    return (W.data_ptr(), tuple(W.shape), tuple(W.stride()), bool(transposed))
+
+
+def _shadow_cast(W, sh, transposed):
+    lib = _lib.load()
+    R, Cc = W.shape
+    check(lib.st_cast_bf16(_raw(W), R, Cc, W.stride(0), None if transposed else _raw(sh.buf),
+                           0 if transposed else sh.buf.stride(0), _raw(sh.buf) if transposed else None,
+                           sh.buf.stride(0) if transposed else 0, stream_ptr()), "st_cast_bf16")
+    sh.version = W._version
+
+
+def bf16_shadow(W, transposed=False):
+    """bf16 copy (or bf16 transpose) of a 2-D fp32 parameter / parameter view, cached until the parameter changes."""
+    if W.dim() != 2 or W.dtype != F32 or not W.is_cuda or W.stride(1) != 1:
+        raise ValueError("bf16_shadow: 2-D fp32 CUDA tensor with unit inner stride expected")
+    key = _shadow_key(W, transposed)
+    sh = _SHADOWS.get(key)
+    if sh is None:
+        if len(_SHADOWS) > 512:
+            _SHADOWS.clear()
+        R, Cc = (W.shape[1], W.shape[0]) if transposed else W.shape
+        sh = _SHADOWS[key] = _Shadow()
+        sh.buf = torch.empty(R, (Cc + 7) // 8 * 8, dtype=BF16, device=W.device)[:, :Cc]
+        sh.version, sh.param = None, W
+    if sh.version != W._version:
+        _shadow_cast(W, sh, transposed)
+    return sh.buf
+
+
+def refresh_shadows():
+    """Re-cast every stale shadow (called before a captured step is replayed: the graph reads the shadows, the
+    casts are deliberately not part of it)."""
+    for key, sh in _SHADOWS.items():
+        if sh.version != sh.param._version:
+            _shadow_cast(sh.param, sh, key[3])
+
+
+def invalidate_shadows():
+    for sh in _SHADOWS.values():
+        sh.version = None
+
+
+def shadows_of(p):
+    """(contiguous same-index bf16 shadow or None, [other shadows]) of a parameter: the fused optimizer writes the
+    first inside its update kernel and marks the others stale."""
+    direct, others = None, []
+    for key, sh in _SHADOWS.items():
+        if key[0] == p.data_ptr() and sh.param.shape == p.shape and sh.param.stride() == p.stride() and not key[3] \
+                and sh.buf.is_contiguous():
+            direct = sh
+        elif sh.param.untyped_storage().data_ptr() == p.untyped_storage().data_ptr():
+            others.append(sh)
+    return direct, others
 
 
 def vocab_ce_fwd(Hs, Wv, bv, target, tag=None):
@@ -514,16 +602,15 @@ def rnn_step_x_tc_bwd(kind, WhhT_b, WxT_b, bs, t, saved, dHs, dX, *, h0=None, c0
     ldt = (N + 7) // 8 * 8
     o = out
     if o is None:
-        mk = lambda: (torch.empty(N, GH, dtype=BF16, device=dev), torch.empty(GH, ldt, dtype=BF16, device=dev))
-        dGb, dGT = mk()
-        dGhb, dGhT = mk() if kind == _lib.ST_GRU else (dGb, dGT)
-        o = {"dGb": dGb, "dGT_full": dGT, "dGT": dGT[:, :N], "dGhb": dGhb, "dGhT_full": dGhT, "dGhT": dGhT[:, :N],
+        dGb = torch.empty(N, GH, dtype=BF16, device=dev)         # row-major only: the GEMMs read them in place (a_t)
+        dGhb = torch.empty(N, GH, dtype=BF16, device=dev) if kind == _lib.ST_GRU else dGb
+        o = {"dGb": dGb, "dGT_full": None, "dGT": None, "dGhb": dGhb, "dGhT_full": None, "dGhT": None,
              "dbih": None, "dbhh": None, "dstate": torch.zeros(2, bs[0], H, dtype=F32, device=dev), "barrier": _barrier(dev)}
     tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
     st = lib.st_rnn_step_x_tc_bwd(kind, H, len(bs), int_array(bs), t, _raw(WhhT_b), _raw(WxT_b), WxT_b.stride(0),
                                   ptr(h0, F32), ptr(c0, F32), ptr(saved["Hs"], F32), ptr(saved["Cs"]),
                                   ptr(saved["gates"], F32), ptr(saved["ghn"]), ptr(dHs, F32), _raw(o["dGb"]),
-                                  _raw(o["dGT_full"]), _raw(o["dGhb"]), _raw(o["dGhT_full"]), ldt, ptr(o["dstate"]),
+                                  _rawn(o["dGT_full"]), _raw(o["dGhb"]), _rawn(o["dGhT_full"]), ldt, ptr(o["dstate"]),
                                   ptr(dX, F32), dX.stride(0), ptr(o["barrier"]),
                                   _raw(query[0]) if query else None, query[0].stride(0) if query else 0,
                                   _raw(query[1]) if query else None, query[1].stride(0) if query else 0,
@@ -537,18 +624,23 @@ def rnn_step_x_tc_bwd(kind, WhhT_b, WxT_b, bs, t, saved, dHs, dX, *, h0=None, c0
 
 
 def rnn_seq_tc_bwd(kind, WhhT_b, bs, saved, dHs, *, h0=None, c0=None, t_range=None, out=None, want_bias=True,
-                   tag=None):
-    """Returns dict(dGb, dGT, dGhb, dGhT, dbih, dbhh, dstate) (bf16 GEMM operands) or None if unsupported."""
+                   tag=None, transposed=False):
+    """Returns dict(dGb, dGhb, dstate[, dGT, dGhT, dbih, dbhh]) (bf16 GEMM operands) or None if unsupported.
+    transposed=False (default): only the row-major gate gradients are written -- the weight-gradient GEMMs read
+    them in place (gemm_bf16 a_t) and the bias gradients are their column sums (colsum)."""
     lib = _lib.load()
     N, H, GH = sum(bs), WhhT_b.shape[0], WhhT_b.shape[1]
     dev = dHs.device
     ldt = (N + 7) // 8 * 8
     o = out
     if o is None:
-        mk = lambda: (torch.empty(N, GH, dtype=BF16, device=dev), torch.empty(GH, ldt, dtype=BF16, device=dev))
+        mk = lambda: (torch.empty(N, GH, dtype=BF16, device=dev),
+                      torch.empty(GH, ldt, dtype=BF16, device=dev) if transposed else None)
         dGb, dGT = mk()
         dGhb, dGhT = mk() if kind == _lib.ST_GRU else (dGb, dGT)
-        o = {"dGb": dGb, "dGT_full": dGT, "dGT": dGT[:, :N], "dGhb": dGhb, "dGhT_full": dGhT, "dGhT": dGhT[:, :N],
+        want_bias = want_bias and transposed
+        o = {"dGb": dGb, "dGT_full": dGT, "dGT": dGT[:, :N] if transposed else None, "dGhb": dGhb, "dGhT_full": dGhT,
+             "dGhT": dGhT[:, :N] if transposed else None,
              "dbih": torch.empty(GH, dtype=F32, device=dev) if want_bias else None,
              "dbhh": torch.empty(GH, dtype=F32, device=dev) if want_bias else None,
              "dstate": torch.zeros(2, bs[0], H, dtype=F32, device=dev), "barrier": _barrier(dev)}
@@ -556,8 +648,8 @@ def rnn_seq_tc_bwd(kind, WhhT_b, bs, saved, dHs, *, h0=None, c0=None, t_range=No
     tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
     st = lib.st_rnn_seq_tc_bwd(kind, H, len(bs), int_array(bs), t_hi, t_lo, ptr(WhhT_b, BF16), ptr(h0, F32),
                                ptr(c0, F32), ptr(saved["Hs"], F32), ptr(saved["Cs"]), ptr(saved["gates"], F32),
-                               ptr(saved["ghn"]), ptr(dHs, F32), _raw(o["dGb"]), _raw(o["dGT_full"]),
-                               _raw(o["dGhb"]), _raw(o["dGhT_full"]), ldt, ptr(o["dbih"]), ptr(o["dbhh"]),
+                               ptr(saved["ghn"]), ptr(dHs, F32), _raw(o["dGb"]), _rawn(o["dGT_full"]),
+                               _raw(o["dGhb"]), _rawn(o["dGhT_full"]), ldt, ptr(o["dbih"]), ptr(o["dbhh"]),
                                ptr(o["dstate"]), ptr(o["barrier"]), stream_ptr())
     if st == -3:
         return None

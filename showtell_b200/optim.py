@@ -35,6 +35,26 @@ def _counts(tensors):
     return (C.c_int64 * len(tensors))(*[t.numel() for t in tensors])
 
 
+def _shadow_ptrs(params):
+    """bf16 shadows (ops.bf16_shadow) the update kernel rewrites in the same pass; other copies of a parameter
+    (transposed, sliced) are marked stale and re-cast on their next use.  Returns (pointer table or None, finish())."""
+    from . import ops
+    table, fresh, any_shadow = [], [], False
+    for p in params:
+        direct, others = ops.shadows_of(p)
+        for sh in others:
+            sh.version = None
+        table.append(direct.buf.data_ptr() if direct is not None else None)
+        if direct is not None:
+            fresh.append((direct, p))
+            any_shadow = True
+
+    def finish():
+        for sh, p in fresh:
+            sh.version = p._version           # the raw-pointer update does not bump the counter: the shadow is current
+    return ((C.c_void_p * len(params))(*table) if any_shadow else None), finish
+
+
 class SGD(torch.optim.Optimizer):
     """torch.optim.SGD(params, lr, momentum) as main.py:98 constructs it (dampening 0, no weight decay / nesterov)."""
 
@@ -78,8 +98,10 @@ class SGD(torch.optim.Optimizer):
                     part = items[i:i + _MAX]
                     ps, gs = [a for a, _, _ in part], [b for _, b, _ in part]
                     ms = _ptrs([c for _, _, c in part]) if mom != 0.0 else None
-                    _lib.check(lib.st_sgd_step(len(part), _ptrs(ps), _ptrs(gs), ms, _counts(ps), lr, mom, first, None,
+                    sh, done = _shadow_ptrs(ps)
+                    _lib.check(lib.st_sgd_step(len(part), _ptrs(ps), _ptrs(gs), ms, sh, _counts(ps), lr, mom, first, None,
                                                _lib.stream_ptr()), "st_sgd_step")
+                    done()
         return loss
 
 
@@ -126,8 +148,10 @@ class Adam(torch.optim.Optimizer):
                 for i in range(0, len(items), _MAX):
                     part = items[i:i + _MAX]
                     ps = [a for a, _, _, _ in part]
+                    sh, done = _shadow_ptrs(ps)
                     _lib.check(lib.st_adam_step(len(part), _ptrs(ps), _ptrs([b for _, b, _, _ in part]),
                                                 _ptrs([c for _, _, c, _ in part]), _ptrs([d for _, _, _, d in part]),
-                                                _counts(ps), lr, float(b1), float(b2), eps, t, None,
+                                                sh, _counts(ps), lr, float(b1), float(b2), eps, t, None,
                                                 _lib.stream_ptr()), "st_adam_step")
+                    done()
         return loss

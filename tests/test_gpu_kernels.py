@@ -141,6 +141,44 @@ def test_colsum(dev, rows, cols):
     assert rel_err(acc, M.double().sum(0) + 1) < 1e-5
 
 
+@pytest.mark.parametrize("rows,cols,ld", [(5120, 10000, 10000), (300, 2048, 2048), (1000, 777, 784), (33, 64, 72), (9, 130, 131)])
+def test_colsum_bf16(dev, rows, cols, ld):
+    """bf16 column sums (db_v from the dlogits, db_ih / db_hh from the gate gradients): vector path and fallback."""
+    from showtell_b200 import ops
+    M = torch.randn(rows, ld, device=dev).bfloat16()[:, :cols]
+    assert rel_err(ops.colsum(M), M.double().sum(0)) < 2e-5
+    acc = torch.ones(cols, device=dev)
+    ops.colsum(M, out=acc, accumulate=True)
+    assert rel_err(acc, M.double().sum(0) + 1) < 2e-5
+
+
+def test_bf16_shadows_follow_the_parameter(dev):
+    """ops.bf16_shadow: one persistent bf16 copy per parameter, re-cast when torch's version counter moves (optimizer
+    steps, load_state_dict), rewritten in place by showtell_b200.optim's own update kernel."""
+    from showtell_b200 import ops, optim
+    w = torch.nn.Parameter(torch.randn(48, 64, device=dev))
+    a = ops.bf16_shadow(w)
+    at = ops.bf16_shadow(w, transposed=True)
+    assert torch.equal(a, w.detach().bfloat16()) and torch.equal(at, w.detach().t().bfloat16())
+    assert ops.bf16_shadow(w.detach()).data_ptr() == a.data_ptr()            # detached alias: same shadow
+    with torch.no_grad():
+        w.mul_(2.0)                                                          # torch-side in-place update
+    b = ops.bf16_shadow(w)
+    assert b.data_ptr() == a.data_ptr() and torch.equal(b, w.detach().bfloat16())
+    w.grad = torch.randn_like(w)
+    for opt in (optim.SGD([w], lr=0.1, momentum=0.9), optim.Adam([w], lr=0.1)):
+        opt.step()                                                           # raw-pointer update: shadow written in the kernel
+        torch.cuda.synchronize()
+        assert torch.equal(a, w.detach().bfloat16())
+        assert torch.equal(ops.bf16_shadow(w, transposed=True), w.detach().t().bfloat16())   # stale-marked, re-cast here
+    v = w[:, 16:48]                                                          # a view (attention: halves of W_ih)
+    sv = ops.bf16_shadow(v.detach())
+    assert torch.equal(sv, v.detach().bfloat16())
+    opt.step()
+    torch.cuda.synchronize()
+    assert torch.equal(ops.bf16_shadow(v.detach()), v.detach().bfloat16())
+
+
 @pytest.mark.parametrize("N,V", [(3, 5), (40, 1000), (7, 10000)])
 def test_ce(dev, N, V):
     from showtell_b200 import ops
