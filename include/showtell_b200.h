@@ -51,6 +51,8 @@ const char* st_last_error(void);
 int64_t st_launch_count(void);
 /* Development / test aid: programmatic dependent launch of the per-step kernels on (default) / off. */
 int st_debug_set_pdl(int on);
+/* A/B timing aid: k-blocks per TMA operation of the BPTT kernel's operand ring (0 = the library's choice, 1 / 2 / 4). */
+int st_debug_set_bwd_kp(int kp);
 /* Device facts the host side sizes grids with. */
 int st_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_optin_bytes);
 

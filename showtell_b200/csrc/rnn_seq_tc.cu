@@ -286,7 +286,21 @@ rnn_seq_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
 }
 
 // --------------------------------------------------------------------------------------- backward
-constexpr int BSTAGES = 9;  // 144 KB of dGh in flight per SM: the phase-2 stream is latency-bound
+// Phase-2 operand ring.  Measured with tools/probe_stream.cu on B200: the stream of the 64 x (G*H) gate-gradient
+// tile is bound by the NUMBER of TMA operations, not by their bytes -- every operation costs ~95-190 ns of serial
+// mbarrier wait + issue in the producing thread and again in the MMA-issuing thread, whatever its size (a 64-row
+// k-block of 8 KB and a 64 KB box take the same time; one SM ingests > 300 GB/s when asked in 64 KB pieces).  So a
+// ring stage holds KP consecutive 64-wide k-blocks fetched by ONE 3-D tensor-map box {64 columns, BT rows, KP
+// k-blocks} (the row-major matrix viewed as (GH/64, N, 64)); the k-blocks land one after the other in the swizzled
+// K-major layout the UMMA descriptors expect.  KP = 4 cut the stream from 6.2 to ~1.5 us per step at B = 256.
+// KP = 1 keeps the 2-D boxes (any G*H; the 3-D view needs G*H % 64 == 0).
+template <int KP, int BT> struct RingCfg { static constexpr int STAGES = (KP == 1) ? 9 : 131072 / (KP * BT * 128); };
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 
 struct TcBwdParams {
   long long* tl;
@@ -299,18 +313,21 @@ struct TcBwdParams {
   int* barrier;
 };
 
-template <int G, int BT>
+template <int G, int BT, int KP>
 __global__ void __launch_bounds__(NTH, 1)
 rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant__ CUtensorMap tmD,
                       const __grid_constant__ StepTable tab, const TcBwdParams p) {
+  constexpr int BSTAGES = RingCfg<KP, BT>::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int H = p.H, GH = G * H, KB = (GH + 63) / 64;
   constexpr uint32_t KBLK_W = UT * 128;          // 16 rows x 128 B
   constexpr uint32_t KBLK_A = BT * 128;          // one k-block of the dGh tile
+  constexpr uint32_t STAGE_A = KP * KBLK_A;      // one ring stage: KP k-blocks
+  const int NOPS = (KB + KP - 1) / KP;           // TMA operations (= ring stages consumed) per step
   uint8_t* sW = smem;                            // [KB][16 rows][128 B]   W_hh^T slice (B operand)
-  uint8_t* sA = smem + (size_t)KB * KBLK_W;      // [BSTAGES][128 rows][128 B]  dGh ring (A operand)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)BSTAGES * KBLK_A);
+  uint8_t* sA = smem + (size_t)KB * KBLK_W;      // [BSTAGES][KP][BT rows][128 B]  dGh ring (A operand)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)BSTAGES * STAGE_A);
   uint64_t* wbar = bars;
   uint64_t* accbar = bars + 1;
   uint64_t* full = bars + 2;
@@ -462,11 +479,12 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
       stamp(p.tl, t, 2);
       proxy_fence_global();
       const int rbase = tab.off[t] + r0;
-      for (int kb = 0; kb < KB; ++kb) {
+      for (int op = 0; op < NOPS; ++op) {
         mbar_wait(&empty[stage_p], phase_p ^ 1);
         if (elect_one()) {
-          mbar_expect_tx(&full[stage_p], KBLK_A);
-          tma_load_2d(sA + (size_t)stage_p * KBLK_A, &tmD, kb * 64, rbase, &full[stage_p]);
+          mbar_expect_tx(&full[stage_p], STAGE_A);   // k-blocks past the last one are zero-filled, bytes still count
+          if (KP == 1) tma_load_2d(sA + (size_t)stage_p * STAGE_A, &tmD, op * 64, rbase, &full[stage_p]);
+          else tma_load_3d(sA + (size_t)stage_p * STAGE_A, &tmD, 0, rbase, op * KP, &full[stage_p]);
         }
         __syncwarp();
         if (++stage_p == BSTAGES) { stage_p = 0; phase_p ^= 1; }
@@ -475,16 +493,24 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
       if (!w_ready) { mbar_wait(wbar, 0); w_ready = true; }
       constexpr uint32_t idesc = umma_idesc(BT, UT);
       const uint64_t adesc0 = umma_desc_k128(smem_u32(sA)), bdesc0 = umma_desc_k128(smem_u32(sW));
-      for (int kb = 0; kb < KB; ++kb) {
+      for (int op = 0; op < NOPS; ++op) {
         mbar_wait(&full[stage_c], phase_c);
-        if (kb == 0) stamp(p.tl, t, 3);
-        if (kb == KB - 1) stamp(p.tl, t, 4);
+        if (op == 0) stamp(p.tl, t, 3);
+        if (op == NOPS - 1) stamp(p.tl, t, 4);
         tc_fence_after();
         // descriptor address fields are in 16-byte units: + stage / k-block offset, + 2 per 16-element k-step
-        const uint64_t ad = adesc0 + (uint64_t)(stage_c * (KBLK_A >> 4)), bd = bdesc0 + (uint64_t)(kb * (KBLK_W >> 4));
+        const uint64_t ad = adesc0 + (uint64_t)(stage_c * (STAGE_A >> 4));
         if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) tc_mma(tmem_base, ad + 2 * kk, bd + 2 * kk, idesc, (kb | kk) != 0);
+          for (int j = 0; j < KP; ++j) {
+            const int kb = op * KP + j;
+            if (kb < KB) {
+              const uint64_t bd = bdesc0 + (uint64_t)(kb * (KBLK_W >> 4));
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                tc_mma(tmem_base, ad + (uint64_t)(j * (KBLK_A >> 4)) + 2 * kk, bd + 2 * kk, idesc, (kb | kk) != 0);
+            }
+          }
           tc_commit(&empty[stage_c]);
         }
         __syncwarp();
@@ -568,11 +594,40 @@ int launch_tc_fwd(const StepTable& tab, TcFwdParams p, const void* Whh_bf16, con
   return ST_OK;
 }
 
-template <int G, int BT>
+// gate-gradient matrix (N, GH) bf16 viewed as (GH/64 k-blocks, N rows, 64 columns): box {64, box_rows, kp}, SW128
+int make_tmap_kblocks(CUtensorMap* map, const void* ptr, int rows, int GH, int box_rows, int kp) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn enc = nullptr;
+  if (!enc) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    ST_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q));
+    ST_REQUIRE(sym != nullptr && q == cudaDriverEntryPointSuccess, ST_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    enc = reinterpret_cast<EncodeFn>(sym);
+  }
+  ST_REQUIRE(ptr && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && GH % 64 == 0, ST_ERR_BAD_SHAPE,
+             "rnn_seq_tc_bwd: the k-block view needs a 16-byte aligned matrix with G*H %% 64 == 0");
+  cuuint64_t dims[3] = {64, (cuuint64_t)rows, (cuuint64_t)(GH / 64)};
+  cuuint64_t strides[2] = {(cuuint64_t)GH * 2, 128};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)kp};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ST_REQUIRE(r == CUDA_SUCCESS, ST_ERR_CUDA, "cuTensorMapEncodeTiled(dGh k-block view) failed with CUresult %d", (int)r);
+  return ST_OK;
+}
+
+int g_bwd_kp = 0;   // st_debug_set_bwd_kp: 0 = choose, 1 / 2 / 4 = k-blocks per TMA operation (A/B timing)
+
+template <int G, int BT, int KP>
 int try_tc_bwd(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cudaStream_t s, bool* launched) {
+  constexpr int BSTAGES = RingCfg<KP, BT>::STAGES;
   const int H = p.H, GH = G * H, KB = (GH + 63) / 64, N = tab.off[tab.nsteps];
-  const size_t smem = 1024 + (size_t)KB * (UT * 128) + (size_t)BSTAGES * (BT * 128) + 256;
-  auto kern = rnn_seq_tc_bwd_kernel<G, BT>;
+  const size_t smem = 1024 + (size_t)KB * (UT * 128) + (size_t)BSTAGES * KP * (BT * 128) + 256;
+  auto kern = rnn_seq_tc_bwd_kernel<G, BT, KP>;
   ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(H / UT, (tab.bs[p.t_lo] + BT - 1) / BT);
   int cores = 0;
@@ -584,7 +639,8 @@ int try_tc_bwd(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cudaS
   if (!*launched) return ST_OK;
   CUtensorMap tmWT, tmD;
   ST_TRY(make_tmap(&tmWT, WhhT_bf16, H, GH, GH, UT, "WhhT_bf16"));
-  ST_TRY(make_tmap(&tmD, p.dGh, N, GH, GH, BT, "dGh_bf16"));
+  if (KP == 1) ST_TRY(make_tmap(&tmD, p.dGh, N, GH, GH, BT, "dGh_bf16"));
+  else ST_TRY(make_tmap_kblocks(&tmD, p.dGh, N, GH, BT, KP));
   // Barrier counters are zeroed by the launch that starts a reverse pass (t_hi == nsteps); later launches
   // of the pass continue them (TcBwdParams::t_zero), which spares a memset node per step.
   if (p.t_hi == p.nsteps) ST_CUDA_TRY(cudaMemsetAsync(p.barrier, 0, sizeof(int) * 64, s));
@@ -609,8 +665,15 @@ int try_tc_bwd(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cudaS
 template <int G>
 int launch_tc_bwd(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cudaStream_t s) {
   bool ok = false;
-  ST_TRY((try_tc_bwd<G, 64>(tab, p, WhhT_bf16, s, &ok)));
-  if (!ok) ST_TRY((try_tc_bwd<G, 128>(tab, p, WhhT_bf16, s, &ok)));
+  const int GH = G * p.H;
+  // k-blocks per TMA operation: 4 when they tile the K extent (G*H % 256 == 0), else 2 (% 128), else 2-D boxes
+  int kp = (GH % 256 == 0) ? 4 : ((GH % 128 == 0) ? 2 : 1);
+  if (g_bwd_kp == 1 || (g_bwd_kp == 2 && GH % 128 == 0) || (g_bwd_kp == 4 && GH % 256 == 0)) kp = g_bwd_kp;
+  if (kp == 4) ST_TRY((try_tc_bwd<G, 64, 4>(tab, p, WhhT_bf16, s, &ok)));
+  else if (kp == 2) ST_TRY((try_tc_bwd<G, 64, 2>(tab, p, WhhT_bf16, s, &ok)));
+  else ST_TRY((try_tc_bwd<G, 64, 1>(tab, p, WhhT_bf16, s, &ok)));
+  if (!ok && kp >= 2) ST_TRY((try_tc_bwd<G, 128, 2>(tab, p, WhhT_bf16, s, &ok)));
+  if (!ok) ST_TRY((try_tc_bwd<G, 128, 1>(tab, p, WhhT_bf16, s, &ok)));
   ST_REQUIRE(ok, ST_ERR_UNSUPPORTED, "rnn_seq_tc_bwd: batch %d x H %d is not co-resident", tab.bs[0], p.H);
   return ST_OK;
 }
@@ -619,6 +682,11 @@ int launch_tc_bwd(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cu
 }  // namespace st
 
 extern "C" {
+
+int st_debug_set_bwd_kp(int kp) {
+  st::g_bwd_kp = (kp == 1 || kp == 2 || kp == 4) ? kp : 0;
+  return ST_OK;
+}
 
 /* development aid: device buffer of (nsteps * 8) int64 receiving %globaltimer stamps of CTA (0,0) */
 void st_debug_set_timeline(void* dev_ptr) { st::g_timeline = reinterpret_cast<long long*>(dev_ptr); }
