@@ -14,7 +14,7 @@ Metric: training tokens/s, whole job.  Without an explicit --workload the same r
 the north-star's other two headline workloads at the same N (attention-GRU training, configs[2];
 beam-3 decoding, configs[4]) and reports them under "others" in the one JSON line.
 
-Our arm times the repo's public API (forward_loss + backward, or sentence_index) with CUDA events
+Our arm times the repo's public API (forward_backward = forward + loss + backward, or sentence_index) with CUDA events
 on the launching stream; `value` has the batch resident in HBM, `e2e` copies every step's inputs
 from pinned host memory (double-buffered on a copy stream, so step i+1's copy runs under step i's
 kernels) and reads the result back every step.  Between timed steps a 256 MiB buffer is rewritten
@@ -344,14 +344,13 @@ def run_ours(name, args, steps, warmup, rank, world, local, want_refs):
     def step(f, c):
         if is_beam:
             return net.sentence_index(f, beam_size=Pn, max_len=max_len)          # utils.py:194
-        for p in params:
-            p.grad = None
+        # the training iteration of main.py:146-151 / main_attn.py:127-133 (zero_grad, forward, loss, backward) through
+        # the library's fused entry point: loss + .grad of every parameter in one call
         if model.startswith("attn"):
-            loss, _ = net.forward_loss(f, c, lengths, alpha_c=1.0, global_tokens=units_per_step,
-                                       global_batch=B * world)
+            loss, _ = net.forward_backward(f, c, lengths, alpha_c=1.0, global_tokens=units_per_step,
+                                           global_batch=B * world)
         else:
-            loss = net.forward_loss(f, c, lengths, global_tokens=units_per_step)
-        loss.backward()
+            loss = net.forward_backward(f, c, lengths, global_tokens=units_per_step)
         if opt is not None:
             opt.step()                                                            # main.py:152
         return loss

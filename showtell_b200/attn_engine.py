@@ -326,6 +326,9 @@ class AttnLogitsFn(torch.autograd.Function):
         names = [n for n, _ in mod.named_parameters()]
         P = {n: p.detach() for n, p in zip(names, params)}
         mode = mod.compute_dtype
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("showtell_b200 attention decoders produce no gradient for cnn_feature (the reference "
+                                      "detaches the grid, Attention/cnn_attn.py:47): pass cnn_feature.detach()")
         f = feature.detach().contiguous()
         f = f if f.dtype == BF16 else f.to(F32)       # bf16 grids (autocast trunk) are consumed as they are
         cap = caption.contiguous()
@@ -359,6 +362,9 @@ class AttnLossFn(torch.autograd.Function):
         names = [n for n, _ in mod.named_parameters()]
         P = {n: p.detach() for n, p in zip(names, params)}
         mode = mod.compute_dtype
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("showtell_b200 attention decoders produce no gradient for cnn_feature (the reference "
+                                      "detaches the grid, Attention/cnn_attn.py:47): pass cnn_feature.detach()")
         f = feature.detach().contiguous()
         f = f if f.dtype == BF16 else f.to(F32)       # bf16 grids (autocast trunk) are consumed as they are
         cap = caption.contiguous()

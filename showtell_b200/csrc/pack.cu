@@ -150,7 +150,22 @@ __global__ void __launch_bounds__(256) colsum_bf16v_kernel(float* __restrict__ o
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = 0.f;
   if (c0 + 8 <= cols) {
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+    int r = r0 + threadIdx.y;
+    for (; r + 24 < r1; r += 32) {                 // four independent 16-byte loads in flight per thread
+      uint4 q[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = __ldcs(reinterpret_cast<const uint4*>(M + (size_t)(r + 8 * u) * ld + c0));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q[u]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(h[i]);
+          s[2 * i] += f.x; s[2 * i + 1] += f.y;
+        }
+      }
+    }
+    for (; r < r1; r += 8) {
       const uint4 q = __ldcs(reinterpret_cast<const uint4*>(M + (size_t)r * ld + c0));
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll

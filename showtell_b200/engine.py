@@ -228,6 +228,30 @@ def vocab_ce(mode, P, Hs, target, denom, need, gout=None, Hs_bf16=None):
     return (loss_sum / denom).reshape(()), dHs, grads, done
 
 
+class DirectCtx:
+    """Stand-in for autograd's ctx when a loss function's forward is run outside autograd (forward_backward): the
+    fused step already produces every gradient, so nothing needs to be recorded."""
+
+    def __init__(self, want_dfeature, n_fixed, n_params):
+        self.needs_input_grad = (False, bool(want_dfeature)) + (False,) * (n_fixed - 2) + (True,) * n_params
+
+    def mark_non_differentiable(self, *a):
+        pass
+
+
+def assign_grads(mod, ctx, feature):
+    """.grad of every parameter := the step's gradient tensors (what loss.backward() would have accumulated into
+    freshly zeroed / None grads, main.py:146,151); the gradient w.r.t. cnn_feature continues into its producer."""
+    for n, p in mod.named_parameters():
+        p.grad = ctx.grads[n]
+    dfeat = getattr(ctx, "dfeat", None)
+    if dfeat is not None and feature.requires_grad:
+        if feature.is_leaf:
+            feature.grad = dfeat if feature.grad is None else feature.grad + dfeat
+        else:
+            feature.backward(dfeat)
+
+
 class BaseLossFn(torch.autograd.Function):
     """forward_loss: mean cross-entropy over the packed tokens (main.py:145,149), with forward and
     backward run back to back (fp32 mode turns the logits buffer into its own gradient in place;

@@ -44,6 +44,20 @@ class RNN(nn.Module):
         return engine.BaseLossFn.apply(self, cnn_feature, image_caption, list(caption_size), global_tokens,
                                        *self._params())
 
+    def forward_backward(self, cnn_feature, image_caption, caption_size, global_tokens=None):
+        """The training iteration's `loss = loss_fn(rnn(...), target); loss.backward()` (main.py:148-151) as ONE call:
+        returns the (detached) loss and leaves every parameter's .grad set to this step's gradient -- the same
+        kernels as forward_loss(...).backward() without the autograd round trip (no chain-rule pass over the
+        gradients with grad_output = 1).  Gradients are SET, not accumulated (the reference zeroes them every
+        iteration, main.py:146); if cnn_feature requires grad its gradient flows on into the encoder head."""
+        params = self._params()
+        ctx = engine.DirectCtx(cnn_feature.requires_grad, 5, len(params))
+        with torch.no_grad():
+            loss = engine.BaseLossFn.forward(ctx, self, cnn_feature, image_caption, list(caption_size), global_tokens,
+                                             *params)
+        engine.assign_grads(self, ctx, cnn_feature)
+        return loss
+
     def sentence_index(self, cnn_feature, beam_size=0, max_len=None, beam_mode="chain", **kw):
         """rnn.py:37-108.  beam_size=0: greedy.  beam_size=K>0: the reference's inline beam search
         (beam_mode="chain"); unlike the reference it is batched over images.  beam_mode="tree" runs

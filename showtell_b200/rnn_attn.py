@@ -61,6 +61,19 @@ class RNN_Attn(nn.Module):
         return attn_engine.AttnLossFn.apply(self, cnn_feature, image_caption, list(caption_size), alpha_c,
                                             global_tokens, global_batch, *self._params())
 
+    def forward_backward(self, cnn_feature, image_caption, caption_size, alpha_c=1.0, global_tokens=None, global_batch=None):
+        """`loss = CE + alpha_c * penalty; loss.backward()` (main_attn.py:129-133) as ONE call: returns (loss, alphas),
+        both detached, and leaves every parameter's .grad set to this step's gradient (set, not accumulated; the
+        grid features get no gradient, as in the reference: cnn_attn.py:47)."""
+        from . import engine
+        params = self._params()
+        ctx = engine.DirectCtx(False, 7, len(params))
+        with torch.no_grad():
+            loss, alphas = attn_engine.AttnLossFn.forward(ctx, self, cnn_feature, image_caption, list(caption_size), alpha_c,
+                                                          global_tokens, global_batch, *params)
+        engine.assign_grads(self, ctx, cnn_feature.detach())
+        return loss, alphas
+
     def sentence_index(self, cnn_feature, vocab, max_len=None):
         """rnn_attn.py:120-145: greedy decoding from vocab('<start>')."""
         max_len = self.cap_max_size if max_len is None else int(max_len)

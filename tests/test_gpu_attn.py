@@ -177,3 +177,25 @@ def test_bf16_grid_features_are_consumed_directly(dtype):
         assert rel_err(outs[0][0], outs[1][0]) < 1e-6 and rel_err(outs[0][1], outs[1][1]) < 1e-6
         for a, b in zip(outs[0][2], outs[1][2]):
             assert float((a - b).abs().max()) <= 1e-5 * max(float(b.abs().max()), 1e-6)
+
+
+def test_forward_backward_and_grid_gradient_request():
+    """RNN_Attn.forward_backward == forward_loss(...).backward(); asking for a gradient w.r.t. the grid raises (the
+    reference detaches it, cnn_attn.py:47) instead of silently returning none."""
+    m, feat, cap, lengths = _random_case("attn_gru", 64, 96, 48, 64, 333, 1, 30, 12, 7, 2, "bf16")
+    m, feat, cap = m.to(DEV), feat.to(DEV), cap.to(DEV)
+    m.zero_grad()
+    loss, alphas = m.forward_loss(feat, cap, lengths, alpha_c=1.0)
+    loss.backward()
+    ref = {n: p.grad.clone() for n, p in m.named_parameters()}
+    for i in range(4):
+        m.zero_grad()
+        l2, a2 = m.forward_backward(feat, cap, lengths, alpha_c=1.0)
+        assert float(l2) == pytest.approx(float(loss), rel=1e-5) and torch.allclose(a2, alphas, rtol=1e-5, atol=1e-7)
+        for n, p in m.named_parameters():
+            if n != "attn.full_att.bias":                     # rounding noise around 0
+                assert torch.allclose(p.grad, ref[n], rtol=2e-4, atol=1e-6 * float(ref[n].abs().max())), (i, n)
+    with pytest.raises(NotImplementedError):
+        m.forward_loss(feat.clone().requires_grad_(True), cap, lengths)
+    with pytest.raises(NotImplementedError):
+        m(feat.clone().requires_grad_(True), cap, lengths)

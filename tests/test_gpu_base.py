@@ -298,3 +298,47 @@ def test_cuda_graph_replay_matches_eager(kind, dtype):
     assert l == pytest.approx(l_ref2, rel=1e-6)
     for n in g_ref2:
         assert torch.allclose(g[n], g_ref2[n], rtol=1e-5, atol=1e-8), n
+
+
+@pytest.mark.parametrize("kind,dtype", [("lstm", "bf16"), ("gru", "fp32")])
+def test_forward_backward_equals_forward_loss_backward(kind, dtype):
+    """RNN.forward_backward: the fused iteration (loss + .grad of every parameter, no autograd round trip) gives the
+    gradients of forward_loss(...).backward(), eagerly and when the step is replayed as a CUDA graph; the gradient
+    w.r.t. cnn_feature continues into its producer."""
+    dev = torch.device("cuda:0")
+    m, feat, cap, lengths = _random_case(kind, 64, 128, 500, 2, 20, 6, 3, True, dtype)
+    m = m.to(dev)
+    cap = cap.to(dev)
+    w = torch.randn(64, 64, device=dev, requires_grad=True)
+    x = feat.to(dev)
+    m.zero_grad()
+    f1 = x @ w
+    loss = m.forward_loss(f1, cap, lengths)
+    loss.backward()
+    ref = {n: p.grad.clone() for n, p in m.named_parameters()}
+    ref_w, ref_loss = w.grad.clone(), float(loss)
+    for i in range(5):                      # eager, eager, capture, replay, replay
+        m.zero_grad()
+        w.grad = None
+        f2 = x @ w
+        l2 = m.forward_backward(f2, cap, lengths)
+        assert not l2.requires_grad and float(l2) == pytest.approx(ref_loss, rel=1e-6), i
+        for n, p in m.named_parameters():
+            assert torch.allclose(p.grad, ref[n], rtol=1e-5, atol=1e-8), (i, n)
+        assert torch.allclose(w.grad, ref_w, rtol=1e-5, atol=1e-8), i
+
+
+def test_stale_loss_raises_instead_of_returning_newer_gradients():
+    """One loss at a time: once the step is replayed from a CUDA graph its gradients live in static
+    storage; backward() of a loss whose gradients a later forward_loss overwrote raises."""
+    dev = torch.device("cuda:0")
+    m, feat, cap, lengths = _random_case("lstm", 64, 128, 500, 1, 12, 6, 4, True, "bf16")
+    m, feat, cap = m.to(dev), feat.to(dev), cap.to(dev)
+    for _ in range(4):
+        m.zero_grad()
+        m.forward_loss(feat, cap, lengths).backward()
+    l1 = m.forward_loss(feat, cap, lengths)
+    l2 = m.forward_loss(feat * 0.5, cap, lengths)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        l1.backward()
+    l2.backward()                           # the latest loss is fine
