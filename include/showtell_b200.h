@@ -367,6 +367,11 @@ int st_attn_hoist_bwd(int nsteps, const int* batch_sizes_host, int P, int A, con
                       int out_bf16, float* dwf, int act, st_stream_t stream);
 int st_attn_ctx_all(int nsteps, const int* batch_sizes_host, int P, int C, int T_cap, const void* F, int in_bf16,
                     const float* alphas, void* ctx, void* ctxT, int ldt, int out_bf16, st_stream_t stream);
+/* Q[(b,p), e] = sum_t alphas[b,t,p] dctx[(t,b), e] over the steps in which row b is live, bf16 (B*P, E): the A operand
+ * of dW_embed = Q^T . F (one tensor-core GEMM over the B*P locations) -- autograd of embed(sum_p alpha_p f_p),
+ * rnn_attn.py:29,70 -- instead of rebuilding the (N, C) contexts with st_attn_ctx_all. */
+int st_attn_embed_q(int nsteps, const int* batch_sizes_host, int P, int E, int T_cap, const float* alphas,
+                    const float* dctx, int ld_dctx, void* Q_bf16, st_stream_t stream);
 int st_attn_penalty(int n, const float* S, float coef, float* pen_sum, float* Gpen, st_stream_t stream);
 int st_add_rows(float* dst, const float* src, int rows, int cols, st_stream_t stream);
 

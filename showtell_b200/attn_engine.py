@@ -57,10 +57,16 @@ def attn_forward(mode, P, kind, L, feature, caption, bs, save):
     sv.update(F=F, mean_f=mean_f)
     # rnn_attn.py:62: every layer starts from init_h(mean_P f) (init_c likewise for the LSTM)
     # (a skinny fp32 product: it runs on the side stream beside the hoisted grid projections below)
-    (h0, c0), init_done = ops.fork(
-        lambda: (_lin_small(mean_f, P["init_h.weight"], P["init_h.bias"]),
-                 _lin_small(mean_f, P["init_c.weight"], P["init_c.bias"]) if kind == _lib.ST_LSTM else None),
-        uses=(mean_f,))
+    if tc and C % 8 == 0:
+        # tensor cores: (B, C) x (H, C)^T with the bf16 mean (an fp32 CUDA-core product here took 230 us at B = 128,
+        # C = 2048 and sat on the critical path in front of the time loop)
+        mean_b, _ = ops.cast_bf16(mean_f, True, False)
+        sv["mean_b"] = mean_b
+        init = lambda name: ops.gemm_bf16(mean_b, ops.bf16_shadow(P[name + ".weight"]), bias=P[name + ".bias"], tag="init_fwd")
+    else:
+        init = lambda name: _lin_small(mean_f, P[name + ".weight"], P[name + ".bias"])
+    (h0, c0), init_done = ops.fork(lambda: (init("init_h"), init("init_c") if kind == _lib.ST_LSTM else None),
+                                   uses=(mean_f,))
     sv.update(h0=h0, c0=c0)
     # hoisted, state-independent projections of the grid
     store = BF16 if mode == "bf16" else F32
@@ -178,7 +184,8 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
     bouts = [None] * L
     # embed.weight needs the feature-space contexts ctx = sum_p alpha_p F_p of every (t,b): known since the
     # forward pass, so the pass over F runs on the side stream beside the latency-bound reverse loop
-    if mode == "bf16":
+    embed_q = mode == "bf16" and E % 8 == 0      # dW_embed = Q^T F as one GEMM (ops.attn_embed_q) instead of rebuilt contexts
+    if mode == "bf16" and not embed_q:
         (ctx, ctxT), ctx_done = ops.fork(lambda: _ctx_bf16(bs, Pn, sv["F"], alphas), uses=(sv["F"], alphas))
     fused_bwd = None                # layer-0 fused step kernel: None = not tried yet, then True / False for the pass
     for t in reversed(range(T)):
@@ -247,6 +254,12 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
         return dWe, ops.colsum(datt1), dwf
 
     (dWe, dbe, dwf), enc_done = ops.fork(enc_chain, uses=(att1, att2_all, de_all, wf, sv["F"]))
+    emb_done = None
+    if embed_q:
+        # dW_embed = Q^T F: a third independent chain (one pass over alphas / dctx, then a 2*E*B*P*C FLOP GEMM)
+        grads["embed.weight"], emb_done = ops.fork(
+            lambda: ops.gemm_bf16(ops.attn_embed_q(bs, Pn, alphas, dctx_all), sv["F"], a_t=True, b_t=True, tag="embed_dw"),
+            uses=(alphas, dctx_all, sv["F"]), lane=1)
     h0_b16 = ops.cast_bf16(h0, True, False)[0] if tc else None
     for l in range(L):
         Hprev = ops.shift_states(outs[l]["Hs"], bs, h0) if not tc else None
@@ -278,9 +291,14 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
     grads["attn.decoder_att.weight"] = weight_grad(mode, datt2_b if tc else datt2_all, Hprev_top, "att2_dw")
     grads["attn.decoder_att.bias"] = ops.colsum(datt2_all)
     grads["attn.full_att.weight"] = dwf.reshape(1, -1)
-    grads["attn.full_att.bias"] = ops.colsum(de_all.reshape(-1, 1))
+    # sum of every de (== 0 up to rounding: softmax is shift invariant): two-stage column sum
+    nde = de_all.numel()
+    wde = 256 if nde % 256 == 0 else (Pn if nde % Pn == 0 else 1)
+    grads["attn.full_att.bias"] = ops.colsum(ops.colsum(de_all.reshape(-1, wde)).reshape(-1, 1))
     # embed: ctx_e = W_embed ctx + b with ctx = sum_p alpha_p F_p rebuilt for all (t,b) in one pass
-    if mode == "bf16":
+    if embed_q:
+        pass                                     # forked above
+    elif mode == "bf16":
         dc_b, _ = ops.cast_bf16(dctx_all, True, False)
         ops.join(ctx_done)
         grads["embed.weight"] = ops.gemm_bf16(dc_b, ctx, a_t=True, b_t=True, tag="embed_dw")
@@ -294,12 +312,17 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
     for l in range(1, L):
         dh0 = dh0 + bouts[l]["dstate"][0]
         dc0 = dc0 + bouts[l]["dstate"][1]
-    grads["init_h.weight"] = ops.sgemm(dh0, sv["mean_f"], transA=True)
+    if "mean_b" in sv:
+        dinit = lambda d: ops.gemm_bf16(ops.cast_bf16(d, True, False)[0], sv["mean_b"], a_t=True, b_t=True, tag="init_dw")
+    else:
+        dinit = lambda d: ops.sgemm(d, sv["mean_f"], transA=True)
+    grads["init_h.weight"] = dinit(dh0)
     grads["init_h.bias"] = ops.colsum(dh0)
     if kind == _lib.ST_LSTM:
-        grads["init_c.weight"] = ops.sgemm(dc0, sv["mean_f"], transA=True)
+        grads["init_c.weight"] = dinit(dc0)
         grads["init_c.bias"] = ops.colsum(dc0)
     ops.join(enc_done)
+    ops.join(emb_done)
     return grads
 
 

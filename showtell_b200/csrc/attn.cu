@@ -359,6 +359,60 @@ __device__ __forceinline__ void ld4(const __nv_bfloat16* p, float (&v)[4]) {
   v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
   v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
 }
+// dW_embed without rebuilding the feature-space contexts: with ctx[(t,b),:] = sum_p alpha[b,t,p] F[b,p,:],
+//   dW_embed[e,c] = sum_{t,b} dctx_e[(t,b),e] ctx[(t,b),c] = sum_{(b,p)} Q[(b,p),e] F[(b,p),c],
+//   Q[(b,p),e] = sum_t alpha[b,t,p] dctx_e[(t,b),e]      (t over the steps in which row b is live)
+// so one pass forms Q (B*P, E) as bf16 -- reading alphas and the (N,E) gradients only -- and ONE tensor-core GEMM
+// Q^T . F over the B*P locations (both operands in place, MN-major) replaces the pass that re-reads the whole grid
+// F (B*P*C) once per live step chunk (attn_ctx_all: 148 us at config 3) plus a small GEMM.
+// CTA = one batch row x QP locations; thread = 2 adjacent embedding columns (blockDim = ceil(E/2) rounded to warps).
+constexpr int QP = 28, QT = 16;
+__global__ void __launch_bounds__(NT)
+attn_embed_q_kernel(const __grid_constant__ StepTable tab, int P, int E, int Tcap, const float* __restrict__ alphas,
+                    const float* __restrict__ dctx, int ldd, __nv_bfloat16* __restrict__ Q) {
+  __shared__ float s_al[QT][QP];
+  const int b = blockIdx.y, p0 = blockIdx.x * QP, np = min(QP, P - p0);
+  int len = 0;
+  while (len < tab.nsteps && tab.bs[len] > b) ++len;
+  for (int eb = 0; eb < E; eb += 2 * NT) {                    // one pass when E <= 512; uniform trip count (barriers inside)
+    const int e0 = eb + 2 * threadIdx.x;
+    const bool on = e0 < E, two = e0 + 1 < E;
+    float acc0[QP], acc1[QP];
+#pragma unroll
+    for (int i = 0; i < QP; ++i) acc0[i] = acc1[i] = 0.f;
+    for (int t0 = 0; t0 < len; t0 += QT) {
+      const int nt = min(QT, len - t0);
+      __syncthreads();
+      for (int i = threadIdx.x; i < QT * QP; i += NT) {
+        const int ti = i / QP, pi = i % QP;
+        s_al[ti][pi] = (ti < nt && pi < np) ? alphas[((size_t)b * Tcap + t0 + ti) * P + p0 + pi] : 0.f;
+      }
+      __syncthreads();
+      for (int ti = 0; ti < nt; ++ti) {
+        const float* d = dctx + ((size_t)tab.off[t0 + ti] + b) * ldd + e0;
+        const float d0 = on ? d[0] : 0.f, d1 = two ? d[1] : 0.f;
+#pragma unroll
+        for (int pi = 0; pi < QP; ++pi) {
+          const float a = s_al[ti][pi];
+          acc0[pi] = fmaf(a, d0, acc0[pi]);
+          acc1[pi] = fmaf(a, d1, acc1[pi]);
+        }
+      }
+    }
+#pragma unroll
+    for (int pi = 0; pi < QP; ++pi) {
+      if (pi < np && on) {
+        __nv_bfloat16* q = Q + ((size_t)b * P + p0 + pi) * E + e0;
+        if (two && (E & 1) == 0) *reinterpret_cast<__nv_bfloat162*>(q) = __floats2bfloat162_rn(acc0[pi], acc1[pi]);
+        else {
+          q[0] = __float2bfloat16(acc0[pi]);
+          if (two) q[1] = __float2bfloat16(acc1[pi]);
+        }
+      }
+    }
+  }
+}
+
 template <typename T, typename TO>
 __global__ void __launch_bounds__(NT)
 attn_ctx_all_kernel(const __grid_constant__ StepTable tab, int P, int C, int Tcap, const T* __restrict__ F,
@@ -600,6 +654,21 @@ int st_attn_ctx_all(int nsteps, const int* batch_sizes_host, int P, int C, int T
     attn_ctx_all_kernel<float, float><<<grid, NT, smem, s>>>(tab, P, C, T_cap, (const float*)F, alphas,
                                                              (float*)ctx, (float*)ctxT, ldt);
   ST_LAUNCH_TRY("attn_ctx_all_kernel");
+  return ST_OK;
+}
+
+int st_attn_embed_q(int nsteps, const int* batch_sizes_host, int P, int E, int T_cap, const float* alphas,
+                    const float* dctx, int ld_dctx, void* Q_bf16, st_stream_t stream) {
+  using namespace st;
+  StepTable tab;
+  ST_TRY(make_step_table(tab, nsteps, batch_sizes_host));
+  ST_REQUIRE(alphas && dctx && Q_bf16, ST_ERR_NULL, "st_attn_embed_q: NULL pointer");
+  ST_REQUIRE(P >= 1 && E >= 1 && T_cap >= nsteps && ld_dctx >= E, ST_ERR_BAD_SHAPE,
+             "st_attn_embed_q: P=%d E=%d T_cap=%d ld_dctx=%d", P, E, T_cap, ld_dctx);
+  dim3 grid((P + QP - 1) / QP, tab.bs[0]);
+  attn_embed_q_kernel<<<grid, NT, 0, as_stream(stream)>>>(tab, P, E, T_cap, alphas, dctx, ld_dctx,
+                                                        reinterpret_cast<__nv_bfloat16*>(Q_bf16));
+  ST_LAUNCH_TRY("attn_embed_q_kernel");
   return ST_OK;
 }
 

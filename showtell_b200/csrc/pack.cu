@@ -117,17 +117,24 @@ __global__ void pack_targets_kernel(const __grid_constant__ StepTable tab, int64
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
 
-// out[c] (+)= sum_r M[r,c].  CTA = 32 columns x 8 row-stripes over a 256-row slab.
+// out[c] (+)= sum_r M[r,c].  CTA = 32 columns x 8 row-stripes over a CS_SLAB-row slab, four loads in flight per thread.
+constexpr int CS_SLAB = 128;
 template <typename T>
 __global__ void colsum_kernel(float* __restrict__ out, const T* __restrict__ M, int rows, int cols,
                               int ld) {
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
-  const int r0 = blockIdx.y * 256;
+  const int r0 = blockIdx.y * CS_SLAB;
   float s = 0.f;
   if (c < cols) {
-    const int r1 = min(rows, r0 + 256);
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) s += to_f32(M[(size_t)r * ld + c]);
+    const int r1 = min(rows, r0 + CS_SLAB);
+    int r = r0 + threadIdx.y;
+    for (; r + 24 < r1; r += 32) {
+      const float v0 = to_f32(M[(size_t)r * ld + c]), v1 = to_f32(M[(size_t)(r + 8) * ld + c]);
+      const float v2 = to_f32(M[(size_t)(r + 16) * ld + c]), v3 = to_f32(M[(size_t)(r + 24) * ld + c]);
+      s += (v0 + v1) + (v2 + v3);
+    }
+    for (; r < r1; r += 8) s += to_f32(M[(size_t)r * ld + c]);
   }
   red[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
@@ -357,7 +364,7 @@ int st_colsum(float* out, const void* M, int m_is_bf16, int rows, int cols, int 
   cudaStream_t s = as_stream(stream);
   if (!accumulate) ST_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float) * cols, s));
   if (rows == 0) return ST_OK;
-  dim3 grid((cols + 31) / 32, (rows + 255) / 256), block(32, 8);
+  dim3 grid((cols + 31) / 32, (rows + CS_SLAB - 1) / CS_SLAB), block(32, 8);
   ST_REQUIRE(grid.y <= 65535, ST_ERR_BAD_SHAPE, "st_colsum: too many rows (%d)", rows);
   if (m_is_bf16 && (ld & 7) == 0 && (reinterpret_cast<uintptr_t>(M) & 15) == 0 && cols >= 64) {
     dim3 gv((cols + 255) / 256, (rows + 255) / 256);

@@ -39,8 +39,8 @@ OVERLAP = True    # run independent kernel groups of a step on a second stream (
 _SIDE = {}
 
 
-def fork(fn, uses=()):
-    """Runs fn() on this device's side stream (`uses`: the tensors it reads, kept alive for it), ordered after everything issued so far on the current
+def fork(fn, uses=(), lane=0):
+    """Runs fn() on this device's side stream number `lane` (`uses`: the tensors it reads, kept alive for it), ordered after everything issued so far on the current
     stream, and returns (fn's result, event to join on).  Used for work that the rest of the step
     does not depend on (the vocabulary dW GEMM runs beside the BPTT kernel, which occupies at most
     128 of the 148 SMs and is latency-bound).  Capturable: fork/join become graph dependencies.
@@ -48,9 +48,9 @@ def fork(fn, uses=()):
     if not OVERLAP or TIMER is not None:
         return fn(), None
     dev = torch.cuda.current_device()
-    side = _SIDE.get(dev)
+    side = _SIDE.get((dev, lane))
     if side is None:
-        side = _SIDE[dev] = torch.cuda.Stream(device=dev)
+        side = _SIDE[(dev, lane)] = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream()
     ready = torch.cuda.Event()
     ready.record(main)
@@ -740,6 +740,18 @@ def attn_ctx_all(bs, Pn, F, alphas, want=True, want_t=False, out_dtype=None):
                               ptr(alphas, F32), _raw(ctx) if want else None, _raw(cT) if want_t else None, ld,
                               int(dt == BF16), stream_ptr()), "st_attn_ctx_all")
     return ctx, cT
+
+
+def attn_embed_q(bs, Pn, alphas, dctx):
+    """Q (B*P, E) bf16 = sum_t alphas[b,t,p] dctx[(t,b),:]: dW_embed = gemm_bf16(Q, F, a_t=True, b_t=True)."""
+    lib = _lib.load()
+    B, E = bs[0], dctx.shape[1]
+    if E % 8:
+        raise ValueError("attn_embed_q: E must be a multiple of 8 (bf16 TMA operand rows)")
+    Q = torch.empty(B * Pn, E, dtype=BF16, device=dctx.device)
+    check(lib.st_attn_embed_q(len(bs), int_array(bs), Pn, E, alphas.shape[1], ptr(alphas, F32), ptr(dctx, F32),
+                              dctx.stride(0), _raw(Q), stream_ptr()), "st_attn_embed_q")
+    return Q
 
 
 def attn_penalty(S, coef):

@@ -320,3 +320,22 @@ def test_scale_multi(dev):
     many = [torch.randn(17, generator=gen).to(dev) for _ in range(40)]  # more than one table
     for o, t in zip(ops.scale_multi(many, g), many):
         assert torch.equal(o, t * g)
+
+
+@pytest.mark.parametrize("lengths,P,E", [([5, 5, 4, 2, 1], 30, 64), ([20] * 9, 196, 512), ([18, 7, 3], 49, 72)])
+def test_attn_embed_q(dev, lengths, P, E):
+    """Q[(b,p), e] = sum_t alphas[b,t,p] dctx[(t,b), e] over each row's live steps (the A operand of dW_embed = Q^T F)."""
+    from showtell_b200 import _lib, ops
+    bs = _lib.batch_sizes(lengths)
+    B, T, N = len(lengths), len(bs), sum(bs)
+    g = torch.Generator().manual_seed(P + E)
+    alphas = torch.rand(B, T + 2, P, generator=g)
+    dctx = torch.randn(N, E, generator=g)
+    ref = torch.zeros(B, P, E, dtype=torch.float64)
+    off = 0
+    for t, bt in enumerate(bs):
+        ref[:bt] += alphas[:bt, t, :, None].double() * dctx[off:off + bt, None, :].double()
+        off += bt
+    Q = ops.attn_embed_q(bs, P, alphas.to(dev), dctx.to(dev))
+    assert Q.shape == (B * P, E) and Q.dtype == torch.bfloat16
+    assert rel_err(Q.float(), ref.reshape(B * P, E)) < 5e-3

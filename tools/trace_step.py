@@ -29,10 +29,7 @@ def main():
     lengths = [T] * B
 
     def step():
-        m.zero_grad()
-        out = m.forward_loss(feat, cap, lengths)
-        loss = out[0] if isinstance(out, tuple) else out
-        loss.backward()
+        m.forward_backward(feat, cap, lengths)
 
     for _ in range(6):
         step()
