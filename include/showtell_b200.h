@@ -112,6 +112,18 @@ int st_split_tf32(const float* src, int rows, int cols, int lds, float* hi, floa
 int st_gemm_tf32x3(int M, int N, int K, const float* A_hi, const float* A_lo, int lda, const float* B_hi,
                    const float* B_lo, int ldb, float* C, int ldc, const float* bias, float alpha, float beta,
                    st_stream_t stream);
+/* The same fp32-accurate product fused with a per-row top-K of A.B^T + bias (rnn.py:51 `max(1)[1]`, rnn.py:63,90-91
+ * `topk(k)`; beam_search.py:84 `argsort`): the (M, N) logits are never written.  Each epilogue warp keeps the best `topk`
+ * (<= 8) of its columns per row (cand_val / cand_idx: scratch of M * st_topk_parts(N) entries each), a merge kernel picks
+ * the `topk` best per row: value descending, the LOWER column index first among equal values.
+ * Outputs (any may be NULL): val / idx (M, out_stride), tok[m * tok_stride] = best index as int64.
+ * row_max / row_sum (both or neither; then part_stats = scratch of M * st_topk_parts(N) / 4 floats): the soft-max
+ * normaliser of each row, row_sum = sum_j exp(x_j - row_max)  (beam_search.py:85-88 costs -log p). */
+int st_topk_parts(int N);
+int st_gemm_tf32x3_topk(int M, int N, int K, const float* A_hi, const float* A_lo, int lda, const float* B_hi,
+                        const float* B_lo, int ldb, const float* bias, int topk, float* cand_val, int32_t* cand_idx,
+                        float* val, int32_t* idx, int out_stride, int64_t* tok, int tok_stride, float* part_stats,
+                        float* row_max, float* row_sum, st_stream_t stream);
 /* Development / test aid: pin the kernel behind st_gemm_bf16 and st_vocab_ce_*: 2 = CTA-pair kernel
  * (cta_group::2, 256x256 tiles, stream-K), 128 / 256 = single-CTA kernel with that tile width, 0 = choose. */
 int st_debug_gemm_variant(int variant);
@@ -412,6 +424,9 @@ typedef struct {
 } st_rnn_weights;
 
 int64_t st_decode_workspace_bytes(const st_rnn_weights* w, int n_img, int K, int max_len);
+/* Development / test aid: the projected-embedding table of gemm_mode 1 (EP = emb . W_ih^T + b_ih, built once per call):
+ * 0 = by size (rows * max_len >= V), 1 = always, -1 = never.  Set before st_decode_workspace_bytes. */
+int st_debug_decode_table(int mode);
 
 /* RNN.sentence_index(cnn_feature) greedy (rnn.py:44-58, rnn_lstm.py:35-57):
  * feature (n_img, E) -> tokens (n_img, max_len) int64. */

@@ -2,10 +2,15 @@
 //   st_decode_greedy      RNN.sentence_index(beam_size=0)      rnn.py:44-58, rnn_lstm.py:35-57
 //   st_decode_beam_chain  RNN.sentence_index(beam_size=K)      rnn.py:60-108   ("chain" beam)
 //   st_decode_beam_tree   beam_search.beam_search()            beam_search.py:45-97 ("tree" beam)
-// Images are independent, so every step is batched over the images of the call: the recurrent
-// step is one launch of the rnn_seq kernel with a single time step, the vocabulary projection one
-// GEMM over all rows, followed by a row-wise arg-max / top-K and a per-image bookkeeping kernel
-// that reproduces the reference's ranking rules (documented at each kernel).
+// Images are independent, so every step is batched over the images of the call.  Two arithmetic modes:
+//   gemm_mode 0 (fp32, CUDA cores): per step {embedding gather, input GEMM, rnn_seq single-step kernel, vocabulary
+//     GEMM into (rows, V) logits, row-wise arg-max / top-K}.
+//   gemm_mode 1 (3xTF32, tensor cores; fp32-accurate): every product of the loop on tcgen05 and the logits are NEVER
+//     written: per dependent step {W_hh GEMM, gate kernel, vocabulary GEMM with the top-K (+ soft-max normaliser)
+//     kept in its epilogue, candidate merge} = 4 launches.  The input projection of a fed-back word is a row of the
+//     table  EP = emb . W_ih^T + b_ih  (V rows, built once per call; per-step GEMM for short calls), which the gate
+//     kernel gathers by token id.
+// A per-image bookkeeping kernel reproduces the reference's ranking rules (documented at each kernel).
 #include <cfloat>
 
 #include "common.cuh"
@@ -23,6 +28,12 @@ extern "C" int st_gemm_tf32x3(int M, int N, int K, const float* A_hi, const floa
                               float beta, st_stream_t stream);
 extern "C" int st_topk_rows(const float* X, int ld, int rows, int cols, int K, float* val,
                             int32_t* idx, int out_stride, st_stream_t stream);
+extern "C" int st_topk_parts(int N);
+extern "C" int st_gemm_tf32x3_topk(int M, int N, int K, const float* A_hi, const float* A_lo, int lda, const float* B_hi,
+                                   const float* B_lo, int ldb, const float* bias, int topk, float* cand_val,
+                                   int32_t* cand_idx, float* val, int32_t* idx, int out_stride, int64_t* tok,
+                                   int tok_stride, float* part_stats, float* row_max, float* row_sum,
+                                   st_stream_t stream);
 
 namespace st {
 namespace {
@@ -60,28 +71,115 @@ int check_weights(const st_rnn_weights* w) {
 // st_gemm_tf32x3); the latter needs rows of 4 floats (E, H multiples of 4).
 inline bool use_tc(const st_rnn_weights* w) { return w->gemm_mode == 1 && w->E % 4 == 0 && w->H % 4 == 0; }
 
+constexpr int FUSED_TOPK_MAX = 8;   // TOPK_SLOTS of the fused epilogue (gemm_tc.cu)
+int g_force_table = 0;              // st_debug_decode_table: 0 = by size, 1 = always, -1 = never
+
+__device__ __forceinline__ void split_store(float x, float* hi, float* lo) {
+  const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);   // as st_split_tf32
+  *hi = h;
+  *lo = x - h;
+}
+
+template <typename I>
+__global__ void gather_emb_kernel(float* __restrict__ X, const float* __restrict__ emb, int E,
+                                  const I* __restrict__ tok, int stride) {
+  const int64_t id = (int64_t)tok[(size_t)blockIdx.x * stride];
+  const float* src = emb + id * E;
+  float* dst = X + (size_t)blockIdx.x * E;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) dst[e] = src[e];
+}
+
+// Where a step's input projection Gx = W_ih x + b_ih comes from: a (rows, G*H) matrix, or -- the fed-back word of
+// each row given by tok[row * stride] (int32 or int64) -- rows of the projected-embedding table EP (V, G*H).
+struct GxSrc {
+  const float* gx;
+  const void* tok;
+  int tok64, stride;
+};
+
+// One recurrent step from the two projections (tensor-core path of the decoding loops): Gx (see GxSrc) and
+// Gh = W_hh h + b_hh (NULL on the first step, h = 0: Gh = b_hh) -> gates, state update (the formulas of
+// rnn_seq.cu, i.e. nn.GRU / nn.LSTM), h' written as fp32 AND as its (hi, lo) tf32 split -- the operand of the next
+// W_hh / vocabulary / next-layer products, so no separate split pass exists in the loop.
+template <int G>
+__global__ void __launch_bounds__(256) decode_gate_kernel(int rows, int H, GxSrc src, const float* __restrict__ Gh,
+                                                          const float* __restrict__ bhh, const float* __restrict__ h_prev,
+                                                          const float* __restrict__ c_prev, float* __restrict__ h_out,
+                                                          float* __restrict__ c_out, float* __restrict__ h_hi,
+                                                          float* __restrict__ h_lo) {
+  const long long n = (long long)rows * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / H), u = (int)(i - (long long)r * H);
+    int64_t gr = r;
+    if (src.tok)
+      gr = src.tok64 ? reinterpret_cast<const int64_t*>(src.tok)[(size_t)r * src.stride]
+                     : (int64_t) reinterpret_cast<const int32_t*>(src.tok)[(size_t)r * src.stride];
+    const float* gx = src.gx + (size_t)gr * G * H;
+    const float* gh = Gh ? Gh + (size_t)r * G * H : bhh;
+    float hv;
+    if (G == 4) {
+      const float ig = sigmoidf_(gx[u] + gh[u]);
+      const float fg = sigmoidf_(gx[H + u] + gh[H + u]);
+      const float gg = tanhf(gx[2 * H + u] + gh[2 * H + u]);
+      const float og = sigmoidf_(gx[3 * H + u] + gh[3 * H + u]);
+      const float cp = c_prev ? c_prev[i] : 0.f;
+      const float c2 = fmaf(fg, cp, ig * gg);
+      c_out[i] = c2;
+      hv = og * tanhf(c2);
+    } else {
+      const float rr = sigmoidf_(gx[u] + gh[u]);
+      const float zz = sigmoidf_(gx[H + u] + gh[H + u]);
+      const float nn = tanhf(fmaf(rr, gh[2 * H + u], gx[2 * H + u]));
+      const float hp = h_prev ? h_prev[i] : 0.f;
+      hv = fmaf(zz, hp - nn, nn);
+    }
+    h_out[i] = hv;
+    split_store(hv, h_hi + i, h_lo + i);
+  }
+}
+
+// X (rows, E) = emb[tok[row * stride]] written directly as its (hi, lo) tf32 split (Embedding lookup, rnn.py:53,85)
+__global__ void gather_emb_split_kernel(float* __restrict__ X_hi, float* __restrict__ X_lo, const float* __restrict__ emb,
+                                        int E, const void* __restrict__ tok, int tok64, int stride) {
+  const int64_t id = tok64 ? reinterpret_cast<const int64_t*>(tok)[(size_t)blockIdx.x * stride]
+                           : (int64_t) reinterpret_cast<const int32_t*>(tok)[(size_t)blockIdx.x * stride];
+  const float* src = emb + id * E;
+  for (int e = threadIdx.x; e < E; e += blockDim.x)
+    split_store(src[e], X_hi + (size_t)blockIdx.x * E + e, X_lo + (size_t)blockIdx.x * E + e);
+}
+
 // Per-call decoder state: double-buffered h/c per layer for `rows` rows, plus GEMM scratch.
 struct Rig {
   const st_rnn_weights* w;
   int rows, G;
-  bool tc;
+  bool tc;      // gemm_mode 1: all products on the tensor cores
+  bool fused;   // tc and K <= FUSED_TOPK_MAX: vocabulary projection fused with the top-K, no logits buffer
+  bool table;   // tc and enough row-steps to amortise it: input projections of fed-back words from the EP table
   float *X, *Gx0, *GxL, *logits;
   float* h[2][MAXL];
   float* c[2][MAXL];
   float *Wih_hi[MAXL], *Wih_lo[MAXL], *Wv_hi, *Wv_lo, *act_hi, *act_lo;   // tc: tf32 splits
+  // tc: W_hh splits, the hidden projection Gh, the (hi, lo) split of each layer's state (written by the gate kernel),
+  // top-K candidates / soft-max partials of the fused vocabulary projection, the projected-embedding table
+  float *Whh_hi[MAXL], *Whh_lo[MAXL], *Gh, *hs_hi[2][MAXL], *hs_lo[2][MAXL], *cand_val, *part_stats, *EP, *emb_hi, *emb_lo;
+  int32_t* cand_idx;
   int* barrier;
   int cur;
   cudaStream_t s;
 
-  void carve(Bump& b, const st_rnn_weights* w_, int rows_) {
+  // `steps`: time steps of the call (table decision); K: widest top-K the loop asks for
+  void carve(Bump& b, const st_rnn_weights* w_, int rows_, int K, int steps) {
     w = w_;
     rows = rows_;
     G = (w->kind == ST_LSTM) ? 4 : 3;
     tc = use_tc(w);
+    fused = tc && K <= FUSED_TOPK_MAX;
+    table = tc && (int64_t)rows * steps >= (int64_t)w->V && g_force_table >= 0;
+    if (tc && g_force_table > 0) table = true;
     X = b.take<float>((int64_t)rows * w->E);
     Gx0 = b.take<float>((int64_t)rows * G * w->H);
     GxL = b.take<float>((int64_t)rows * G * w->H);
-    logits = b.take<float>((int64_t)rows * w->V);
+    logits = fused ? nullptr : b.take<float>((int64_t)rows * w->V);
     for (int i = 0; i < 2; ++i)
       for (int l = 0; l < w->L; ++l) {
         h[i][l] = b.take<float>((int64_t)rows * w->H);
@@ -92,25 +190,102 @@ struct Rig {
         const int64_t n = (int64_t)G * w->H * (l == 0 ? w->E : w->H);
         Wih_hi[l] = b.take<float>(n);
         Wih_lo[l] = b.take<float>(n);
+        Whh_hi[l] = b.take<float>((int64_t)G * w->H * w->H);
+        Whh_lo[l] = b.take<float>((int64_t)G * w->H * w->H);
+        for (int i = 0; i < 2; ++i) {
+          hs_hi[i][l] = b.take<float>((int64_t)rows * w->H);
+          hs_lo[i][l] = b.take<float>((int64_t)rows * w->H);
+        }
       }
       Wv_hi = b.take<float>((int64_t)w->V * w->H);
       Wv_lo = b.take<float>((int64_t)w->V * w->H);
       const int64_t wide = w->E > w->H ? w->E : w->H;
       act_hi = b.take<float>((int64_t)rows * wide);
       act_lo = b.take<float>((int64_t)rows * wide);
+      Gh = b.take<float>((int64_t)rows * G * w->H);
+      const int parts = st_topk_parts(w->V);
+      cand_val = b.take<float>((int64_t)rows * parts);
+      cand_idx = b.take<int32_t>((int64_t)rows * parts);
+      part_stats = b.take<float>((int64_t)rows * (parts / 4));
+      EP = emb_hi = emb_lo = nullptr;
+      if (table) {
+        EP = b.take<float>((int64_t)w->V * G * w->H);
+        emb_hi = b.take<float>((int64_t)w->V * w->E);
+        emb_lo = b.take<float>((int64_t)w->V * w->E);
+      }
     }
     barrier = b.take<int>(64);
     cur = 0;
   }
-  // tc: split the (constant) weights once per call
+  // tc: split the (constant) weights once per call; build the projected-embedding table
   int prepare() {
     if (!tc) return ST_OK;
     for (int l = 0; l < w->L; ++l) {
       const int in = l == 0 ? w->E : w->H;
       ST_TRY(st_split_tf32(w->Wih_host[l], G * w->H, in, in, Wih_hi[l], Wih_lo[l], in, s));
+      ST_TRY(st_split_tf32(w->Whh_host[l], G * w->H, w->H, w->H, Whh_hi[l], Whh_lo[l], w->H, s));
     }
-    return st_split_tf32(w->Wv, w->V, w->H, w->H, Wv_hi, Wv_lo, w->H, s);
+    ST_TRY(st_split_tf32(w->Wv, w->V, w->H, w->H, Wv_hi, Wv_lo, w->H, s));
+    if (table) {   // EP[v] = W_ih0 emb[v] + b_ih0: the same product, row for row, the per-step input GEMM would form
+      ST_TRY(st_split_tf32(w->emb, w->V, w->E, w->E, emb_hi, emb_lo, w->E, s));
+      ST_TRY(st_gemm_tf32x3(w->V, G * w->H, w->E, emb_hi, emb_lo, w->E, Wih_hi[0], Wih_lo[0], w->E, EP, G * w->H,
+                            w->bih_host[0], 1.f, 0.f, s));
+    }
+    return ST_OK;
   }
+  // ---- tensor-core loop
+  int gate(int l, GxSrc src, bool first, int nxt) {
+    const int H = w->H;
+    const long long n = (long long)rows * H;
+    int sms = 0;
+    ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
+    const long long blocks = (n + 255) / 256;
+    const unsigned grid = (unsigned)(blocks < 8LL * sms ? blocks : 8LL * sms);
+    const float* gh = first ? nullptr : Gh;
+    if (w->kind == ST_LSTM)
+      decode_gate_kernel<4><<<grid, 256, 0, s>>>(rows, H, src, gh, w->bhh_host[l], first ? nullptr : h[cur][l],
+                                                 first ? nullptr : c[cur][l], h[nxt][l], c[nxt][l], hs_hi[nxt][l], hs_lo[nxt][l]);
+    else
+      decode_gate_kernel<3><<<grid, 256, 0, s>>>(rows, H, src, gh, w->bhh_host[l], first ? nullptr : h[cur][l], nullptr,
+                                                 h[nxt][l], nullptr, hs_hi[nxt][l], hs_lo[nxt][l]);
+    ST_LAUNCH_TRY("decode_gate_kernel");
+    return ST_OK;
+  }
+  // One time step through all layers on the tensor cores.  Input of layer 0: the projection in Gx0 (tok == NULL: the
+  // image feature, rnn.py:47-49) or the embedding of each row's fed-back word (rnn.py:53,85).
+  int step_tc(const void* tok, int tok64, int stride, bool first) {
+    const int H = w->H, nxt = cur ^ 1;
+    GxSrc src{Gx0, nullptr, 0, 0};
+    if (tok && table) {
+      src = GxSrc{EP, tok, tok64, stride};
+    } else if (tok) {
+      gather_emb_split_kernel<<<rows, 128, 0, s>>>(act_hi, act_lo, w->emb, w->E, tok, tok64, stride);
+      ST_LAUNCH_TRY("gather_emb_split_kernel");
+      ST_TRY(st_gemm_tf32x3(rows, G * H, w->E, act_hi, act_lo, w->E, Wih_hi[0], Wih_lo[0], w->E, Gx0, G * H, w->bih_host[0],
+                            1.f, 0.f, s));
+    }
+    for (int l = 0; l < w->L; ++l) {
+      if (l > 0) {
+        ST_TRY(st_gemm_tf32x3(rows, G * H, H, hs_hi[nxt][l - 1], hs_lo[nxt][l - 1], H, Wih_hi[l], Wih_lo[l], H, GxL, G * H,
+                              w->bih_host[l], 1.f, 0.f, s));
+        src = GxSrc{GxL, nullptr, 0, 0};
+      }
+      if (!first)
+        ST_TRY(st_gemm_tf32x3(rows, G * H, H, hs_hi[cur][l], hs_lo[cur][l], H, Whh_hi[l], Whh_lo[l], H, Gh, G * H,
+                              w->bhh_host[l], 1.f, 0.f, s));
+      ST_TRY(gate(l, src, first, nxt));
+    }
+    cur = nxt;
+    return ST_OK;
+  }
+  // top-K of the vocabulary logits of the current top state, logits never written (rnn.py:50-51, 88-91); optionally the
+  // rows' soft-max normaliser (beam_search.py:85-88)
+  int vocab_topk(int K, float* val, int32_t* idx, int out_stride, int64_t* tok, int tok_stride, float* row_max = nullptr,
+                 float* row_sum = nullptr) {
+    return st_gemm_tf32x3_topk(rows, w->V, w->H, hs_hi[cur][w->L - 1], hs_lo[cur][w->L - 1], w->H, Wv_hi, Wv_lo, w->H, w->bv, K,
+                               cand_val, cand_idx, val, idx, out_stride, tok, tok_stride, part_stats, row_max, row_sum, s);
+  }
+  // ---- generic pieces (fp32 mode; tc mode for the feature projection and for K > FUSED_TOPK_MAX)
   // out (rows, N) = in (rows, K) . W^T + bias
   int linear(const float* in, int K, const float* W, const float* W_hi, const float* W_lo, const float* bias, int N,
              float* out) {
@@ -122,7 +297,7 @@ struct Rig {
   int input_proj(const float* Xin) {
     return linear(Xin, w->E, w->Wih_host[0], Wih_hi[0], Wih_lo[0], w->bih_host[0], G * w->H, Gx0);
   }
-  // One time step through all layers; reads state `cur` (zeros when first), writes and flips.
+  // One time step through all layers (fp32 mode); reads state `cur` (zeros when first), writes and flips.
   int step(bool first) {
     const int H = w->H, nxt = cur ^ 1;
     for (int l = 0; l < w->L; ++l) {
@@ -138,30 +313,36 @@ struct Rig {
     cur = nxt;
     return ST_OK;
   }
+  // One time step in the call's arithmetic mode: the fed-back words tok (NULL: Gx0 already holds the projection)
+  int advance(const void* tok, int tok64, int stride, bool first) {
+    if (tc) return step_tc(tok, tok64, stride, first);
+    if (tok) {
+      if (tok64) gather_emb_kernel<int64_t><<<rows, 128, 0, s>>>(X, w->emb, w->E, (const int64_t*)tok, stride);
+      else gather_emb_kernel<int32_t><<<rows, 128, 0, s>>>(X, w->emb, w->E, (const int32_t*)tok, stride);
+      ST_LAUNCH_TRY("gather_emb_kernel");
+      ST_TRY(input_proj(X));
+    }
+    return step(first);
+  }
+  // top-K of the vocabulary logits of the current top state -> val / idx (rows, out_stride) and / or tok (int64)
+  int top_words(int K, float* val, int32_t* idx, int out_stride, int64_t* tok, int tok_stride) {
+    if (fused) return vocab_topk(K, val, idx, out_stride, tok, tok_stride);
+    ST_TRY(vocab_logits());
+    if (tok) ST_TRY(st_argmax_rows(logits, w->V, rows, w->V, tok, tok_stride, s));
+    if (val || idx) ST_TRY(st_topk_rows(logits, w->V, rows, w->V, K, val, idx, out_stride, s));
+    return ST_OK;
+  }
   float* top() { return h[cur][w->L - 1]; }
   int vocab_logits() { return linear(top(), w->H, w->Wv, Wv_hi, Wv_lo, w->bv, w->V, logits); }
 };
 
-int64_t rig_bytes(const st_rnn_weights* w, int64_t rows) {
-  const int G = (w->kind == ST_LSTM) ? 4 : 3;
-  int64_t f = rows * w->E + 2 * rows * G * w->H + rows * w->V + 4 * (int64_t)w->L * rows * w->H;
-  int64_t slots = 8 + 4 * w->L;
-  if (use_tc(w)) {
-    f += 2 * ((int64_t)G * w->H * w->E + (int64_t)(w->L - 1) * G * w->H * w->H + (int64_t)w->V * w->H);
-    f += 2 * rows * (w->E > w->H ? w->E : w->H);
-    slots += 2 * w->L + 4;
-  }
-  return f * 4 + 256 * slots + 64 * 4;
+int64_t rig_bytes(const st_rnn_weights* w, int64_t rows, int K, int steps) {
+  Bump dry{nullptr, 0, 0};   // the same carve on a null base: only the offsets are computed
+  Rig r;
+  r.carve(dry, w, (int)rows, K, steps);
+  return dry.used + 256;
 }
 
-template <typename I>
-__global__ void gather_emb_kernel(float* __restrict__ X, const float* __restrict__ emb, int E,
-                                  const I* __restrict__ tok, int stride) {
-  const int64_t id = (int64_t)tok[(size_t)blockIdx.x * stride];
-  const float* src = emb + id * E;
-  float* dst = X + (size_t)blockIdx.x * E;
-  for (int e = threadIdx.x; e < E; e += blockDim.x) dst[e] = src[e];
-}
 
 // ----------------------------------------------------------------------------- chain beam
 __global__ void chain_init_kernel(int n, int K, int max_len, const int32_t* __restrict__ words,
@@ -410,11 +591,15 @@ __global__ void tree_expand_kernel(TreeBufs b, int cur_seq, int len) {
 }
 
 __global__ void gather_state_kernel(float* __restrict__ dst, const float* __restrict__ src, int H, int K,
-                                    const int32_t* __restrict__ parent_slot) {
+                                    const int32_t* __restrict__ parent_slot, float* __restrict__ dst_hi,
+                                    float* __restrict__ dst_lo) {
   const int row = blockIdx.x, img = row / K;
   const float* s = src + (size_t)(img * K + parent_slot[row]) * H;
   float* d = dst + (size_t)row * H;
-  for (int e = threadIdx.x; e < H; e += blockDim.x) d[e] = s[e];
+  for (int e = threadIdx.x; e < H; e += blockDim.x) {
+    d[e] = s[e];
+    if (dst_hi) split_store(s[e], dst_hi + (size_t)row * H + e, dst_lo + (size_t)row * H + e);   // tc: next W_hh operand
+  }
 }
 
 __global__ void spread_root_kernel(float* __restrict__ dst, const float* __restrict__ src, int H, int K) {
@@ -440,6 +625,11 @@ __global__ void tree_finish_kernel(TreeBufs b, int32_t* __restrict__ out_tok, in
 
 extern "C" {
 
+int st_debug_decode_table(int mode) {
+  st::g_force_table = mode;
+  return ST_OK;
+}
+
 int64_t st_decode_workspace_bytes(const st_rnn_weights* w, int n_img, int K, int max_len) {
   using namespace st;
   if (check_weights(w) != ST_OK || n_img < 1 || max_len < 1) return -1;
@@ -452,7 +642,7 @@ int64_t st_decode_workspace_bytes(const st_rnn_weights* w, int n_img, int K, int
                   + (int64_t)n_img * 32 * SL * 4 + (int64_t)n_img * 32 * 8 + (int64_t)n_img * 16  // hypotheses
                   + (int64_t)n_img * w->H * 16   // initial-state scratch of the tree beam
                   + 64 * 256;
-  return rig_bytes(w, rows) + extra;
+  return rig_bytes(w, rows, (int)k, max_len) + extra;
 }
 
 int st_decode_greedy(const st_rnn_weights* w, const float* feature, int n_img, int max_len,
@@ -464,20 +654,15 @@ int st_decode_greedy(const st_rnn_weights* w, const float* feature, int n_img, i
   Bump b{(char*)workspace, workspace_bytes, 0};
   Rig rig;
   rig.s = as_stream(stream);
-  rig.carve(b, w, n_img);
+  rig.carve(b, w, n_img, 1, max_len);
   ST_REQUIRE(b.used <= b.cap, ST_ERR_WORKSPACE, "st_decode_greedy: workspace %lld < %lld",
              (long long)b.cap, (long long)b.used);
   ST_TRY(rig.prepare());
   ST_TRY(rig.input_proj(feature));                                           // rnn.py:41,49
   for (int step = 0; step < max_len; ++step) {
-    ST_TRY(rig.step(step == 0));                                             // rnn.py:49
-    ST_TRY(rig.vocab_logits());                                              // rnn.py:50
-    ST_TRY(st_argmax_rows(rig.logits, w->V, n_img, w->V, tokens + step, max_len, stream));  // :51
-    if (step + 1 < max_len) {
-      gather_emb_kernel<int64_t><<<n_img, 128, 0, rig.s>>>(rig.X, w->emb, w->E, tokens + step, max_len);
-      ST_LAUNCH_TRY("gather_emb_kernel");                                    // rnn.py:53
-      ST_TRY(rig.input_proj(rig.X));
-    }
+    // rnn.py:49 (step 0: the image feature) / rnn.py:53 (the embedding of the previous arg-max)
+    ST_TRY(rig.advance(step ? tokens + step - 1 : nullptr, 1, max_len, step == 0));
+    ST_TRY(rig.top_words(1, nullptr, nullptr, 0, tokens + step, max_len));    // rnn.py:50-51
   }
   return ST_OK;
 }
@@ -495,7 +680,7 @@ int st_decode_beam_chain(const st_rnn_weights* w, const float* feature, int n_im
   Bump b{(char*)workspace, workspace_bytes, 0};
   Rig rig;
   rig.s = as_stream(stream);
-  rig.carve(b, w, n_img);
+  rig.carve(b, w, n_img, K, max_len);
   int32_t* words = b.take<int32_t>((int64_t)n_img * K);
   float* vals0 = b.take<float>((int64_t)n_img * K);
   int32_t* sent[2] = {b.take<int32_t>((int64_t)n_img * K * max_len),
@@ -509,22 +694,16 @@ int st_decode_beam_chain(const st_rnn_weights* w, const float* feature, int n_im
   const int tpb = 128;
 
   ST_TRY(rig.input_proj(feature));
-  ST_TRY(rig.step(true));                                                    // rnn.py:61
-  ST_TRY(rig.vocab_logits());                                                // rnn.py:62
-  ST_TRY(st_topk_rows(rig.logits, w->V, n_img, w->V, K, vals0, words, K, stream));  // rnn.py:63
+  ST_TRY(rig.advance(nullptr, 0, 0, true));                                  // rnn.py:61
+  ST_TRY(rig.top_words(K, vals0, words, K, nullptr, 0));                     // rnn.py:62-63
   chain_init_kernel<<<(n_img * K + tpb - 1) / tpb, tpb, 0, s>>>(n_img, K, max_len, words, vals0, sent[0],
                                                                trace_scores, trace_words);
   ST_LAUNCH_TRY("chain_init_kernel");
   int cur = 0;
   for (int pos = 1; pos < max_len; ++pos) {                                  // rnn.py:77-79
     for (int k = 0; k < K; ++k) {                                            // rnn.py:83
-      gather_emb_kernel<int32_t><<<n_img, 128, 0, s>>>(rig.X, w->emb, w->E, words + k, K);
-      ST_LAUNCH_TRY("gather_emb_kernel");                                    // rnn.py:85
-      ST_TRY(rig.input_proj(rig.X));
-      ST_TRY(rig.step(false));            // the ONE chained state, rnn.py:87
-      ST_TRY(rig.vocab_logits());                                            // rnn.py:88
-      ST_TRY(st_topk_rows(rig.logits, w->V, n_img, w->V, K, cand_val + k * K, cand_idx + k * K, K * K,
-                          stream));                                          // rnn.py:90-91
+      ST_TRY(rig.advance(words + k, 0, K, false));   // rnn.py:85-87: embedding of beam k's word, the ONE chained state
+      ST_TRY(rig.top_words(K, cand_val + k * K, cand_idx + k * K, K * K, nullptr, 0));   // rnn.py:88-91
     }
     chain_select_kernel<<<(n_img + 63) / 64, 64, 0, s>>>(n_img, K, max_len, pos, cand_val, cand_idx,
                                                          sent[cur], sent[cur ^ 1], words, trace_scores,
@@ -556,7 +735,7 @@ int st_decode_beam_tree(const st_rnn_weights* w, const float* feature, int n_img
   Rig rig;
   rig.s = as_stream(stream);
   const int rows = n_img * K;
-  rig.carve(b, w, rows);
+  rig.carve(b, w, rows, K, max_length);
   TreeBufs tb;
   tb.n = n_img; tb.K = K; tb.num_hyp = num_hyp; tb.SL = max_length + 1;
   tb.node_val = b.take<int32_t>(rows);
@@ -593,6 +772,7 @@ int st_decode_beam_tree(const st_rnn_weights* w, const float* feature, int n_img
                         nullptr, h_init, nullptr, nullptr, nullptr, rig.barrier, stream));
   spread_root_kernel<<<rows, 128, 0, s>>>(rig.h[rig.cur][0], h_init, H, K);
   ST_LAUNCH_TRY("spread_root_kernel");
+  if (rig.tc) ST_TRY(st_split_tf32(rig.h[rig.cur][0], rows, H, H, rig.hs_hi[rig.cur][0], rig.hs_lo[rig.cur][0], H, s));
   tree_init_kernel<<<gi, tpb, 0, s>>>(tb, start_id);
   ST_LAUNCH_TRY("tree_init_kernel");
 
@@ -603,18 +783,21 @@ int st_decode_beam_tree(const st_rnn_weights* w, const float* feature, int n_img
     ST_LAUNCH_TRY("tree_retire_kernel");
     tree_tokens_kernel<<<(rows + 127) / 128, 128, 0, s>>>(tb, tok_rows);
     ST_LAUNCH_TRY("tree_tokens_kernel");
-    gather_emb_kernel<int32_t><<<rows, 128, 0, s>>>(rig.X, w->emb, w->E, tok_rows, 1);
-    ST_LAUNCH_TRY("gather_emb_kernel");
-    ST_TRY(rig.input_proj(rig.X));
-    ST_TRY(rig.step(false));                                                  // generate_function, :83
-    ST_TRY(rig.vocab_logits());
-    row_softmax_stats_kernel<<<rows, 256, 0, s>>>(rig.logits, w->V, w->V, tb.row_max, tb.row_sum);
-    ST_LAUNCH_TRY("row_softmax_stats_kernel");
-    ST_TRY(st_topk_rows(rig.logits, w->V, rows, w->V, K, tb.tk_val, tb.tk_idx, K, stream));  // :84
+    ST_TRY(rig.advance(tok_rows, 0, 1, false));                               // generate_function, :83
+    if (rig.fused) {                                                          // :84 top-K + soft-max normaliser, no logits
+      ST_TRY(rig.vocab_topk(K, tb.tk_val, tb.tk_idx, K, nullptr, 0, tb.row_max, tb.row_sum));
+    } else {
+      ST_TRY(rig.vocab_logits());
+      row_softmax_stats_kernel<<<rows, 256, 0, s>>>(rig.logits, w->V, w->V, tb.row_max, tb.row_sum);
+      ST_LAUNCH_TRY("row_softmax_stats_kernel");
+      ST_TRY(st_topk_rows(rig.logits, w->V, rows, w->V, K, tb.tk_val, tb.tk_idx, K, stream));
+    }
     tree_expand_kernel<<<gi, tpb, 0, s>>>(tb, cur_seq, len);                  // :86-94
     ST_LAUNCH_TRY("tree_expand_kernel");
     // new node s inherits the post-step state of its parent: gather h[cur] -> h[cur^1], flip
-    gather_state_kernel<<<rows, 128, 0, s>>>(rig.h[rig.cur ^ 1][0], rig.h[rig.cur][0], H, K, tb.parent_slot);
+    gather_state_kernel<<<rows, 128, 0, s>>>(rig.h[rig.cur ^ 1][0], rig.h[rig.cur][0], H, K, tb.parent_slot,
+                                             rig.tc ? rig.hs_hi[rig.cur ^ 1][0] : nullptr,
+                                             rig.tc ? rig.hs_lo[rig.cur ^ 1][0] : nullptr);
     ST_LAUNCH_TRY("gather_state_kernel");
     rig.cur ^= 1;
     cur_seq ^= 1;

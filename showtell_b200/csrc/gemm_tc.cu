@@ -61,7 +61,8 @@ struct PairCfg {
   static constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + STG_BYTES + 256;
 };
 
-enum { EPI_STORE = 0, EPI_CE_FWD = 1, EPI_CE_BWD = 2 };
+enum { EPI_STORE = 0, EPI_CE_FWD = 1, EPI_CE_BWD = 2, EPI_TOPK = 3 };
+constexpr int TOPK_SLOTS = 8;   // per-row candidates kept per epilogue warp (K <= 8 on the fused path)
 int g_variant = 0;   // st_debug_gemm_variant: 0 = choose, 128 / 256 = single-CTA tile width, 2 = CTA pairs
 int g_streamk = 1;   // st_debug_gemm_variant(v | 0x1000) turns stream-K off
 
@@ -80,6 +81,10 @@ struct TcParams {
   float scale;
   __nv_bfloat16 *P, *PT;  // bwd: (M, ldp) and (N, ldpt)
   int ldp, ldpt;
+  float* tk_val;          // EPI_TOPK: (M, npart, tk_k) partial top values (descending) ...
+  int32_t* tk_idx;        // ... and their column indices (ties: lower index first); npart as for the CE partials
+  int tk_k;               // candidates written per (row, part): the caller's K (<= TOPK_SLOTS).  With pmax / psum set the
+                          // epilogue also keeps the soft-max partials (running max, sum of exp) of its columns.
   int streamk;            // pair kernel: 1 = stream-K schedule (C zeroed by the launcher)
 };
 
@@ -109,10 +114,14 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tbase,
   const bool row_ok = row < p.M;
   const uint32_t stg_s = smem_u32(stg);
   float run_m = -FLT_MAX, run_s = 0.f, tl = 0.f;  // EPI_CE_FWD
+  float tkv[TOPK_SLOTS];                            // EPI_TOPK: this row's best TOPK_SLOTS logits of the warp's columns,
+  int tki[TOPK_SLOTS];                              // descending; equal values keep the lower column first
+#pragma unroll
+  for (int q = 0; q < TOPK_SLOTS; ++q) { tkv[q] = -FLT_MAX; tki[q] = 0x7fffffff; }
   bool have_tl = false;
   int tgt = -1;
   float lse_l2 = 0.f;
-  if (EPI != EPI_STORE && row_ok) tgt = (int)p.target[row];
+  if ((EPI == EPI_CE_FWD || EPI == EPI_CE_BWD) && row_ok) tgt = (int)p.target[row];
   if (EPI == EPI_CE_BWD && row_ok) lse_l2 = p.lse[row] * LOG2E;
   const float* bias = (p.bias && first_k) ? p.bias : nullptr;
   // 16-byte vector stores need an aligned base and leading dimension (views into wider buffers may have neither)
@@ -222,6 +231,36 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tbase,
             }
         }
       }
+    } else if (EPI == EPI_TOPK) {
+      // rnn.py:51,63,90-91: arg-max / top-K of the vocabulary logits without writing them.  Columns arrive in
+      // increasing order, so a strict '>' keeps the lower index among equal values (torch.max's first-maximum rule).
+      if (p.pmax) {   // beam_search.py:84-88 ranks by soft-max probability: keep the normaliser's partials too
+        float cm = -FLT_MAX;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full || nb + j < p.N) cm = fmaxf(cm, v[j]);
+        const float nm = fmaxf(run_m, cm);
+        float s0 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full || nb + j < p.N) s0 += expf(v[j] - nm);
+        run_s = fmaf(run_s, expf(run_m - nm), s0);
+        run_m = nm;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x = (full || nb + j < p.N) ? v[j] : -FLT_MAX;
+        if (x > tkv[TOPK_SLOTS - 1]) {
+          tkv[TOPK_SLOTS - 1] = x; tki[TOPK_SLOTS - 1] = nb + j;
+#pragma unroll
+          for (int q = TOPK_SLOTS - 1; q > 0; --q) {
+            if (tkv[q] > tkv[q - 1]) {
+              const float tv = tkv[q]; tkv[q] = tkv[q - 1]; tkv[q - 1] = tv;
+              const int ti = tki[q]; tki[q] = tki[q - 1]; tki[q - 1] = ti;
+            }
+          }
+        }
+      }
     } else if (EPI == EPI_CE_FWD) {
       if (!full) {
 #pragma unroll
@@ -310,6 +349,17 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tbase,
             }
         }
       }
+    }
+  }
+  if (EPI == EPI_TOPK && row_ok) {
+    float* ov = p.tk_val + ((size_t)row * p.npart + part) * p.tk_k;
+    int32_t* oi = p.tk_idx + ((size_t)row * p.npart + part) * p.tk_k;
+#pragma unroll
+    for (int q = 0; q < TOPK_SLOTS; ++q)
+      if (q < p.tk_k) { ov[q] = tkv[q]; oi[q] = tki[q]; }
+    if (p.pmax) {
+      p.pmax[(size_t)row * p.npart + part] = run_m;
+      p.psum[(size_t)row * p.npart + part] = run_s;
     }
   }
   if (EPI == EPI_CE_FWD && row_ok) {
@@ -514,7 +564,7 @@ template <int BN> struct Tf32Cfg {
   static constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + STG_BYTES + 256;
 };
 
-template <int BN>
+template <int BN, int EPI = EPI_STORE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                    const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const TcParams p) {
@@ -624,8 +674,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t tbase = tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16);
-      epilogue_warp<EPI_STORE>(p, tbase, m0 + ew * 32, n0, half * (BN / 64), BN / 64, stg + (warp - 4) * 4096, lane, false,
-                               true, 0);
+      epilogue_warp<EPI>(p, tbase, m0 + ew * 32, n0, half * (BN / 64), BN / 64, stg + (warp - 4) * 4096, lane, false,
+                         true, (n0 / BN) * 2 + half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -654,7 +704,7 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, int rows, int c
   }
 }
 
-template <int BN>
+template <int BN, int EPI = EPI_STORE>
 int launch_tf32x3(const TcParams& p, const float* Ah, const float* Al, int lda, const float* Bh, const float* Bl, int ldb,
                   cudaStream_t s, int sms) {
   CUtensorMap tmAh, tmAl, tmBh, tmBl;
@@ -662,7 +712,7 @@ int launch_tf32x3(const TcParams& p, const float* Ah, const float* Al, int lda, 
   ST_TRY(make_tmap_f32(&tmAl, Al, p.M, p.K, lda, BM, "A_lo"));
   ST_TRY(make_tmap_f32(&tmBh, Bh, p.N, p.K, ldb, BN, "B_hi"));
   ST_TRY(make_tmap_f32(&tmBl, Bl, p.N, p.K, ldb, BN, "B_lo"));
-  auto kern = gemm_tf32x3_kernel<BN>;
+  auto kern = gemm_tf32x3_kernel<BN, EPI>;
   ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tf32Cfg<BN>::SMEM_BYTES));
   const int ntiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int grid = ntiles < sms ? ntiles : sms;
@@ -890,6 +940,57 @@ __global__ void __launch_bounds__(256) ce_combine_kernel(int M, int npart, const
   }
 }
 
+// Per row: the K best of the npart * K candidates the epilogues kept (value descending, lower column index first
+// among equal values).  One warp per row, K rounds of warp arg-max with exclusion.  Writes (val, idx) with row stride
+// `out_stride` and/or the best index as int64 (greedy decoding: token matrix column).  With pmax / psum: also the row's
+// soft-max normaliser from the epilogues' partials: row_max, row_sum = sum_j exp(x_j - row_max).
+__global__ void __launch_bounds__(256) topk_merge_kernel(int M, int npart, int K, const float* __restrict__ cv,
+                                                         const int32_t* __restrict__ ci, float* __restrict__ val,
+                                                         int32_t* __restrict__ idx, int out_stride,
+                                                         int64_t* __restrict__ tok, int tok_stride,
+                                                         const float* __restrict__ pmax, const float* __restrict__ psum,
+                                                         float* __restrict__ row_max, float* __restrict__ row_sum) {
+  const int lane = threadIdx.x & 31, m = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const int ncand = npart * K;
+  const float* v = cv + (size_t)m * ncand;
+  const int32_t* ix = ci + (size_t)m * ncand;
+  float pv = FLT_MAX;            // the previous winner: candidates must rank strictly after it
+  int pi = -1;
+  for (int k = 0; k < K; ++k) {
+    float bv = -FLT_MAX;
+    int bi = 0x7fffffff;
+    for (int c = lane; c < ncand; c += 32) {
+      const float x = v[c];
+      const int i = ix[c];
+      const bool after_prev = (x < pv) || (x == pv && i > pi);
+      const bool better = (x > bv) || (x == bv && i < bi);
+      if (after_prev && better) { bv = x; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    pv = bv; pi = bi;
+    if (lane == 0) {
+      if (val) val[(size_t)m * out_stride + k] = bv;
+      if (idx) idx[(size_t)m * out_stride + k] = bi;
+      if (tok && k == 0) tok[(size_t)m * tok_stride] = bi;
+    }
+  }
+  if (pmax) {
+    float mx = -FLT_MAX;
+    for (int c = lane; c < npart; c += 32) mx = fmaxf(mx, pmax[(size_t)m * npart + c]);
+    mx = warp_max(mx);
+    float sm = 0.f;
+    for (int c = lane; c < npart; c += 32) sm += psum[(size_t)m * npart + c] * expf(pmax[(size_t)m * npart + c] - mx);
+    sm = warp_sum(sm);
+    if (lane == 0) { row_max[m] = mx; row_sum[m] = sm; }
+  }
+}
+
 // fp32 (rows, cols) -> bf16 copy and/or bf16 transpose (cols, rows).  32x32 tiles through smem.
 __global__ void cast_bf16_kernel(const float* __restrict__ src, int rows, int cols, int lds,
                                  __nv_bfloat16* __restrict__ dst, int ldd, __nv_bfloat16* __restrict__ dstT,
@@ -1109,6 +1210,36 @@ int st_gemm_tf32x3(int M, int N, int K, const float* A_hi, const float* A_lo, in
   ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
   return pick_bn(M, N, sms) == 256 ? launch_tf32x3<256>(p, A_hi, A_lo, lda, B_hi, B_lo, ldb, as_stream(stream), sms)
                                    : launch_tf32x3<128>(p, A_hi, A_lo, lda, B_hi, B_lo, ldb, as_stream(stream), sms);
+}
+
+int st_topk_parts(int N) { return 2 * ((N + 127) / 128) * st::TOPK_SLOTS; }
+
+int st_gemm_tf32x3_topk(int M, int N, int K, const float* A_hi, const float* A_lo, int lda, const float* B_hi,
+                        const float* B_lo, int ldb, const float* bias, int topk, float* cand_val, int32_t* cand_idx,
+                        float* val, int32_t* idx, int out_stride, int64_t* tok, int tok_stride, float* part_stats,
+                        float* row_max, float* row_sum, st_stream_t stream) {
+  using namespace st;
+  ST_REQUIRE(cand_val && cand_idx && (val || idx || tok), ST_ERR_NULL, "st_gemm_tf32x3_topk: NULL pointer");
+  ST_REQUIRE((!row_max && !row_sum) || (row_max && row_sum && part_stats), ST_ERR_NULL,
+             "st_gemm_tf32x3_topk: row_max, row_sum and part_stats go together");
+  ST_REQUIRE(M >= 1 && N >= 1 && K >= 1 && topk >= 1 && topk <= TOPK_SLOTS && topk <= N && (!(val || idx) || out_stride >= topk) &&
+                 (!tok || tok_stride >= 1),
+             ST_ERR_BAD_SHAPE, "st_gemm_tf32x3_topk: M=%d N=%d K=%d topk=%d (max %d)", M, N, K, topk, (int)TOPK_SLOTS);
+  TcParams p{};
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.alpha = 1.f;
+  p.tk_val = cand_val; p.tk_idx = cand_idx; p.tk_k = topk;
+  int sms = 0;
+  ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
+  cudaStream_t s = as_stream(stream);
+  const int bn = pick_bn(M, N, sms);
+  p.npart = 2 * ((N + bn - 1) / bn);
+  if (row_max) { p.pmax = part_stats; p.psum = part_stats + (size_t)M * p.npart; }
+  if (bn == 256) ST_TRY((launch_tf32x3<256, EPI_TOPK>(p, A_hi, A_lo, lda, B_hi, B_lo, ldb, s, sms)));
+  else ST_TRY((launch_tf32x3<128, EPI_TOPK>(p, A_hi, A_lo, lda, B_hi, B_lo, ldb, s, sms)));
+  topk_merge_kernel<<<(M + 7) / 8, 256, 0, s>>>(M, p.npart, topk, cand_val, cand_idx, val, idx, out_stride, tok, tok_stride,
+                                               p.pmax, p.psum, row_max, row_sum);
+  ST_LAUNCH_TRY("topk_merge_kernel");
+  return ST_OK;
 }
 
 int st_debug_gemm_variant(int variant) {

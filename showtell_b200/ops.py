@@ -366,6 +366,32 @@ def gemm_tf32x3(A, B, *, bias=None, alpha=1.0, beta=0.0, out=None):
     return out
 
 
+def gemm_tf32x3_topk(A, B, K_top, *, bias=None, want_tokens=False, want_stats=False):
+    """Per-row top-K of A . B^T + bias (fp32-accurate 3xTF32 product) without materialising the product.
+    A, B: (hi, lo) pairs from split_tf32.  Returns (val (M,K) f32, idx (M,K) i32[, tok (M,) i64][, row_max, row_sum]);
+    row_sum = sum_j exp(x_j - row_max), the soft-max normaliser of the row."""
+    lib = _lib.load()
+    (Ah, Al), (Bh, Bl) = A, B
+    M, K = Ah.shape
+    N = Bh.shape[0]
+    dev = Ah.device
+    parts = lib.st_topk_parts(N)
+    cv = torch.empty(M, parts, dtype=F32, device=dev)
+    ci = torch.empty(M, parts, dtype=I32, device=dev)
+    val = torch.empty(M, K_top, dtype=F32, device=dev)
+    idx = torch.empty(M, K_top, dtype=I32, device=dev)
+    tok = torch.empty(M, dtype=I64, device=dev) if want_tokens else None
+    ps = torch.empty(M, parts // 4, dtype=F32, device=dev) if want_stats else None
+    rmax = torch.empty(M, dtype=F32, device=dev) if want_stats else None
+    rsum = torch.empty(M, dtype=F32, device=dev) if want_stats else None
+    check(lib.st_gemm_tf32x3_topk(M, N, K, _raw(Ah), _raw(Al), Ah.stride(0), _raw(Bh), _raw(Bl), Bh.stride(0), ptr(bias, F32),
+                                  int(K_top), ptr(cv), ptr(ci), ptr(val), ptr(idx), K_top, ptr(tok), 1, ptr(ps), ptr(rmax),
+                                  ptr(rsum), stream_ptr()),
+          "st_gemm_tf32x3_topk")
+    out = (val, idx) + ((tok,) if want_tokens else ()) + ((rmax, rsum) if want_stats else ())
+    return out
+
+
 def cast_bf16(src, want=True, want_t=False):
     """fp32 (R,C) -> (bf16 (R,C) or None, bf16 transpose (C,R) or None).  Leading dimensions are
     padded to multiples of 8 so the results are valid TMA operands; the returned tensors are the

@@ -78,6 +78,31 @@ def test_golden_greedy(name):
     assert np.array_equal(tok1.cpu().numpy(), g["greedy_b1"])
 
 
+@pytest.fixture
+def table_mode():
+    """st_debug_decode_table: pin how the tensor-core decoding loops obtain the input projection of a fed-back word
+    (1 = rows of the projected-embedding table, -1 = a GEMM per step); restored to "by size" afterwards."""
+    from showtell_b200 import _lib
+    lib = _lib.load()
+    yield lambda mode: lib.st_debug_decode_table(int(mode))
+    lib.st_debug_decode_table(0)
+
+
+@pytest.mark.parametrize("table", [-1, 1])
+@pytest.mark.parametrize("name", BASE_CASES)
+def test_golden_greedy_tensor_cores(name, table, table_mode):
+    """decode_gemm="tf32x3": every product of the loop on the tensor cores, arg-max fused into the vocabulary
+    projection (no logits buffer) -- the same tokens as the reference run."""
+    dev = torch.device("cuda:0")
+    g = load_golden(name)
+    m = _module(g, dev)
+    m.decode_gemm = "tf32x3"
+    table_mode(table)
+    feat = torch.from_numpy(g["cnn_feature"]).to(dev)
+    assert np.array_equal(m.sentence_index(feat).cpu().numpy(), g["greedy"])
+    assert np.array_equal(m.sentence_index(feat[:1]).cpu().numpy(), g["greedy_b1"])
+
+
 # ranking margins (in logit units) below which a chain-beam round is decided by the rounding noise of the
 # products: 1e-5 for fp32 CUDA-core GEMMs, 4e-5 for the 3xTF32 tensor-core GEMMs (test_gemm_tf32x3_is_fp32_accurate)
 EPS = {"fp32": 1e-5, "tf32x3": 4e-5}
@@ -222,15 +247,47 @@ def _parity_train(kind, E, H, V, L, B, T, ragged, dtype, TOL):
     assert rel_err(logits, ex["logits"]) < TOL
 
 
-@pytest.mark.parametrize("kind,L", [("gru", 1), ("lstm", 1), ("gru", 2)])
-def test_oracle_parity_greedy_full_size(kind, L):
+@pytest.mark.parametrize("gemm,table", [("fp32", 0), ("tf32x3", -1), ("tf32x3", 1)])
+@pytest.mark.parametrize("kind,L", [("gru", 1), ("lstm", 1), ("gru", 2), ("lstm", 2)])
+def test_oracle_parity_greedy_full_size(kind, L, gemm, table, table_mode):
     dev = torch.device("cuda:0")
     m, feat, _, _ = _random_case(kind, 512, 512, 10000, L, 16, 20, 11, False)
+    m.decode_gemm = gemm
+    table_mode(table)
     p = {k: v.detach().clone() for k, v in m.state_dict().items()}
     with torch.no_grad():
         ref = O.rnn_greedy(p, kind, feat)
     tok = m.to(dev).sentence_index(feat.to(dev))
     assert np.array_equal(tok.cpu().numpy(), ref.numpy())
+
+
+@pytest.mark.parametrize("gemm", ["fp32", "tf32x3"])
+def test_oracle_parity_beam_tree_full_size(gemm):
+    """beam_search.py:45-97 at E=H=512, V=10000, beam 3, 20 rounds, 24 images in one call against the oracle's
+    per-image run.  The <end> logit is lifted so hypotheses finish at various lengths.  tf32x3: top-K and the
+    soft-max normaliser come out of the vocabulary GEMM's epilogue (no logits buffer)."""
+    dev = torch.device("cuda:0")
+    n, K, NH, T, end_id = 24, 3, 3, 20, 2
+    m, feat, _, _ = _random_case("gru", 512, 512, 10000, 1, n, 20, 23, False)
+    with torch.no_grad():
+        m.linear.bias[end_id] += 0.45
+    m.decode_gemm = gemm
+    p = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    tok, ln, cost = m.to(dev).sentence_index(feat.to(dev), beam_size=K, beam_mode="tree", max_len=T, start_id=1,
+                                            end_id=end_id, num_hypotheses=NH)
+    tok, ln, cost = tok.cpu(), ln.cpu(), cost.cpu()
+    same = finished = 0
+    for i in range(n):
+        init_fn, gen_fn = O.gru_tree_callbacks(p, feat[i])
+        ref = O.beam_search_tree(init_fn, gen_fn, np.zeros((1, 1), np.int32), 1, end_id, K, NH, T)
+        finished += len(ref)
+        ours = [tok[i, j, :int(ln[i, j])].tolist() for j in range(NH) if int(ln[i, j]) > 0]
+        if ours == [h.to_sequence_of_values() for h in ref]:
+            same += 1
+            for j, h in enumerate(ref):
+                assert abs(float(cost[i, j]) - h.cum_cost) < 1e-3 * max(1.0, abs(h.cum_cost)), (i, j)
+    print(f"tree beam-{K} ({gemm}), full size: {same}/{n} images with identical hypothesis lists, {finished} finished hypotheses")
+    assert finished >= n and same >= 0.9 * n
 
 
 @pytest.mark.parametrize("gemm", ["fp32", "tf32x3"])

@@ -380,3 +380,27 @@ def test_rnn_step_backward_with_folded_context_gradient(kind, H, lengths, monkey
     assert float((fused["dGb"].float() - ref["dGb"].float()).abs().max()) <= 2e-2 * float(ref["dGb"].float().abs().max())
     assert fused["dGT"] is None                      # row-major gate gradients only: the GEMMs read them in place
     assert float((dX - dX_ref).abs().max() / dX_ref.abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("M,N,K,topk", [(100, 50, 40, 3), (129, 257, 72, 5), (640, 10000, 512, 3), (4096, 10000, 512, 1),
+                                        (37, 1000, 2048, 8), (300, 10000, 512, 5)])
+def test_gemm_tf32x3_fused_topk(M, N, K, topk):
+    """Vocabulary projection fused with arg-max / top-K (rnn.py:51,63,90-91): same values and indices as the
+    materialised 3xTF32 product followed by torch.topk; exact ties resolve to the lower index (torch.max's rule)."""
+    from showtell_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K + topk)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    B = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    B[N // 2] = B[N // 3]                                   # two identical columns: an exact tie in every row
+    bias = torch.randn(N, generator=g).to(DEV)
+    bias[N // 2] = bias[N // 3]
+    sa, sb = ops.split_tf32(A), ops.split_tf32(B)
+    full = ops.gemm_tf32x3(sa, sb, bias=bias)
+    val, idx, tok, rmax, rsum = ops.gemm_tf32x3_topk(sa, sb, topk, bias=bias, want_tokens=True, want_stats=True)
+    rv, ri = torch.sort(full, dim=1, descending=True, stable=True)   # stable: lower index first among equal values
+    assert torch.equal(val, rv[:, :topk]), float((val - rv[:, :topk]).abs().max())
+    assert torch.equal(idx.long(), ri[:, :topk])
+    assert torch.equal(tok, ri[:, 0])
+    assert torch.equal(rmax, full.max(1)[0])                        # soft-max normaliser of the same logits
+    lse = rmax.double() + rsum.double().log()
+    assert float((lse - torch.logsumexp(full.double(), 1)).abs().max()) < 1e-5
