@@ -95,6 +95,7 @@ def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True, 
     input gradient exists (bf16 mode: before layer 0's weight-gradient products), so the embedding
     gradient and its exchange can start while the last weight gradients are still being formed."""
     dH = dHs_top
+    pending = []
     for l in reversed(range(L)):
         _, Whh, _, _ = layer_params(P, l)
         sv = layers[l]
@@ -103,14 +104,22 @@ def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True, 
             b = ops.rnn_seq_tc_bwd(kind, ops.bf16_shadow(Whh, transposed=True), bs, sv["out"], dH, tag="seq_bwd")
         if b is not None:                                                  # tensor-core BPTT: bf16 gate gradients out
             need_dx = l > 0 or need_dx0
-            dH = ops.gemm_bf16(b["dGb"], sv["lin"].Wb, b_t=True, tag="ih_dx") if need_dx else None     # dG W_ih
+            dGb, dGhb, lin, Hsb = b["dGb"], b["dGhb"], sv["lin"], sv["out"]["Hsb"]
+            # Everything below reads the gate gradients and nothing else of this step: the weight-gradient products
+            # and the bias sums run as concurrent chains on side streams (each far too small to fill the GPU) beside
+            # the input-gradient chain  dG W_ih -> embedding / feature gradients  on the main stream.
+            (grads[f"unit.weight_hh_l{l}"],), e1 = ops.fork(
+                lambda: (ops.gemm_bf16(dGhb, ops.shift_states(Hsb, bs), a_t=True, b_t=True, tag="hh_dw"),),
+                uses=(dGhb, Hsb), lane=1)
+            (grads[f"unit.weight_ih_l{l}"],), e2 = ops.fork(lambda: (lin.bwd_bf16(dGb, None, need_dx=False)[1],),
+                                                            uses=(dGb, lin.Xb), lane=2)
+            (grads[f"unit.bias_ih_l{l}"], grads[f"unit.bias_hh_l{l}"]), e3 = ops.fork(
+                lambda: (lambda s: (s, ops.colsum(dGhb) if dGhb is not dGb else s))(ops.colsum(dGb)),
+                uses=(dGb, dGhb), lane=3)
+            pending += [e1, e2, e3]
+            dH = ops.gemm_bf16(dGb, lin.Wb, b_t=True, tag="ih_dx") if need_dx else None     # dG W_ih
             if l == 0 and dx0_ready is not None:
                 dx0_ready(dH)
-            Hprev_b = ops.shift_states(sv["out"]["Hsb"], bs)
-            grads[f"unit.weight_hh_l{l}"] = ops.gemm_bf16(b["dGhb"], Hprev_b, a_t=True, b_t=True, tag="hh_dw")
-            grads[f"unit.bias_ih_l{l}"] = ops.colsum(b["dGb"])
-            grads[f"unit.bias_hh_l{l}"] = ops.colsum(b["dGhb"]) if b["dGhb"] is not b["dGb"] else grads[f"unit.bias_ih_l{l}"]
-            _, grads[f"unit.weight_ih_l{l}"] = sv["lin"].bwd_bf16(b["dGb"], None, need_dx=False)
             continue
         Hprev = ops.shift_states(sv["out"]["Hs"], bs)
         b = ops.rnn_seq_bwd(kind, Whh, bs, sv["out"], dH, tag="seq_bwd")
@@ -120,6 +129,8 @@ def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True, 
         grads[f"unit.weight_ih_l{l}"], grads[f"unit.bias_ih_l{l}"] = dW, db
         if l == 0 and dx0_ready is not None:
             dx0_ready(dH)
+    for e in pending:
+        ops.join(e)
     return dH
 
 
