@@ -53,6 +53,18 @@ int64_t st_launch_count(void);
 int st_debug_set_pdl(int on);
 /* A/B timing aid: k-blocks per TMA operation of the BPTT kernel's operand ring (0 = the library's choice, 1 / 2 / 4). */
 int st_debug_set_bwd_kp(int kp);
+/* ... and its K split: low byte 0 = choose, 1 = every CTA streams the whole K extent, 4 = K split over clusters of 4
+ * unit tiles; bits 8.. = batch-tile height of the K-split kernel (0 = choose, 64, 128). */
+int st_debug_set_bwd_ks(int ks);
+/* 1 = launch the multi-step tensor-core BPTT kernel cooperatively (needed only if two persistent recurrent kernels may
+ * run on one device at the same time); default 0 = ordinary launch (no wait for a drained GPU). */
+int st_debug_set_coop(int on);
+/* CTAs (= SMs) the BPTT kernel st_rnn_seq_tc_bwd occupies for a batch of B rows: the host side gives the rest of the
+ * GPU to the GEMMs it runs beside it (st_gemm_set_sm_limit). */
+int st_rnn_seq_tc_bwd_ctas(int kind, int H, int B);
+/* Cap on the persistent grid of the st_gemm_bf16* / st_vocab_ce_* launches that follow (0 = all SMs): a GEMM launched
+ * beside a cooperative recurrent kernel must leave that kernel's SMs free, or the two serialise. */
+int st_gemm_set_sm_limit(int n);
 /* Device facts the host side sizes grids with. */
 int st_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_optin_bytes);
 

@@ -48,6 +48,10 @@ _SIGS = {
     "st_gemm_tf32x3_topk": (_I, [_I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
     "st_debug_set_pdl": (_I, [_I]),
     "st_debug_set_bwd_kp": (_I, [_I]),
+    "st_debug_set_bwd_ks": (_I, [_I]),
+    "st_debug_set_coop": (_I, [_I]),
+    "st_rnn_seq_tc_bwd_ctas": (_I, [_I, _I, _I]),
+    "st_gemm_set_sm_limit": (_I, [_I]),
     "st_scale_multi": (_I, [_I, _P, _P, _P, _P, _P]),
     "st_bn1d_fwd": (_I, [_P, _I, _I, _I, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _I, _P]),
     "st_bn1d_bwd": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
@@ -116,6 +120,10 @@ def load():
         fn.argtypes = args
     if os.environ.get("SHOWTELL_PDL", "1") == "0":       # A/B switch for programmatic dependent launch
         lib.st_debug_set_pdl(0)
+    if os.environ.get("SHOWTELL_COOP", "0") == "1":        # cooperative launches of the persistent BPTT kernel
+        lib.st_debug_set_coop(1)
+    if os.environ.get("SHOWTELL_BWD_KS"):                  # A/B switch for the BPTT kernel's K split / tile height
+        lib.st_debug_set_bwd_ks(int(os.environ["SHOWTELL_BWD_KS"]))
     _lib = lib
     return lib
 

@@ -65,6 +65,12 @@ enum { EPI_STORE = 0, EPI_CE_FWD = 1, EPI_CE_BWD = 2, EPI_TOPK = 3 };
 constexpr int TOPK_SLOTS = 8;   // per-row candidates kept per epilogue warp (K <= 8 on the fused path)
 int g_variant = 0;   // st_debug_gemm_variant: 0 = choose, 128 / 256 = single-CTA tile width, 2 = CTA pairs
 int g_streamk = 1;   // st_debug_gemm_variant(v | 0x1000) turns stream-K off
+int g_sm_limit = 0;  // st_gemm_set_sm_limit: cap on the persistent grids (0 = all SMs)
+inline int gemm_sms(int* sms) {
+  ST_TRY(st_device_info(sms, nullptr, nullptr, nullptr));
+  if (g_sm_limit > 0 && g_sm_limit < *sms) *sms = g_sm_limit;
+  return ST_OK;
+}
 
 struct TcParams {
   int M, N, K;
@@ -1116,7 +1122,7 @@ template <int AMN, int BMN>
 int launch_tc_major(const TcParams& p, const void* A, int lda, const void* B, int ldb, cudaStream_t s) {
   ST_REQUIRE(p.M >= 1 && p.N >= 1 && p.K >= 1, ST_ERR_BAD_SHAPE, "gemm_bf16: M=%d N=%d K=%d", p.M, p.N, p.K);
   int sms = 0;
-  ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
+  ST_TRY(gemm_sms(&sms));
   const int bn = (g_variant == 128 || g_variant == 256) ? g_variant : pick_variant<EPI_STORE>(p, sms);
   return bn == 256 ? launch_tc_bn<EPI_STORE, 256, AMN, BMN>(p, A, lda, B, ldb, s, sms)
                    : launch_tc_bn<EPI_STORE, 128, AMN, BMN>(p, A, lda, B, ldb, s, sms);
@@ -1126,7 +1132,7 @@ template <int EPI>
 int launch_tc(const TcParams& p, const void* A, int lda, const void* B, int ldb, cudaStream_t s, int bn = 0) {
   ST_REQUIRE(p.M >= 1 && p.N >= 1 && p.K >= 1, ST_ERR_BAD_SHAPE, "gemm_bf16: M=%d N=%d K=%d", p.M, p.N, p.K);
   int sms = 0;
-  ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
+  ST_TRY(gemm_sms(&sms));
   if (bn == 0 && want_narrow<EPI>(p, sms)) return launch_tc_bn<EPI_STORE, 64>(p, A, lda, B, ldb, s, sms);
   if (bn == 0) bn = pick_variant<EPI>(p, sms);
   if (bn == 2) return launch_tc_pair<EPI>(p, A, lda, B, ldb, s, sms);
@@ -1239,6 +1245,11 @@ int st_gemm_tf32x3_topk(int M, int N, int K, const float* A_hi, const float* A_l
   topk_merge_kernel<<<(M + 7) / 8, 256, 0, s>>>(M, p.npart, topk, cand_val, cand_idx, val, idx, out_stride, tok, tok_stride,
                                                p.pmax, p.psum, row_max, row_sum);
   ST_LAUNCH_TRY("topk_merge_kernel");
+  return ST_OK;
+}
+
+int st_gemm_set_sm_limit(int n) {
+  st::g_sm_limit = n > 0 ? n : 0;
   return ST_OK;
 }
 

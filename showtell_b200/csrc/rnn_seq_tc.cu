@@ -19,6 +19,9 @@
 // Generic-proxy global stores of step t are read by TMA (async proxy) in step t+1 / phase 2: the
 // writers publish with red.release.gpu on the batch tile's arrival counter, the single TMA-issuing
 // thread acquires it and issues fence.proxy.async before the loads.
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -52,6 +55,25 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void proxy_fence_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+// ---- thread-block-cluster helpers of the K-split BPTT kernel
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 16 bytes into a peer CTA's shared memory; completes 16 bytes on the peer's mbarrier (no fences, no remote arrive)
+__device__ __forceinline__ void st_async_v4(uint32_t dst_cluster, float a, float b, float c, float d, uint32_t bar_cluster) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(dst_cluster), "f"(a), "f"(b), "f"(c), "f"(d), "r"(bar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void lds8(uint32_t addr, float (&v)[8]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(addr + 16));
+}
 
 __device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
   const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
@@ -313,26 +335,41 @@ struct TcBwdParams {
   int* barrier;
 };
 
-template <int G, int BT, int KP>
+// KS = 1: every CTA streams the whole K = G*H extent of its batch tile's gate gradients.
+// KS = 4: the K extent is split over a thread-block cluster of 4 unit tiles of the same batch tile.  CTA j of
+// the cluster streams k-blocks [j KB/4, (j+1) KB/4) only -- a quarter of the TMA bytes and a quarter of the MMA
+// instructions per step, both of which bound the step (a 64 x N x 16 MMA costs ~23 clocks whatever N is; tools/
+// probe_mma.cu) -- against the W_hh^T rows of ALL 64 units of the cluster, so its accumulator is a K-partial of the
+// cluster's 64 x 64 output tile.  The partials of the 16 units each CTA owns are sent to it through distributed
+// shared memory (st.async, completing bytes on the owner's mbarrier) and summed there in a fixed order.
+template <int G, int BT, int KP, int KS>
 __global__ void __launch_bounds__(NTH, 1)
 rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_constant__ CUtensorMap tmD,
                       const __grid_constant__ StepTable tab, const TcBwdParams p) {
   constexpr int BSTAGES = RingCfg<KP, BT>::STAGES;
+  constexpr int NU = UT * KS;                    // units of the MMA's N dimension
+  static_assert(KS == 1 || KS == 4, "K split: clusters of 4 unit tiles");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int H = p.H, GH = G * H, KB = (GH + 63) / 64;
-  constexpr uint32_t KBLK_W = UT * 128;          // 16 rows x 128 B
+  const int KBC = KB / KS;                       // k-blocks this CTA streams per step (launcher: KB % KS == 0, KBC % KP == 0)
+  const int krank = (KS == 1) ? 0 : (int)(blockIdx.x % KS);   // rank in the cluster (cluster = KS consecutive x)
+  const int kb0 = krank * KBC;
+  constexpr uint32_t KBLK_W = NU * 128;          // NU rows x 128 B
   constexpr uint32_t KBLK_A = BT * 128;          // one k-block of the dGh tile
   constexpr uint32_t STAGE_A = KP * KBLK_A;      // one ring stage: KP k-blocks
-  const int NOPS = (KB + KP - 1) / KP;           // TMA operations (= ring stages consumed) per step
-  uint8_t* sW = smem;                            // [KB][16 rows][128 B]   W_hh^T slice (B operand)
-  uint8_t* sA = smem + (size_t)KB * KBLK_W;      // [BSTAGES][KP][BT rows][128 B]  dGh ring (A operand)
+  const int NOPS = (KBC + KP - 1) / KP;          // TMA operations (= ring stages consumed) per step
+  uint8_t* sW = smem;                            // [KBC][NU rows][128 B]   W_hh^T slice (B operand)
+  uint8_t* sA = smem + (size_t)KBC * KBLK_W;     // [BSTAGES][KP][BT rows][128 B]  dGh ring (A operand)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)BSTAGES * STAGE_A);
   uint64_t* wbar = bars;
   uint64_t* accbar = bars + 1;
-  uint64_t* full = bars + 2;
+  uint64_t* xbar = bars + 2;                     // K split: the peers' partials have landed
+  uint64_t* full = bars + 3;
   uint64_t* empty = full + BSTAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty + BSTAGES);
+  float* xbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);   // K split: [KS-1 sources][BT rows][UT units]
+  constexpr uint32_t XBYTES = (KS - 1) * BT * UT * 4;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u0 = blockIdx.x * UT, r0 = blockIdx.y * BT;
@@ -340,23 +377,29 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
   if (warp == 0 && lane == 0) {
     mbar_init(wbar, 1);
     mbar_init(accbar, 1);
+    mbar_init(xbar, 1);
     for (int i = 0; i < BSTAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // K split: arm the exchange barrier for the first step (bytes may arrive before or after; each later phase is
+    // armed by the thread that saw the previous one complete -- never two arrivals in one phase)
+    if (KS > 1) mbar_expect_tx(xbar, (KS - 1) * BT * UT * 4);
   }
+  constexpr uint32_t TCOLS = NU < 32 ? 32u : (uint32_t)NU;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(32u)
+                 "r"(TCOLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
+  if (KS > 1) cluster_sync_();    // every peer's exchange barrier exists before anyone can send to it
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   if (warp == 0 && lane == 0) {
-    mbar_expect_tx(wbar, (uint32_t)KB * KBLK_W);
-    for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + (size_t)kb * KBLK_W, &tmWT, kb * 64, u0, wbar);
+    mbar_expect_tx(wbar, (uint32_t)KBC * KBLK_W);
+    for (int kb = 0; kb < KBC; ++kb) tma_load_2d(sW + (size_t)kb * KBLK_W, &tmWT, (kb0 + kb) * 64, u0 - krank * UT, wbar);
   }
 
   pdl_wait();                 // see the forward kernel: the prologue overlapped the previous kernel's tail
@@ -483,15 +526,15 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
         mbar_wait(&empty[stage_p], phase_p ^ 1);
         if (elect_one()) {
           mbar_expect_tx(&full[stage_p], STAGE_A);   // k-blocks past the last one are zero-filled, bytes still count
-          if (KP == 1) tma_load_2d(sA + (size_t)stage_p * STAGE_A, &tmD, op * 64, rbase, &full[stage_p]);
-          else tma_load_3d(sA + (size_t)stage_p * STAGE_A, &tmD, 0, rbase, op * KP, &full[stage_p]);
+          if (KP == 1) tma_load_2d(sA + (size_t)stage_p * STAGE_A, &tmD, (kb0 + op) * 64, rbase, &full[stage_p]);
+          else tma_load_3d(sA + (size_t)stage_p * STAGE_A, &tmD, 0, rbase, kb0 + op * KP, &full[stage_p]);
         }
         __syncwarp();
         if (++stage_p == BSTAGES) { stage_p = 0; phase_p ^= 1; }
       }
     } else if (warp == 1) {   // whole warp, uniform control flow; one elected lane issues (see elect_one)
       if (!w_ready) { mbar_wait(wbar, 0); w_ready = true; }
-      constexpr uint32_t idesc = umma_idesc(BT, UT);
+      constexpr uint32_t idesc = umma_idesc(BT, NU);
       const uint64_t adesc0 = umma_desc_k128(smem_u32(sA)), bdesc0 = umma_desc_k128(smem_u32(sW));
       for (int op = 0; op < NOPS; ++op) {
         mbar_wait(&full[stage_c], phase_c);
@@ -504,7 +547,7 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
 #pragma unroll
           for (int j = 0; j < KP; ++j) {
             const int kb = op * KP + j;
-            if (kb < KB) {
+            if (kb < KBC) {
               const uint64_t bd = bdesc0 + (uint64_t)(kb * (KBLK_W >> 4));
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
@@ -523,7 +566,39 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
       if (threadIdx.x == 64) stamp(p.tl, t, 5);
       tc_fence_after();
       float acc[HALF];
-      tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + hf * HALF, acc);
+      if (KS == 1) {
+        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + hf * HALF, acc);
+      } else {
+        // K-partials of the cluster's 64 x 64 tile: columns [16 d, 16 d + 16) belong to CTA d.  Keep mine, send the
+        // others' (every live lane sends, masked rows included: the owner counts bytes).
+        const uint32_t xb = smem_u32(xbuf), xr = smem_u32(xbar);
+#pragma unroll
+        for (int d = 0; d < KS; ++d) {
+          float v[HALF];
+          tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + d * UT + hf * HALF, v);
+          if (d == krank) {
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) acc[j] = v[j];
+          } else if (lane_ok) {
+            const int slot = (krank + KS - d - 1) % KS;                      // 0 .. KS-2, one per source
+            const uint32_t dst = mapa_u32(xb + (uint32_t)(((slot * BT + row) * UT + hf * HALF) * 4), (uint32_t)d);
+            const uint32_t bar = mapa_u32(xr, (uint32_t)d);
+            st_async_v4(dst, v[0], v[1], v[2], v[3], bar);
+            st_async_v4(dst + 16, v[4], v[5], v[6], v[7], bar);
+          }
+        }
+        mbar_wait(xbar, aph);
+        if (warp == 2 && lane == 0) mbar_expect_tx(xbar, XBYTES);            // next step's phase
+        if (lane_ok) {
+#pragma unroll
+          for (int sidx = 0; sidx < KS - 1; ++sidx) {                        // fixed order: deterministic sums
+            float v[HALF];
+            lds8(xb + (uint32_t)(((sidx * BT + row) * UT + hf * HALF) * 4), v);
+#pragma unroll
+            for (int j = 0; j < HALF; ++j) acc[j] += v[j];
+          }
+        }
+      }
       if (r_ok) {
 #pragma unroll
         for (int j = 0; j < HALF; ++j) dhrec[j] = acc[j] + direct[j];
@@ -543,7 +618,7 @@ rnn_seq_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmWT, const __grid_con
     if (lane == 0 && !w_ready) mbar_wait(wbar, 0);
     __syncwarp();
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
   }
 }
 
@@ -620,38 +695,79 @@ int make_tmap_kblocks(CUtensorMap* map, const void* ptr, int rows, int GH, int b
   return ST_OK;
 }
 
+int g_coop = 0;     // st_debug_set_coop: 1 = cooperative launches for the multi-step recurrent kernels
 int g_bwd_kp = 0;   // st_debug_set_bwd_kp: 0 = choose, 1 / 2 / 4 = k-blocks per TMA operation (A/B timing)
+int g_bwd_ks = 0;   // st_debug_set_bwd_ks: 0 = choose, 1 = no K split, 4 = K split over clusters of 4 unit tiles
 
-template <int G, int BT, int KP>
+template <int G, int BT, int KP, int KS>
 int try_tc_bwd(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cudaStream_t s, bool* launched) {
   constexpr int BSTAGES = RingCfg<KP, BT>::STAGES;
   const int H = p.H, GH = G * H, KB = (GH + 63) / 64, N = tab.off[tab.nsteps];
-  const size_t smem = 1024 + (size_t)KB * (UT * 128) + (size_t)BSTAGES * KP * (BT * 128) + 256;
-  auto kern = rnn_seq_tc_bwd_kernel<G, BT, KP>;
-  ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  *launched = false;
+  if (KS > 1 && (H % (UT * KS) != 0 || GH % 64 != 0 || KB % KS != 0 || (KB / KS) % KP != 0)) return ST_OK;
+  const size_t smem = 1024 + (size_t)(KB / KS) * (UT * KS * 128) + (size_t)BSTAGES * KP * (BT * 128) + 512 +
+                      (size_t)(KS - 1) * BT * UT * 4 + 64;
+  auto kern = rnn_seq_tc_bwd_kernel<G, BT, KP, KS>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return ST_OK;
+  }
   dim3 grid(H / UT, (tab.bs[p.t_lo] + BT - 1) / BT);
-  int cores = 0;
-  ST_TRY(coresident((const void*)kern, smem, &cores));
   // the tile height is chosen from the FULL batch so that every launch of a reverse pass agrees on it
   // (the barrier counters carry over between the launches)
   const int gy_full = (tab.bs[0] + BT - 1) / BT;
-  *launched = (int)(grid.x * gy_full) <= cores && gy_full <= 64;
-  if (!*launched) return ST_OK;
+  if (gy_full > 64) return ST_OK;
+  const bool one_step = p.t_hi - p.t_lo == 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(NTH); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (KS > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = KS; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = at; cfg.numAttrs = na;
+  if (KS > 1) {
+    int nclusters = 0;
+    cfg.gridDim = dim3(H / UT, gy_full);
+    const cudaError_t oe = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
+    if (getenv("ST_DEBUG")) fprintf(stderr, "rnn_seq_tc_bwd K split: occupancy query %s, %d clusters of %d for %d CTAs\n",
+                                    cudaGetErrorString(oe), nclusters, KS, (int)(grid.x * gy_full));
+    if (oe != cudaSuccess) { cudaGetLastError(); return ST_OK; }
+    if (nclusters * KS < (int)(grid.x * gy_full)) return ST_OK;
+    cfg.gridDim = grid;
+  } else {
+    int cores = 0;
+    ST_TRY(coresident((const void*)kern, smem, &cores));
+    if ((int)(grid.x * gy_full) > cores) return ST_OK;
+  }
+  *launched = true;
   CUtensorMap tmWT, tmD;
-  ST_TRY(make_tmap(&tmWT, WhhT_bf16, H, GH, GH, UT, "WhhT_bf16"));
+  ST_TRY(make_tmap(&tmWT, WhhT_bf16, H, GH, GH, UT * KS, "WhhT_bf16"));
   if (KP == 1) ST_TRY(make_tmap(&tmD, p.dGh, N, GH, GH, BT, "dGh_bf16"));
   else ST_TRY(make_tmap_kblocks(&tmD, p.dGh, N, GH, BT, KP));
   // Barrier counters are zeroed by the launch that starts a reverse pass (t_hi == nsteps); later launches
   // of the pass continue them (TcBwdParams::t_zero), which spares a memset node per step.
   if (p.t_hi == p.nsteps) ST_CUDA_TRY(cudaMemsetAsync(p.barrier, 0, sizeof(int) * 64, s));
-  if (p.t_hi - p.t_lo == 1) {
-    // one step: phase 1 -> barrier -> phase 2 among CTAs that all fit on the device (checked above); an
-    // ordinary launch, programmatically chained to the previous kernel, instead of a cooperative one
-    ST_CUDA_TRY(launch_pdl(kern, grid, dim3(NTH), smem, s, tmWT, tmD, tab, p));
+  // The CTAs meet at device-wide barriers and all fit on the device (checked above).  An ordinary launch,
+  // programmatically chained to the previous kernel: a COOPERATIVE launch starts only once the GPU has drained --
+  // measured 17 us of idle SMs per training step while the vocabulary bias-gradient sums of the side stream finish --
+  // whereas ordinary CTAs start as SMs free up.  Nothing resident can wait on this kernel (its programmatic dependents
+  // are scheduled only after every CTA of this grid is resident), so all its CTAs do become resident; the one
+  // thing the caller must not do is run TWO persistent recurrent kernels on one device at the same time
+  // (SHOWTELL_COOP=1 / st_debug_set_coop(1) restores cooperative launches for that case).
+  if (one_step || !g_coop) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    if (g_pdl) ++na;
   } else {
-    void* args[] = {(void*)&tmWT, (void*)&tmD, (void*)&tab, (void*)&p};
-    ST_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)kern, grid, dim3(NTH), args, smem, s));
+    at[na].id = cudaLaunchAttributeCooperative;
+    at[na].val.cooperative = 1;
+    ++na;
   }
+  cfg.numAttrs = na;
+  ST_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmWT, tmD, tab, p));
   note_launch();
   if (p.t_lo == 0 && p.dbih != nullptr && p.dGT != nullptr) {
     // bias gradients = row sums of the transposed gate gradients (contiguous per gate row)
@@ -662,18 +778,42 @@ int try_tc_bwd(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cudaS
   return ST_OK;
 }
 
+int g_bwd_bt = 0;   // st_debug_set_bwd_ks(ks | bt << 8): batch-tile height of the K-split kernel, 0 = choose
+
+// Batch-tile height of the K-split kernel: 64 rows.  (128-row tiles halve the CTAs but measured 8.9 us instead of
+// 5.8 us per step at B = 256, H = 512: twice the stores in front of every release, twice the exchange bytes.)
+inline int ksplit_bt(int B, int H) {
+  (void)B; (void)H;
+  return g_bwd_bt == 128 ? 128 : 64;
+}
+
+template <int G, int BT>
+int try_tc_bwd_ks(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cudaStream_t s, bool* ok) {
+  const int kbc = ((G * p.H + 63) / 64) / 4;
+  // 128-row tiles: 64 KB ring stages at 4 k-blocks per operation -- two stages are one step's operands
+  if (kbc % 4 == 0) return try_tc_bwd<G, BT, 4, 4>(tab, p, WhhT_bf16, s, ok);
+  if (kbc % 2 == 0) return try_tc_bwd<G, BT, 2, 4>(tab, p, WhhT_bf16, s, ok);
+  return try_tc_bwd<G, BT, 1, 4>(tab, p, WhhT_bf16, s, ok);
+}
+
 template <int G>
 int launch_tc_bwd(const StepTable& tab, TcBwdParams p, const void* WhhT_bf16, cudaStream_t s) {
   bool ok = false;
-  const int GH = G * p.H;
+  const int GH = G * p.H, KB = (GH + 63) / 64;
+  // K split over clusters of 4 unit tiles (see the kernel): a quarter of the bytes and MMAs per CTA and step
+  if (g_bwd_ks != 1 && GH % 64 == 0 && KB % 4 == 0) {
+    if (ksplit_bt(tab.bs[0], p.H) == 128) ST_TRY((try_tc_bwd_ks<G, 128>(tab, p, WhhT_bf16, s, &ok)));
+    if (!ok) ST_TRY((try_tc_bwd_ks<G, 64>(tab, p, WhhT_bf16, s, &ok)));
+    if (ok) return ST_OK;
+  }
   // k-blocks per TMA operation: 4 when they tile the K extent (G*H % 256 == 0), else 2 (% 128), else 2-D boxes
   int kp = (GH % 256 == 0) ? 4 : ((GH % 128 == 0) ? 2 : 1);
   if (g_bwd_kp == 1 || (g_bwd_kp == 2 && GH % 128 == 0) || (g_bwd_kp == 4 && GH % 256 == 0)) kp = g_bwd_kp;
-  if (kp == 4) ST_TRY((try_tc_bwd<G, 64, 4>(tab, p, WhhT_bf16, s, &ok)));
-  else if (kp == 2) ST_TRY((try_tc_bwd<G, 64, 2>(tab, p, WhhT_bf16, s, &ok)));
-  else ST_TRY((try_tc_bwd<G, 64, 1>(tab, p, WhhT_bf16, s, &ok)));
-  if (!ok && kp >= 2) ST_TRY((try_tc_bwd<G, 128, 2>(tab, p, WhhT_bf16, s, &ok)));
-  if (!ok) ST_TRY((try_tc_bwd<G, 128, 1>(tab, p, WhhT_bf16, s, &ok)));
+  if (kp == 4) ST_TRY((try_tc_bwd<G, 64, 4, 1>(tab, p, WhhT_bf16, s, &ok)));
+  else if (kp == 2) ST_TRY((try_tc_bwd<G, 64, 2, 1>(tab, p, WhhT_bf16, s, &ok)));
+  else ST_TRY((try_tc_bwd<G, 64, 1, 1>(tab, p, WhhT_bf16, s, &ok)));
+  if (!ok && kp >= 2) ST_TRY((try_tc_bwd<G, 128, 2, 1>(tab, p, WhhT_bf16, s, &ok)));
+  if (!ok) ST_TRY((try_tc_bwd<G, 128, 1, 1>(tab, p, WhhT_bf16, s, &ok)));
   ST_REQUIRE(ok, ST_ERR_UNSUPPORTED, "rnn_seq_tc_bwd: batch %d x H %d is not co-resident", tab.bs[0], p.H);
   return ST_OK;
 }
@@ -686,6 +826,26 @@ extern "C" {
 int st_debug_set_bwd_kp(int kp) {
   st::g_bwd_kp = (kp == 1 || kp == 2 || kp == 4) ? kp : 0;
   return ST_OK;
+}
+
+int st_debug_set_bwd_ks(int ks) {
+  const int bt = ks >> 8;
+  ks &= 0xff;
+  st::g_bwd_ks = (ks == 1 || ks == 4) ? ks : 0;
+  st::g_bwd_bt = (bt == 64 || bt == 128) ? bt : 0;
+  return ST_OK;
+}
+
+int st_debug_set_coop(int on) {
+  st::g_coop = on ? 1 : 0;
+  return ST_OK;
+}
+
+int st_rnn_seq_tc_bwd_ctas(int kind, int H, int B) {
+  using namespace st;
+  const int G = kind == ST_LSTM ? 4 : 3, GH = G * H, KB = (GH + 63) / 64;
+  if (g_bwd_ks != 1 && GH % 64 == 0 && KB % 4 == 0 && H % 64 == 0) return (H / UT) * ((B + ksplit_bt(B, H) - 1) / ksplit_bt(B, H));
+  return (H / UT) * ((B + 63) / 64);
 }
 
 /* development aid: device buffer of (nsteps * 8) int64 receiving %globaltimer stamps of CTA (0,0) */

@@ -89,11 +89,12 @@ def stack_forward(mode, P, kind, L, X, bs, save):
     return layers[-1]["out"]["Hs"], layers
 
 
-def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True, dx0_ready=None):
+def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True, dx0_ready=None, after_bptt=None):
     """BPTT through the L layers, top down.  Fills grads[...] for the unit.* parameters and returns
     the gradient w.r.t. the packed layer-0 input (N, in_0).  `dx0_ready(dX)`: called as soon as that
     input gradient exists (bf16 mode: before layer 0's weight-gradient products), so the embedding
-    gradient and its exchange can start while the last weight gradients are still being formed."""
+    gradient and its exchange can start while the last weight gradients are still being formed.
+    `after_bptt()`: called right after the top layer's BPTT kernel is issued (work to be ordered behind it)."""
     dH = dHs_top
     pending = []
     for l in reversed(range(L)):
@@ -102,6 +103,9 @@ def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True, 
         b = None
         if sv["tc"]:
             b = ops.rnn_seq_tc_bwd(kind, ops.bf16_shadow(Whh, transposed=True), bs, sv["out"], dH, tag="seq_bwd")
+            if b is not None and after_bptt is not None and l == L - 1:
+                after_bptt()
+                after_bptt = None
         if b is not None:                                                  # tensor-core BPTT: bf16 gate gradients out
             need_dx = l > 0 or need_dx0
             dGb, dGhb, lin, Hsb = b["dGb"], b["dGhb"], sv["lin"], sv["out"]["Hsb"]
@@ -123,6 +127,9 @@ def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True, 
             continue
         Hprev = ops.shift_states(sv["out"]["Hs"], bs)
         b = ops.rnn_seq_bwd(kind, Whh, bs, sv["out"], dH, tag="seq_bwd")
+        if after_bptt is not None and l == L - 1:
+            after_bptt()
+            after_bptt = None
         grads[f"unit.weight_hh_l{l}"] = weight_grad(mode, b["dGh"], Hprev, "hh_dw")  # dGh^T Hprev
         grads[f"unit.bias_hh_l{l}"] = ops.colsum(b["dGh"])
         dH, dW, db = sv["lin"].bwd(b["dG"], need_dx=(l > 0 or need_dx0))
@@ -140,20 +147,23 @@ def base_forward(mode, P, kind, L, feature, caption, bs, save):
 
 
 def base_backward_from_dHs(mode, P, kind, L, caption, bs, layers, dHs, grads, want_dfeature, feature_shape,
-                           emb_out=None, emb_done=None):
+                           emb_out=None, emb_done=None, after_bptt=None):
     """`emb_out()` / `emb_done()`: data parallelism -- buffer for the embedding gradient, and a call
     the moment it is final (the layer-0 weight gradients are formed after it)."""
     box = {}
+    # the embedding gradient is a scatter-add into zeros: clear the (V, E) buffer beside the BPTT kernel, not after it
+    dEmb = emb_out() if emb_out is not None else torch.empty_like(P["embeddings.weight"])
+    _, zeroed = ops.fork(dEmb.zero_, lane=4)
 
     def dx0_ready(dX):
-        dEmb = emb_out().zero_() if emb_out is not None else torch.zeros_like(P["embeddings.weight"])
+        ops.join(zeroed)
         box["dfeat"] = torch.empty(feature_shape, dtype=F32, device=dX.device) if want_dfeature else None
         ops.pack_inputs_bwd(dX, dEmb, box["dfeat"], caption, bs, True)
         grads["embeddings.weight"] = dEmb
         if emb_done is not None:
             emb_done()
 
-    stack_backward(mode, P, kind, L, bs, layers, dHs, grads, dx0_ready=dx0_ready)
+    stack_backward(mode, P, kind, L, bs, layers, dHs, grads, dx0_ready=dx0_ready, after_bptt=after_bptt)
     return box["dfeat"]
 
 
@@ -203,14 +213,18 @@ class BaseLogitsFn(torch.autograd.Function):
         return (None, dfeat, None, None) + tuple(grads[n] for n in ctx.names)
 
 
-def vocab_ce(mode, P, Hs, target, denom, need, gout=None, Hs_bf16=None):
+def vocab_ce(mode, P, Hs, target, denom, need, gout=None, Hs_bf16=None, side_sms=None, defer_db=False):
     """Mean cross-entropy of the vocabulary projection of Hs (N,H) and, if `need`, its gradients.
     Returns (loss (0-d), dHs or None, grads dict, event).  bf16 mode: the weight / bias gradients do
     not feed the rest of the backward pass, so they run on the side stream (ops.fork) beside the BPTT
     kernels; `event` marks their completion (None when they ran in line) -- ops.join it, or hand it to
     the gradient reducer, before the gradients are read.  `gout`: optional [dW, db] output tensors (a
     gradient reducer's symmetric bucket) for bf16 mode.  `Hs_bf16`: the bf16 copy of Hs the recurrent kernel
-    already wrote (else Hs is cast once)."""
+    already wrote (else Hs is cast once).  `side_sms`: SMs the side-stream products may occupy (None: all) -- the
+    cooperative BPTT kernel that follows on the main stream needs the rest free to start.  `defer_db` (bf16 mode):
+    the bias gradient -- column sums over the 100 MB dlogits matrix, a long grid that would sit in front of the BPTT
+    kernel's CTAs -- is not issued here: grads["_late_db"] = a function that issues it (the caller orders it behind the
+    BPTT kernel, where HBM is idle) and returns (db, event)."""
     Wv, bv = P["linear.weight"], P["linear.bias"]
     grads = {}
     if mode == "fp32":
@@ -231,10 +245,19 @@ def vocab_ce(mode, P, Hs, target, denom, need, gout=None, Hs_bf16=None):
         # dlogits = (softmax - onehot) / denom recomputed tile by tile and written ONCE, row-major bf16; the three
         # products below read it in place: dW = dlogits^T Hs (both operands MN-major), db = column sums, dHs = dlogits W_v
         Pm, _ = ops.vocab_ce_bwd(Hb, Wb, bv, target, lse, 1.0 / denom, want_t=False, tag="vocab_dlogits")
-        (grads["linear.weight"], grads["linear.bias"]), done = ops.fork(
-            lambda: (ops.gemm_bf16(Pm, Hb, a_t=True, b_t=True, tag="vocab_dw", out=gout[0] if gout else None),
-                     ops.colsum(Pm, out=gout[1] if gout else None)),
-            uses=(Pm, Hb))
+        # dW / db do not feed the rest of the backward pass: side stream, beside dHs = dlogits W_v and whatever follows.
+        # (A cooperative launch -- the BPTT kernel -- starts only on a drained GPU, so nothing launched before it can
+        # run beside it; `side_sms` caps the side products' persistent grid for callers that want to leave SMs free.)
+        def weight_grads():
+            with ops.gemm_sm_limit(side_sms):
+                dW = ops.gemm_bf16(Pm, Hb, a_t=True, b_t=True, tag="vocab_dw", out=gout[0] if gout else None)
+            return dW, (None if defer_db else ops.colsum(Pm, out=gout[1] if gout and len(gout) > 1 else None))
+
+        (grads["linear.weight"], db), done = ops.fork(weight_grads, uses=(Pm, Hb))
+        if defer_db:
+            grads["_late_db"] = lambda: ops.fork(lambda: ops.colsum(Pm), uses=(Pm,), lane=5)
+        else:
+            grads["linear.bias"] = db
         dHs = ops.gemm_bf16(Pm, Wb, b_t=True, tag="vocab_dx")
     return (loss_sum / denom).reshape(()), dHs, grads, done
 
@@ -288,18 +311,30 @@ class BaseLossFn(torch.autograd.Function):
         def body(feat, cap):
             Hs, layers = base_forward(mode, P, kind, L, feat, cap, bs, need)
             target = ops.pack_targets(cap, bs, P["linear.weight"].shape[0])
-            gout = red.slots([P["linear.weight"].shape, P["linear.bias"].shape]) if (red is not None and need) else None
-            loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, denom, need, gout=gout,
+            # bf16 mode: the vocabulary bias gradient is issued behind the BPTT kernel (see vocab_ce) and, under data
+            # parallelism, travels with the last bucket instead of the vocabulary weight's
+            defer = False     # measured: the sums then lengthen the backward tail by what they save in front of BPTT
+            lin = ["linear.weight"] if defer else ["linear.weight", "linear.bias"]
+            gout = red.slots([P[n].shape for n in lin]) if (red is not None and need) else None
+            loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, denom, need, gout=gout, defer_db=defer,
                                                Hs_bf16=layers[-1]["out"]["Hsb"] if layers[-1]["tc"] else None)
+            late = grads.pop("_late_db", None)
+            box = {}
+
+            def after_bptt():
+                if late is not None:
+                    grads["linear.bias"], box["db_done"] = late()
+
             dfeat = None
             if need and red is None:
-                dfeat = base_backward_from_dHs(mode, P, kind, L, cap, bs, layers, dHs, grads, want_dfeat, feat.shape)
+                dfeat = base_backward_from_dHs(mode, P, kind, L, cap, bs, layers, dHs, grads, want_dfeat, feat.shape,
+                                               after_bptt=after_bptt)
                 ops.join(vdone)
+                ops.join(box.get("db_done"))
             elif need:
                 # data parallel: three exchanges on the reducer's side stream, each issued the moment its
                 # gradients are final -- the vocabulary projection's overlaps BPTT, the embedding's (the
                 # large one) overlaps the layer-0 weight-gradient products, the small recurrent weights' is last
-                lin = ["linear.weight", "linear.bias"]
                 grads.update(zip(lin, red.reduce([grads[n] for n in lin], ready=vdone)))
                 emb = ["embeddings.weight"]
 
@@ -311,7 +346,8 @@ class BaseLossFn(torch.autograd.Function):
                     grads.update(zip(emb, red.reduce([grads[n] for n in emb])))
 
                 dfeat = base_backward_from_dHs(mode, P, kind, L, cap, bs, layers, dHs, grads, want_dfeat, feat.shape,
-                                               emb_out=emb_out, emb_done=emb_done)
+                                               emb_out=emb_out, emb_done=emb_done, after_bptt=after_bptt)
+                ops.join(box.get("db_done"))
                 rest = [n for n in names if n not in lin and n not in emb]
                 grads.update(zip(rest, red.reduce([grads[n] for n in rest])))
                 red.finish()

@@ -67,6 +67,28 @@ def fork(fn, uses=(), lane=0):
     return out, done
 
 
+class gemm_sm_limit:
+    """Context: the tensor-core GEMMs launched inside occupy at most `n` SMs (None / 0: all)."""
+
+    def __init__(self, n):
+        self.n = int(n or 0)
+
+    def __enter__(self):
+        if self.n:
+            _lib.load().st_gemm_set_sm_limit(self.n)
+
+    def __exit__(self, *a):
+        if self.n:
+            _lib.load().st_gemm_set_sm_limit(0)
+
+
+def bptt_side_sms(kind, H, B):
+    """SMs left over beside the tensor-core BPTT kernel for a batch of B rows (at least a quarter of the GPU)."""
+    lib = _lib.load()
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return max(sms - lib.st_rnn_seq_tc_bwd_ctas(int(kind), int(H), int(B)), sms // 4)
+
+
 def join(done):
     """The current stream waits for a fork()ed group."""
     if done is not None:

@@ -146,16 +146,29 @@ def test_vocab_ce_fused(M, V, H, variant, gemm_variant):
     assert float(P.float().sum(1).abs().max()) < 2e-2 * scale
 
 
+@pytest.fixture
+def bwd_ks():
+    """st_debug_set_bwd_ks: pin the BPTT kernel's K split (1 = none, 4 = clusters of 4 unit tiles); restored after."""
+    from showtell_b200 import _lib
+    lib = _lib.load()
+    yield lambda ks: lib.st_debug_set_bwd_ks(int(ks))
+    lib.st_debug_set_bwd_ks(0)
+
+
+@pytest.mark.parametrize("ks", [1, 4 | (64 << 8), 4 | (128 << 8)])     # low byte: K split; bits 8..: batch-tile height
 @pytest.mark.parametrize("kind", ["gru", "lstm"])
 @pytest.mark.parametrize("H,lengths,init", [
     (64, [5, 5, 4, 2], False),
     (128, sorted([9, 9, 8, 6, 5, 3] * 30, reverse=True), True),    # 180 rows: two batch tiles, ragged
+    (256, sorted([6, 5, 5, 3] * 20, reverse=True), True),          # GRU: 3 k-blocks per CTA of a K-split cluster
     (512, [20] * 200 + [13] * 56, False),                          # config-2 shape
 ])
-def test_rnn_seq_tensor_core_vs_cuda_core(kind, H, lengths, init):
+def test_rnn_seq_tensor_core_vs_cuda_core(kind, H, lengths, init, ks, bwd_ks):
     """The tcgen05 persistent recurrence (bf16 operands, fp32 state) against the fp32 CUDA-core
-    kernels on the same bf16-rounded W_hh: forward states, gate gradients, dh0/dc0, bias grads."""
+    kernels on the same bf16-rounded W_hh: forward states, gate gradients, dh0/dc0, bias grads.
+    ks: the BPTT kernel with every CTA streaming all of K (1) / K split over clusters of 4 unit tiles (4)."""
     from showtell_b200 import _lib, ops
+    bwd_ks(ks)
     k = _lib.ST_LSTM if kind == "lstm" else _lib.ST_GRU
     G = 4 if kind == "lstm" else 3
     bs = _lib.batch_sizes(lengths)
@@ -194,11 +207,13 @@ def test_rnn_seq_tensor_core_vs_cuda_core(kind, H, lengths, init):
     assert rel_err(tb["dbhh"], ops.colsum(rb["dGh"])) < 2e-2
 
 
+@pytest.mark.parametrize("ks", [1, 4 | (64 << 8), 4 | (128 << 8)])
 @pytest.mark.parametrize("kind", ["gru", "lstm"])
-def test_rnn_seq_tensor_core_stepwise_equals_whole(kind, monkeypatch):
+def test_rnn_seq_tensor_core_stepwise_equals_whole(kind, ks, bwd_ks, monkeypatch):
     """Partial step ranges (used by the attention loop) resume from the packed state rows and must
     reproduce the whole-sequence persistent run bit for bit."""
     from showtell_b200 import _lib, ops
+    bwd_ks(ks)
     k = _lib.ST_LSTM if kind == "lstm" else _lib.ST_GRU
     G = 4 if kind == "lstm" else 3
     H, lengths = 128, [7, 7, 6, 4, 4, 2]

@@ -35,12 +35,13 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 constexpr int GH = 2048, KB = 32, MAXS = 16;
 
 __global__ void __launch_bounds__(128, 1) stream_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* tile_major, __nv_bfloat16* rowmajor,
-                                                        int R, int S, int REP, int mode, int fresh, int* counters, long long* out, const __grid_constant__ CUtensorMap tm3, int KP) {
+                                                        int R, int S, int REP, int mode, int fresh, int* counters, long long* out, const __grid_constant__ CUtensorMap tm3, int KP, int ksplit) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full[MAXS], empty[MAXS];
   const uint32_t kbytes = (uint32_t)R * 128 * (mode == 2 ? KP : 1);
-  const int nops = mode == 2 ? KB / KP : KB;
+  const int nops = (mode == 2 ? KB / KP : KB) / ksplit;   // ksplit = 2: the CTAs of a pair stream one half of K each
+  const int op0 = (blockIdx.x % ksplit) * nops;
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -78,8 +79,8 @@ __global__ void __launch_bounds__(128, 1) stream_kernel(const __grid_constant__ 
       for (int kb = 0; kb < nops; ++kb) {
         mbar_wait(&empty[stage_p], ph_p ^ 1);
         mbar_expect_tx(&full[stage_p], kbytes);
-        if (mode == 2) tma_load_3d(smem + (size_t)stage_p * kbytes, &tm3, 0, y * R, kb * KP, &full[stage_p]);
-        else if (mode == 0) tma_load_2d(smem + (size_t)stage_p * kbytes, &tm, kb * 64, y * R, &full[stage_p]);
+        if (mode == 2) tma_load_3d(smem + (size_t)stage_p * kbytes, &tm3, 0, y * R, (op0 + kb) * KP, &full[stage_p]);
+        else if (mode == 0) tma_load_2d(smem + (size_t)stage_p * kbytes, &tm, (op0 + kb) * 64, y * R, &full[stage_p]);
         else bulk_load(smem + (size_t)stage_p * kbytes, tile_major + (((size_t)y * KB + kb) * R) * 64, kbytes, &full[stage_p]);
         if (++stage_p == S) { stage_p = 0; ph_p ^= 1; }
       }
@@ -117,14 +118,17 @@ int main() {
   cudaMalloc(&counters, 64 * sizeof(int));
   long long* out;
   cudaMalloc(&out, 256 * sizeof(long long));
-  struct Cfg { int X, Y, R, S, mode, fresh, KP; };
+  struct Cfg { int X, Y, R, S, mode, fresh, KP, ksplit; };
   std::vector<Cfg> cfgs;
-  cfgs.push_back({32, 4, 64, 9, 0, 1, 1});
-  cfgs.push_back({32, 4, 128, 9, 0, 1, 1});      // bigger 2-D boxes: does the time follow the bytes?
-  cfgs.push_back({32, 2, 256, 6, 0, 1, 1});
-  for (int kp : {1, 2, 4, 8}) cfgs.push_back({32, 4, 64, kp >= 4 ? 3 : 6, 2, 1, kp});   // 3-D boxes: kp k-blocks per op
-  for (int kp : {2, 4, 8}) cfgs.push_back({16, 8, 32, 4, 2, 1, kp});
-  cfgs.push_back({16, 4, 64, 3, 2, 1, 4});
+  cfgs.push_back({32, 4, 64, 9, 0, 1, 1, 1});
+  cfgs.push_back({32, 4, 128, 9, 0, 1, 1, 1});      // bigger 2-D boxes: does the time follow the bytes?
+  cfgs.push_back({32, 2, 256, 6, 0, 1, 1, 1});
+  for (int kp : {1, 2, 4, 8}) cfgs.push_back({32, 4, 64, kp >= 4 ? 3 : 6, 2, 1, kp, 1});   // 3-D boxes: kp k-blocks per op
+  for (int kp : {2, 4, 8}) cfgs.push_back({16, 8, 32, 4, 2, 1, kp, 1});
+  cfgs.push_back({16, 4, 64, 3, 2, 1, 4, 1});
+  for (int kp : {2, 4}) cfgs.push_back({32, 4, 64, 4, 2, 1, kp, 2});   // K split over CTA pairs: half the bytes per SM
+  cfgs.push_back({32, 4, 64, 4, 2, 0, 4, 1});   // not rewritten between repetitions
+  cfgs.push_back({32, 4, 64, 4, 2, 0, 4, 2});
   const int REP = 20;
   for (const Cfg& c : cfgs) {
     CUtensorMap tm;
@@ -150,7 +154,7 @@ int main() {
     for (int it = 0; it < 2; ++it) {   // second run is the measurement
       cudaMemset(counters, 0, 64 * sizeof(int));
       void* args[] = {(void*)&tm, (void*)&tilemajor, (void*)&rowmajor, (void*)&c.R, (void*)&c.S, (void*)&REP, (void*)&c.mode, (void*)&c.fresh,
-                      (void*)&counters, (void*)&out, (void*)&tm3, (void*)&c.KP};
+                      (void*)&counters, (void*)&out, (void*)&tm3, (void*)&c.KP, (void*)&c.ksplit};
       cudaError_t e = cudaLaunchCooperativeKernel((const void*)stream_kernel, dim3(c.X, c.Y), dim3(128), args, smem, 0);
       if (e != cudaSuccess) { printf("launch failed: %s\n", cudaGetErrorString(e)); return 1; }
       e = cudaDeviceSynchronize();
@@ -160,9 +164,9 @@ int main() {
     cudaMemcpy(h.data(), out, sizeof(long long) * c.X * c.Y, cudaMemcpyDeviceToHost);
     long long mx = 0, sum = 0;
     for (long long v : h) { mx = v > mx ? v : mx; sum += v; }
-    const double bytes = (double)KB * c.R * 128;   // per CTA per repetition
+    const double bytes = (double)KB * c.R * 128 / c.ksplit;   // per CTA per repetition
     const double us_max = mx / 1e3 / REP, us_mean = sum / 1e3 / REP / h.size();
-    printf("grid (%2d,%2d) R=%3d S=%2d KP=%d mode=%s fresh=%d: per step %.2f us (max CTA) %.2f us (mean); per-SM %.1f GB/s, aggregate %.2f TB/s\n", c.X, c.Y,
+    printf("grid (%2d,%2d) ksplit=%d R=%3d S=%2d KP=%d mode=%s fresh=%d: per step %.2f us (max CTA) %.2f us (mean); per-SM %.1f GB/s, aggregate %.2f TB/s\n", c.X, c.Y, c.ksplit,
            c.R, c.S, c.KP, c.mode == 2 ? "3-D box" : (c.mode ? "bulk-contiguous" : "tensor-map-box "), c.fresh, us_max, us_mean, bytes / us_mean / 1e3,
            bytes * h.size() / us_max / 1e6);
   }

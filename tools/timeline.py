@@ -4,6 +4,7 @@ import torch
 from showtell_b200 import _lib, ops
 lib = _lib.load()
 lib.st_debug_set_timeline.argtypes = [ctypes.c_void_p]
+lib.st_debug_set_bwd_ks(int(os.environ.get("ST_BWD_KS", "0")))
 dev = "cuda:0"
 H, B, T = 512, 256, 20
 k, G = _lib.ST_LSTM, 4
