@@ -239,12 +239,17 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
             dq = ops.sgemm(datt2_all[o0:o1], Wd)
             ops.add_rows(bouts[L - 1]["dstate"][0], dq, bt)
 
-    if tc:                          # bias gradients = column sums of the bf16 gate gradients
-        for l in range(L):
-            bouts[l]["dbih"] = ops.colsum(bouts[l]["dGb"])
-            bouts[l]["dbhh"] = ops.colsum(bouts[l]["dGhb"]) if kind == _lib.ST_GRU else bouts[l]["dbih"]
-    # ---- hoisted weight gradients.  The encoder-projection chain (one pass over att1, then the largest GEMM
-    # of the step) is independent of the recurrent ones: side stream.
+    # ---- everything below reads what the reverse loop left behind and is mutually independent: it runs as concurrent
+    # chains on side streams (ops.fork lanes) -- each far too small to fill the GPU, and issued serially they were a
+    # quarter of the step -- while the main stream carries the chain that ends in the embedding gradient.
+    pending = []
+
+    def side(fn, uses, lane):
+        out, ev = ops.fork(fn, uses=uses, lane=lane)
+        pending.append(ev)
+        return out, ev
+
+    # the encoder-projection chain: one pass over att1, then the largest GEMM of the step
     def enc_chain():
         datt1, _, dwf = ops.attn_hoist_bwd(bs, Pn, att1, att2_all, de_all, wf, want_t=False)
         if mode == "bf16":
@@ -253,48 +258,103 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
             dWe = ops.sgemm(datt1, sv["F"], transA=True, tag="att1_dw")
         return dWe, ops.colsum(datt1), dwf
 
-    (dWe, dbe, dwf), enc_done = ops.fork(enc_chain, uses=(att1, att2_all, de_all, wf, sv["F"]))
-    emb_done = None
+    (dWe, dbe, dwf), _ = side(enc_chain, (att1, att2_all, de_all, wf, sv["F"]), 0)
     if embed_q:
-        # dW_embed = Q^T F: a third independent chain (one pass over alphas / dctx, then a 2*E*B*P*C FLOP GEMM)
-        grads["embed.weight"], emb_done = ops.fork(
+        # dW_embed = Q^T F: one pass over alphas / dctx, then a 2*E*B*P*C FLOP GEMM
+        grads["embed.weight"], _ = side(
             lambda: ops.gemm_bf16(ops.attn_embed_q(bs, Pn, alphas, dctx_all), sv["F"], a_t=True, b_t=True, tag="embed_dw"),
-            uses=(alphas, dctx_all, sv["F"]), lane=1)
-    h0_b16 = ops.cast_bf16(h0, True, False)[0] if tc else None
-    for l in range(L):
-        Hprev = ops.shift_states(outs[l]["Hs"], bs, h0) if not tc else None
-        inp = X0 if l == 0 else outs[l - 1]["Hs"]
-        if tc:
-            Hprev_b = Hprev = ops.shift_states(outs[l]["Hsb"], bs, h0_b16)
-            inp_b = ops.cast_bf16(X0, True, False)[0] if l == 0 else outs[l - 1]["Hsb"]
-            grads[f"unit.weight_hh_l{l}"] = ops.gemm_bf16(bouts[l]["dGhb"], Hprev_b, a_t=True, b_t=True, tag="hh_dw")
-            grads[f"unit.weight_ih_l{l}"] = ops.gemm_bf16(bouts[l]["dGb"], inp_b, a_t=True, b_t=True, tag="ih_dw")
-            grads[f"unit.bias_hh_l{l}"], grads[f"unit.bias_ih_l{l}"] = bouts[l]["dbhh"], bouts[l]["dbih"]
+            (alphas, dctx_all, sv["F"]), 1)
+    # initial state: every layer started from the same h0 / c0 (rnn_attn.py:62)
+    dh0 = bouts[0]["dstate"][0]
+    dc0 = bouts[0]["dstate"][1]
+    for l in range(1, L):
+        dh0 = dh0 + bouts[l]["dstate"][0]
+        dc0 = dc0 + bouts[l]["dstate"][1]
+
+    # the bias gradients and the other small column sums: one chain of their own
+    def small_sums():
+        out = {}
+        if tc:                      # bias gradients = column sums of the bf16 gate gradients
+            for l in range(L):
+                out[f"unit.bias_ih_l{l}"] = ops.colsum(bouts[l]["dGb"])
+                out[f"unit.bias_hh_l{l}"] = ops.colsum(bouts[l]["dGhb"]) if kind == _lib.ST_GRU else out[f"unit.bias_ih_l{l}"]
         else:
-            grads[f"unit.weight_hh_l{l}"] = weight_grad(mode, bouts[l]["dGh"], Hprev, "hh_dw")
-            grads[f"unit.bias_hh_l{l}"] = ops.colsum(bouts[l]["dGh"])
-            grads[f"unit.weight_ih_l{l}"] = weight_grad(mode, bouts[l]["dG"], inp, "ih_dw")
-            grads[f"unit.bias_ih_l{l}"] = ops.colsum(bouts[l]["dG"])
-        if l == L - 1:
-            Hprev_top = Hprev
+            for l in range(L):
+                out[f"unit.bias_hh_l{l}"] = ops.colsum(bouts[l]["dGh"])
+                out[f"unit.bias_ih_l{l}"] = ops.colsum(bouts[l]["dG"])
+        out["attn.decoder_att.bias"] = ops.colsum(datt2_all)
+        # sum of every de (== 0 up to rounding: softmax is shift invariant): two-stage column sum
+        nde = de_all.numel()
+        wde = 256 if nde % 256 == 0 else (Pn if nde % Pn == 0 else 1)
+        out["attn.full_att.bias"] = ops.colsum(ops.colsum(de_all.reshape(-1, wde)).reshape(-1, 1))
+        out["embed.bias"] = ops.colsum(dctx_all)
+        out["init_h.bias"] = ops.colsum(dh0)
+        if kind == _lib.ST_LSTM:
+            out["init_c.bias"] = ops.colsum(dc0)
+        return out
+
+    sums, sums_done = side(small_sums, (datt2_all, de_all, dctx_all, dh0), 4)
+
+    if "mean_b" in sv:
+        dinit = lambda d: ops.gemm_bf16(ops.cast_bf16(d, True, False)[0], sv["mean_b"], a_t=True, b_t=True, tag="init_dw")
+    else:
+        dinit = lambda d: ops.sgemm(d, sv["mean_f"], transA=True)
+    (grads["init_h.weight"], dic), _ = side(lambda: (dinit(dh0), dinit(dc0) if kind == _lib.ST_LSTM else None),
+                                            (dh0, sv["mean_f"]), 5)
+    if kind == _lib.ST_LSTM:
+        grads["init_c.weight"] = dic
+
+    # recurrent weight gradients: W_hh (and the decoder_att weight, which reads the same shifted states) on one lane,
+    # W_ih on another
+    h0_b16 = ops.cast_bf16(h0, True, False)[0] if tc else None
+
+    def hh_chain():
+        out, top = {}, None
+        for l in range(L):
+            if tc:
+                Hprev = ops.shift_states(outs[l]["Hsb"], bs, h0_b16)
+                out[f"unit.weight_hh_l{l}"] = ops.gemm_bf16(bouts[l]["dGhb"], Hprev, a_t=True, b_t=True, tag="hh_dw")
+            else:
+                Hprev = ops.shift_states(outs[l]["Hs"], bs, h0)
+                out[f"unit.weight_hh_l{l}"] = weight_grad(mode, bouts[l]["dGh"], Hprev, "hh_dw")
+            if l == L - 1:
+                top = Hprev
+        out["attn.decoder_att.weight"] = weight_grad(mode, datt2_b if tc else datt2_all, top, "att2_dw")
+        return out
+
+    def ih_chain():
+        out = {}
+        for l in range(L):
+            if tc:
+                inp_b = ops.cast_bf16(X0, True, False)[0] if l == 0 else outs[l - 1]["Hsb"]
+                out[f"unit.weight_ih_l{l}"] = ops.gemm_bf16(bouts[l]["dGb"], inp_b, a_t=True, b_t=True, tag="ih_dw")
+            else:
+                inp = X0 if l == 0 else outs[l - 1]["Hs"]
+                out[f"unit.weight_ih_l{l}"] = weight_grad(mode, bouts[l]["dG"], inp, "ih_dw")
+        return out
+
+    whh, hh_done = side(hh_chain, (X0, datt2_all), 2)
+    wih, ih_done = side(ih_chain, (X0,), 3)
+    # main stream: the embedding gradient (the buffer is cleared on a lane of its own)
+    dEmb = emb_out() if emb_out is not None else torch.empty_like(P["embeddings.weight"])
+    _, zeroed = ops.fork(dEmb.zero_, lane=6)
     if tc:
         dXemb = ops.gemm_bf16(bouts[0]["dGb"], W["ihe"][0], b_t=True, tag="ih_dx")
     else:
         dXemb = ops.sgemm(bouts[0]["dG"], Wih0[:, :E], tag="ih_dx")
-    dEmb = emb_out().zero_() if emb_out is not None else torch.zeros_like(P["embeddings.weight"])
+    ops.join(zeroed)
     ops.pack_inputs_bwd(dXemb, dEmb, None, caption, bs, False)
     grads["embeddings.weight"] = dEmb
+    for ev in (hh_done, ih_done, sums_done):
+        ops.join(ev)
+    grads.update(whh)
+    grads.update(wih)
+    grads.update(sums)
     if recurrent_done is not None:
         recurrent_done(grads)
     # attention parameters
     grads["attn.encoder_att.weight"], grads["attn.encoder_att.bias"] = dWe, dbe
-    grads["attn.decoder_att.weight"] = weight_grad(mode, datt2_b if tc else datt2_all, Hprev_top, "att2_dw")
-    grads["attn.decoder_att.bias"] = ops.colsum(datt2_all)
     grads["attn.full_att.weight"] = dwf.reshape(1, -1)
-    # sum of every de (== 0 up to rounding: softmax is shift invariant): two-stage column sum
-    nde = de_all.numel()
-    wde = 256 if nde % 256 == 0 else (Pn if nde % Pn == 0 else 1)
-    grads["attn.full_att.bias"] = ops.colsum(ops.colsum(de_all.reshape(-1, wde)).reshape(-1, 1))
     # embed: ctx_e = W_embed ctx + b with ctx = sum_p alpha_p F_p rebuilt for all (t,b) in one pass
     if embed_q:
         pass                                     # forked above
@@ -305,24 +365,8 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
     else:
         ctx, _ = ops.attn_ctx_all(bs, Pn, sv["F"], alphas)
         grads["embed.weight"] = ops.sgemm(dctx_all, ctx, transA=True, tag="embed_dw")
-    grads["embed.bias"] = ops.colsum(dctx_all)
-    # initial state: every layer started from the same h0 / c0 (rnn_attn.py:62)
-    dh0 = bouts[0]["dstate"][0]
-    dc0 = bouts[0]["dstate"][1]
-    for l in range(1, L):
-        dh0 = dh0 + bouts[l]["dstate"][0]
-        dc0 = dc0 + bouts[l]["dstate"][1]
-    if "mean_b" in sv:
-        dinit = lambda d: ops.gemm_bf16(ops.cast_bf16(d, True, False)[0], sv["mean_b"], a_t=True, b_t=True, tag="init_dw")
-    else:
-        dinit = lambda d: ops.sgemm(d, sv["mean_f"], transA=True)
-    grads["init_h.weight"] = dinit(dh0)
-    grads["init_h.bias"] = ops.colsum(dh0)
-    if kind == _lib.ST_LSTM:
-        grads["init_c.weight"] = dinit(dc0)
-        grads["init_c.bias"] = ops.colsum(dc0)
-    ops.join(enc_done)
-    ops.join(emb_done)
+    for ev in pending:
+        ops.join(ev)
     return grads
 
 

@@ -149,6 +149,57 @@ relayout_kernel(const TI* __restrict__ f, int C, int P, T* __restrict__ F, T* __
   }
 }
 
+// The common case of relayout_kernel -- P % 4 == 0, C % 64 == 0, bf16 F, no transposed copy -- with an order of
+// magnitude fewer instructions (the general kernel issued 51 per element and was issue-bound at 2.4 TB/s):
+//   load:  warp per CHANNEL PAIR; a lane reads 4 consecutive locations of both channels (128-bit / 64-bit loads, rows
+//          are 16 / 8-byte aligned) and stores them as 4 (even, odd) pairs, 64-bit, conflict-free; the channel means
+//          come out of the same registers (warp sum);
+//   store: warp per LOCATION; a lane reads its channel pair (64-bit, row stride odd in pairs: conflict-free), converts
+//          and stores 4 bytes -- 128 contiguous bytes per warp instruction.
+template <typename TI>
+__global__ void __launch_bounds__(NT)
+relayout_fast_kernel(const TI* __restrict__ f, int C, int P, __nv_bfloat16* __restrict__ F, float* __restrict__ mean_f) {
+  extern __shared__ float2 tile2[];               // [32 channel pairs][PS2], PS2 = P | 1
+  const int PS2 = P | 1;
+  const int b = blockIdx.y, c0 = blockIdx.x * RL_CH;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const TI* src = f + ((size_t)b * C + c0) * P;
+  const int nq = P >> 2;                          // 4-location groups per channel row
+  const float inv_p = 1.f / (float)P;
+  for (int cp = warp; cp < RL_CH / 2; cp += NT / 32) {
+    const TI* r0 = src + (size_t)(2 * cp) * P;
+    const TI* r1 = r0 + P;
+    float s0 = 0.f, s1 = 0.f;
+    for (int q = lane; q < nq; q += 32) {
+      float a[4], c[4];
+      if (sizeof(TI) == 4) {
+        const float4 va = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(r0) + 4 * q);
+        const float4 vc = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(r1) + 4 * q);
+        a[0] = va.x; a[1] = va.y; a[2] = va.z; a[3] = va.w; c[0] = vc.x; c[1] = vc.y; c[2] = vc.z; c[3] = vc.w;
+      } else {
+        const uint2 ua = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(r0) + 4 * q);
+        const uint2 uc = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(r1) + 4 * q);
+        a[0] = __uint_as_float(ua.x << 16); a[1] = __uint_as_float(ua.x & 0xffff0000u);
+        a[2] = __uint_as_float(ua.y << 16); a[3] = __uint_as_float(ua.y & 0xffff0000u);
+        c[0] = __uint_as_float(uc.x << 16); c[1] = __uint_as_float(uc.x & 0xffff0000u);
+        c[2] = __uint_as_float(uc.y << 16); c[3] = __uint_as_float(uc.y & 0xffff0000u);
+      }
+      float2* d = tile2 + (size_t)cp * PS2 + 4 * q;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { d[i] = make_float2(a[i], c[i]); s0 += a[i]; s1 += c[i]; }
+    }
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    if (lane == 0) *reinterpret_cast<float2*>(mean_f + (size_t)b * C + c0 + 2 * cp) = make_float2(s0 * inv_p, s1 * inv_p);
+  }
+  __syncthreads();
+  __nv_bfloat16* dst = F + ((size_t)b * P) * C + c0 + 2 * lane;
+  for (int p = warp; p < P; p += NT / 32) {
+    const float2 v = tile2[(size_t)lane * PS2 + p];
+    *reinterpret_cast<__nv_bfloat162*>(dst + (size_t)p * C) = __floats2bfloat162_rn(v.x, v.y);
+  }
+}
+
 template <typename T, int ACT>
 __global__ void __launch_bounds__(NT)
 attn_step_fwd_kernel(int P, int A, int E, const T* __restrict__ att1, const T* __restrict__ Fe,
@@ -366,20 +417,26 @@ __device__ __forceinline__ void ld4(const __nv_bfloat16* p, float (&v)[4]) {
 // Q^T . F over the B*P locations (both operands in place, MN-major) replaces the pass that re-reads the whole grid
 // F (B*P*C) once per live step chunk (attn_ctx_all: 148 us at config 3) plus a small GEMM.
 // CTA = one batch row x QP locations; thread = 2 adjacent embedding columns (blockDim = ceil(E/2) rounded to warps).
-constexpr int QP = 28, QT = 16;
+constexpr int QP = 28, QT = 20;
 __global__ void __launch_bounds__(NT)
 attn_embed_q_kernel(const __grid_constant__ StepTable tab, int P, int E, int Tcap, const float* __restrict__ alphas,
                     const float* __restrict__ dctx, int ldd, __nv_bfloat16* __restrict__ Q) {
-  __shared__ float s_al[QT][QP];
+  __shared__ __align__(16) float s_al[QT][QP];                 // rows of 112 B: four locations per 128-bit broadcast read
   const int b = blockIdx.y, p0 = blockIdx.x * QP, np = min(QP, P - p0);
   int len = 0;
   while (len < tab.nsteps && tab.bs[len] > b) ++len;
   for (int eb = 0; eb < E; eb += 2 * NT) {                    // one pass when E <= 512; uniform trip count (barriers inside)
     const int e0 = eb + 2 * threadIdx.x;
     const bool on = e0 < E, two = e0 + 1 < E;
+    const bool pairld = two && (ldd & 1) == 0 && (reinterpret_cast<uintptr_t>(dctx) & 7) == 0;
     float acc0[QP], acc1[QP];
 #pragma unroll
     for (int i = 0; i < QP; ++i) acc0[i] = acc1[i] = 0.f;
+    auto load_d = [&](int t, float& d0, float& d1) {
+      const float* d = dctx + ((size_t)tab.off[t] + b) * ldd + e0;
+      if (pairld) { const float2 v = *reinterpret_cast<const float2*>(d); d0 = v.x; d1 = v.y; }
+      else { d0 = on ? d[0] : 0.f; d1 = two ? d[1] : 0.f; }
+    };
     for (int t0 = 0; t0 < len; t0 += QT) {
       const int nt = min(QT, len - t0);
       __syncthreads();
@@ -387,15 +444,19 @@ attn_embed_q_kernel(const __grid_constant__ StepTable tab, int P, int E, int Tca
         const int ti = i / QP, pi = i % QP;
         s_al[ti][pi] = (ti < nt && pi < np) ? alphas[((size_t)b * Tcap + t0 + ti) * P + p0 + pi] : 0.f;
       }
+      float n0 = 0.f, n1 = 0.f;
+      load_d(t0, n0, n1);
       __syncthreads();
       for (int ti = 0; ti < nt; ++ti) {
-        const float* d = dctx + ((size_t)tab.off[t0 + ti] + b) * ldd + e0;
-        const float d0 = on ? d[0] : 0.f, d1 = two ? d[1] : 0.f;
+        const float d0 = n0, d1 = n1;
+        if (ti + 1 < nt) load_d(t0 + ti + 1, n0, n1);          // next step's gradient row while this one is used
 #pragma unroll
-        for (int pi = 0; pi < QP; ++pi) {
-          const float a = s_al[ti][pi];
-          acc0[pi] = fmaf(a, d0, acc0[pi]);
-          acc1[pi] = fmaf(a, d1, acc1[pi]);
+        for (int pi = 0; pi < QP; pi += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(&s_al[ti][pi]);
+          acc0[pi] = fmaf(a.x, d0, acc0[pi]);         acc1[pi] = fmaf(a.x, d1, acc1[pi]);
+          acc0[pi + 1] = fmaf(a.y, d0, acc0[pi + 1]); acc1[pi + 1] = fmaf(a.y, d1, acc1[pi + 1]);
+          acc0[pi + 2] = fmaf(a.z, d0, acc0[pi + 2]); acc1[pi + 2] = fmaf(a.z, d1, acc1[pi + 2]);
+          acc0[pi + 3] = fmaf(a.w, d0, acc0[pi + 3]); acc1[pi + 3] = fmaf(a.w, d1, acc1[pi + 3]);
         }
       }
     }
@@ -410,6 +471,113 @@ attn_embed_q_kernel(const __grid_constant__ StepTable tab, int P, int E, int Tca
         }
       }
     }
+  }
+}
+
+// LeakyReLU(0.2) form of attn_hoist_bwd_kernel (rnn_attn.py:26), without the transposed copy.  act'(s) is 1 or 0.2, so
+//   g[t,p] = de[t,p] act'(s) = 0.2 de[t,p] + 0.8 de[t,p] [s > 0],    s = att1[b,p,a] + att2[t,b,a]  (> 0  <=>  att1 > -att2)
+// and a tuple costs one compare and two predicated adds -- into a per-location and a per-step accumulator:
+//   datt1[b,p,a] = w_f[a] (0.2 D_p + 0.8 A_p),        A_p = sum_t de[t,p][s > 0],   D_p = sum_t de[t,p]
+//   dw_f[a]     += sum_p att1[b,p,a] (0.2 D_p + 0.8 A_p) + sum_t att2[t,b,a] (0.2 D_t + 0.8 A_t)      (act(s) = s act'(s))
+// with D_p / D_t (independent of a) summed once per CTA.  63 M -> ~25 M warp instructions at config 3.
+template <typename T, typename TO>
+__global__ void __launch_bounds__(NT, 3)
+attn_hoist_bwd_lrelu_kernel(const __grid_constant__ StepTable tab, int P, int A, const T* __restrict__ att1,
+                            const float* __restrict__ att2, const float* __restrict__ de, const float* __restrict__ wf,
+                            TO* __restrict__ datt1, float* __restrict__ dwf) {
+  __shared__ __align__(16) float s_de[HB_P][HB_T];       // [p][t] of the chunk, zero padded
+  __shared__ float s_dp[HB_P], s_dpt[HB_P], s_dt[HB_T];  // chunk sums over t, their total over the chunks, chunk sums over p
+  __shared__ int s_row[HB_T];                            // packed row of (t0 + ti, b)
+  const int b = blockIdx.y, p0 = blockIdx.x * HB_P, np = min(HB_P, P - p0), tid = threadIdx.x;
+  const int a = blockIdx.z * NT + tid;                   // grid.z = blocks of NT attention units
+  const bool a_ok = a < A;
+  int len = 0;
+  while (len < tab.nsteps && tab.bs[len] > b) ++len;     // steps in which row b is live
+  constexpr int GP = 7;                                  // locations per group: their att1 values are loaded together,
+  static_assert(HB_P % GP == 0, "location groups");      // one group ahead of the arithmetic
+  const T* a1 = att1 + ((size_t)b * P + p0) * A + a;
+  float ap[HB_P], dw = 0.f;
+#pragma unroll
+  for (int i = 0; i < HB_P; ++i) ap[i] = 0.f;
+  if (tid < HB_P) s_dpt[tid] = 0.f;
+  for (int t0 = 0; t0 < len; t0 += HB_T) {
+    const int nt = min(HB_T, len - t0);
+    __syncthreads();
+    if (tid < HB_T) s_row[tid] = tid < nt ? tab.off[t0 + tid] + b : -1;
+    __syncthreads();
+    for (int i = tid; i < HB_P * HB_T; i += NT) {
+      const int pi = i / HB_T, ti = i - pi * HB_T, r = s_row[ti];
+      s_de[pi][ti] = (pi < np && r >= 0) ? de[(size_t)r * P + p0 + pi] : 0.f;
+    }
+    float na2[HB_T];                                      // -att2[t,b,a]
+#pragma unroll
+    for (int ti = 0; ti < HB_T; ++ti) {
+      const int r = s_row[ti];
+      na2[ti] = (a_ok && r >= 0) ? -att2[(size_t)r * A + a] : 0.f;
+    }
+    float s1n[GP];
+#pragma unroll
+    for (int j = 0; j < GP; ++j) s1n[j] = (a_ok && j < np) ? ldf(a1 + (size_t)j * A) : 0.f;
+    __syncthreads();
+    if (tid < HB_P) {
+      float v = 0.f;
+#pragma unroll
+      for (int ti = 0; ti < HB_T; ++ti) v += s_de[tid][ti];
+      s_dp[tid] = v;
+      s_dpt[tid] += v;
+    } else if (tid >= 32 && tid < 32 + HB_T) {
+      float v = 0.f;
+      for (int pi = 0; pi < HB_P; ++pi) v += s_de[pi][tid - 32];
+      s_dt[tid - 32] = v;
+    }
+    __syncthreads();
+    // sum_{t,p} [s > 0] de a2[t]  (the step part of dw_f) as four independent predicated-FMA chains
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+    for (int g = 0; g < HB_P / GP; ++g) {
+      float s1c[GP];
+#pragma unroll
+      for (int j = 0; j < GP; ++j) s1c[j] = s1n[j];
+      if (g + 1 < HB_P / GP) {
+#pragma unroll
+        for (int j = 0; j < GP; ++j) {
+          const int pn = (g + 1) * GP + j;
+          s1n[j] = (a_ok && pn < np) ? ldf(a1 + (size_t)pn * A) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < GP; ++j) {
+        const int pi = g * GP + j;
+        if (pi < np) {
+          const float s1 = s1c[j];
+          float apc0 = 0.f, apc1 = 0.f;
+#pragma unroll
+          for (int ti = 0; ti < HB_T; ti += 4) {
+            const float4 d4 = *reinterpret_cast<const float4*>(&s_de[pi][ti]);
+            if (s1 > na2[ti]) { apc0 += d4.x; q0 = fmaf(d4.x, na2[ti], q0); }
+            if (s1 > na2[ti + 1]) { apc1 += d4.y; q1 = fmaf(d4.y, na2[ti + 1], q1); }
+            if (s1 > na2[ti + 2]) { apc0 += d4.z; q2 = fmaf(d4.z, na2[ti + 2], q2); }
+            if (s1 > na2[ti + 3]) { apc1 += d4.w; q3 = fmaf(d4.w, na2[ti + 3], q3); }
+          }
+          const float apc = apc0 + apc1;
+          ap[pi] += apc;
+          dw = fmaf(s1, fmaf(0.8f, apc, 0.2f * s_dp[pi]), dw);
+        }
+      }
+    }
+    if (a_ok) {
+      dw = fmaf(-0.8f, (q0 + q1) + (q2 + q3), dw);        // q sums de * (-att2)
+#pragma unroll
+      for (int ti = 0; ti < HB_T; ++ti) dw = fmaf(-0.2f * na2[ti], s_dt[ti], dw);
+    }
+  }
+  __syncthreads();
+  if (a_ok) {
+    const float w = wf[a];
+#pragma unroll
+    for (int pi = 0; pi < HB_P; ++pi)
+      if (pi < np) stf(datt1 + ((size_t)b * P + p0 + pi) * A + a, w * fmaf(0.8f, ap[pi], 0.2f * s_dpt[pi]));
+    atomicAdd(dwf + a, dw);
   }
 }
 
@@ -511,6 +679,19 @@ static int relayout_any(const void* f, int f_bf16, int B, int C, int P, void* F,
   const size_t smem = sizeof(float) * RL_CH * (size_t)(P | 1);
   ST_REQUIRE(smem <= 200 * 1024, ST_ERR_BAD_SHAPE, "st_attn_relayout: P=%d too large", P);
   cudaStream_t s = as_stream(stream);
+  if (out_bf16 && !FT && (P & 3) == 0 && C % RL_CH == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(F) & 3) == 0 && (reinterpret_cast<uintptr_t>(mean_f) & 7) == 0) {
+    const size_t sm2 = sizeof(float2) * (RL_CH / 2) * (size_t)(P | 1);
+    if (f_bf16) {
+      ST_CUDA_TRY(cudaFuncSetAttribute(relayout_fast_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+      relayout_fast_kernel<__nv_bfloat16><<<grid, NT, sm2, s>>>((const __nv_bfloat16*)f, C, P, (__nv_bfloat16*)F, mean_f);
+    } else {
+      ST_CUDA_TRY(cudaFuncSetAttribute(relayout_fast_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+      relayout_fast_kernel<float><<<grid, NT, sm2, s>>>((const float*)f, C, P, (__nv_bfloat16*)F, mean_f);
+    }
+    ST_LAUNCH_TRY("relayout_fast_kernel");
+    return ST_OK;
+  }
 #define ST_RELAYOUT(T, TI)                                                                               \
   do {                                                                                                   \
     auto kern = relayout_kernel<T, TI>;                                                                  \
@@ -618,6 +799,15 @@ int st_attn_hoist_bwd(int nsteps, const int* batch_sizes_host, int P, int A, con
   ST_CUDA_TRY(cudaMemsetAsync(dwf, 0, sizeof(float) * A, s));
   const size_t smem = sizeof(float) * HB_P * HB_T + (datt1T ? (size_t)A * (HB_P + 1) * (in_bf16 ? 2 : 4) : 0);
   ST_REQUIRE(smem <= 200 * 1024, ST_ERR_BAD_SHAPE, "st_attn_hoist_bwd: A=%d too large", A);
+  if (act == 0 && !datt1T) {     // LeakyReLU without the transposed copy: the compare + predicated-add form
+    const dim3 g3(grid.x, grid.y, (A + NT - 1) / NT);
+    if (in_bf16) attn_hoist_bwd_lrelu_kernel<__nv_bfloat16, __nv_bfloat16><<<g3, NT, 0, s>>>(
+        tab, P, A, (const __nv_bfloat16*)att1, att2, de, wf, (__nv_bfloat16*)datt1, dwf);
+    else attn_hoist_bwd_lrelu_kernel<float, float><<<g3, NT, 0, s>>>(tab, P, A, (const float*)att1, att2, de, wf,
+                                                                    (float*)datt1, dwf);
+    ST_LAUNCH_TRY("attn_hoist_bwd_lrelu_kernel");
+    return ST_OK;
+  }
 #define ST_LAUNCH_H(T, ACT)                                                                                 \
   do {                                                                                                      \
     auto kern = attn_hoist_bwd_kernel<T, T, ACT>;                                                           \

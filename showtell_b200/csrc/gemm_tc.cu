@@ -65,6 +65,7 @@ enum { EPI_STORE = 0, EPI_CE_FWD = 1, EPI_CE_BWD = 2, EPI_TOPK = 3 };
 constexpr int TOPK_SLOTS = 8;   // per-row candidates kept per epilogue warp (K <= 8 on the fused path)
 int g_variant = 0;   // st_debug_gemm_variant: 0 = choose, 128 / 256 = single-CTA tile width, 2 = CTA pairs
 int g_streamk = 1;   // st_debug_gemm_variant(v | 0x1000) turns stream-K off
+int g_mn3d = 1;      // st_debug_gemm_variant(v | 0x2000): MN-major operands through 2-D boxes (A/B timing)
 int g_sm_limit = 0;  // st_gemm_set_sm_limit: cap on the persistent grids (0 = all SMs)
 inline int gemm_sms(int* sms) {
   ST_TRY(st_device_info(sms, nullptr, nullptr, nullptr));
@@ -92,6 +93,7 @@ struct TcParams {
   int tk_k;               // candidates written per (row, part): the caller's K (<= TOPK_SLOTS).  With pmax / psum set the
                           // epilogue also keeps the soft-max partials (running max, sum of exp) of its columns.
   int streamk;            // pair kernel: 1 = stream-K schedule (C zeroed by the launcher)
+  int a3d, b3d;           // MN-major operand given as the 3-D tensor map (make_tmap_mn3d): one TMA operation per k-block
 };
 
 __device__ __forceinline__ float ex2_fast(float x) {   // 2^x, MUFU only (inputs here are <= ~0: no range fix-up needed)
@@ -479,13 +481,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (elect_one()) {
           mbar_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* a = smem + (size_t)stage * STAGE_BYTES;
-          if (AMN) {
+          if (AMN && p.a3d) {
+            tma_load_3d(a, &tmA, 0, k * BK, m0 / 64, &full[stage]);
+          } else if (AMN) {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) tma_load_2d(a + j * 8192, &tmA, m0 + 64 * j, k * BK, &full[stage]);
           } else {
             tma_load_2d(a, &tmA, k * BK, m0, &full[stage]);
           }
-          if (BMN) {
+          if (BMN && p.b3d) {
+            tma_load_3d(a + A_BYTES, &tmB, 0, k * BK, n0 / 64, &full[stage]);
+          } else if (BMN) {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j) tma_load_2d(a + A_BYTES + j * 8192, &tmB, n0 + 64 * j, k * BK, &full[stage]);
           } else {
@@ -1038,9 +1044,14 @@ inline bool want_streamk(const TcParams& p, int ntiles, int kb, int workers) {
 template <int EPI, int BN, int AMN = 0, int BMN = 0>
 int launch_tc_bn(TcParams p, const void* A, int lda, const void* B, int ldb, cudaStream_t s, int sms) {
   CUtensorMap tmA, tmB;
-  if (AMN) ST_TRY(make_tmap(&tmA, A, p.K, p.M, lda, 64, "A (MN-major)"));
+  // MN-major operands whose (m|n) extent is a multiple of 64: one 3-D box per k-block instead of BM/64 (BN/64) 2-D boxes
+  p.a3d = (AMN && p.M % 64 == 0 && g_mn3d) ? 1 : 0;
+  p.b3d = (BMN && p.N % 64 == 0 && g_mn3d) ? 1 : 0;
+  if (AMN && p.a3d) ST_TRY(make_tmap_mn3d(&tmA, A, p.K, p.M, lda, BM / 64, "A (MN-major)"));
+  else if (AMN) ST_TRY(make_tmap(&tmA, A, p.K, p.M, lda, 64, "A (MN-major)"));
   else ST_TRY(make_tmap(&tmA, A, p.M, p.K, lda, BM, "A"));
-  if (BMN) ST_TRY(make_tmap(&tmB, B, p.K, p.N, ldb, 64, "B (MN-major)"));
+  if (BMN && p.b3d) ST_TRY(make_tmap_mn3d(&tmB, B, p.K, p.N, ldb, BN / 64, "B (MN-major)"));
+  else if (BMN) ST_TRY(make_tmap(&tmB, B, p.K, p.N, ldb, 64, "B (MN-major)"));
   else ST_TRY(make_tmap(&tmB, B, p.N, p.K, ldb, BN, "B"));
   auto kern = gemm_tc_kernel<EPI, BN, AMN, BMN>;
   ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<BN>::SMEM_BYTES));
@@ -1255,6 +1266,7 @@ int st_gemm_set_sm_limit(int n) {
 
 int st_debug_gemm_variant(int variant) {
   st::g_streamk = (variant & 0x1000) ? 0 : 1;
+  st::g_mn3d = (variant & 0x2000) ? 0 : 1;
   variant &= 0xfff;
   st::g_variant = (variant == 2 || variant == 128 || variant == 256) ? variant : 0;
   return ST_OK;

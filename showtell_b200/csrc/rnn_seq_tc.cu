@@ -317,13 +317,6 @@ rnn_seq_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
 // K-major layout the UMMA descriptors expect.  KP = 4 cut the stream from 6.2 to ~1.5 us per step at B = 256.
 // KP = 1 keeps the 2-D boxes (any G*H; the 3-D view needs G*H % 64 == 0).
 template <int KP, int BT> struct RingCfg { static constexpr int STAGES = (KP == 1) ? 9 : 131072 / (KP * BT * 128); };
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-
 struct TcBwdParams {
   long long* tl;
   int H, t_hi, t_lo, nsteps, t_zero;

@@ -11,6 +11,9 @@ namespace st {
 // box_rows box and 128-byte swizzle; out-of-bounds elements read as zero.  (tmap.cu)
 int make_tmap(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, const char* what);
 
+// MN-major operand (krows, mn) viewed as (mn / 64, krows, 64): box of nblk 64 x 64 blocks per operation (tmap.cu)
+int make_tmap_mn3d(CUtensorMap* map, const void* ptr, int krows, int mn, int ld, int nblk, const char* what);
+
 int make_tmap_f32(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows, const char* what);
 
 #ifdef __CUDACC__
@@ -44,6 +47,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 // One lane of a converged warp (elect.sync).  Issue loops run with the WHOLE warp so that loop counters,
