@@ -332,24 +332,21 @@ class BaseLossFn(torch.autograd.Function):
                 ops.join(vdone)
                 ops.join(box.get("db_done"))
             elif need:
-                # data parallel: three exchanges on the reducer's side stream, each issued the moment its
-                # gradients are final -- the vocabulary projection's overlaps BPTT, the embedding's (the
-                # large one) overlaps the layer-0 weight-gradient products, the small recurrent weights' is last
+                # data parallel: two exchanges on the reducer's side stream -- the vocabulary projection's overlaps BPTT ...
                 grads.update(zip(lin, red.reduce([grads[n] for n in lin], ready=vdone)))
-                emb = ["embeddings.weight"]
+                # ... and ONE exchange for everything the end of the backward pass produces (recurrent weights, biases,
+                # the embedding): their gradients become final within a few microseconds of each other, and every
+                # exchange pays a launch and two cross-GPU barriers
+                last = [n for n in names if n not in lin and n != "embeddings.weight"] + ["embeddings.weight"]
 
                 def emb_out():
-                    v = red.slots([P["embeddings.weight"].shape])
-                    return v[0] if v else torch.empty_like(P["embeddings.weight"])
-
-                def emb_done():
-                    grads.update(zip(emb, red.reduce([grads[n] for n in emb])))
+                    v = red.slots([P[n].shape for n in last])
+                    return v[-1] if v else torch.empty_like(P["embeddings.weight"])
 
                 dfeat = base_backward_from_dHs(mode, P, kind, L, cap, bs, layers, dHs, grads, want_dfeat, feat.shape,
-                                               emb_out=emb_out, emb_done=emb_done, after_bptt=after_bptt)
+                                               emb_out=emb_out, after_bptt=after_bptt)
                 ops.join(box.get("db_done"))
-                rest = [n for n in names if n not in lin and n not in emb]
-                grads.update(zip(rest, red.reduce([grads[n] for n in rest])))
+                grads.update(zip(last, red.reduce([grads[n] for n in last])))
                 red.finish()
             return loss, (grads if need else None), dfeat
 
