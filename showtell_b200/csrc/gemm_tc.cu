@@ -94,6 +94,8 @@ struct TcParams {
                           // epilogue also keeps the soft-max partials (running max, sum of exp) of its columns.
   int streamk;            // pair kernel: 1 = stream-K schedule (C zeroed by the launcher)
   int a3d, b3d;           // MN-major operand given as the 3-D tensor map (make_tmap_mn3d): one TMA operation per k-block
+  int mc;                 // 1: launched as clusters of two CTAs that work on vertically adjacent tiles (same columns) and
+                          // SHARE the B tile: each loads half of it and multicasts it into both CTAs' shared memory
 };
 
 __device__ __forceinline__ float ex2_fast(float x) {   // 2^x, MUFU only (inputs here are <= ~0: no range fix-up needed)
@@ -411,7 +413,41 @@ struct WorkSched {
   }
 };
 
+__device__ __forceinline__ uint32_t cluster_rank_() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all_() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA loads that land at the same CTA-relative address in every CTA of `mask` and complete bytes on each one's mbarrier
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+// completion of this thread's MMAs -> one arrival on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+
 // ------------------------------------------------------------------------------------ 1-CTA kernel
+// p.mc = 1 ("B-multicast pairs"): the operand stream of these GEMMs is bound by the L2 -> SM bandwidth (a 128 x 256
+// tile pulls 48 KB per k-block; 148 SMs x ~80 GB/s = the measured 12 TB/s L2 ceiling, which is what the 5120 x 10000 x
+// 512 and 25088 x 512 x 2048 products ran at).  Launched as clusters of two CTAs that take the tiles (2m, n) and
+// (2m + 1, n) in lock step, each CTA loads its own A tile and HALF of the shared B tile, multicast into both CTAs:
+// 32 KB instead of 48 KB per CTA and k-block.  A stage is free once BOTH CTAs' MMAs have read it (multicast commit).
 // AMN / BMN = 1: that operand is given "MN-major" -- as the (K, M) resp. (K, N) row-major matrix, i.e. the
 // transpose of the K-major form -- and is consumed in place: TMA boxes of 64 k-rows x 64 (m|n) columns land
 // as 8 KB blocks [k][128 B] (128-byte swizzle), the UMMA descriptor walks them with LBO = 8 KB (next 64 m|n)
@@ -434,7 +470,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = (p.M + BM - 1) / BM, nt = (p.N + BN - 1) / BN;
+  const int mc = p.mc;                                             // pairs: "tile" = two vertically adjacent tiles
+  const int crank = mc ? (int)cluster_rank_() : 0;
+  const int nworkers = mc ? (int)(gridDim.x >> 1) : (int)gridDim.x, worker = mc ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int mt = mc ? ((p.M + 2 * BM - 1) / (2 * BM)) : ((p.M + BM - 1) / BM), nt = (p.N + BN - 1) / BN;
+  const int BMS = mc ? 2 * BM : BM;                                // rows per (pair) tile
   const int ntiles = mt * nt, kb = (p.K + BK - 1) / BK;
   const bool nfast = nt < mt;  // consecutive tiles walk the shorter dimension: the long operand streams once
 
@@ -445,7 +485,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], mc ? 2 : 1);   // pairs: a stage also holds the peer's half of B -> both CTAs' MMAs release it
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tfull[i], 1);
@@ -461,6 +501,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (mc) cluster_sync_all_();            // the peer's barriers exist before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   // PDL: everything above overlapped the previous kernel's tail; its outputs (our operands, and buffers it
@@ -471,16 +512,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // Producer and MMA warps run their loops with all 32 lanes (uniform control flow keeps addresses and UMMA
   // descriptors in uniform registers); only the TMA / tcgen05 instructions are issued by one elected lane.
   if (warp == 0) {  // ------------------------------------------------------------ TMA producer
-    WorkSched sched(ntiles, kb, gridDim.x, blockIdx.x, p.streamk);
+    WorkSched sched(ntiles, kb, nworkers, worker, p.streamk);
     int stage = 0, tile, k0, k1;
     uint32_t phase = 0;
     while (sched.next(tile, k0, k1)) {
-      const int m0 = (nfast ? tile / nt : tile % mt) * BM, n0 = (nfast ? tile % nt : tile / mt) * BN;
+      const int m0 = (nfast ? tile / nt : tile % mt) * BMS + crank * BM, n0 = (nfast ? tile % nt : tile / mt) * BN;
       for (int k = k0; k < k1; ++k) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
           mbar_expect_tx(&full[stage], STAGE_BYTES);
           uint8_t* a = smem + (size_t)stage * STAGE_BYTES;
+          if (mc) {
+            // own A tile; this CTA's half of the B tile into both CTAs (the other half arrives from the peer)
+            if (AMN && p.a3d) tma_load_3d(a, &tmA, 0, k * BK, m0 / 64, &full[stage]);
+            else if (AMN) {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(a + j * 8192, &tmA, m0 + 64 * j, k * BK, &full[stage]);
+            } else tma_load_2d(a, &tmA, k * BK, m0, &full[stage]);
+            uint8_t* bh = a + A_BYTES + crank * (TileCfg<BN>::B_BYTES / 2);
+            const int nh = n0 + crank * (BN / 2);
+            if (BMN) tma_load_3d_mc(bh, &tmB, 0, k * BK, nh / 64, &full[stage], (uint16_t)3);
+            else tma_load_2d_mc(bh, &tmB, k * BK, nh, &full[stage], (uint16_t)3);
+          } else {
           if (AMN && p.a3d) {
             tma_load_3d(a, &tmA, 0, k * BK, m0 / 64, &full[stage]);
           } else if (AMN) {
@@ -497,6 +550,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             tma_load_2d(a + A_BYTES, &tmB, k * BK, n0, &full[stage]);
           }
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -508,7 +562,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint64_t bdesc0 = BMN ? umma_desc_mn128(smem_u32(smem) + A_BYTES) : umma_desc_k128(smem_u32(smem) + A_BYTES);
     // descriptor start-address step per 16-deep k-step, in 16-byte units: K-major 32 B, MN-major two 8-row groups
     constexpr uint64_t astep = AMN ? 128 : 2, bstep = BMN ? 128 : 2;
-    WorkSched sched(ntiles, kb, gridDim.x, blockIdx.x, p.streamk);
+    WorkSched sched(ntiles, kb, nworkers, worker, p.streamk);
     int stage = 0, acc = 0, tile, k0, k1;
     uint32_t phase = 0, acc_phase = 0;
     while (sched.next(tile, k0, k1)) {
@@ -524,7 +578,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int kk = 0; kk < BK / UK; ++kk)
             tc_mma(d_tmem, adesc0 + so + astep * kk, bdesc0 + so + bstep * kk, idesc, (k > k0) || (kk != 0));
-          tc_commit(&empty[stage]);  // smem slot free once these MMAs retire
+          if (mc) tc_commit_mc(&empty[stage], (uint16_t)3);   // ... in both CTAs: each holds half of the other's B tile
+          else tc_commit(&empty[stage]);  // smem slot free once these MMAs retire
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -536,11 +591,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 4) {  // ------------------------------------------------------ epilogue
     // 8 warps: warp w owns TMEM lanes 32*(w%4)..+31 (32 rows) and one half of the tile's BN columns.
     const int ew = warp & 3, half = (warp - 4) >> 2;
-    WorkSched sched(ntiles, kb, gridDim.x, blockIdx.x, p.streamk);
+    WorkSched sched(ntiles, kb, nworkers, worker, p.streamk);
     int acc = 0, tile, k0, k1;
     uint32_t acc_phase = 0;
     while (sched.next(tile, k0, k1)) {
-      const int m0 = (nfast ? tile / nt : tile % mt) * BM, n0 = (nfast ? tile % nt : tile / mt) * BN;
+      const int m0 = (nfast ? tile / nt : tile % mt) * BMS + crank * BM, n0 = (nfast ? tile % nt : tile / mt) * BN;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t tbase = tmem_base + acc * BN + ((uint32_t)(ew * 32) << 16);
@@ -555,6 +610,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (mc) cluster_sync_all_();            // the peer may still be signalling this CTA's barriers
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -1041,28 +1097,51 @@ inline bool want_streamk(const TcParams& p, int ntiles, int kb, int workers) {
   return saved_us > cost_us;
 }
 
+int g_mc = 0;    // st_debug_gemm_variant(v | 0x4000 / 0x8000): B-multicast CTA pairs forced on / off (0 = choose)
+
 template <int EPI, int BN, int AMN = 0, int BMN = 0>
 int launch_tc_bn(TcParams p, const void* A, int lda, const void* B, int ldb, cudaStream_t s, int sms) {
   CUtensorMap tmA, tmB;
+  auto kern = gemm_tc_kernel<EPI, BN, AMN, BMN>;
+  ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<BN>::SMEM_BYTES));
+  const int mt1 = (p.M + BM - 1) / BM, ntn = (p.N + BN - 1) / BN, kb = (p.K + BK - 1) / BK;
+  // B-multicast pairs (see the kernel).  Measured on B200: no gain where the tile grid is large (multicast over two CTAs
+  // does not lower the L2 traffic enough to matter: 5120 x 10000 x 512 and 25088 x 512 x 2048 run at the same 55-58 us),
+  // but the long-K weight-gradient products with a handful of row tiles -- dW_enc / dW_embed = X^T F, 512 x 2048 x 25088,
+  // 32 tiles cut into stream-K ranges -- go from 87 to 64 us.  MN-major B: its columns in whole 64-blocks (3-D map).
+  const bool mc_ok = BN >= 128 && mt1 >= 2 && sms >= 2 && (!BMN || (p.N % 64 == 0 && g_mn3d));
+  p.mc = (mc_ok && g_mc >= 0 && (g_mc > 0 || (mt1 <= 8 && kb >= 128))) ? 1 : 0;
   // MN-major operands whose (m|n) extent is a multiple of 64: one 3-D box per k-block instead of BM/64 (BN/64) 2-D boxes
   p.a3d = (AMN && p.M % 64 == 0 && g_mn3d) ? 1 : 0;
   p.b3d = (BMN && p.N % 64 == 0 && g_mn3d) ? 1 : 0;
   if (AMN && p.a3d) ST_TRY(make_tmap_mn3d(&tmA, A, p.K, p.M, lda, BM / 64, "A (MN-major)"));
   else if (AMN) ST_TRY(make_tmap(&tmA, A, p.K, p.M, lda, 64, "A (MN-major)"));
   else ST_TRY(make_tmap(&tmA, A, p.M, p.K, lda, BM, "A"));
-  if (BMN && p.b3d) ST_TRY(make_tmap_mn3d(&tmB, B, p.K, p.N, ldb, BN / 64, "B (MN-major)"));
+  const int bdiv = p.mc ? 2 : 1;                                   // pairs load B in halves
+  if (BMN && p.b3d) ST_TRY(make_tmap_mn3d(&tmB, B, p.K, p.N, ldb, BN / 64 / bdiv, "B (MN-major)"));
   else if (BMN) ST_TRY(make_tmap(&tmB, B, p.K, p.N, ldb, 64, "B (MN-major)"));
-  else ST_TRY(make_tmap(&tmB, B, p.N, p.K, ldb, BN, "B"));
-  auto kern = gemm_tc_kernel<EPI, BN, AMN, BMN>;
-  ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<BN>::SMEM_BYTES));
-  const int ntiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN), kb = (p.K + BK - 1) / BK;
-  int grid = ntiles < sms ? ntiles : sms;
-  p.streamk = want_streamk<EPI>(p, ntiles, kb, sms) ? 1 : 0;
+  else ST_TRY(make_tmap(&tmB, B, p.N, p.K, ldb, BN / bdiv, "B"));
+  const int workers = p.mc ? sms / 2 : sms;
+  const int ntiles = (p.mc ? (mt1 + 1) / 2 : mt1) * ntn;
+  int grid = ntiles < workers ? ntiles : workers;
+  p.streamk = want_streamk<EPI>(p, ntiles, kb, workers) ? 1 : 0;
   if (p.streamk) {
-    grid = sms;
+    grid = workers;
     ST_CUDA_TRY(cudaMemset2DAsync(p.C, (size_t)p.ldc * 4, 0, (size_t)p.N * 4, p.M, s));
   }
-  ST_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(NTHREADS), TileCfg<BN>::SMEM_BYTES, s, tmA, tmB, p));
+  if (!p.mc) {
+    ST_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(NTHREADS), TileCfg<BN>::SMEM_BYTES, s, tmA, tmB, p));
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = TileCfg<BN>::SMEM_BYTES; cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
+    ST_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  }
   note_launch();
   return ST_OK;
 }
@@ -1267,6 +1346,7 @@ int st_gemm_set_sm_limit(int n) {
 int st_debug_gemm_variant(int variant) {
   st::g_streamk = (variant & 0x1000) ? 0 : 1;
   st::g_mn3d = (variant & 0x2000) ? 0 : 1;
+  st::g_mc = (variant & 0x4000) ? 1 : ((variant & 0x8000) ? -1 : 0);
   variant &= 0xfff;
   st::g_variant = (variant == 2 || variant == 128 || variant == 256) ? variant : 0;
   return ST_OK;

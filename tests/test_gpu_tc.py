@@ -19,8 +19,12 @@ def gemm_variant():
     lib.st_debug_gemm_variant(0)
 
 
-# variant: 0 = the library's choice, 128 / 256 = single-CTA kernel, 2 = CTA-pair kernel (cta_group::2)
-@pytest.mark.parametrize("variant", [0, 128, 256, 2])
+# variant: 0 = the library's choice, 128 / 256 = single-CTA kernel, 2 = CTA-pair kernel (cta_group::2);
+# | 0x4000 = B-multicast CTA pairs wherever the shape allows them, | 0x8000 = never
+MC, NOMC = 0x4000, 0x8000
+
+
+@pytest.mark.parametrize("variant", [0, 128, 256, 2, MC | 128, MC | 256, NOMC])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 512), (256, 384, 128), (5120, 2048, 512),
                                    (100, 50, 40), (129, 257, 72), (640, 10000, 512), (37, 1000, 2048),
                                    (5120, 512, 10000),      # dX of the vocabulary projection: stream-K, 40 tiles
@@ -53,7 +57,7 @@ def test_gemm_bf16(M, N, K, variant, gemm_variant):
     assert bool((wide[:, :4] == 7).all()) and bool((wide[:, 4 + N:] == 7).all())
 
 
-@pytest.mark.parametrize("variant", [0, 128, 256])
+@pytest.mark.parametrize("variant", [0, 128, 256, MC | 128, MC | 256, NOMC])
 @pytest.mark.parametrize("a_t,b_t", [(True, True), (False, True), (True, False)])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 256, 128), (256, 384, 192), (100, 50, 40), (129, 257, 72),
                                    (10000, 512, 5120),      # dW of the vocabulary projection: P^T . Hs
@@ -120,7 +124,7 @@ def test_cast_bf16():
     assert d.stride(0) % 8 == 0 and dT.stride(0) % 8 == 0
 
 
-@pytest.mark.parametrize("variant", [0, 128, 256, 2])
+@pytest.mark.parametrize("variant", [0, 128, 256, 2, MC | 256, NOMC])
 @pytest.mark.parametrize("M,V,H", [(64, 128, 64), (300, 1000, 128), (640, 10000, 512), (5120, 10000, 512),
                                    (2555, 9999, 512)])
 def test_vocab_ce_fused(M, V, H, variant, gemm_variant):

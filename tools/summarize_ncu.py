@@ -39,7 +39,10 @@ def to_us(v, unit):
 
 
 def full(rep, out, title):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):         # `ncu -i X.ncu-rep --page raw --csv` already run on the GPU box (reports over 64 MB do not travel)
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     want = OrderedDict([

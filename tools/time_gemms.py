@@ -37,6 +37,9 @@ def main():
         W = torch.randn(A, C, device=dev).to(BF)
         d1 = torch.randn(BP, A, device=dev).to(BF)
         bench("att1_fwd  F W^T        (25088,512,2048) K-major", lambda: ops.gemm_bf16(F, W, out_dtype=BF), 2.0 * BP * A * C)
+        Hb2 = torch.randn(5120, 512, device=dev).to(BF)
+        Wv2 = torch.randn(10000, 512, device=dev).to(BF)
+        bench("vocab-like Hs Wv^T     (5120,10000,512) K-major", lambda: ops.gemm_bf16(Hb2, Wv2, out_dtype=BF), 2.0 * 5120 * 10000 * 512)
         bench("att1_dw   d1^T F       (512,2048,25088) MN/MN", lambda: ops.gemm_bf16(d1, F, a_t=True, b_t=True), 2.0 * BP * A * C)
         for n_tok, tag in ((2560, "cfg3"), (5120, "cfg2")):
             Pm = torch.randn(n_tok, V, device=dev).to(BF)
