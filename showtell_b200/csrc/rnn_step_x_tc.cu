@@ -23,40 +23,6 @@ namespace {
 
 constexpr int UT = 16, HALF = 8, NTH = 320, MAXKB = 8, MAXST = 16;
 
-__device__ __forceinline__ float tanh_fast(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
-  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
-  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-}
-__device__ __forceinline__ void st8bf(__nv_bfloat16* p, const float (&v)[8]) {
-  uint32_t w[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-    w[q] = *reinterpret_cast<uint32_t*>(&h);
-  }
-  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
-}
-
 struct StepXParams {
   int H, EX, t, nstages;
   const float *Gx, *bhh, *h0, *c0;      // Gx (N, G*H): hoisted W_ih[:, :E] emb + b_ih
@@ -242,8 +208,6 @@ rnn_step_x_tc_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_cons
 // once (N = 32) and the n k-blocks twice (dGh_n -> columns 0..15, dG_n -> columns 16..31, N = 16 each).
 // Requires EX == H (one grid of H/16 unit tiles covers both outputs) and H % 64 == 0.
 constexpr int XB_STAGES = 9;
-
-__device__ __forceinline__ void proxy_fence_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
 struct StepXBwdParams {
   int H, t, nsteps, nstages;
