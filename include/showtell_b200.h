@@ -136,6 +136,24 @@ int st_gemm_tf32x3_topk(int M, int N, int K, const float* A_hi, const float* A_l
                         const float* B_lo, int ldb, const float* bias, int topk, float* cand_val, int32_t* cand_idx,
                         float* val, int32_t* idx, int out_stride, int64_t* tok, int tok_stride, float* part_stats,
                         float* row_max, float* row_sum, st_stream_t stream);
+/* Screening pass of the decoding loops: the bf16 product A . B^T + bias with only the ST_SCREEN_SLOTS largest values (and
+ * their columns) of every part (128 columns; 64 when N <= 128) kept per row -- cand_val / cand_idx (M, *npart_out,
+ * ST_SCREEN_SLOTS), *npart_out * ST_SCREEN_SLOTS <= st_topk_parts(N).  The caller bounds the bf16 rounding error and
+ * re-scores the survivors exactly (st_vocab_topk_screen). */
+enum { ST_SCREEN_SLOTS = 3 };
+int st_gemm_bf16_screen(int M, int N, int K, const void* A_bf16, int lda, const void* B_bf16, int ldb, const float* bias,
+                        float* cand_val, int32_t* cand_idx, int* npart_out, st_stream_t stream);
+/* out[0] = max over rows of the row's 2-norm (W (rows, cols) fp32 contiguous): the weight factor of the screening bound. */
+int st_row_norm_max(const float* W, int rows, int cols, float* out, st_stream_t stream);
+/* Exact per-row top-K (K <= 8) of h . Wv^T + bv (rnn.py:51 `max(1)[1]`, rnn.py:63,90-91 `topk`) WITHOUT the (M, V) logits
+ * and at a fraction of the fp32-accurate product's cost: bf16 screening GEMM (st_gemm_bf16_screen), a per-row bound of its
+ * rounding error (c |h| wmax, wmax = st_row_norm_max(Wv)), exact fp32 re-scoring of every column that can still be in
+ * the top K (decode.cu: screen_select_kernel states the argument).  h / Wv fp32 and their bf16 roundings (M, H) / (V, H),
+ * H % 8 == 0; cand_val / cand_idx: scratch of M * st_topk_parts(V) entries.  Outputs as st_gemm_tf32x3_topk: value
+ * descending, the lower column first among equal values. */
+int st_vocab_topk_screen(int M, int V, int H, const float* h, const void* h_bf16, const float* Wv, const void* Wv_bf16,
+                         const float* bv, const float* wmax, int K, float* cand_val, int32_t* cand_idx, float* val,
+                         int32_t* idx, int out_stride, int64_t* tok, int tok_stride, st_stream_t stream);
 /* Development / test aid: pin the kernel behind st_gemm_bf16 and st_vocab_ce_*: 2 = CTA-pair kernel
  * (cta_group::2, 256x256 tiles, stream-K), 128 / 256 = single-CTA kernel with that tile width, 0 = choose. */
 int st_debug_gemm_variant(int variant);
@@ -439,6 +457,9 @@ int64_t st_decode_workspace_bytes(const st_rnn_weights* w, int n_img, int K, int
 /* Development / test aid: the projected-embedding table of gemm_mode 1 (EP = emb . W_ih^T + b_ih, built once per call):
  * 0 = by size (rows * max_len >= V), 1 = always, -1 = never.  Set before st_decode_workspace_bytes. */
 int st_debug_decode_table(int mode);
+/* ... and the vocabulary projection of gemm_mode 1: 0 / 1 = bf16 screening GEMM + exact fp32 re-scoring of the columns
+ * that can still be among the top K (default), -1 = the 3xTF32 product with the top-K in its epilogue. */
+int st_debug_decode_screen(int mode);
 
 /* RNN.sentence_index(cnn_feature) greedy (rnn.py:44-58, rnn_lstm.py:35-57):
  * feature (n_img, E) -> tokens (n_img, max_len) int64. */

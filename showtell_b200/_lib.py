@@ -45,6 +45,10 @@ _SIGS = {
     "st_gemm_tf32x3": (_I, [_I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _F, _F, _P]),
     "st_topk_parts": (_I, [_I]),
     "st_debug_decode_table": (_I, [_I]),
+    "st_debug_decode_screen": (_I, [_I]),
+    "st_row_norm_max": (_I, [_P, _I, _I, _P, _P]),
+    "st_vocab_topk_screen": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P]),
+    "st_gemm_bf16_screen": (_I, [_I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P]),
     "st_gemm_tf32x3_topk": (_I, [_I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
     "st_debug_set_pdl": (_I, [_I]),
     "st_debug_set_bwd_kp": (_I, [_I]),

@@ -11,6 +11,8 @@
 //     table  EP = emb . W_ih^T + b_ih  (V rows, built once per call; per-step GEMM for short calls), which the gate
 //     kernel gathers by token id.
 // A per-image bookkeeping kernel reproduces the reference's ranking rules (documented at each kernel).
+#include <cuda_bf16.h>
+
 #include <cfloat>
 
 #include "common.cuh"
@@ -34,6 +36,16 @@ extern "C" int st_gemm_tf32x3_topk(int M, int N, int K, const float* A_hi, const
                                    int32_t* cand_idx, float* val, int32_t* idx, int out_stride, int64_t* tok,
                                    int tok_stride, float* part_stats, float* row_max, float* row_sum,
                                    st_stream_t stream);
+
+extern "C" int st_gemm_bf16_screen(int M, int N, int K, const void* A, int lda, const void* B, int ldb, const float* bias,
+                                 float* cand_val, int32_t* cand_idx, int* npart_out, st_stream_t stream);
+extern "C" int st_cast_bf16(const float* src, int rows, int cols, int lds, void* dst, int ldd, void* dstT, int lddT,
+                            st_stream_t stream);
+
+extern "C" int st_row_norm_max(const float* W, int rows, int cols, float* out, st_stream_t stream);
+extern "C" int st_vocab_topk_screen(int M, int V, int H, const float* h, const void* h_bf16, const float* Wv, const void* Wv_bf16,
+                                    const float* bv, const float* wmax, int K, float* cand_val, int32_t* cand_idx, float* val,
+                                    int32_t* idx, int out_stride, int64_t* tok, int tok_stride, st_stream_t stream);
 
 namespace st {
 namespace {
@@ -73,6 +85,7 @@ inline bool use_tc(const st_rnn_weights* w) { return w->gemm_mode == 1 && w->E %
 
 constexpr int FUSED_TOPK_MAX = 8;   // TOPK_SLOTS of the fused epilogue (gemm_tc.cu)
 int g_force_table = 0;              // st_debug_decode_table: 0 = by size, 1 = always, -1 = never
+int g_screen = 0;                   // st_debug_decode_screen: 0 / 1 = bf16 screening + exact re-scoring, -1 = 3xTF32 fused top-K
 
 __device__ __forceinline__ void split_store(float x, float* hi, float* lo) {
   const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);   // as st_split_tf32
@@ -106,7 +119,7 @@ __global__ void __launch_bounds__(256) decode_gate_kernel(int rows, int H, GxSrc
                                                           const float* __restrict__ bhh, const float* __restrict__ h_prev,
                                                           const float* __restrict__ c_prev, float* __restrict__ h_out,
                                                           float* __restrict__ c_out, float* __restrict__ h_hi,
-                                                          float* __restrict__ h_lo) {
+                                                          float* __restrict__ h_lo, __nv_bfloat16* __restrict__ h_bf) {
   const long long n = (long long)rows * H;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / H), u = (int)(i - (long long)r * H);
@@ -135,6 +148,218 @@ __global__ void __launch_bounds__(256) decode_gate_kernel(int rows, int H, GxSrc
     }
     h_out[i] = hv;
     split_store(hv, h_hi + i, h_lo + i);
+    if (h_bf) h_bf[i] = __float2bfloat16(hv);       // operand of the screening GEMM (top layer)
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Vocabulary projection of the tensor-core decoding loops as "screen, then re-score" (rnn.py:50-51, 62-63, 88-91).
+// The ranking of 10 000 logits needs fp32 accuracy only among the few columns that can be in the top K at all:
+//   1. screening: the bf16 tensor-core product (one MMA per k-step instead of the three of 3xTF32) with the 8 largest
+//      approximate logits of every 128-column part kept in the epilogue (st_gemm_bf16_screen; logits never written);
+//   2. error bound of a row: both operands are rounded to bf16 (relative 2^-9 each), so
+//        |approx_v - exact_v| <= 2^-8 (1 + 2^-10) sum_i |h_i w_vi| (+ fp32 accumulation)  <=  eps := c |h| max_v |w_v|
+//      (Cauchy-Schwarz; c = 2^-7.9).  With a_K = the K-th largest KEPT approximation (a lower bound of the K-th largest
+//      approximation overall), K columns have exact logits >= a_K - eps, hence so has the K-th largest exact logit, and
+//      every column of the exact top K has an approximation >= tau := a_K - 2 eps;
+//   3. a part whose last kept value is < tau has kept every column >= tau; otherwise ALL of its columns are re-scored;
+//   4. the survivors (typically 5-20 of 10 000) get their exact logit b_v + <h, w_v> in fp32 (one warp per row, fixed
+//      summation order) and the top K of those is the result: value descending, lower column first among equals.
+// One warp per row.  wmax = max_v |w_v|_2 (one scalar per call).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr float SCREEN_C = 0.0041874f;   // 2^-7.9
+
+__global__ void __launch_bounds__(256) row_norm_max_kernel(const float* __restrict__ W, int rows, int cols, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) { const float v = W[(size_t)r * cols + c]; s = fmaf(v, v, s); }
+  s = warp_sum(s);
+  if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(sqrtf(s)));   // non-negative floats order as ints
+}
+
+template <int KMAX>
+__device__ __forceinline__ void topk_insert(float (&bv)[KMAX], int (&bi)[KMAX], float v, int i) {
+  // sorted list (value descending, lower index first among equals); an index already present is ignored
+#pragma unroll
+  for (int q = 0; q < KMAX; ++q)
+    if (bi[q] == i) return;
+  if (!(v > bv[KMAX - 1] || (v == bv[KMAX - 1] && i < bi[KMAX - 1]))) return;
+  bv[KMAX - 1] = v; bi[KMAX - 1] = i;
+#pragma unroll
+  for (int q = KMAX - 1; q > 0; --q) {
+    if (bv[q] > bv[q - 1] || (bv[q] == bv[q - 1] && bi[q] < bi[q - 1])) {
+      const float tv = bv[q]; bv[q] = bv[q - 1]; bv[q - 1] = tv;
+      const int ti = bi[q]; bi[q] = bi[q - 1]; bi[q - 1] = ti;
+    }
+  }
+}
+
+constexpr int SC_CAND = 64, SC_OVER = 8;   // per row: survivors re-scored one by one / parts re-scored as a whole
+
+__global__ void __launch_bounds__(256) screen_select_kernel(int M, int H, int V, int npart, int part_cols, int K,
+                                                            const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx,
+                                                            const float* __restrict__ h, const float* __restrict__ Wv,
+                                                            const float* __restrict__ bv, const float* __restrict__ wmax,
+                                                            float* __restrict__ val, int32_t* __restrict__ idx, int out_stride,
+                                                            int64_t* __restrict__ tok, int tok_stride) {
+  extern __shared__ __align__(16) float s_h[];      // [8 warps][H]
+  __shared__ int s_cand[8][SC_CAND];                // survivors of each warp's row
+  __shared__ int s_over[8][SC_OVER], s_nover[8];    // parts of each warp's row that are re-scored as a whole
+  __shared__ float s_res[128];                      // exact logits of one such part (phase B)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, m = blockIdx.x * 8 + wid;
+  const bool valid = m < M;
+  float* hs = s_h + (size_t)wid * H;
+  constexpr int SL = ST_SCREEN_SLOTS, KMAX = 8;
+  float bestv[KMAX];
+  int besti[KMAX];
+#pragma unroll
+  for (int q = 0; q < KMAX; ++q) { bestv[q] = -FLT_MAX; besti[q] = 0x7fffffff - q; }
+  // exact logits of two columns of a row whose state sits in `hrow` (shared memory): lane j sums the elements
+  // i = j (mod 32) in increasing order, the 32 partial sums meet in the xor-shuffle tree (a fixed summation order:
+  // a column's value does not depend on who computes it); every lane ends with both values.  All loads of a
+  // 512-element block of both rows are in flight before the first multiply.
+  auto exact2 = [&](const float* hrow, int va, int vb, float& sa, float& sb) {
+    const float* wa = Wv + (size_t)va * H;
+    const float* wb = Wv + (size_t)vb * H;
+    sa = 0.f; sb = 0.f;
+    for (int i0 = 0; i0 < H; i0 += 512) {
+      float xa[16], xb[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int i = i0 + lane + 32 * j;
+        xa[j] = i < H ? wa[i] : 0.f;
+        xb[j] = i < H ? wb[i] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int i = i0 + lane + 32 * j;
+        if (i < H) { const float hv = hrow[i]; sa = fmaf(hv, xa[j], sa); sb = fmaf(hv, xb[j], sb); }
+      }
+    }
+    sa = warp_sum(sa) + bv[va];
+    sb = warp_sum(sb) + bv[vb];
+  };
+  int ncnd = 0, nover = 0;
+  if (valid) {
+    // ---- phase A: this warp's row.  State and its norm; the bound; a_K; survivors and parts to re-score as a whole
+    float hh = 0.f;
+    for (int i = lane; i < H; i += 32) { const float v = h[(size_t)m * H + i]; hs[i] = v; hh = fmaf(v, v, hh); }
+    hh = warp_sum(hh);
+    __syncwarp();
+    const float eps = SCREEN_C * sqrtf(hh) * (*wmax);
+    const int ncand = npart * SL;
+    const float* cv = cand_val + (size_t)m * ncand;
+    const int32_t* ci = cand_idx + (size_t)m * ncand;
+    // a lower bound a_K of the K-th largest approximation: the K-th largest KEPT one (K rounds of warp arg-max with
+    // exclusion, as topk_merge_kernel; a part may have dropped some of the overall K largest, which only lowers it)
+    float pv = FLT_MAX;
+    int pi = -1;
+    for (int k = 0; k < K; ++k) {
+      float b = -FLT_MAX;
+      int bi = 0x7fffffff;
+      for (int c = lane; c < ncand; c += 32) {
+        const float x = cv[c];
+        const int i = ci[c];
+        const bool after_prev = (x < pv) || (x == pv && i > pi);
+        if (after_prev && ((x > b) || (x == b && i < bi))) { b = x; bi = i; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, b, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > b || (ov == b && oi < bi)) { b = ov; bi = oi; }
+      }
+      pv = b; pi = bi;
+    }
+    const float tau = pv - 2.f * eps;
+    for (int p0 = 0; p0 < npart; p0 += 32) {         // a lane looks at one part's kept entries (descending)
+      const int part = p0 + lane;
+      int xi[SL], npass = 0;
+#pragma unroll
+      for (int q = 0; q < SL; ++q) {
+        const float x = part < npart ? cv[part * SL + q] : -FLT_MAX;
+        xi[q] = part < npart ? ci[part * SL + q] : -1;
+        if (x >= tau && xi[q] >= 0 && xi[q] < V) npass = q + 1;
+      }
+      // a part whose LAST kept value still passes may have dropped columns that pass: all of its columns are re-scored
+      // (so are parts whose survivors no longer fit the list)
+      bool whole = npass == SL;
+      const int mine = whole ? 0 : npass;
+      int before = mine;                              // inclusive prefix sum over the lanes
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, before, o);
+        if (lane >= o) before += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, before, 31);
+      if (ncnd + total > SC_CAND) whole = whole || npass > 0;
+      else {
+#pragma unroll
+        for (int q = 0; q < SL - 1; ++q)
+          if (q < mine) s_cand[wid][ncnd + before - mine + q] = xi[q];
+      }
+      if (ncnd + total <= SC_CAND) ncnd += total;
+      unsigned over = __ballot_sync(0xffffffffu, whole);
+      while (over) {
+        const int b = __ffs(over) - 1;
+        over &= over - 1;
+        if (nover < SC_OVER) {
+          if (lane == 0) s_over[wid][nover] = p0 + b;
+          ++nover;
+        } else {                                      // (more such parts than the list holds: re-scored right here)
+          const int pt = p0 + b;
+          const int v0 = (pt >> 1) * (2 * part_cols) + (pt & 1) * part_cols, v1 = min(V, v0 + part_cols);
+          for (int v = v0; v < v1; v += 2) {
+            float sa, sb;
+            exact2(hs, v, min(v + 1, v1 - 1), sa, sb);
+            topk_insert<KMAX>(bestv, besti, sa, v);
+            if (v + 1 < v1) topk_insert<KMAX>(bestv, besti, sb, v + 1);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    for (int j = 0; j < ncnd; j += 2) {               // the survivors, two columns per round trip
+      const int va = s_cand[wid][j], vb = s_cand[wid][min(j + 1, ncnd - 1)];
+      float sa, sb;
+      exact2(hs, va, vb, sa, sb);
+      topk_insert<KMAX>(bestv, besti, sa, va);
+      if (j + 1 < ncnd) topk_insert<KMAX>(bestv, besti, sb, vb);
+    }
+  }
+  if (lane == 0) s_nover[wid] = nover;
+  __syncthreads();
+  // ---- phase B: whole parts, by the whole block (rare: a handful of rows per call): warp w scores 16 of the columns
+  for (int wo = 0; wo < 8; ++wo) {
+    const int n = s_nover[wo];                        // block-uniform
+    for (int e = 0; e < n; ++e) {
+      const int pt = s_over[wo][e];
+      const int v0 = (pt >> 1) * (2 * part_cols) + (pt & 1) * part_cols, v1 = min(V, v0 + part_cols);
+      const int per = (part_cols + 7) / 8;
+      for (int j = 0; j < per; j += 2) {
+        const int va = v0 + wid * per + j, vb = va + 1;
+        if (va < v1) {
+          float sa, sb;
+          exact2(s_h + (size_t)wo * H, va, min(vb, v1 - 1), sa, sb);
+          if (lane == 0) { s_res[va - v0] = sa; if (vb < v1 && j + 1 < per) s_res[vb - v0] = sb; }
+        }
+      }
+      __syncthreads();
+      if (wid == wo)
+        for (int v = v0; v < v1; ++v) topk_insert<KMAX>(bestv, besti, s_res[v - v0], v);
+      __syncthreads();
+    }
+  }
+  if (valid && lane == 0) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k < K) {
+        if (val) val[(size_t)m * out_stride + k] = bestv[k];
+        if (idx) idx[(size_t)m * out_stride + k] = besti[k];
+      }
+    }
+    if (tok) tok[(size_t)m * tok_stride] = besti[0];
   }
 }
 
@@ -155,6 +380,7 @@ struct Rig {
   bool tc;      // gemm_mode 1: all products on the tensor cores
   bool fused;   // tc and K <= FUSED_TOPK_MAX: vocabulary projection fused with the top-K, no logits buffer
   bool table;   // tc and enough row-steps to amortise it: input projections of fed-back words from the EP table
+  bool screen;  // fused: vocabulary projection as bf16 screening + exact re-scoring (see screen_select_kernel)
   float *X, *Gx0, *GxL, *logits;
   float* h[2][MAXL];
   float* c[2][MAXL];
@@ -163,6 +389,8 @@ struct Rig {
   // top-K candidates / soft-max partials of the fused vocabulary projection, the projected-embedding table
   float *Whh_hi[MAXL], *Whh_lo[MAXL], *Gh, *hs_hi[2][MAXL], *hs_lo[2][MAXL], *cand_val, *part_stats, *EP, *emb_hi, *emb_lo;
   int32_t* cand_idx;
+  __nv_bfloat16 *Wv_b, *hb[2];   // screen: bf16 vocabulary weights, bf16 copy of the top layer's state
+  float* wmax;                   // screen: max_v |w_v|_2
   int* barrier;
   int cur;
   cudaStream_t s;
@@ -176,6 +404,7 @@ struct Rig {
     fused = tc && K <= FUSED_TOPK_MAX;
     table = tc && (int64_t)rows * steps >= (int64_t)w->V && g_force_table >= 0;
     if (tc && g_force_table > 0) table = true;
+    screen = fused && g_screen >= 0 && w->H % 8 == 0 && w->H <= 1536;
     X = b.take<float>((int64_t)rows * w->E);
     Gx0 = b.take<float>((int64_t)rows * G * w->H);
     GxL = b.take<float>((int64_t)rows * G * w->H);
@@ -207,6 +436,14 @@ struct Rig {
       cand_val = b.take<float>((int64_t)rows * parts);
       cand_idx = b.take<int32_t>((int64_t)rows * parts);
       part_stats = b.take<float>((int64_t)rows * (parts / 4));
+      Wv_b = hb[0] = hb[1] = nullptr;
+      wmax = nullptr;
+      if (screen) {
+        Wv_b = b.take<__nv_bfloat16>((int64_t)w->V * w->H);
+        hb[0] = b.take<__nv_bfloat16>((int64_t)rows * w->H);
+        hb[1] = b.take<__nv_bfloat16>((int64_t)rows * w->H);
+        wmax = b.take<float>(4);
+      }
       EP = emb_hi = emb_lo = nullptr;
       if (table) {
         EP = b.take<float>((int64_t)w->V * G * w->H);
@@ -226,6 +463,10 @@ struct Rig {
       ST_TRY(st_split_tf32(w->Whh_host[l], G * w->H, w->H, w->H, Whh_hi[l], Whh_lo[l], w->H, s));
     }
     ST_TRY(st_split_tf32(w->Wv, w->V, w->H, w->H, Wv_hi, Wv_lo, w->H, s));
+    if (screen) {
+      ST_TRY(st_cast_bf16(w->Wv, w->V, w->H, w->H, Wv_b, w->H, nullptr, 0, s));
+      ST_TRY(st_row_norm_max(w->Wv, w->V, w->H, wmax, s));
+    }
     if (table) {   // EP[v] = W_ih0 emb[v] + b_ih0: the same product, row for row, the per-step input GEMM would form
       ST_TRY(st_split_tf32(w->emb, w->V, w->E, w->E, emb_hi, emb_lo, w->E, s));
       ST_TRY(st_gemm_tf32x3(w->V, G * w->H, w->E, emb_hi, emb_lo, w->E, Wih_hi[0], Wih_lo[0], w->E, EP, G * w->H,
@@ -242,12 +483,13 @@ struct Rig {
     const long long blocks = (n + 255) / 256;
     const unsigned grid = (unsigned)(blocks < 8LL * sms ? blocks : 8LL * sms);
     const float* gh = first ? nullptr : Gh;
+    __nv_bfloat16* hbf = (screen && l == w->L - 1) ? hb[nxt] : nullptr;
     if (w->kind == ST_LSTM)
       decode_gate_kernel<4><<<grid, 256, 0, s>>>(rows, H, src, gh, w->bhh_host[l], first ? nullptr : h[cur][l],
-                                                 first ? nullptr : c[cur][l], h[nxt][l], c[nxt][l], hs_hi[nxt][l], hs_lo[nxt][l]);
+                                                 first ? nullptr : c[cur][l], h[nxt][l], c[nxt][l], hs_hi[nxt][l], hs_lo[nxt][l], hbf);
     else
       decode_gate_kernel<3><<<grid, 256, 0, s>>>(rows, H, src, gh, w->bhh_host[l], first ? nullptr : h[cur][l], nullptr,
-                                                 h[nxt][l], nullptr, hs_hi[nxt][l], hs_lo[nxt][l]);
+                                                 h[nxt][l], nullptr, hs_hi[nxt][l], hs_lo[nxt][l], hbf);
     ST_LAUNCH_TRY("decode_gate_kernel");
     return ST_OK;
   }
@@ -282,6 +524,10 @@ struct Rig {
   // rows' soft-max normaliser (beam_search.py:85-88)
   int vocab_topk(int K, float* val, int32_t* idx, int out_stride, int64_t* tok, int tok_stride, float* row_max = nullptr,
                  float* row_sum = nullptr) {
+    if (screen && !row_max) {   // (the tree beam's soft-max normaliser needs every logit at fp32 accuracy: 3xTF32 path)
+      return st_vocab_topk_screen(rows, w->V, w->H, h[cur][w->L - 1], hb[cur], w->Wv, Wv_b, w->bv, wmax, K, cand_val, cand_idx,
+                                  val, idx, out_stride, tok, tok_stride, s);
+    }
     return st_gemm_tf32x3_topk(rows, w->V, w->H, hs_hi[cur][w->L - 1], hs_lo[cur][w->L - 1], w->H, Wv_hi, Wv_lo, w->H, w->bv, K,
                                cand_val, cand_idx, val, idx, out_stride, tok, tok_stride, part_stats, row_max, row_sum, s);
   }
@@ -627,6 +873,40 @@ extern "C" {
 
 int st_debug_decode_table(int mode) {
   st::g_force_table = mode;
+  return ST_OK;
+}
+
+int st_row_norm_max(const float* W, int rows, int cols, float* out, st_stream_t stream) {
+  using namespace st;
+  ST_REQUIRE(W && out, ST_ERR_NULL, "st_row_norm_max: NULL pointer");
+  ST_REQUIRE(rows >= 1 && cols >= 1, ST_ERR_BAD_SHAPE, "st_row_norm_max: rows=%d cols=%d", rows, cols);
+  cudaStream_t s = as_stream(stream);
+  ST_CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(float), s));
+  row_norm_max_kernel<<<(rows + 7) / 8, 256, 0, s>>>(W, rows, cols, out);
+  ST_LAUNCH_TRY("row_norm_max_kernel");
+  return ST_OK;
+}
+
+int st_vocab_topk_screen(int M, int V, int H, const float* h, const void* h_bf16, const float* Wv, const void* Wv_bf16,
+                         const float* bv, const float* wmax, int K, float* cand_val, int32_t* cand_idx, float* val,
+                         int32_t* idx, int out_stride, int64_t* tok, int tok_stride, st_stream_t stream) {
+  using namespace st;
+  ST_REQUIRE(h && h_bf16 && Wv && Wv_bf16 && bv && wmax && cand_val && cand_idx && (val || idx || tok), ST_ERR_NULL,
+             "st_vocab_topk_screen: NULL pointer");
+  ST_REQUIRE(M >= 1 && V >= 1 && H >= 8 && H % 8 == 0 && H <= 1536 && K >= 1 && K <= 8 && K <= V &&
+                 (!(val || idx) || out_stride >= K) && (!tok || tok_stride >= 1),
+             ST_ERR_BAD_SHAPE, "st_vocab_topk_screen: M=%d V=%d H=%d K=%d", M, V, H, K);
+  int npart = 0;
+  ST_TRY(st_gemm_bf16_screen(M, V, H, h_bf16, H, Wv_bf16, H, bv, cand_val, cand_idx, &npart, stream));
+  const int part_cols = V > 128 ? 128 : 64;
+  screen_select_kernel<<<(M + 7) / 8, 256, (size_t)8 * H * sizeof(float), as_stream(stream)>>>(
+      M, H, V, npart, part_cols, K, cand_val, cand_idx, h, Wv, bv, wmax, val, idx, out_stride, tok, tok_stride);
+  ST_LAUNCH_TRY("screen_select_kernel");
+  return ST_OK;
+}
+
+int st_debug_decode_screen(int mode) {
+  st::g_screen = mode;
   return ST_OK;
 }
 

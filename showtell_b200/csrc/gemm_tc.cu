@@ -61,7 +61,7 @@ struct PairCfg {
   static constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + STG_BYTES + 256;
 };
 
-enum { EPI_STORE = 0, EPI_CE_FWD = 1, EPI_CE_BWD = 2, EPI_TOPK = 3 };
+enum { EPI_STORE = 0, EPI_CE_FWD = 1, EPI_CE_BWD = 2, EPI_TOPK = 3, EPI_TOPS = 4 };   // TOPS: screening, ST_SCREEN_SLOTS per part
 constexpr int TOPK_SLOTS = 8;   // per-row candidates kept per epilogue warp (K <= 8 on the fused path)
 int g_variant = 0;   // st_debug_gemm_variant: 0 = choose, 128 / 256 = single-CTA tile width, 2 = CTA pairs
 int g_streamk = 1;   // st_debug_gemm_variant(v | 0x1000) turns stream-K off
@@ -124,10 +124,12 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tbase,
   const bool row_ok = row < p.M;
   const uint32_t stg_s = smem_u32(stg);
   float run_m = -FLT_MAX, run_s = 0.f, tl = 0.f;  // EPI_CE_FWD
-  float tkv[TOPK_SLOTS];                            // EPI_TOPK: this row's best TOPK_SLOTS logits of the warp's columns,
-  int tki[TOPK_SLOTS];                              // descending; equal values keep the lower column first
+  constexpr bool TOPX = EPI == EPI_TOPK || EPI == EPI_TOPS;
+  constexpr int TS = (EPI == EPI_TOPS) ? (int)ST_SCREEN_SLOTS : TOPK_SLOTS;   // candidates kept per (row, part)
+  float tkv[TS];                                    // EPI_TOPK / TOPS: this row's best TS logits of the warp's columns,
+  int tki[TS];                                      // descending; equal values keep the lower column first
 #pragma unroll
-  for (int q = 0; q < TOPK_SLOTS; ++q) { tkv[q] = -FLT_MAX; tki[q] = 0x7fffffff; }
+  for (int q = 0; q < TS; ++q) { tkv[q] = -FLT_MAX; tki[q] = 0x7fffffff; }
   bool have_tl = false;
   int tgt = -1;
   float lse_l2 = 0.f;
@@ -241,10 +243,10 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tbase,
             }
         }
       }
-    } else if (EPI == EPI_TOPK) {
+    } else if (TOPX) {
       // rnn.py:51,63,90-91: arg-max / top-K of the vocabulary logits without writing them.  Columns arrive in
       // increasing order, so a strict '>' keeps the lower index among equal values (torch.max's first-maximum rule).
-      if (p.pmax) {   // beam_search.py:84-88 ranks by soft-max probability: keep the normaliser's partials too
+      if (EPI == EPI_TOPK && p.pmax) {   // beam_search.py:84-88 ranks by soft-max probability: keep the normaliser's partials too
         float cm = -FLT_MAX;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
@@ -260,10 +262,10 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tbase,
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float x = (full || nb + j < p.N) ? v[j] : -FLT_MAX;
-        if (x > tkv[TOPK_SLOTS - 1]) {
-          tkv[TOPK_SLOTS - 1] = x; tki[TOPK_SLOTS - 1] = nb + j;
+        if (x > tkv[TS - 1]) {
+          tkv[TS - 1] = x; tki[TS - 1] = nb + j;
 #pragma unroll
-          for (int q = TOPK_SLOTS - 1; q > 0; --q) {
+          for (int q = TS - 1; q > 0; --q) {
             if (tkv[q] > tkv[q - 1]) {
               const float tv = tkv[q]; tkv[q] = tkv[q - 1]; tkv[q - 1] = tv;
               const int ti = tki[q]; tki[q] = tki[q - 1]; tki[q - 1] = ti;
@@ -361,13 +363,13 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tbase,
       }
     }
   }
-  if (EPI == EPI_TOPK && row_ok) {
+  if (TOPX && row_ok) {
     float* ov = p.tk_val + ((size_t)row * p.npart + part) * p.tk_k;
     int32_t* oi = p.tk_idx + ((size_t)row * p.npart + part) * p.tk_k;
 #pragma unroll
-    for (int q = 0; q < TOPK_SLOTS; ++q)
+    for (int q = 0; q < TS; ++q)
       if (q < p.tk_k) { ov[q] = tkv[q]; oi[q] = tki[q]; }
-    if (p.pmax) {
+    if (EPI == EPI_TOPK && p.pmax) {
       p.pmax[(size_t)row * p.npart + part] = run_m;
       p.psum[(size_t)row * p.npart + part] = run_s;
     }
@@ -1341,6 +1343,20 @@ int st_gemm_tf32x3_topk(int M, int N, int K, const float* A_hi, const float* A_l
 int st_gemm_set_sm_limit(int n) {
   st::g_sm_limit = n > 0 ? n : 0;
   return ST_OK;
+}
+
+int st_gemm_bf16_screen(int M, int N, int K, const void* A, int lda, const void* B, int ldb, const float* bias,
+                        float* cand_val, int32_t* cand_idx, int* npart_out, st_stream_t stream) {
+  using namespace st;
+  ST_REQUIRE(A && B && cand_val && cand_idx && npart_out, ST_ERR_NULL, "st_gemm_bf16_screen: NULL pointer");
+  ST_REQUIRE(M >= 1 && N >= 1 && K >= 1, ST_ERR_BAD_SHAPE, "st_gemm_bf16_screen: M=%d N=%d K=%d", M, N, K);
+  TcParams p{};
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.alpha = 1.f;
+  p.tk_val = cand_val; p.tk_idx = cand_idx; p.tk_k = ST_SCREEN_SLOTS;
+  const int bn = N > 128 ? 256 : 128;
+  p.npart = 2 * ((N + bn - 1) / bn);
+  *npart_out = p.npart;
+  return launch_tc<EPI_TOPS>(p, A, lda, B, ldb, as_stream(stream), bn);
 }
 
 int st_debug_gemm_variant(int variant) {

@@ -414,6 +414,28 @@ def gemm_tf32x3_topk(A, B, K_top, *, bias=None, want_tokens=False, want_stats=Fa
     return out
 
 
+def vocab_topk_screen(h, Wv, bv, K_top, want_tokens=False):
+    """Exact per-row top-K of h . Wv^T + bv through the bf16 screening GEMM + fp32 re-scoring (st_vocab_topk_screen).
+    h (M, H), Wv (V, H), bv (V) fp32.  Returns (val (M,K) f32, idx (M,K) i32[, tok (M,) i64])."""
+    lib = _lib.load()
+    M, H = h.shape
+    V = Wv.shape[0]
+    dev = h.device
+    hb, Wb = h.to(torch.bfloat16).contiguous(), Wv.to(torch.bfloat16).contiguous()
+    wmax = torch.zeros(1, dtype=F32, device=dev)
+    check(lib.st_row_norm_max(ptr(Wv, F32), V, H, ptr(wmax), stream_ptr()), "st_row_norm_max")
+    parts = lib.st_topk_parts(V)
+    cv = torch.empty(M, parts, dtype=F32, device=dev)
+    ci = torch.empty(M, parts, dtype=I32, device=dev)
+    val = torch.empty(M, K_top, dtype=F32, device=dev)
+    idx = torch.empty(M, K_top, dtype=I32, device=dev)
+    tok = torch.empty(M, dtype=I64, device=dev) if want_tokens else None
+    check(lib.st_vocab_topk_screen(M, V, H, ptr(h, F32), ptr(hb), ptr(Wv, F32), ptr(Wb), ptr(bv, F32), ptr(wmax), int(K_top),
+                                   ptr(cv), ptr(ci), ptr(val), ptr(idx), K_top, ptr(tok), 1, stream_ptr()),
+          "st_vocab_topk_screen")
+    return (val, idx, tok) if want_tokens else (val, idx)
+
+
 def cast_bf16(src, want=True, want_t=False):
     """fp32 (R,C) -> (bf16 (R,C) or None, bf16 transpose (C,R) or None).  Leading dimensions are
     padded to multiples of 8 so the results are valid TMA operands; the returned tensors are the

@@ -247,17 +247,20 @@ def _parity_train(kind, E, H, V, L, B, T, ragged, dtype, TOL):
     assert rel_err(logits, ex["logits"]) < TOL
 
 
-@pytest.mark.parametrize("gemm,table", [("fp32", 0), ("tf32x3", -1), ("tf32x3", 1)])
+@pytest.mark.parametrize("gemm,table", [("fp32", 0), ("tf32x3", -1), ("tf32x3", 1), ("tf32x3", 3)])
 @pytest.mark.parametrize("kind,L", [("gru", 1), ("lstm", 1), ("gru", 2), ("lstm", 2)])
 def test_oracle_parity_greedy_full_size(kind, L, gemm, table, table_mode):
     dev = torch.device("cuda:0")
     m, feat, _, _ = _random_case(kind, 512, 512, 10000, L, 16, 20, 11, False)
     m.decode_gemm = gemm
-    table_mode(table)
+    from showtell_b200 import _lib
+    _lib.load().st_debug_decode_screen(-1 if table == 3 else 0)     # 3: table + the 3xTF32 fused arg-max instead of screening
+    table_mode(1 if table == 3 else table)
     p = {k: v.detach().clone() for k, v in m.state_dict().items()}
     with torch.no_grad():
         ref = O.rnn_greedy(p, kind, feat)
     tok = m.to(dev).sentence_index(feat.to(dev))
+    _lib.load().st_debug_decode_screen(0)
     assert np.array_equal(tok.cpu().numpy(), ref.numpy())
 
 

@@ -139,8 +139,9 @@ def test_attention_fp32_kink_tensors(model, B, T, P):
         assert_close_with_kink_bound(n + " (reference fp32 GPU)", ggpu[n], g64[n], bnd, 1e-4)
 
 
-@pytest.mark.parametrize("K,gemm,table", [(3, "tf32x3", -1), (3, "tf32x3", 1), (3, "fp32", 0), (5, "tf32x3", 1), (9, "tf32x3", 1)])
-def test_beam_chain_at_bench_dims(K, gemm, table):
+@pytest.mark.parametrize("K,gemm,table,screen", [(3, "tf32x3", -1, 0), (3, "tf32x3", 1, 0), (3, "tf32x3", 1, -1), (3, "fp32", 0, 0),
+                                                 (5, "tf32x3", 1, 0), (5, "tf32x3", 1, -1), (9, "tf32x3", 1, 0)])
+def test_beam_chain_at_bench_dims(K, gemm, table, screen):
     """BASELINE config 5: chain beam (rnn.py:60-108), E=H=512, V=10000, max_len 20, 64 images in one call.  Every row
     whose rankings are separated by more than the GEMM's rounding noise must equal the oracle's caption token for
     token (asserted inside _check_chain), and at least 90 % of ALL rows must."""
@@ -149,6 +150,7 @@ def test_beam_chain_at_bench_dims(K, gemm, table):
     from test_gpu_base import EPS, _check_chain
     from showtell_b200 import _lib
     _lib.load().st_debug_decode_table(table)   # tf32x3: input projections from the embedding table (1) / per-step GEMM (-1)
+    _lib.load().st_debug_decode_screen(screen)  # tf32x3: vocabulary top-K by bf16 screening + re-scoring (0) / 3xTF32 epilogue (-1)
     torch.manual_seed(13)
     g = torch.Generator().manual_seed(13)
     n = 64
@@ -164,7 +166,8 @@ def test_beam_chain_at_bench_dims(K, gemm, table):
         with torch.no_grad():
             same += int(tok[i].tolist() == O.rnn_beam_chain(p, feat[i:i + 1], K, 20).tolist())
     _lib.load().st_debug_decode_table(0)
-    print(f"\nbeam-{K} ({gemm}, table {table}), {n} images at bench dims: {same}/{n} captions identical to the oracle, "
+    _lib.load().st_debug_decode_screen(0)
+    print(f"\nbeam-{K} ({gemm}, table {table}, screen {screen}), {n} images at bench dims: {same}/{n} captions identical to the oracle, "
           f"{full}/{n} separated by > {EPS[gemm]:g} in every round (all of those identical)")
     # wider beams rank more candidates per round, so more rounds hang on a margin inside the rounding noise
     assert same >= 0.9 * n and full >= (0.5 if K <= 5 else 0.25) * n

@@ -425,3 +425,37 @@ def test_gemm_tf32x3_fused_topk(M, N, K, topk):
     assert torch.equal(rmax, full.max(1)[0])                        # soft-max normaliser of the same logits
     lse = rmax.double() + rsum.double().log()
     assert float((lse - torch.logsumexp(full.double(), 1)).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("M,V,H,topk,cluster", [(64, 1000, 64, 3, 0), (300, 10000, 512, 5, 0), (4096, 10000, 512, 3, 0),
+                                                (257, 10000, 512, 1, 0), (128, 10000, 512, 3, 12), (100, 300, 128, 8, 20)])
+def test_vocab_topk_screen_is_exact(M, V, H, topk, cluster):
+    """bf16 screening + fp32 re-scoring (st_vocab_topk_screen) returns the exact top-K of the fp32 logits: compared with
+    float64 logits wherever the decisive margins exceed fp32 rounding noise.  `cluster` columns of ONE 128-column part
+    are near-copies of the row's best column (relative perturbation 1e-4, far inside the bf16 error band): more
+    survivors than a part keeps, which forces the re-score-the-whole-part path."""
+    from showtell_b200 import ops
+    g = torch.Generator().manual_seed(M + V + H + topk)
+    h = torch.tanh(torch.randn(M, H, generator=g)).to(DEV)
+    W = ((torch.rand(V, H, generator=g) * 2 - 1) / H ** 0.5).to(DEV)
+    b = ((torch.rand(V, generator=g) * 2 - 1) / H ** 0.5).to(DEV)
+    if cluster:
+        base = int(torch.argmax((h[:1].double() @ W.double().t() + b.double())[0]))
+        lo = (base // 128) * 128
+        cols = [c for c in range(lo, min(V, lo + 128)) if c != base][:cluster]
+        for j, c in enumerate(cols):
+            W[c] = W[base] * (1.0 + 1e-4 * (j + 1) * (-1) ** j)
+            b[c] = b[base]
+        h[1:] = h[:1] + 1e-3 * torch.randn(M - 1, H, generator=g).to(DEV)     # every row sees the same crowd at the top
+    val, idx, tok = ops.vocab_topk_screen(h, W, b, topk, want_tokens=True)
+    ref = h.double() @ W.double().t() + b.double()
+    rv, ri = torch.sort(ref, dim=1, descending=True, stable=True)
+    # rows whose first topk + 1 reference values are separated by more than fp32 noise must match index for index
+    noise = 2e-6 * ref.abs().max()
+    sep = ((rv[:, :topk] - rv[:, 1:topk + 1]) > noise).all(dim=1)
+    assert int(sep.sum()) >= 0.8 * M, int(sep.sum())
+    assert torch.equal(idx.long()[sep], ri[:, :topk][sep])
+    assert torch.equal(tok[sep], ri[:, 0][sep])
+    assert float((val.double() - torch.gather(ref, 1, idx.long())).abs().max()) < noise   # the values are the logits of the returned columns
+    # and on every row the returned values are the K largest up to that noise
+    assert float((val.double() - rv[:, :topk]).abs().max()) < 2 * noise
