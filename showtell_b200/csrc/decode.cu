@@ -120,35 +120,56 @@ __global__ void __launch_bounds__(256) decode_gate_kernel(int rows, int H, GxSrc
                                                           const float* __restrict__ c_prev, float* __restrict__ h_out,
                                                           float* __restrict__ c_out, float* __restrict__ h_hi,
                                                           float* __restrict__ h_lo, __nv_bfloat16* __restrict__ h_bf) {
-  const long long n = (long long)rows * H;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(i / H), u = (int)(i - (long long)r * H);
+  // a thread owns 4 adjacent hidden units of one row (H % 4 == 0: every access is a 16-byte vector)
+  const int H4 = H >> 2;
+  const long long n4 = (long long)rows * H4;
+  for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i4 / H4), u = (int)(i4 - (long long)r * H4) * 4;
     int64_t gr = r;
     if (src.tok)
       gr = src.tok64 ? reinterpret_cast<const int64_t*>(src.tok)[(size_t)r * src.stride]
                      : (int64_t) reinterpret_cast<const int32_t*>(src.tok)[(size_t)r * src.stride];
-    const float* gx = src.gx + (size_t)gr * G * H;
-    const float* gh = Gh ? Gh + (size_t)r * G * H : bhh;
-    float hv;
-    if (G == 4) {
-      const float ig = sigmoidf_(gx[u] + gh[u]);
-      const float fg = sigmoidf_(gx[H + u] + gh[H + u]);
-      const float gg = tanhf(gx[2 * H + u] + gh[2 * H + u]);
-      const float og = sigmoidf_(gx[3 * H + u] + gh[3 * H + u]);
-      const float cp = c_prev ? c_prev[i] : 0.f;
-      const float c2 = fmaf(fg, cp, ig * gg);
-      c_out[i] = c2;
-      hv = og * tanhf(c2);
-    } else {
-      const float rr = sigmoidf_(gx[u] + gh[u]);
-      const float zz = sigmoidf_(gx[H + u] + gh[H + u]);
-      const float nn = tanhf(fmaf(rr, gh[2 * H + u], gx[2 * H + u]));
-      const float hp = h_prev ? h_prev[i] : 0.f;
-      hv = fmaf(zz, hp - nn, nn);
+    const float* gx = src.gx + (size_t)gr * G * H + u;
+    const float* gh = (Gh ? Gh + (size_t)r * G * H : bhh) + u;
+    float x[G][4], y[G][4];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float4 a = *reinterpret_cast<const float4*>(gx + g * H), b = *reinterpret_cast<const float4*>(gh + g * H);
+      x[g][0] = a.x; x[g][1] = a.y; x[g][2] = a.z; x[g][3] = a.w;
+      y[g][0] = b.x; y[g][1] = b.y; y[g][2] = b.z; y[g][3] = b.w;
     }
-    h_out[i] = hv;
-    split_store(hv, h_hi + i, h_lo + i);
-    if (h_bf) h_bf[i] = __float2bfloat16(hv);       // operand of the screening GEMM (top layer)
+    const size_t i = (size_t)r * H + u;
+    float prev[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* pp = (G == 4) ? c_prev : h_prev;
+    if (pp) { const float4 v = *reinterpret_cast<const float4*>(pp + i); prev[0] = v.x; prev[1] = v.y; prev[2] = v.z; prev[3] = v.w; }
+    float hv[4], cv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (G == 4) {
+        const float ig = sigmoidf_(x[0][k] + y[0][k]);
+        const float fg = sigmoidf_(x[1][k] + y[1][k]);
+        const float gg = tanhf(x[2][k] + y[2][k]);
+        const float og = sigmoidf_(x[G - 1][k] + y[G - 1][k]);
+        cv[k] = fmaf(fg, prev[k], ig * gg);
+        hv[k] = og * tanhf(cv[k]);
+      } else {
+        const float rr = sigmoidf_(x[0][k] + y[0][k]);
+        const float zz = sigmoidf_(x[1][k] + y[1][k]);
+        const float nn = tanhf(fmaf(rr, y[2][k], x[2][k]));
+        hv[k] = fmaf(zz, prev[k] - nn, nn);
+      }
+    }
+    if (G == 4) *reinterpret_cast<float4*>(c_out + i) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+    *reinterpret_cast<float4*>(h_out + i) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+    float hi[4], lo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) split_store(hv[k], &hi[k], &lo[k]);
+    *reinterpret_cast<float4*>(h_hi + i) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<float4*>(h_lo + i) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    if (h_bf) {      // operand of the screening GEMM (top layer)
+      const __nv_bfloat162 p0 = __floats2bfloat162_rn(hv[0], hv[1]), p1 = __floats2bfloat162_rn(hv[2], hv[3]);
+      *reinterpret_cast<uint2*>(h_bf + i) = make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+    }
   }
 }
 
@@ -477,7 +498,7 @@ struct Rig {
   // ---- tensor-core loop
   int gate(int l, GxSrc src, bool first, int nxt) {
     const int H = w->H;
-    const long long n = (long long)rows * H;
+    const long long n = (long long)rows * (H / 4);          // a thread per 4 units (use_tc: H % 4 == 0)
     int sms = 0;
     ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
     const long long blocks = (n + 255) / 256;
