@@ -47,6 +47,18 @@ enum { ST_MAX_STEPS = 128 }; /* longest padded caption the sequence kernels acce
 
 int st_version(void);
 const char* st_last_error(void);
+/* ---- collate on the device (utils.py:61-77 `create_batch`): samples sorted by caption length, longest first, ties in
+ * their original order (Python's stable sort).  lengths (B) int64 on the device -> perm (B): sorted position r holds
+ * original sample perm[r]; sorted_len (B); batch_sizes (T) int32 = #{i : len_i > t} (what rnn.py:31's
+ * pack_padded_sequence derives).  T may be 0 (no batch_sizes). */
+int st_collate_sort(const int64_t* lengths, int B, int T, int64_t* perm, int64_t* sorted_len, int32_t* batch_sizes,
+                    st_stream_t stream);
+/* dst row r = src row perm[r] for rows of row_bytes bytes (features of any dtype / shape; rows <= 65535). */
+int st_gather_rows_bytes(void* dst, const void* src, const int64_t* perm, int rows, int64_t row_bytes, st_stream_t stream);
+/* The sorted caption matrix, re-padded with zeros from each caption's length on (utils.py:72-75):
+ * dst (B, T_out) <- src (B, T_in) rows perm[r]. */
+int st_collate_captions(int64_t* dst, const int64_t* src, const int64_t* perm, const int64_t* sorted_len, int B, int T_in,
+                        int T_out, st_stream_t stream);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t st_launch_count(void);
 /* Development / test aid: programmatic dependent launch of the per-step kernels on (default) / off. */

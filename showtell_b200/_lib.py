@@ -44,6 +44,9 @@ _SIGS = {
     "st_split_tf32": (_I, [_P, _I, _I, _I, _P, _P, _I, _P]),
     "st_gemm_tf32x3": (_I, [_I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _P, _F, _F, _P]),
     "st_topk_parts": (_I, [_I]),
+    "st_collate_sort": (_I, [_P, _I, _I, _P, _P, _P, _P]),
+    "st_gather_rows_bytes": (_I, [_P, _P, _P, _I, C.c_int64, _P]),
+    "st_collate_captions": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "st_debug_decode_table": (_I, [_I]),
     "st_debug_decode_screen": (_I, [_I]),
     "st_row_norm_max": (_I, [_P, _I, _I, _P, _P]),

@@ -31,17 +31,66 @@ def sort_batch(features, captions, lengths):
     """features (B, ...), captions (B, T) int64 zero-padded, lengths (B,) tensor or list, in ANY order ->
     (features, captions[:, :max_len], lengths list, perm) in the decoder's order (length-descending, stable).
     `perm` (B,) int64 on the tensors' device maps sorted row i to original row perm[i]: `out[perm] = sorted_out`
-    restores the caller's order (e.g. for the tokens of `sentence_index`)."""
+    restores the caller's order (e.g. for the tokens of `sentence_index`).
+    CUDA tensors: the library's collate kernels (st_collate_sort: stable rank by counting, st_gather_rows_bytes,
+    st_collate_captions); CPU tensors (host-side use, tests): torch.sort + index_select."""
     dev = captions.device
     L = torch.as_tensor(lengths, dtype=torch.int64, device=dev)
     if L.dim() != 1 or L.shape[0] != captions.shape[0] or features.shape[0] != captions.shape[0]:
         raise ValueError("sort_batch: features, captions and lengths must agree on the batch size")
     if L.numel() == 0:
         raise RuntimeError("empty batch")
+    if captions.is_cuda:
+        return _sort_batch_cuda(features, captions, L)
     Ls, perm = torch.sort(L, descending=True, stable=True)
     lens = [int(x) for x in Ls.tolist()]                       # the only device -> host traffic: B integers
+    _check_lengths(lens, captions.shape[1])
+    return (features.index_select(0, perm), captions.index_select(0, perm)[:, :lens[0]].contiguous(), lens, perm)
+
+
+def _check_lengths(lens, width):
     if lens[-1] <= 0:
         raise RuntimeError("Length of all samples has to be greater than 0")
-    if lens[0] > captions.shape[1]:
+    if lens[0] > width:
         raise ValueError("sort_batch: a length exceeds the padded caption width")
-    return (features.index_select(0, perm), captions.index_select(0, perm)[:, :lens[0]].contiguous(), lens, perm)
+
+
+def _sort_batch_cuda(features, captions, L):
+    from . import _lib
+    from ._lib import check, ptr, stream_ptr
+    lib = _lib.load()
+    if not features.is_cuda:
+        raise RuntimeError("sort_batch: features and captions must live on the same device")
+    B, T = captions.shape
+    if B > 65535:
+        raise ValueError("sort_batch: at most 65535 samples per batch")
+    dev = captions.device
+    captions = captions.contiguous()
+    features = features.contiguous()
+    L = L.contiguous()
+    perm = torch.empty(B, dtype=torch.int64, device=dev)
+    Ls = torch.empty(B, dtype=torch.int64, device=dev)
+    check(lib.st_collate_sort(ptr(L), B, 0, ptr(perm), ptr(Ls), None, stream_ptr()), "st_collate_sort")
+    lens = [int(x) for x in Ls.tolist()]                       # the only device -> host traffic: B integers
+    _check_lengths(lens, T)
+    cap = torch.empty(B, lens[0], dtype=torch.int64, device=dev)
+    check(lib.st_collate_captions(ptr(cap), ptr(captions), ptr(perm), ptr(Ls), B, T, lens[0], stream_ptr()), "st_collate_captions")
+    feat = torch.empty_like(features)
+    row_bytes = features[0].numel() * features.element_size()
+    check(lib.st_gather_rows_bytes(ptr(feat), ptr(features), ptr(perm), B, row_bytes, stream_ptr()), "st_gather_rows_bytes")
+    return feat, cap, lens, perm
+
+
+def device_batch_sizes(lengths_dev, T):
+    """batch_sizes (T,) int32 on the device for (unsorted) device lengths: #{i : len_i > t} (rnn.py:31's
+    pack_padded_sequence derives the same numbers from the sorted lengths)."""
+    from . import _lib
+    from ._lib import check, ptr, stream_ptr
+    lib = _lib.load()
+    L = lengths_dev.to(torch.int64).contiguous()
+    B = L.shape[0]
+    perm = torch.empty(B, dtype=torch.int64, device=L.device)
+    Ls = torch.empty(B, dtype=torch.int64, device=L.device)
+    bs = torch.empty(T, dtype=torch.int32, device=L.device)
+    check(lib.st_collate_sort(ptr(L), B, int(T), ptr(perm), ptr(Ls), ptr(bs), stream_ptr()), "st_collate_sort")
+    return bs

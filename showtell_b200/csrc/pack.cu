@@ -277,10 +277,114 @@ __global__ void __launch_bounds__(256) scale_multi_kernel(const ScaleTable tab, 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- collate (utils.py:61-77)
+// create_batch sorts the samples by caption length, longest first, with Python's STABLE sort: the position of sample i
+// is  #{j : len_j > len_i} + #{j < i : len_j == len_i}.  One thread per sample counts both over all B lengths (staged
+// through shared memory); B is a data-loader batch, so the B^2 compares are microseconds.  batch_sizes[t] =
+// #{i : len_i > t} is what pack_padded_sequence (rnn.py:31) derives from the sorted lengths.
+__global__ void __launch_bounds__(256) collate_rank_kernel(const int64_t* __restrict__ len, int B, int64_t* __restrict__ perm,
+                                                           int64_t* __restrict__ sorted_len) {
+  __shared__ int64_t tile[256];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int64_t mine = i < B ? len[i] : 0;
+  int rank = 0;
+  for (int j0 = 0; j0 < B; j0 += 256) {
+    __syncthreads();
+    tile[threadIdx.x] = j0 + threadIdx.x < B ? len[j0 + threadIdx.x] : INT64_MIN;
+    __syncthreads();
+    const int n = min(256, B - j0);
+    for (int j = 0; j < n; ++j) {
+      const int64_t o = tile[j];
+      rank += (o > mine) || (o == mine && j0 + j < i);
+    }
+  }
+  if (i < B) {
+    perm[rank] = i;
+    sorted_len[rank] = mine;
+  }
+}
+
+__global__ void __launch_bounds__(256) collate_batch_sizes_kernel(const int64_t* __restrict__ len, int B, int T,
+                                                                  int32_t* __restrict__ batch_sizes) {
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= T) return;
+  int n = 0;
+  for (int i = 0; i < B; ++i) n += len[i] > t;
+  batch_sizes[t] = n;
+}
+
+// dst row r = src row perm[r], 16 bytes per thread step (rows are multiples of 16 bytes and 16-byte aligned) or bytewise
+__global__ void __launch_bounds__(256) gather_rows_bytes_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src,
+                                                                const int64_t* __restrict__ perm, long long row_bytes, int vec) {
+  const long long r = blockIdx.y;
+  const uint8_t* s = src + (size_t)perm[r] * row_bytes;
+  uint8_t* d = dst + (size_t)r * row_bytes;
+  if (vec) {
+    const long long n16 = row_bytes >> 4;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n16; i += (long long)gridDim.x * 256)
+      reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(s)[i];
+  } else {
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < row_bytes; i += (long long)gridDim.x * 256) d[i] = s[i];
+  }
+}
+
+// sorted, re-padded caption matrix: dst (B, T_out) <- src (B, T_in) rows perm[r], zeros from the caption's length on
+// (utils.py:72-75 builds the padded matrix from zeros)
+__global__ void __launch_bounds__(256) collate_captions_kernel(int64_t* __restrict__ dst, const int64_t* __restrict__ src,
+                                                               const int64_t* __restrict__ perm,
+                                                               const int64_t* __restrict__ sorted_len, int T_in, int T_out) {
+  const int r = blockIdx.x;
+  const int64_t* s = src + (size_t)perm[r] * T_in;
+  const int64_t n = sorted_len[r];
+  for (int t = threadIdx.x; t < T_out; t += 256) dst[(size_t)r * T_out + t] = (t < n && t < T_in) ? s[t] : 0;
+}
+
 }  // namespace
 }  // namespace st
 
 extern "C" {
+
+int st_collate_sort(const int64_t* lengths, int B, int T, int64_t* perm, int64_t* sorted_len, int32_t* batch_sizes,
+                    st_stream_t stream) {
+  using namespace st;
+  ST_REQUIRE(lengths && perm && sorted_len, ST_ERR_NULL, "st_collate_sort: NULL pointer");
+  ST_REQUIRE(B >= 1 && T >= 0 && (T == 0 || batch_sizes), ST_ERR_BAD_SHAPE, "st_collate_sort: B=%d T=%d", B, T);
+  cudaStream_t s = as_stream(stream);
+  collate_rank_kernel<<<(B + 255) / 256, 256, 0, s>>>(lengths, B, perm, sorted_len);
+  ST_LAUNCH_TRY("collate_rank_kernel");
+  if (T > 0) {
+    collate_batch_sizes_kernel<<<(T + 255) / 256, 256, 0, s>>>(lengths, B, T, batch_sizes);
+    ST_LAUNCH_TRY("collate_batch_sizes_kernel");
+  }
+  return ST_OK;
+}
+
+int st_gather_rows_bytes(void* dst, const void* src, const int64_t* perm, int rows, int64_t row_bytes, st_stream_t stream) {
+  using namespace st;
+  ST_REQUIRE(dst && src && perm, ST_ERR_NULL, "st_gather_rows_bytes: NULL pointer");
+  ST_REQUIRE(rows >= 1 && rows <= 65535 && row_bytes >= 1, ST_ERR_BAD_SHAPE, "st_gather_rows_bytes: rows=%d row_bytes=%lld",
+             rows, (long long)row_bytes);
+  const int vec = (row_bytes % 16 == 0) && (reinterpret_cast<uintptr_t>(dst) % 16 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0);
+  const long long units = vec ? row_bytes / 16 : row_bytes;
+  const unsigned gx = (unsigned)((units + 255) / 256 < 64 ? (units + 255) / 256 : 64);
+  gather_rows_bytes_kernel<<<dim3(gx, rows), 256, 0, as_stream(stream)>>>(reinterpret_cast<uint8_t*>(dst),
+                                                                          reinterpret_cast<const uint8_t*>(src), perm, row_bytes, vec);
+  ST_LAUNCH_TRY("gather_rows_bytes_kernel");
+  return ST_OK;
+}
+
+int st_collate_captions(int64_t* dst, const int64_t* src, const int64_t* perm, const int64_t* sorted_len, int B, int T_in,
+                        int T_out, st_stream_t stream) {
+  using namespace st;
+  ST_REQUIRE(dst && src && perm && sorted_len, ST_ERR_NULL, "st_collate_captions: NULL pointer");
+  ST_REQUIRE(B >= 1 && T_in >= 1 && T_out >= 1, ST_ERR_BAD_SHAPE, "st_collate_captions: B=%d T_in=%d T_out=%d", B, T_in, T_out);
+  collate_captions_kernel<<<B, 256, 0, as_stream(stream)>>>(dst, src, perm, sorted_len, T_in, T_out);
+  ST_LAUNCH_TRY("collate_captions_kernel");
+  return ST_OK;
+}
+
+
 
 int st_pack_inputs(float* X, int ldx, const float* emb, int E, int V, const float* feature,
                    const int64_t* caption, int T_cap, int with_feature, int nsteps,
