@@ -408,6 +408,10 @@ int st_attn_relayout(const float* f, int B, int C, int P, void* F, void* FT, int
  * produces it; halves the largest host-to-device / HBM read of the step). */
 int st_attn_relayout_bf16in(const void* f_bf16, int B, int C, int P, void* F, void* FT, int ldft, int out_bf16,
                             float* mean_f, st_stream_t stream);
+/* Channels-last grids: a trunk run in torch.channels_last hands the decoder (B, P, C) = F itself -- no re-layout pass;
+ * this is the one thing still needed from the grid: mean_f (B, C) fp32 = the channel means over the P locations
+ * (rnn_attn.py:62).  F fp32 or bf16, contiguous. */
+int st_grid_mean_bpc(const void* F, int f_bf16, int B, int P, int C, float* mean_f, st_stream_t stream);
 int st_attn_step_fwd(int rows, int P, int A, int E, const void* att1, const void* Fe, int in_bf16,
                      const float* att2, const float* wf, const float* bf, const float* b_embed, float* alphas,
                      int alpha_stride, float* S, float* ctx_out, int ld_ctx, void* ctx_out_bf16, int ld_ctx_bf16,

@@ -91,6 +91,7 @@ _SIGS = {
     "st_shift_states": (_I, [_P, _P, _P, _I, _I, _IP, _P]),
     "st_shift_states_bf16": (_I, [_P, _P, _P, _I, _I, _IP, _P]),
     "st_attn_relayout": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
+    "st_grid_mean_bpc": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "st_attn_relayout_bf16in": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
     "st_attn_step_fwd": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _P, _I, _I, _P]),
     "st_attn_step_bwd": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _I, _P]),

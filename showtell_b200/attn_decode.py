@@ -13,15 +13,22 @@ F32, I64 = torch.float32, torch.int64
 def greedy(mod, feature, start_id, max_len):
     if not feature.is_cuda:
         raise RuntimeError("showtell_b200 runs on CUDA tensors only (no CPU fallback)")
-    if feature.dim() != 3 or feature.shape[1] != mod.nos_filters:
-        raise ValueError(f"cnn_feature must be (B, {mod.nos_filters}, P)")
+    from .attn_engine import grid_layout
+    lay = grid_layout(mod)                                 # "BCP" channels-first (the reference) / "BPC" channels-last
+    if feature.dim() != 3 or feature.shape[2 if lay == "BPC" else 1] != mod.nos_filters:
+        raise ValueError(f"cnn_feature must be (B, {mod.nos_filters}, P)" if lay == "BCP" else
+                         f"cnn_feature must be (B, P, {mod.nos_filters})")
     P = {n: p.detach() for n, p in mod.named_parameters()}
     kind, L = mod._kind, mod.num_layers
     f = feature.detach().contiguous().to(F32)
-    B, C, Pn = f.shape
     E, H = mod.embed_dim, mod.num_hidden_units
     dev = f.device
-    F, _, mean_f = ops.attn_relayout(f, bf16=False, want_t=False)
+    if lay == "BPC":
+        B, Pn, C = f.shape
+        F, mean_f = ops.attn_grid_bpc(f, bf16=False)
+    else:
+        B, C, Pn = f.shape
+        F, _, mean_f = ops.attn_relayout(f, bf16=False, want_t=False)
     h = [ops.sgemm(mean_f, P["init_h.weight"], transB=True, bias=P["init_h.bias"])] * L
     c = [ops.sgemm(mean_f, P["init_c.weight"], transB=True, bias=P["init_c.bias"])] * L if kind == _lib.ST_LSTM \
         else [None] * L

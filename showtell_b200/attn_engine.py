@@ -42,9 +42,13 @@ def _use_tc(mode, kind, P, B):
     return (E % 8 == 0 and A % 8 == 0 and H % 8 == 0 and ops.rnn_seq_tc_fits(kind, H, B))
 
 
-def attn_forward(mode, P, kind, L, feature, caption, bs, save):
-    """Returns (Hs_top (N,H), alphas (B,Tcap,P), saved dict)."""
-    B, C, Pn = feature.shape
+def attn_forward(mode, P, kind, L, feature, caption, bs, save, layout="BCP"):
+    """Returns (Hs_top (N,H), alphas (B,Tcap,P), saved dict).  layout: "BCP" = the reference's channels-first grid
+    (cnn_attn.py:49), "BPC" = channels-last (the grid IS the (B*P, C) operand: no re-layout pass)."""
+    if layout == "BPC":
+        B, Pn, C = feature.shape
+    else:
+        B, C, Pn = feature.shape
     T, N, off = len(bs), sum(bs), _offsets(bs)
     Tcap = caption.shape[1]
     E = P["embeddings.weight"].shape[1]
@@ -53,7 +57,10 @@ def attn_forward(mode, P, kind, L, feature, caption, bs, save):
     sv = {"bs": bs, "off": off, "Pn": Pn, "B": B, "tc": tc}
 
     # (no transposed copy of the grid: dW_enc = datt1^T F reads F in place as an MN-major GEMM operand)
-    F, FT, mean_f = ops.attn_relayout(feature, bf16=(mode == "bf16"), want_t=False)
+    if layout == "BPC":
+        (F, mean_f), FT = ops.attn_grid_bpc(feature, bf16=(mode == "bf16")), None
+    else:
+        F, FT, mean_f = ops.attn_relayout(feature, bf16=(mode == "bf16"), want_t=False)
     sv.update(F=F, mean_f=mean_f)
     # rnn_attn.py:62: every layer starts from init_h(mean_P f) (init_c likewise for the LSTM)
     # (a skinny fp32 product: it runs on the side stream beside the hoisted grid projections below)
@@ -370,11 +377,19 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
     return grads
 
 
-def _check_inputs(feature, caption, lengths, C):
+def grid_layout(mod):
+    lay = getattr(mod, "grid_layout", "BCP")
+    if lay not in ("BCP", "BPC"):
+        raise ValueError('grid_layout must be "BCP" (channels-first, the reference) or "BPC" (channels-last)')
+    return lay
+
+
+def _check_inputs(feature, caption, lengths, C, layout="BCP"):
     if not (feature.is_cuda and caption.is_cuda):
         raise RuntimeError("showtell_b200 runs on CUDA tensors only (no CPU fallback)")
-    if feature.dim() != 3 or feature.shape[1] != C:
-        raise ValueError(f"cnn_feature must be (B, {C}, P) channels-first, got {tuple(feature.shape)}")
+    if feature.dim() != 3 or feature.shape[2 if layout == "BPC" else 1] != C:
+        want = f"(B, P, {C}) channels-last" if layout == "BPC" else f"(B, {C}, P) channels-first"
+        raise ValueError(f"cnn_feature must be {want}, got {tuple(feature.shape)}")
     if caption.dim() != 2 or caption.shape[0] != feature.shape[0] or caption.dtype != torch.int64:
         raise ValueError("image_caption must be (B, T) int64")
     if len(lengths) != feature.shape[0]:
@@ -399,9 +414,10 @@ class AttnLogitsFn(torch.autograd.Function):
         f = feature.detach().contiguous()
         f = f if f.dtype == BF16 else f.to(F32)       # bf16 grids (autocast trunk) are consumed as they are
         cap = caption.contiguous()
-        bs = _check_inputs(f, cap, lengths, mod.nos_filters)
+        lay = grid_layout(mod)
+        bs = _check_inputs(f, cap, lengths, mod.nos_filters, lay)
         save = any(ctx.needs_input_grad)
-        Hs, alphas, sv = attn_forward(mode, P, mod._kind, mod.num_layers, f, cap, bs, save)
+        Hs, alphas, sv = attn_forward(mode, P, mod._kind, mod.num_layers, f, cap, bs, save, layout=lay)
         vocab = Linear(mode, P["linear.weight"], P["linear.bias"], save, "vocab")
         logits = vocab.fwd(Hs)                                                        # rnn_attn.py:71,115
         ctx.names, ctx.P, ctx.mod, ctx.vocab, ctx.sv, ctx.caption = names, P, mod, vocab, sv, cap
@@ -435,16 +451,17 @@ class AttnLossFn(torch.autograd.Function):
         f = feature.detach().contiguous()
         f = f if f.dtype == BF16 else f.to(F32)       # bf16 grids (autocast trunk) are consumed as they are
         cap = caption.contiguous()
-        bs = _check_inputs(f, cap, lengths, mod.nos_filters)
+        lay = grid_layout(mod)
+        bs = _check_inputs(f, cap, lengths, mod.nos_filters, lay)
         need = any(ctx.needs_input_grad)
         kind, L = mod._kind, mod.num_layers
         dt = float(denom_tokens if denom_tokens is not None else sum(bs))
         db = float(denom_batch if denom_batch is not None else f.shape[0])
-        coef = float(alpha_c) / (db * f.shape[2])
+        coef = float(alpha_c) / (db * f.shape[1 if lay == "BPC" else 2])
         red = getattr(mod, "grad_reducer", None)       # data parallelism: parallel.GradReducer
 
         def body(feat, capt):
-            Hs, alphas, sv = attn_forward(mode, P, kind, L, feat, capt, bs, need)
+            Hs, alphas, sv = attn_forward(mode, P, kind, L, feat, capt, bs, need, layout=lay)
             target = ops.pack_targets(capt, bs, P["linear.weight"].shape[0])
             gout = red.slots([P["linear.weight"].shape, P["linear.bias"].shape]) if (red is not None and need) else None
             loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, dt, need, gout=gout)
@@ -477,7 +494,7 @@ class AttnLossFn(torch.autograd.Function):
                 g2.update(grads)
             return loss, alphas, g2
 
-        key = ("attn", mode, kind, L, tuple(bs), tuple(f.shape), str(f.dtype), tuple(cap.shape), need, dt, db, float(alpha_c),
+        key = ("attn", mode, kind, L, lay, tuple(bs), tuple(f.shape), str(f.dtype), tuple(cap.shape), need, dt, db, float(alpha_c),
                tuple(p.data_ptr() for p in params))
         loss, alphas, ctx.grads = graphs.run(mod, key, body, (f, cap))
         ctx.names, ctx.mod, ctx.ticket = names, mod, graphs.ticket(mod)

@@ -200,6 +200,23 @@ relayout_fast_kernel(const TI* __restrict__ f, int C, int P, __nv_bfloat16* __re
   }
 }
 
+// Channels-last grids (B, P, C): F = the grid itself; only the channel means over the P locations are needed
+// (rnn_attn.py:62 `cnn_feature.mean(dim=2)` of the channels-first tensor).  Thread per channel, coalesced rows.
+template <typename T>
+__global__ void __launch_bounds__(NT) grid_mean_bpc_kernel(const T* __restrict__ F, int P, int C, float* __restrict__ mean_f) {
+  const int b = blockIdx.y, c = blockIdx.x * NT + threadIdx.x;
+  if (c >= C) return;
+  const T* src = F + (size_t)b * P * C + c;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int p = 0;
+  for (; p + 3 < P; p += 4) {
+    s0 += ldf(src + (size_t)p * C); s1 += ldf(src + (size_t)(p + 1) * C);
+    s2 += ldf(src + (size_t)(p + 2) * C); s3 += ldf(src + (size_t)(p + 3) * C);
+  }
+  for (; p < P; ++p) s0 += ldf(src + (size_t)p * C);
+  mean_f[(size_t)b * C + c] = ((s0 + s1) + (s2 + s3)) / (float)P;
+}
+
 template <typename T, int ACT>
 __global__ void __launch_bounds__(NT)
 attn_step_fwd_kernel(int P, int A, int E, const T* __restrict__ att1, const T* __restrict__ Fe,
@@ -702,6 +719,17 @@ static int relayout_any(const void* f, int f_bf16, int B, int C, int P, void* F,
   else          { if (f_bf16) ST_RELAYOUT(float, __nv_bfloat16); else ST_RELAYOUT(float, float); }
 #undef ST_RELAYOUT
   ST_LAUNCH_TRY("relayout_kernel");
+  return ST_OK;
+}
+
+int st_grid_mean_bpc(const void* F, int f_bf16, int B, int P, int C, float* mean_f, st_stream_t stream) {
+  using namespace st;
+  ST_REQUIRE(F && mean_f, ST_ERR_NULL, "st_grid_mean_bpc: NULL pointer");
+  ST_REQUIRE(B >= 1 && B <= 65535 && P >= 1 && C >= 1, ST_ERR_BAD_SHAPE, "st_grid_mean_bpc: B=%d P=%d C=%d", B, P, C);
+  dim3 grid((C + NT - 1) / NT, B);
+  if (f_bf16) grid_mean_bpc_kernel<__nv_bfloat16><<<grid, NT, 0, as_stream(stream)>>>((const __nv_bfloat16*)F, P, C, mean_f);
+  else grid_mean_bpc_kernel<float><<<grid, NT, 0, as_stream(stream)>>>((const float*)F, P, C, mean_f);
+  ST_LAUNCH_TRY("grid_mean_bpc_kernel");
   return ST_OK;
 }
 

@@ -748,6 +748,21 @@ def attn_relayout(f, bf16=False, want_t=True):
     return F, FT, mean_f
 
 
+def attn_grid_bpc(f, bf16=False):
+    """Channels-last grid f (B, P, C) fp32 or bf16 -> F (B*P, C) in the compute storage type (the grid itself when the
+    types agree: no copy), mean_f (B, C) fp32."""
+    lib = _lib.load()
+    B, Pn, Cc = f.shape
+    F = f.reshape(B * Pn, Cc)
+    if bf16 and F.dtype != BF16:
+        F = cast_bf16(F, True, False)[0]
+    elif not bf16 and F.dtype != F32:
+        F = F.to(F32)
+    mean_f = torch.empty(B, Cc, dtype=F32, device=f.device)
+    check(lib.st_grid_mean_bpc(_raw(f), int(f.dtype == BF16), B, Pn, Cc, ptr(mean_f), stream_ptr()), "st_grid_mean_bpc")
+    return F, mean_f
+
+
 def attn_step_fwd(rows, Pn, att1, Fe, att2, wf, bf, b_embed, alphas_t, alpha_stride, S, ctx_out, act=ACT_LEAKY,
                   ctx_bf16=None, tag="attn_fwd"):
     """att1 (B*P, A), Fe (B*P, E) (fp32 or bf16), att2 (rows, A).  alphas_t / ctx_out are (possibly

@@ -199,3 +199,35 @@ def test_forward_backward_and_grid_gradient_request():
         m.forward_loss(feat.clone().requires_grad_(True), cap, lengths)
     with pytest.raises(NotImplementedError):
         m(feat.clone().requires_grad_(True), cap, lengths)
+
+
+@pytest.mark.parametrize("dtype,feat_dtype", [("fp32", torch.float32), ("bf16", torch.float32), ("bf16", torch.bfloat16)])
+def test_channels_last_grid_equals_channels_first(dtype, feat_dtype):
+    """grid_layout = "BPC": a channels-last grid (B, P, C) gives the same loss, alphas, gradients and greedy tokens as
+    the reference's channels-first (B, C, P) tensor of the same values (cnn_attn.py:49) -- without the re-layout pass."""
+    from showtell_b200.rnn_attn import RNN_Attn
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    B, C, Pn, T = 12, 256, 36, 7
+    m = RNN_Attn(64, C, 64, 64, 300, 1, dtype=dtype).to(dev)
+    feat = torch.relu(torch.randn(B, C, Pn, device=dev)).to(feat_dtype)
+    cap = torch.randint(4, 300, (B, T), device=dev)
+    lengths = sorted([T] * 4 + [5] * 4 + [3] * 4, reverse=True)
+    la, al_a = m.forward_backward(feat, cap, lengths)
+    ga = {n: p.grad.clone() for n, p in m.named_parameters()}
+    m.grid_layout = "BPC"
+    lb, al_b = m.forward_backward(feat.transpose(1, 2).contiguous(), cap, lengths)
+    tol = 1e-5 if dtype == "fp32" else 2e-3          # bf16: the channel means are summed in a different order
+    assert abs(float(la) - float(lb)) <= tol * abs(float(la))
+    assert float((al_a - al_b).abs().max()) <= tol
+    for n, p in m.named_parameters():
+        if n == "attn.full_att.bias":        # its gradient is the sum of every d e = 0 up to rounding (softmax is shift invariant)
+            continue
+        assert rel_err(p.grad, ga[n]) <= (10 * tol if dtype == "bf16" else tol), n
+    if dtype == "fp32":
+        tb = m.sentence_index(feat.transpose(1, 2).contiguous(), 1)
+        m.grid_layout = "BCP"
+        assert torch.equal(tb, m.sentence_index(feat, 1))
+    with pytest.raises(ValueError):
+        m.grid_layout = "BPC"
+        m.forward_backward(feat, cap, lengths)             # a channels-first tensor under the channels-last setting
