@@ -292,6 +292,11 @@ int st_rowsum_bf16(float* out, const void* M, int rows, int cols, int ld, st_str
  * nblocks.  Stream-ordered, CUDA-graph capturable; count % 4 == 0 and 16-byte aligned mappings. */
 enum { ST_AR_MAX_WORLD = 8, ST_AR_MAX_BLOCKS = 64 };
 int st_allreduce_flag_words(int world);
+/* Wall-clock bound of a cross-GPU barrier wait inside st_allreduce_sum_f32 (default 5 minutes; ms <= 0 restores it).  A
+ * wait that times out sets an error word instead of trapping: st_allreduce_error() returns 0, or 1 + the peer that did
+ * not arrive (the results of that exchange are then undefined).  Reading it costs no synchronisation (mapped host word). */
+int st_allreduce_set_timeout_ms(int64_t ms);
+int st_allreduce_error(void);
 int st_allreduce_sum_f32(void* const* peers_host, void* multicast, void* const* flags_host, int rank, int world,
                          int64_t count, int nblocks, st_stream_t stream);
 

@@ -47,6 +47,8 @@ _SIGS = {
     "st_collate_sort": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "st_gather_rows_bytes": (_I, [_P, _P, _P, _I, C.c_int64, _P]),
     "st_collate_captions": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "st_allreduce_set_timeout_ms": (_I, [C.c_int64]),
+    "st_allreduce_error": (_I, []),
     "st_debug_decode_table": (_I, [_I]),
     "st_debug_decode_screen": (_I, [_I]),
     "st_row_norm_max": (_I, [_P, _I, _I, _P, _P]),

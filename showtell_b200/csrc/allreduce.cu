@@ -30,7 +30,19 @@ struct ArParams {
   float* mc;
   int rank, world;
   long long count4;   // number of 16-byte units
+  unsigned long long timeout_ns;   // wall-clock bound of a cross-GPU barrier wait
+  int* error;                      // mapped host word: set to 1 + peer when a wait timed out
 };
+
+unsigned long long g_timeout_ns = 300ull * 1000000000ull;   // st_allreduce_set_timeout_ms; default 5 minutes
+int* g_error_host = nullptr;                                 // cudaHostAllocMapped word, read by st_allreduce_error()
+int* g_error_dev = nullptr;
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ void st_flag(uint32_t* p, uint32_t v) {
@@ -56,8 +68,20 @@ __device__ __forceinline__ void peer_barrier(const ArParams& p, uint32_t value) 
     fence_sys();                                                     // release what this CTA wrote
     st_flag(channel(p.flag[peer], p.world) + p.rank, value);
     const uint32_t* from = channel(p.flag[p.rank], p.world) + peer;
-    for (unsigned spin = 0; (int32_t)(ld_flag(from) - value) < 0; ++spin)
-      if (spin > (1u << 26)) __trap();
+    // A peer may legitimately be late by seconds (evaluation, a checkpoint, a data-loader stall, a first-time JIT): the
+    // wait is bounded by WALL TIME (default 5 minutes), not by a poll count; on timeout the error word is set for the
+    // host (st_allreduce_error) and the kernel goes on -- it never hangs and never kills the context of a healthy rank.
+    unsigned long long t0 = 0;
+    for (unsigned spin = 0; (int32_t)(ld_flag(from) - value) < 0; ++spin) {
+      if ((spin & 0x3ff) == 0x3ff) {
+        const unsigned long long now = global_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > p.timeout_ns) {
+          if (p.error) *reinterpret_cast<volatile int*>(p.error) = 1 + peer;
+          break;
+        }
+      }
+    }
     fence_sys();                                                     // acquire what the peers wrote
   }
   __syncthreads();
@@ -142,6 +166,17 @@ extern "C" {
 
 int st_allreduce_flag_words(int world) { return ST_AR_MAX_BLOCKS * (world + 1); }
 
+int st_allreduce_set_timeout_ms(int64_t ms) {
+  st::g_timeout_ns = ms > 0 ? (unsigned long long)ms * 1000000ull : 300ull * 1000000000ull;
+  return ST_OK;
+}
+
+int st_allreduce_error(void) {
+  if (!st::g_error_host) return 0;
+  const int e = *reinterpret_cast<volatile int*>(st::g_error_host);
+  return e;
+}
+
 int st_allreduce_sum_f32(void* const* peers_host, void* multicast, void* const* flags_host, int rank, int world,
                          int64_t count, int nblocks, st_stream_t stream) {
   using namespace st;
@@ -164,6 +199,13 @@ int st_allreduce_sum_f32(void* const* peers_host, void* multicast, void* const* 
   ST_REQUIRE(reinterpret_cast<uintptr_t>(multicast) % 16 == 0, ST_ERR_BAD_SHAPE,
              "st_allreduce_sum_f32: multicast mapping is not 16-byte aligned");
   p.mc = reinterpret_cast<float*>(multicast);
+  if (!g_error_host) {
+    ST_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&g_error_host), sizeof(int), cudaHostAllocMapped));
+    *g_error_host = 0;
+    ST_CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_error_dev), g_error_host, 0));
+  }
+  p.timeout_ns = g_timeout_ns;
+  p.error = g_error_dev;
   p.rank = rank;
   p.world = world;
   p.count4 = count / 4;

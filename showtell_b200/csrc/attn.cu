@@ -562,23 +562,37 @@ attn_hoist_bwd_lrelu_kernel(const __grid_constant__ StepTable tab, int P, int A,
           s1n[j] = (a_ok && pn < np) ? ldf(a1 + (size_t)pn * A) : 0.f;
         }
       }
+      // two locations per pass of the step loop: their compare -> predicated-add chains are independent, which
+      // gives the scheduler something to issue while a predicate is in flight
 #pragma unroll
-      for (int j = 0; j < GP; ++j) {
-        const int pi = g * GP + j;
-        if (pi < np) {
-          const float s1 = s1c[j];
-          float apc0 = 0.f, apc1 = 0.f;
+      for (int j = 0; j < GP; j += 2) {
+        const int pa = g * GP + j, pb = pa + 1;
+        const bool has_b = (j + 1 < GP) && pb < np;
+        if (pa < np) {
+          const float sa = s1c[j], sb = has_b ? s1c[(j + 1 < GP) ? j + 1 : j] : -FLT_MAX;   // -FLT_MAX: never above a threshold
+          const int pbs = has_b ? pb : pa;
+          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
           for (int ti = 0; ti < HB_T; ti += 4) {
-            const float4 d4 = *reinterpret_cast<const float4*>(&s_de[pi][ti]);
-            if (s1 > na2[ti]) { apc0 += d4.x; q0 = fmaf(d4.x, na2[ti], q0); }
-            if (s1 > na2[ti + 1]) { apc1 += d4.y; q1 = fmaf(d4.y, na2[ti + 1], q1); }
-            if (s1 > na2[ti + 2]) { apc0 += d4.z; q2 = fmaf(d4.z, na2[ti + 2], q2); }
-            if (s1 > na2[ti + 3]) { apc1 += d4.w; q3 = fmaf(d4.w, na2[ti + 3], q3); }
+            const float4 d = *reinterpret_cast<const float4*>(&s_de[pa][ti]);
+            const float4 e = *reinterpret_cast<const float4*>(&s_de[pbs][ti]);
+            if (sa > na2[ti]) { a0 += d.x; q0 = fmaf(d.x, na2[ti], q0); }
+            if (sb > na2[ti]) { b0 += e.x; q2 = fmaf(e.x, na2[ti], q2); }
+            if (sa > na2[ti + 1]) { a1 += d.y; q1 = fmaf(d.y, na2[ti + 1], q1); }
+            if (sb > na2[ti + 1]) { b1 += e.y; q3 = fmaf(e.y, na2[ti + 1], q3); }
+            if (sa > na2[ti + 2]) { a0 += d.z; q0 = fmaf(d.z, na2[ti + 2], q0); }
+            if (sb > na2[ti + 2]) { b0 += e.z; q2 = fmaf(e.z, na2[ti + 2], q2); }
+            if (sa > na2[ti + 3]) { a1 += d.w; q1 = fmaf(d.w, na2[ti + 3], q1); }
+            if (sb > na2[ti + 3]) { b1 += e.w; q3 = fmaf(e.w, na2[ti + 3], q3); }
           }
-          const float apc = apc0 + apc1;
-          ap[pi] += apc;
-          dw = fmaf(s1, fmaf(0.8f, apc, 0.2f * s_dp[pi]), dw);
+          const float apa = a0 + a1;
+          ap[pa] += apa;
+          dw = fmaf(sa, fmaf(0.8f, apa, 0.2f * s_dp[pa]), dw);
+          if (has_b) {
+            const float apb = b0 + b1;
+            ap[pb] += apb;
+            dw = fmaf(sb, fmaf(0.8f, apb, 0.2f * s_dp[pb]), dw);
+          }
         }
       }
     }

@@ -383,6 +383,8 @@ def gemm_tf32x3(A, B, *, bias=None, alpha=1.0, beta=0.0, out=None):
         raise ValueError(f"gemm_tf32x3: inner dimensions differ ({K} vs {Kb})")
     if out is None:
         out = torch.empty(M, N, dtype=F32, device=Ah.device)
+    elif tuple(out.shape) != (M, N) or out.stride(1) != 1 or out.dtype != F32 or not out.is_cuda:
+        raise ValueError(f"gemm_tf32x3: `out` must be a ({M}, {N}) fp32 CUDA tensor with unit inner stride")
     check(lib.st_gemm_tf32x3(M, N, K, _raw(Ah), _raw(Al), Ah.stride(0), _raw(Bh), _raw(Bl), Bh.stride(0), _raw(out),
                              out.stride(0), ptr(bias, F32), float(alpha), float(beta), stream_ptr()), "st_gemm_tf32x3")
     return out

@@ -120,6 +120,13 @@ class GradReducer:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("GradReducer: a symmetric bucket cannot be created during CUDA-graph capture "
                                    "(run the step eagerly once first)")
+            # every rank must run the same exchanges with the same number of CTAs, or the barrier epochs desynchronise
+            mine = (self.nblocks, tuple(sorted(self._skip)), self._call, tuple(tuple(t.shape) for t in tensors))
+            seen = [None] * self.world
+            dist.all_gather_object(seen, mine, group=self.group)
+            if any(x != mine for x in seen):
+                raise RuntimeError(f"GradReducer: ranks disagree on the exchange setup (CTAs, skipped exchanges, position, "
+                                   f"shapes): {seen}")
             try:
                 b = _SymBucket([t.shape for t in tensors], self.group, tensors[0].device)
             except Exception as exc:                    # no peer access on this node: NCCL does the exchange
@@ -182,3 +189,9 @@ class GradReducer:
             torch.cuda.current_stream().wait_event(ev)
         self._pending = []
         self._call = 0
+        if self.backend == "symm" and self._buckets:
+            from . import _lib
+            err = _lib.load().st_allreduce_error()          # a mapped host word: no synchronisation
+            if err:
+                raise RuntimeError(f"showtell_b200: a gradient exchange timed out waiting for rank {err - 1} "
+                                   "(st_allreduce_set_timeout_ms; the gradients of that step are undefined)")
