@@ -243,6 +243,7 @@ __global__ void __launch_bounds__(256) screen_select_kernel(int M, int H, int V,
   auto exact2 = [&](const float* hrow, int va, int vb, float& sa, float& sb) {
     const float* wa = Wv + (size_t)va * H;
     const float* wb = Wv + (size_t)vb * H;
+    const float ba = bv[va], bb = bv[vb];              // issued with the rows, not after the reduction
     sa = 0.f; sb = 0.f;
     for (int i0 = 0; i0 < H; i0 += 512) {
       float xa[16], xb[16];
@@ -258,8 +259,8 @@ __global__ void __launch_bounds__(256) screen_select_kernel(int M, int H, int V,
         if (i < H) { const float hv = hrow[i]; sa = fmaf(hv, xa[j], sa); sb = fmaf(hv, xb[j], sb); }
       }
     }
-    sa = warp_sum(sa) + bv[va];
-    sb = warp_sum(sb) + bv[vb];
+    sa = warp_sum(sa) + ba;
+    sb = warp_sum(sb) + bb;
   };
   int ncnd = 0, nover = 0;
   if (valid) {
