@@ -130,6 +130,8 @@ def load():
         fn.argtypes = args
     if os.environ.get("SHOWTELL_PDL", "1") == "0":       # A/B switch for programmatic dependent launch
         lib.st_debug_set_pdl(0)
+    if os.environ.get("SHOWTELL_GEMM_VARIANT"):            # A/B switch: st_debug_gemm_variant flags (e.g. 0x10000: no pair kernel)
+        lib.st_debug_gemm_variant(int(os.environ["SHOWTELL_GEMM_VARIANT"], 0))
     if os.environ.get("SHOWTELL_COOP", "0") == "1":        # cooperative launches of the persistent BPTT kernel
         lib.st_debug_set_coop(1)
     if os.environ.get("SHOWTELL_BWD_KS"):                  # A/B switch for the BPTT kernel's K split / tile height

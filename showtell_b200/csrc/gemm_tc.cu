@@ -813,11 +813,14 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
       : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx_at(uint32_t cluster_addr, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
+  // default semantics (release at CTA scope), as CUTLASS's ClusterTransactionBarrier does for the leader's barrier: with
+  // .release.cluster every call became MEMBAR.ALL.CTA + ERRBAR on the producer thread -- once per k-block, which made the
+  // PRODUCER the bottleneck of the pair kernel (tensor pipe 29 %, ncu)
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
                : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_at(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -1186,10 +1189,17 @@ int launch_tc_pair(TcParams p, const void* A, int lda, const void* B, int ldb, c
 }
 
 // Kernel + tile choice for a problem: 128 / 256 = single-CTA kernel with that tile width; 2 = CTA-pair kernel
-// (only when pinned: measured on B200 it does not beat the 256-wide single-CTA tiles).
+// (cta_group::2, 256 x 256 tiles over two SMs: 32 KB instead of 48 KB of operands per CTA and k-block, which is what
+// bounds the big products -- 51 against 56-58 us on 25088 x 512 x 2048 and 5120 x 10000 x 512).  K-major operands only.
+int g_pair_auto = 1;   // st_debug_gemm_variant(v | 0x10000): never choose the pair kernel
 template <int EPI>
 inline int pick_variant(const TcParams& p, int sms) {
   if (g_variant) return g_variant;
+  if (g_pair_auto && p.M >= 512 && p.N >= 256 && p.K >= 256) {
+    // enough 256 x 256 tiles to keep every pair busy for several rounds (or stream-K over the pairs)
+    const long t2 = (long)((p.M + 255) / 256) * ((p.N + 255) / 256);
+    if (t2 >= 2L * (sms / 2)) return 2;
+  }
   if (p.N > 128) {
     const int ntiles = ((p.M + BM - 1) / BM) * ((p.N + 255) / 256), kb = (p.K + BK - 1) / BK;
     if (want_streamk<EPI>(p, ntiles, kb, sms)) return 256;
@@ -1363,6 +1373,7 @@ int st_debug_gemm_variant(int variant) {
   st::g_streamk = (variant & 0x1000) ? 0 : 1;
   st::g_mn3d = (variant & 0x2000) ? 0 : 1;
   st::g_mc = (variant & 0x4000) ? 1 : ((variant & 0x8000) ? -1 : 0);
+  st::g_pair_auto = (variant & 0x10000) ? 0 : 1;
   variant &= 0xfff;
   st::g_variant = (variant == 2 || variant == 128 || variant == 256) ? variant : 0;
   return ST_OK;
