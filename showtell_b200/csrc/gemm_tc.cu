@@ -812,6 +812,12 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx_at(uint32_t cluster_addr, uint32_t bytes) {
   // default semantics (release at CTA scope), as CUTLASS's ClusterTransactionBarrier does for the leader's barrier: with
   // .release.cluster every call became MEMBAR.ALL.CTA + ERRBAR on the producer thread -- once per k-block, which made the
@@ -852,7 +858,9 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
                : "memory");
 }
 
-template <int EPI>
+// AMN / BMN: that operand MN-major (see gemm_tc_kernel), given as the 3-D tensor map of make_tmap_mn3d with two 64-wide
+// blocks per box: a CTA's 128 rows of A / its 128-column half of B are one operation each either way.
+template <int EPI, int AMN = 0, int BMN = 0>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const TcParams p) {
@@ -913,8 +921,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (elect_one()) {
           mbar_expect_tx_at(mapa_rank0(smem_u32(&full[stage])), STAGE_BYTES);
           uint8_t* a = smem + (size_t)stage * STAGE_BYTES;
-          tma_load_2d_pair(a, &tmA, k * BK, m0, &full[stage]);
-          tma_load_2d_pair(a + A_BYTES, &tmB, k * BK, n0, &full[stage]);
+          if (AMN) tma_load_3d_pair(a, &tmA, 0, k * BK, m0 / 64, &full[stage]);
+          else tma_load_2d_pair(a, &tmA, k * BK, m0, &full[stage]);
+          if (BMN) tma_load_3d_pair(a + A_BYTES, &tmB, 0, k * BK, n0 / 64, &full[stage]);
+          else tma_load_2d_pair(a + A_BYTES, &tmB, k * BK, n0, &full[stage]);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -922,8 +932,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     if (rank == 0) {  // ------------------------------------------------- MMA issuer (leader CTA only)
-      constexpr uint32_t idesc = umma_idesc(2 * BM, BN);
-      const uint64_t adesc0 = umma_desc_k128(smem_u32(smem)), bdesc0 = umma_desc_k128(smem_u32(smem) + A_BYTES);
+      constexpr uint32_t idesc = umma_idesc(2 * BM, BN) | (AMN ? (1u << 15) : 0u) | (BMN ? (1u << 16) : 0u);
+      const uint64_t adesc0 = AMN ? umma_desc_mn128(smem_u32(smem)) : umma_desc_k128(smem_u32(smem));
+      const uint64_t bdesc0 = BMN ? umma_desc_mn128(smem_u32(smem) + A_BYTES) : umma_desc_k128(smem_u32(smem) + A_BYTES);
+      constexpr uint64_t astep = AMN ? 128 : 2, bstep = BMN ? 128 : 2;
       WorkSched sched(ntiles, kb, npairs, pair, p.streamk);
       int stage = 0, acc = 0, tile, k0, k1;
       uint32_t phase = 0, acc_phase = 0;
@@ -938,7 +950,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < BK / UK; ++kk)
-              tc_mma_pair(d_tmem, adesc0 + so + 2 * kk, bdesc0 + so + 2 * kk, idesc, (k > k0) || (kk != 0));
+              tc_mma_pair(d_tmem, adesc0 + so + astep * kk, bdesc0 + so + bstep * kk, idesc, (k > k0) || (kk != 0));
             tc_commit_pair(&empty[stage]);
           }
           __syncwarp();
@@ -1159,12 +1171,14 @@ inline int pick_bn(int M, int N, int sms) {
   return (r256 * 750 <= r128 * 600) ? 256 : 128;
 }
 
-template <int EPI>
+template <int EPI, int AMN = 0, int BMN = 0>
 int launch_tc_pair(TcParams p, const void* A, int lda, const void* B, int ldb, cudaStream_t s, int sms) {
   CUtensorMap tmA, tmB;
-  ST_TRY(make_tmap(&tmA, A, p.M, p.K, lda, BM, "A"));
-  ST_TRY(make_tmap(&tmB, B, p.N, p.K, ldb, BM, "B"));
-  auto kern = gemm_tc2_kernel<EPI>;
+  if (AMN) ST_TRY(make_tmap_mn3d(&tmA, A, p.K, p.M, lda, 2, "A (MN-major)"));
+  else ST_TRY(make_tmap(&tmA, A, p.M, p.K, lda, BM, "A"));
+  if (BMN) ST_TRY(make_tmap_mn3d(&tmB, B, p.K, p.N, ldb, 2, "B (MN-major)"));
+  else ST_TRY(make_tmap(&tmB, B, p.N, p.K, ldb, BM, "B"));
+  auto kern = gemm_tc2_kernel<EPI, AMN, BMN>;
   ST_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PairCfg::SMEM_BYTES));
   const int pairs = sms / 2;
   const int ntiles = ((p.M + 255) / 256) * ((p.N + 255) / 256), kb = (p.K + BK - 1) / BK;
@@ -1199,6 +1213,8 @@ inline int pick_variant(const TcParams& p, int sms) {
     // enough 256 x 256 tiles to keep every pair busy for several rounds (or stream-K over the pairs)
     const long t2 = (long)((p.M + 255) / 256) * ((p.N + 255) / 256);
     if (t2 >= 2L * (sms / 2)) return 2;
+    // (few tiles + long K, i.e. stream-K over the pairs: measured equal or slower than the single-CTA kernel -- 66.6 vs
+    //  64.5 us for 512 x 2048 x 25088, 29.4 vs 25.4 us for 2048 x 512 x 5120 -- so those stay where they were)
   }
   if (p.N > 128) {
     const int ntiles = ((p.M + BM - 1) / BM) * ((p.N + 255) / 256), kb = (p.K + BK - 1) / BK;
@@ -1225,7 +1241,10 @@ int launch_tc_major(const TcParams& p, const void* A, int lda, const void* B, in
   ST_REQUIRE(p.M >= 1 && p.N >= 1 && p.K >= 1, ST_ERR_BAD_SHAPE, "gemm_bf16: M=%d N=%d K=%d", p.M, p.N, p.K);
   int sms = 0;
   ST_TRY(gemm_sms(&sms));
-  const int bn = (g_variant == 128 || g_variant == 256) ? g_variant : pick_variant<EPI_STORE>(p, sms);
+  int bn = (g_variant == 128 || g_variant == 256) ? g_variant : pick_variant<EPI_STORE>(p, sms);
+  // the pair kernel takes MN-major operands as 3-D maps of whole 64-blocks
+  if (bn == 2 && ((AMN && p.M % 64 != 0) || (BMN && p.N % 64 != 0) || !g_mn3d)) bn = (g_variant == 2) ? 256 : pick_bn(p.M, p.N, sms);
+  if (bn == 2) return launch_tc_pair<EPI_STORE, AMN, BMN>(p, A, lda, B, ldb, s, sms);
   return bn == 256 ? launch_tc_bn<EPI_STORE, 256, AMN, BMN>(p, A, lda, B, ldb, s, sms)
                    : launch_tc_bn<EPI_STORE, 128, AMN, BMN>(p, A, lda, B, ldb, s, sms);
 }

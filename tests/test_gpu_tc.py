@@ -57,7 +57,7 @@ def test_gemm_bf16(M, N, K, variant, gemm_variant):
     assert bool((wide[:, :4] == 7).all()) and bool((wide[:, 4 + N:] == 7).all())
 
 
-@pytest.mark.parametrize("variant", [0, 128, 256, MC | 128, MC | 256, NOMC])
+@pytest.mark.parametrize("variant", [0, 128, 256, 2, MC | 128, MC | 256, NOMC])
 @pytest.mark.parametrize("a_t,b_t", [(True, True), (False, True), (True, False)])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 256, 128), (256, 384, 192), (100, 50, 40), (129, 257, 72),
                                    (10000, 512, 5120),      # dW of the vocabulary projection: P^T . Hs
