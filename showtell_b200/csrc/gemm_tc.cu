@@ -1385,7 +1385,12 @@ int st_gemm_bf16_screen(int M, int N, int K, const void* A, int lda, const void*
   const int bn = N > 128 ? 256 : 128;
   p.npart = 2 * ((N + bn - 1) / bn);
   *npart_out = p.npart;
-  return launch_tc<EPI_TOPS>(p, A, lda, B, ldb, as_stream(stream), bn);
+  // the CTA-pair kernel has the same 256-column tiles (same parts) and is the faster one on large problems
+  int sms = 0;
+  ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
+  const long t2 = (long)((M + 255) / 256) * ((N + 255) / 256);
+  const int variant = (g_variant == 0 && g_pair_auto && M >= 512 && N >= 256 && K >= 256 && t2 >= 2L * (sms / 2)) ? 2 : bn;
+  return launch_tc<EPI_TOPS>(p, A, lda, B, ldb, as_stream(stream), variant);
 }
 
 int st_debug_gemm_variant(int variant) {
