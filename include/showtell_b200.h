@@ -397,11 +397,13 @@ int st_shift_states_bf16(void* Hprev, const void* Hs, const void* h0, int H, int
  *   ctx_out_bf16 (optional): bf16 copy of ctx_out, the A operand of the tensor-core W_ih[:,E:] product
  * st_attn_step_bwd: dalpha_p = <dctx[b,:], Fe[b,p,:]> + dalpha[b*dalpha_stride + p] (may be NULL);
  *   de = alpha * (dalpha - sum alpha dalpha) -> de_out (rows,P);  datt2 (rows,A) = sum_p de_p w_f act'(.)
- *   (+ optional bf16 copy datt2_bf16 (rows,A)).  Rows whose A*sizeof and E*sizeof are 512/1024/2048 bytes
- *   run the streaming kernels (bulk-async-copy ring, attn_stream.cu), other shapes a generic kernel.
+ *   (+ optional bf16 copy datt2_bf16 (rows,A); + optional gt (rows,A) = sum_p de_p act'(.), i.e. datt2 before the
+ *   factor w_f: with it st_attn_hoist_bwd forms the step part of dw_f as sum att2 * gt instead of once more per tuple).
+ *   Rows whose A*sizeof and E*sizeof are 512/1024/2048 bytes run the streaming kernels (bulk-async-copy ring,
+ *   attn_stream.cu), other shapes a generic kernel.
  * st_attn_hoist_bwd (after the loop; de (N,P), att2 (N,A) packed time-major):
  *   datt1[b,p,a] = w_f[a] sum_t de[t,b,p] act'(att1[b,p,a] + att2[t,b,a]) (+ transposed copy),
- *   dwf[a] = sum_{t,b,p} de act(.)
+ *   dwf[a] = sum_{t,b,p} de act(.)  (gt, optional: the (N,A) tensor st_attn_step_bwd wrote, see there)
  * st_attn_ctx_all: ctx[(t,b), c] = sum_p alphas[b,t,p] F[b,p,c] for all live (t,b) (for dW_embed); ctx / ctxT
  *   are fp32 (out_bf16 = 0) or bf16.
  * st_attn_penalty: pen_sum = sum (1 - S)^2, Gpen = -2 coef (1 - S)          (main_attn.py:131)
@@ -424,10 +426,10 @@ int st_attn_step_fwd(int rows, int P, int A, int E, const void* att1, const void
 int st_attn_step_bwd(int rows, int P, int A, int E, const void* att1, const void* Fe, int in_bf16,
                      const float* att2, const float* wf, const float* alphas, int alpha_stride,
                      const float* dalpha, int dalpha_stride, const float* dctx, int ld_dctx, float* de_out,
-                     float* datt2, void* datt2_bf16, int act, st_stream_t stream);
+                     float* datt2, void* datt2_bf16, float* gt, int act, st_stream_t stream);
 int st_attn_hoist_bwd(int nsteps, const int* batch_sizes_host, int P, int A, const void* att1, int in_bf16,
                       const float* att2, const float* de, const float* wf, void* datt1, void* datt1T, int ldt,
-                      int out_bf16, float* dwf, int act, st_stream_t stream);
+                      int out_bf16, float* dwf, const float* gt, int act, st_stream_t stream);
 int st_attn_ctx_all(int nsteps, const int* batch_sizes_host, int P, int C, int T_cap, const void* F, int in_bf16,
                     const float* alphas, void* ctx, void* ctxT, int ldt, int out_bf16, st_stream_t stream);
 /* Q[(b,p), e] = sum_t alphas[b,t,p] dctx[(t,b), e] over the steps in which row b is live, bf16 (B*P, E): the A operand

@@ -96,8 +96,8 @@ _SIGS = {
     "st_grid_mean_bpc": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "st_attn_relayout_bf16in": (_I, [_P, _I, _I, _I, _P, _P, _I, _I, _P, _P]),
     "st_attn_step_fwd": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _P, _I, _I, _P]),
-    "st_attn_step_bwd": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _I, _P]),
-    "st_attn_hoist_bwd": (_I, [_I, _IP, _I, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _I, _P]),
+    "st_attn_step_bwd": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _I, _P]),
+    "st_attn_hoist_bwd": (_I, [_I, _IP, _I, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _P]),
     "st_attn_ctx_all": (_I, [_I, _IP, _I, _I, _I, _P, _I, _P, _P, _P, _I, _I, _P]),
     "st_attn_embed_q": (_I, [_I, _IP, _I, _I, _I, _P, _P, _I, _P, _P]),
     "st_attn_penalty": (_I, [_I, _P, _F, _P, _P, _P]),

@@ -185,6 +185,7 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
     grads = {}
     de_all = torch.empty(N, Pn, dtype=F32, device=dev)
     datt2_all = torch.empty(N, A, dtype=F32, device=dev)
+    gt_all = torch.empty(N, A, dtype=F32, device=dev)        # datt2 before the factor w_f (feeds dw_f, see attn_hoist_bwd)
     datt2_b = torch.empty(N, A, dtype=BF16, device=dev) if tc else None
     dctx_all = torch.empty(N, E, dtype=F32, device=dev)
     dHs = [torch.empty(N, H, dtype=F32, device=dev) for _ in range(L - 1)] + [dHs_top]
@@ -236,7 +237,7 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
             dal, dal_stride = Gpen, Pn
         ops.attn_step_bwd(bt, Pn, att1, Fe, att2_all[o0:o1], wf, alphas[:, t, :], Tcap * Pn, dal, dal_stride,
                           dctx_all[o0:o1], de_all[o0:o1], datt2_all[o0:o1],
-                          datt2_bf16=datt2_b[o0:o1] if tc else None)
+                          datt2_bf16=datt2_b[o0:o1] if tc else None, gt=gt_all[o0:o1])
         # the query was the PRE-step top-layer hidden: its gradient joins the carried dh of the top layer
         if tc and fused0 and L == 1 and ops.query_fold_ok(A) and t > 0:
             pass                         # consumed by the next (t-1) fused step kernel
@@ -258,7 +259,7 @@ def attn_backward(mode, P, kind, L, caption, sv, dHs_top, dalphas=None, Gpen=Non
 
     # the encoder-projection chain: one pass over att1, then the largest GEMM of the step
     def enc_chain():
-        datt1, _, dwf = ops.attn_hoist_bwd(bs, Pn, att1, att2_all, de_all, wf, want_t=False)
+        datt1, _, dwf = ops.attn_hoist_bwd(bs, Pn, att1, att2_all, de_all, wf, want_t=False, gt_all=gt_all)
         if mode == "bf16":
             dWe = ops.gemm_bf16(datt1, sv["F"], a_t=True, b_t=True, tag="att1_dw")               # datt1^T F, both in place
         else:

@@ -23,6 +23,8 @@
 #include <cfloat>
 
 #include "attn_stream.cuh"
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace st {
@@ -281,7 +283,7 @@ attn_step_bwd_kernel(int P, int A, int E, const T* __restrict__ att1, const T* _
                      const float* __restrict__ att2, const float* __restrict__ wf,
                      const float* __restrict__ alphas, int alpha_stride, const float* __restrict__ dal,
                      int dal_stride, const float* __restrict__ dctx, int ld_dctx, float* __restrict__ de_out,
-                     float* __restrict__ datt2, __nv_bfloat16* __restrict__ datt2_bf16) {
+                     float* __restrict__ datt2, __nv_bfloat16* __restrict__ datt2_bf16, float* __restrict__ gt_out) {
   extern __shared__ float sm[];
   float* s_att2 = sm;             // [A]
   float* s_wf = sm + A;           // [A]
@@ -320,6 +322,7 @@ attn_step_bwd_kernel(int P, int A, int E, const T* __restrict__ att1, const T* _
     float acc = 0.f;
     const float a2 = s_att2[a];
     for (int p = 0; p < P; ++p) acc = fmaf(s_de[p], act_d<ACT>(ldf(a1 + (size_t)p * A + a) + a2), acc);
+    if (gt_out) gt_out[(size_t)b * A + a] = acc;
     datt2[(size_t)b * A + a] = acc * s_wf[a];
     if (datt2_bf16) datt2_bf16[(size_t)b * A + a] = __float2bfloat16(acc * s_wf[a]);
   }
@@ -497,7 +500,37 @@ attn_embed_q_kernel(const __grid_constant__ StepTable tab, int P, int E, int Tca
 //   datt1[b,p,a] = w_f[a] (0.2 D_p + 0.8 A_p),        A_p = sum_t de[t,p][s > 0],   D_p = sum_t de[t,p]
 //   dw_f[a]     += sum_p att1[b,p,a] (0.2 D_p + 0.8 A_p) + sum_t att2[t,b,a] (0.2 D_t + 0.8 A_t)      (act(s) = s act'(s))
 // with D_p / D_t (independent of a) summed once per CTA.  63 M -> ~25 M warp instructions at config 3.
-template <typename T, typename TO>
+// out[c] += sum_r X[r,c] Y[r,c]  (the step part of dw_f: X = att2 (N,A), Y = gt (N,A); a few MB)
+constexpr int CSP_ROWS = 16;
+__global__ void __launch_bounds__(256) colsum_prod_kernel(float* __restrict__ out, const float* __restrict__ X,
+                                                          const float* __restrict__ Y, int rows, int cols) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= cols) return;
+  const int r0 = blockIdx.y * CSP_ROWS, r1 = min(rows, r0 + CSP_ROWS);
+  float s0 = 0.f, s1 = 0.f;
+  if (r1 - r0 == CSP_ROWS) {                      // all 2 * CSP_ROWS loads in flight at once
+    float x[CSP_ROWS], y[CSP_ROWS];
+#pragma unroll
+    for (int i = 0; i < CSP_ROWS; ++i) {
+      x[i] = X[(size_t)(r0 + i) * cols + c];
+      y[i] = Y[(size_t)(r0 + i) * cols + c];
+    }
+#pragma unroll
+    for (int i = 0; i < CSP_ROWS; i += 2) {
+      s0 = fmaf(x[i], y[i], s0);
+      s1 = fmaf(x[i + 1], y[i + 1], s1);
+    }
+  } else {
+    for (int r = r0; r < r1; ++r) s0 = fmaf(X[(size_t)r * cols + c], Y[(size_t)r * cols + c], s0);
+  }
+  atomicAdd(out + c, s0 + s1);
+}
+
+// FULL: P is a multiple of HB_P, A a multiple of NT and every offset fits 31 bits (the launcher checks): no tail
+// predicates, 32-bit index arithmetic -- a third fewer instructions around the tuple loop.
+// GT: the step part of dw_f, sum_{t,p} g[t,p] att2[t], is formed by the launcher as sum_rows att2 * gt from the tensor
+// the per-step attention backward kernels already computed (gt[(t,b),a] = sum_p g[t,p]): a third of the tuple work less.
+template <typename T, typename TO, bool FULL, bool GT>
 __global__ void __launch_bounds__(NT, 3)
 attn_hoist_bwd_lrelu_kernel(const __grid_constant__ StepTable tab, int P, int A, const T* __restrict__ att1,
                             const float* __restrict__ att2, const float* __restrict__ de, const float* __restrict__ wf,
@@ -505,14 +538,15 @@ attn_hoist_bwd_lrelu_kernel(const __grid_constant__ StepTable tab, int P, int A,
   __shared__ __align__(16) float s_de[HB_P][HB_T];       // [p][t] of the chunk, zero padded
   __shared__ float s_dp[HB_P], s_dpt[HB_P], s_dt[HB_T];  // chunk sums over t, their total over the chunks, chunk sums over p
   __shared__ int s_row[HB_T];                            // packed row of (t0 + ti, b)
-  const int b = blockIdx.y, p0 = blockIdx.x * HB_P, np = min(HB_P, P - p0), tid = threadIdx.x;
+  using IX = typename std::conditional<FULL, int, size_t>::type;   // offsets
+  const int b = blockIdx.y, p0 = blockIdx.x * HB_P, np = FULL ? HB_P : min(HB_P, P - p0), tid = threadIdx.x;
   const int a = blockIdx.z * NT + tid;                   // grid.z = blocks of NT attention units
-  const bool a_ok = a < A;
+  const bool a_ok = FULL || a < A;
   int len = 0;
   while (len < tab.nsteps && tab.bs[len] > b) ++len;     // steps in which row b is live
   constexpr int GP = 7;                                  // locations per group: their att1 values are loaded together,
   static_assert(HB_P % GP == 0, "location groups");      // one group ahead of the arithmetic
-  const T* a1 = att1 + ((size_t)b * P + p0) * A + a;
+  const T* a1 = att1 + ((IX)b * P + p0) * A + a;
   float ap[HB_P], dw = 0.f;
 #pragma unroll
   for (int i = 0; i < HB_P; ++i) ap[i] = 0.f;
@@ -524,17 +558,17 @@ attn_hoist_bwd_lrelu_kernel(const __grid_constant__ StepTable tab, int P, int A,
     __syncthreads();
     for (int i = tid; i < HB_P * HB_T; i += NT) {
       const int pi = i / HB_T, ti = i - pi * HB_T, r = s_row[ti];
-      s_de[pi][ti] = (pi < np && r >= 0) ? de[(size_t)r * P + p0 + pi] : 0.f;
+      s_de[pi][ti] = (pi < np && r >= 0) ? de[(IX)r * P + p0 + pi] : 0.f;
     }
     float na2[HB_T];                                      // -att2[t,b,a]
 #pragma unroll
     for (int ti = 0; ti < HB_T; ++ti) {
       const int r = s_row[ti];
-      na2[ti] = (a_ok && r >= 0) ? -att2[(size_t)r * A + a] : 0.f;
+      na2[ti] = (a_ok && r >= 0) ? -att2[(IX)r * A + a] : 0.f;
     }
     float s1n[GP];
 #pragma unroll
-    for (int j = 0; j < GP; ++j) s1n[j] = (a_ok && j < np) ? ldf(a1 + (size_t)j * A) : 0.f;
+    for (int j = 0; j < GP; ++j) s1n[j] = (a_ok && j < np) ? ldf(a1 + (IX)j * A) : 0.f;
     __syncthreads();
     if (tid < HB_P) {
       float v = 0.f;
@@ -559,7 +593,7 @@ attn_hoist_bwd_lrelu_kernel(const __grid_constant__ StepTable tab, int P, int A,
 #pragma unroll
         for (int j = 0; j < GP; ++j) {
           const int pn = (g + 1) * GP + j;
-          s1n[j] = (a_ok && pn < np) ? ldf(a1 + (size_t)pn * A) : 0.f;
+          s1n[j] = (a_ok && pn < np) ? ldf(a1 + (IX)pn * A) : 0.f;
         }
       }
       // two locations per pass of the step loop: their compare -> predicated-add chains are independent, which
@@ -576,14 +610,14 @@ attn_hoist_bwd_lrelu_kernel(const __grid_constant__ StepTable tab, int P, int A,
           for (int ti = 0; ti < HB_T; ti += 4) {
             const float4 d = *reinterpret_cast<const float4*>(&s_de[pa][ti]);
             const float4 e = *reinterpret_cast<const float4*>(&s_de[pbs][ti]);
-            if (sa > na2[ti]) { a0 += d.x; q0 = fmaf(d.x, na2[ti], q0); }
-            if (sb > na2[ti]) { b0 += e.x; q2 = fmaf(e.x, na2[ti], q2); }
-            if (sa > na2[ti + 1]) { a1 += d.y; q1 = fmaf(d.y, na2[ti + 1], q1); }
-            if (sb > na2[ti + 1]) { b1 += e.y; q3 = fmaf(e.y, na2[ti + 1], q3); }
-            if (sa > na2[ti + 2]) { a0 += d.z; q0 = fmaf(d.z, na2[ti + 2], q0); }
-            if (sb > na2[ti + 2]) { b0 += e.z; q2 = fmaf(e.z, na2[ti + 2], q2); }
-            if (sa > na2[ti + 3]) { a1 += d.w; q1 = fmaf(d.w, na2[ti + 3], q1); }
-            if (sb > na2[ti + 3]) { b1 += e.w; q3 = fmaf(e.w, na2[ti + 3], q3); }
+            if (sa > na2[ti]) { a0 += d.x; if (!GT) q0 = fmaf(d.x, na2[ti], q0); }
+            if (sb > na2[ti]) { b0 += e.x; if (!GT) q2 = fmaf(e.x, na2[ti], q2); }
+            if (sa > na2[ti + 1]) { a1 += d.y; if (!GT) q1 = fmaf(d.y, na2[ti + 1], q1); }
+            if (sb > na2[ti + 1]) { b1 += e.y; if (!GT) q3 = fmaf(e.y, na2[ti + 1], q3); }
+            if (sa > na2[ti + 2]) { a0 += d.z; if (!GT) q0 = fmaf(d.z, na2[ti + 2], q0); }
+            if (sb > na2[ti + 2]) { b0 += e.z; if (!GT) q2 = fmaf(e.z, na2[ti + 2], q2); }
+            if (sa > na2[ti + 3]) { a1 += d.w; if (!GT) q1 = fmaf(d.w, na2[ti + 3], q1); }
+            if (sb > na2[ti + 3]) { b1 += e.w; if (!GT) q3 = fmaf(e.w, na2[ti + 3], q3); }
           }
           const float apa = a0 + a1;
           ap[pa] += apa;
@@ -596,7 +630,7 @@ attn_hoist_bwd_lrelu_kernel(const __grid_constant__ StepTable tab, int P, int A,
         }
       }
     }
-    if (a_ok) {
+    if (a_ok && !GT) {
       dw = fmaf(-0.8f, (q0 + q1) + (q2 + q3), dw);        // q sums de * (-att2)
 #pragma unroll
       for (int ti = 0; ti < HB_T; ++ti) dw = fmaf(-0.2f * na2[ti], s_dt[ti], dw);
@@ -607,7 +641,7 @@ attn_hoist_bwd_lrelu_kernel(const __grid_constant__ StepTable tab, int P, int A,
     const float w = wf[a];
 #pragma unroll
     for (int pi = 0; pi < HB_P; ++pi)
-      if (pi < np) stf(datt1 + ((size_t)b * P + p0 + pi) * A + a, w * fmaf(0.8f, ap[pi], 0.2f * s_dpt[pi]));
+      if (pi < np) stf(datt1 + ((IX)b * P + p0 + pi) * A + a, w * fmaf(0.8f, ap[pi], 0.2f * s_dpt[pi]));
     atomicAdd(dwf + a, dw);
   }
 }
@@ -794,7 +828,7 @@ int st_attn_step_fwd(int rows, int P, int A, int E, const void* att1, const void
 int st_attn_step_bwd(int rows, int P, int A, int E, const void* att1, const void* Fe, int in_bf16,
                      const float* att2, const float* wf, const float* alphas, int alpha_stride,
                      const float* dalpha, int dalpha_stride, const float* dctx, int ld_dctx, float* de_out,
-                     float* datt2, void* datt2_bf16, int act, st_stream_t stream) {
+                     float* datt2, void* datt2_bf16, float* gt, int act, st_stream_t stream) {
   using namespace st;
   ST_REQUIRE(att1 && Fe && att2 && wf && alphas && dctx && de_out && datt2, ST_ERR_NULL,
              "st_attn_step_bwd: NULL pointer");
@@ -807,6 +841,7 @@ int st_attn_step_bwd(int rows, int P, int A, int E, const void* att1, const void
     sp.alphas_r = alphas; sp.alpha_stride = alpha_stride; sp.dal = dalpha; sp.dal_stride = dalpha_stride;
     sp.dctx = dctx; sp.ld_dctx = ld_dctx; sp.de_out = de_out; sp.datt2 = datt2;
     sp.datt2_bf16 = reinterpret_cast<__nv_bfloat16*>(datt2_bf16);
+    sp.gt_out = gt;
     const int r = attn_stream_try(true, rows, in_bf16, act, sp, as_stream(stream));
     if (r != 0) return r < 0 ? r : ST_OK;
   }
@@ -816,7 +851,7 @@ int st_attn_step_bwd(int rows, int P, int A, int E, const void* att1, const void
 #define ST_LAUNCH_BWD(T, ACT)                                                                         \
   attn_step_bwd_kernel<T, ACT><<<rows, NT, smem, s>>>(P, A, E, (const T*)att1, (const T*)Fe, att2, wf, alphas, \
                                                       alpha_stride, dalpha, dalpha_stride, dctx, ld_dctx, de_out, datt2, \
-                                                      (__nv_bfloat16*)datt2_bf16)
+                                                      (__nv_bfloat16*)datt2_bf16, gt)
   if (in_bf16) { if (act == 0) ST_LAUNCH_BWD(__nv_bfloat16, 0); else ST_LAUNCH_BWD(__nv_bfloat16, 1); }
   else         { if (act == 0) ST_LAUNCH_BWD(float, 0); else ST_LAUNCH_BWD(float, 1); }
 #undef ST_LAUNCH_BWD
@@ -826,7 +861,7 @@ int st_attn_step_bwd(int rows, int P, int A, int E, const void* att1, const void
 
 int st_attn_hoist_bwd(int nsteps, const int* batch_sizes_host, int P, int A, const void* att1, int in_bf16,
                       const float* att2, const float* de, const float* wf, void* datt1, void* datt1T, int ldt,
-                      int out_bf16, float* dwf, int act, st_stream_t stream) {
+                      int out_bf16, float* dwf, const float* gt, int act, st_stream_t stream) {
   using namespace st;
   StepTable tab;
   ST_TRY(make_step_table(tab, nsteps, batch_sizes_host));
@@ -843,10 +878,19 @@ int st_attn_hoist_bwd(int nsteps, const int* batch_sizes_host, int P, int A, con
   ST_REQUIRE(smem <= 200 * 1024, ST_ERR_BAD_SHAPE, "st_attn_hoist_bwd: A=%d too large", A);
   if (act == 0 && !datt1T) {     // LeakyReLU without the transposed copy: the compare + predicated-add form
     const dim3 g3(grid.x, grid.y, (A + NT - 1) / NT);
-    if (in_bf16) attn_hoist_bwd_lrelu_kernel<__nv_bfloat16, __nv_bfloat16><<<g3, NT, 0, s>>>(
-        tab, P, A, (const __nv_bfloat16*)att1, att2, de, wf, (__nv_bfloat16*)datt1, dwf);
-    else attn_hoist_bwd_lrelu_kernel<float, float><<<g3, NT, 0, s>>>(tab, P, A, (const float*)att1, att2, de, wf,
-                                                                    (float*)datt1, dwf);
+    const int Ntok = tab.off[tab.nsteps];
+    const bool full = P % HB_P == 0 && A % NT == 0 && (long long)B * P * A < (1LL << 31) && (long long)Ntok * A < (1LL << 31) &&
+                      (long long)Ntok * P < (1LL << 31);
+#define ST_LAUNCH_L(T, FULL, GT) attn_hoist_bwd_lrelu_kernel<T, T, FULL, GT><<<g3, NT, 0, s>>>(tab, P, A, (const T*)att1, att2, de, wf, (T*)datt1, dwf)
+#define ST_LAUNCH_LF(T) do { if (full) { if (gt) ST_LAUNCH_L(T, true, true); else ST_LAUNCH_L(T, true, false); } \
+                             else { if (gt) ST_LAUNCH_L(T, false, true); else ST_LAUNCH_L(T, false, false); } } while (0)
+    if (in_bf16) ST_LAUNCH_LF(__nv_bfloat16); else ST_LAUNCH_LF(float);
+#undef ST_LAUNCH_LF
+#undef ST_LAUNCH_L
+    if (gt) {
+      ST_LAUNCH_TRY("attn_hoist_bwd_lrelu_kernel");
+      colsum_prod_kernel<<<dim3((A + 255) / 256, (Ntok + CSP_ROWS - 1) / CSP_ROWS), 256, 0, s>>>(dwf, att2, gt, Ntok, A);
+    }
     ST_LAUNCH_TRY("attn_hoist_bwd_lrelu_kernel");
     return ST_OK;
   }

@@ -279,6 +279,7 @@ __global__ void __launch_bounds__(C::SNT) attn_stream_kernel(const int nrows, co
       p.ctx_out[(size_t)b * p.ld_ctx + col] = s;
       if (p.ctx_bf16) p.ctx_bf16[(size_t)b * p.ld_ctx_bf16 + col] = __float2bfloat16(s);
     } else {
+      if (p.gt_out) p.gt_out[(size_t)b * p.A + col] = s;
       s *= p.wf[col];
       p.datt2[(size_t)b * p.A + col] = s;
       if (p.datt2_bf16) p.datt2_bf16[(size_t)b * p.A + col] = __float2bfloat16(s);

@@ -19,6 +19,7 @@ struct StreamParams {
   int dal_stride, ld_dctx;
   float *de_out, *datt2;
   __nv_bfloat16* datt2_bf16;      // optional bf16 copy (rows, A)
+  float* gt_out;                  // optional (rows, A): datt2 before the factor w_f
 };
 
 // Returns 1 if the streaming path handles this shape (and launched it), 0 if the caller must use

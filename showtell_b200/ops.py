@@ -783,7 +783,7 @@ def attn_step_fwd(rows, Pn, att1, Fe, att2, wf, bf, b_embed, alphas_t, alpha_str
 
 
 def attn_step_bwd(rows, Pn, att1, Fe, att2, wf, alphas_t, alpha_stride, dalpha, dalpha_stride, dctx, de_out,
-                  datt2, act=ACT_LEAKY, datt2_bf16=None, tag="attn_bwd"):
+                  datt2, act=ACT_LEAKY, datt2_bf16=None, gt=None, tag="attn_bwd"):
     lib = _lib.load()
     A, E = att1.shape[1], Fe.shape[1]
     tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
@@ -791,14 +791,16 @@ def attn_step_bwd(rows, Pn, att1, Fe, att2, wf, alphas_t, alpha_stride, dalpha, 
                                ptr(wf, F32), _raw(alphas_t), alpha_stride,
                                _raw(dalpha) if dalpha is not None else None, dalpha_stride, _raw(dctx),
                                dctx.stride(0), _raw(de_out), _raw(datt2),
-                               _raw(datt2_bf16) if datt2_bf16 is not None else None, act, stream_ptr()),
+                               _raw(datt2_bf16) if datt2_bf16 is not None else None,
+                               _raw(gt) if gt is not None else None, act, stream_ptr()),
           "st_attn_step_bwd")
     if tok:
         TIMER.end(tok)
 
 
-def attn_hoist_bwd(bs, Pn, att1, att2_all, de_all, wf, want_t=True, act=ACT_LEAKY):
-    """Returns (datt1 (B*P, A), datt1T (A, B*P) or None, dwf (A,)) in att1's storage type."""
+def attn_hoist_bwd(bs, Pn, att1, att2_all, de_all, wf, want_t=True, act=ACT_LEAKY, gt_all=None):
+    """Returns (datt1 (B*P, A), datt1T (A, B*P) or None, dwf (A,)) in att1's storage type.  gt_all (N, A): the tensor
+    attn_step_bwd(gt=...) filled during the reverse loop (optional; lets the pass skip a third of its work)."""
     lib = _lib.load()
     A = att1.shape[1]
     BP = att1.shape[0]
@@ -810,7 +812,8 @@ def attn_hoist_bwd(bs, Pn, att1, att2_all, de_all, wf, want_t=True, act=ACT_LEAK
     isb = int(att1.dtype == BF16)
     check(lib.st_attn_hoist_bwd(len(bs), int_array(bs), Pn, A, _raw(att1), isb, ptr(att2_all, F32),
                                 ptr(de_all, F32), ptr(wf, F32), _raw(datt1), _raw(dT) if want_t else None, ld,
-                                isb, ptr(dwf), act, stream_ptr()), "st_attn_hoist_bwd")
+                                isb, ptr(dwf), ptr(gt_all, F32) if gt_all is not None else None, act, stream_ptr()),
+          "st_attn_hoist_bwd")
     return datt1, dT, dwf
 
 
