@@ -381,6 +381,10 @@ int st_shift_states(float* Hprev, const float* Hs, const float* h0, int H, int n
 int st_shift_states_bf16(void* Hprev, const void* Hs, const void* h0, int H, int nsteps,
                          const int* batch_sizes_host, st_stream_t stream);
 
+/* Development / test aid: 1 = skip the bulk-copy relayout kernel (keeps the register-path kernels reachable for the
+ * parity tests), 0 = default. */
+int st_debug_relayout_legacy(int on);
+
 /* ------------------------------------------------------------------------------------------
  * Soft attention (Attention/rnn_attn.py:8-31 Attention_Net, :60-76 rnn_iterator).  The reference
  * recomputes encoder_att(f) inside every step; here the state-independent parts are hoisted

@@ -42,25 +42,37 @@ def _use_tc(mode, kind, P, B):
     return (E % 8 == 0 and A % 8 == 0 and H % 8 == 0 and ops.rnn_seq_tc_fits(kind, H, B))
 
 
-def attn_forward(mode, P, kind, L, feature, caption, bs, save, layout="BCP"):
-    """Returns (Hs_top (N,H), alphas (B,Tcap,P), saved dict).  layout: "BCP" = the reference's channels-first grid
-    (cnn_attn.py:49), "BPC" = channels-last (the grid IS the (B*P, C) operand: no re-layout pass)."""
+def grid_operands(mode, feature, layout="BCP", out=None):
+    """The decoder's view of the feature grid: F (B*P, C) rows in the compute storage type + the channel means (B, C).
+    layout "BCP" = the reference's channels-first grid (cnn_attn.py:49: one re-layout pass), "BPC" = channels-last
+    (the grid IS the operand).  out = (F, mean_f): write into these (graphs.run's static operands)."""
+    # (no transposed copy of the grid: dW_enc = datt1^T F reads F in place as an MN-major GEMM operand)
     if layout == "BPC":
-        B, Pn, C = feature.shape
+        return ops.attn_grid_bpc(feature, bf16=(mode == "bf16"), out=out)
+    F, _, mean_f = ops.attn_relayout(feature, bf16=(mode == "bf16"), want_t=False, out=out)
+    return F, mean_f
+
+
+def attn_forward(mode, P, kind, L, feature, caption, bs, save, layout="BCP", grid=None):
+    """Returns (Hs_top (N,H), alphas (B,Tcap,P), saved dict).  layout: see grid_operands.  grid = (F, mean_f, Pn): the
+    operands grid_operands already produced (`feature` is then unused)."""
+    if grid is not None:
+        F, mean_f, Pn = grid
+        B, C = mean_f.shape
     else:
-        B, C, Pn = feature.shape
+        if layout == "BPC":
+            B, Pn, C = feature.shape
+        else:
+            B, C, Pn = feature.shape
+        F, mean_f = grid_operands(mode, feature, layout)
+    FT = None
     T, N, off = len(bs), sum(bs), _offsets(bs)
     Tcap = caption.shape[1]
     E = P["embeddings.weight"].shape[1]
-    dev = feature.device
+    dev = F.device
     tc = _use_tc(mode, kind, P, B)
     sv = {"bs": bs, "off": off, "Pn": Pn, "B": B, "tc": tc}
 
-    # (no transposed copy of the grid: dW_enc = datt1^T F reads F in place as an MN-major GEMM operand)
-    if layout == "BPC":
-        (F, mean_f), FT = ops.attn_grid_bpc(feature, bf16=(mode == "bf16")), None
-    else:
-        F, FT, mean_f = ops.attn_relayout(feature, bf16=(mode == "bf16"), want_t=False)
     sv.update(F=F, mean_f=mean_f)
     # rnn_attn.py:62: every layer starts from init_h(mean_P f) (init_c likewise for the LSTM)
     # (a skinny fp32 product: it runs on the side stream beside the hoisted grid projections below)
@@ -461,8 +473,19 @@ class AttnLossFn(torch.autograd.Function):
         coef = float(alpha_c) / (db * f.shape[1 if lay == "BPC" else 2])
         red = getattr(mod, "grad_reducer", None)       # data parallelism: parallel.GradReducer
 
-        def body(feat, capt):
-            Hs, alphas, sv = attn_forward(mode, P, kind, L, feat, capt, bs, need, layout=lay)
+        Pn = f.shape[1 if lay == "BPC" else 2]
+
+        def prologue(inputs, out):
+            # eager, in front of the step graph: the grid is read ONCE, re-laid / cast straight into the graph's
+            # static operands (no device copy of the 200 MB grid into a static input first)
+            F, mean_f = grid_operands(mode, inputs[0], lay, out=None if out is None else (out[0], out[1]))
+            if out is None:
+                return [F, mean_f, inputs[1]]
+            out[2].copy_(inputs[1], non_blocking=True)
+            return out
+
+        def body(F, mean_f, capt):
+            Hs, alphas, sv = attn_forward(mode, P, kind, L, None, capt, bs, need, layout=lay, grid=(F, mean_f, Pn))
             target = ops.pack_targets(capt, bs, P["linear.weight"].shape[0])
             gout = red.slots([P["linear.weight"].shape, P["linear.bias"].shape]) if (red is not None and need) else None
             loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, dt, need, gout=gout)
@@ -497,7 +520,7 @@ class AttnLossFn(torch.autograd.Function):
 
         key = ("attn", mode, kind, L, lay, tuple(bs), tuple(f.shape), str(f.dtype), tuple(cap.shape), need, dt, db, float(alpha_c),
                tuple(p.data_ptr() for p in params))
-        loss, alphas, ctx.grads = graphs.run(mod, key, body, (f, cap))
+        loss, alphas, ctx.grads = graphs.run(mod, key, body, (f, cap), prologue=prologue)
         ctx.names, ctx.mod, ctx.ticket = names, mod, graphs.ticket(mod)
         loss, alphas = loss.clone(), alphas.clone()
         ctx.mark_non_differentiable(alphas)

@@ -26,6 +26,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace st {
 namespace {
@@ -199,6 +200,90 @@ relayout_fast_kernel(const TI* __restrict__ f, int C, int P, __nv_bfloat16* __re
   for (int p = warp; p < P; p += NT / 32) {
     const float2 v = tile2[(size_t)lane * PS2 + p];
     *reinterpret_cast<__nv_bfloat162*>(dst + (size_t)p * C) = __floats2bfloat162_rn(v.x, v.y);
+  }
+}
+
+// The common case again (bf16 F, no transposed copy, C % 64 == 0), bound by HBM instead of by load latency: the 64
+// channel rows of a block are CONTIGUOUS in the channels-first grid, so four bulk copies (cp.async.bulk, 16 rows
+// each) bring the whole 50 KB tile into shared memory with every byte in flight at once -- relayout_fast_kernel
+// walked it with two 16-byte loads per thread at a time (8 dependent round trips per warp, 1 TB/s).  The tile keeps
+// the global layout [channel][location]; a thread then owns one location and 16 channels: 16 conflict-free
+// reads (consecutive lanes = consecutive locations), one 32-byte store into the channels-last row.
+// Persistent blocks (two per SM) walk the tiles with a two-stage ring: the copy of the next tile is issued before the
+// current one is processed, so reads stay in flight through the store phase (one tile per block, 4 blocks per SM,
+// ran all blocks in lock step -- load, then store -- at 4.0 TB/s).  Consecutive tiles are consecutive in the grid.
+constexpr int RL_NT = 512;
+template <typename TI>
+__global__ void __launch_bounds__(RL_NT)
+relayout_bulk_kernel(const TI* __restrict__ f, int C, int P, int ntiles, __nv_bfloat16* __restrict__ F,
+                     float* __restrict__ mean_f) {
+  extern __shared__ __align__(128) uint8_t rl_raw[];
+  __shared__ uint64_t bar[2];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t tile_bytes = (uint32_t)RL_CH * (uint32_t)P * (uint32_t)sizeof(TI);
+  const uint32_t stage_bytes = (tile_bytes + 127u) & ~127u;
+  const int tiles_per_b = C / RL_CH;
+  auto issue = [&](int t, int stage) {             // thread 0: four bulk copies of 16 channel rows each
+    const uint32_t part = tile_bytes / 4;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(f) + (size_t)t * tile_bytes;   // tile t = (b, c0 / RL_CH)
+    mbar_expect_tx(&bar[stage], tile_bytes);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(rl_raw) + stage * stage_bytes + i * part),
+                   "l"(src + (size_t)i * part), "r"(part), "r"(smem_u32(&bar[stage]))
+                   : "memory");
+  };
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    issue(blockIdx.x, 0);
+  }
+  __syncthreads();
+  const float inv_p = 1.f / (float)P;
+  uint32_t ph[2] = {0u, 0u};
+  int stage = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, stage ^= 1) {
+    if (tid == 0 && t + (int)gridDim.x < ntiles) issue(t + gridDim.x, stage ^ 1);   // freed by the barrier below
+    mbar_wait(&bar[stage], ph[stage]);
+    ph[stage] ^= 1u;
+    const TI* tile = reinterpret_cast<const TI*>(rl_raw + stage * stage_bytes);
+    const int b = t / tiles_per_b, c0 = (t - b * tiles_per_b) * RL_CH;
+    {                                              // channel means: a warp sums its RPW rows side by side
+      constexpr int RPW = RL_CH / (RL_NT / 32);
+      const TI* rows = tile + (warp * RPW) * P;
+      float sm[RPW];
+#pragma unroll
+      for (int k = 0; k < RPW; ++k) sm[k] = 0.f;
+      for (int p = lane; p < P; p += 32) {
+#pragma unroll
+        for (int k = 0; k < RPW; ++k) sm[k] += ldf(rows + k * P + p);
+      }
+      float mine = 0.f;
+#pragma unroll
+      for (int k = 0; k < RPW; ++k) {
+        const float v = warp_sum(sm[k]);
+        if (lane == k) mine = v;
+      }
+      if (lane < RPW) mean_f[(size_t)b * C + c0 + warp * RPW + lane] = mine * inv_p;
+    }
+    __nv_bfloat16* dst = F + ((size_t)b * P) * C + c0;
+    for (int it = tid; it < P * (RL_CH / 16); it += RL_NT) {
+      const int g = it / P, p = it - g * P;
+      const TI* tp = tile + (16 * g) * P + p;
+      uint32_t o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(ldf(tp + (2 * i) * P), ldf(tp + (2 * i + 1) * P));
+        o[i] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      // one full 32-byte sector per lane (256-bit store): 16-byte stores left every sector half written per request
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + (size_t)p * C + 16 * g),
+                   "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                   : "memory");
+    }
+    __syncthreads();                               // every read of this stage is done before it is filled again
   }
 }
 
@@ -733,6 +818,9 @@ __global__ void add_rows_kernel(float* __restrict__ dst, const float* __restrict
 
 extern "C" {
 
+static int g_relayout_legacy = 0;
+int st_debug_relayout_legacy(int on) { g_relayout_legacy = on ? 1 : 0; return ST_OK; }
+
 static int relayout_any(const void* f, int f_bf16, int B, int C, int P, void* F, void* FT, int ldft, int out_bf16,
                         float* mean_f, st_stream_t stream) {
   using namespace st;
@@ -744,6 +832,27 @@ static int relayout_any(const void* f, int f_bf16, int B, int C, int P, void* F,
   const size_t smem = sizeof(float) * RL_CH * (size_t)(P | 1);
   ST_REQUIRE(smem <= 200 * 1024, ST_ERR_BAD_SHAPE, "st_attn_relayout: P=%d too large", P);
   cudaStream_t s = as_stream(stream);
+  const size_t tile_bytes = (size_t)RL_CH * P * (f_bf16 ? 2 : 4);
+  const size_t ring_bytes = 2 * ((tile_bytes + 127) & ~(size_t)127);
+  if (out_bf16 && !FT && C % RL_CH == 0 && ring_bytes <= 200 * 1024 && (reinterpret_cast<uintptr_t>(f) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(F) & 31) == 0 && !g_relayout_legacy) {
+    int dev = 0, sms = 0;
+    ST_CUDA_TRY(cudaGetDevice(&dev));
+    ST_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long ntiles = (long long)B * (C / RL_CH);
+    ST_REQUIRE(ntiles < (1ll << 30), ST_ERR_BAD_SHAPE, "st_attn_relayout: grid too large");
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(208 * 1024) / (ring_bytes + 1024)));
+    const int nblk = (int)std::min<long long>(ntiles, (long long)per_sm * sms);
+    if (f_bf16) {
+      ST_CUDA_TRY(cudaFuncSetAttribute(relayout_bulk_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
+      relayout_bulk_kernel<__nv_bfloat16><<<nblk, RL_NT, ring_bytes, s>>>((const __nv_bfloat16*)f, C, P, (int)ntiles, (__nv_bfloat16*)F, mean_f);
+    } else {
+      ST_CUDA_TRY(cudaFuncSetAttribute(relayout_bulk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
+      relayout_bulk_kernel<float><<<nblk, RL_NT, ring_bytes, s>>>((const float*)f, C, P, (int)ntiles, (__nv_bfloat16*)F, mean_f);
+    }
+    ST_LAUNCH_TRY("relayout_bulk_kernel");
+    return ST_OK;
+  }
   if (out_bf16 && !FT && (P & 3) == 0 && C % RL_CH == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(F) & 3) == 0 && (reinterpret_cast<uintptr_t>(mean_f) & 7) == 0) {
     const size_t sm2 = sizeof(float2) * (RL_CH / 2) * (size_t)(P | 1);

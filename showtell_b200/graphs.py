@@ -56,16 +56,31 @@ def check_ticket(mod, tk):
             "several outstanding losses)")
 
 
+def _copy_prologue(inputs, out):
+    """Default prologue: the operands are the inputs themselves (copied into the static operands on replay)."""
+    if out is None:
+        return list(inputs)
+    for dst, src in zip(out, inputs):
+        dst.copy_(src, non_blocking=True)
+    return out
+
+
 def enabled(mod):
     return getattr(mod, "use_cuda_graphs", True) and ops.TIMER is None
 
 
-def run(mod, key, body, inputs):
+def run(mod, key, body, inputs, prologue=None):
     """body(*inputs) -> pytree of tensors (dict / tuple / tensor / None).  Runs it eagerly, or via a
-    captured graph once `key` has been seen often enough."""
+    captured graph once `key` has been seen often enough.
+    prologue(inputs, out) -> operands: an eager pass in front of the graph that turns the caller's inputs into the
+    body's operands -- body(*operands) -- writing them into `out` (the graph's static operands) when it is given.
+    A step whose first kernel re-lays a large input (the attention decoders' 200 MB grid) thereby reads the
+    caller's tensor once, instead of a device copy into a static input followed by the re-layout of that copy."""
     mod.__dict__["_last_run_static"] = False
+    if prologue is None:
+        prologue = _copy_prologue
     if not enabled(mod):
-        return body(*inputs)
+        return body(*prologue(inputs, None))
     cache = mod.__dict__.setdefault("_step_graphs", {})
     e = cache.get(key)
     if e is None:
@@ -74,16 +89,15 @@ def run(mod, key, body, inputs):
         e = cache[key] = _Entry()
     if e.graph is not None:
         ops.refresh_shadows()                     # bf16 weight shadows live outside the graph (ops.bf16_shadow)
-        for dst, src in zip(e.static_in, inputs):
-            dst.copy_(src, non_blocking=True)
+        prologue(inputs, e.static_in)
         e.graph.replay()
         mod.__dict__["_last_run_static"] = True
         return e.out
     e.seen += 1
     if e.failed or e.seen <= _EAGER_CALLS_BEFORE_CAPTURE:
-        return body(*inputs)
+        return body(*prologue(inputs, None))
     try:
-        static_in = [t.clone() for t in inputs]
+        static_in = [t.clone() if t.data_ptr() in {i.data_ptr() for i in inputs} else t for t in prologue(inputs, None)]
         ops.refresh_shadows()                     # fresh before capture: no cast becomes part of the graph
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
@@ -98,4 +112,4 @@ def run(mod, key, body, inputs):
         import warnings
         warnings.warn(f"showtell_b200: CUDA-graph capture failed ({exc}); continuing eagerly")
         torch.cuda.synchronize()
-        return body(*inputs)
+        return body(*prologue(inputs, None))

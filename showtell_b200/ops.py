@@ -735,32 +735,51 @@ def rnn_seq_tc_bwd(kind, WhhT_b, bs, saved, dHs, *, h0=None, c0=None, t_range=No
 ACT_LEAKY, ACT_TANH = 0, 1
 
 
-def attn_relayout(f, bf16=False, want_t=True):
-    """f (B,C,P) fp32 or bf16 channels-first -> F (B*P, C), FT (C, B*P) or None, mean_f (B,C)."""
+def attn_relayout(f, bf16=False, want_t=True, out=None):
+    """f (B,C,P) fp32 or bf16 channels-first -> F (B*P, C), FT (C, B*P) or None, mean_f (B,C).
+    out = (F, mean_f): write into these (a step graph's static operands) instead of fresh tensors."""
     lib = _lib.load()
     B, Cc, Pn = f.shape
     dt = BF16 if bf16 else F32
-    F = torch.empty(B * Pn, Cc, dtype=dt, device=f.device)
+    if out is not None:
+        F, mean_f = out
+        if want_t or F.shape != (B * Pn, Cc) or F.dtype != dt or not F.is_contiguous() or mean_f.shape != (B, Cc):
+            raise ValueError("attn_relayout: out= does not match the grid")
+    else:
+        F = torch.empty(B * Pn, Cc, dtype=dt, device=f.device)
+        mean_f = torch.empty(B, Cc, dtype=F32, device=f.device)
     ld = (B * Pn + 7) // 8 * 8
     FT = torch.empty(Cc, ld, dtype=dt, device=f.device)[:, :B * Pn] if want_t else None
-    mean_f = torch.empty(B, Cc, dtype=F32, device=f.device)
     fn = lib.st_attn_relayout_bf16in if f.dtype == BF16 else lib.st_attn_relayout
     check(fn(ptr(f, f.dtype), B, Cc, Pn, _raw(F), _raw(FT) if want_t else None, ld, int(bf16),
              ptr(mean_f), stream_ptr()), "st_attn_relayout")
     return F, FT, mean_f
 
 
-def attn_grid_bpc(f, bf16=False):
+def attn_grid_bpc(f, bf16=False, out=None):
     """Channels-last grid f (B, P, C) fp32 or bf16 -> F (B*P, C) in the compute storage type (the grid itself when the
-    types agree: no copy), mean_f (B, C) fp32."""
+    types agree: no copy), mean_f (B, C) fp32.  out = (F, mean_f): write into these instead (a step graph's static
+    operands: the cast, or one copy when the types agree, lands there directly)."""
     lib = _lib.load()
     B, Pn, Cc = f.shape
     F = f.reshape(B * Pn, Cc)
-    if bf16 and F.dtype != BF16:
-        F = cast_bf16(F, True, False)[0]
-    elif not bf16 and F.dtype != F32:
-        F = F.to(F32)
-    mean_f = torch.empty(B, Cc, dtype=F32, device=f.device)
+    dt = BF16 if bf16 else F32
+    if out is not None:
+        oF, mean_f = out
+        if oF.shape != F.shape or oF.dtype != dt or not oF.is_contiguous() or mean_f.shape != (B, Cc):
+            raise ValueError("attn_grid_bpc: out= does not match the grid")
+        if bf16 and F.dtype != BF16:
+            check(lib.st_cast_bf16(_raw(F), B * Pn, Cc, F.stride(0), _raw(oF), oF.stride(0), None, 0, stream_ptr()),
+                  "st_cast_bf16")
+        else:
+            oF.copy_(F)
+        F = oF
+    else:
+        if bf16 and F.dtype != BF16:
+            F = cast_bf16(F, True, False)[0]
+        elif not bf16 and F.dtype != F32:
+            F = F.to(F32)
+        mean_f = torch.empty(B, Cc, dtype=F32, device=f.device)
     check(lib.st_grid_mean_bpc(_raw(f), int(f.dtype == BF16), B, Pn, Cc, ptr(mean_f), stream_ptr()), "st_grid_mean_bpc")
     return F, mean_f
 

@@ -231,3 +231,25 @@ def test_channels_last_grid_equals_channels_first(dtype, feat_dtype):
     with pytest.raises(ValueError):
         m.grid_layout = "BPC"
         m.forward_backward(feat, cap, lengths)             # a channels-first tensor under the channels-last setting
+
+
+@pytest.mark.parametrize("legacy", [0, 1])
+@pytest.mark.parametrize("in_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,C,P", [(3, 64, 196), (2, 512, 49), (5, 128, 50), (2, 192, 7), (1, 96, 196)])
+def test_relayout_channels_first_to_last(B, C, P, in_dtype, legacy):
+    """utils.py:37 / rnn_attn.py:62: (B, C, P) grid -> (B*P, C) bf16 rows + channel means.  A relayout and a cast:
+    bit-exact against torch; the means within fp32 rounding.  legacy=1 keeps the register-path kernels covered
+    (C = 96 is not a multiple of the 64-channel tile: always the general kernel)."""
+    from showtell_b200 import _lib, ops
+    torch.manual_seed(B * 1000 + C + P)
+    f = torch.randn(B, C, P, device=DEV).to(in_dtype)
+    lib = _lib.load()
+    lib.st_debug_relayout_legacy(legacy)
+    try:
+        F, _, mean_f = ops.attn_relayout(f, bf16=True, want_t=False)
+    finally:
+        lib.st_debug_relayout_legacy(0)
+    want = f.float().permute(0, 2, 1).reshape(B * P, C).to(torch.bfloat16)
+    assert torch.equal(F, want)
+    ref_mean = f.double().mean(dim=2)
+    assert float((mean_f.double() - ref_mean).abs().max()) < 1e-6
