@@ -297,6 +297,9 @@ int st_allreduce_flag_words(int world);
  * not arrive (the results of that exchange are then undefined).  Reading it costs no synchronisation (mapped host word). */
 int st_allreduce_set_timeout_ms(int64_t ms);
 int st_allreduce_error(void);
+/* Development / A-B aid: world == 2 uses peer loads / stores instead of the multicast reduce (default 1; every rank
+ * must use the same setting). */
+int st_debug_allreduce_pair_p2p(int on);
 int st_allreduce_sum_f32(void* const* peers_host, void* multicast, void* const* flags_host, int rank, int world,
                          int64_t count, int nblocks, st_stream_t stream);
 

@@ -52,6 +52,7 @@ _SIGS = {
     "st_debug_decode_table": (_I, [_I]),
     "st_debug_decode_screen": (_I, [_I]),
     "st_debug_relayout_legacy": (_I, [_I]),
+    "st_debug_allreduce_pair_p2p": (_I, [_I]),
     "st_row_norm_max": (_I, [_P, _I, _I, _P, _P]),
     "st_vocab_topk_screen": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _P, _I, _P]),
     "st_gemm_bf16_screen": (_I, [_I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P]),

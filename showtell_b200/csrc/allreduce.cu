@@ -159,6 +159,48 @@ __global__ void __launch_bounds__(AR_THREADS, 1) allreduce_sum_kernel(const ArPa
   if (threadIdx.x == 0) *my_epoch = epoch + 2;
 }
 
+// Two GPUs: the switch's multicast reduce tops out at ~300 GB/s bus bandwidth there (it pulls BOTH copies through
+// the switch, the requester's own included), plain peer loads / stores move half the bytes over the links.  One peer
+// round trip per unit, so the loop keeps AR_UNROLL2 16-byte peer loads in flight per thread (4 gave 115 GB/s with 16
+// CTAs: latency-bound).  Sums are formed as (rank 0's value) + (rank 1's value) on both ranks: bit-identical.
+constexpr int AR_UNROLL2 = 8;
+__global__ void __launch_bounds__(AR_THREADS, 1) allreduce2_kernel(const ArParams p) {
+  uint32_t* my_epoch = channel(p.flag[p.rank], p.world) + p.world;
+  const uint32_t epoch = *my_epoch;
+  peer_barrier(p, epoch + 1);
+  const long long per = (p.count4 + 1) / 2;
+  const long long lo = min(p.count4, per * p.rank), hi = min(p.count4, lo + per);
+  const long long stride = (long long)gridDim.x * AR_THREADS;
+  float* mine = p.peer[p.rank];
+  float* other = p.peer[p.rank ^ 1];
+  for (long long base = lo + (long long)blockIdx.x * AR_THREADS + threadIdx.x; base < hi; base += stride * AR_UNROLL2) {
+    float4 a[AR_UNROLL2], b[AR_UNROLL2];
+#pragma unroll
+    for (int u = 0; u < AR_UNROLL2; ++u) {
+      const long long i = base + u * stride;
+      if (i < hi) b[u] = ld_peer(other + 4 * i);
+    }
+#pragma unroll
+    for (int u = 0; u < AR_UNROLL2; ++u) {
+      const long long i = base + u * stride;
+      if (i < hi) a[u] = ld_peer(mine + 4 * i);
+    }
+#pragma unroll
+    for (int u = 0; u < AR_UNROLL2; ++u) {
+      const long long i = base + u * stride;
+      if (i >= hi) continue;
+      const float4 x = p.rank == 0 ? a[u] : b[u], y = p.rank == 0 ? b[u] : a[u];      // rank order on both sides
+      const float4 r = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+      st_peer(other + 4 * i, r);
+      st_peer(mine + 4 * i, r);
+    }
+  }
+  peer_barrier(p, epoch + 2);
+  if (threadIdx.x == 0) *my_epoch = epoch + 2;
+}
+
+int g_pair_p2p = 1;   // st_debug_allreduce_pair_p2p
+
 }  // namespace
 }  // namespace st
 
@@ -168,6 +210,11 @@ int st_allreduce_flag_words(int world) { return ST_AR_MAX_BLOCKS * (world + 1); 
 
 int st_allreduce_set_timeout_ms(int64_t ms) {
   st::g_timeout_ns = ms > 0 ? (unsigned long long)ms * 1000000ull : 300ull * 1000000000ull;
+  return ST_OK;
+}
+
+int st_debug_allreduce_pair_p2p(int on) {
+  st::g_pair_p2p = on ? 1 : 0;
   return ST_OK;
 }
 
@@ -209,7 +256,8 @@ int st_allreduce_sum_f32(void* const* peers_host, void* multicast, void* const* 
   p.rank = rank;
   p.world = world;
   p.count4 = count / 4;
-  if (multicast) allreduce_sum_kernel<true><<<nblocks, AR_THREADS, 0, as_stream(stream)>>>(p);
+  if (world == 2 && (g_pair_p2p || !multicast)) allreduce2_kernel<<<nblocks, AR_THREADS, 0, as_stream(stream)>>>(p);
+  else if (multicast) allreduce_sum_kernel<true><<<nblocks, AR_THREADS, 0, as_stream(stream)>>>(p);
   else allreduce_sum_kernel<false><<<nblocks, AR_THREADS, 0, as_stream(stream)>>>(p);
   ST_LAUNCH_TRY("allreduce_sum_kernel");
   return ST_OK;

@@ -20,6 +20,9 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     rank, world = dist.get_rank(), dist.get_world_size()
     force_p2p = os.environ.get("AR_FORCE_P2P", "0") == "1"
+    pair = os.environ.get("AR_PAIR_P2P", "1") == "1"            # world 2: peer loads / stores (default) or multicast
+    from showtell_b200 import _lib
+    _lib.load().st_debug_allreduce_pair_p2p(int(pair))
     for numel in (2048 + 4, 5_120_000 + 10_000, 7_225_344):
         shapes = [(numel,)]
         b = parallel._SymBucket(shapes, None, dev)
@@ -54,7 +57,7 @@ def main():
             t_sym = e0.elapsed_time(e1) / 20
             if rank == 0:
                 print(f"numel {numel:9d} ({numel * 4 / 1e6:6.2f} MB) nblocks {nblocks:2d} "
-                      f"{'multicast' if b.multicast else 'p2p':9s} err {err:.1e} identical {same} "
+                      f"{'pair-p2p' if (world == 2 and pair) else 'multicast' if b.multicast else 'p2p':9s} err {err:.1e} identical {same} "
                       f"{t_sym * 1e3:8.1f} us  busbw {2 * (world - 1) / world * numel * 4 / t_sym / 1e6:7.1f} GB/s",
                       flush=True)
         y = x * 1e-3
