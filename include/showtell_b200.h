@@ -150,8 +150,9 @@ int st_gemm_tf32x3_topk(int M, int N, int K, const float* A_hi, const float* A_l
                         float* row_max, float* row_sum, st_stream_t stream);
 /* Screening pass of the decoding loops: the bf16 product A . B^T + bias with only the ST_SCREEN_SLOTS largest values (and
  * their columns) of every part (128 columns; 64 when N <= 128) kept per row -- cand_val / cand_idx (M, *npart_out,
- * ST_SCREEN_SLOTS), *npart_out * ST_SCREEN_SLOTS <= st_topk_parts(N).  The caller bounds the bf16 rounding error and
- * re-scores the survivors exactly (st_vocab_topk_screen). */
+ * ST_SCREEN_SLOTS), *npart_out * ST_SCREEN_SLOTS <= st_topk_parts(N).  A kept value carries its column's position in the
+ * low 7 mantissa bits (relative perturbation < 2^-16; equal approximations rank lower column first).  The caller bounds
+ * the bf16 rounding error plus that perturbation and re-scores the survivors exactly (st_vocab_topk_screen). */
 enum { ST_SCREEN_SLOTS = 3 };
 int st_gemm_bf16_screen(int M, int N, int K, const void* A_bf16, int lda, const void* B_bf16, int ldb, const float* bias,
                         float* cand_val, int32_t* cand_idx, int* npart_out, st_stream_t stream);

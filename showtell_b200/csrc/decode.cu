@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(256) decode_gate_kernel(int rows, int H, GxSrc
 //        |approx_v - exact_v| <= 2^-8 (1 + 2^-10) sum_i |h_i w_vi| (+ fp32 accumulation)  <=  eps := c |h| max_v |w_v|
 //      (Cauchy-Schwarz; c = 2^-7.9).  With a_K = the K-th largest KEPT approximation (a lower bound of the K-th largest
 //      approximation overall), K columns have exact logits >= a_K - eps, hence so has the K-th largest exact logit, and
-//      every column of the exact top K has an approximation >= tau := a_K - 2 eps;
+//      every column of the exact top K has an approximation >= tau := a_K - 2 eps (the kept values also carry their
+//      column in the low 7 mantissa bits -- gemm_tc.cu -- a further 2^-16 relative, added to eps below);
 //   3. a part whose last kept value is < tau has kept every column >= tau; otherwise ALL of its columns are re-scored;
 //   4. the survivors (typically 5-20 of 10 000) get their exact logit b_v + <h, w_v> in fp32 (one warp per row, fixed
 //      summation order) and the top K of those is the result: value descending, lower column first among equals.
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(256) screen_select_kernel(int M, int H, int V,
     const int32_t* ci = cand_idx + (size_t)m * ncand;
     // a lower bound a_K of the K-th largest approximation: the K-th largest KEPT one (K rounds of warp arg-max with
     // exclusion, as topk_merge_kernel; a part may have dropped some of the overall K largest, which only lowers it)
-    float pv = FLT_MAX;
+    float pv = FLT_MAX, a1 = 0.f;
     int pi = -1;
     for (int k = 0; k < K; ++k) {
       float b = -FLT_MAX;
@@ -293,8 +294,12 @@ __global__ void __launch_bounds__(256) screen_select_kernel(int M, int H, int V,
         if (ov > b || (ov == b && oi < bi)) { b = ov; bi = oi; }
       }
       pv = b; pi = bi;
+      if (k == 0) a1 = b;
     }
-    const float tau = pv - 2.f * eps;
+    // the screening epilogue stores the column's position in the low 7 mantissa bits of a kept value: a relative
+    // perturbation below 2^-16 of values that lie between tau and a_1, bounded here with a factor 2 to spare
+    const float delta = 3.0517578125e-5f * (fmaxf(fabsf(a1), fabsf(pv)) + 2.f * eps);
+    const float tau = pv - 2.f * (eps + delta);
     for (int p0 = 0; p0 < npart; p0 += 32) {         // a lane looks at one part's kept entries (descending)
       const int part = p0 + lane;
       int xi[SL], npass = 0;

@@ -259,16 +259,35 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tbase,
         run_s = fmaf(run_s, expf(run_m - nm), s0);
         run_m = nm;
       }
+      if (EPI == EPI_TOPS) {
+        // Screening keeps APPROXIMATE logits (the caller re-scores the survivors exactly and widens its threshold by
+        // the perturbation, decode.cu): the column's position inside the 128-column part replaces the low 7 mantissa
+        // bits (as 127 - position: among equal values the lower column is the larger number), so the three best are
+        // five min / max per column -- no index registers, no divergent insertion (the (value, index) insertion
+        // below made this epilogue, not the MMAs, the bound of the screening product: 86 us against 55).
+        static_assert(EPI != EPI_TOPS || TS >= 3, "screening keeps 3 per part");
+        const uint32_t e = 127u ^ (uint32_t)(nb & 127);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float x = (full || nb + j < p.N) ? v[j] : -FLT_MAX;
-        if (x > tkv[TS - 1]) {
-          tkv[TS - 1] = x; tki[TS - 1] = nb + j;
+        for (int j = 0; j < 32; ++j) {
+          const float xr = (full || nb + j < p.N) ? v[j] : -FLT_MAX;
+          const float x = __uint_as_float(((__float_as_uint(xr) & 0xffffff80u) | e) ^ (uint32_t)j);
+          const float t = fminf(tkv[0], x);
+          tkv[2] = fmaxf(tkv[2], fminf(tkv[1], t));
+          tkv[1] = fmaxf(tkv[1], t);
+          tkv[0] = fmaxf(tkv[0], x);
+        }
+      } else {
 #pragma unroll
-          for (int q = TS - 1; q > 0; --q) {
-            if (tkv[q] > tkv[q - 1]) {
-              const float tv = tkv[q]; tkv[q] = tkv[q - 1]; tkv[q - 1] = tv;
-              const int ti = tki[q]; tki[q] = tki[q - 1]; tki[q - 1] = ti;
+        for (int j = 0; j < 32; ++j) {
+          const float x = (full || nb + j < p.N) ? v[j] : -FLT_MAX;
+          if (x > tkv[TS - 1]) {
+            tkv[TS - 1] = x; tki[TS - 1] = nb + j;
+#pragma unroll
+            for (int q = TS - 1; q > 0; --q) {
+              if (tkv[q] > tkv[q - 1]) {
+                const float tv = tkv[q]; tkv[q] = tkv[q - 1]; tkv[q - 1] = tv;
+                const int ti = tki[q]; tki[q] = tki[q - 1]; tki[q - 1] = ti;
+              }
             }
           }
         }
@@ -366,6 +385,11 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, uint32_t tbase,
   if (TOPX && row_ok) {
     float* ov = p.tk_val + ((size_t)row * p.npart + part) * p.tk_k;
     int32_t* oi = p.tk_idx + ((size_t)row * p.npart + part) * p.tk_k;
+    if (EPI == EPI_TOPS) {                           // the column rides in the value's low bits
+      const int col0 = (n0 + chunk0 * 32) & ~127;    // the 128-aligned block this warp's part lies in
+#pragma unroll
+      for (int q = 0; q < TS; ++q) tki[q] = col0 + 127 - (int)(__float_as_uint(tkv[q]) & 127u);
+    }
 #pragma unroll
     for (int q = 0; q < TS; ++q)
       if (q < p.tk_k) { ov[q] = tkv[q]; oi[q] = tki[q]; }
