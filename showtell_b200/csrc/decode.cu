@@ -12,6 +12,7 @@
 //     kernel gathers by token id.
 // A per-image bookkeeping kernel reproduces the reference's ranking rules (documented at each kernel).
 #include <cuda_bf16.h>
+#include <type_traits>
 
 #include <cfloat>
 
@@ -217,9 +218,14 @@ __device__ __forceinline__ void topk_insert(float (&bv)[KMAX], int (&bi)[KMAX], 
   }
 }
 
-constexpr int SC_CAND = 64, SC_OVER = 8;   // per row: survivors re-scored one by one / parts re-scored as a whole
+constexpr int SC_CAND = 64, SC_OVER = 96;  // per row: survivors re-scored one by one / parts re-scored as a whole
+constexpr int SC_PPL = 3;                  // fast path: a lane owns the kept values of up to 3 parts (npart <= 96)
 
-__global__ void __launch_bounds__(256) screen_select_kernel(int M, int H, int V, int npart, int part_cols, int K,
+// KMAX: list length (4 for K <= 4: the insertion is a third of the instructions of a re-scored column).
+// A kept value carries its column: (128-aligned base of its part) + 127 - (low 7 mantissa bits)  (gemm_tc.cu, EPI_TOPS);
+// cand_idx is what the screening GEMM wrote for the general path (npart > 96).
+template <int KMAX>
+__global__ void __launch_bounds__(256, 4) screen_select_kernel(int M, int H, int V, int npart, int part_cols, int K,
                                                             const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx,
                                                             const float* __restrict__ h, const float* __restrict__ Wv,
                                                             const float* __restrict__ bv, const float* __restrict__ wmax,
@@ -227,123 +233,221 @@ __global__ void __launch_bounds__(256) screen_select_kernel(int M, int H, int V,
                                                             int64_t* __restrict__ tok, int tok_stride) {
   extern __shared__ __align__(16) float s_h[];      // [8 warps][H]
   __shared__ int s_cand[8][SC_CAND];                // survivors of each warp's row
-  __shared__ int s_over[8][SC_OVER], s_nover[8];    // parts of each warp's row that are re-scored as a whole
+  __shared__ unsigned short s_over[8][SC_OVER];     // parts of each warp's row that are re-scored as a whole (the fast
+  __shared__ int s_nover[8];                        // path has at most SC_OVER parts: the list cannot overflow there)
   __shared__ float s_res[128];                      // exact logits of one such part (phase B)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, m = blockIdx.x * 8 + wid;
   const bool valid = m < M;
   float* hs = s_h + (size_t)wid * H;
-  constexpr int SL = ST_SCREEN_SLOTS, KMAX = 8;
+  constexpr int SL = ST_SCREEN_SLOTS;
+  // 128-bit path of the exact dot products (H = 512 at the bench dims)
+  const bool vec = (H & 127) == 0 && ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(Wv)) & 15) == 0;
   float bestv[KMAX];
   int besti[KMAX];
 #pragma unroll
   for (int q = 0; q < KMAX; ++q) { bestv[q] = -FLT_MAX; besti[q] = 0x7fffffff - q; }
-  // exact logits of two columns of a row whose state sits in `hrow` (shared memory): lane j sums the elements
-  // i = j (mod 32) in increasing order, the 32 partial sums meet in the xor-shuffle tree (a fixed summation order:
-  // a column's value does not depend on who computes it); every lane ends with both values.  All loads of a
-  // 512-element block of both rows are in flight before the first multiply.
+  // exact logits of two columns of a row whose state sits in `hrow` (shared memory).  A fixed summation order: lane j
+  // sums its elements in increasing order (vec: the float4s j, j + 32, ... of the row, x y z w in turn; else the
+  // elements i = j mod 32), the 32 partial sums meet in the xor-shuffle tree -- a column's value does not depend on
+  // who computes it; every lane ends with both values.  All loads of a 512-element block of both rows are in flight
+  // before the first multiply.
   auto exact2 = [&](const float* hrow, int va, int vb, float& sa, float& sb) {
     const float* wa = Wv + (size_t)va * H;
     const float* wb = Wv + (size_t)vb * H;
     const float ba = bv[va], bb = bv[vb];              // issued with the rows, not after the reduction
     sa = 0.f; sb = 0.f;
-    for (int i0 = 0; i0 < H; i0 += 512) {
-      float xa[16], xb[16];
+    if (vec) {
+      const float4* wa4 = reinterpret_cast<const float4*>(wa);
+      const float4* wb4 = reinterpret_cast<const float4*>(wb);
+      const float4* h4 = reinterpret_cast<const float4*>(hrow);
+      const int n4 = H >> 2;
+      if ((n4 & 127) == 0) {                           // H a multiple of 512: four 128-bit loads per column in flight
+        for (int i0 = 0; i0 < n4; i0 += 128) {
+          float4 xa[4], xb[4];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int i = i0 + lane + 32 * j;
-        xa[j] = i < H ? wa[i] : 0.f;
-        xb[j] = i < H ? wb[i] : 0.f;
+          for (int j = 0; j < 4; ++j) {
+            xa[j] = __ldg(wa4 + i0 + lane + 32 * j);
+            xb[j] = __ldg(wb4 + i0 + lane + 32 * j);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 hv = h4[i0 + lane + 32 * j];
+            sa = fmaf(hv.x, xa[j].x, sa); sa = fmaf(hv.y, xa[j].y, sa); sa = fmaf(hv.z, xa[j].z, sa); sa = fmaf(hv.w, xa[j].w, sa);
+            sb = fmaf(hv.x, xb[j].x, sb); sb = fmaf(hv.y, xb[j].y, sb); sb = fmaf(hv.z, xb[j].z, sb); sb = fmaf(hv.w, xb[j].w, sb);
+          }
+        }
+      } else {                                         // same order of additions, one load per column at a time
+        for (int i = lane; i < n4; i += 32) {
+          const float4 xa = __ldg(wa4 + i), xb = __ldg(wb4 + i), hv = h4[i];
+          sa = fmaf(hv.x, xa.x, sa); sa = fmaf(hv.y, xa.y, sa); sa = fmaf(hv.z, xa.z, sa); sa = fmaf(hv.w, xa.w, sa);
+          sb = fmaf(hv.x, xb.x, sb); sb = fmaf(hv.y, xb.y, sb); sb = fmaf(hv.z, xb.z, sb); sb = fmaf(hv.w, xb.w, sb);
+        }
       }
+    } else {
+      for (int i0 = 0; i0 < H; i0 += 512) {
+        float xa[16], xb[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int i = i0 + lane + 32 * j;
-        if (i < H) { const float hv = hrow[i]; sa = fmaf(hv, xa[j], sa); sb = fmaf(hv, xb[j], sb); }
+        for (int j = 0; j < 16; ++j) {
+          const int i = i0 + lane + 32 * j;
+          xa[j] = i < H ? wa[i] : 0.f;
+          xb[j] = i < H ? wb[i] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int i = i0 + lane + 32 * j;
+          if (i < H) { const float hv = hrow[i]; sa = fmaf(hv, xa[j], sa); sb = fmaf(hv, xb[j], sb); }
+        }
       }
     }
     sa = warp_sum(sa) + ba;
     sb = warp_sum(sb) + bb;
   };
+  auto part_first = [&](int pt) { return (pt >> 1) * (2 * part_cols) + (pt & 1) * part_cols; };
   int ncnd = 0, nover = 0;
+  // one 32-part group of the threshold pass: lane's part `part` kept xv[] (descending) at columns xi[]
+  auto threshold_group = [&](auto may_overflow, int p0, int part, const float (&xv)[SL], const int (&xi)[SL], float tau) {
+    int npass = 0;
+#pragma unroll
+    for (int q = 0; q < SL; ++q)
+      if (part < npart && xv[q] >= tau && xi[q] >= 0 && xi[q] < V) npass = q + 1;
+    // a part whose LAST kept value still passes may have dropped columns that pass: all of its columns are re-scored
+    // (so are parts whose survivors no longer fit the list)
+    bool whole = npass == SL;
+    const int mine = whole ? 0 : npass;
+    int before = mine;                              // inclusive prefix sum over the lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, before, o);
+      if (lane >= o) before += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, before, 31);
+    if (ncnd + total > SC_CAND) whole = whole || npass > 0;
+    else {
+#pragma unroll
+      for (int q = 0; q < SL - 1; ++q)
+        if (q < mine) s_cand[wid][ncnd + before - mine + q] = xi[q];
+    }
+    if (ncnd + total <= SC_CAND) ncnd += total;
+    unsigned over = __ballot_sync(0xffffffffu, whole);
+    while (over) {
+      const int b = __ffs(over) - 1;
+      over &= over - 1;
+      if (!decltype(may_overflow)::value || (nover < SC_OVER && p0 + b < 65536)) {
+        if (lane == 0) s_over[wid][nover] = (unsigned short)(p0 + b);
+        ++nover;
+      } else if constexpr (decltype(may_overflow)::value) {   // (list full: re-scored right here)
+        const int v0 = part_first(p0 + b), v1 = min(V, v0 + part_cols);
+        for (int v = v0; v < v1; v += 2) {
+          float sa, sb;
+          exact2(hs, v, min(v + 1, v1 - 1), sa, sb);
+          topk_insert<KMAX>(bestv, besti, sa, v);
+          if (v + 1 < v1) topk_insert<KMAX>(bestv, besti, sb, v + 1);
+        }
+      }
+    }
+  };
   if (valid) {
     // ---- phase A: this warp's row.  State and its norm; the bound; a_K; survivors and parts to re-score as a whole
+    const int ncand = npart * SL;
+    const float* cv = cand_val + (size_t)m * ncand;
+    const bool fast = npart <= 32 * SC_PPL;
+    float kv[SC_PPL][SL];                            // fast path: kept values of the parts lane, lane + 32, lane + 64
+    if (fast) {
+#pragma unroll
+      for (int a = 0; a < SC_PPL; ++a) {
+        const int part = lane + 32 * a;
+#pragma unroll
+        for (int q = 0; q < SL; ++q) kv[a][q] = part < npart ? cv[part * SL + q] : -FLT_MAX;
+      }
+    }
     float hh = 0.f;
-    for (int i = lane; i < H; i += 32) { const float v = h[(size_t)m * H + i]; hs[i] = v; hh = fmaf(v, v, hh); }
+    if (vec) {
+      const float4* src = reinterpret_cast<const float4*>(h + (size_t)m * H);
+      for (int i = lane; i < (H >> 2); i += 32) {
+        const float4 v = src[i];
+        reinterpret_cast<float4*>(hs)[i] = v;
+        hh = fmaf(v.x, v.x, hh); hh = fmaf(v.y, v.y, hh); hh = fmaf(v.z, v.z, hh); hh = fmaf(v.w, v.w, hh);
+      }
+    } else {
+      for (int i = lane; i < H; i += 32) { const float v = h[(size_t)m * H + i]; hs[i] = v; hh = fmaf(v, v, hh); }
+    }
     hh = warp_sum(hh);
     __syncwarp();
     const float eps = SCREEN_C * sqrtf(hh) * (*wmax);
-    const int ncand = npart * SL;
-    const float* cv = cand_val + (size_t)m * ncand;
-    const int32_t* ci = cand_idx + (size_t)m * ncand;
-    // a lower bound a_K of the K-th largest approximation: the K-th largest KEPT one (K rounds of warp arg-max with
-    // exclusion, as topk_merge_kernel; a part may have dropped some of the overall K largest, which only lowers it)
+    // a lower bound a_K of the K-th largest approximation: the K-th largest KEPT one (a part may have dropped some of
+    // the overall K largest, which only lowers it).  K rounds of {warp maximum, one instance of it removed}.
     float pv = FLT_MAX, a1 = 0.f;
-    int pi = -1;
-    for (int k = 0; k < K; ++k) {
-      float b = -FLT_MAX;
-      int bi = 0x7fffffff;
-      for (int c = lane; c < ncand; c += 32) {
-        const float x = cv[c];
-        const int i = ci[c];
-        const bool after_prev = (x < pv) || (x == pv && i > pi);
-        if (after_prev && ((x > b) || (x == b && i < bi))) { b = x; bi = i; }
-      }
+    if (fast) {
+      float w[SC_PPL * SL];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, b, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > b || (ov == b && oi < bi)) { b = ov; bi = oi; }
+      for (int a = 0; a < SC_PPL; ++a)
+#pragma unroll
+        for (int q = 0; q < SL; ++q) w[a * SL + q] = kv[a][q];
+      for (int k = 0; k < K; ++k) {
+        float lm = w[0];
+#pragma unroll
+        for (int j = 1; j < SC_PPL * SL; ++j) lm = fmaxf(lm, w[j]);
+        const float gm = warp_max(lm);
+        const int owner = __ffs(__ballot_sync(0xffffffffu, lm == gm)) - 1;
+        bool open = lane == owner;
+#pragma unroll
+        for (int j = 0; j < SC_PPL * SL; ++j) {
+          const bool hit = open && w[j] == gm;
+          w[j] = hit ? -FLT_MAX : w[j];
+          open = open && !hit;
+        }
+        pv = gm;
+        if (k == 0) a1 = gm;
       }
-      pv = b; pi = bi;
-      if (k == 0) a1 = b;
+    } else {
+      const int32_t* ci = cand_idx + (size_t)m * ncand;
+      int pi = -1;
+      for (int k = 0; k < K; ++k) {
+        float b = -FLT_MAX;
+        int bi = 0x7fffffff;
+        for (int c = lane; c < ncand; c += 32) {
+          const float x = cv[c];
+          const int i = ci[c];
+          const bool after_prev = (x < pv) || (x == pv && i > pi);
+          if (after_prev && ((x > b) || (x == b && i < bi))) { b = x; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, b, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > b || (ov == b && oi < bi)) { b = ov; bi = oi; }
+        }
+        pv = b; pi = bi;
+        if (k == 0) a1 = b;
+      }
     }
     // the screening epilogue stores the column's position in the low 7 mantissa bits of a kept value: a relative
     // perturbation below 2^-16 of values that lie between tau and a_1, bounded here with a factor 2 to spare
     const float delta = 3.0517578125e-5f * (fmaxf(fabsf(a1), fabsf(pv)) + 2.f * eps);
     const float tau = pv - 2.f * (eps + delta);
-    for (int p0 = 0; p0 < npart; p0 += 32) {         // a lane looks at one part's kept entries (descending)
-      const int part = p0 + lane;
-      int xi[SL], npass = 0;
+    if (fast) {
 #pragma unroll
-      for (int q = 0; q < SL; ++q) {
-        const float x = part < npart ? cv[part * SL + q] : -FLT_MAX;
-        xi[q] = part < npart ? ci[part * SL + q] : -1;
-        if (x >= tau && xi[q] >= 0 && xi[q] < V) npass = q + 1;
-      }
-      // a part whose LAST kept value still passes may have dropped columns that pass: all of its columns are re-scored
-      // (so are parts whose survivors no longer fit the list)
-      bool whole = npass == SL;
-      const int mine = whole ? 0 : npass;
-      int before = mine;                              // inclusive prefix sum over the lanes
+      for (int a = 0; a < SC_PPL; ++a) {
+        if (32 * a >= npart) break;                   // warp-uniform
+        const int part = lane + 32 * a;
+        const int base = part_first(part) & ~127;
+        int xi[SL];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, before, o);
-        if (lane >= o) before += t;
+        for (int q = 0; q < SL; ++q) xi[q] = base + 127 - (int)(__float_as_uint(kv[a][q]) & 127u);
+        threshold_group(std::false_type{}, 32 * a, part, kv[a], xi, tau);
       }
-      const int total = __shfl_sync(0xffffffffu, before, 31);
-      if (ncnd + total > SC_CAND) whole = whole || npass > 0;
-      else {
+    } else {
+      const int32_t* ci = cand_idx + (size_t)m * ncand;
+      for (int p0 = 0; p0 < npart; p0 += 32) {       // a lane looks at one part's kept entries (descending)
+        const int part = p0 + lane;
+        float xv[SL];
+        int xi[SL];
 #pragma unroll
-        for (int q = 0; q < SL - 1; ++q)
-          if (q < mine) s_cand[wid][ncnd + before - mine + q] = xi[q];
-      }
-      if (ncnd + total <= SC_CAND) ncnd += total;
-      unsigned over = __ballot_sync(0xffffffffu, whole);
-      while (over) {
-        const int b = __ffs(over) - 1;
-        over &= over - 1;
-        if (nover < SC_OVER) {
-          if (lane == 0) s_over[wid][nover] = p0 + b;
-          ++nover;
-        } else {                                      // (more such parts than the list holds: re-scored right here)
-          const int pt = p0 + b;
-          const int v0 = (pt >> 1) * (2 * part_cols) + (pt & 1) * part_cols, v1 = min(V, v0 + part_cols);
-          for (int v = v0; v < v1; v += 2) {
-            float sa, sb;
-            exact2(hs, v, min(v + 1, v1 - 1), sa, sb);
-            topk_insert<KMAX>(bestv, besti, sa, v);
-            if (v + 1 < v1) topk_insert<KMAX>(bestv, besti, sb, v + 1);
-          }
+        for (int q = 0; q < SL; ++q) {
+          xv[q] = part < npart ? cv[part * SL + q] : -FLT_MAX;
+          xi[q] = part < npart ? ci[part * SL + q] : -1;
         }
+        threshold_group(std::true_type{}, p0, part, xv, xi, tau);
       }
     }
     __syncwarp();
@@ -362,7 +466,7 @@ __global__ void __launch_bounds__(256) screen_select_kernel(int M, int H, int V,
     const int n = s_nover[wo];                        // block-uniform
     for (int e = 0; e < n; ++e) {
       const int pt = s_over[wo][e];
-      const int v0 = (pt >> 1) * (2 * part_cols) + (pt & 1) * part_cols, v1 = min(V, v0 + part_cols);
+      const int v0 = part_first(pt), v1 = min(V, v0 + part_cols);
       const int per = (part_cols + 7) / 8;
       for (int j = 0; j < per; j += 2) {
         const int va = v0 + wid * per + j, vb = va + 1;
@@ -926,8 +1030,12 @@ int st_vocab_topk_screen(int M, int V, int H, const float* h, const void* h_bf16
   int npart = 0;
   ST_TRY(st_gemm_bf16_screen(M, V, H, h_bf16, H, Wv_bf16, H, bv, cand_val, cand_idx, &npart, stream));
   const int part_cols = V > 128 ? 128 : 64;
-  screen_select_kernel<<<(M + 7) / 8, 256, (size_t)8 * H * sizeof(float), as_stream(stream)>>>(
-      M, H, V, npart, part_cols, K, cand_val, cand_idx, h, Wv, bv, wmax, val, idx, out_stride, tok, tok_stride);
+  if (K <= 4)
+    screen_select_kernel<4><<<(M + 7) / 8, 256, (size_t)8 * H * sizeof(float), as_stream(stream)>>>(
+        M, H, V, npart, part_cols, K, cand_val, cand_idx, h, Wv, bv, wmax, val, idx, out_stride, tok, tok_stride);
+  else
+    screen_select_kernel<8><<<(M + 7) / 8, 256, (size_t)8 * H * sizeof(float), as_stream(stream)>>>(
+        M, H, V, npart, part_cols, K, cand_val, cand_idx, h, Wv, bv, wmax, val, idx, out_stride, tok, tok_stride);
   ST_LAUNCH_TRY("screen_select_kernel");
   return ST_OK;
 }
