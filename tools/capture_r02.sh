@@ -20,7 +20,7 @@ ls -la /tmp/${T}_lstm_full.ncu-rep
 # 3. attention-GRU: the big GEMMs, one recurrent step pair and one attention step pair
 STEP="python tools/ncu_step.py attn_gru 128 196 bf16"
 $STEP > /dev/null 2>&1 && \
-ncu --set full --clock-control none --profile-from-start off -k regex:"gemm_tc_kernel|rnn_step_x|attn_stream" -c 48 -f -o /tmp/${T}_attn_full $STEP > gpurun_out/${T}_ncu_full_attn.log 2>&1
+ncu --set full --clock-control none --profile-from-start off -k regex:"gemm_tc|rnn_step_x|attn_stream|relayout|hoist|embed_q" -c 64 -f -o /tmp/${T}_attn_full $STEP > gpurun_out/${T}_ncu_full_attn.log 2>&1
 echo "full attn rc=$?"
 ncu -i /tmp/${T}_attn_full.ncu-rep --page raw --csv > gpurun_out/${T}_attn_full_raw.csv 2>/dev/null
 ls -la /tmp/${T}_attn_full.ncu-rep
@@ -29,4 +29,10 @@ CMD="python bench.py --workload beam3 --steps 1 --warmup 3 --no-cpu-baseline --n
 $CMD > gpurun_out/${T}_plain_beam.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/${T}_launches_beam3.csv $CMD > gpurun_out/${T}_ncu_list_beam.log 2>&1
 echo "list beam rc=$?"
+# 5. ncu --set full of the decode-step kernels (screening GEMM, select, W_hh 3xTF32, gate) of a beam-3 call
+STEP="python tools/run_beam_once.py 3 4096"
+$STEP > /dev/null 2>&1 && \
+ncu --set full --clock-control none -k regex:"gemm_tc2|screen_select|tf32x3|decode_gate" -s 40 -c 8 -f -o /tmp/${T}_beam_full $STEP > gpurun_out/${T}_ncu_full_beam.log 2>&1
+echo "full beam rc=$?"
+ncu -i /tmp/${T}_beam_full.ncu-rep --page raw --csv > gpurun_out/${T}_beam_full_raw.csv 2>/dev/null
 du -sh gpurun_out
