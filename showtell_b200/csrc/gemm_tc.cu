@@ -65,6 +65,7 @@ enum { EPI_STORE = 0, EPI_CE_FWD = 1, EPI_CE_BWD = 2, EPI_TOPK = 3, EPI_TOPS = 4
 constexpr int TOPK_SLOTS = 8;   // per-row candidates kept per epilogue warp (K <= 8 on the fused path)
 int g_variant = 0;   // st_debug_gemm_variant: 0 = choose, 128 / 256 = single-CTA tile width, 2 = CTA pairs
 int g_streamk = 1;   // st_debug_gemm_variant(v | 0x1000) turns stream-K off
+int g_tf32_bn192 = 1; // st_debug_gemm_variant(v | 0x20000) turns the 192-column tiles of the 3xTF32 product off
 int g_mn3d = 1;      // st_debug_gemm_variant(v | 0x2000): MN-major operands through 2-D boxes (A/B timing)
 int g_sm_limit = 0;  // st_gemm_set_sm_limit: cap on the persistent grids (0 = all SMs)
 inline int gemm_sms(int* sms) {
@@ -653,8 +654,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // 32-column k-blocks A_hi | A_lo | B_hi | B_lo.
 template <int BN> struct Tf32Cfg {
   static constexpr uint32_t A_B = BM * 128, B_B = BN * 128, STAGE_BYTES = 2 * (A_B + B_B);
-  static constexpr int STAGES = (BN == 256) ? 2 : 3;
-  static constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;
+  static constexpr int STAGES = (BN == 128) ? 3 : 2;
+  static constexpr uint32_t TMEM_COLS = (ACC_STAGES * BN <= 256) ? 256 : 512;   // power of two (192-column tiles: 384 -> 512)
   static constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + STG_BYTES + 256;
 };
 
@@ -1359,8 +1360,21 @@ int st_gemm_tf32x3(int M, int N, int K, const float* A_hi, const float* A_lo, in
   p.C = C; p.ldc = ldc; p.c_bf16 = 0; p.bias = bias; p.alpha = alpha; p.beta = beta;
   int sms = 0;
   ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
-  return pick_bn(M, N, sms) == 256 ? launch_tf32x3<256>(p, A_hi, A_lo, lda, B_hi, B_lo, ldb, as_stream(stream), sms)
-                                   : launch_tf32x3<128>(p, A_hi, A_lo, lda, B_hi, B_lo, ldb, as_stream(stream), sms);
+  // Tile width by modelled time: waves of tiles x operand bytes per tile (this product streams (BM + BN) x K x 8 bytes
+  // per tile and is bound by that stream).  4096 x 1536 (the decode step's W_hh product): 192 tiles of 256 columns are
+  // 1.3 waves on 148 SMs and run as 2; 256 tiles of 192 columns are 2 shorter ones.
+  const long mt = (M + BM - 1) / BM;
+  long best = -1;
+  int bn = 256;
+  for (int c : {256, 192, 128}) {
+    if (c == 192 && (g_tf32_bn192 == 0 || N < 384)) continue;
+    const long tiles = mt * ((N + c - 1) / c), waves = (tiles + sms - 1) / sms, cost = waves * (BM + c);
+    if (best < 0 || cost < best) { best = cost; bn = c; }
+  }
+  if (N <= 128) bn = 128;
+  if (bn == 256) return launch_tf32x3<256>(p, A_hi, A_lo, lda, B_hi, B_lo, ldb, as_stream(stream), sms);
+  if (bn == 192) return launch_tf32x3<192>(p, A_hi, A_lo, lda, B_hi, B_lo, ldb, as_stream(stream), sms);
+  return launch_tf32x3<128>(p, A_hi, A_lo, lda, B_hi, B_lo, ldb, as_stream(stream), sms);
 }
 
 int st_topk_parts(int N) { return 2 * ((N + 127) / 128) * st::TOPK_SLOTS; }
@@ -1419,6 +1433,7 @@ int st_gemm_bf16_screen(int M, int N, int K, const void* A, int lda, const void*
 
 int st_debug_gemm_variant(int variant) {
   st::g_streamk = (variant & 0x1000) ? 0 : 1;
+  st::g_tf32_bn192 = (variant & 0x20000) ? 0 : 1;
   st::g_mn3d = (variant & 0x2000) ? 0 : 1;
   st::g_mc = (variant & 0x4000) ? 1 : ((variant & 0x8000) ? -1 : 0);
   st::g_pair_auto = (variant & 0x10000) ? 0 : 1;
