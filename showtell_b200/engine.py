@@ -89,7 +89,20 @@ def stack_forward(mode, P, kind, L, X, bs, save):
     return layers[-1]["out"]["Hs"], layers
 
 
-def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True, dx0_ready=None, after_bptt=None):
+def bptt_prealloc(P, kind, L, bs, layers):
+    """Buffers of the tensor-core BPTT kernels, created (and the two small ones zero-filled) on a side stream: called
+    before the vocabulary products are issued, so nothing but the dHs product stands between them and the BPTT kernel
+    (the fills used to sit there: ~10 us of launch latency on the critical path).  {layer: (buffers, event)}."""
+    pre = {}
+    for l in range(L):
+        if layers[l]["tc"]:
+            WhhT = ops.bf16_shadow(layer_params(P, l)[1], transposed=True)
+            pre[l] = ops.fork(lambda W=WhhT: ops.rnn_seq_tc_bwd_buffers(kind, W, bs, W.device), lane=6)
+    return pre
+
+
+def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True, dx0_ready=None, after_bptt=None,
+                   prealloc=None):
     """BPTT through the L layers, top down.  Fills grads[...] for the unit.* parameters and returns
     the gradient w.r.t. the packed layer-0 input (N, in_0).  `dx0_ready(dX)`: called as soon as that
     input gradient exists (bf16 mode: before layer 0's weight-gradient products), so the embedding
@@ -102,7 +115,11 @@ def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True, 
         sv = layers[l]
         b = None
         if sv["tc"]:
-            b = ops.rnn_seq_tc_bwd(kind, ops.bf16_shadow(Whh, transposed=True), bs, sv["out"], dH, tag="seq_bwd")
+            bufs = None
+            if prealloc is not None and l in prealloc:
+                bufs, ev = prealloc[l]
+                ops.join(ev)
+            b = ops.rnn_seq_tc_bwd(kind, ops.bf16_shadow(Whh, transposed=True), bs, sv["out"], dH, tag="seq_bwd", out=bufs)
             if b is not None and after_bptt is not None and l == L - 1:
                 after_bptt()
                 after_bptt = None
@@ -147,7 +164,7 @@ def base_forward(mode, P, kind, L, feature, caption, bs, save):
 
 
 def base_backward_from_dHs(mode, P, kind, L, caption, bs, layers, dHs, grads, want_dfeature, feature_shape,
-                           emb_out=None, emb_done=None, after_bptt=None):
+                           emb_out=None, emb_done=None, after_bptt=None, prealloc=None):
     """`emb_out()` / `emb_done()`: data parallelism -- buffer for the embedding gradient, and a call
     the moment it is final (the layer-0 weight gradients are formed after it)."""
     box = {}
@@ -163,7 +180,8 @@ def base_backward_from_dHs(mode, P, kind, L, caption, bs, layers, dHs, grads, wa
         if emb_done is not None:
             emb_done()
 
-    stack_backward(mode, P, kind, L, bs, layers, dHs, grads, dx0_ready=dx0_ready, after_bptt=after_bptt)
+    stack_backward(mode, P, kind, L, bs, layers, dHs, grads, dx0_ready=dx0_ready, after_bptt=after_bptt,
+                   prealloc=prealloc)
     return box["dfeat"]
 
 
@@ -240,6 +258,8 @@ def vocab_ce(mode, P, Hs, target, denom, need, gout=None, Hs_bf16=None, side_sms
     Wb = ops.bf16_shadow(Wv)
     Hb = Hs_bf16 if Hs_bf16 is not None else _bf16(Hs)
     loss_sum, lse = ops.vocab_ce_fwd(Hb, Wb, bv, target, tag="vocab_fwd")
+    # (the mean: a one-element kernel, kept off the main stream -- there it sat between the dHs product and BPTT)
+    loss, loss_done = ops.fork(lambda: (loss_sum / denom).reshape(()), uses=(loss_sum,), lane=7)
     dHs, done = None, None
     if need:
         # dlogits = (softmax - onehot) / denom recomputed tile by tile and written ONCE, row-major bf16; the three
@@ -259,7 +279,8 @@ def vocab_ce(mode, P, Hs, target, denom, need, gout=None, Hs_bf16=None, side_sms
         else:
             grads["linear.bias"] = db
         dHs = ops.gemm_bf16(Pm, Wb, b_t=True, tag="vocab_dx")
-    return (loss_sum / denom).reshape(()), dHs, grads, done
+    ops.join(loss_done)
+    return loss, dHs, grads, done
 
 
 class DirectCtx:
@@ -316,6 +337,7 @@ class BaseLossFn(torch.autograd.Function):
             defer = False     # measured: the sums then lengthen the backward tail by what they save in front of BPTT
             lin = ["linear.weight"] if defer else ["linear.weight", "linear.bias"]
             gout = red.slots([P[n].shape for n in lin]) if (red is not None and need) else None
+            pre = bptt_prealloc(P, kind, L, bs, layers) if need else None
             loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, denom, need, gout=gout, defer_db=defer,
                                                Hs_bf16=layers[-1]["out"]["Hsb"] if layers[-1]["tc"] else None)
             late = grads.pop("_late_db", None)
@@ -328,7 +350,7 @@ class BaseLossFn(torch.autograd.Function):
             dfeat = None
             if need and red is None:
                 dfeat = base_backward_from_dHs(mode, P, kind, L, cap, bs, layers, dHs, grads, want_dfeat, feat.shape,
-                                               after_bptt=after_bptt)
+                                               after_bptt=after_bptt, prealloc=pre)
                 ops.join(vdone)
                 ops.join(box.get("db_done"))
             elif need:
@@ -344,7 +366,7 @@ class BaseLossFn(torch.autograd.Function):
                     return v[-1] if v else torch.empty_like(P["embeddings.weight"])
 
                 dfeat = base_backward_from_dHs(mode, P, kind, L, cap, bs, layers, dHs, grads, want_dfeat, feat.shape,
-                                               emb_out=emb_out, after_bptt=after_bptt)
+                                               emb_out=emb_out, after_bptt=after_bptt, prealloc=pre)
                 ops.join(box.get("db_done"))
                 grads.update(zip(last, red.reduce([grads[n] for n in last])))
                 red.finish()

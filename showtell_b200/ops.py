@@ -695,6 +695,24 @@ def rnn_step_x_tc_bwd(kind, WhhT_b, WxT_b, bs, t, saved, dHs, dX, *, h0=None, c0
     return o
 
 
+def rnn_seq_tc_bwd_buffers(kind, WhhT_b, bs, dev, want_bias=True, transposed=False):
+    """The output / scratch buffers of rnn_seq_tc_bwd (its `out=`).  Two of them are zero-filled (the incoming state
+    gradient and the kernel's hand-off counters): a caller that creates them early on a side stream (ops.fork) keeps
+    those two small fills out of the dependency chain  dHs product -> BPTT kernel."""
+    N, H, GH = sum(bs), WhhT_b.shape[0], WhhT_b.shape[1]
+    ldt = (N + 7) // 8 * 8
+    mk = lambda: (torch.empty(N, GH, dtype=BF16, device=dev),
+                  torch.empty(GH, ldt, dtype=BF16, device=dev) if transposed else None)
+    dGb, dGT = mk()
+    dGhb, dGhT = mk() if kind == _lib.ST_GRU else (dGb, dGT)
+    want_bias = want_bias and transposed
+    return {"dGb": dGb, "dGT_full": dGT, "dGT": dGT[:, :N] if transposed else None, "dGhb": dGhb, "dGhT_full": dGhT,
+            "dGhT": dGhT[:, :N] if transposed else None,
+            "dbih": torch.empty(GH, dtype=F32, device=dev) if want_bias else None,
+            "dbhh": torch.empty(GH, dtype=F32, device=dev) if want_bias else None,
+            "dstate": torch.zeros(2, bs[0], H, dtype=F32, device=dev), "barrier": _barrier(dev)}
+
+
 def rnn_seq_tc_bwd(kind, WhhT_b, bs, saved, dHs, *, h0=None, c0=None, t_range=None, out=None, want_bias=True,
                    tag=None, transposed=False):
     """Returns dict(dGb, dGhb, dstate[, dGT, dGhT, dbih, dbhh]) (bf16 GEMM operands) or None if unsupported.
@@ -706,16 +724,7 @@ def rnn_seq_tc_bwd(kind, WhhT_b, bs, saved, dHs, *, h0=None, c0=None, t_range=No
     ldt = (N + 7) // 8 * 8
     o = out
     if o is None:
-        mk = lambda: (torch.empty(N, GH, dtype=BF16, device=dev),
-                      torch.empty(GH, ldt, dtype=BF16, device=dev) if transposed else None)
-        dGb, dGT = mk()
-        dGhb, dGhT = mk() if kind == _lib.ST_GRU else (dGb, dGT)
-        want_bias = want_bias and transposed
-        o = {"dGb": dGb, "dGT_full": dGT, "dGT": dGT[:, :N] if transposed else None, "dGhb": dGhb, "dGhT_full": dGhT,
-             "dGhT": dGhT[:, :N] if transposed else None,
-             "dbih": torch.empty(GH, dtype=F32, device=dev) if want_bias else None,
-             "dbhh": torch.empty(GH, dtype=F32, device=dev) if want_bias else None,
-             "dstate": torch.zeros(2, bs[0], H, dtype=F32, device=dev), "barrier": _barrier(dev)}
+        o = rnn_seq_tc_bwd_buffers(kind, WhhT_b, bs, dev, want_bias=want_bias, transposed=transposed)
     t_hi, t_lo = t_range if t_range is not None else (len(bs), 0)
     tok = TIMER.begin(tag) if (TIMER is not None and tag) else None
     st = lib.st_rnn_seq_tc_bwd(kind, H, len(bs), int_array(bs), t_hi, t_lo, ptr(WhhT_b, BF16), ptr(h0, F32),
