@@ -77,6 +77,10 @@ int st_rnn_seq_tc_bwd_ctas(int kind, int H, int B);
 /* Cap on the persistent grid of the st_gemm_bf16* / st_vocab_ce_* launches that follow (0 = all SMs): a GEMM launched
  * beside a cooperative recurrent kernel must leave that kernel's SMs free, or the two serialise. */
 int st_gemm_set_sm_limit(int n);
+/* 1: the fp32 outputs of the st_gemm_bf16 calls that follow have already been cleared by the caller (a stream-K launch
+ * reduces partial tiles into C and otherwise clears it itself, a memset in front of the kernel); 0 = default.  Lets a
+ * step clear such a buffer early, off its critical path. */
+int st_gemm_set_c_zeroed(int on);
 /* Device facts the host side sizes grids with. */
 int st_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_optin_bytes);
 

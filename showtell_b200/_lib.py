@@ -63,6 +63,7 @@ _SIGS = {
     "st_debug_set_coop": (_I, [_I]),
     "st_rnn_seq_tc_bwd_ctas": (_I, [_I, _I, _I]),
     "st_gemm_set_sm_limit": (_I, [_I]),
+    "st_gemm_set_c_zeroed": (_I, [_I]),
     "st_scale_multi": (_I, [_I, _P, _P, _P, _P, _P]),
     "st_bn1d_fwd": (_I, [_P, _I, _I, _I, _P, _P, _F, _F, _I, _P, _P, _P, _P, _P, _I, _P]),
     "st_bn1d_bwd": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P]),

@@ -485,10 +485,14 @@ class AttnLossFn(torch.autograd.Function):
             return out
 
         def body(F, mean_f, capt):
+            # (the packed targets depend on the captions only: formed beside the forward pass)
+            target, tdone = ops.fork(lambda: ops.pack_targets(capt, bs, P["linear.weight"].shape[0]), uses=(capt,), lane=7)
             Hs, alphas, sv = attn_forward(mode, P, kind, L, None, capt, bs, need, layout=lay, grid=(F, mean_f, Pn))
-            target = ops.pack_targets(capt, bs, P["linear.weight"].shape[0])
+            ops.join(tdone)
             gout = red.slots([P["linear.weight"].shape, P["linear.bias"].shape]) if (red is not None and need) else None
-            loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, dt, need, gout=gout)
+            # the stream-K dHs product reduces into a cleared buffer: cleared early, beside the forward loop
+            dHs_out = ops.fork(lambda: torch.zeros_like(Hs), lane=7) if (need and mode == "bf16") else None
+            loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, dt, need, gout=gout, dHs_out=dHs_out)
             pen_sum, Gpen = ops.attn_penalty(sv["S"], coef)
             loss = loss + coef * pen_sum.reshape(())
             g2 = None

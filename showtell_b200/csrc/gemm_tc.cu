@@ -68,6 +68,7 @@ int g_streamk = 1;   // st_debug_gemm_variant(v | 0x1000) turns stream-K off
 int g_tf32_bn192 = 1; // st_debug_gemm_variant(v | 0x20000) turns the 192-column tiles of the 3xTF32 product off
 int g_mn3d = 1;      // st_debug_gemm_variant(v | 0x2000): MN-major operands through 2-D boxes (A/B timing)
 int g_sm_limit = 0;  // st_gemm_set_sm_limit: cap on the persistent grids (0 = all SMs)
+int g_c_zeroed = 0;  // st_gemm_set_c_zeroed: the caller has already cleared C (stream-K launches skip their memset)
 inline int gemm_sms(int* sms) {
   ST_TRY(st_device_info(sms, nullptr, nullptr, nullptr));
   if (g_sm_limit > 0 && g_sm_limit < *sms) *sms = g_sm_limit;
@@ -94,6 +95,7 @@ struct TcParams {
   int tk_k;               // candidates written per (row, part): the caller's K (<= TOPK_SLOTS).  With pmax / psum set the
                           // epilogue also keeps the soft-max partials (running max, sum of exp) of its columns.
   int streamk;            // pair kernel: 1 = stream-K schedule (C zeroed by the launcher)
+  float* zero_word;       // cleared by the kernel's first thread (the CE forward's loss accumulator: no memset in front)
   int a3d, b3d;           // MN-major operand given as the 3-D tensor map (make_tmap_mn3d): one TMA operation per k-block
   int mc;                 // 1: launched as clusters of two CTAs that work on vertically adjacent tiles (same columns) and
                           // SHARE the B tile: each loads half of it and multicasts it into both CTAs' shared memory
@@ -535,6 +537,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // still reads that we overwrite) are safe from here on.
   pdl_wait();
   pdl_launch_dependents();
+  if (p.zero_word && blockIdx.x == 0 && threadIdx.x == 0) *p.zero_word = 0.f;
 
   // Producer and MMA warps run their loops with all 32 lanes (uniform control flow keeps addresses and UMMA
   // descriptors in uniform registers); only the TMA / tcgen05 instructions are issued by one elected lane.
@@ -709,6 +712,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_consta
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   pdl_wait();
   pdl_launch_dependents();
+  if (p.zero_word && blockIdx.x == 0 && threadIdx.x == 0) *p.zero_word = 0.f;
 
   if (warp == 0) {  // ------------------------------------------------------------ TMA producer
     int stage = 0;
@@ -931,6 +935,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  if (p.zero_word && blockIdx.x == 0 && threadIdx.x == 0) *p.zero_word = 0.f;
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
@@ -1169,7 +1174,7 @@ int launch_tc_bn(TcParams p, const void* A, int lda, const void* B, int ldb, cud
   p.streamk = want_streamk<EPI>(p, ntiles, kb, workers) ? 1 : 0;
   if (p.streamk) {
     grid = workers;
-    ST_CUDA_TRY(cudaMemset2DAsync(p.C, (size_t)p.ldc * 4, 0, (size_t)p.N * 4, p.M, s));
+    if (!g_c_zeroed) ST_CUDA_TRY(cudaMemset2DAsync(p.C, (size_t)p.ldc * 4, 0, (size_t)p.N * 4, p.M, s));
   }
   if (!p.mc) {
     ST_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(NTHREADS), TileCfg<BN>::SMEM_BYTES, s, tmA, tmB, p));
@@ -1211,7 +1216,7 @@ int launch_tc_pair(TcParams p, const void* A, int lda, const void* B, int ldb, c
   int npairs = ntiles < pairs ? ntiles : pairs;
   if (p.streamk) {
     npairs = pairs;
-    ST_CUDA_TRY(cudaMemset2DAsync(p.C, (size_t)p.ldc * 4, 0, (size_t)p.N * 4, p.M, s));
+    if (!g_c_zeroed) ST_CUDA_TRY(cudaMemset2DAsync(p.C, (size_t)p.ldc * 4, 0, (size_t)p.N * 4, p.M, s));
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * npairs);
@@ -1330,7 +1335,7 @@ int st_vocab_ce_fwd(int M, int V, int H, const void* Hs, int ldh, const void* Wv
   ST_TRY(st_device_info(&sms, nullptr, nullptr, nullptr));
   const int bn = pick_variant<EPI_CE_FWD>(p, sms);
   p.npart = 2 * ((V + (bn == 128 ? 127 : 255)) / (bn == 128 ? 128 : 256));   // <= st_vocab_ce_parts(V)
-  ST_CUDA_TRY(cudaMemsetAsync(loss_sum, 0, sizeof(float), s));
+  p.zero_word = loss_sum;   // cleared by the GEMM kernel itself; ce_combine_kernel (stream-ordered behind it) accumulates
   ST_TRY(launch_tc<EPI_CE_FWD>(p, Hs, ldh, Wv, ldw, s, bn));
   ce_combine_kernel<<<(M + 7) / 8, 256, 0, s>>>(M, p.npart, part_max, part_sum, tlogit, lse, loss_sum);
   ST_LAUNCH_TRY("ce_combine_kernel");
@@ -1404,6 +1409,11 @@ int st_gemm_tf32x3_topk(int M, int N, int K, const float* A_hi, const float* A_l
   topk_merge_kernel<<<(M + 7) / 8, 256, 0, s>>>(M, p.npart, topk, cand_val, cand_idx, val, idx, out_stride, tok, tok_stride,
                                                p.pmax, p.psum, row_max, row_sum);
   ST_LAUNCH_TRY("topk_merge_kernel");
+  return ST_OK;
+}
+
+int st_gemm_set_c_zeroed(int on) {
+  st::g_c_zeroed = on ? 1 : 0;
   return ST_OK;
 }
 

@@ -97,7 +97,14 @@ def bptt_prealloc(P, kind, L, bs, layers):
     for l in range(L):
         if layers[l]["tc"]:
             WhhT = ops.bf16_shadow(layer_params(P, l)[1], transposed=True)
-            pre[l] = ops.fork(lambda W=WhhT: ops.rnn_seq_tc_bwd_buffers(kind, W, bs, W.device), lane=6)
+            Wih = layer_params(P, l)[0]
+
+            def make(W=WhhT, n_in=Wih.shape[1]):
+                o = ops.rnn_seq_tc_bwd_buffers(kind, W, bs, W.device)
+                o["dX"] = torch.zeros(sum(bs), n_in, dtype=F32, device=W.device)   # output of the stream-K dG W_ih product
+                return o
+
+            pre[l] = ops.fork(make, lane=6)
     return pre
 
 
@@ -138,7 +145,11 @@ def stack_backward(mode, P, kind, L, bs, layers, dHs_top, grads, need_dx0=True, 
                 lambda: (lambda s: (s, ops.colsum(dGhb) if dGhb is not dGb else s))(ops.colsum(dGb)),
                 uses=(dGb, dGhb), lane=3)
             pending += [e1, e2, e3]
-            dH = ops.gemm_bf16(dGb, lin.Wb, b_t=True, tag="ih_dx") if need_dx else None     # dG W_ih
+            if need_dx and bufs is not None and "dX" in bufs:                                # dG W_ih
+                with ops.gemm_c_zeroed():
+                    dH = ops.gemm_bf16(dGb, lin.Wb, b_t=True, tag="ih_dx", out=bufs["dX"])
+            else:
+                dH = ops.gemm_bf16(dGb, lin.Wb, b_t=True, tag="ih_dx") if need_dx else None
             if l == 0 and dx0_ready is not None:
                 dx0_ready(dH)
             continue
@@ -231,7 +242,7 @@ class BaseLogitsFn(torch.autograd.Function):
         return (None, dfeat, None, None) + tuple(grads[n] for n in ctx.names)
 
 
-def vocab_ce(mode, P, Hs, target, denom, need, gout=None, Hs_bf16=None, side_sms=None, defer_db=False):
+def vocab_ce(mode, P, Hs, target, denom, need, gout=None, Hs_bf16=None, side_sms=None, defer_db=False, dHs_out=None):
     """Mean cross-entropy of the vocabulary projection of Hs (N,H) and, if `need`, its gradients.
     Returns (loss (0-d), dHs or None, grads dict, event).  bf16 mode: the weight / bias gradients do
     not feed the rest of the backward pass, so they run on the side stream (ops.fork) beside the BPTT
@@ -242,7 +253,8 @@ def vocab_ce(mode, P, Hs, target, denom, need, gout=None, Hs_bf16=None, side_sms
     cooperative BPTT kernel that follows on the main stream needs the rest free to start.  `defer_db` (bf16 mode):
     the bias gradient -- column sums over the 100 MB dlogits matrix, a long grid that would sit in front of the BPTT
     kernel's CTAs -- is not issued here: grads["_late_db"] = a function that issues it (the caller orders it behind the
-    BPTT kernel, where HBM is idle) and returns (db, event)."""
+    BPTT kernel, where HBM is idle) and returns (db, event).  `dHs_out` (bf16 mode): (zero-filled (N, H) fp32 buffer,
+    event) -- cleared early on a side stream, so the stream-K dHs product does not clear it on the critical path."""
     Wv, bv = P["linear.weight"], P["linear.bias"]
     grads = {}
     if mode == "fp32":
@@ -278,7 +290,12 @@ def vocab_ce(mode, P, Hs, target, denom, need, gout=None, Hs_bf16=None, side_sms
             grads["_late_db"] = lambda: ops.fork(lambda: ops.colsum(Pm), uses=(Pm,), lane=5)
         else:
             grads["linear.bias"] = db
-        dHs = ops.gemm_bf16(Pm, Wb, b_t=True, tag="vocab_dx")
+        if dHs_out is not None:
+            ops.join(dHs_out[1])
+            with ops.gemm_c_zeroed():
+                dHs = ops.gemm_bf16(Pm, Wb, b_t=True, tag="vocab_dx", out=dHs_out[0])
+        else:
+            dHs = ops.gemm_bf16(Pm, Wb, b_t=True, tag="vocab_dx")
     ops.join(loss_done)
     return loss, dHs, grads, done
 
@@ -330,15 +347,19 @@ class BaseLossFn(torch.autograd.Function):
         red = getattr(mod, "grad_reducer", None)       # data parallelism: parallel.GradReducer
 
         def body(feat, cap):
+            # the packed targets depend on the captions only: formed beside the forward pass, not between the forward
+            # recurrence and the vocabulary product
+            target, tdone = ops.fork(lambda: ops.pack_targets(cap, bs, P["linear.weight"].shape[0]), uses=(cap,), lane=7)
             Hs, layers = base_forward(mode, P, kind, L, feat, cap, bs, need)
-            target = ops.pack_targets(cap, bs, P["linear.weight"].shape[0])
+            ops.join(tdone)
             # bf16 mode: the vocabulary bias gradient is issued behind the BPTT kernel (see vocab_ce) and, under data
             # parallelism, travels with the last bucket instead of the vocabulary weight's
             defer = False     # measured: the sums then lengthen the backward tail by what they save in front of BPTT
             lin = ["linear.weight"] if defer else ["linear.weight", "linear.bias"]
             gout = red.slots([P[n].shape for n in lin]) if (red is not None and need) else None
             pre = bptt_prealloc(P, kind, L, bs, layers) if need else None
-            loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, denom, need, gout=gout, defer_db=defer,
+            dHs_out = ops.fork(lambda: torch.zeros_like(Hs), lane=6) if (need and mode == "bf16") else None
+            loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, denom, need, gout=gout, defer_db=defer, dHs_out=dHs_out,
                                                Hs_bf16=layers[-1]["out"]["Hsb"] if layers[-1]["tc"] else None)
             late = grads.pop("_late_db", None)
             box = {}

@@ -82,6 +82,17 @@ class gemm_sm_limit:
             _lib.load().st_gemm_set_sm_limit(0)
 
 
+class gemm_c_zeroed:
+    """Context: the fp32 `out=` buffers of the gemm_bf16 calls inside were cleared by the caller (torch.zeros on a side
+    stream, early): a stream-K launch then skips the memset it would put in front of its kernel."""
+
+    def __enter__(self):
+        _lib.load().st_gemm_set_c_zeroed(1)
+
+    def __exit__(self, *a):
+        _lib.load().st_gemm_set_c_zeroed(0)
+
+
 def bptt_side_sms(kind, H, B):
     """SMs left over beside the tensor-core BPTT kernel for a batch of B rows (at least a quarter of the GPU)."""
     lib = _lib.load()
