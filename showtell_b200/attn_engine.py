@@ -485,10 +485,8 @@ class AttnLossFn(torch.autograd.Function):
             return out
 
         def body(F, mean_f, capt):
-            # (the packed targets depend on the captions only: formed beside the forward pass)
-            target, tdone = ops.fork(lambda: ops.pack_targets(capt, bs, P["linear.weight"].shape[0]), uses=(capt,), lane=7)
             Hs, alphas, sv = attn_forward(mode, P, kind, L, None, capt, bs, need, layout=lay, grid=(F, mean_f, Pn))
-            ops.join(tdone)
+            target = ops.pack_targets(capt, bs, P["linear.weight"].shape[0])
             gout = red.slots([P["linear.weight"].shape, P["linear.bias"].shape]) if (red is not None and need) else None
             # the stream-K dHs product reduces into a cleared buffer: cleared early, beside the forward loop
             dHs_out = ops.fork(lambda: torch.zeros_like(Hs), lane=7) if (need and mode == "bf16") else None

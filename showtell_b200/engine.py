@@ -349,8 +349,10 @@ class BaseLossFn(torch.autograd.Function):
         def body(feat, cap):
             # the packed targets depend on the captions only: formed beside the forward pass, not between the forward
             # recurrence and the vocabulary product
+            # (issued after pack_inputs: that call is where a bad token id of an EARLIER step is reported)
+            X = ops.pack_inputs(P["embeddings.weight"], feat, cap, bs, True, bf16=(mode == "bf16"))   # rnn.py:29-31
             target, tdone = ops.fork(lambda: ops.pack_targets(cap, bs, P["linear.weight"].shape[0]), uses=(cap,), lane=7)
-            Hs, layers = base_forward(mode, P, kind, L, feat, cap, bs, need)
+            Hs, layers = stack_forward(mode, P, kind, L, X, bs, need)
             ops.join(tdone)
             # bf16 mode: the vocabulary bias gradient is issued behind the BPTT kernel (see vocab_ce) and, under data
             # parallelism, travels with the last bucket instead of the vocabulary weight's
