@@ -242,7 +242,8 @@ class BaseLogitsFn(torch.autograd.Function):
         return (None, dfeat, None, None) + tuple(grads[n] for n in ctx.names)
 
 
-def vocab_ce(mode, P, Hs, target, denom, need, gout=None, Hs_bf16=None, side_sms=None, defer_db=False, dHs_out=None):
+def vocab_ce(mode, P, Hs, target, denom, need, gout=None, Hs_bf16=None, side_sms=None, defer_db=False, dHs_out=None,
+             fork_loss=True):
     """Mean cross-entropy of the vocabulary projection of Hs (N,H) and, if `need`, its gradients.
     Returns (loss (0-d), dHs or None, grads dict, event).  bf16 mode: the weight / bias gradients do
     not feed the rest of the backward pass, so they run on the side stream (ops.fork) beside the BPTT
@@ -271,7 +272,8 @@ def vocab_ce(mode, P, Hs, target, denom, need, gout=None, Hs_bf16=None, side_sms
     Hb = Hs_bf16 if Hs_bf16 is not None else _bf16(Hs)
     loss_sum, lse = ops.vocab_ce_fwd(Hb, Wb, bv, target, tag="vocab_fwd")
     # (the mean: a one-element kernel, kept off the main stream -- there it sat between the dHs product and BPTT)
-    loss, loss_done = ops.fork(lambda: (loss_sum / denom).reshape(()), uses=(loss_sum,), lane=7)
+    loss, loss_done = (ops.fork(lambda: (loss_sum / denom).reshape(()), uses=(loss_sum,), lane=7) if fork_loss
+                       else (None, None))
     dHs, done = None, None
     if need:
         # dlogits = (softmax - onehot) / denom recomputed tile by tile and written ONCE, row-major bf16; the three
@@ -297,6 +299,8 @@ def vocab_ce(mode, P, Hs, target, denom, need, gout=None, Hs_bf16=None, side_sms
         else:
             dHs = ops.gemm_bf16(Pm, Wb, b_t=True, tag="vocab_dx")
     ops.join(loss_done)
+    if loss is None:
+        loss = (loss_sum / denom).reshape(())
     return loss, dHs, grads, done
 
 
@@ -350,18 +354,31 @@ class BaseLossFn(torch.autograd.Function):
             # the packed targets depend on the captions only: formed beside the forward pass, not between the forward
             # recurrence and the vocabulary product
             # (issued after pack_inputs: that call is where a bad token id of an EARLIER step is reported)
+            # Single GPU only: under data parallelism the extra side-stream work (this, the early BPTT buffers, the loss
+            # mean) changed which kernels reach the SMs first around the BPTT kernel and the vocabulary bucket's exchange
+            # no longer overlapped it (2 GPUs: 0.634 -> 0.684 ms) -- that path keeps the serial order it was measured with.
+            lean = red is None
             X = ops.pack_inputs(P["embeddings.weight"], feat, cap, bs, True, bf16=(mode == "bf16"))   # rnn.py:29-31
-            target, tdone = ops.fork(lambda: ops.pack_targets(cap, bs, P["linear.weight"].shape[0]), uses=(cap,), lane=7)
+            if lean:
+                target, tdone = ops.fork(lambda: ops.pack_targets(cap, bs, P["linear.weight"].shape[0]), uses=(cap,), lane=7)
             Hs, layers = stack_forward(mode, P, kind, L, X, bs, need)
-            ops.join(tdone)
+            if lean:
+                ops.join(tdone)
+            else:
+                target = ops.pack_targets(cap, bs, P["linear.weight"].shape[0])
             # bf16 mode: the vocabulary bias gradient is issued behind the BPTT kernel (see vocab_ce) and, under data
             # parallelism, travels with the last bucket instead of the vocabulary weight's
             defer = False     # measured: the sums then lengthen the backward tail by what they save in front of BPTT
             lin = ["linear.weight"] if defer else ["linear.weight", "linear.bias"]
             gout = red.slots([P[n].shape for n in lin]) if (red is not None and need) else None
-            pre = bptt_prealloc(P, kind, L, bs, layers) if need else None
-            dHs_out = ops.fork(lambda: torch.zeros_like(Hs), lane=6) if (need and mode == "bf16") else None
+            pre = bptt_prealloc(P, kind, L, bs, layers) if (need and lean) else None
+            # (the dHs product keeps its own clear: with it the side stream's dW product, issued first, also STARTS first
+            # and the two persistent grids share the GPU -- dW and db are then final before BPTT starts, which is what the
+            # data-parallel exchange of that bucket overlaps; cleared early, dHs took every SM first and the bucket was
+            # ready only after BPTT: 0.653 -> 0.745 ms at 8 GPUs)
+            dHs_out = None
             loss, dHs, grads, vdone = vocab_ce(mode, P, Hs, target, denom, need, gout=gout, defer_db=defer, dHs_out=dHs_out,
+                                               fork_loss=lean,
                                                Hs_bf16=layers[-1]["out"]["Hsb"] if layers[-1]["tc"] else None)
             late = grads.pop("_late_db", None)
             box = {}
